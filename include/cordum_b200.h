@@ -1,0 +1,267 @@
+/* cordum_b200.h — C ABI of the B200-native policy-gate + dispatch engine.
+ *
+ * This is the drop-in boundary for ONE path of cordum-io/cordum: the batched
+ * form of
+ *   safetykernel.(*server).evaluate        core/controlplane/safetykernel/kernel.go:129-257
+ *   config.(*SafetyPolicy).Evaluate        core/infra/config/safety_policy.go:187-206
+ *   scheduler.(*Engine).checkSafetyDecision post-step   core/controlplane/scheduler/engine.go:524-531
+ *   scheduler.(*LeastLoadedStrategy).PickSubject        core/controlplane/scheduler/strategy_least_loaded.go:40-136
+ *
+ * The reference has no FFI; its seams are Go interfaces and one gRPC service
+ * (SURVEY.md §8b).  Each entry point below names the reference call it stands
+ * behind; INTEGRATION.md shows the cgo adapters a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no C++/torch types cross this boundary
+ *   - every function returns int32 status: 0 = OK, <0 = error (CORDUM_E_*);
+ *     cordum_last_error() returns a thread-local message owned by the library
+ *   - strings are (offset,len) spans into a caller-owned byte arena; the
+ *     library never keeps a caller pointer after the call returns (cgo rule)
+ *   - the library owns every buffer it allocates (pinned host + device)
+ *   - any CUDA failure makes the handle sticky-failed: callers must then fail
+ *     closed (DENY / retryable routing error), never fall back to a CPU path
+ */
+#ifndef CORDUM_B200_H
+#define CORDUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status */
+#define CORDUM_OK 0
+#define CORDUM_E_INVALID (-1)   /* bad argument / malformed input document        */
+#define CORDUM_E_CAPACITY (-2)  /* a dictionary exceeded its mask width (64)      */
+#define CORDUM_E_CUDA (-3)      /* CUDA runtime / kernel failure (sticky)         */
+#define CORDUM_E_STATE (-4)     /* call order violated (e.g. dispatch before load)*/
+#define CORDUM_E_NODEVICE (-5)  /* no CUDA device: the product has NO CPU path    */
+
+/* ------------------------------------------------------ wire: string spans */
+typedef struct cordum_str {
+  uint32_t off; /* byte offset into the arena   */
+  uint32_t len; /* byte length; 0 = empty string */
+} cordum_str;
+
+/* Columnar batch of string-level job envelopes.
+ *
+ * Field set = what evaluate()/PickSubject() read from CAP v2
+ * PolicyCheckRequest / JobRequest:
+ *   kernel.go:133-138 (topic, tenant, meta.tenant_id), :348-368 (meta),
+ *   :381-414 (labels: secrets_present, mcp.*), :218 (effective_config),
+ *   strategy_least_loaded.go:46-62 (labels, meta.requires, raw topic).
+ * List-valued fields are CSR: entries [off[j], off[j+1]) belong to job j.
+ * Labels are a map: keys unique per job (if repeated, the last one wins).
+ */
+typedef struct cordum_envelopes {
+  uint32_t n_jobs;
+  const uint8_t* arena;
+  uint64_t arena_len;
+  const cordum_str* topic;            /* req.Topic, raw (untrimmed)                         */
+  const cordum_str* tenant;           /* PolicyCheckRequest.Tenant (scheduler route: ExtractTenant, tenant.go:8-21) */
+  const cordum_str* principal_id;     /* PrincipalId (actor-id fallback, kernel.go:352,364)  */
+  const cordum_str* effective_config; /* raw JSON bytes, len 0 = absent (safety_client.go:91-95) */
+  const uint8_t* has_meta;            /* req.Meta != nil                                    */
+  const cordum_str* meta_tenant_id;   /* Meta.TenantId                                      */
+  const cordum_str* actor_id;         /* Meta.ActorId                                       */
+  const uint8_t* actor_type;          /* 0 unspecified, 1 human, 2 service (kernel.go:370)  */
+  const cordum_str* capability;       /* Meta.Capability                                    */
+  const cordum_str* pack_id;          /* Meta.PackId                                        */
+  const uint32_t* risk_off;           /* n_jobs+1 */
+  const cordum_str* risk_tags;        /* Meta.RiskTags                                      */
+  const uint32_t* requires_off;       /* n_jobs+1 */
+  const cordum_str* requires_;        /* Meta.Requires                                      */
+  const uint32_t* label_off;          /* n_jobs+1 */
+  const cordum_str* label_keys;       /* req.Labels                                         */
+  const cordum_str* label_vals;
+  const uint8_t* approved;            /* may be NULL. 1 = host verified the approval record and
+                                         job hash (engine.go:484-522): policy is bypassed     */
+} cordum_envelopes;
+
+/* Worker registry snapshot = map[worker_id]*Heartbeat (registry_memory.go:71-84),
+ * columnar.  Index in these arrays is the worker "slot" reported in results. */
+typedef struct cordum_workers {
+  uint32_t n_workers;
+  const uint8_t* arena;
+  uint64_t arena_len;
+  const cordum_str* worker_id;
+  const cordum_str* pool;
+  const int32_t* active_jobs;
+  const int32_t* max_parallel_jobs;
+  const float* cpu_load;
+  const float* gpu_utilization;
+  const uint32_t* label_off; /* n_workers+1 */
+  const cordum_str* label_keys;
+  const cordum_str* label_vals;
+} cordum_workers;
+
+/* Per-worker load record: the only heartbeat fields that change between
+ * heartbeats of a live worker.  16 B; the multi-GPU exchange all-gathers these. */
+typedef struct cordum_worker_load {
+  int32_t active_jobs;
+  int32_t max_parallel_jobs;
+  float cpu_load;
+  float gpu_utilization;
+} cordum_worker_load;
+
+/* ------------------------------------------------------- result record */
+/* decision codes (DecisionType, core/protocol/pb/v1/pb.go:61-66; numeric values are
+ * this ABI's own, the Go adapter maps them) */
+#define CORDUM_DEC_UNSPECIFIED 0
+#define CORDUM_DEC_ALLOW 1
+#define CORDUM_DEC_DENY 2
+#define CORDUM_DEC_REQUIRE_HUMAN 3
+#define CORDUM_DEC_THROTTLE 4
+#define CORDUM_DEC_ALLOW_WITH_CONSTRAINTS 5
+
+/* reason codes: host formats the exact strings (kernel.go:172,175,221,225;
+ * safety_policy.go:410,413; engine.go:500) */
+#define CORDUM_REASON_NONE 0
+#define CORDUM_REASON_RULE 1            /* rules[rule_idx].reason                   */
+#define CORDUM_REASON_MISSING_TOPIC 2   /* "missing topic"                          */
+#define CORDUM_REASON_UNSUPPORTED_TOPIC 3 /* "unsupported topic"                    */
+#define CORDUM_REASON_TENANT_MCP 4      /* 4..11: field*2 + (0 denied | 1 not allowed), field = server,tool,resource,action */
+#define CORDUM_REASON_EFF_DENIED_TOPIC 12
+#define CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC 13
+#define CORDUM_REASON_EFF_MCP 14        /* 14..21, same sub-layout as TENANT_MCP    */
+#define CORDUM_REASON_APPROVAL_GRANTED 22 /* "approval granted" (engine.go:500)     */
+
+/* route status (strategy_least_loaded.go:40-136; errors.go:5-14) */
+#define CORDUM_ROUTE_NOT_ATTEMPTED 0    /* decision did not allow dispatch (engine.go:298-347) */
+#define CORDUM_ROUTE_OK 1               /* worker_slot valid: subject "worker.<id>.jobs"       */
+#define CORDUM_ROUTE_OK_PREFERRED 2     /* preferred_worker_id shortcut (:73-87)               */
+#define CORDUM_ROUTE_MISSING_TOPIC 3    /* :41-43                                              */
+#define CORDUM_ROUTE_NO_POOL_PREFERRED 4 /* ErrNoPoolMapping, preferred pool not mapped (:52)  */
+#define CORDUM_ROUTE_NO_POOL_TOPIC 5    /* ErrNoPoolMapping, topic has no pools (:57)          */
+#define CORDUM_ROUTE_NO_POOL_REQUIRES 6 /* ErrNoPoolMapping, no pool satisfies requires (:65)  */
+#define CORDUM_ROUTE_NO_WORKERS 7       /* ErrNoWorkers (:118)                                 */
+#define CORDUM_ROUTE_POOL_OVERLOADED 8  /* ErrPoolOverloaded (:116)                            */
+
+/* flags */
+#define CORDUM_F_APPROVAL_REQUIRED 0x01 /* kernel.go:233                                        */
+#define CORDUM_F_HAS_SNAPSHOT 0x02      /* response carries policy_snapshot/rule_id (not the early DENY returns, kernel.go:171-176) */
+#define CORDUM_F_CONSTRAINTS 0x04       /* response carries rules[rule_idx].constraints (kernel.go:198,244) */
+#define CORDUM_F_TIE 0x08               /* the minimum load score was shared by >1 candidate; the lowest
+                                           worker_id (bytewise) was chosen      */
+#define CORDUM_F_APPROVED_BYPASS 0x10   /* engine.go:484-522 path                                */
+
+typedef struct cordum_decision {
+  uint8_t decision;       /* CORDUM_DEC_*: the safety kernel's PolicyCheckResponse.Decision   */
+  uint8_t sched_decision; /* CORDUM_DEC_* after engine.go:528-530 (approval_required & ALLOW* ->
+                             REQUIRE_HUMAN i.e. SafetyRequireApproval); what engine.go:298 switches on */
+  uint8_t flags;          /* CORDUM_F_*                                                        */
+  uint8_t route_status;   /* CORDUM_ROUTE_*                                                    */
+  uint8_t reason_code;    /* CORDUM_REASON_*                                                   */
+  uint8_t reserved[3];
+  int32_t rule_idx;       /* first matching rule, -1 = none (default allow)                    */
+  int32_t worker_slot;    /* routed worker slot, -1 = none                                     */
+} cordum_decision;        /* 16 bytes */
+
+/* dispatch modes */
+#define CORDUM_MODE_POLICY_ONLY 1      /* SafetyKernel Check/Evaluate/Explain/Simulate (kernel.go:106-120) */
+#define CORDUM_MODE_POLICY_AND_ROUTE 2 /* processJob: checkSafetyDecision + PickSubject (engine.go:294,393) */
+#define CORDUM_MODE_ROUTE_ONLY 3       /* SchedulingStrategy.PickSubject alone (types.go:40-42)            */
+
+/* ------------------------------------------------------------- engine */
+typedef struct cordum_engine cordum_engine;
+typedef struct cordum_batch cordum_batch;
+
+typedef struct cordum_engine_opts {
+  int32_t device;          /* CUDA device ordinal                                   */
+  uint32_t max_topics;     /* capacity of the topic dictionary (0 = default 65536)   */
+  uint32_t max_effcfgs;    /* capacity of distinct effective configs (0 = 4096)      */
+  uint32_t encode_threads; /* host threads for cordum_encode (0 = hardware threads)  */
+} cordum_engine_opts;
+
+const char* cordum_last_error(void);
+const char* cordum_version(void);
+
+/* Replaces nothing in the reference: process-level setup.  Fails with
+ * CORDUM_E_NODEVICE when no GPU is present — there is no CPU fallback. */
+int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out);
+void cordum_engine_destroy(cordum_engine* e);
+
+/* safetykernel.(*server).setPolicy (kernel.go:510-521): swap the rule set.
+ * policy_json = the merged config.SafetyPolicy (safety_policy.go:13-107) marshalled
+ * with its yaml tag names as JSON keys; len 0 = nil policy (allow-all, kernel.go:187).
+ * snapshot is kept (newest first, 10 deep) for ListSnapshots (kernel.go:122-127). */
+int32_t cordum_policy_load(cordum_engine* e, const char* policy_json, uint64_t len,
+                           const char* snapshot, uint64_t snapshot_len);
+/* ListSnapshots: writes up to cap NUL-separated snapshot ids, newest first. */
+int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint32_t* n_out);
+
+/* (*LeastLoadedStrategy).UpdateRouting (strategy_least_loaded.go:28-30).
+ * routing_json = {"topics": {topic: [pool,...]}, "pools": {pool: {"requires": [...]}}}
+ * i.e. scheduler.PoolRouting (routing.go:4-12) as built by buildRouting
+ * (cmd/cordum-scheduler/config_overlay.go:155-174). */
+int32_t cordum_routing_load(cordum_engine* e, const char* routing_json, uint64_t len);
+
+/* WorkerRegistry snapshot (types.go:34-37; registry_memory.go:71-84): replace the table. */
+int32_t cordum_workers_load(cordum_engine* e, const cordum_workers* w);
+/* Heartbeat deltas for live workers (registry_memory.go:43-51): host-side loads by slot. */
+int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slots,
+                              const cordum_worker_load* loads);
+/* Same, but the full slot-ordered load table is already on the device (e.g. the
+ * receive buffer of the NCCL all-gather of per-rank slices).
+ * dptr: n_workers x cordum_worker_load on this engine's device; stream: cudaStream_t
+ * the data was produced on (0 = legacy default). */
+int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint32_t n_workers,
+                                        void* stream);
+
+/* Library-owned pinned SoA slabs for up to max_jobs jobs. */
+int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out);
+void cordum_batch_free(cordum_batch* b);
+
+/* Request normalisation + dictionary coding of a batch of envelopes into the
+ * batch's column-major attribute arrays (kernel.go:133-185, 348-414;
+ * strategy_least_loaded.go:46-62,195-222).  Host work, multi-threaded. */
+int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env);
+
+/* Batched evaluate() [+ post-step + PickSubject()].  Blocking:
+ * H2D of the encoded columns, kernels, D2H of the decision records. */
+int32_t cordum_dispatch(cordum_engine* e, cordum_batch* b, uint32_t mode);
+/* Pipelined form: enqueue on the batch's stream / wait for it. */
+int32_t cordum_dispatch_async(cordum_engine* e, cordum_batch* b, uint32_t mode);
+int32_t cordum_batch_wait(cordum_batch* b);
+/* Device-resident form used for kernel-only timing: assumes the columns of the
+ * last dispatch on this batch are still in HBM; runs the kernels only, no copies. */
+int32_t cordum_dispatch_resident(cordum_engine* e, cordum_batch* b, uint32_t mode);
+
+uint32_t cordum_batch_size(const cordum_batch* b);
+/* Decision records of the last completed dispatch (pinned host memory, n = batch size). */
+const cordum_decision* cordum_batch_results(const cordum_batch* b);
+/* Device time of the last completed dispatch on this batch (CUDA events on the
+ * batch stream): total, and the fused policy+route kernel alone.  Milliseconds. */
+int32_t cordum_batch_timing(const cordum_batch* b, float* total_ms, float* kernel_ms);
+
+/* Host-side materialisation of what the record indexes (pure functions of rule_idx /
+ * reason_code / worker_slot).  Each writes a NUL-terminated string
+ * into buf (truncating to cap) and returns the full length. */
+int64_t cordum_rule_id(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
+int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap);
+int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap);
+/* JSON of rules[rule_idx].constraints / .remediations as loaded (kernel.go:244,247). */
+int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
+int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
+
+/* Introspection for tests/bench: table sizes and algorithmic byte counts. */
+typedef struct cordum_table_stats {
+  uint32_t n_rules, n_rules_padded, n_segments;
+  uint32_t n_topics, n_tenants, n_pools, n_workers, n_workers_routable;
+  uint64_t passrow_bytes;  /* all pass-row tables                         */
+  uint64_t rulecol_bytes;  /* per-rule columns                            */
+  uint64_t routing_bytes;  /* topic->pool CSR + pool columns              */
+  uint64_t worker_bytes;   /* worker columns                              */
+  uint32_t job_in_bytes;   /* bytes of encoded columns per job            */
+  uint32_t job_out_bytes;  /* bytes of decision record per job            */
+} cordum_table_stats;
+int32_t cordum_stats(cordum_engine* e, cordum_table_stats* out);
+
+/* Number of kernels this library has launched on the handle since creation. */
+uint64_t cordum_launch_count(cordum_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORDUM_B200_H */

@@ -1,0 +1,1331 @@
+// oracle.cpp — CPU ORACLE for the policy-gate + dispatch path.
+//
+// *** TEST INFRASTRUCTURE.  NOT PRODUCT CODE.  ***
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may build, load or call this.  The product never routes through it.
+//
+// What it is: a string-level, one-job-at-a-time C++17 restatement of the reference's
+// Go implementation (cordum-io/cordum @ c7ddbe09).  It keeps the reference's
+// algorithmic structure on purpose — a linear first-match scan over the rule list with
+// TrimSpace+EqualFold string compares and path.Match globbing per job, and a full scan
+// of the worker map per job — so that (a) it can be checked line against line, and
+// (b) timed on host cores it stands in for the reference's CPU path ("port").
+//
+// Reference map (paths relative to /root/reference):
+//   core/infra/config/safety_policy.go:187-416      Evaluate, normalizeDecision, legacyRules, matchRule,
+//                                                   containsString/Any/All, labelsMatch, matchTopic, mcpMatch,
+//                                                   MCPAllowed, matchMCPField
+//   core/controlplane/safetykernel/kernel.go:129-257 evaluate; :348-483 helpers
+//   core/infra/config/effective.go:12-39            ParseEffectiveSafety (+ categories.go:6-35 field types)
+//   core/controlplane/scheduler/engine.go:298-347,484-531   decision switch, approval bypass, post-step
+//   core/controlplane/scheduler/safety_client.go:117-132    decisionFromProto
+//   core/controlplane/scheduler/strategy_least_loaded.go:40-274   PickSubject and helpers
+//   core/infra/bus/nats.go:94-99                    DirectSubject
+// Third-party semantics restated (not under /root/reference): Go 1.24 stdlib
+//   strings.TrimSpace, strings.EqualFold, strings.ToLower, strings.HasPrefix, path.Match,
+//   encoding/json (object/field typing as used by ParseEffectiveSafety).
+//
+// PARITY PINNING: the Go reference cannot be built or run here (no Go toolchain, CAP
+// module not vendored).  This oracle is pinned against every known-answer test the
+// reference holds for the path (tests/test_oracle_kats.py lists them by file:line) and
+// against an independent pure-Python restatement (oracle/py_oracle.py) on randomized
+// inputs.  Behaviour the reference's tests do not exercise (see SURVEY.md §8c last row)
+// is "pinned only by two independent restatements of the cited lines".
+// Known limitation shared with the product: case folding / lower-casing is ASCII-only
+// (Go folds all of Unicode); every string in the reference's fixtures and in the
+// synthetic configs is ASCII.  TrimSpace handles the full Unicode White_Space set.
+//
+// Tie rule: Go's map iteration order is random and PickSubject keeps the
+// first strict minimum, so on equal scores the reference's answer is nondeterministic.
+// The oracle visits workers in ascending worker_id byte order, which is one of the
+// reference's possible executions, and reports whether the minimum was shared.
+
+#include "oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../common/mini_json.hpp"
+
+using sv = std::string_view;
+
+namespace {
+
+thread_local std::string g_err;
+
+// ============================================================ Go string primitives
+constexpr uint32_t kRuneError = 0xFFFD;
+
+// utf8.DecodeRuneInString
+uint32_t decode_rune(sv s, int& n) {
+  if (s.empty()) { n = 0; return kRuneError; }
+  auto b = [&](size_t i) { return (unsigned char)s[i]; };
+  unsigned b0 = b(0);
+  if (b0 < 0x80) { n = 1; return b0; }
+  auto cont = [&](size_t i, unsigned lo, unsigned hi) { return i < s.size() && b(i) >= lo && b(i) <= hi; };
+  if (b0 >= 0xC2 && b0 <= 0xDF) {
+    if (cont(1, 0x80, 0xBF)) { n = 2; return ((b0 & 0x1F) << 6) | (b(1) & 0x3F); }
+  } else if (b0 >= 0xE0 && b0 <= 0xEF) {
+    unsigned lo = 0x80, hi = 0xBF;
+    if (b0 == 0xE0) lo = 0xA0;
+    if (b0 == 0xED) hi = 0x9F;
+    if (cont(1, lo, hi) && cont(2, 0x80, 0xBF)) {
+      n = 3;
+      return ((b0 & 0x0F) << 12) | ((b(1) & 0x3F) << 6) | (b(2) & 0x3F);
+    }
+  } else if (b0 >= 0xF0 && b0 <= 0xF4) {
+    unsigned lo = 0x80, hi = 0xBF;
+    if (b0 == 0xF0) lo = 0x90;
+    if (b0 == 0xF4) hi = 0x8F;
+    if (cont(1, lo, hi) && cont(2, 0x80, 0xBF) && cont(3, 0x80, 0xBF)) {
+      n = 4;
+      return ((b0 & 0x07) << 18) | ((b(1) & 0x3F) << 12) | ((b(2) & 0x3F) << 6) | (b(3) & 0x3F);
+    }
+  }
+  n = 1;
+  return kRuneError;
+}
+
+// utf8.DecodeLastRuneInString
+uint32_t decode_last_rune(sv s, int& n) {
+  int end = (int)s.size();
+  if (end == 0) { n = 0; return kRuneError; }
+  int start = end - 1;
+  unsigned r = (unsigned char)s[start];
+  if (r < 0x80) { n = 1; return r; }
+  int lim = end - 4;
+  if (lim < 0) lim = 0;
+  for (start--; start >= lim; start--)
+    if ((((unsigned char)s[start]) & 0xC0) != 0x80) break;
+  if (start < 0) start = 0;
+  int size;
+  uint32_t rr = decode_rune(s.substr(start, end - start), size);
+  if (start + size != end) { n = 1; return kRuneError; }
+  n = size;
+  return rr;
+}
+
+// unicode.IsSpace
+bool is_space_rune(uint32_t r) {
+  if (r <= 0xFF) return r == '\t' || r == '\n' || r == '\v' || r == '\f' || r == '\r' || r == ' ' || r == 0x85 || r == 0xA0;
+  return r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 || r == 0x202F || r == 0x205F ||
+         r == 0x3000;
+}
+
+// strings.TrimSpace
+sv trim_space(sv s) {
+  while (!s.empty()) {
+    int n;
+    uint32_t r = decode_rune(s, n);
+    if (!is_space_rune(r)) break;
+    s.remove_prefix(n);
+  }
+  while (!s.empty()) {
+    int n;
+    uint32_t r = decode_last_rune(s, n);
+    if (!is_space_rune(r)) break;
+    s.remove_suffix(n);
+  }
+  return s;
+}
+
+inline unsigned char ascii_lower(unsigned char c) { return (c >= 'A' && c <= 'Z') ? (unsigned char)(c + 32) : c; }
+
+// strings.EqualFold — ASCII folding only (see header note)
+bool equal_fold(sv a, sv b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); ++i)
+    if (ascii_lower((unsigned char)a[i]) != ascii_lower((unsigned char)b[i])) return false;
+  return true;
+}
+
+// strings.ToLower — ASCII only
+std::string to_lower(sv s) {
+  std::string o(s);
+  for (auto& c : o) c = (char)ascii_lower((unsigned char)c);
+  return o;
+}
+
+bool has_prefix(sv s, sv p) { return s.size() >= p.size() && s.substr(0, p.size()) == p; }
+
+// ------------------------------------------------------------------ path.Match
+// Follows go1.24 src/path/match.go: Match / scanChunk / matchChunk / getEsc.
+struct ChunkScan { bool star; sv chunk; sv rest; };
+
+ChunkScan scan_chunk(sv pattern) {
+  bool star = false;
+  while (!pattern.empty() && pattern[0] == '*') { pattern.remove_prefix(1); star = true; }
+  bool inrange = false;
+  size_t i = 0;
+  for (; i < pattern.size(); ++i) {
+    char c = pattern[i];
+    if (c == '\\') { if (i + 1 < pattern.size()) ++i; }
+    else if (c == '[') inrange = true;
+    else if (c == ']') inrange = false;
+    else if (c == '*') { if (!inrange) break; }
+  }
+  return {star, pattern.substr(0, i), pattern.substr(i)};
+}
+
+// returns false on ErrBadPattern
+bool get_esc(sv& chunk, uint32_t& r) {
+  if (chunk.empty() || chunk[0] == '-' || chunk[0] == ']') return false;
+  if (chunk[0] == '\\') {
+    chunk.remove_prefix(1);
+    if (chunk.empty()) return false;
+  }
+  int n;
+  r = decode_rune(chunk, n);
+  bool bad = (r == kRuneError && n == 1);
+  chunk.remove_prefix(n);
+  if (chunk.empty()) bad = true;
+  return !bad;
+}
+
+// ok: matched, rest = remainder of s.  err: bad pattern.
+void match_chunk(sv chunk, sv s, sv& rest, bool& ok, bool& err) {
+  ok = false; err = false; rest = sv();
+  bool failed = false;
+  while (!chunk.empty()) {
+    if (!failed && s.empty()) failed = true;
+    char c = chunk[0];
+    if (c == '[') {
+      uint32_t r = 0;
+      if (!failed) { int n; r = decode_rune(s, n); s.remove_prefix(n); }
+      chunk.remove_prefix(1);
+      bool negated = false;
+      if (!chunk.empty() && chunk[0] == '^') { negated = true; chunk.remove_prefix(1); }
+      bool match = false;
+      int nrange = 0;
+      while (true) {
+        if (!chunk.empty() && chunk[0] == ']' && nrange > 0) { chunk.remove_prefix(1); break; }
+        uint32_t lo, hi;
+        if (!get_esc(chunk, lo)) { err = true; return; }
+        hi = lo;
+        if (chunk[0] == '-') {
+          chunk.remove_prefix(1);
+          if (!get_esc(chunk, hi)) { err = true; return; }
+        }
+        if (lo <= r && r <= hi) match = true;
+        nrange++;
+      }
+      if (match == negated) failed = true;
+    } else if (c == '?') {
+      if (!failed) {
+        if (s[0] == '/') failed = true;
+        int n; decode_rune(s, n); s.remove_prefix(n);
+      }
+      chunk.remove_prefix(1);
+    } else {
+      if (c == '\\') {
+        chunk.remove_prefix(1);
+        if (chunk.empty()) { err = true; return; }
+      }
+      if (!failed) {
+        if (chunk[0] != s[0]) failed = true;
+        s.remove_prefix(1);
+      }
+      chunk.remove_prefix(1);
+    }
+  }
+  if (failed) return;
+  rest = s;
+  ok = true;
+}
+
+// 1 match, 0 no match, -1 ErrBadPattern
+int path_match(sv pattern, sv name) {
+  while (!pattern.empty()) {
+    ChunkScan sc = scan_chunk(pattern);
+    bool star = sc.star;
+    sv chunk = sc.chunk;
+    pattern = sc.rest;
+    if (star && chunk.empty()) return name.find('/') == sv::npos ? 1 : 0;
+    sv t; bool ok, err;
+    match_chunk(chunk, name, t, ok, err);
+    if (ok && (t.empty() || !pattern.empty())) { name = t; continue; }
+    if (err) return -1;
+    bool advanced = false;
+    if (star) {
+      for (size_t i = 0; i < name.size() && name[i] != '/'; ++i) {
+        match_chunk(chunk, name.substr(i + 1), t, ok, err);
+        if (ok) {
+          if (pattern.empty() && !t.empty()) continue;
+          name = t;
+          advanced = true;
+          break;
+        }
+        if (err) return -1;
+      }
+    }
+    if (advanced) continue;
+    while (!pattern.empty()) {
+      ChunkScan s2 = scan_chunk(pattern);
+      pattern = s2.rest;
+      sv tt; bool ok2, err2;
+      match_chunk(s2.chunk, sv(), tt, ok2, err2);
+      if (err2) return -1;
+    }
+    return 0;
+  }
+  return name.empty() ? 1 : 0;
+}
+
+// ============================================================ policy model
+// safety_policy.go:13-107
+struct MCPPolicy {
+  std::vector<std::string> allow_servers, deny_servers, allow_tools, deny_tools, allow_resources, deny_resources,
+      allow_actions, deny_actions;
+};
+struct PolicyMatch {
+  std::vector<std::string> tenants, topics, capabilities, risk_tags, requires_, pack_ids, actor_ids, actor_types;
+  std::vector<std::pair<std::string, std::string>> labels;  // map, unique keys
+  int secrets_present = -1;                                  // *bool: -1 nil, 0 false, 1 true
+  MCPPolicy mcp;
+};
+struct PolicyConstraints {
+  int64_t max_runtime_ms = 0; int32_t max_retries = 0; int64_t max_artifact_bytes = 0; int32_t max_concurrent_jobs = 0;
+  bool isolated = false;
+  size_t n_network_allowlist = 0, n_fs_read_only = 0, n_fs_read_write = 0, n_allowed_tools = 0, n_allowed_commands = 0;
+  int32_t max_files = 0, max_lines = 0;
+  size_t n_deny_path_globs = 0;
+  std::string redaction_level;
+};
+struct PolicyRule {
+  std::string id, decision, reason;
+  PolicyMatch match;
+  PolicyConstraints constraints;
+};
+struct TenantPolicy {
+  std::vector<std::string> allow_topics, deny_topics;
+  MCPPolicy mcp;
+};
+struct SafetyPolicy {
+  std::string default_tenant;
+  std::vector<PolicyRule> rules;
+  std::map<std::string, TenantPolicy> tenants;   // sorted: deterministic legacy-rule order
+  std::vector<PolicyRule> effective_rules;       // rules, or legacyRules(p) when len(rules)==0
+};
+
+// safety_policy.go:110-146
+struct MCPRequest { std::string server, tool, resource, action; };
+struct PolicyMeta {
+  std::string actor_id, actor_type, capability, pack_id;
+  std::vector<std::string> risk_tags, requires_;
+};
+using LabelMap = std::unordered_map<std::string, std::string>;
+struct PolicyInput {
+  std::string tenant, topic;
+  const LabelMap* labels = nullptr;   // nil when the job has no labels
+  PolicyMeta meta;
+  bool secrets_present = false;
+  MCPRequest mcp;
+};
+struct PolicyDecision {
+  std::string decision = "allow";
+  std::string reason;
+  int rule_idx = -1;
+  bool approval_required = false;
+};
+
+// safety_policy.go:208-223
+std::string normalize_decision(sv raw) {
+  std::string s = to_lower(trim_space(raw));
+  if (s == "allow" || s == "permit") return "allow";
+  if (s == "deny" || s == "block") return "deny";
+  if (s == "require_approval" || s == "require-approval" || s == "require_human") return "require_approval";
+  if (s == "allow_with_constraints" || s == "allow-with-constraints") return "allow_with_constraints";
+  if (s == "throttle") return "throttle";
+  return "allow";
+}
+
+// safety_policy.go:296-306
+bool contains_string(const std::vector<std::string>& list, sv value) {
+  if (value.empty()) return false;
+  for (auto& v : list)
+    if (equal_fold(trim_space(v), trim_space(value))) return true;
+  return false;
+}
+// :308-318
+bool contains_any(const std::vector<std::string>& list, const std::vector<std::string>& values) {
+  if (list.empty() || values.empty()) return false;
+  for (auto& v : values)
+    if (contains_string(list, v)) return true;
+  return false;
+}
+// :320-330
+bool contains_all(const std::vector<std::string>& values, const std::vector<std::string>& required) {
+  if (required.empty()) return true;
+  for (auto& v : required)
+    if (!contains_string(values, v)) return false;
+  return true;
+}
+// :332-345
+bool labels_match(const std::vector<std::pair<std::string, std::string>>& required, const LabelMap* actual) {
+  if (required.empty()) return true;
+  if (!actual || actual->empty()) return false;
+  for (auto& kv : required) {
+    auto it = actual->find(kv.first);
+    sv have = it == actual->end() ? sv() : sv(it->second);
+    if (have != sv(kv.second)) return false;
+  }
+  return true;
+}
+// :356-363
+bool match_topic(sv pattern, sv topic) {
+  pattern = trim_space(pattern);
+  if (pattern.empty()) return false;
+  return path_match(pattern, topic) == 1;
+}
+// :347-354
+bool match_any_topic(const std::vector<std::string>& patterns, sv topic) {
+  for (auto& p : patterns)
+    if (match_topic(p, topic)) return true;
+  return false;
+}
+// :404-406
+bool mcp_used(const MCPRequest& r) {
+  return !trim_space(r.server).empty() || !trim_space(r.tool).empty() || !trim_space(r.resource).empty() ||
+         !trim_space(r.action).empty();
+}
+// :408-416 ; code: 0 ok, 1 denied, 2 not allowed
+int match_mcp_field(sv value, const std::vector<std::string>& allow, const std::vector<std::string>& deny) {
+  if (contains_string(deny, value)) return 1;
+  if (!allow.empty() && !contains_string(allow, value)) return 2;
+  return 0;
+}
+// :385-402 ; returns 0 if allowed else 1 + field*2 + (code-1)
+int mcp_allowed(const MCPPolicy& p, const MCPRequest& r) {
+  if (!mcp_used(r)) return 0;
+  int c;
+  if ((c = match_mcp_field(r.server, p.allow_servers, p.deny_servers))) return 1 + 0 + (c - 1);
+  if ((c = match_mcp_field(r.tool, p.allow_tools, p.deny_tools))) return 1 + 2 + (c - 1);
+  if ((c = match_mcp_field(r.resource, p.allow_resources, p.deny_resources))) return 1 + 4 + (c - 1);
+  if ((c = match_mcp_field(r.action, p.allow_actions, p.deny_actions))) return 1 + 6 + (c - 1);
+  return 0;
+}
+// :365-382
+bool mcp_match(const MCPPolicy& p, const MCPRequest& r) { return mcp_allowed(p, r) == 0; }
+
+std::string mcp_reason(int code, const MCPRequest& r) {   // code = mcp_allowed() result, >0
+  int k = code - 1;
+  int field = k / 2;
+  bool not_allowed = k & 1;
+  static const char* names[4] = {"server", "tool", "resource", "action"};
+  const std::string* vals[4] = {&r.server, &r.tool, &r.resource, &r.action};
+  // fmt %q: Go-quoted string.  Values here are label text; quote like strconv.Quote for
+  // printable ASCII (escape \ and "); other bytes are passed through (tests use ASCII).
+  std::string q = "\"";
+  for (char c : *vals[field]) {
+    if (c == '"' || c == '\\') q.push_back('\\');
+    q.push_back(c);
+  }
+  q.push_back('"');
+  return std::string("mcp ") + names[field] + " " + q + (not_allowed ? " not allowed" : " denied");
+}
+
+// :259-294
+bool match_rule(const PolicyMatch& m, const PolicyInput& in) {
+  if (!m.tenants.empty() && !contains_string(m.tenants, in.tenant)) return false;
+  if (!m.topics.empty() && !match_any_topic(m.topics, in.topic)) return false;
+  if (!m.capabilities.empty() && !contains_string(m.capabilities, in.meta.capability)) return false;
+  if (!m.risk_tags.empty() && !contains_any(m.risk_tags, in.meta.risk_tags)) return false;
+  if (!m.requires_.empty() && !contains_all(in.meta.requires_, m.requires_)) return false;
+  if (!m.pack_ids.empty() && !contains_string(m.pack_ids, in.meta.pack_id)) return false;
+  if (!m.actor_ids.empty() && !contains_string(m.actor_ids, in.meta.actor_id)) return false;
+  if (!m.actor_types.empty() && !contains_string(m.actor_types, in.meta.actor_type)) return false;
+  if (m.secrets_present >= 0 && in.secrets_present != (m.secrets_present == 1)) return false;
+  if (!m.labels.empty() && !labels_match(m.labels, in.labels)) return false;
+  if (!mcp_match(m.mcp, in.mcp)) return false;
+  return true;
+}
+
+// :225-257 — tenants visited in sorted key order (Go: random, harmless — see SURVEY A.2)
+std::vector<PolicyRule> legacy_rules(const SafetyPolicy& p) {
+  std::vector<PolicyRule> out;
+  for (auto& kv : p.tenants) {
+    const std::string& tenant = kv.first;
+    const TenantPolicy& tp = kv.second;
+    for (size_t i = 0; i < tp.deny_topics.size(); ++i) {
+      PolicyRule r;
+      r.id = "legacy:" + tenant + ":deny:" + std::to_string(i + 1);
+      r.decision = "deny";
+      std::string q = "\"";
+      for (char c : tp.deny_topics[i]) { if (c == '"' || c == '\\') q.push_back('\\'); q.push_back(c); }
+      q.push_back('"');
+      r.reason = "topic " + q + " denied by tenant policy";
+      r.match.tenants = {tenant};
+      r.match.topics = {tp.deny_topics[i]};
+      r.match.mcp = tp.mcp;
+      out.push_back(std::move(r));
+    }
+    for (size_t i = 0; i < tp.allow_topics.size(); ++i) {
+      PolicyRule r;
+      r.id = "legacy:" + tenant + ":allow:" + std::to_string(i + 1);
+      r.decision = "allow";
+      r.match.tenants = {tenant};
+      r.match.topics = {tp.allow_topics[i]};
+      r.match.mcp = tp.mcp;
+      out.push_back(std::move(r));
+    }
+  }
+  return out;
+}
+
+// :187-206
+PolicyDecision policy_evaluate(const SafetyPolicy& p, const PolicyInput& in) {
+  const std::vector<PolicyRule>& rules = p.effective_rules;
+  for (size_t i = 0; i < rules.size(); ++i) {
+    if (match_rule(rules[i].match, in)) {
+      PolicyDecision d;
+      d.decision = normalize_decision(rules[i].decision);
+      d.reason = rules[i].reason;
+      d.rule_idx = (int)i;
+      d.approval_required = d.decision == "require_approval";
+      return d;
+    }
+  }
+  return PolicyDecision{};
+}
+
+// kernel.go:447-453
+bool constraints_empty(const PolicyConstraints& c) {
+  return c.max_runtime_ms == 0 && c.max_retries == 0 && c.max_artifact_bytes == 0 && c.max_concurrent_jobs == 0 &&
+         !c.isolated && c.n_network_allowlist == 0 && c.n_fs_read_only == 0 && c.n_fs_read_write == 0 &&
+         c.n_allowed_tools == 0 && c.n_allowed_commands == 0 && c.max_files == 0 && c.max_lines == 0 &&
+         c.n_deny_path_globs == 0 && trim_space(c.redaction_level).empty();
+}
+
+// ------------------------------------------------------------ JSON → policy
+bool str_list(const mjson::Value* v, std::vector<std::string>& out, const char* what) {
+  out.clear();
+  if (!v || v->is_null()) return true;
+  if (!v->is_arr()) { g_err = std::string(what) + ": expected a list"; return false; }
+  for (auto& e : v->arr) {
+    if (e.is_null()) { out.emplace_back(); continue; }
+    if (!e.is_str()) { g_err = std::string(what) + ": expected strings"; return false; }
+    out.push_back(e.s);
+  }
+  return true;
+}
+bool parse_mcp(const mjson::Value* v, MCPPolicy& m) {
+  if (!v || v->is_null()) return true;
+  if (!v->is_obj()) { g_err = "mcp: expected object"; return false; }
+  return str_list(v->get("allow_servers"), m.allow_servers, "allow_servers") &&
+         str_list(v->get("deny_servers"), m.deny_servers, "deny_servers") &&
+         str_list(v->get("allow_tools"), m.allow_tools, "allow_tools") &&
+         str_list(v->get("deny_tools"), m.deny_tools, "deny_tools") &&
+         str_list(v->get("allow_resources"), m.allow_resources, "allow_resources") &&
+         str_list(v->get("deny_resources"), m.deny_resources, "deny_resources") &&
+         str_list(v->get("allow_actions"), m.allow_actions, "allow_actions") &&
+         str_list(v->get("deny_actions"), m.deny_actions, "deny_actions");
+}
+std::string jstr(const mjson::Value* v) { return (v && v->is_str()) ? v->s : std::string(); }
+int64_t jint(const mjson::Value* v) {
+  if (!v || !v->is_num()) return 0;
+  return v->is_int ? v->i : (int64_t)v->d;
+}
+size_t jlen(const mjson::Value* v) { return (v && v->is_arr()) ? v->arr.size() : 0; }
+
+bool parse_policy(sv text, std::unique_ptr<SafetyPolicy>& out) {
+  out.reset();
+  if (text.empty()) return true;   // nil policy
+  mjson::Value root;
+  std::string err;
+  if (!mjson::parse(text, root, &err)) { g_err = "policy json: " + err; return false; }
+  if (root.is_null()) return true;
+  if (!root.is_obj()) { g_err = "policy json: expected object"; return false; }
+  auto p = std::make_unique<SafetyPolicy>();
+  p->default_tenant = jstr(root.get("default_tenant"));
+  if (const mjson::Value* rules = root.get("rules"); rules && !rules->is_null()) {
+    if (!rules->is_arr()) { g_err = "rules: expected list"; return false; }
+    for (auto& rv : rules->arr) {
+      if (!rv.is_obj()) { g_err = "rule: expected object"; return false; }
+      PolicyRule r;
+      r.id = jstr(rv.get("id"));
+      r.decision = jstr(rv.get("decision"));
+      r.reason = jstr(rv.get("reason"));
+      if (const mjson::Value* m = rv.get("match"); m && m->is_obj()) {
+        if (!str_list(m->get("tenants"), r.match.tenants, "tenants") ||
+            !str_list(m->get("topics"), r.match.topics, "topics") ||
+            !str_list(m->get("capabilities"), r.match.capabilities, "capabilities") ||
+            !str_list(m->get("risk_tags"), r.match.risk_tags, "risk_tags") ||
+            !str_list(m->get("requires"), r.match.requires_, "requires") ||
+            !str_list(m->get("pack_ids"), r.match.pack_ids, "pack_ids") ||
+            !str_list(m->get("actor_ids"), r.match.actor_ids, "actor_ids") ||
+            !str_list(m->get("actor_types"), r.match.actor_types, "actor_types"))
+          return false;
+        if (const mjson::Value* l = m->get("labels"); l && l->is_obj()) {
+          std::map<std::string, std::string> tmp;   // map: last duplicate wins
+          for (auto& kv : l->obj) tmp[kv.first] = kv.second.is_str() ? kv.second.s : std::string();
+          for (auto& kv : tmp) r.match.labels.emplace_back(kv.first, kv.second);
+        }
+        if (const mjson::Value* s = m->get("secrets_present"); s && s->is_bool()) r.match.secrets_present = s->b ? 1 : 0;
+        if (!parse_mcp(m->get("mcp"), r.match.mcp)) return false;
+      }
+      if (const mjson::Value* c = rv.get("constraints"); c && c->is_obj()) {
+        PolicyConstraints& pc = r.constraints;
+        if (const mjson::Value* b = c->get("budgets"); b && b->is_obj()) {
+          pc.max_runtime_ms = jint(b->get("max_runtime_ms"));
+          pc.max_retries = (int32_t)jint(b->get("max_retries"));
+          pc.max_artifact_bytes = jint(b->get("max_artifact_bytes"));
+          pc.max_concurrent_jobs = (int32_t)jint(b->get("max_concurrent_jobs"));
+        }
+        if (const mjson::Value* s = c->get("sandbox"); s && s->is_obj()) {
+          const mjson::Value* iso = s->get("isolated");
+          pc.isolated = iso && iso->is_bool() && iso->b;
+          pc.n_network_allowlist = jlen(s->get("network_allowlist"));
+          pc.n_fs_read_only = jlen(s->get("fs_read_only"));
+          pc.n_fs_read_write = jlen(s->get("fs_read_write"));
+        }
+        if (const mjson::Value* t = c->get("toolchain"); t && t->is_obj()) {
+          pc.n_allowed_tools = jlen(t->get("allowed_tools"));
+          pc.n_allowed_commands = jlen(t->get("allowed_commands"));
+        }
+        if (const mjson::Value* d = c->get("diff"); d && d->is_obj()) {
+          pc.max_files = (int32_t)jint(d->get("max_files"));
+          pc.max_lines = (int32_t)jint(d->get("max_lines"));
+          pc.n_deny_path_globs = jlen(d->get("deny_path_globs"));
+        }
+        pc.redaction_level = jstr(c->get("redaction_level"));
+      }
+      p->rules.push_back(std::move(r));
+    }
+  }
+  if (const mjson::Value* ten = root.get("tenants"); ten && ten->is_obj()) {
+    for (auto& kv : ten->obj) {
+      TenantPolicy tp;
+      if (kv.second.is_obj()) {
+        if (!str_list(kv.second.get("allow_topics"), tp.allow_topics, "allow_topics") ||
+            !str_list(kv.second.get("deny_topics"), tp.deny_topics, "deny_topics") ||
+            !parse_mcp(kv.second.get("mcp"), tp.mcp))
+          return false;
+      }
+      p->tenants[kv.first] = std::move(tp);   // last duplicate wins
+    }
+  }
+  p->effective_rules = p->rules.empty() ? legacy_rules(*p) : p->rules;   // safety_policy.go:188-191
+  out = std::move(p);
+  return true;
+}
+
+// ------------------------------------------------------------ effective config
+// categories.go:6-35 / effective.go:12-39, decoded with encoding/json typing rules.
+struct EffSafety { std::vector<std::string> allowed_topics, denied_topics; MCPPolicy mcp; };
+
+bool key_fold_eq(sv a, sv b) { return equal_fold(a, b); }
+
+bool json_str_list(const mjson::Value& v, std::vector<std::string>& out) {   // []string target
+  if (v.is_null()) { out.clear(); return true; }
+  if (!v.is_arr()) return false;
+  out.clear();
+  bool ok = true;
+  for (auto& e : v.arr) {
+    if (e.is_null()) out.emplace_back();
+    else if (e.is_str()) out.push_back(e.s);
+    else { out.emplace_back(); ok = false; }
+  }
+  return ok;
+}
+
+// Find the struct field a JSON key addresses: exact match first, else case-insensitive.
+int field_index(sv key, const char* const* names, int n) {
+  for (int i = 0; i < n; ++i) if (key == names[i]) return i;
+  for (int i = 0; i < n; ++i) if (key_fold_eq(key, names[i])) return i;
+  return -1;
+}
+
+bool decode_mcp_policy(const mjson::Value& v, MCPPolicy& m) {
+  if (v.is_null()) return true;
+  if (!v.is_obj()) return false;
+  static const char* names[8] = {"allow_servers", "deny_servers", "allow_tools", "deny_tools",
+                                 "allow_resources", "deny_resources", "allow_actions", "deny_actions"};
+  std::vector<std::string>* dst[8] = {&m.allow_servers, &m.deny_servers, &m.allow_tools, &m.deny_tools,
+                                      &m.allow_resources, &m.deny_resources, &m.allow_actions, &m.deny_actions};
+  bool ok = true;
+  for (auto& kv : v.obj) {
+    int f = field_index(kv.first, names, 8);
+    if (f < 0) continue;
+    if (!json_str_list(kv.second, *dst[f])) ok = false;
+  }
+  return ok;
+}
+
+bool decode_safety_config(const mjson::Value& v, EffSafety& cfg) {
+  cfg = EffSafety{};
+  if (v.is_null()) return true;   // Unmarshal of null into a struct is a no-op, no error
+  if (!v.is_obj()) return false;
+  enum { B, S, L, M, P };   // bool, string, []string, map[string]float64, MCPPolicy
+  static const char* names[] = {"pii_detection_enabled", "pii_action", "pii_types", "allowed_email_domains",
+                                "injection_detection", "injection_action", "injection_sensitivity",
+                                "content_filter_enabled", "blocked_categories", "anomaly_detection",
+                                "anomaly_thresholds", "allowed_topics", "denied_topics", "allowed_repo_hosts",
+                                "denied_repo_hosts", "mcp"};
+  static const int kinds[] = {B, S, L, L, B, S, S, B, L, B, M, L, L, L, L, P};
+  bool ok = true;
+  std::vector<std::string> scratch;
+  for (auto& kv : v.obj) {
+    int f = field_index(kv.first, names, 16);
+    if (f < 0) continue;
+    const mjson::Value& x = kv.second;
+    switch (kinds[f]) {
+      case B: if (!x.is_null() && !x.is_bool()) ok = false; break;
+      case S: if (!x.is_null() && !x.is_str()) ok = false; break;
+      case L: {
+        std::vector<std::string>* dst = &scratch;
+        if (f == 11) dst = &cfg.allowed_topics;
+        if (f == 12) dst = &cfg.denied_topics;
+        if (!json_str_list(x, *dst)) ok = false;
+        break;
+      }
+      case M:
+        if (x.is_null()) break;
+        if (!x.is_obj()) { ok = false; break; }
+        for (auto& e : x.obj) if (!e.second.is_null() && !e.second.is_num()) ok = false;
+        break;
+      case P: if (!decode_mcp_policy(x, cfg.mcp)) ok = false; break;
+    }
+  }
+  return ok;
+}
+
+// effective.go:12-39
+bool parse_effective_safety(sv payload, EffSafety& cfg) {
+  if (payload.empty()) return false;
+  mjson::Value top;
+  if (!mjson::parse(payload, top)) return false;
+  if (!top.is_obj()) return false;   // null → empty map; other kinds → type error
+  if (const mjson::Value* raw = top.get("safety")) {
+    if (decode_safety_config(*raw, cfg)) return true;
+  }
+  if (const mjson::Value* raw = top.get("data")) {
+    if (raw->is_obj()) {
+      if (const mjson::Value* sraw = raw->get("safety")) {
+        if (decode_safety_config(*sraw, cfg)) return true;
+      }
+    }
+  }
+  cfg = EffSafety{};
+  return false;
+}
+
+// kernel.go:455-474
+bool config_match(sv pattern, sv value) {
+  pattern = trim_space(pattern);
+  if (pattern.empty()) return false;
+  return path_match(pattern, value) == 1;
+}
+bool match_any(const std::vector<std::string>& patterns, sv value) {
+  if (value.empty()) return false;
+  for (auto& p : patterns)
+    if (config_match(p, value)) return true;
+  return false;
+}
+
+// ============================================================ routing model
+struct PoolProfile { std::vector<std::string> requires_; };
+struct PoolRouting {
+  std::unordered_map<std::string, std::vector<std::string>> topics;
+  std::unordered_map<std::string, PoolProfile> pools;
+};
+struct Worker {
+  std::string id, pool;
+  int32_t active = 0, max_parallel = 0;
+  float cpu = 0, gpu = 0;
+  LabelMap labels;
+  uint32_t slot = 0;
+};
+
+bool parse_routing(sv text, PoolRouting& out) {
+  out = PoolRouting{};
+  if (text.empty()) return true;
+  mjson::Value root;
+  std::string err;
+  if (!mjson::parse(text, root, &err)) { g_err = "routing json: " + err; return false; }
+  if (root.is_null()) return true;
+  if (!root.is_obj()) { g_err = "routing json: expected object"; return false; }
+  if (const mjson::Value* t = root.get("topics"); t && t->is_obj()) {
+    for (auto& kv : t->obj) {
+      std::vector<std::string> pools;
+      if (kv.second.is_str()) pools.push_back(kv.second.s);           // pools.go:107-111
+      else if (!str_list(&kv.second, pools, "topic pools")) return false;
+      out.topics[kv.first] = std::move(pools);
+    }
+  }
+  if (const mjson::Value* p = root.get("pools"); p && p->is_obj()) {
+    for (auto& kv : p->obj) {
+      PoolProfile prof;
+      if (kv.second.is_obj() && !str_list(kv.second.get("requires"), prof.requires_, "requires")) return false;
+      out.pools[kv.first] = std::move(prof);
+    }
+  }
+  return true;
+}
+
+// strategy_least_loaded.go:157-159 — float32, left to right, IEEE RN
+inline float load_score(const Worker& w) {
+  volatile float a = (float)w.active;
+  volatile float b = w.cpu / 100.0f;
+  volatile float c = w.gpu / 100.0f;
+  volatile float ab = a + b;
+  return ab + c;
+}
+// :177-193
+inline bool is_overloaded(const Worker& w) {
+  if (w.max_parallel > 0) {
+    volatile float u = (float)w.active / (float)w.max_parallel;
+    if (u >= 0.9f) return true;
+  }
+  if (w.cpu >= 90.0f) return true;
+  if (w.gpu >= 90.0f) return true;
+  return false;
+}
+// :161-175
+bool matches_labels(const Worker& w, const std::vector<std::pair<std::string, std::string>>& required) {
+  if (required.empty()) return true;
+  if (w.labels.empty()) return false;
+  for (auto& kv : required) {
+    auto it = w.labels.find(kv.first);
+    sv have = it == w.labels.end() ? sv() : sv(it->second);
+    if (have != sv(kv.second)) return false;
+  }
+  return true;
+}
+// :195-222
+std::vector<std::pair<std::string, std::string>> filter_placement_labels(const LabelMap* labels) {
+  std::vector<std::pair<std::string, std::string>> out;
+  if (!labels || labels->empty()) return out;
+  for (auto& kv : *labels) {
+    const std::string& k = kv.first;
+    if (k == "preferred_worker_id" || k == "preferred_pool") continue;
+    if (k == "approval_granted" || k == "secrets_present") continue;
+    if (has_prefix(k, "cordum.")) continue;
+    if (k == "workflow_id" || k == "run_id" || k == "step_id" || k == "node_id") continue;
+    if (k == "worker_id") continue;
+    out.emplace_back(k, kv.second);
+  }
+  return out;
+}
+// :241-265
+bool pool_satisfies(const std::vector<std::string>& pool_requires, const std::vector<std::string>& job_requires) {
+  if (job_requires.empty()) return true;
+  if (pool_requires.empty()) return false;
+  std::unordered_set<std::string> set;
+  for (auto& r : pool_requires) {
+    std::string q = to_lower(trim_space(r));
+    if (!q.empty()) set.insert(q);
+  }
+  for (auto& r : job_requires) {
+    std::string need = to_lower(trim_space(r));
+    if (need.empty()) continue;
+    if (!set.count(need)) return false;
+  }
+  return true;
+}
+// :224-239
+std::vector<std::string> filter_eligible_pools(const std::vector<std::string>& pools,
+                                               const std::vector<std::string>& requires_,
+                                               const std::unordered_map<std::string, PoolProfile>& cfgs) {
+  if (pools.empty()) return {};
+  if (requires_.empty()) return pools;
+  std::vector<std::string> out;
+  static const PoolProfile kZero;
+  for (auto& pool : pools) {
+    auto it = cfgs.find(pool);
+    const PoolProfile& prof = it == cfgs.end() ? kZero : it->second;
+    if (pool_satisfies(prof.requires_, requires_)) out.push_back(pool);
+  }
+  return out;
+}
+
+}  // namespace
+
+// ============================================================ context + per-job evaluation
+struct oracle_ctx {
+  std::unique_ptr<SafetyPolicy> policy;   // may be null (allow-all)
+  PoolRouting routing;
+  std::vector<Worker> workers;                              // by slot
+  std::unordered_map<std::string, uint32_t> worker_by_id;   // the registry map (last slot wins)
+  std::vector<uint32_t> visit_order;                        // live slots, ascending worker_id bytes
+};
+
+namespace {
+
+struct JobView {   // one envelope, string level
+  sv topic, tenant, principal, effcfg, meta_tenant, actor_id, capability, pack_id;
+  bool has_meta = false;
+  int actor_type = 0;
+  std::vector<std::string> risk_tags, requires_;
+  LabelMap labels;
+  bool approved = false;
+};
+
+inline sv span(const cordum_envelopes* e, const cordum_str* col, uint32_t j) {
+  if (!col) return sv();
+  return sv((const char*)e->arena + col[j].off, col[j].len);
+}
+
+JobView view_job(const cordum_envelopes* e, uint32_t j) {
+  JobView v;
+  v.topic = span(e, e->topic, j);
+  v.tenant = span(e, e->tenant, j);
+  v.principal = span(e, e->principal_id, j);
+  v.effcfg = span(e, e->effective_config, j);
+  v.has_meta = e->has_meta ? e->has_meta[j] != 0 : false;
+  v.meta_tenant = span(e, e->meta_tenant_id, j);
+  v.actor_id = span(e, e->actor_id, j);
+  v.actor_type = e->actor_type ? e->actor_type[j] : 0;
+  v.capability = span(e, e->capability, j);
+  v.pack_id = span(e, e->pack_id, j);
+  if (e->risk_off)
+    for (uint32_t k = e->risk_off[j]; k < e->risk_off[j + 1]; ++k) v.risk_tags.emplace_back(span(e, e->risk_tags, k));
+  if (e->requires_off)
+    for (uint32_t k = e->requires_off[j]; k < e->requires_off[j + 1]; ++k)
+      v.requires_.emplace_back(span(e, e->requires_, k));
+  if (e->label_off)
+    for (uint32_t k = e->label_off[j]; k < e->label_off[j + 1]; ++k)
+      v.labels[std::string(span(e, e->label_keys, k))] = std::string(span(e, e->label_vals, k));
+  v.approved = e->approved ? e->approved[j] != 0 : false;
+  return v;
+}
+
+// kernel.go:407-414
+std::string pick_label(const LabelMap& labels, std::initializer_list<const char*> keys) {
+  for (const char* k : keys) {
+    auto it = labels.find(k);
+    if (it != labels.end()) {
+      sv t = trim_space(it->second);
+      if (!t.empty()) return std::string(t);
+    }
+  }
+  return {};
+}
+// kernel.go:395-405
+MCPRequest extract_mcp(const LabelMap& labels) {
+  MCPRequest r;
+  if (labels.empty()) return r;
+  r.server = pick_label(labels, {"mcp.server", "mcp_server", "mcpServer"});
+  r.tool = pick_label(labels, {"mcp.tool", "mcp_tool", "mcpTool"});
+  r.resource = pick_label(labels, {"mcp.resource", "mcp_resource", "mcpResource"});
+  r.action = to_lower(pick_label(labels, {"mcp.action", "mcp_action", "mcpAction"}));
+  return r;
+}
+// kernel.go:381-393
+bool secrets_present(const PolicyMeta& meta, const LabelMap& labels) {
+  auto it = labels.find("secrets_present");
+  if (it != labels.end()) {
+    sv v = trim_space(it->second);
+    if (!v.empty()) return v == "true" || v == "1" || equal_fold(v, "yes");
+  }
+  for (auto& tag : meta.risk_tags)
+    if (equal_fold(tag, "secrets")) return true;
+  return false;
+}
+
+struct FullResult {
+  cordum_decision rec;
+  std::string reason, rule_id, subject, route_error;
+};
+
+const char* dec_name(int d) {
+  switch (d) {
+    case CORDUM_DEC_ALLOW: return "ALLOW";
+    case CORDUM_DEC_DENY: return "DENY";
+    case CORDUM_DEC_REQUIRE_HUMAN: return "REQUIRE_HUMAN";
+    case CORDUM_DEC_THROTTLE: return "THROTTLE";
+    case CORDUM_DEC_ALLOW_WITH_CONSTRAINTS: return "ALLOW_WITH_CONSTRAINTS";
+    default: return "UNSPECIFIED";
+  }
+}
+
+// kernel.go:129-257
+void kernel_evaluate(const oracle_ctx* ctx, const JobView& v, FullResult& out, bool want_strings) {
+  cordum_decision& rec = out.rec;
+  int decision = CORDUM_DEC_ALLOW;
+  std::string reason;
+  int reason_code = CORDUM_REASON_NONE;
+
+  std::string topic(trim_space(v.topic));
+  std::string tenant(trim_space(v.tenant));
+  if (tenant.empty() && v.has_meta) tenant = std::string(trim_space(v.meta_tenant));
+  const SafetyPolicy* policy = ctx->policy.get();
+  std::string default_tenant;
+  if (policy) default_tenant = std::string(trim_space(policy->default_tenant));
+  if (tenant.empty()) tenant = default_tenant;
+  if (tenant.empty()) tenant = "default";
+
+  if (topic.empty()) {
+    rec.decision = CORDUM_DEC_DENY; rec.reason_code = CORDUM_REASON_MISSING_TOPIC;
+    if (want_strings) out.reason = "missing topic";
+    return;
+  }
+  if (!has_prefix(topic, "job.")) {
+    rec.decision = CORDUM_DEC_DENY; rec.reason_code = CORDUM_REASON_UNSUPPORTED_TOPIC;
+    if (want_strings) out.reason = "unsupported topic";
+    return;
+  }
+
+  PolicyInput in;
+  in.tenant = tenant;
+  in.topic = topic;
+  in.labels = v.labels.empty() ? nullptr : &v.labels;
+  // policyMetaFromRequest kernel.go:348-368
+  if (!v.has_meta) {
+    if (!v.principal.empty()) in.meta.actor_id = std::string(v.principal);
+  } else {
+    in.meta.actor_id = std::string(v.actor_id);
+    in.meta.actor_type = v.actor_type == 1 ? "human" : v.actor_type == 2 ? "service" : "";
+    in.meta.capability = std::string(v.capability);
+    in.meta.risk_tags = v.risk_tags;
+    in.meta.requires_ = v.requires_;
+    in.meta.pack_id = std::string(v.pack_id);
+    if (in.meta.actor_id.empty()) in.meta.actor_id = std::string(v.principal);
+  }
+  in.mcp = extract_mcp(v.labels);
+  in.secrets_present = secrets_present(in.meta, v.labels);
+
+  PolicyDecision pd;
+  int tenant_mcp = 0;
+  if (policy) {
+    pd = policy_evaluate(*policy, in);
+    auto it = policy->tenants.find(tenant);   // exact-string map lookup, kernel.go:190
+    if (it != policy->tenants.end()) {
+      tenant_mcp = mcp_allowed(it->second.mcp, in.mcp);
+      if (tenant_mcp) {
+        pd.decision = "deny";
+        pd.reason = mcp_reason(tenant_mcp, in.mcp);
+      }
+    }
+  }
+  bool has_constraints = false;
+  if (policy && pd.rule_idx >= 0) has_constraints = !constraints_empty(policy->effective_rules[pd.rule_idx].constraints);
+
+  if (pd.decision == "deny") { decision = CORDUM_DEC_DENY; reason = pd.reason; }
+  else if (pd.decision == "require_approval") { decision = CORDUM_DEC_REQUIRE_HUMAN; reason = pd.reason; }
+  else if (pd.decision == "throttle") { decision = CORDUM_DEC_THROTTLE; reason = pd.reason; }
+  else if (pd.decision == "allow_with_constraints") decision = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+  else if (pd.decision == "allow") { if (has_constraints) decision = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS; }
+  if (decision == CORDUM_DEC_DENY || decision == CORDUM_DEC_REQUIRE_HUMAN || decision == CORDUM_DEC_THROTTLE) {
+    if (tenant_mcp) reason_code = CORDUM_REASON_TENANT_MCP + (tenant_mcp - 1);
+    else reason_code = pd.rule_idx >= 0 ? CORDUM_REASON_RULE : CORDUM_REASON_NONE;
+  }
+
+  // kernel.go:218-231
+  EffSafety eff;
+  if (parse_effective_safety(v.effcfg, eff)) {
+    if (match_any(eff.denied_topics, topic)) {
+      decision = CORDUM_DEC_DENY;
+      reason = "topic '" + topic + "' denied by effective config";
+      reason_code = CORDUM_REASON_EFF_DENIED_TOPIC;
+    }
+    if (!eff.allowed_topics.empty() && !match_any(eff.allowed_topics, topic)) {
+      decision = CORDUM_DEC_DENY;
+      reason = "topic '" + topic + "' not allowed by effective config";
+      reason_code = CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC;
+    }
+    if (int c = mcp_allowed(eff.mcp, in.mcp)) {
+      decision = CORDUM_DEC_DENY;
+      reason = mcp_reason(c, in.mcp);
+      reason_code = CORDUM_REASON_EFF_MCP + (c - 1);
+    }
+  }
+
+  bool approval_required = pd.approval_required || decision == CORDUM_DEC_REQUIRE_HUMAN;
+  rec.decision = (uint8_t)decision;
+  rec.reason_code = (uint8_t)reason_code;
+  rec.rule_idx = pd.rule_idx;
+  rec.flags = CORDUM_F_HAS_SNAPSHOT | (approval_required ? CORDUM_F_APPROVAL_REQUIRED : 0) |
+              (has_constraints ? CORDUM_F_CONSTRAINTS : 0);
+  if (want_strings) {
+    out.reason = reason;
+    if (policy && pd.rule_idx >= 0) out.rule_id = policy->effective_rules[pd.rule_idx].id;
+  }
+}
+
+// strategy_least_loaded.go:40-136
+void pick_subject(const oracle_ctx* ctx, const JobView& v, FullResult& out, bool want_strings) {
+  cordum_decision& rec = out.rec;
+  rec.worker_slot = -1;
+  if (v.topic.empty()) {
+    rec.route_status = CORDUM_ROUTE_MISSING_TOPIC;
+    if (want_strings) out.route_error = "missing topic";
+    return;
+  }
+  const PoolRouting& routing = ctx->routing;
+  const LabelMap* labels = v.labels.empty() ? nullptr : &v.labels;
+  auto required = filter_placement_labels(labels);
+  std::string pool_hint;
+  if (labels) { auto it = labels->find("preferred_pool"); if (it != labels->end()) pool_hint = it->second; }
+  std::vector<std::string> topic_pools;
+  { auto it = routing.topics.find(std::string(v.topic)); if (it != routing.topics.end()) topic_pools = it->second; }
+  if (!pool_hint.empty()) {
+    if (std::find(topic_pools.begin(), topic_pools.end(), pool_hint) == topic_pools.end()) {
+      rec.route_status = CORDUM_ROUTE_NO_POOL_PREFERRED;
+      if (want_strings) out.route_error = "no_pool_mapping";
+      return;
+    }
+    topic_pools = {pool_hint};
+  }
+  if (topic_pools.empty()) {
+    rec.route_status = CORDUM_ROUTE_NO_POOL_TOPIC;
+    if (want_strings) out.route_error = "no_pool_mapping";
+    return;
+  }
+  std::vector<std::string> job_requires;
+  if (v.has_meta) job_requires = v.requires_;
+  auto eligible = filter_eligible_pools(topic_pools, job_requires, routing.pools);
+  if (eligible.empty()) {
+    rec.route_status = CORDUM_ROUTE_NO_POOL_REQUIRES;
+    if (want_strings) out.route_error = "no_pool_mapping";
+    return;
+  }
+  std::unordered_set<std::string> pool_set(eligible.begin(), eligible.end());
+
+  std::string preferred;
+  if (labels) { auto it = labels->find("preferred_worker_id"); if (it != labels->end()) preferred = it->second; }
+  if (!preferred.empty()) {
+    auto it = ctx->worker_by_id.find(preferred);
+    if (it != ctx->worker_by_id.end()) {
+      const Worker& hb = ctx->workers[it->second];
+      if (pool_set.count(hb.pool) && matches_labels(hb, required) && !is_overloaded(hb)) {
+        // DirectSubject(preferredWorker) != "" always holds here (preferred non-empty)
+        rec.route_status = CORDUM_ROUTE_OK_PREFERRED;
+        rec.worker_slot = (int32_t)hb.slot;
+        if (want_strings) out.subject = "worker." + preferred + ".jobs";
+        return;
+      }
+    }
+  }
+  const Worker* selected = nullptr;
+  float best = 0;
+  int overloaded = 0, total = 0, n_at_min = 0;
+  for (uint32_t slot : ctx->visit_order) {
+    const Worker& hb = ctx->workers[slot];
+    if (!pool_set.count(hb.pool)) continue;
+    if (!matches_labels(hb, required)) continue;
+    total++;
+    if (is_overloaded(hb)) { overloaded++; continue; }
+    float score = load_score(hb);
+    if (!selected || score < best) { selected = &hb; best = score; n_at_min = 1; }
+    else if (score == best) n_at_min++;
+  }
+  if (!selected) {
+    if (total > 0 && overloaded == total) {
+      rec.route_status = CORDUM_ROUTE_POOL_OVERLOADED;
+      if (want_strings) out.route_error = "pool_overloaded";
+    } else {
+      rec.route_status = CORDUM_ROUTE_NO_WORKERS;
+      if (want_strings) out.route_error = "no_workers";
+    }
+    return;
+  }
+  rec.route_status = CORDUM_ROUTE_OK;
+  rec.worker_slot = (int32_t)selected->slot;
+  if (n_at_min > 1) rec.flags |= CORDUM_F_TIE;
+  if (want_strings) out.subject = selected->id.empty() ? std::string(v.topic) : "worker." + selected->id + ".jobs";
+}
+
+void eval_job(const oracle_ctx* ctx, const cordum_envelopes* env, uint32_t j, uint32_t mode, FullResult& out,
+              bool want_strings) {
+  std::memset(&out.rec, 0, sizeof(out.rec));
+  out.rec.rule_idx = -1;
+  out.rec.worker_slot = -1;
+  JobView v = view_job(env, j);
+  if (mode == CORDUM_MODE_ROUTE_ONLY) { pick_subject(ctx, v, out, want_strings); return; }
+  if (mode == CORDUM_MODE_POLICY_AND_ROUTE && v.approved) {
+    // engine.go:484-522: stored approval + matching job hash (verified by the host) → ALLOW, policy skipped
+    out.rec.decision = CORDUM_DEC_ALLOW;
+    out.rec.sched_decision = CORDUM_DEC_ALLOW;
+    out.rec.reason_code = CORDUM_REASON_APPROVAL_GRANTED;
+    out.rec.flags = CORDUM_F_APPROVED_BYPASS;
+    if (want_strings) out.reason = "approval granted";
+  } else {
+    kernel_evaluate(ctx, v, out, want_strings);
+    // safety_client.go:117-132 maps enums 1:1; engine.go:528-530:
+    int sd = out.rec.decision;
+    if ((out.rec.flags & CORDUM_F_APPROVAL_REQUIRED) &&
+        (sd == CORDUM_DEC_ALLOW || sd == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS))
+      sd = CORDUM_DEC_REQUIRE_HUMAN;
+    out.rec.sched_decision = (uint8_t)sd;
+  }
+  if (mode == CORDUM_MODE_POLICY_AND_ROUTE) {
+    // engine.go:298-347: only ALLOW / ALLOW_WITH_CONSTRAINTS continue to PickSubject (:393)
+    int sd = out.rec.sched_decision;
+    if (sd == CORDUM_DEC_ALLOW || sd == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS) pick_subject(ctx, v, out, want_strings);
+  }
+}
+
+void json_escape(std::string& o, sv s) {
+  o.push_back('"');
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back((char)c); }
+    else if (c < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o.push_back((char)c);
+  }
+  o.push_back('"');
+}
+
+void rebuild_registry(oracle_ctx* c) {
+  c->worker_by_id.clear();
+  for (uint32_t s = 0; s < c->workers.size(); ++s) c->worker_by_id[c->workers[s].id] = s;   // last wins
+  c->visit_order.clear();
+  for (auto& kv : c->worker_by_id) c->visit_order.push_back(kv.second);
+  std::sort(c->visit_order.begin(), c->visit_order.end(),
+            [&](uint32_t a, uint32_t b) { return c->workers[a].id < c->workers[b].id; });
+}
+
+}  // namespace
+
+// ============================================================ C ABI
+extern "C" {
+
+const char* oracle_last_error(void) { return g_err.c_str(); }
+oracle_ctx* oracle_create(void) { return new oracle_ctx(); }
+void oracle_destroy(oracle_ctx* c) { delete c; }
+
+int32_t oracle_policy_load(oracle_ctx* c, const char* json, uint64_t len) {
+  std::unique_ptr<SafetyPolicy> p;
+  if (!parse_policy(sv(json ? json : "", len), p)) return CORDUM_E_INVALID;
+  c->policy = std::move(p);
+  return CORDUM_OK;
+}
+
+int32_t oracle_routing_load(oracle_ctx* c, const char* json, uint64_t len) {
+  PoolRouting r;
+  if (!parse_routing(sv(json ? json : "", len), r)) return CORDUM_E_INVALID;
+  c->routing = std::move(r);
+  return CORDUM_OK;
+}
+
+int32_t oracle_workers_load(oracle_ctx* c, const cordum_workers* w) {
+  c->workers.clear();
+  if (w) {
+    c->workers.resize(w->n_workers);
+    auto sp = [&](const cordum_str* col, uint32_t i) { return sv((const char*)w->arena + col[i].off, col[i].len); };
+    for (uint32_t i = 0; i < w->n_workers; ++i) {
+      Worker& x = c->workers[i];
+      x.slot = i;
+      x.id = std::string(sp(w->worker_id, i));
+      x.pool = std::string(sp(w->pool, i));
+      x.active = w->active_jobs[i];
+      x.max_parallel = w->max_parallel_jobs[i];
+      x.cpu = w->cpu_load[i];
+      x.gpu = w->gpu_utilization[i];
+      if (w->label_off)
+        for (uint32_t k = w->label_off[i]; k < w->label_off[i + 1]; ++k)
+          x.labels[std::string(sp(w->label_keys, k))] = std::string(sp(w->label_vals, k));
+    }
+  }
+  rebuild_registry(c);
+  return CORDUM_OK;
+}
+
+int32_t oracle_workers_update(oracle_ctx* c, uint32_t n, const uint32_t* slots, const cordum_worker_load* loads) {
+  for (uint32_t i = 0; i < n; ++i) {
+    if (slots[i] >= c->workers.size()) { g_err = "slot out of range"; return CORDUM_E_INVALID; }
+    Worker& x = c->workers[slots[i]];
+    x.active = loads[i].active_jobs;
+    x.max_parallel = loads[i].max_parallel_jobs;
+    x.cpu = loads[i].cpu_load;
+    x.gpu = loads[i].gpu_utilization;
+  }
+  return CORDUM_OK;
+}
+
+int32_t oracle_eval(oracle_ctx* c, const cordum_envelopes* env, uint32_t first, uint32_t count, uint32_t mode,
+                    uint32_t threads, cordum_decision* out) {
+  if (!c || !env || !out) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if ((uint64_t)first + count > env->n_jobs) { g_err = "job range out of bounds"; return CORDUM_E_INVALID; }
+  if (threads == 0) threads = 1;
+  if (threads > count) threads = count ? count : 1;
+  std::atomic<uint32_t> next{0};
+  auto work = [&]() {
+    FullResult r;
+    const uint32_t grain = 16;
+    while (true) {
+      uint32_t b = next.fetch_add(grain);
+      if (b >= count) break;
+      uint32_t e = std::min(count, b + grain);
+      for (uint32_t k = b; k < e; ++k) {
+        eval_job(c, env, first + k, mode, r, false);
+        out[k] = r.rec;
+      }
+    }
+  };
+  if (threads == 1) work();
+  else {
+    std::vector<std::thread> ts;
+    for (uint32_t t = 0; t < threads; ++t) ts.emplace_back(work);
+    for (auto& t : ts) t.join();
+  }
+  return CORDUM_OK;
+}
+
+int64_t oracle_eval_one_json(oracle_ctx* c, const cordum_envelopes* env, uint32_t job, uint32_t mode, char* buf,
+                             uint64_t cap) {
+  if (!c || !env || job >= env->n_jobs) return -1;
+  FullResult r;
+  eval_job(c, env, job, mode, r, true);
+  std::string o = "{";
+  o += "\"decision\": \""; o += dec_name(r.rec.decision); o += "\"";
+  o += ", \"sched_decision\": \""; o += dec_name(r.rec.sched_decision); o += "\"";
+  o += ", \"reason\": "; json_escape(o, r.reason);
+  o += ", \"reason_code\": " + std::to_string(r.rec.reason_code);
+  o += ", \"rule_id\": "; json_escape(o, r.rule_id);
+  o += ", \"rule_idx\": " + std::to_string(r.rec.rule_idx);
+  o += std::string(", \"approval_required\": ") + ((r.rec.flags & CORDUM_F_APPROVAL_REQUIRED) ? "true" : "false");
+  o += std::string(", \"has_snapshot\": ") + ((r.rec.flags & CORDUM_F_HAS_SNAPSHOT) ? "true" : "false");
+  o += std::string(", \"has_constraints\": ") + ((r.rec.flags & CORDUM_F_CONSTRAINTS) ? "true" : "false");
+  o += std::string(", \"tie\": ") + ((r.rec.flags & CORDUM_F_TIE) ? "true" : "false");
+  o += ", \"route_status\": " + std::to_string(r.rec.route_status);
+  o += ", \"subject\": "; json_escape(o, r.subject);
+  o += ", \"route_error\": "; json_escape(o, r.route_error);
+  o += ", \"worker_slot\": " + std::to_string(r.rec.worker_slot);
+  o += "}";
+  if (buf && cap) {
+    size_t n = std::min<size_t>(o.size(), cap - 1);
+    std::memcpy(buf, o.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)o.size();
+}
+
+int32_t oracle_path_match(const char* pat, uint64_t plen, const char* name, uint64_t nlen) {
+  return path_match(sv(pat, plen), sv(name, nlen));
+}
+int32_t oracle_equal_fold(const char* a, uint64_t alen, const char* b, uint64_t blen) {
+  return equal_fold(sv(a, alen), sv(b, blen)) ? 1 : 0;
+}
+void oracle_trim_space(const char* s, uint64_t n, uint64_t* off, uint64_t* len) {
+  sv t = trim_space(sv(s, n));
+  *off = (uint64_t)(t.data() - s);
+  *len = t.size();
+  if (t.empty()) *off = 0;
+}
+int32_t oracle_normalize_decision(const char* s, uint64_t n) {
+  std::string d = normalize_decision(sv(s, n));
+  if (d == "deny") return CORDUM_DEC_DENY;
+  if (d == "require_approval") return CORDUM_DEC_REQUIRE_HUMAN;
+  if (d == "throttle") return CORDUM_DEC_THROTTLE;
+  if (d == "allow_with_constraints") return CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+  return CORDUM_DEC_ALLOW;
+}
+int32_t oracle_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied) {
+  EffSafety cfg;
+  bool ok = parse_effective_safety(sv(s, n), cfg);
+  if (n_allowed) *n_allowed = (uint32_t)cfg.allowed_topics.size();
+  if (n_denied) *n_denied = (uint32_t)cfg.denied_topics.size();
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,334 @@
+"""Known-answer tests the REFERENCE holds for the hot path, restated as data.
+
+Every case cites the reference test it reproduces (paths relative to
+/root/reference/core).  The same table is run against
+  - the C++ oracle            (tests/test_oracle_kats.py, CPU)
+  - the Python oracle         (tests/test_oracle_kats.py, CPU)
+  - the CUDA engine via C ABI (tests/test_gpu_parity.py, -m gpu)
+A case = dict(name, ref, policy, routing, workers, job, mode, expect) where expect maps
+result keys to required values, or to a callable predicate.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+from cordum_b200 import policy_io, wire
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+ROUTE_NAMES = {
+    wire.ROUTE_NOT_ATTEMPTED: "", wire.ROUTE_OK: "ok", wire.ROUTE_OK_PREFERRED: "ok_preferred",
+    wire.ROUTE_MISSING_TOPIC: "missing topic", wire.ROUTE_NO_POOL_PREFERRED: "no_pool_mapping:preferred",
+    wire.ROUTE_NO_POOL_TOPIC: "no_pool_mapping:topic", wire.ROUTE_NO_POOL_REQUIRES: "no_pool_mapping:requires",
+    wire.ROUTE_NO_WORKERS: "no_workers", wire.ROUTE_POOL_OVERLOADED: "pool_overloaded",
+}
+
+
+def golden(name):
+    with open(os.path.join(HERE, "golden", name)) as f:
+        return json.load(f)
+
+
+def routing_for_topic(topic, pool):   # scheduler/strategy_least_loaded_test.go:9-18
+    return {"topics": {topic: [pool]}, "pools": {pool: {"requires": []}}}
+
+
+def hb(worker_id, pool, active=0, cpu=0.0, gpu=0.0, maxp=0, labels=None):
+    return {"worker_id": worker_id, "pool": pool, "active_jobs": active, "max_parallel_jobs": maxp,
+            "cpu_load": cpu, "gpu_utilization": gpu, "labels": labels or {}}
+
+
+P, PR, R = wire.MODE_POLICY_ONLY, wire.MODE_POLICY_AND_ROUTE, wire.MODE_ROUTE_ONLY
+CASES = []
+
+
+def case(name, ref, job, expect, policy=None, routing=None, workers=None, mode=P):
+    CASES.append(dict(name=name, ref=ref, policy=policy, routing=routing, workers=workers or [], job=job,
+                      mode=mode, expect=expect))
+
+
+# ---------------------------------------------------------------- infra/config/safety_policy_test.go
+_rule1 = {"rules": [{"id": "rule1", "decision": "deny", "reason": "blocked",
+                     "match": {"tenants": ["t1"], "topics": ["job.sre.*"], "capabilities": ["cap"],
+                               "risk_tags": ["write"], "requires": ["git"], "labels": {"env": "prod"}}}]}
+_job1 = {"tenant": "t1", "topic": "job.sre.collect", "labels": {"env": "prod"},
+         "meta": {"capability": "cap", "risk_tags": ["write"], "requires": ["git", "net"], "pack_id": "pack"}}
+case("EvaluateRuleMatch", "infra/config/safety_policy_test.go:15-48", _job1,
+     {"decision": "DENY", "rule_id": "rule1", "reason": "blocked"}, policy=_rule1)
+# each predicate of that rule is necessary (matchRule, safety_policy.go:259-294)
+for _k, _mut in {
+    "tenant": lambda j: j.update(tenant="t2"),
+    "topic": lambda j: j.update(topic="job.other.collect"),
+    "capability": lambda j: j["meta"].update(capability="other"),
+    "risk": lambda j: j["meta"].update(risk_tags=["read"]),
+    "requires": lambda j: j["meta"].update(requires=["net"]),
+    "labels": lambda j: j.update(labels={"env": "dev"}),
+    "nolabels": lambda j: j.update(labels={}),
+}.items():
+    _j = json.loads(json.dumps(_job1))
+    _mut(_j)
+    case("EvaluateRuleMatch/miss-" + _k, "infra/config/safety_policy.go:259-294", _j,
+         {"decision": "ALLOW", "rule_id": "", "rule_idx": -1}, policy=_rule1)
+
+_legacy = {"tenants": {"t1": {"allow_topics": ["job.allowed"], "deny_topics": ["job.blocked"]}}}
+case("EvaluateLegacyRules/deny", "infra/config/safety_policy_test.go:50-62", {"tenant": "t1", "topic": "job.blocked"},
+     {"decision": "DENY", "rule_id": "legacy:t1:deny:1", "reason": 'topic "job.blocked" denied by tenant policy'},
+     policy=_legacy)
+case("EvaluateLegacyRules/allow", "infra/config/safety_policy_test.go:50-62", {"tenant": "t1", "topic": "job.allowed"},
+     {"decision": "ALLOW", "rule_id": "legacy:t1:allow:1"}, policy=_legacy)
+
+_remed = {"rules": [{"id": "rule-remediate", "decision": "deny",
+                     "match": {"tenants": ["t1"], "topics": ["job.db.delete"]},
+                     "remediations": [{"id": "archive", "title": "Archive instead of delete",
+                                       "summary": "Use archive flow for safer retention",
+                                       "replacement_topic": "job.db.archive"}]}]}
+case("EvaluateRemediations", "infra/config/safety_policy_test.go:64-89", {"tenant": "t1", "topic": "job.db.delete"},
+     {"decision": "DENY", "rule_id": "rule-remediate", "rule_idx": 0}, policy=_remed)
+
+_secmcp = {"rules": [{"id": "sm", "decision": "deny", "reason": "sm",
+                      "match": {"secrets_present": True, "mcp": {"allow_servers": ["srv"]}}}]}
+case("MatchRuleSecretsAndMCP/match", "infra/config/safety_policy_test.go:107-126",
+     {"tenant": "default", "topic": "job.x", "labels": {"secrets_present": "true", "mcp.server": "srv"}},
+     {"decision": "DENY", "rule_id": "sm"}, policy=_secmcp)
+case("MatchRuleSecretsAndMCP/secrets-false", "infra/config/safety_policy_test.go:107-126",
+     {"tenant": "default", "topic": "job.x", "labels": {"secrets_present": "no", "mcp.server": "srv"}},
+     {"decision": "ALLOW", "rule_id": ""}, policy=_secmcp)
+
+_mcpal = {"default_tenant": "default",
+          "tenants": {"default": {"allow_topics": ["job.*"], "mcp": {"allow_servers": ["srv"], "deny_tools": ["bad"]}}}}
+case("MCPAllowed/denied-tool", "infra/config/safety_policy_test.go:128-141",
+     {"tenant": "default", "topic": "job.x", "labels": {"mcp.server": "srv", "mcp.tool": "bad"}},
+     {"decision": "DENY", "reason": 'mcp tool "bad" denied'}, policy=_mcpal)
+case("MCPAllowed/allowed-tool", "infra/config/safety_policy_test.go:128-141",
+     {"tenant": "default", "topic": "job.x", "labels": {"mcp.server": "srv", "mcp.tool": "good"}},
+     {"decision": "ALLOW", "reason": ""}, policy=_mcpal)
+
+# ---------------------------------------------------------------- controlplane/safetykernel/kernel_test.go
+case("CheckMCPPolicyDenies", "controlplane/safetykernel/kernel_test.go:16-46",
+     {"job_id": "job-1", "topic": "job.default", "tenant": "default",
+      "labels": {"mcp.server": "blocked.example.com", "mcp.tool": "read"}},
+     {"decision": "DENY"},
+     policy={"default_tenant": "default",
+             "tenants": {"default": {"allow_topics": ["job.*"], "mcp": {"deny_servers": ["blocked.example.com"]}}}})
+case("CheckMCPPolicyRequiresFieldWhenAllowlistSet", "controlplane/safetykernel/kernel_test.go:48-77",
+     {"job_id": "job-2", "topic": "job.default", "tenant": "default", "labels": {"mcp.tool": "read"}},
+     {"decision": "DENY", "reason": 'mcp server "" not allowed'},
+     policy={"default_tenant": "default",
+             "tenants": {"default": {"allow_topics": ["job.*"], "mcp": {"allow_servers": ["github.com"]}}}})
+case("CheckReturnsRemediations", "controlplane/safetykernel/kernel_test.go:79-118",
+     {"job_id": "job-5", "topic": "job.db.delete", "tenant": "default"},
+     {"decision": "DENY", "rule_id": "deny-delete", "rule_idx": 0},
+     policy={"default_tenant": "default",
+             "rules": [{"id": "deny-delete", "decision": "deny",
+                        "match": {"tenants": ["default"], "topics": ["job.db.delete"]},
+                        "remediations": [{"id": "archive", "title": "Archive instead",
+                                          "summary": "Use archive flow for retention",
+                                          "replacement_topic": "job.db.archive"}]}]})
+case("CheckAppliesEffectiveConfigDeny", "controlplane/safetykernel/kernel_test.go:120-145",
+     {"job_id": "job-3", "topic": "job.deny", "tenant": "default",
+      "effective_config": b'{"safety":{"denied_topics":["job.deny"]}}'},
+     {"decision": "DENY", "reason": lambda r: "denied" in r},
+     policy={"default_tenant": "default", "tenants": {"default": {"allow_topics": ["job.*"]}}})
+
+# TestPolicyLoaderLoadsFragments :156-223 — fragments "alpha","beta" merged in sorted key order, "disabled" skipped
+_alpha = policy_io.parse_safety_policy("default_tenant: default\ntenants:\n  default:\n    allow_topics:\n      - job.*\n")
+_beta = policy_io.parse_safety_policy(
+    "rules:\n  - id: require-prod\n    match:\n      topics:\n        - job.prod.*\n    decision: require_approval\n    reason: prod writes\n")
+_frag = policy_io.merge_policies(policy_io.merge_policies(None, _alpha), _beta)
+case("PolicyLoaderLoadsFragments", "controlplane/safetykernel/kernel_test.go:156-223",
+     {"tenant": "default", "topic": "job.prod.test"},
+     {"decision": "REQUIRE_HUMAN", "rule_id": "require-prod", "reason": "prod writes", "approval_required": True},
+     policy=_frag)
+
+case("EvaluateExplainSimulate", "controlplane/safetykernel/kernel_test.go:225-250",
+     {"job_id": "job-9", "topic": "job.test", "tenant": "default"}, {"decision": "ALLOW", "has_snapshot": True},
+     policy={"default_tenant": "default", "tenants": {"default": {"allow_topics": ["job.*"]}}})
+case("EvaluateMissingTopic", "controlplane/safetykernel/kernel_test.go:270-282", {},
+     {"decision": "DENY", "reason": "missing topic", "has_snapshot": False}, policy={"default_tenant": "default"})
+case("EvaluateUnsupportedTopic", "controlplane/safetykernel/kernel.go:174-176", {"topic": "sys.destroy"},
+     {"decision": "DENY", "reason": "unsupported topic", "has_snapshot": False}, policy={"default_tenant": "default"})
+case("EvaluateNilPolicy", "controlplane/safetykernel/kernel.go:187-196", {"topic": "job.any"},
+     {"decision": "ALLOW", "rule_id": "", "has_snapshot": True}, policy=None)
+
+# helpers_test.go — policyMetaFromRequest :10-33 (principal fallback; service actor type)
+_actor = {"rules": [{"id": "by-actor", "decision": "deny", "match": {"actor_ids": ["p1"]}},
+                    {"id": "by-type", "decision": "throttle", "reason": "svc", "match": {"actor_types": ["service"]}}]}
+case("PolicyMetaFromRequest/principal-fallback", "controlplane/safetykernel/helpers_test.go:10-16",
+     {"topic": "job.x", "principal_id": "p1"}, {"decision": "DENY", "rule_id": "by-actor"}, policy=_actor)
+case("PolicyMetaFromRequest/meta", "controlplane/safetykernel/helpers_test.go:18-32",
+     {"topic": "job.x", "principal_id": "p1",
+      "meta": {"actor_id": "a1", "actor_type": 2, "capability": "cap", "risk_tags": ["write"], "requires": ["git"],
+               "pack_id": "pack"}},
+     {"decision": "THROTTLE", "rule_id": "by-type", "reason": "svc"}, policy=_actor)
+# TestSecretsPresent :35-47
+_sec = {"rules": [{"id": "sec", "decision": "deny", "match": {"secrets_present": True}}]}
+case("SecretsPresent/label-true", "controlplane/safetykernel/helpers_test.go:36-39",
+     {"topic": "job.x", "labels": {"secrets_present": "true"}}, {"decision": "DENY"}, policy=_sec)
+case("SecretsPresent/label-no", "controlplane/safetykernel/helpers_test.go:40-42",
+     {"topic": "job.x", "labels": {"secrets_present": "no"}}, {"decision": "ALLOW"}, policy=_sec)
+case("SecretsPresent/risk-tag", "controlplane/safetykernel/helpers_test.go:43-46",
+     {"topic": "job.x", "meta": {"risk_tags": ["secrets"]}}, {"decision": "DENY"}, policy=_sec)
+case("SecretsPresent/label-TRUE-is-false", "controlplane/safetykernel/kernel.go:384",
+     {"topic": "job.x", "labels": {"secrets_present": "TRUE"}}, {"decision": "ALLOW"}, policy=_sec)
+case("SecretsPresent/label-YES", "controlplane/safetykernel/kernel.go:384",
+     {"topic": "job.x", "labels": {"secrets_present": " Yes "}}, {"decision": "DENY"}, policy=_sec)
+# TestExtractMCPRequest :49-60 (alias keys; action lower-cased)
+_mcpx = {"rules": [{"id": "mx", "decision": "deny",
+                    "match": {"mcp": {"allow_servers": ["srv"], "allow_tools": ["tool"], "allow_resources": ["res"],
+                                      "allow_actions": ["read"]}}}]}
+case("ExtractMCPRequest", "controlplane/safetykernel/helpers_test.go:49-60",
+     {"topic": "job.x", "labels": {"mcp.server": "srv", "mcp_tool": "tool", "mcpResource": "res", "mcp_action": "READ"}},
+     {"decision": "DENY", "rule_id": "mx"}, policy=_mcpx)
+# TestConstraintsHelpers :62-71 + kernel.go:211-214 promotion
+case("ConstraintsPromoteAllow", "controlplane/safetykernel/helpers_test.go:62-71",
+     {"topic": "job.x"}, {"decision": "ALLOW_WITH_CONSTRAINTS", "has_constraints": True, "reason": ""},
+     policy={"rules": [{"id": "c", "decision": "allow", "reason": "dropped",
+                        "constraints": {"budgets": {"max_runtime_ms": 1}}}]})
+
+# ---------------------------------------------------------------- controlplane/scheduler/strategy_least_loaded_test.go
+_rt = routing_for_topic("job.default", "default")
+case("LeastLoaded/PicksPoolMatch", "controlplane/scheduler/strategy_least_loaded_test.go:20-35",
+     {"topic": "job.default"}, {"route": "ok", "subject": "worker.w2.jobs"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 2, 50), hb("w2", "default", 1, 10), hb("w3", "other", 0, 0)])
+case("LeastLoaded/NoWorkers", "controlplane/scheduler/strategy_least_loaded_test.go:37-43",
+     {"topic": "job.default"}, {"route": "no_workers"}, routing=_rt, mode=R)
+case("LeastLoaded/NoPoolConfigured", "controlplane/scheduler/strategy_least_loaded_test.go:45-51",
+     {"topic": "job.unknown"}, {"route": "no_pool_mapping:topic"}, routing=_rt, mode=R)
+case("LeastLoaded/UsesLoadScore", "controlplane/scheduler/strategy_least_loaded_test.go:53-68",
+     {"topic": "job.default"}, {"route": "ok", "subject": "worker.w2.jobs"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 1, 90, 0), hb("w2", "default", 1, 10, 0)])
+case("LeastLoaded/HonorsPreferredWorker", "controlplane/scheduler/strategy_least_loaded_test.go:70-92",
+     {"topic": "job.default", "labels": {"preferred_worker_id": "w2"}},
+     {"route": "ok_preferred", "subject": "worker.w2.jobs"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 5, 90), hb("w2", "default", 2, 50), hb("w3", "default", 1, 10)])
+case("LeastLoaded/IgnoresWorkflowLabelsForPlacement", "controlplane/scheduler/strategy_least_loaded_test.go:94-117",
+     {"topic": "job.default", "labels": {"workflow_id": "wf-1", "run_id": "run-1", "step_id": "step-1", "node_id": "n-1"}},
+     {"route": "ok", "subject": "worker.w1.jobs"}, routing=_rt, mode=R, workers=[hb("w1", "default", 0, 10)])
+case("LeastLoaded/DoesNotMarkIdleWorkerOverloaded", "controlplane/scheduler/strategy_least_loaded_test.go:119-132",
+     {"topic": "job.default"}, {"route": "ok", "subject": "worker.w1.jobs"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 0, 1, maxp=1)])
+case("LeastLoaded/MarksWorkerOverloadedWhenAtCapacity", "controlplane/scheduler/strategy_least_loaded_test.go:134-144",
+     {"topic": "job.default"}, {"route": "pool_overloaded"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 1, 1, maxp=1)])
+# TestFilterPlacementLabels :146-168 — only region+gpu constrain placement
+_lab = {"preferred_worker_id": "w1", "preferred_pool": "default", "approval_granted": "true", "secrets_present": "true",
+        "cordum.trace": "trace", "workflow_id": "wf", "run_id": "run", "step_id": "step", "node_id": "node",
+        "worker_id": "worker", "region": "us-east", "gpu": "true"}
+case("FilterPlacementLabels/match", "controlplane/scheduler/strategy_least_loaded_test.go:146-168",
+     {"topic": "job.default", "labels": dict(_lab, preferred_worker_id="zz")},
+     {"route": "ok", "subject": "worker.w2.jobs"}, routing=_rt, mode=R,
+     workers=[hb("w1", "default", 0, 0, labels={"region": "us-east"}),
+              hb("w2", "default", 3, 0, labels={"region": "us-east", "gpu": "true", "extra": "1"})])
+case("FilterPlacementLabels/none-match", "controlplane/scheduler/strategy_least_loaded_test.go:146-168",
+     {"topic": "job.default", "labels": dict(_lab, preferred_worker_id="zz")}, {"route": "no_workers"}, routing=_rt,
+     mode=R, workers=[hb("w1", "default", 0, 0, labels={"region": "us-east"}), hb("w2", "default", 0, 0)])
+# TestFilterEligiblePools :170-185 / TestPoolSatisfies :187-197
+_rt3 = {"topics": {"job.t": ["p1", "p2", "p3"]},
+        "pools": {"p1": {"requires": ["linux", "gpu"]}, "p2": {"requires": ["linux"]}, "p3": {}}}
+_w3 = [hb("a1", "p1", 5), hb("a2", "p2", 4), hb("a3", "p3", 0)]
+case("FilterEligiblePools/linux", "controlplane/scheduler/strategy_least_loaded_test.go:170-181",
+     {"topic": "job.t", "meta": {"requires": ["linux"]}}, {"route": "ok", "subject": "worker.a2.jobs"}, routing=_rt3,
+     mode=R, workers=_w3)
+case("FilterEligiblePools/none", "controlplane/scheduler/strategy_least_loaded_test.go:182-185",
+     {"topic": "job.t", "meta": {"requires": []}}, {"route": "ok", "subject": "worker.a3.jobs"}, routing=_rt3, mode=R,
+     workers=_w3)
+case("PoolSatisfies/case-trim", "controlplane/scheduler/strategy_least_loaded_test.go:187-190",
+     {"topic": "job.t", "meta": {"requires": ["gpu", "linux"]}}, {"route": "ok", "subject": "worker.g.jobs"},
+     routing={"topics": {"job.t": ["gp"]}, "pools": {"gp": {"requires": ["GPU", " linux "]}}}, mode=R,
+     workers=[hb("g", "gp")])
+case("PoolSatisfies/missing", "controlplane/scheduler/strategy_least_loaded_test.go:191-193",
+     {"topic": "job.t", "meta": {"requires": ["gpu", "linux"]}}, {"route": "no_pool_mapping:requires"},
+     routing={"topics": {"job.t": ["gp"]}, "pools": {"gp": {"requires": ["gpu"]}}}, mode=R, workers=[hb("g", "gp")])
+case("PoolSatisfies/empty-pool-requires", "controlplane/scheduler/strategy_least_loaded_test.go:194-196",
+     {"topic": "job.t", "meta": {"requires": ["gpu"]}}, {"route": "no_pool_mapping:requires"},
+     routing={"topics": {"job.t": ["gp"]}, "pools": {"gp": {}}}, mode=R, workers=[hb("g", "gp")])
+# TestIsOverloadedThresholds :208-218
+case("IsOverloaded/cpu95", "controlplane/scheduler/strategy_least_loaded_test.go:209-211",
+     {"topic": "job.default"}, {"route": "pool_overloaded"}, routing=_rt, mode=R, workers=[hb("w", "default", cpu=95)])
+case("IsOverloaded/gpu95", "controlplane/scheduler/strategy_least_loaded_test.go:212-214",
+     {"topic": "job.default"}, {"route": "pool_overloaded"}, routing=_rt, mode=R, workers=[hb("w", "default", gpu=95)])
+case("IsOverloaded/ok", "controlplane/scheduler/strategy_least_loaded_test.go:215-217",
+     {"topic": "job.default"}, {"route": "ok"}, routing=_rt, mode=R, workers=[hb("w", "default", cpu=10, gpu=10)])
+case("PreferredPool/not-mapped", "controlplane/scheduler/strategy_least_loaded.go:50-53",
+     {"topic": "job.default", "labels": {"preferred_pool": "other"}}, {"route": "no_pool_mapping:preferred"},
+     routing=_rt, mode=R, workers=[hb("w", "default")])
+case("MissingTopic/route", "controlplane/scheduler/strategy_least_loaded.go:41-43", {"topic": ""},
+     {"route": "missing topic"}, routing=_rt, mode=R)
+
+# ---------------------------------------------------------------- scheduler glue
+# engine_test.go:332-356 (SafetyBasic denies sys.destroy -> DENIED, nothing dispatched)
+case("EngineDenyNotDispatched", "controlplane/scheduler/engine_test.go:332-356",
+     {"topic": "sys.destroy", "tenant": "default"}, {"sched_decision": "DENY", "route": "", "worker_slot": -1},
+     policy={"default_tenant": "default"}, routing=_rt, workers=[hb("w1", "default")], mode=PR)
+# integration_test.go:48-135 (heartbeat -> job submit -> direct subject worker.<id>.jobs)
+case("IntegrationDirectSubject", "controlplane/scheduler/integration_test.go:48-135",
+     {"topic": "job.default", "tenant": "default"}, {"sched_decision": "ALLOW", "route": "ok", "subject": "worker.w1.jobs"},
+     policy={"default_tenant": "default", "tenants": {"default": {"allow_topics": ["job.*"]}}}, routing=_rt,
+     workers=[hb("w1", "default", 0, 5, maxp=4)], mode=PR)
+# engine.go:528-530 post-step; REQUIRE_APPROVAL is not dispatched
+case("ApprovalPostStep", "controlplane/scheduler/engine.go:524-531",
+     {"topic": "job.prod.x", "tenant": "default"},
+     {"decision": "REQUIRE_HUMAN", "sched_decision": "REQUIRE_HUMAN", "approval_required": True, "route": ""},
+     policy=_frag, routing={"topics": {"job.prod.x": ["default"]}, "pools": {"default": {}}},
+     workers=[hb("w1", "default")], mode=PR)
+case("ApprovedBypass", "controlplane/scheduler/engine.go:484-522",
+     {"topic": "job.prod.x", "tenant": "default", "labels": {"approval_granted": "true"}, "approved": True},
+     {"decision": "ALLOW", "sched_decision": "ALLOW", "reason": "approval granted", "route": "ok",
+      "subject": "worker.w1.jobs"},
+     policy=_frag, routing={"topics": {"job.prod.x": ["default"]}, "pools": {"default": {}}},
+     workers=[hb("w1", "default")], mode=PR)
+
+# ---------------------------------------------------------------- fixtures: BASELINE config 1 and 5
+_c1 = golden("c1_hello_pack.json")
+_c1_workers = [hb("hello-worker-a", "hello-pack", 0, maxp=4), hb("hello-worker-b", "hello-pack", 1, maxp=4)]
+_c1_job = {"topic": "job.hello-pack.echo", "tenant": "default",
+           "meta": {"capability": "hello-pack.echo", "pack_id": "hello-pack"},
+           "labels": {"workflow_id": "wf", "run_id": "run", "step_id": "step"}}
+case("C1/hello-pack", "examples/hello-pack/pack.yaml:43-50 + SURVEY §8d config 1", _c1_job,
+     {"decision": "ALLOW", "sched_decision": "ALLOW", "rule_id": "hello-pack-allow", "reason": "", "route": "ok",
+      "subject": "worker.hello-worker-a.jobs"},
+     policy=_c1["policy"], routing=_c1["routing"], workers=_c1_workers, mode=PR)
+_c5 = golden("c5_demo_guardrails.json")
+_c5_workers = [hb("demo-worker", "demo-guardrails", 0, maxp=8)]
+
+
+def c5_job(kind, approved=False):
+    j = {"tenant": "default", "topic": "job.demo-guardrails." + ("write" if kind.startswith("write") else kind),
+         "meta": {"capability": "demo-guardrails." + kind, "pack_id": "demo-guardrails", "risk_tags": []}, "labels": {}}
+    if kind == "write":
+        j["meta"]["risk_tags"] = ["write", "prod"]
+    if approved:
+        j["labels"]["approval_granted"] = "true"
+        j["approved"] = True
+    return j
+
+
+case("C5/write-requires-approval", "examples/demo-guardrails/overlays/policy.fragment.yaml:2-9", c5_job("write"),
+     {"decision": "REQUIRE_HUMAN", "sched_decision": "REQUIRE_HUMAN", "approval_required": True,
+      "rule_id": "demo-guardrails-approval", "reason": "Write operations require approval.", "route": ""},
+     policy=_c5["policy"], routing=_c5["routing"], workers=_c5_workers, mode=PR)
+case("C5/write-no-tags-default-allow", "examples/demo-guardrails/overlays/policy.fragment.yaml:2-9",
+     c5_job("write-untagged"),
+     {"decision": "ALLOW", "rule_id": "", "route": "ok", "subject": "worker.demo-worker.jobs"},
+     policy=_c5["policy"], routing=_c5["routing"], workers=_c5_workers, mode=PR)
+case("C5/dangerous-denied", "examples/demo-guardrails/overlays/policy.fragment.yaml:10-24", c5_job("dangerous"),
+     {"decision": "DENY", "rule_id": "demo-guardrails-deny", "rule_idx": 1, "reason": "Dangerous operation blocked.",
+      "route": ""},
+     policy=_c5["policy"], routing=_c5["routing"], workers=_c5_workers, mode=PR)
+case("C5/safe-allowed", "examples/demo-guardrails/overlays/policy.fragment.yaml:25-29", c5_job("safe"),
+     {"decision": "ALLOW", "rule_id": "demo-guardrails-allow-safe", "route": "ok"},
+     policy=_c5["policy"], routing=_c5["routing"], workers=_c5_workers, mode=PR)
+case("C5/write-approved-replay", "tools/scripts/demo_guardrails.sh:27-93 + engine.go:484-522",
+     c5_job("write", approved=True),
+     {"decision": "ALLOW", "sched_decision": "ALLOW", "route": "ok", "subject": "worker.demo-worker.jobs"},
+     policy=_c5["policy"], routing=_c5["routing"], workers=_c5_workers, mode=PR)
+
+
+def check(case_, got: dict):
+    for key, want in case_["expect"].items():
+        have = got[key]
+        if callable(want):
+            assert want(have), "%s [%s]: %s=%r fails predicate" % (case_["name"], case_["ref"], key, have)
+        else:
+            assert have == want, "%s [%s]: %s=%r, reference expects %r" % (case_["name"], case_["ref"], key, have, want)
