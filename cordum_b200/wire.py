@@ -238,6 +238,40 @@ class EnvelopeBatch:
         )
         return EnvelopeBatch(n, ar.array(), cols)
 
+    def _s(self, span) -> str:
+        o, n = int(span["off"]), int(span["len"])
+        return bytes(self.arena[o:o + n]).decode("utf-8", "surrogateescape")
+
+    def to_jobs(self, first: int = 0, count: int | None = None) -> list[dict]:
+        """Decode back to Python-level jobs (for the dict-level oracle and debugging)."""
+        c = self.cols
+        count = self.n_jobs - first if count is None else count
+        out = []
+        for j in range(first, first + count):
+            job = {"topic": self._s(c["topic"][j]), "tenant": self._s(c["tenant"][j]),
+                   "principal_id": self._s(c["principal_id"][j]), "labels": {}, "meta": None,
+                   "approved": bool(c["approved"][j])}
+            ec = c["effective_config"][j]
+            if ec["len"]:
+                job["effective_config"] = bytes(self.arena[int(ec["off"]): int(ec["off"]) + int(ec["len"])])
+            if c["has_meta"][j]:
+                job["meta"] = {
+                    "tenant_id": self._s(c["meta_tenant_id"][j]), "actor_id": self._s(c["actor_id"][j]),
+                    "actor_type": int(c["actor_type"][j]), "capability": self._s(c["capability"][j]),
+                    "pack_id": self._s(c["pack_id"][j]),
+                    "risk_tags": [self._s(c["risk_tags"][k]) for k in range(c["risk_off"][j], c["risk_off"][j + 1])],
+                    "requires": [self._s(c["requires_"][k]) for k in range(c["requires_off"][j], c["requires_off"][j + 1])],
+                }
+            for k in range(c["label_off"][j], c["label_off"][j + 1]):
+                job["labels"][self._s(c["label_keys"][k])] = self._s(c["label_vals"][k])
+            out.append(job)
+        return out
+
+    def with_approved(self, mask) -> "EnvelopeBatch":
+        cols = dict(self.cols)
+        cols["approved"] = np.ascontiguousarray(mask, dtype=np.uint8)
+        return EnvelopeBatch(self.n_jobs, self.arena, cols)
+
     def slice(self, first: int, count: int) -> "EnvelopeBatch":
         """A view-free copy of jobs [first, first+count) (CSR columns re-based)."""
         cols = {}
@@ -283,6 +317,22 @@ class WorkerTable:
     def worker_id(self, slot: int) -> str:
         s = self.cols["worker_id"][slot]
         return bytes(self.arena[int(s["off"]): int(s["off"]) + int(s["len"])]).decode("utf-8", "replace")
+
+    def to_workers(self) -> list[dict]:
+        c = self.cols
+
+        def st(span):
+            o, n = int(span["off"]), int(span["len"])
+            return bytes(self.arena[o:o + n]).decode("utf-8", "surrogateescape")
+
+        out = []
+        for i in range(self.n_workers):
+            out.append({"worker_id": st(c["worker_id"][i]), "pool": st(c["pool"][i]),
+                        "active_jobs": int(c["active_jobs"][i]), "max_parallel_jobs": int(c["max_parallel_jobs"][i]),
+                        "cpu_load": float(c["cpu_load"][i]), "gpu_utilization": float(c["gpu_utilization"][i]),
+                        "labels": {st(c["label_keys"][k]): st(c["label_vals"][k])
+                                   for k in range(c["label_off"][i], c["label_off"][i + 1])}})
+        return out
 
     @staticmethod
     def from_workers(workers: Iterable[dict]) -> "WorkerTable":
