@@ -1,0 +1,101 @@
+"""ctypes binding of libcordum_b200.so (include/cordum_b200.h).
+
+The shared library is built in-tree by `__graft_entry__.build()` (cordum_b200/csrc/Makefile).
+If it is missing this module raises — there is no Python or CPU fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import wire
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcordum_b200.so")
+
+# every symbol include/cordum_b200.h declares (the CPU test-suite checks they are all exported)
+API = [
+    "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
+    "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
+    "cordum_workers_set_loads_device", "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
+    "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_batch_fetch", "cordum_batch_stream",
+    "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_rule_id", "cordum_reason",
+    "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
+    "cordum_launch_count", "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
+    "cordum_test_parse_effective",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "cordum_b200: %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, i64, cp = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_char_p
+    L.cordum_last_error.restype = cp
+    L.cordum_version.restype = cp
+    L.cordum_engine_create.argtypes = [C.POINTER(wire.CordumEngineOpts), C.POINTER(vp)]
+    L.cordum_engine_destroy.argtypes = [vp]
+    L.cordum_engine_destroy.restype = None
+    L.cordum_policy_load.argtypes = [vp, cp, u64, cp, u64]
+    L.cordum_policy_snapshots.argtypes = [vp, cp, u64, C.POINTER(u32)]
+    L.cordum_routing_load.argtypes = [vp, cp, u64]
+    L.cordum_workers_load.argtypes = [vp, vp]
+    L.cordum_workers_update.argtypes = [vp, u32, vp, vp]
+    L.cordum_workers_set_loads_device.argtypes = [vp, vp, u32, vp]
+    L.cordum_batch_alloc.argtypes = [vp, u32, C.POINTER(vp)]
+    L.cordum_batch_free.argtypes = [vp]
+    L.cordum_batch_free.restype = None
+    L.cordum_encode.argtypes = [vp, vp, vp]
+    for f in ("cordum_dispatch", "cordum_dispatch_async", "cordum_dispatch_resident"):
+        getattr(L, f).argtypes = [vp, vp, u32]
+    L.cordum_batch_wait.argtypes = [vp]
+    L.cordum_batch_fetch.argtypes = [vp]
+    L.cordum_batch_stream.argtypes = [vp]
+    L.cordum_batch_stream.restype = vp
+    L.cordum_batch_size.argtypes = [vp]
+    L.cordum_batch_size.restype = u32
+    L.cordum_batch_results.argtypes = [vp]
+    L.cordum_batch_results.restype = vp
+    L.cordum_batch_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cordum_rule_id.argtypes = [vp, i32, cp, u64]
+    L.cordum_rule_id.restype = i64
+    L.cordum_rule_constraints_json.argtypes = [vp, i32, cp, u64]
+    L.cordum_rule_constraints_json.restype = i64
+    L.cordum_rule_remediations_json.argtypes = [vp, i32, cp, u64]
+    L.cordum_rule_remediations_json.restype = i64
+    L.cordum_reason.argtypes = [vp, vp, u32, cp, u64]
+    L.cordum_reason.restype = i64
+    L.cordum_subject.argtypes = [vp, vp, u32, cp, u64]
+    L.cordum_subject.restype = i64
+    L.cordum_stats.argtypes = [vp, C.POINTER(wire.CordumTableStats)]
+    L.cordum_launch_count.argtypes = [vp]
+    L.cordum_launch_count.restype = u64
+    L.cordum_test_glob.argtypes = [cp, u64, cp, u64]
+    L.cordum_test_trim.argtypes = [cp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.cordum_test_normalize_decision.argtypes = [cp, u64]
+    L.cordum_test_parse_effective.argtypes = [cp, u64, C.POINTER(u32), C.POINTER(u32)]
+    # host-only hooks (CPU tests of the table compiler / encoder)
+    L.cordum_test_last_error.restype = cp
+    L.cordum_test_host_new.argtypes = [u32, u32, u32]
+    L.cordum_test_host_new.restype = vp
+    L.cordum_test_host_free.argtypes = [vp]
+    L.cordum_test_host_free.restype = None
+    L.cordum_test_host_policy.argtypes = [vp, cp, u64]
+    L.cordum_test_host_routing.argtypes = [vp, cp, u64]
+    L.cordum_test_host_workers.argtypes = [vp, vp]
+    L.cordum_test_host_update.argtypes = [vp, u32, vp, vp]
+    L.cordum_test_slab_bytes.argtypes = [u32]
+    L.cordum_test_slab_bytes.restype = u64
+    L.cordum_test_host_encode.argtypes = [vp, vp, vp]
+    L.cordum_test_host_table.argtypes = [vp, cp, C.POINTER(vp), C.POINTER(u64)]
+    L.cordum_test_host_scalar.argtypes = [vp, cp]
+    L.cordum_test_host_scalar.restype = u64
+    _lib = L
+    return L

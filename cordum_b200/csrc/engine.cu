@@ -1,0 +1,594 @@
+// engine.cu — device memory, streams, dispatch and the extern "C" boundary
+// (include/cordum_b200.h).  The product has NO CPU evaluation path: every decision
+// record is produced by kernels.cu; without a CUDA device engine creation fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cordum_b200.h"
+#include "host.hpp"
+#include "kernels.h"
+
+using cordum::Host;
+using cordum::HostColumns;
+using cordum::HostTables;
+using cordum::sv;
+
+namespace {
+thread_local std::string g_err;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t upload(const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      size_t want = bytes + bytes / 4 + 256;
+      cudaError_t e = cudaMalloc(&p, want);
+      if (e != cudaSuccess) { cap = 0; return e; }
+      cap = want;
+    }
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s);
+  }
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    cap = e == cudaSuccess ? bytes : 0;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// column slab layout for n jobs: 14 u32 columns, then 5 u64 columns (each 16 B aligned)
+constexpr int kU32Cols = 14, kU64Cols = 5;
+inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+inline size_t slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) + kU64Cols * align16((size_t)n * 8); }
+
+}  // namespace
+
+struct cordum_engine {
+  int device = 0;
+  int sm_count = 148;
+  std::unique_ptr<Host> host;
+  std::mutex mu;                 // serialises table sync
+  bool failed = false;           // sticky CUDA failure
+  std::string fail_msg;
+  cudaStream_t s_tables = nullptr;
+  cudaEvent_t ev_tables = nullptr;
+  DeviceTables dt{};             // device pointers + scalars, as passed to kernels
+  // device copies, one DevBuf per host vector
+  DevBuf b_row_tenant, b_row_topic, b_row_cap, b_row_pack, b_row_actor, b_row_combo, b_row_risk, b_row_check, b_row_mcp[4];
+  DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic;
+  DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
+  DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
+  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush;
+  uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
+  bool pools_dirty = true;       // K2 must run before the next dispatch
+  bool loads_on_device = false;  // last load table came from cordum_workers_set_loads_device
+  std::atomic<uint64_t> launches{0};
+};
+
+struct cordum_batch {
+  cordum_engine* e = nullptr;
+  uint32_t max_jobs = 0, n = 0;
+  uint64_t epoch = 0;
+  bool encoded = false, resident = false, pending = false;
+  uint8_t* h_cols = nullptr;     // pinned
+  uint8_t* d_cols = nullptr;
+  cordum_decision* h_out = nullptr;   // pinned
+  cordum_decision* d_out = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  float total_ms = 0, kernel_ms = 0;
+  HostColumns hc{};
+};
+
+namespace {
+
+int fail(cordum_engine* e, cudaError_t err, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(err);
+  if (e) { e->failed = true; e->fail_msg = g_err; }
+  return CORDUM_E_CUDA;
+}
+#define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(e, _e, what); } while (0)
+
+// carve the column pointers out of a slab for n jobs
+template <class P32, class P64>
+void carve(uint8_t* base, uint32_t n, P32** u32cols, P64** u64cols) {
+  size_t off = 0;
+  for (int i = 0; i < kU32Cols; ++i) { u32cols[i] = (P32*)(base + off); off += align16((size_t)n * 4); }
+  for (int i = 0; i < kU64Cols; ++i) { u64cols[i] = (P64*)(base + off); off += align16((size_t)n * 8); }
+}
+void host_columns(uint8_t* base, uint32_t n, HostColumns& c) {
+  uint32_t* a[kU32Cols]; uint64_t* b[kU64Cols];
+  carve(base, n, a, b);
+  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
+  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
+  c.effcfg = a[12]; c.flags = a[13];
+  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
+}
+void device_columns(uint8_t* base, uint32_t n, JobColumns& c) {
+  const uint32_t* a[kU32Cols]; const uint64_t* b[kU64Cols];
+  carve(base, n, a, b);
+  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
+  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
+  c.effcfg = a[12]; c.flags = a[13];
+  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
+}
+
+template <class T>
+cudaError_t up(DevBuf& b, const std::vector<T>& v, cudaStream_t s) { return b.upload(v.data(), v.size() * sizeof(T), s); }
+
+// Bring the device tables up to date with the host tables.  Called with host mutex held.
+int sync_tables(cordum_engine* e) {
+  const HostTables& t = e->host->tables();
+  DeviceTables& d = e->dt;
+  bool any = t.v_policy != e->v_policy || t.v_topic != e->v_topic || t.v_mcp != e->v_mcp || t.v_routing != e->v_routing ||
+             t.v_workers != e->v_workers || (t.v_loads != e->v_loads);
+  if (!any) return CORDUM_OK;
+  // Tables may be reallocated: nothing may be in flight.  Table changes are rare (policy/routing
+  // reload, first sight of a topic) so a full device sync here is acceptable.
+  CK(cudaDeviceSynchronize(), "sync before table upload");
+  cudaStream_t s = e->s_tables;
+  if (t.v_policy != e->v_policy) {
+    CK(up(e->b_row_tenant, t.row_tenant.data, s), "upload"); CK(up(e->b_row_cap, t.row_cap.data, s), "upload");
+    CK(up(e->b_row_pack, t.row_pack.data, s), "upload"); CK(up(e->b_row_actor, t.row_actor.data, s), "upload");
+    CK(up(e->b_row_combo, t.row_combo.data, s), "upload"); CK(up(e->b_row_risk, t.row_risk.data, s), "upload");
+    CK(up(e->b_row_check, t.row_check.data, s), "upload");
+    CK(up(e->b_req_need, t.rule_req_need, s), "upload"); CK(up(e->b_lab_need, t.rule_lab_need, s), "upload");
+    CK(up(e->b_rule_dec, t.rule_dec, s), "upload");
+    d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4;
+    d.row_tenant = (const Row16*)e->b_row_tenant.p; d.n_tenant = t.row_tenant.n_rows;
+    d.row_cap = (const Row16*)e->b_row_cap.p; d.n_cap = t.row_cap.n_rows;
+    d.row_pack = (const Row16*)e->b_row_pack.p; d.n_pack = t.row_pack.n_rows;
+    d.row_actor = (const Row16*)e->b_row_actor.p; d.n_actor = t.row_actor.n_rows;
+    d.row_combo = (const Row16*)e->b_row_combo.p; d.row_risk = (const Row16*)e->b_row_risk.p;
+    d.row_check = (const Row16*)e->b_row_check.p;
+    d.rule_req_need = (const uint64_t*)e->b_req_need.p; d.rule_lab_need = (const uint64_t*)e->b_lab_need.p;
+    d.rule_dec = (const uint8_t*)e->b_rule_dec.p;
+    e->v_policy = t.v_policy;
+  }
+  if (t.v_topic != e->v_topic) {
+    CK(up(e->b_row_topic, t.row_topic.data, s), "upload"); CK(up(e->b_eff_topic, t.eff_topic, s), "upload");
+    CK(up(e->b_topic_pool_off, t.topic_pool_off, s), "upload"); CK(up(e->b_topic_pool_cnt, t.topic_pool_cnt, s), "upload");
+    CK(up(e->b_pool_list, t.pool_list, s), "upload");
+    d.row_topic = (const Row16*)e->b_row_topic.p; d.n_topic = t.row_topic.n_rows;
+    d.eff_topic = (const uint8_t*)e->b_eff_topic.p; d.topic_stride = t.topic_stride;
+    d.topic_pool_off = (const uint32_t*)e->b_topic_pool_off.p; d.topic_pool_cnt = (const uint32_t*)e->b_topic_pool_cnt.p;
+    d.pool_list = (const uint32_t*)e->b_pool_list.p;
+    e->v_topic = t.v_topic;
+  }
+  if (t.v_mcp != e->v_mcp) {
+    for (int f = 0; f < 4; ++f) {
+      CK(up(e->b_row_mcp[f], t.row_mcp[f].data, s), "upload");
+      d.row_mcp[f] = (const Row16*)e->b_row_mcp[f].p; d.n_mcp[f] = t.row_mcp[f].n_rows;
+    }
+    CK(up(e->b_tenant_mcp, t.tenant_mcp, s), "upload"); CK(up(e->b_eff_mcp, t.eff_mcp, s), "upload");
+    d.tenant_mcp = (const uint8_t*)e->b_tenant_mcp.p; d.eff_mcp = (const uint8_t*)e->b_eff_mcp.p; d.mcp_stride = t.mcp_stride;
+    e->v_mcp = t.v_mcp;
+  }
+  if (t.v_routing != e->v_routing) {
+    CK(up(e->b_pool_req_mask, t.pool_req_mask, s), "upload"); CK(up(e->b_pool_req_nonempty, t.pool_req_nonempty, s), "upload");
+    d.pool_req_mask = (const uint64_t*)e->b_pool_req_mask.p; d.pool_req_nonempty = (const uint8_t*)e->b_pool_req_nonempty.p;
+    d.req_blank_mask = t.req_blank_mask; d.n_pools = t.n_pools;
+    e->v_routing = t.v_routing;
+  }
+  if (t.v_workers != e->v_workers) {
+    CK(up(e->b_pool_off, t.pool_off, s), "upload"); CK(up(e->b_pos_pool, t.pos_pool, s), "upload");
+    CK(up(e->b_pos_slot, t.pos_slot, s), "upload"); CK(up(e->b_pos_rank, t.pos_rank, s), "upload");
+    CK(up(e->b_slot_pos, t.slot_pos, s), "upload"); CK(up(e->b_rank_slot, t.rank_slot, s), "upload");
+    CK(up(e->b_pos_label_lo, t.pos_label_lo, s), "upload"); CK(up(e->b_pos_label_hi, t.pos_label_hi, s), "upload");
+    CK(e->b_pos_key.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+    CK(e->b_pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
+    CK(e->b_pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+    d.n_pos = t.n_pos; d.n_pools = t.n_pools;
+    d.pool_off = (const uint32_t*)e->b_pool_off.p; d.pos_pool = (const uint32_t*)e->b_pos_pool.p;
+    d.pos_slot = (const uint32_t*)e->b_pos_slot.p; d.pos_rank = (const uint32_t*)e->b_pos_rank.p;
+    d.slot_pos = (const uint32_t*)e->b_slot_pos.p; d.rank_slot = (const uint32_t*)e->b_rank_slot.p;
+    d.pos_label_lo = (const uint64_t*)e->b_pos_label_lo.p; d.pos_label_hi = (const uint64_t*)e->b_pos_label_hi.p;
+    d.pos_key = (uint64_t*)e->b_pos_key.p; d.pool_best = (uint64_t*)e->b_pool_best.p; d.pool_mincnt = (uint32_t*)e->b_pool_mincnt.p;
+    e->v_workers = t.v_workers;
+    e->pools_dirty = true;
+    e->loads_on_device = false;
+  }
+  if (t.v_loads != e->v_loads) {
+    if (!e->loads_on_device) {
+      CK(up(e->b_loads, t.loads, s), "upload");
+      d.loads = (const Load16*)e->b_loads.p;
+    }
+    e->v_loads = t.v_loads;
+    e->pools_dirty = true;
+  }
+  CK(cudaStreamSynchronize(s), "table upload");
+  return CORDUM_OK;
+}
+
+// K2 when the worker loads changed; batches wait on ev_tables.
+int refresh_pools(cordum_engine* e) {
+  if (!e->pools_dirty) return CORDUM_OK;
+  CK(launch_worker_pools(e->dt, e->s_tables), "worker_pool_kernel");
+  if (e->dt.n_pools) e->launches++;
+  CK(cudaEventRecord(e->ev_tables, e->s_tables), "event record");
+  e->pools_dirty = false;
+  return CORDUM_OK;
+}
+
+int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool copy_out, bool flush_l2) {
+  if (!e || !b) { g_err = "null handle"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  if (mode < CORDUM_MODE_POLICY_ONLY || mode > CORDUM_MODE_ROUTE_ONLY) { g_err = "bad mode"; return CORDUM_E_INVALID; }
+  if (!b->encoded) { g_err = "batch has not been encoded"; return CORDUM_E_STATE; }
+  if (!copy_in && !b->resident) { g_err = "batch columns are not resident on the device"; return CORDUM_E_STATE; }
+  if (b->pending) { CK(cudaStreamSynchronize(b->stream), "wait previous"); b->pending = false; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> gh(e->host->mutex());
+    if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
+    int rc = sync_tables(e);
+    if (rc) return rc;
+    rc = refresh_pools(e);
+    if (rc) return rc;
+  }
+  cudaStream_t s = b->stream;
+  CK(cudaStreamWaitEvent(s, e->ev_tables, 0), "wait tables");
+  if (flush_l2) {   // evict the job columns from L2 between timed iterations (outside the timed region)
+    if (!e->b_flush.p) CK(e->b_flush.reserve(size_t(256) << 20), "alloc flush buffer");
+    CK(cudaMemsetAsync(e->b_flush.p, 0, e->b_flush.cap, s), "flush");
+  }
+  CK(cudaEventRecord(b->ev0, s), "event");
+  if (copy_in) {
+    CK(cudaMemcpyAsync(b->d_cols, b->h_cols, slab_bytes(b->n), cudaMemcpyHostToDevice, s), "H2D columns");
+    b->resident = true;
+  }
+  CK(cudaEventRecord(b->ev1, s), "event");
+  KParams P;
+  device_columns(b->d_cols, b->n, P.cols);
+  P.t = e->dt;
+  P.out = b->d_out;
+  P.n_jobs = b->n;
+  CK(launch_dispatch(P, mode, e->sm_count, s), "dispatch_kernel");
+  if (b->n) e->launches++;
+  CK(cudaEventRecord(b->ev2, s), "event");
+  if (copy_out) CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, s), "D2H results");
+  CK(cudaEventRecord(b->ev3, s), "event");
+  b->pending = true;
+  return CORDUM_OK;
+}
+
+int wait(cordum_batch* b) {
+  cordum_engine* e = b->e;
+  if (!b->pending) return CORDUM_OK;
+  CK(cudaStreamSynchronize(b->stream), "batch wait");
+  b->pending = false;
+  CK(cudaEventElapsedTime(&b->total_ms, b->ev0, b->ev3), "elapsed");
+  CK(cudaEventElapsedTime(&b->kernel_ms, b->ev1, b->ev2), "elapsed");
+  return CORDUM_OK;
+}
+
+int64_t copy_out(const std::string& s, char* buf, uint64_t cap) {
+  if (buf && cap) {
+    size_t n = std::min<size_t>(s.size(), cap - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
+}
+
+std::string go_quote(sv s) {
+  std::string o = "\"";
+  for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
+  o.push_back('"');
+  return o;
+}
+
+}  // namespace
+
+// ============================================================ C ABI
+extern "C" {
+
+const char* cordum_last_error(void) { return g_err.c_str(); }
+const char* cordum_version(void) { return "cordum-b200 0.1 (sm_100a)"; }
+
+int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out) {
+  if (!out) { g_err = "null out"; return CORDUM_E_INVALID; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0) {
+    g_err = std::string("no CUDA device (") + (ce == cudaSuccess ? "count 0" : cudaGetErrorString(ce)) +
+            "): cordum-b200 has no CPU evaluation path";
+    return CORDUM_E_NODEVICE;
+  }
+  auto e = std::make_unique<cordum_engine>();
+  e->device = opts ? opts->device : 0;
+  if (e->device < 0 || e->device >= count) { g_err = "bad device ordinal"; return CORDUM_E_INVALID; }
+  cordum_engine* ep = e.get();
+  {
+    cordum_engine* e = ep;
+    CK(cudaSetDevice(e->device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, e->device), "device properties");
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->s_tables, cudaStreamNonBlocking), "stream");
+    CK(cudaEventCreateWithFlags(&e->ev_tables, cudaEventDisableTiming), "event");
+    CK(cudaEventRecord(e->ev_tables, e->s_tables), "event");
+  }
+  e->host = std::make_unique<Host>(opts ? opts->max_topics : 0, opts ? opts->max_effcfgs : 0, opts ? opts->encode_threads : 0);
+  *out = e.release();
+  return CORDUM_OK;
+}
+
+void cordum_engine_destroy(cordum_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  DevBuf* all[] = {&e->b_row_tenant, &e->b_row_topic, &e->b_row_cap, &e->b_row_pack, &e->b_row_actor, &e->b_row_combo,
+                   &e->b_row_risk, &e->b_row_check, &e->b_row_mcp[0], &e->b_row_mcp[1], &e->b_row_mcp[2], &e->b_row_mcp[3],
+                   &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic,
+                   &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
+                   &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
+                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_loads, &e->b_pos_key, &e->b_pool_best, &e->b_pool_mincnt,
+                   &e->b_flush};
+  for (DevBuf* b : all) b->release();
+  if (e->ev_tables) cudaEventDestroy(e->ev_tables);
+  if (e->s_tables) cudaStreamDestroy(e->s_tables);
+  delete e;
+}
+
+int32_t cordum_policy_load(cordum_engine* e, const char* json, uint64_t len, const char* snapshot, uint64_t slen) {
+  if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
+  return e->host->load_policy(sv(json ? json : "", json ? len : 0), sv(snapshot ? snapshot : "", snapshot ? slen : 0), g_err);
+}
+
+int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint32_t* n_out) {
+  if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  uint64_t off = 0;
+  uint32_t n = 0;
+  for (auto& s : e->host->snapshots()) {
+    if (off + s.size() + 1 > cap) break;
+    std::memcpy(buf + off, s.data(), s.size());
+    buf[off + s.size()] = 0;
+    off += s.size() + 1;
+    ++n;
+  }
+  if (n_out) *n_out = n;
+  return CORDUM_OK;
+}
+
+int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
+  if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
+  return e->host->load_routing(sv(json ? json : "", json ? len : 0), g_err);
+}
+
+int32_t cordum_workers_load(cordum_engine* e, const cordum_workers* w) {
+  if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
+  return e->host->load_workers(w, g_err);
+}
+
+int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slots, const cordum_worker_load* loads) {
+  if (!e || (n && (!slots || !loads))) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  int rc = e->host->update_loads(n, slots, loads, g_err);
+  if (rc == CORDUM_OK) { std::lock_guard<std::mutex> g(e->mu); e->loads_on_device = false; }
+  return rc;
+}
+
+int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint32_t n_workers, void* stream) {
+  if (!e || !dptr) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<std::mutex> gh(e->host->mutex());
+  if (n_workers != e->host->tables().n_slots) { g_err = "load table size does not match the worker registry"; return CORDUM_E_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  int rc = sync_tables(e);
+  if (rc) return rc;
+  // order after the producer (e.g. the NCCL all-gather stream), then copy on the tables stream
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+  CK(cudaEventRecord(ev, (cudaStream_t)stream), "event record");
+  CK(cudaStreamWaitEvent(e->s_tables, ev, 0), "wait producer");
+  cudaEventDestroy(ev);
+  CK(e->b_loads.reserve((size_t)std::max<uint32_t>(n_workers, 1) * sizeof(Load16)), "alloc loads");
+  CK(cudaMemcpyAsync(e->b_loads.p, dptr, (size_t)n_workers * sizeof(Load16), cudaMemcpyDeviceToDevice, e->s_tables), "D2D loads");
+  e->dt.loads = (const Load16*)e->b_loads.p;
+  e->loads_on_device = true;
+  e->pools_dirty = true;
+  return refresh_pools(e);
+}
+
+int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out) {
+  if (!e || !out || max_jobs == 0) { g_err = "bad argument"; return CORDUM_E_INVALID; }
+  *out = nullptr;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  auto b = std::make_unique<cordum_batch>();
+  b->e = e;
+  b->max_jobs = max_jobs;
+  size_t bytes = slab_bytes(max_jobs);
+  CK(cudaHostAlloc((void**)&b->h_cols, bytes, cudaHostAllocDefault), "pinned columns");
+  CK(cudaMalloc((void**)&b->d_cols, bytes), "device columns");
+  CK(cudaHostAlloc((void**)&b->h_out, (size_t)max_jobs * sizeof(cordum_decision), cudaHostAllocDefault), "pinned results");
+  CK(cudaMalloc((void**)&b->d_out, (size_t)max_jobs * sizeof(cordum_decision)), "device results");
+  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
+  CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event");
+  CK(cudaEventCreate(&b->ev2), "event"); CK(cudaEventCreate(&b->ev3), "event");
+  *out = b.release();
+  return CORDUM_OK;
+}
+
+void cordum_batch_free(cordum_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->e->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->h_cols) cudaFreeHost(b->h_cols);
+  if (b->d_cols) cudaFree(b->d_cols);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  if (b->d_out) cudaFree(b->d_out);
+  for (cudaEvent_t ev : {b->ev0, b->ev1, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
+  if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
+  if (b->pending) { int rc = wait(b); if (rc) return rc; }
+  b->n = env->n_jobs;
+  b->encoded = false;
+  b->resident = false;
+  host_columns(b->h_cols, b->n, b->hc);
+  uint64_t epoch_before = e->host->epoch();
+  int rc = e->host->encode(env, b->hc, g_err);
+  if (rc) return rc;
+  b->epoch = epoch_before;
+  b->encoded = true;
+  return CORDUM_OK;
+}
+
+int32_t cordum_dispatch_async(cordum_engine* e, cordum_batch* b, uint32_t mode) { return run(e, b, mode, true, true, false); }
+int32_t cordum_batch_wait(cordum_batch* b) {
+  if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
+  return wait(b);
+}
+int32_t cordum_dispatch(cordum_engine* e, cordum_batch* b, uint32_t mode) {
+  int rc = run(e, b, mode, true, true, false);
+  return rc ? rc : wait(b);
+}
+int32_t cordum_dispatch_resident(cordum_engine* e, cordum_batch* b, uint32_t mode) {
+  int rc = run(e, b, mode, false, false, true);
+  return rc ? rc : wait(b);
+}
+
+uint32_t cordum_batch_size(const cordum_batch* b) { return b ? b->n : 0; }
+const cordum_decision* cordum_batch_results(const cordum_batch* b) { return b ? b->h_out : nullptr; }
+int32_t cordum_batch_timing(const cordum_batch* b, float* total_ms, float* kernel_ms) {
+  if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
+  if (total_ms) *total_ms = b->total_ms;
+  if (kernel_ms) *kernel_ms = b->kernel_ms;
+  return CORDUM_OK;
+}
+/* copies the decision records still on the device into the pinned result buffer (after a resident run) */
+int32_t cordum_batch_fetch(cordum_batch* b) {
+  if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
+  cordum_engine* e = b->e;
+  CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, b->stream), "D2H results");
+  CK(cudaStreamSynchronize(b->stream), "fetch");
+  return CORDUM_OK;
+}
+/* raw CUDA stream of a batch (cudaStream_t) so a harness can bracket launches with its own events */
+void* cordum_batch_stream(cordum_batch* b) { return b ? (void*)b->stream : nullptr; }
+
+int64_t cordum_rule_id(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const auto& rules = e->host->policy().rules;
+  if (rule_idx < 0 || (size_t)rule_idx >= rules.size()) return copy_out(std::string(), buf, cap);
+  return copy_out(rules[rule_idx].id, buf, cap);
+}
+int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const auto& rules = e->host->policy().rules;
+  if (rule_idx < 0 || (size_t)rule_idx >= rules.size() || !rules[rule_idx].has_constraints) return copy_out(std::string(), buf, cap);
+  return copy_out(rules[rule_idx].constraints_json, buf, cap);
+}
+int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const auto& rules = e->host->policy().rules;
+  if (rule_idx < 0 || (size_t)rule_idx >= rules.size()) return copy_out(std::string(), buf, cap);
+  return copy_out(rules[rule_idx].remediations_json, buf, cap);
+}
+
+int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
+  if (!e || !b || job >= b->n) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const cordum_decision& r = b->h_out[job];
+  const uint32_t code = r.reason_code;
+  std::string s;
+  static const char* fields[4] = {"server", "tool", "resource", "action"};
+  if (code == CORDUM_REASON_RULE) {
+    const auto& rules = e->host->policy().rules;
+    if (r.rule_idx >= 0 && (size_t)r.rule_idx < rules.size()) s = rules[r.rule_idx].reason;
+  } else if (code == CORDUM_REASON_MISSING_TOPIC) s = "missing topic";
+  else if (code == CORDUM_REASON_UNSUPPORTED_TOPIC) s = "unsupported topic";
+  else if (code == CORDUM_REASON_APPROVAL_GRANTED) s = "approval granted";
+  else if (code == CORDUM_REASON_EFF_DENIED_TOPIC || code == CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC) {
+    std::string topic(cordum::trim_space(e->host->topic_raw(b->hc.topic[job])));
+    s = "topic '" + topic + (code == CORDUM_REASON_EFF_DENIED_TOPIC ? "' denied by effective config" : "' not allowed by effective config");
+  } else if ((code >= CORDUM_REASON_TENANT_MCP && code < CORDUM_REASON_TENANT_MCP + 8) ||
+             (code >= CORDUM_REASON_EFF_MCP && code < CORDUM_REASON_EFF_MCP + 8)) {
+    uint32_t k = code >= CORDUM_REASON_EFF_MCP ? code - CORDUM_REASON_EFF_MCP : code - CORDUM_REASON_TENANT_MCP;
+    int f = (int)(k >> 1);
+    // canonical (trimmed, ASCII-lowered) form of the value; the Go adapter substitutes the
+    // request's own spelling, which it still holds
+    std::string v = e->host->mcp_value_string(f, b->hc.mcp[f][job]);
+    s = std::string("mcp ") + fields[f] + " " + go_quote(v) + ((k & 1) ? " not allowed" : " denied");
+  }
+  return copy_out(s, buf, cap);
+}
+
+int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
+  if (!e || !b || job >= b->n) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const cordum_decision& r = b->h_out[job];
+  std::string s;
+  if ((r.route_status == CORDUM_ROUTE_OK || r.route_status == CORDUM_ROUTE_OK_PREFERRED) && r.worker_slot >= 0 &&
+      (uint32_t)r.worker_slot < e->host->n_worker_slots()) {
+    const std::string& id = e->host->worker_id((uint32_t)r.worker_slot);
+    s = id.empty() ? e->host->topic_raw(b->hc.topic[job]) : "worker." + id + ".jobs";   // bus/nats.go:94-99; :131-135
+  }
+  return copy_out(s, buf, cap);
+}
+
+int32_t cordum_stats(cordum_engine* e, cordum_table_stats* out) {
+  if (!e || !out) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  const HostTables& t = e->host->tables();
+  std::memset(out, 0, sizeof *out);
+  out->n_rules = t.n_rules; out->n_rules_padded = t.n_seg * CORDUM_SEG_RULES; out->n_segments = t.n_seg;
+  out->n_topics = t.row_topic.n_rows; out->n_tenants = t.row_tenant.n_rows; out->n_pools = t.n_pools;
+  out->n_workers = t.n_slots; out->n_workers_routable = t.n_pos;
+  size_t rows = t.row_tenant.data.size() + t.row_topic.data.size() + t.row_cap.data.size() + t.row_pack.data.size() +
+                t.row_actor.data.size() + t.row_combo.data.size() + t.row_risk.data.size() + t.row_check.data.size();
+  for (int f = 0; f < 4; ++f) rows += t.row_mcp[f].data.size();
+  out->passrow_bytes = rows * 4;
+  out->rulecol_bytes = (uint64_t)t.n_rules * (8 + 8 + 1) + t.tenant_mcp.size() + t.eff_mcp.size() + t.eff_topic.size();
+  out->routing_bytes = (t.topic_pool_off.size() + t.topic_pool_cnt.size() + t.pool_list.size()) * 4 + (uint64_t)t.n_pools * 9;
+  out->worker_bytes = (uint64_t)t.n_pos * (4 * 3 + 16 + 8) + (uint64_t)t.n_slots * (16 + 8) + (uint64_t)t.n_pools * 16;
+  out->job_in_bytes = CORDUM_JOB_IN_BYTES;
+  out->job_out_bytes = CORDUM_JOB_OUT_BYTES;
+  return CORDUM_OK;
+}
+
+uint64_t cordum_launch_count(cordum_engine* e) { return e ? e->launches.load() : 0; }
+
+/* ---- test hooks: the product's own string primitives, for differential tests against the oracle */
+int32_t cordum_test_glob(const char* pat, uint64_t plen, const char* name, uint64_t nlen) {
+  return cordum::test_glob(sv(pat, plen), sv(name, nlen));
+}
+void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len) {
+  sv t = cordum::trim_space(sv(s, n));
+  *off = t.empty() ? 0 : (uint64_t)(t.data() - s);
+  *len = t.size();
+}
+int32_t cordum_test_normalize_decision(const char* s, uint64_t n) { return cordum::normalize_decision_code(sv(s, n)); }
+int32_t cordum_test_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied) {
+  cordum::EffSafety cfg;
+  bool ok = cordum::parse_effective_safety(sv(s, n), cfg);
+  if (n_allowed) *n_allowed = (uint32_t)cfg.allowed_topics.size();
+  if (n_denied) *n_denied = (uint32_t)cfg.denied_topics.size();
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1166 @@
+// host.cpp — models, table compiler and job encoder (see host.hpp).
+#include "host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <set>
+#include <thread>
+
+#include "../../common/mini_json.hpp"
+
+namespace cordum {
+
+// ============================================================ small helpers
+namespace {
+
+constexpr uint32_t kMiss = 0xFFFFFFFFu;
+
+// fold_key without heap allocation for ordinary-sized values
+struct FoldBuf {
+  char small[160];
+  std::string big;
+  sv view;
+  explicit FoldBuf(sv raw) {
+    sv t = trim_space(raw);
+    if (t.size() <= sizeof small) {
+      for (size_t i = 0; i < t.size(); ++i) small[i] = lower_ascii(t[i]);
+      view = sv(small, t.size());
+    } else {
+      big = lower_copy(t);
+      view = big;
+    }
+  }
+};
+
+bool fold_eq(sv a, sv b) {   // strings.EqualFold, ASCII
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); ++i)
+    if (lower_ascii(a[i]) != lower_ascii(b[i])) return false;
+  return true;
+}
+
+// dictionary lookup of a job value under containsString semantics (safety_policy.go:296-306)
+inline uint32_t lookup_value(const Dict& d, sv raw) {
+  if (raw.empty()) return CORDUM_ID_EMPTY;
+  FoldBuf f(raw);
+  return d.table.find(f.view, CORDUM_ID_OTHER);
+}
+
+inline void set_bit(Bits& b, uint32_t r) { b[r >> 5] |= 1u << (r & 31); }
+inline void or_bits(uint32_t* dst, const Bits& src) { for (size_t i = 0; i < src.size(); ++i) dst[i] |= src[i]; }
+
+std::string json_quote(sv s) {
+  std::string o = "\"";
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back((char)c); }
+    else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o.push_back((char)c);
+  }
+  o.push_back('"');
+  return o;
+}
+
+void json_dump(const mjson::Value& v, std::string& o) {
+  switch (v.kind) {
+    case mjson::Kind::Null: o += "null"; break;
+    case mjson::Kind::Bool: o += v.b ? "true" : "false"; break;
+    case mjson::Kind::Number:
+      if (v.is_int) o += std::to_string(v.i);
+      else { char b[40]; snprintf(b, sizeof b, "%.17g", v.d); o += b; }
+      break;
+    case mjson::Kind::String: o += json_quote(v.s); break;
+    case mjson::Kind::Array:
+      o.push_back('[');
+      for (size_t i = 0; i < v.arr.size(); ++i) { if (i) o.push_back(','); json_dump(v.arr[i], o); }
+      o.push_back(']');
+      break;
+    case mjson::Kind::Object:
+      o.push_back('{');
+      for (size_t i = 0; i < v.obj.size(); ++i) {
+        if (i) o.push_back(',');
+        o += json_quote(v.obj[i].first);
+        o.push_back(':');
+        json_dump(v.obj[i].second, o);
+      }
+      o.push_back('}');
+      break;
+  }
+}
+
+bool get_strings(const mjson::Value* v, std::vector<std::string>& out, const char* what, std::string& err) {
+  out.clear();
+  if (!v || v->is_null()) return true;
+  if (!v->is_arr()) { err = std::string(what) + " must be a list of strings"; return false; }
+  for (auto& e : v->arr) {
+    if (e.is_null()) out.emplace_back();
+    else if (e.is_str()) out.push_back(e.s);
+    else { err = std::string(what) + " must be a list of strings"; return false; }
+  }
+  return true;
+}
+
+const char* kMcpAllow[4] = {"allow_servers", "allow_tools", "allow_resources", "allow_actions"};
+const char* kMcpDeny[4] = {"deny_servers", "deny_tools", "deny_resources", "deny_actions"};
+
+bool get_mcp(const mjson::Value* v, McpLists& m, std::string& err) {
+  if (!v || v->is_null()) return true;
+  if (!v->is_obj()) { err = "mcp must be a mapping"; return false; }
+  for (int f = 0; f < 4; ++f)
+    if (!get_strings(v->get(kMcpAllow[f]), m.allow[f], kMcpAllow[f], err) ||
+        !get_strings(v->get(kMcpDeny[f]), m.deny[f], kMcpDeny[f], err))
+      return false;
+  return true;
+}
+
+int64_t num_i(const mjson::Value* v) { return (v && v->is_num()) ? (v->is_int ? v->i : (int64_t)v->d) : 0; }
+size_t arr_n(const mjson::Value* v) { return (v && v->is_arr()) ? v->arr.size() : 0; }
+bool is_true(const mjson::Value* v) { return v && v->is_bool() && v->b; }
+
+// isConstraintsEmpty, kernel.go:447-453
+bool constraints_nonempty(const mjson::Value* c) {
+  if (!c || !c->is_obj()) return false;
+  const mjson::Value* b = c->get("budgets");
+  if (b && b->is_obj() && (num_i(b->get("max_runtime_ms")) || num_i(b->get("max_retries")) ||
+                           num_i(b->get("max_artifact_bytes")) || num_i(b->get("max_concurrent_jobs"))))
+    return true;
+  const mjson::Value* s = c->get("sandbox");
+  if (s && s->is_obj() && (is_true(s->get("isolated")) || arr_n(s->get("network_allowlist")) ||
+                           arr_n(s->get("fs_read_only")) || arr_n(s->get("fs_read_write"))))
+    return true;
+  const mjson::Value* t = c->get("toolchain");
+  if (t && t->is_obj() && (arr_n(t->get("allowed_tools")) || arr_n(t->get("allowed_commands")))) return true;
+  const mjson::Value* d = c->get("diff");
+  if (d && d->is_obj() && (num_i(d->get("max_files")) || num_i(d->get("max_lines")) || arr_n(d->get("deny_path_globs"))))
+    return true;
+  const mjson::Value* r = c->get("redaction_level");
+  if (r && r->is_str() && !trim_space(r->s).empty()) return true;
+  return false;
+}
+
+std::string go_quote(sv s) {   // fmt %q for the printable-ASCII strings that occur in policies
+  std::string o = "\"";
+  for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
+  o.push_back('"');
+  return o;
+}
+
+}  // namespace
+
+// ============================================================ document parsing
+uint8_t normalize_decision_code(sv raw) {   // safety_policy.go:208-223
+  std::string s = fold_key(raw);
+  if (s == "deny" || s == "block") return CORDUM_DEC_DENY;
+  if (s == "require_approval" || s == "require-approval" || s == "require_human") return CORDUM_DEC_REQUIRE_HUMAN;
+  if (s == "allow_with_constraints" || s == "allow-with-constraints") return CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+  if (s == "throttle") return CORDUM_DEC_THROTTLE;
+  return CORDUM_DEC_ALLOW;   // allow | permit | anything else
+}
+
+bool parse_policy_json(sv text, PolicyModel& out, std::string& err) {
+  out = PolicyModel{};
+  if (text.empty()) return true;   // nil policy: allow-all (kernel.go:187)
+  mjson::Value root;
+  if (!mjson::parse(text, root, &err)) { err = "policy: " + err; return false; }
+  if (root.is_null()) return true;
+  if (!root.is_obj()) { err = "policy: expected a mapping"; return false; }
+  out.nil = false;
+  if (const mjson::Value* v = root.get("default_tenant"); v && v->is_str()) out.default_tenant = v->s;
+  std::map<std::string, TenantModel> tenants;
+  if (const mjson::Value* tv = root.get("tenants"); tv && tv->is_obj()) {
+    for (auto& kv : tv->obj) {
+      TenantModel t;
+      t.name = kv.first;
+      if (kv.second.is_obj()) {
+        if (!get_strings(kv.second.get("allow_topics"), t.allow_topics, "allow_topics", err) ||
+            !get_strings(kv.second.get("deny_topics"), t.deny_topics, "deny_topics", err) ||
+            !get_mcp(kv.second.get("mcp"), t.mcp, err))
+          return false;
+      }
+      tenants[kv.first] = std::move(t);
+    }
+  }
+  for (auto& kv : tenants) out.tenants.push_back(std::move(kv.second));
+  if (const mjson::Value* rv = root.get("rules"); rv && !rv->is_null()) {
+    if (!rv->is_arr()) { err = "policy: rules must be a list"; return false; }
+    for (auto& r : rv->arr) {
+      if (!r.is_obj()) { err = "policy: rule must be a mapping"; return false; }
+      RuleModel m;
+      if (auto* v = r.get("id"); v && v->is_str()) m.id = v->s;
+      if (auto* v = r.get("decision"); v && v->is_str()) m.decision = v->s;
+      if (auto* v = r.get("reason"); v && v->is_str()) m.reason = v->s;
+      if (const mjson::Value* mv = r.get("match"); mv && mv->is_obj()) {
+        if (!get_strings(mv->get("tenants"), m.tenants, "tenants", err) ||
+            !get_strings(mv->get("topics"), m.topics, "topics", err) ||
+            !get_strings(mv->get("capabilities"), m.capabilities, "capabilities", err) ||
+            !get_strings(mv->get("risk_tags"), m.risk_tags, "risk_tags", err) ||
+            !get_strings(mv->get("requires"), m.requires_, "requires", err) ||
+            !get_strings(mv->get("pack_ids"), m.pack_ids, "pack_ids", err) ||
+            !get_strings(mv->get("actor_ids"), m.actor_ids, "actor_ids", err) ||
+            !get_strings(mv->get("actor_types"), m.actor_types, "actor_types", err) ||
+            !get_mcp(mv->get("mcp"), m.mcp, err))
+          return false;
+        if (auto* l = mv->get("labels"); l && l->is_obj()) {
+          std::map<std::string, std::string> uniq;
+          for (auto& kv : l->obj) uniq[kv.first] = kv.second.is_str() ? kv.second.s : std::string();
+          m.labels.assign(uniq.begin(), uniq.end());
+        }
+        if (auto* s = mv->get("secrets_present"); s && s->is_bool()) m.secrets_present = s->b ? 1 : 0;
+      }
+      if (const mjson::Value* c = r.get("constraints")) {
+        m.has_constraints = constraints_nonempty(c);
+        if (!c->is_null()) json_dump(*c, m.constraints_json);
+      }
+      if (const mjson::Value* rm = r.get("remediations"); rm && rm->is_arr() && !rm->arr.empty())
+        json_dump(*rm, m.remediations_json);
+      out.rules.push_back(std::move(m));
+    }
+  }
+  if (out.rules.empty()) {   // legacyRules, safety_policy.go:225-257 (tenants in sorted order)
+    for (auto& t : out.tenants) {
+      for (size_t i = 0; i < t.deny_topics.size(); ++i) {
+        RuleModel m;
+        m.id = "legacy:" + t.name + ":deny:" + std::to_string(i + 1);
+        m.decision = "deny";
+        m.reason = "topic " + go_quote(t.deny_topics[i]) + " denied by tenant policy";
+        m.tenants = {t.name};
+        m.topics = {t.deny_topics[i]};
+        m.mcp = t.mcp;
+        out.rules.push_back(std::move(m));
+      }
+      for (size_t i = 0; i < t.allow_topics.size(); ++i) {
+        RuleModel m;
+        m.id = "legacy:" + t.name + ":allow:" + std::to_string(i + 1);
+        m.decision = "allow";
+        m.tenants = {t.name};
+        m.topics = {t.allow_topics[i]};
+        m.mcp = t.mcp;
+        out.rules.push_back(std::move(m));
+      }
+    }
+  }
+  return true;
+}
+
+bool parse_routing_json(sv text, RoutingModel& out, std::string& err) {
+  out = RoutingModel{};
+  if (text.empty()) return true;
+  mjson::Value root;
+  if (!mjson::parse(text, root, &err)) { err = "routing: " + err; return false; }
+  if (root.is_null()) return true;
+  if (!root.is_obj()) { err = "routing: expected a mapping"; return false; }
+  if (const mjson::Value* t = root.get("topics"); t && t->is_obj()) {
+    std::map<std::string, std::vector<std::string>> uniq;
+    for (auto& kv : t->obj) {
+      std::vector<std::string> pools;
+      if (kv.second.is_str()) pools.push_back(kv.second.s);   // pools.go:107-111 single-pool form
+      else if (!get_strings(&kv.second, pools, "topic pools", err)) return false;
+      uniq[kv.first] = std::move(pools);
+    }
+    out.topics.assign(uniq.begin(), uniq.end());
+  }
+  if (const mjson::Value* p = root.get("pools"); p && p->is_obj()) {
+    std::map<std::string, std::vector<std::string>> uniq;
+    for (auto& kv : p->obj) {
+      std::vector<std::string> req;
+      if (kv.second.is_obj() && !get_strings(kv.second.get("requires"), req, "requires", err)) return false;
+      uniq[kv.first] = std::move(req);
+    }
+    out.pools.assign(uniq.begin(), uniq.end());
+  }
+  return true;
+}
+
+// ---- effective.go:12-39 with encoding/json typing (field names match case-insensitively;
+//      any field of the wrong JSON type makes that Unmarshal fail)
+namespace {
+bool eff_list(const mjson::Value& v, std::vector<std::string>* dst) {
+  if (v.is_null()) { if (dst) dst->clear(); return true; }
+  if (!v.is_arr()) return false;
+  bool ok = true;
+  std::vector<std::string> tmp;
+  for (auto& e : v.arr) {
+    if (e.is_str()) tmp.push_back(e.s);
+    else { tmp.emplace_back(); if (!e.is_null()) ok = false; }
+  }
+  if (dst) *dst = std::move(tmp);
+  return ok;
+}
+int name_index(sv key, const char* const* names, int n) {
+  for (int i = 0; i < n; ++i) if (key == names[i]) return i;
+  for (int i = 0; i < n; ++i) if (fold_eq(key, names[i])) return i;
+  return -1;
+}
+bool eff_mcp(const mjson::Value& v, McpLists& m) {
+  if (v.is_null()) return true;
+  if (!v.is_obj()) return false;
+  static const char* names[8] = {"allow_servers", "deny_servers", "allow_tools", "deny_tools",
+                                 "allow_resources", "deny_resources", "allow_actions", "deny_actions"};
+  bool ok = true;
+  for (auto& kv : v.obj) {
+    int f = name_index(kv.first, names, 8);
+    if (f < 0) continue;
+    std::vector<std::string>* dst = (f & 1) ? &m.deny[f >> 1] : &m.allow[f >> 1];
+    if (!eff_list(kv.second, dst)) ok = false;
+  }
+  return ok;
+}
+bool eff_struct(const mjson::Value& v, EffSafety& cfg) {
+  cfg = EffSafety{};
+  if (v.is_null()) return true;
+  if (!v.is_obj()) return false;
+  // categories.go:6-35 — kinds: b bool, s string, l []string, m map[string]float64, p MCPPolicy
+  static const char* names[16] = {"pii_detection_enabled", "pii_action", "pii_types", "allowed_email_domains",
+                                  "injection_detection", "injection_action", "injection_sensitivity",
+                                  "content_filter_enabled", "blocked_categories", "anomaly_detection",
+                                  "anomaly_thresholds", "allowed_topics", "denied_topics", "allowed_repo_hosts",
+                                  "denied_repo_hosts", "mcp"};
+  static const char kinds[17] = "bsllbssblbmllllp";
+  bool ok = true;
+  for (auto& kv : v.obj) {
+    int f = name_index(kv.first, names, 16);
+    if (f < 0) continue;
+    const mjson::Value& x = kv.second;
+    switch (kinds[f]) {
+      case 'b': if (!x.is_null() && !x.is_bool()) ok = false; break;
+      case 's': if (!x.is_null() && !x.is_str()) ok = false; break;
+      case 'l':
+        if (!eff_list(x, f == 11 ? &cfg.allowed_topics : f == 12 ? &cfg.denied_topics : nullptr)) ok = false;
+        break;
+      case 'm':
+        if (x.is_null()) break;
+        if (!x.is_obj()) { ok = false; break; }
+        for (auto& e : x.obj) if (!e.second.is_null() && !e.second.is_num()) ok = false;
+        break;
+      case 'p': if (!eff_mcp(x, cfg.mcp)) ok = false; break;
+    }
+  }
+  return ok;
+}
+}  // namespace
+
+bool parse_effective_safety(sv payload, EffSafety& out) {
+  out = EffSafety{};
+  if (payload.empty()) return false;
+  mjson::Value top;
+  if (!mjson::parse(payload, top) || !top.is_obj()) return false;
+  if (const mjson::Value* raw = top.get("safety"))
+    if (eff_struct(*raw, out)) return true;
+  if (const mjson::Value* data = top.get("data"); data && data->is_obj())
+    if (const mjson::Value* raw = data->get("safety"))
+      if (eff_struct(*raw, out)) return true;
+  out = EffSafety{};
+  return false;
+}
+
+int test_glob(sv pattern, sv name) {
+  Glob g(pattern);
+  if (!g.valid()) return -1;
+  return g.match(name) ? 1 : 0;
+}
+
+// ============================================================ Host
+Host::Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads)
+    : max_topics_(max_topics ? max_topics : 65536), max_effcfgs_(max_effcfgs ? max_effcfgs : 4096) {
+  unsigned hw = std::thread::hardware_concurrency();
+  threads_ = encode_threads ? encode_threads : (hw ? hw : 4);
+  if (threads_ > 64) threads_ = 64;
+  std::string err;
+  compile_policy();
+  compile_routing();
+  compile_mcp_tables();
+  rebuild_topics();
+  load_workers(nullptr, err);
+}
+
+// ------------------------------------------------------------ policy compile
+void Host::compile_policy() {
+  HostTables& t = t_;
+  const auto& rules = policy_.rules;
+  const uint32_t R = (uint32_t)rules.size();
+  t.n_rules = R;
+  t.n_seg = std::max<uint32_t>(1, (R + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
+  t.row_words = t.n_seg * 32;
+  const uint32_t W = t.row_words;
+  d_tenant_.clear(); d_cap_.clear(); d_pack_.clear(); d_actor_.clear(); d_risk_.clear();
+  for (auto& d : d_mcp_) d.clear();
+  d_req_.clear();
+  tenant_pol_.clear(); label_key_.clear(); label_key_pairs_.clear(); label_empty_mask_ = 0;
+  patterns_.clear();
+  default_tenant_trim_ = std::string(trim_space(policy_.default_tenant));
+  for (size_t i = 0; i < policy_.tenants.size(); ++i) tenant_pol_.put(policy_.tenants[i].name, (uint32_t)i + 1);
+
+  // requires dictionary is shared with the pools: rule tokens first, then pool tokens
+  auto scalar_rows = [&](Dict& d, RowTable& rt, auto list_of) {
+    Bits vac(W, 0);
+    std::vector<std::vector<uint32_t>> hits;   // hits[id-2] = rules
+    for (uint32_t r = 0; r < R; ++r) {
+      const std::vector<std::string>& lst = list_of(rules[r]);
+      if (lst.empty()) { set_bit(vac, r); continue; }
+      for (auto& e : lst) {
+        uint32_t id = d.intern(fold_key(e));
+        if (hits.size() < id - 1) hits.resize(id - 1);
+        hits[id - 2].push_back(r);
+      }
+    }
+    rt.init(d.size(), W);
+    for (uint32_t id = 0; id < d.size(); ++id) {
+      uint32_t* row = rt.row(id);
+      or_bits(row, vac);
+      if (id >= 2 && id - 2 < hits.size())
+        for (uint32_t r : hits[id - 2]) row[r >> 5] |= 1u << (r & 31);
+    }
+  };
+  scalar_rows(d_tenant_, t.row_tenant, [](const RuleModel& m) -> const std::vector<std::string>& { return m.tenants; });
+  scalar_rows(d_cap_, t.row_cap, [](const RuleModel& m) -> const std::vector<std::string>& { return m.capabilities; });
+  scalar_rows(d_pack_, t.row_pack, [](const RuleModel& m) -> const std::vector<std::string>& { return m.pack_ids; });
+  scalar_rows(d_actor_, t.row_actor, [](const RuleModel& m) -> const std::vector<std::string>& { return m.actor_ids; });
+
+  // risk tags: containsAny (safety_policy.go:308-318) -> OR of per-tag rows
+  {
+    Bits vac(W, 0);
+    std::vector<std::vector<uint32_t>> hits;
+    for (uint32_t r = 0; r < R; ++r) {
+      if (rules[r].risk_tags.empty()) { set_bit(vac, r); continue; }
+      for (auto& e : rules[r].risk_tags) {
+        uint32_t id = d_risk_.intern(fold_key(e));
+        if (hits.size() < id - 1) hits.resize(id - 1);
+        hits[id - 2].push_back(r);
+      }
+    }
+    uint32_t nb = d_risk_.size() - 2;
+    t.row_risk.init(1 + nb, W);
+    or_bits(t.row_risk.row(0), vac);
+    for (uint32_t b = 0; b < nb; ++b) {
+      uint32_t* row = t.row_risk.row(1 + b);
+      or_bits(row, vac);
+      if (b < hits.size()) for (uint32_t r : hits[b]) row[r >> 5] |= 1u << (r & 31);
+    }
+  }
+
+  // topics: distinct trimmed patterns
+  vac_topic_.assign(W, 0);
+  {
+    std::unordered_map<std::string, uint32_t> idx;
+    for (uint32_t r = 0; r < R; ++r) {
+      if (rules[r].topics.empty()) { set_bit(vac_topic_, r); continue; }
+      for (auto& e : rules[r].topics) {
+        sv p = trim_space(e);
+        if (p.empty()) continue;   // matchTopic: empty pattern never matches
+        auto it = idx.find(std::string(p));
+        if (it == idx.end()) {
+          it = idx.emplace(std::string(p), (uint32_t)patterns_.size()).first;
+          patterns_.push_back(Pattern{Glob(p), {}});
+        }
+        auto& rl = patterns_[it->second].rules;
+        if (rl.empty() || rl.back() != r) rl.push_back(r);
+      }
+    }
+  }
+
+  // per-rule columns: decision, requires / labels need-masks, alive
+  t.rule_dec.assign((size_t)t.n_seg * CORDUM_SEG_RULES, 0);
+  t.rule_req_need.assign((size_t)t.n_seg * CORDUM_SEG_RULES, 0);
+  t.rule_lab_need.assign((size_t)t.n_seg * CORDUM_SEG_RULES, 0);
+  Bits alive(W, 0), check(W, 0);
+  uint32_t n_pairs = 0;
+  for (uint32_t r = 0; r < R; ++r) {
+    const RuleModel& m = rules[r];
+    t.rule_dec[r] = normalize_decision_code(m.decision) | (m.has_constraints ? 0x80 : 0);
+    bool dead = false;
+    uint64_t need = 0;
+    for (auto& q : m.requires_) {
+      if (q.empty()) { dead = true; continue; }   // containsString(values, "") is always false (:297)
+      uint32_t id = d_req_.intern(fold_key(q));
+      need |= (id - 2 < 64) ? (1ull << (id - 2)) : 0;
+    }
+    t.rule_req_need[r] = need;
+    uint64_t lneed = 0;
+    for (auto& kv : m.labels) {
+      uint32_t ki = label_key_.find(kv.first, kMiss);
+      if (ki == kMiss) { ki = (uint32_t)label_key_pairs_.size(); label_key_.put(kv.first, ki); label_key_pairs_.emplace_back(); }
+      auto& pairs = label_key_pairs_[ki];
+      uint32_t bit = kMiss;
+      for (auto& pv : pairs) if (pv.first == kv.second) bit = pv.second;
+      if (bit == kMiss) {
+        bit = n_pairs++;
+        pairs.emplace_back(kv.second, bit);
+        if (kv.second.empty() && bit < 64) label_empty_mask_ |= 1ull << bit;
+      }
+      if (bit < 64) lneed |= 1ull << bit;
+    }
+    t.rule_lab_need[r] = lneed;
+    if (!dead) set_bit(alive, r);
+    if (need || lneed) set_bit(check, r);
+  }
+  policy_capacity_error_.clear();
+  if (d_risk_.size() - 2 > 64) policy_capacity_error_ = "more than 64 distinct risk tags referenced by rules";
+  if (n_pairs > 64) policy_capacity_error_ = "more than 64 distinct label pairs referenced by rules";
+  t.row_check.init(1, W);
+  or_bits(t.row_check.row(0), check);
+
+  // combo rows: (actor_type in {"", human, service}) x secrets_present, ANDed with the alive mask
+  t.row_combo.init(6, W);
+  static const char* at_names[3] = {"", "human", "service"};
+  for (int at = 0; at < 3; ++at)
+    for (int s = 0; s < 2; ++s) {
+      uint32_t* row = t.row_combo.row(at * 2 + s);
+      for (uint32_t r = 0; r < R; ++r) {
+        const RuleModel& m = rules[r];
+        bool ok = true;
+        if (!m.actor_types.empty()) {
+          ok = false;
+          if (at != 0)
+            for (auto& e : m.actor_types) if (fold_key(e) == at_names[at]) ok = true;
+        }
+        if (m.secrets_present >= 0 && (m.secrets_present == 1) != (s == 1)) ok = false;
+        if (ok && (alive[r >> 5] >> (r & 31) & 1)) row[r >> 5] |= 1u << (r & 31);
+      }
+    }
+  t.v_policy++;
+}
+
+// ------------------------------------------------------------ routing compile
+void Host::compile_routing() {
+  HostTables& t = t_;
+  d_pool_.clear();
+  routing_topics_.clear();
+  for (auto& p : routing_.pools) d_pool_.intern(p.first);
+  for (size_t i = 0; i < routing_.topics.size(); ++i) {
+    routing_topics_.put(routing_.topics[i].first, (uint32_t)i);
+    for (auto& p : routing_.topics[i].second) d_pool_.intern(p);
+  }
+  t.n_pools = d_pool_.size() - 2;
+  t.pool_req_mask.assign(std::max<uint32_t>(t.n_pools, 1), 0);
+  t.pool_req_nonempty.assign(std::max<uint32_t>(t.n_pools, 1), 0);
+  for (auto& p : routing_.pools) {
+    uint32_t pid = d_pool_.table.find(p.first, 0) - 2;
+    t.pool_req_nonempty[pid] = p.second.empty() ? 0 : 1;   // poolSatisfies: len(poolRequires)==0 -> false (:245)
+    uint64_t mask = 0;
+    for (auto& q : p.second) {
+      std::string k = fold_key(q);   // ToLower(TrimSpace(req)) (:250); blank tokens are dropped (:251)
+      if (k.empty()) continue;
+      uint32_t id = d_req_.intern(k);
+      if (id - 2 < 64) mask |= 1ull << (id - 2);
+    }
+    t.pool_req_mask[pid] = mask;
+  }
+  routing_capacity_error_.clear();
+  if (d_req_.size() - 2 > 64) routing_capacity_error_ = "more than 64 distinct requires tokens across rules and pools";
+  uint32_t blank = d_req_.table.find(sv(), 0);
+  t.req_blank_mask = (blank >= 2 && blank - 2 < 64) ? (1ull << (blank - 2)) : 0;
+  t.v_routing++;
+}
+
+// ------------------------------------------------------------ MCP tables (rule rows, tenant + effective-config verdicts)
+void Host::compile_mcp_tables() {
+  HostTables& t = t_;
+  const auto& rules = policy_.rules;
+  const uint32_t R = (uint32_t)rules.size(), W = t.row_words;
+  // intern every referenced value first so ids are final
+  auto intern_lists = [&](const McpLists& m) {
+    for (int f = 0; f < 4; ++f) {
+      for (auto& e : m.allow[f]) d_mcp_[f].intern(fold_key(e));
+      for (auto& e : m.deny[f]) d_mcp_[f].intern(fold_key(e));
+    }
+  };
+  for (auto& r : rules) intern_lists(r.mcp);
+  for (auto& tn : policy_.tenants) intern_lists(tn.mcp);
+  for (size_t i = 1; i < effcfgs_.size(); ++i) intern_lists(effcfgs_[i].mcp);
+  uint32_t stride = 2;
+  for (int f = 0; f < 4; ++f) stride = std::max(stride, d_mcp_[f].size());
+  t.mcp_stride = stride;
+  // rule rows: bit r = value not denied by r and (r has no allow list or value in it)  (:408-416)
+  for (int f = 0; f < 4; ++f) {
+    Dict& d = d_mcp_[f];
+    Bits base(W, 0);
+    std::vector<std::vector<uint32_t>> allow_hits(d.size()), deny_hits(d.size());
+    for (uint32_t r = 0; r < R; ++r) {
+      const McpLists& m = rules[r].mcp;
+      if (m.allow[f].empty()) set_bit(base, r);
+      for (auto& e : m.allow[f]) allow_hits[d.table.find(fold_key(e), 0)].push_back(r);
+      for (auto& e : m.deny[f]) deny_hits[d.table.find(fold_key(e), 0)].push_back(r);
+    }
+    t.row_mcp[f].init(d.size(), W);
+    for (uint32_t id = 0; id < d.size(); ++id) {
+      uint32_t* row = t.row_mcp[f].row(id);
+      or_bits(row, base);
+      if (id >= 2) {
+        for (uint32_t r : allow_hits[id]) row[r >> 5] |= 1u << (r & 31);
+        for (uint32_t r : deny_hits[id]) row[r >> 5] &= ~(1u << (r & 31));
+      }
+    }
+  }
+  auto verdicts = [&](const McpLists& m, uint8_t* dst) {   // dst[4][stride]
+    for (int f = 0; f < 4; ++f) {
+      std::set<uint32_t> allow, deny;
+      for (auto& e : m.allow[f]) allow.insert(d_mcp_[f].table.find(fold_key(e), 0));
+      for (auto& e : m.deny[f]) deny.insert(d_mcp_[f].table.find(fold_key(e), 0));
+      for (uint32_t id = 0; id < stride; ++id) {
+        uint8_t v = 0;
+        bool named = id >= 2;
+        if (named && deny.count(id)) v = 1;
+        else if (!m.allow[f].empty() && !(named && allow.count(id))) v = 2;
+        dst[(size_t)f * stride + id] = v;
+      }
+    }
+  };
+  size_t nt = std::max<size_t>(policy_.tenants.size(), 1);
+  t.tenant_mcp.assign(nt * 4 * stride, 0);
+  for (size_t i = 0; i < policy_.tenants.size(); ++i) verdicts(policy_.tenants[i].mcp, &t.tenant_mcp[i * 4 * stride]);
+  t.n_effcfg = (uint32_t)effcfgs_.size() ? (uint32_t)effcfgs_.size() - 1 : 0;
+  t.eff_mcp.assign((size_t)(t.n_effcfg + 1) * 4 * stride, 0);
+  for (size_t i = 1; i < effcfgs_.size(); ++i)
+    if (effcfg_ok_[i]) verdicts(effcfgs_[i].mcp, &t.eff_mcp[i * 4 * stride]);
+  t.v_mcp++;
+}
+
+// ------------------------------------------------------------ topics
+void Host::topic_row(sv trimmed, Bits& out) const {
+  out = vac_topic_;
+  for (auto& p : patterns_)
+    if (p.glob.match(trimmed))
+      for (uint32_t r : p.rules) out[r >> 5] |= 1u << (r & 31);
+}
+
+void Host::eff_topic_fill(uint32_t cfg, uint32_t topic_id) {
+  uint8_t v = 0;
+  if (effcfg_ok_[cfg]) {
+    sv topic = trim_space(topic_keys_[topic_id]);
+    if (!topic.empty()) {   // matchAny: value == "" -> false (kernel.go:456)
+      const EffGlobs& g = eff_globs_[cfg];
+      for (auto& gl : g.denied) if (gl.match(topic)) { v |= 1; break; }
+      if (g.has_allowed) {
+        bool any = false;
+        for (auto& gl : g.allowed) if (gl.match(topic)) { any = true; break; }
+        if (!any) v |= 2;
+      }
+    } else if (eff_globs_[cfg].has_allowed) v |= 2;
+  }
+  t_.eff_topic[(size_t)cfg * t_.topic_stride + topic_id] = v;
+}
+
+// Recompute every per-topic table for the topics known so far (ids are stable).
+void Host::rebuild_topics() {
+  HostTables& t = t_;
+  if (topic_keys_.empty()) {   // id 0 = the empty raw topic
+    topic_keys_.emplace_back();
+    topic_ids_.put(sv(), 0);
+  }
+  for (auto& tp : routing_.topics)   // pre-seed so steady state has no dictionary misses
+    if (!topic_ids_.contains(tp.first) && topic_keys_.size() < max_topics_) {
+      topic_ids_.put(tp.first, (uint32_t)topic_keys_.size());
+      topic_keys_.push_back(tp.first);
+    }
+  const uint32_t n = (uint32_t)topic_keys_.size(), W = t.row_words;
+  t.row_topic.init(n, W);
+  topic_entries_.assign(n, TopicEntry{0, 0, 0});
+  topic_pools_.assign(n, {});
+  t.pool_list.clear();
+  // rows in parallel (glob matching dominates at 4k rules x 2k topics)
+  std::atomic<uint32_t> next{0};
+  auto work = [&]() {
+    Bits row;
+    for (uint32_t i; (i = next.fetch_add(1)) < n;) {
+      sv trimmed = trim_space(topic_keys_[i]);
+      uint32_t fl = 0;
+      if (topic_keys_[i].empty()) fl |= JF_TOPIC_RAW_EMPTY;
+      if (trimmed.empty()) fl |= JF_TOPIC_MISSING;
+      else if (!starts_with(trimmed, "job.")) fl |= JF_TOPIC_UNSUPPORTED;
+      topic_entries_[i].flags = fl;
+      if (!(fl & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED))) {
+        topic_row(trimmed, row);
+        std::memcpy(t.row_topic.row(i), row.data(), W * 4);
+      }
+    }
+  };
+  uint32_t nth = std::min<uint32_t>(threads_, std::max<uint32_t>(1, n / 16));
+  if (nth <= 1) work();
+  else {
+    std::vector<std::thread> ts;
+    for (uint32_t k = 0; k < nth; ++k) ts.emplace_back(work);
+    for (auto& th : ts) th.join();
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t ri = routing_topics_.find(topic_keys_[i], kMiss);
+    topic_entries_[i].pool_off = (uint32_t)t.pool_list.size();
+    if (ri != kMiss) {
+      topic_pools_[i] = routing_.topics[ri].second;
+      for (auto& p : routing_.topics[ri].second) {
+        uint32_t pid = d_pool_.table.find(p, 0) - 2;
+        bool dup = false;
+        for (uint32_t k = topic_entries_[i].pool_off; k < t.pool_list.size(); ++k) dup |= t.pool_list[k] == pid;
+        if (!dup) t.pool_list.push_back(pid);
+      }
+    }
+    topic_entries_[i].pool_cnt = (uint32_t)t.pool_list.size() - topic_entries_[i].pool_off;
+  }
+  t.topic_pool_off.resize(n);
+  t.topic_pool_cnt.resize(n);
+  for (uint32_t i = 0; i < n; ++i) { t.topic_pool_off[i] = topic_entries_[i].pool_off; t.topic_pool_cnt[i] = topic_entries_[i].pool_cnt; }
+  if (t.pool_list.empty()) t.pool_list.push_back(0);
+  // effective-config topic verdicts
+  uint32_t stride = 1024;
+  while (stride < n) stride *= 2;
+  t.topic_stride = stride;
+  t.eff_topic.assign((size_t)(t.n_effcfg + 1) * stride, 0);
+  for (uint32_t c = 1; c <= t.n_effcfg; ++c)
+    for (uint32_t i = 0; i < n; ++i) eff_topic_fill(c, i);
+  t.v_topic++;
+}
+
+uint32_t Host::add_topic(sv raw) {
+  uint32_t id = topic_ids_.find(raw, kMiss);
+  if (id != kMiss) return id;
+  if (topic_keys_.size() >= max_topics_) return kMiss;
+  HostTables& t = t_;
+  id = (uint32_t)topic_keys_.size();
+  topic_ids_.put(raw, id);
+  topic_keys_.emplace_back(raw);
+  sv trimmed = trim_space(topic_keys_.back());
+  TopicEntry e{0, (uint32_t)t.pool_list.size(), 0};
+  if (trimmed.empty()) e.flags |= JF_TOPIC_MISSING;
+  else if (!starts_with(trimmed, "job.")) e.flags |= JF_TOPIC_UNSUPPORTED;
+  Bits row(t.row_words, 0);
+  if (!e.flags) topic_row(trimmed, row);
+  t.row_topic.append(row);
+  topic_pools_.emplace_back();
+  uint32_t ri = routing_topics_.find(raw, kMiss);
+  if (t.topic_pool_off.empty() && t.pool_list.size() == 1) {}   // keep placeholder entry
+  if (ri != kMiss) {
+    topic_pools_.back() = routing_.topics[ri].second;
+    for (auto& p : routing_.topics[ri].second) {
+      uint32_t pid = d_pool_.table.find(p, 0) - 2;
+      bool dup = false;
+      for (uint32_t k = e.pool_off; k < t.pool_list.size(); ++k) dup |= t.pool_list[k] == pid;
+      if (!dup) t.pool_list.push_back(pid);
+    }
+  }
+  e.pool_cnt = (uint32_t)t.pool_list.size() - e.pool_off;
+  topic_entries_.push_back(e);
+  t.topic_pool_off.push_back(e.pool_off);
+  t.topic_pool_cnt.push_back(e.pool_cnt);
+  if (id >= t.topic_stride) {   // grow the effective-config x topic table
+    uint32_t stride = t.topic_stride;
+    while (stride <= id) stride *= 2;
+    std::vector<uint8_t> grown((size_t)(t.n_effcfg + 1) * stride, 0);
+    for (uint32_t c = 0; c <= t.n_effcfg; ++c)
+      std::memcpy(&grown[(size_t)c * stride], &t.eff_topic[(size_t)c * t.topic_stride], t.topic_stride);
+    t.eff_topic.swap(grown);
+    t.topic_stride = stride;
+  }
+  for (uint32_t c = 1; c <= t.n_effcfg; ++c) eff_topic_fill(c, id);
+  t.v_topic++;
+  return id;
+}
+
+uint32_t Host::add_effcfg(sv payload) {
+  uint32_t id = effcfg_ids_.find(payload, kMiss);
+  if (id != kMiss) return id;
+  if (effcfg_ids_.size() >= max_effcfgs_) return kMiss;
+  EffSafety cfg;
+  bool ok = parse_effective_safety(payload, cfg);
+  if (!ok) { effcfg_ids_.put(payload, 0); return 0; }   // unparsable: the overlay is skipped (kernel.go:218)
+  if (effcfgs_.empty()) { effcfgs_.emplace_back(); effcfg_ok_.push_back(0); eff_globs_.emplace_back(); }
+  id = (uint32_t)effcfgs_.size();
+  effcfg_ids_.put(payload, id);
+  EffGlobs g;
+  g.has_allowed = !cfg.allowed_topics.empty();
+  for (auto& p : cfg.denied_topics) { sv tp = trim_space(p); if (!tp.empty()) g.denied.emplace_back(tp); }
+  for (auto& p : cfg.allowed_topics) { sv tp = trim_space(p); if (!tp.empty()) g.allowed.emplace_back(tp); }
+  effcfgs_.push_back(std::move(cfg));
+  effcfg_ok_.push_back(1);
+  eff_globs_.push_back(std::move(g));
+  HostTables& t = t_;
+  compile_mcp_tables();   // dictionaries may have grown; sets n_effcfg
+  t.eff_topic.resize((size_t)(t.n_effcfg + 1) * t.topic_stride, 0);
+  for (uint32_t i = 0; i < topic_keys_.size(); ++i) eff_topic_fill(id, i);
+  t.v_topic++;
+  return id;
+}
+
+// ------------------------------------------------------------ documents
+int Host::load_policy(sv json, sv snapshot, std::string& err) {
+  PolicyModel m;
+  if (!parse_policy_json(json, m, err)) return CORDUM_E_INVALID;
+  std::lock_guard<std::mutex> g(mu_);
+  PolicyModel old = std::move(policy_);
+  policy_ = std::move(m);
+  compile_policy();
+  compile_routing();
+  if (!policy_capacity_error_.empty() || !routing_capacity_error_.empty()) {
+    err = policy_capacity_error_.empty() ? routing_capacity_error_ : policy_capacity_error_;
+    policy_ = std::move(old);   // keep serving the previous policy (watchPolicy keeps the old one on failure, kernel.go:495-499)
+    compile_policy();
+    compile_routing();
+    compile_mcp_tables();
+    rebuild_topics();
+    return CORDUM_E_CAPACITY;
+  }
+  compile_mcp_tables();
+  rebuild_topics();
+  epoch_++;
+  snapshot_ = std::string(snapshot);
+  if (!snapshot.empty()) {   // setPolicy, kernel.go:510-521
+    snapshots_.insert(snapshots_.begin(), snapshot_);
+    if (snapshots_.size() > 10) snapshots_.resize(10);
+  }
+  return CORDUM_OK;
+}
+
+int Host::load_routing(sv json, std::string& err) {
+  RoutingModel m;
+  if (!parse_routing_json(json, m, err)) return CORDUM_E_INVALID;
+  std::lock_guard<std::mutex> g(mu_);
+  RoutingModel old = std::move(routing_);
+  routing_ = std::move(m);
+  compile_policy();   // the requires dictionary is shared: rebuild both sides
+  compile_routing();
+  if (!routing_capacity_error_.empty()) {
+    err = routing_capacity_error_;
+    routing_ = std::move(old);
+    compile_policy();
+    compile_routing();
+    compile_mcp_tables();
+    rebuild_topics();
+    return CORDUM_E_CAPACITY;
+  }
+  compile_mcp_tables();
+  rebuild_topics();
+  epoch_++;
+  std::string e2;
+  return compile_workers(e2) == CORDUM_OK ? CORDUM_OK : (err = e2, CORDUM_E_CAPACITY);
+}
+
+int Host::load_workers(const cordum_workers* w, std::string& err) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto& store = workers_raw_;
+  store.clear();
+  t_.loads.clear();
+  worker_ids_.clear();
+  if (w) {
+    auto sp = [&](const cordum_str* col, uint32_t i) { return sv((const char*)w->arena + col[i].off, col[i].len); };
+    store.resize(w->n_workers);
+    t_.loads.resize(w->n_workers);
+    worker_ids_.resize(w->n_workers);
+    for (uint32_t i = 0; i < w->n_workers; ++i) {
+      float cpu = w->cpu_load[i], gpu = w->gpu_utilization[i];
+      if (cpu != cpu || gpu != gpu) { err = "worker load is NaN (ordering undefined in the reference)"; return CORDUM_E_INVALID; }
+      store[i].id = std::string(sp(w->worker_id, i));
+      store[i].pool = std::string(sp(w->pool, i));
+      worker_ids_[i] = store[i].id;
+      if (w->label_off)
+        for (uint32_t k = w->label_off[i]; k < w->label_off[i + 1]; ++k) {
+          std::string key(sp(w->label_keys, k));
+          bool found = false;
+          for (auto& kv : store[i].labels) if (kv.first == key) { kv.second = std::string(sp(w->label_vals, k)); found = true; }
+          if (!found) store[i].labels.emplace_back(key, std::string(sp(w->label_vals, k)));
+        }
+      t_.loads[i] = Load16{w->active_jobs[i], w->max_parallel_jobs[i], cpu, gpu};
+    }
+  }
+  epoch_++;
+  return compile_workers(err);
+}
+
+int Host::compile_workers(std::string& err) {
+  HostTables& t = t_;
+  auto& store = workers_raw_;
+  const uint32_t n = (uint32_t)store.size();
+  t.n_slots = n;
+  worker_slot_.clear();
+  place_pair_.clear();
+  place_key_.clear();
+  for (uint32_t s = 0; s < n; ++s) worker_slot_.put(store[s].id, s);   // map semantics: last wins
+  std::vector<uint32_t> live;
+  for (uint32_t s = 0; s < n; ++s) if (worker_slot_.find(store[s].id, kMiss) == s) live.push_back(s);
+  std::sort(live.begin(), live.end(), [&](uint32_t a, uint32_t b) { return store[a].id < store[b].id; });
+  t.rank_slot.assign(std::max<uint32_t>(n, 1), 0);
+  std::vector<uint32_t> rank_of(n, 0);
+  for (uint32_t r = 0; r < live.size(); ++r) { t.rank_slot[r] = live[r]; rank_of[live[r]] = r; }
+  // routable = live and in a pool the routing table knows
+  struct Pos { uint32_t pool, rank, slot; };
+  std::vector<Pos> pos;
+  for (uint32_t s : live) {
+    uint32_t pid = d_pool_.table.find(store[s].pool, 0);
+    if (pid >= 2) pos.push_back({pid - 2, rank_of[s], s});
+  }
+  std::sort(pos.begin(), pos.end(), [](const Pos& a, const Pos& b) { return a.pool != b.pool ? a.pool < b.pool : a.rank < b.rank; });
+  // placement-label dictionary: pairs (k,v!=""), per-key "absent or empty" bits, "has any label" bit
+  uint32_t nbits = 0;
+  place_any_bit_ = nbits++;
+  for (auto& p : pos)
+    for (auto& kv : store[p.slot].labels) {
+      if (place_key_.find(kv.first, kMiss) == kMiss) place_key_.put(kv.first, nbits++);
+      if (!kv.second.empty()) {
+        std::string pk = kv.first; pk.push_back('\0'); pk += kv.second;
+        if (place_pair_.find(pk, kMiss) == kMiss) place_pair_.put(pk, nbits++);
+      }
+    }
+  place_bits_ = nbits;
+  if (nbits > 128) { err = "more than 128 placement-label bits (pairs + keys) on routable workers"; return CORDUM_E_CAPACITY; }
+  const uint32_t np = (uint32_t)pos.size();
+  t.n_pos = np;
+  uint32_t cap = std::max<uint32_t>(np, 1);
+  t.pos_pool.assign(cap, 0); t.pos_slot.assign(cap, 0); t.pos_rank.assign(cap, 0);
+  t.pos_label_lo.assign(cap, 0); t.pos_label_hi.assign(cap, 0);
+  t.slot_pos.assign(std::max<uint32_t>(n, 1), 0);
+  t.pool_off.assign(t.n_pools + 1, 0);
+  // all keys, to set the "absent or empty" bits
+  std::vector<std::pair<std::string, uint32_t>> keys;
+  {
+    std::set<std::string> seen;
+    for (auto& p : pos) for (auto& kv : store[p.slot].labels) if (seen.insert(kv.first).second)
+      keys.emplace_back(kv.first, place_key_.find(kv.first, 0));
+  }
+  for (uint32_t i = 0; i < np; ++i) {
+    const Pos& p = pos[i];
+    t.pos_pool[i] = p.pool; t.pos_slot[i] = p.slot; t.pos_rank[i] = p.rank;
+    t.slot_pos[p.slot] = i + 1;
+    t.pool_off[p.pool + 1]++;
+    uint64_t m[2] = {0, 0};
+    auto setb = [&](uint32_t b) { m[b >> 6] |= 1ull << (b & 63); };
+    const auto& labels = store[p.slot].labels;
+    if (!labels.empty()) {
+      setb(place_any_bit_);
+      for (auto& k : keys) {
+        const std::string* val = nullptr;
+        for (auto& kv : labels) if (kv.first == k.first) val = &kv.second;
+        if (!val || val->empty()) setb(k.second);   // labels[k] == "" (matchesLabels, :169-171)
+        else {
+          std::string pk = k.first; pk.push_back('\0'); pk += *val;
+          setb(place_pair_.find(pk, 0));
+        }
+      }
+    }
+    t.pos_label_lo[i] = m[0]; t.pos_label_hi[i] = m[1];
+  }
+  for (uint32_t p = 0; p < t.n_pools; ++p) t.pool_off[p + 1] += t.pool_off[p];
+  if (t.loads.empty()) t.loads.push_back(Load16{0, 0, 0.f, 0.f});
+  t.v_workers++;
+  t.v_loads++;
+  return CORDUM_OK;
+}
+
+int Host::update_loads(uint32_t n, const uint32_t* slots, const cordum_worker_load* loads, std::string& err) {
+  std::lock_guard<std::mutex> g(mu_);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (slots[i] >= t_.n_slots) { err = "worker slot out of range"; return CORDUM_E_INVALID; }
+    if (loads[i].cpu_load != loads[i].cpu_load || loads[i].gpu_utilization != loads[i].gpu_utilization) {
+      err = "worker load is NaN"; return CORDUM_E_INVALID;
+    }
+    t_.loads[slots[i]] = Load16{loads[i].active_jobs, loads[i].max_parallel_jobs, loads[i].cpu_load, loads[i].gpu_utilization};
+  }
+  t_.v_loads++;
+  return CORDUM_OK;
+}
+
+std::string Host::mcp_value_string(int field, uint32_t id) const {
+  if (id >= 2 && id - 2 < d_mcp_[field].keys.size()) return d_mcp_[field].keys[id - 2];
+  return std::string();
+}
+const std::vector<std::string>& Host::topic_pool_names(uint32_t topic_id) const {
+  static const std::vector<std::string> none;
+  return topic_id < topic_pools_.size() ? topic_pools_[topic_id] : none;
+}
+
+// ============================================================ encoder
+namespace {
+inline sv span(const cordum_envelopes* e, const cordum_str* col, uint32_t j) {
+  return col ? sv((const char*)e->arena + col[j].off, col[j].len) : sv();
+}
+// labels that never constrain placement (filterPlacementLabels, strategy_least_loaded.go:195-222)
+inline bool placement_skips(sv k) {
+  switch (k.size()) {
+    case 6: return k == "run_id";
+    case 7: return k == "step_id" || k == "node_id";
+    case 9: return k == "worker_id";
+    case 11: return k == "workflow_id";
+    case 14: return k == "preferred_pool";
+    case 15: return k == "secrets_present";
+    case 16: return k == "approval_granted";
+    case 19: return k == "preferred_worker_id";
+    default: return false;
+  }
+}
+// mcp label aliases (kernel.go:400-403): field*3 + variant, or -1
+inline int mcp_key(sv k) {
+  if (k.size() < 8 || k[0] != 'm' || k[1] != 'c' || k[2] != 'p') return -1;
+  static const char* names[12] = {"mcp.server", "mcp_server", "mcpServer", "mcp.tool", "mcp_tool", "mcpTool",
+                                  "mcp.resource", "mcp_resource", "mcpResource", "mcp.action", "mcp_action", "mcpAction"};
+  for (int i = 0; i < 12; ++i) if (k == names[i]) return i;
+  return -1;
+}
+}  // namespace
+
+void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss) const {
+  uint32_t flags = 0;
+  // ---- topic (dictionary keyed by the RAW string: policy sees TrimSpace(topic), routing the raw one)
+  sv topic_raw = span(env, env->topic, j);
+  uint32_t tid = topic_ids_.find(topic_raw, kMiss);
+  if (tid == kMiss) { miss = true; tid = 0; }
+  out.topic[j] = tid;
+  flags |= topic_entries_[tid].flags;
+  // ---- tenant (kernel.go:134-169)
+  const bool has_meta = env->has_meta && env->has_meta[j];
+  sv tenant = trim_space(span(env, env->tenant, j));
+  if (tenant.empty() && has_meta) tenant = trim_space(span(env, env->meta_tenant_id, j));
+  if (tenant.empty()) tenant = default_tenant_trim_;
+  if (tenant.empty()) tenant = "default";
+  out.tenant_pol[j] = tenant_pol_.find(tenant, 0);   // exact-string map lookup (kernel.go:190)
+  out.tenant[j] = lookup_value(d_tenant_, tenant);
+  // ---- meta (policyMetaFromRequest, kernel.go:348-368)
+  sv principal = span(env, env->principal_id, j);
+  sv cap, pack, actor = principal;
+  int at = 0;
+  if (has_meta) {
+    cap = span(env, env->capability, j);
+    pack = span(env, env->pack_id, j);
+    sv a = span(env, env->actor_id, j);
+    if (!a.empty()) actor = a;
+    int raw_at = env->actor_type ? env->actor_type[j] : 0;
+    at = (raw_at == 1 || raw_at == 2) ? raw_at : 0;
+  }
+  out.capability[j] = lookup_value(d_cap_, cap);
+  out.pack[j] = lookup_value(d_pack_, pack);
+  out.actor[j] = lookup_value(d_actor_, actor);
+  // ---- risk tags / requires
+  uint64_t risk = 0, req = 0;
+  bool secrets_tag = false;
+  if (has_meta && env->risk_off)
+    for (uint32_t k = env->risk_off[j]; k < env->risk_off[j + 1]; ++k) {
+      sv tag = span(env, env->risk_tags, k);
+      if (fold_eq(tag, "secrets")) secrets_tag = true;   // kernel.go:387-391 (no trim)
+      uint32_t id = lookup_value(d_risk_, tag);
+      if (id >= 2 && id - 2 < 64) risk |= 1ull << (id - 2);
+    }
+  if (has_meta && env->requires_off) {
+    uint32_t a = env->requires_off[j], b = env->requires_off[j + 1];
+    if (b > a) flags |= JF_REQ_NONEMPTY;
+    for (uint32_t k = a; k < b; ++k) {
+      FoldBuf f(span(env, env->requires_, k));
+      uint32_t id = d_req_.table.find(f.view, 0);
+      if (id >= 2 && id - 2 < 64) req |= 1ull << (id - 2);
+      else if (!f.view.empty()) flags |= JF_REQ_UNKNOWN;   // no pool declares it -> no pool satisfies (:255-262)
+    }
+  }
+  out.risk_mask[j] = risk;
+  out.req_mask[j] = req;
+  // ---- labels: one pass
+  uint64_t lab = label_empty_mask_, place[2] = {0, 0};
+  sv mcpv[12];
+  sv secrets_label, pref_pool, pref_worker;
+  bool have_secrets_label = false;
+  uint32_t la = env->label_off ? env->label_off[j] : 0, lb = env->label_off ? env->label_off[j + 1] : 0;
+  if (lb > la) flags |= JF_HAS_LABELS;
+  for (uint32_t k = la; k < lb; ++k) {
+    sv key = span(env, env->label_keys, k), val = span(env, env->label_vals, k);
+    bool shadowed = false;   // map semantics: a later entry with the same key wins
+    for (uint32_t k2 = k + 1; k2 < lb && !shadowed; ++k2) shadowed = span(env, env->label_keys, k2) == key;
+    if (shadowed) continue;
+    // rule label pairs: labels.get(k,"") == v
+    uint32_t ki = label_key_.find(key, kMiss);
+    if (ki != kMiss)
+      for (auto& pv : label_key_pairs_[ki]) {
+        if (pv.second >= 64) continue;
+        if (sv(pv.first) == val) lab |= 1ull << pv.second; else lab &= ~(1ull << pv.second);
+      }
+    int mk = mcp_key(key);
+    if (mk >= 0) mcpv[mk] = trim_space(val);
+    if (key == "secrets_present") { secrets_label = trim_space(val); have_secrets_label = true; }
+    else if (key == "preferred_pool") pref_pool = val;
+    else if (key == "preferred_worker_id") pref_worker = val;
+    // placement constraint?
+    if (placement_skips(key) || starts_with(key, "cordum.")) continue;
+    uint32_t bit;
+    if (!val.empty()) {
+      char small[256];
+      std::string big;
+      sv pk;
+      size_t n = key.size() + 1 + val.size();
+      if (n <= sizeof small) {
+        std::memcpy(small, key.data(), key.size()); small[key.size()] = 0; std::memcpy(small + key.size() + 1, val.data(), val.size());
+        pk = sv(small, n);
+      } else { big.assign(key); big.push_back('\0'); big.append(val); pk = big; }
+      bit = place_pair_.find(pk, kMiss);
+      if (bit == kMiss) { flags |= JF_PLACE_UNSAT; continue; }
+    } else {
+      bit = place_key_.find(key, kMiss);
+      if (bit == kMiss) bit = place_any_bit_;   // no worker carries this key: any labelled worker passes
+    }
+    place[bit >> 6] |= 1ull << (bit & 63);
+  }
+  out.lab_mask[j] = lab;
+  out.place_lo[j] = place[0];
+  out.place_hi[j] = place[1];
+  // ---- MCP request (extractMCPRequest, kernel.go:395-414) and secrets (kernel.go:381-393)
+  bool used = false;
+  for (int f = 0; f < 4; ++f) {
+    sv v;
+    for (int a = 0; a < 3 && v.empty(); ++a) v = mcpv[f * 3 + a];
+    out.mcp[f][j] = lookup_value(d_mcp_[f], v);
+    used |= !v.empty();
+  }
+  if (used) flags |= JF_MCP_USED;
+  bool secrets = secrets_tag;
+  if (have_secrets_label && !secrets_label.empty())
+    secrets = secrets_label == "true" || secrets_label == "1" || fold_eq(secrets_label, "yes");
+  flags |= (uint32_t)(at * 2 + (secrets ? 1 : 0));
+  // ---- routing hints
+  uint32_t pp = 0, pw = 0;
+  if (!pref_pool.empty()) { uint32_t id = d_pool_.table.find(pref_pool, 0); pp = id >= 2 ? id - 1 : CORDUM_PREF_UNKNOWN; }
+  if (!pref_worker.empty()) { uint32_t s = worker_slot_.find(pref_worker, kMiss); pw = s != kMiss ? s + 1 : CORDUM_PREF_UNKNOWN; }
+  out.pref_pool[j] = pp;
+  out.pref_worker[j] = pw;
+  // ---- effective config
+  sv eff = span(env, env->effective_config, j);
+  uint32_t eid = 0;
+  if (!eff.empty()) {
+    eid = effcfg_ids_.find(eff, kMiss);
+    if (eid == kMiss) { miss = true; eid = 0; }
+  }
+  out.effcfg[j] = eid;
+  if (env->approved && env->approved[j]) flags |= JF_APPROVED;
+  out.flags[j] = flags;
+}
+
+void Host::encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
+                        std::vector<uint32_t>& misses) const {
+  for (uint32_t j = a; j < b; ++j) {
+    bool miss = false;
+    encode_job(env, j, out, miss);
+    if (miss) misses.push_back(j);
+  }
+}
+
+int Host::encode(const cordum_envelopes* env, HostColumns& out, std::string& err) {
+  if (!env) { err = "null envelopes"; return CORDUM_E_INVALID; }
+  std::lock_guard<std::mutex> g(mu_);
+  const uint32_t n = env->n_jobs;
+  uint32_t nth = std::min<uint32_t>(threads_, std::max<uint32_t>(1, n / 4096));
+  std::vector<std::vector<uint32_t>> misses(nth);
+  if (nth <= 1) encode_range(env, 0, n, out, misses[0]);
+  else {
+    std::vector<std::thread> ts;
+    uint32_t per = (n + nth - 1) / nth;
+    for (uint32_t k = 0; k < nth; ++k) {
+      uint32_t a = std::min(n, k * per), b = std::min(n, a + per);
+      ts.emplace_back([&, a, b, k]() { encode_range(env, a, b, out, misses[k]); });
+    }
+    for (auto& t : ts) t.join();
+  }
+  // dictionary misses: register the new topics / effective configs, then re-encode just those jobs
+  for (auto& lst : misses)
+    for (uint32_t j : lst) {
+      sv topic_raw = span(env, env->topic, j);
+      if (add_topic(topic_raw) == kMiss) { err = "topic dictionary full (max_topics)"; return CORDUM_E_CAPACITY; }
+      sv eff = span(env, env->effective_config, j);
+      if (!eff.empty() && add_effcfg(eff) == kMiss) { err = "effective-config dictionary full (max_effcfgs)"; return CORDUM_E_CAPACITY; }
+      bool miss = false;
+      encode_job(env, j, out, miss);
+    }
+  return CORDUM_OK;
+}
+
+}  // namespace cordum

@@ -1,0 +1,277 @@
+// host.hpp — host side of the engine: policy/routing/worker models, the table compiler
+// (strings -> dictionary-coded pass-rows and columns) and the job encoder.
+// No CUDA in here: engine.cu owns device memory and uploads what this produces.
+//
+// Reference semantics compiled into tables (nothing here runs per job on the GPU path
+// except encode(), which is pure dictionary lookup):
+//   matchRule predicates            core/infra/config/safety_policy.go:259-294
+//   legacyRules                     :225-257          normalizeDecision :208-223
+//   MCPAllowed / matchMCPField      :385-416
+//   request normalisation           core/controlplane/safetykernel/kernel.go:133-185, 348-414
+//   ParseEffectiveSafety            core/infra/config/effective.go:12-39
+//   pool / label filtering          core/controlplane/scheduler/strategy_least_loaded.go:161-265
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cordum_b200.h"
+#include "gostr.hpp"
+#include "tables.h"
+
+namespace cordum {
+
+// ------------------------------------------------------------------ string-keyed hash table
+// Open addressing, keyed by bytes, lookups take a string_view (no allocation on the encode path).
+class StrTable {
+ public:
+  StrTable() { slots_.assign(16, Slot{}); }
+  static uint64_t hash(sv s) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    return h | 1;
+  }
+  // returns value or `miss`
+  uint32_t find(sv key, uint32_t miss) const {
+    uint64_t h = hash(key);
+    size_t m = slots_.size() - 1;
+    for (size_t i = h & m;; i = (i + 1) & m) {
+      const Slot& s = slots_[i];
+      if (s.hash == 0) return miss;
+      if (s.hash == h && s.len == key.size() && std::char_traits<char>::compare(pool_.data() + s.off, key.data(), s.len) == 0)
+        return s.val;
+    }
+  }
+  bool contains(sv key) const { return find(key, 0xFFFFFFFEu) != 0xFFFFFFFEu; }
+  void put(sv key, uint32_t val) {
+    if ((count_ + 1) * 2 > slots_.size()) grow();
+    uint64_t h = hash(key);
+    size_t m = slots_.size() - 1;
+    for (size_t i = h & m;; i = (i + 1) & m) {
+      Slot& s = slots_[i];
+      if (s.hash == 0) {
+        s.hash = h; s.off = (uint32_t)pool_.size(); s.len = (uint32_t)key.size(); s.val = val;
+        pool_.append(key.data(), key.size());
+        ++count_;
+        return;
+      }
+      if (s.hash == h && s.len == key.size() && std::char_traits<char>::compare(pool_.data() + s.off, key.data(), s.len) == 0) {
+        s.val = val;
+        return;
+      }
+    }
+  }
+  size_t size() const { return count_; }
+  void clear() { slots_.assign(16, Slot{}); pool_.clear(); count_ = 0; }
+
+ private:
+  struct Slot { uint64_t hash = 0; uint32_t off = 0, len = 0, val = 0; };
+  std::vector<Slot> slots_;
+  std::string pool_;
+  size_t count_ = 0;
+  void grow() {
+    std::vector<Slot> old;
+    old.swap(slots_);
+    slots_.assign(old.size() * 2, Slot{});
+    size_t m = slots_.size() - 1;
+    for (auto& s : old) {
+      if (!s.hash) continue;
+      size_t i = s.hash & m;
+      while (slots_[i].hash) i = (i + 1) & m;
+      slots_[i] = s;
+    }
+  }
+};
+
+// Dictionary of canonical strings: id 0 = raw-empty, 1 = other, >=2 referenced values.
+struct Dict {
+  StrTable table;
+  std::vector<std::string> keys;   // keys[id-2]
+  uint32_t intern(sv canon) {
+    uint32_t id = table.find(canon, 0);
+    if (id) return id;
+    id = (uint32_t)keys.size() + 2;
+    keys.emplace_back(canon);
+    table.put(canon, id);
+    return id;
+  }
+  uint32_t size() const { return (uint32_t)keys.size() + 2; }
+  void clear() { table.clear(); keys.clear(); }
+};
+
+// ------------------------------------------------------------------ models
+struct McpLists { std::vector<std::string> allow[4], deny[4]; };   // server, tool, resource, action
+
+struct RuleModel {
+  std::string id, decision, reason;
+  std::vector<std::string> tenants, topics, capabilities, risk_tags, requires_, pack_ids, actor_ids, actor_types;
+  std::vector<std::pair<std::string, std::string>> labels;
+  int secrets_present = -1;
+  McpLists mcp;
+  bool has_constraints = false;
+  std::string constraints_json, remediations_json;
+};
+struct TenantModel { std::string name; std::vector<std::string> allow_topics, deny_topics; McpLists mcp; };
+struct PolicyModel {
+  bool nil = true;
+  std::string default_tenant;
+  std::vector<RuleModel> rules;       // effective rule list (legacy expansion applied)
+  std::vector<TenantModel> tenants;   // sorted by name bytes
+};
+struct RoutingModel {
+  std::vector<std::pair<std::string, std::vector<std::string>>> topics;
+  std::vector<std::pair<std::string, std::vector<std::string>>> pools;   // name -> requires
+};
+struct EffSafety { std::vector<std::string> allowed_topics, denied_topics; McpLists mcp; };
+// Worker snapshot kept as strings so that routing changes can recompile the worker tables.
+struct WorkerRaw { std::string id, pool; std::vector<std::pair<std::string, std::string>> labels; };
+
+bool parse_policy_json(sv text, PolicyModel& out, std::string& err);
+bool parse_routing_json(sv text, RoutingModel& out, std::string& err);
+bool parse_effective_safety(sv payload, EffSafety& out);
+uint8_t normalize_decision_code(sv raw);   // CORDUM_DEC_*
+
+// ------------------------------------------------------------------ compiled host tables
+using Bits = std::vector<uint32_t>;   // one pass-row: n_seg*32 words
+
+struct RowTable {                      // rows for one attribute, row-major
+  uint32_t n_rows = 0, row_words = 0;
+  std::vector<uint32_t> data;
+  void init(uint32_t rows, uint32_t words) { n_rows = rows; row_words = words; data.assign((size_t)rows * words, 0); }
+  uint32_t* row(uint32_t r) { return data.data() + (size_t)r * row_words; }
+  const uint32_t* row(uint32_t r) const { return data.data() + (size_t)r * row_words; }
+  void append(const Bits& b) { data.insert(data.end(), b.begin(), b.end()); ++n_rows; }
+};
+
+struct TopicEntry { uint32_t flags; uint32_t pool_off, pool_cnt; };
+
+struct HostTables {
+  // policy
+  uint32_t n_rules = 0, n_seg = 1, row_words = 32;
+  RowTable row_tenant, row_topic, row_cap, row_pack, row_actor, row_combo, row_risk, row_check, row_mcp[4];
+  std::vector<uint64_t> rule_req_need, rule_lab_need;
+  std::vector<uint8_t> rule_dec;
+  uint32_t mcp_stride = 2;
+  std::vector<uint8_t> tenant_mcp, eff_mcp, eff_topic;
+  uint32_t topic_stride = 0, n_effcfg = 0;
+  // routing
+  std::vector<uint32_t> topic_pool_off, topic_pool_cnt, pool_list;
+  std::vector<uint64_t> pool_req_mask;
+  std::vector<uint8_t> pool_req_nonempty;
+  uint64_t req_blank_mask = 0;
+  uint32_t n_pools = 0;
+  // workers
+  uint32_t n_slots = 0, n_pos = 0;
+  std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot;
+  std::vector<uint64_t> pos_label_lo, pos_label_hi;
+  std::vector<Load16> loads;
+  // change counters (engine re-uploads a group when its version moved)
+  uint64_t v_policy = 0, v_topic = 0, v_mcp = 0, v_routing = 0, v_workers = 0, v_loads = 0;
+};
+
+// Encoded batch columns on the host (engine allocates them pinned and hands pointers in).
+struct HostColumns {
+  uint32_t *tenant, *tenant_pol, *topic, *capability, *pack, *actor, *mcp[4], *pref_pool, *pref_worker, *effcfg;
+  uint64_t *risk_mask, *req_mask, *lab_mask, *place_lo, *place_hi;
+  uint32_t* flags;
+};
+
+class Host {
+ public:
+  Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads);
+
+  // documents
+  int load_policy(sv json, sv snapshot, std::string& err);
+  int load_routing(sv json, std::string& err);
+  int load_workers(const cordum_workers* w, std::string& err);
+  int update_loads(uint32_t n, const uint32_t* slots, const cordum_worker_load* loads, std::string& err);
+
+  // encode a batch (thread-safe against itself via mu_)
+  int encode(const cordum_envelopes* env, HostColumns& out, std::string& err);
+
+  // bumps whenever dictionary ids may have been reassigned (policy / routing / worker reload):
+  // batches encoded under an older epoch must be re-encoded before dispatch
+  uint64_t epoch() const { return epoch_; }
+  const HostTables& tables() const { return t_; }
+  HostTables& tables_mut() { return t_; }
+  std::mutex& mutex() { return mu_; }
+
+  // string materialisation
+  const PolicyModel& policy() const { return policy_; }
+  const std::vector<std::string>& snapshots() const { return snapshots_; }
+  const std::string& current_snapshot() const { return snapshot_; }
+  const std::string& worker_id(uint32_t slot) const { return worker_ids_[slot]; }
+  uint32_t n_worker_slots() const { return (uint32_t)worker_ids_.size(); }
+  const std::string& topic_raw(uint32_t topic_id) const { return topic_keys_[topic_id]; }
+  std::string mcp_value_string(int field, uint32_t id) const;
+  const std::vector<std::string>& topic_pool_names(uint32_t topic_id) const;
+  uint32_t n_topics() const { return (uint32_t)topic_keys_.size(); }
+
+ private:
+  std::mutex mu_;
+  uint64_t epoch_ = 1;
+  uint32_t max_topics_, max_effcfgs_, threads_;
+  std::string policy_capacity_error_, routing_capacity_error_;
+  std::vector<WorkerRaw> workers_raw_;
+  PolicyModel policy_;
+  RoutingModel routing_;
+  std::string snapshot_;
+  std::vector<std::string> snapshots_;
+  HostTables t_;
+
+  // policy dictionaries
+  Dict d_tenant_, d_cap_, d_pack_, d_actor_, d_risk_, d_req_, d_mcp_[4];
+  StrTable tenant_pol_;   // exact tenant string -> 1 + index in policy_.tenants
+  StrTable label_key_;    // rule label key -> index into label_key_pairs_
+  std::vector<std::vector<std::pair<std::string, uint32_t>>> label_key_pairs_;   // per key: (value, bit)
+  uint64_t label_empty_mask_ = 0;   // bits of pairs whose value is ""
+  std::string default_tenant_trim_;
+  // topic patterns (distinct trimmed pattern -> rules)
+  struct Pattern { Glob glob; std::vector<uint32_t> rules; };
+  std::vector<Pattern> patterns_;
+  Bits vac_topic_;
+  // topics (dynamic)
+  StrTable topic_ids_;
+  std::vector<std::string> topic_keys_;          // raw topic per id (id 0 = "")
+  std::vector<TopicEntry> topic_entries_;
+  std::vector<std::vector<std::string>> topic_pools_;   // original (not deduplicated) lists for messages
+  // effective configs (dynamic)
+  StrTable effcfg_ids_;
+  std::vector<EffSafety> effcfgs_;               // index = id (0 unused)
+  std::vector<uint8_t> effcfg_ok_;
+  struct EffGlobs { std::vector<Glob> denied, allowed; bool has_allowed = false; };
+  std::vector<EffGlobs> eff_globs_;
+  // routing dictionaries
+  Dict d_pool_;
+  StrTable routing_topics_;   // raw topic -> index in routing_.topics
+  // workers
+  std::vector<std::string> worker_ids_;
+  StrTable worker_slot_;      // worker_id -> slot (last wins)
+  StrTable place_pair_;       // key '\0' value -> bit   (value non-empty)
+  StrTable place_key_;        // key -> bit E_k ("labels non-empty and k absent-or-empty")
+  uint32_t place_any_bit_ = 0; // bit "worker has >= 1 label"
+  uint32_t place_bits_ = 0;
+
+  void compile_policy();
+  void compile_routing();
+  void compile_mcp_tables();
+  int compile_workers(std::string& err);
+  void rebuild_topics();
+  uint32_t add_topic(sv raw);          // under mu_
+  uint32_t add_effcfg(sv payload);     // under mu_
+  void topic_row(sv trimmed, Bits& out) const;
+  void eff_topic_fill(uint32_t cfg, uint32_t topic_id);
+  void encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
+                    std::vector<uint32_t>& misses) const;
+  void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss) const;
+};
+
+// test hooks (also exported through the C ABI as cordum_test_*)
+int test_glob(sv pattern, sv name);   // 1 match, 0 no, -1 malformed
+
+}  // namespace cordum

@@ -1,0 +1,407 @@
+// kernels.cu — sm_100a kernels of the policy-gate + dispatch path.
+//
+//   worker_pool_kernel   per heartbeat epoch: load score / overload per worker, per-pool argmin
+//                        (strategy_least_loaded.go:157-159 loadScore, :177-193 isOverloaded)
+//   dispatch_kernel      per job batch: bit-parallel first-match over the rule set
+//                        (safety_policy.go:187-206, 259-294), decision mapping + tenant MCP +
+//                        effective-config overlay (kernel.go:187-248), scheduler post-step
+//                        (engine.go:528-530), pool filter + least-loaded pick
+//                        (strategy_least_loaded.go:40-136)
+//
+// Integer / bit work only: no tensor cores (north star).  Mapping to the hardware:
+//   * job columns are column-major; a warp loads 32 consecutive jobs with one coalesced
+//     128 B request per u32 column (256 B per u64 column) through the read-only, no-L1-allocate path
+//   * 8 lanes cooperate on one job (4 jobs per warp at a time): one pass-row segment is
+//     1024 rules = 128 B = exactly one cache line = 8 lanes x one 128-bit load
+//   * rows are gathered through L1/L2 (the tables are a few MB: L2-resident, hot rows L1-resident)
+//   * first match = ballot over the 8 lanes + ffs; routing reductions are shuffles
+//   * decision records are written back coalesced, 16 B per lane
+// IEEE float32 with explicit _rn intrinsics, no fast-math: scores compare exactly like Go's.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cordum_b200.h"
+#include "kernels.h"
+
+#define FULL 0xFFFFFFFFu
+#define KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+namespace {
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_row(const Row16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+__device__ __forceinline__ uint64_t shfl64(unsigned mask, uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(mask, (uint32_t)v, src), hi = __shfl_sync(mask, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl64_xor(unsigned mask, uint64_t v, int lanemask) {
+  uint32_t lo = __shfl_xor_sync(mask, (uint32_t)v, lanemask), hi = __shfl_xor_sync(mask, (uint32_t)(v >> 32), lanemask);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// float32 -> uint32 whose unsigned order equals the float order (no NaN by construction)
+__device__ __forceinline__ uint32_t orderable(float s) {
+  if (s == 0.0f) s = 0.0f;   // -0 -> +0: Go's `<` treats them as equal
+  uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// (key, count-at-minimum-score) pairs form a commutative monoid under this merge
+__device__ __forceinline__ void merge_best(uint64_t& key, uint32_t& cnt, uint64_t k2, uint32_t c2) {
+  uint32_t s1 = (uint32_t)(key >> 32), s2 = (uint32_t)(k2 >> 32);
+  if (k2 == KEY_NONE) return;
+  if (key == KEY_NONE || s2 < s1) { key = k2; cnt = c2; }
+  else if (s2 == s1) { key = k2 < key ? k2 : key; cnt += c2; }
+}
+
+// Lowest rule in this lane's 128-bit slice that survives the per-rule subset tests
+// (requires: containsAll, safety_policy.go:320-330; labels: labelsMatch, :332-345), or -1.
+__device__ __forceinline__ int lowest_passing(uint4 acc, uint4 chk, uint32_t base, const DeviceTables& T, uint64_t req_mask,
+                                              uint64_t lab_mask, bool has_labels) {
+  const uint32_t a[4] = {acc.x, acc.y, acc.z, acc.w};
+  const uint32_t c[4] = {chk.x, chk.y, chk.z, chk.w};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint32_t bits = a[w];
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      uint32_t r = base + w * 32 + b;
+      if (!((c[w] >> b) & 1u)) return (int)r;
+      uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
+      bool ok = ((need & ~req_mask) == 0) && (ln == 0 || (has_labels && (ln & ~lab_mask) == 0));
+      if (ok) return (int)r;
+      bits &= bits - 1;
+    }
+  }
+  return -1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ K2: one CTA per pool
+__global__ void __launch_bounds__(128) worker_pool_kernel(DeviceTables T) {
+  const uint32_t p = blockIdx.x;
+  const uint32_t a = T.pool_off[p], b = T.pool_off[p + 1];
+  __shared__ uint64_t s_key[4];
+  __shared__ uint32_t s_cnt[4];
+  uint64_t best = KEY_NONE;
+  for (uint32_t pos = a + threadIdx.x; pos < b; pos += blockDim.x) {
+    const Load16 L = T.loads[T.pos_slot[pos]];
+    bool over = false;
+    if (L.max_parallel > 0) over = __fdiv_rn(__int2float_rn(L.active), __int2float_rn(L.max_parallel)) >= 0.9f;
+    over = over || L.cpu >= 90.0f || L.gpu >= 90.0f;
+    float score = __fadd_rn(__fadd_rn(__int2float_rn(L.active), __fdiv_rn(L.cpu, 100.0f)), __fdiv_rn(L.gpu, 100.0f));
+    uint64_t key = over ? KEY_NONE : (((uint64_t)orderable(score) << 32) | T.pos_rank[pos]);
+    T.pos_key[pos] = key;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { uint64_t v = shfl64_xor(FULL, best, o); best = v < best ? v : best; }
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
+  __syncthreads();
+  best = s_key[0];
+  for (int w = 1; w < 4; ++w) best = s_key[w] < best ? s_key[w] : best;
+  // second pass: how many workers share the minimum score (tie detection)
+  uint32_t cnt = 0;
+  if (best != KEY_NONE)
+    for (uint32_t pos = a + threadIdx.x; pos < b; pos += blockDim.x) {
+      uint64_t k = T.pos_key[pos];
+      cnt += (k != KEY_NONE && (uint32_t)(k >> 32) == (uint32_t)(best >> 32)) ? 1u : 0u;
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T.pool_best[p] = best;
+    T.pool_mincnt[p] = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+  }
+}
+
+// ------------------------------------------------------------------ fused policy + route
+template <int MODE>
+__global__ void __launch_bounds__(256) dispatch_kernel(KParams P) {
+  const DeviceTables& T = P.t;
+  const JobColumns& C = P.cols;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned g = lane >> 3, sub = lane & 7;
+  const unsigned gmask = 0xFFu << (g * 8);
+  const uint32_t n_tiles = (P.n_jobs + 31u) >> 5;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t rowu4 = T.row_u4;
+
+  for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+    const uint32_t j = tile * 32 + lane;
+    const bool valid = j < P.n_jobs;
+    // ---- coalesced column loads: this lane's own job
+    uint32_t c_tenant = 0, c_tpol = 0, c_topic = 0, c_cap = 0, c_pack = 0, c_actor = 0, c_m0 = 0, c_m1 = 0, c_m2 = 0,
+             c_m3 = 0, c_ppool = 0, c_pwork = 0, c_eff = 0, c_flags = 0;
+    uint64_t c_risk = 0, c_req = 0, c_lab = 0, c_plo = 0, c_phi = 0;
+    if (valid) {
+      c_flags = ld_stream_u32(C.flags + j);
+      c_topic = ld_stream_u32(C.topic + j);
+      if (MODE != CORDUM_MODE_ROUTE_ONLY) {
+        c_tenant = ld_stream_u32(C.tenant + j); c_tpol = ld_stream_u32(C.tenant_pol + j);
+        c_cap = ld_stream_u32(C.capability + j); c_pack = ld_stream_u32(C.pack + j); c_actor = ld_stream_u32(C.actor + j);
+        c_m0 = ld_stream_u32(C.mcp[0] + j); c_m1 = ld_stream_u32(C.mcp[1] + j);
+        c_m2 = ld_stream_u32(C.mcp[2] + j); c_m3 = ld_stream_u32(C.mcp[3] + j);
+        c_eff = ld_stream_u32(C.effcfg + j);
+        c_risk = ld_stream_u64(C.risk_mask + j); c_lab = ld_stream_u64(C.lab_mask + j);
+      }
+      c_req = ld_stream_u64(C.req_mask + j);
+      if (MODE != CORDUM_MODE_POLICY_ONLY) {
+        c_ppool = ld_stream_u32(C.pref_pool + j); c_pwork = ld_stream_u32(C.pref_worker + j);
+        c_plo = ld_stream_u64(C.place_lo + j); c_phi = ld_stream_u64(C.place_hi + j);
+      }
+    }
+    uint32_t my_head = 0, my_reason = 0;   // head: decision | sched<<8 | flags<<16 | route<<24
+    int my_rule = -1, my_slot = -1;
+
+#pragma unroll 1
+    for (int round = 0; round < 8; ++round) {
+      const int src = round * 4 + (int)g;   // lane owning the job this 8-lane group works on now
+      const bool jv = __shfl_sync(FULL, (int)valid, src) != 0;
+      const uint32_t flags = __shfl_sync(FULL, c_flags, src);
+      const uint32_t topic = __shfl_sync(FULL, c_topic, src);
+      const uint64_t req_mask = shfl64(FULL, c_req, src);
+      uint32_t tenant = 0, tpol = 0, cap = 0, pack = 0, actor = 0, eff = 0, mid[4] = {0, 0, 0, 0};
+      uint64_t risk = 0, lab = 0;
+      if (MODE != CORDUM_MODE_ROUTE_ONLY) {
+        tenant = __shfl_sync(FULL, c_tenant, src); tpol = __shfl_sync(FULL, c_tpol, src);
+        cap = __shfl_sync(FULL, c_cap, src); pack = __shfl_sync(FULL, c_pack, src); actor = __shfl_sync(FULL, c_actor, src);
+        mid[0] = __shfl_sync(FULL, c_m0, src); mid[1] = __shfl_sync(FULL, c_m1, src);
+        mid[2] = __shfl_sync(FULL, c_m2, src); mid[3] = __shfl_sync(FULL, c_m3, src);
+        eff = __shfl_sync(FULL, c_eff, src);
+        risk = shfl64(FULL, c_risk, src); lab = shfl64(FULL, c_lab, src);
+      }
+      uint32_t ppool = 0, pwork = 0;
+      uint64_t plo = 0, phi = 0;
+      if (MODE != CORDUM_MODE_POLICY_ONLY) {
+        ppool = __shfl_sync(FULL, c_ppool, src); pwork = __shfl_sync(FULL, c_pwork, src);
+        plo = shfl64(FULL, c_plo, src); phi = shfl64(FULL, c_phi, src);
+      }
+
+      uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
+      int rule = -1, slot = -1;
+
+      if (jv) {
+        // =============================================================== policy
+        if (MODE != CORDUM_MODE_ROUTE_ONLY) {
+          if (MODE == CORDUM_MODE_POLICY_AND_ROUTE && (flags & JF_APPROVED)) {
+            // engine.go:484-522: stored approval + matching hash (host-verified): policy skipped
+            dec = sched = CORDUM_DEC_ALLOW; reason = CORDUM_REASON_APPROVAL_GRANTED; rflags = CORDUM_F_APPROVED_BYPASS;
+          } else if (flags & JF_TOPIC_MISSING) {
+            dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_MISSING_TOPIC;          // kernel.go:171-173
+          } else if (flags & JF_TOPIC_UNSUPPORTED) {
+            dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_UNSUPPORTED_TOPIC;      // kernel.go:174-176
+          } else {
+            const bool mcp_used = flags & JF_MCP_USED, has_labels = flags & JF_HAS_LABELS;
+            const Row16* p_combo = T.row_combo + (size_t)(flags & JF_COMBO_MASK) * rowu4 + sub;
+            const Row16* p_tenant = T.row_tenant + (size_t)tenant * rowu4 + sub;
+            const Row16* p_topic = T.row_topic + (size_t)topic * rowu4 + sub;
+            const Row16* p_cap = T.row_cap + (size_t)cap * rowu4 + sub;
+            const Row16* p_pack = T.row_pack + (size_t)pack * rowu4 + sub;
+            const Row16* p_actor = T.row_actor + (size_t)actor * rowu4 + sub;
+            int first = -1;
+            for (uint32_t seg = 0; seg < T.n_seg; ++seg) {
+              const uint32_t so = seg * CORDUM_SEG_U4;
+              // issue the independent gathers together (memory-level parallelism), then combine
+              uint4 r0 = ld_row(p_combo + so), r1 = ld_row(p_tenant + so), r2 = ld_row(p_topic + so),
+                    r3 = ld_row(p_cap + so), r4 = ld_row(p_pack + so), r5 = ld_row(p_actor + so);
+              uint4 rk;
+              if (risk == 0) rk = ld_row(T.row_risk + so + sub);
+              else {
+                rk = make_uint4(0, 0, 0, 0);
+                for (uint64_t m = risk; m; m &= m - 1)   // containsAny: OR over the job's tags (:308-318)
+                  rk = or4(rk, ld_row(T.row_risk + (size_t)(1 + (__ffsll((long long)m) - 1)) * rowu4 + so + sub));
+              }
+              uint4 acc = and4(and4(and4(r0, r1), and4(r2, r3)), and4(and4(r4, r5), rk));
+              if (mcp_used) {   // mcpMatch (:365-382)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) acc = and4(acc, ld_row(T.row_mcp[f] + (size_t)mid[f] * rowu4 + so + sub));
+              }
+              int local = -1;
+              if (acc.x | acc.y | acc.z | acc.w)
+                local = lowest_passing(acc, ld_row(T.row_check + so + sub), seg * CORDUM_SEG_RULES + sub * 128u, T, req_mask,
+                                       lab, has_labels);
+              const unsigned bal = __ballot_sync(gmask, local >= 0);
+              if (bal) { first = __shfl_sync(gmask, local, __ffs(bal) - 1); break; }   // lowest lane = lowest rule
+            }
+            rule = first;
+            uint32_t code = CORDUM_DEC_ALLOW;
+            bool hascons = false;
+            if (first >= 0) { uint8_t rd = __ldg(T.rule_dec + first); code = rd & 0x7Fu; hascons = rd & 0x80u; }
+            const bool rule_approval = code == CORDUM_DEC_REQUIRE_HUMAN;   // safety_policy.go:200
+            // tenant MCP lists (kernel.go:190-195): exact-tenant entry, first failing field wins
+            uint32_t tm = 0;
+            if (mcp_used && tpol) {
+              const uint8_t* base = T.tenant_mcp + (size_t)(tpol - 1) * 4 * T.mcp_stride;
+              for (int f = 0; f < 4 && !tm; ++f) { uint8_t v = __ldg(base + f * T.mcp_stride + mid[f]); if (v) tm = 1 + f * 2 + (v - 1); }
+              if (tm) code = CORDUM_DEC_DENY;
+            }
+            dec = CORDUM_DEC_ALLOW;                                             // kernel.go:198-215
+            if (code == CORDUM_DEC_DENY) { dec = CORDUM_DEC_DENY; reason = tm ? CORDUM_REASON_TENANT_MCP + (tm - 1) : CORDUM_REASON_RULE; }
+            else if (code == CORDUM_DEC_REQUIRE_HUMAN) { dec = CORDUM_DEC_REQUIRE_HUMAN; reason = CORDUM_REASON_RULE; }
+            else if (code == CORDUM_DEC_THROTTLE) { dec = CORDUM_DEC_THROTTLE; reason = CORDUM_REASON_RULE; }
+            else if (code == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS) dec = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+            else if (hascons) dec = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+            if (eff) {                                                          // kernel.go:218-231
+              const uint8_t tb = __ldg(T.eff_topic + (size_t)eff * T.topic_stride + topic);
+              if (tb & 1) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_DENIED_TOPIC; }
+              if (tb & 2) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC; }
+              if (mcp_used) {
+                const uint8_t* base = T.eff_mcp + (size_t)eff * 4 * T.mcp_stride;
+                uint32_t em = 0;
+                for (int f = 0; f < 4 && !em; ++f) { uint8_t v = __ldg(base + f * T.mcp_stride + mid[f]); if (v) em = 1 + f * 2 + (v - 1); }
+                if (em) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_MCP + (em - 1); }
+              }
+            }
+            const bool approval = rule_approval || dec == CORDUM_DEC_REQUIRE_HUMAN;   // kernel.go:233
+            rflags = CORDUM_F_HAS_SNAPSHOT | (approval ? CORDUM_F_APPROVAL_REQUIRED : 0) | (hascons ? CORDUM_F_CONSTRAINTS : 0);
+            sched = dec;                                                         // engine.go:528-530
+            if (approval && (dec == CORDUM_DEC_ALLOW || dec == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)) sched = CORDUM_DEC_REQUIRE_HUMAN;
+          }
+        }
+        // =============================================================== route
+        const bool do_route = MODE == CORDUM_MODE_ROUTE_ONLY ||
+                              (MODE == CORDUM_MODE_POLICY_AND_ROUTE &&
+                               (sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS));   // engine.go:298-347
+        if (do_route) {
+          if (flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
+          else {
+            const uint32_t off = __ldg(T.topic_pool_off + topic);
+            uint32_t cnt = __ldg(T.topic_pool_cnt + topic);
+            int single = -1;
+            if (ppool) {                                                         // preferred_pool (:50-55)
+              bool found = false;
+              if (ppool != CORDUM_PREF_UNKNOWN)
+                for (uint32_t k = sub; k < cnt; k += CORDUM_GROUP) found |= __ldg(T.pool_list + off + k) == ppool - 1;
+              found = __ballot_sync(gmask, found) != 0;
+              if (!found) route = CORDUM_ROUTE_NO_POOL_PREFERRED;
+              else { single = (int)(ppool - 1); cnt = 1; }
+            }
+            if (route == CORDUM_ROUTE_NOT_ATTEMPTED && cnt == 0) route = CORDUM_ROUTE_NO_POOL_TOPIC;   // :56-58
+            if (route == CORDUM_ROUTE_NOT_ATTEMPTED) {
+              const bool req_any = flags & JF_REQ_NONEMPTY, req_unknown = flags & JF_REQ_UNKNOWN;
+              const uint64_t need_req = req_mask & ~T.req_blank_mask;
+              const uint64_t need_lo = plo, need_hi = phi;
+              const bool labelled = (need_lo | need_hi) != 0 || (flags & JF_PLACE_UNSAT);
+              const bool unsat = flags & JF_PLACE_UNSAT;
+              // pool eligibility: poolSatisfies (:241-265)
+              auto eligible = [&](uint32_t pid) -> bool {
+                if (!req_any) return true;
+                return __ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0;
+              };
+              uint64_t best = KEY_NONE;
+              uint32_t bcnt = 0, total = 0, n_elig = 0;
+              // preferred worker needs its pool to be in the eligible set
+              int pw_pos = -1;
+              uint32_t pw_pool = 0xFFFFFFFFu;
+              bool pw_in_set = false;
+              if (pwork && pwork != CORDUM_PREF_UNKNOWN) {
+                uint32_t p1 = __ldg(T.slot_pos + (pwork - 1));
+                if (p1) { pw_pos = (int)p1 - 1; pw_pool = __ldg(T.pos_pool + pw_pos); }
+              }
+              if (!labelled) {
+                for (uint32_t k = sub; k < cnt; k += CORDUM_GROUP) {
+                  uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
+                  if (!eligible(pid)) continue;
+                  n_elig++;
+                  pw_in_set |= pid == pw_pool;
+                  total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
+                  merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
+                }
+              } else {
+                // placement labels: scan the eligible pools' worker slices (matchesLabels, :161-175)
+                for (uint32_t k = 0; k < cnt; ++k) {
+                  uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
+                  if (!eligible(pid)) continue;
+                  if (sub == 0) n_elig++;
+                  pw_in_set |= pid == pw_pool;
+                  if (unsat) continue;
+                  const uint32_t a = __ldg(T.pool_off + pid), b = __ldg(T.pool_off + pid + 1);
+                  for (uint32_t pos = a + sub; pos < b; pos += CORDUM_GROUP) {
+                    uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
+                    if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
+                    total++;
+                    merge_best(best, bcnt, T.pos_key[pos], 1);
+                  }
+                }
+              }
+              // reduce over the 8 lanes of the group
+#pragma unroll
+              for (int o = 4; o; o >>= 1) {
+                uint64_t k2 = shfl64_xor(gmask, best, o);
+                uint32_t c2 = __shfl_xor_sync(gmask, bcnt, o);
+                merge_best(best, bcnt, k2, c2);
+                total += __shfl_xor_sync(gmask, total, o);
+                n_elig += __shfl_xor_sync(gmask, n_elig, o);
+              }
+              pw_in_set = __ballot_sync(gmask, pw_in_set) != 0;
+              if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;            // :64-66
+              else {
+                bool took_pref = false;
+                if (pw_pos >= 0 && pw_in_set && !unsat) {                         // :73-87
+                  uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
+                  bool lab_ok = (llo & need_lo) == need_lo && (lhi & need_hi) == need_hi;
+                  if (lab_ok && T.pos_key[pw_pos] != KEY_NONE) { took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(pwork - 1); }
+                }
+                if (!took_pref) {
+                  if (best != KEY_NONE) {
+                    route = CORDUM_ROUTE_OK;
+                    slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
+                    if (bcnt > 1) rflags |= CORDUM_F_TIE;
+                  } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;   // :114-119
+                }
+              }
+            }
+          }
+        }
+      }
+      // ---- hand the record to the lane that owns this job (lane L was served in round L>>2 by group L&3)
+      const uint32_t head = dec | (sched << 8) | (rflags << 16) | (route << 24);
+      const int from = (int)(lane & 3) * 8;
+      const uint32_t h2 = __shfl_sync(FULL, head, from), r2 = __shfl_sync(FULL, reason, from);
+      const int ru2 = __shfl_sync(FULL, rule, from), sl2 = __shfl_sync(FULL, slot, from);
+      if ((int)(lane >> 2) == round) { my_head = h2; my_reason = r2; my_rule = ru2; my_slot = sl2; }
+    }
+    if (valid) {   // coalesced 16 B store per lane
+      uint4 rec = make_uint4(my_head, my_reason & 0xFFu, (uint32_t)my_rule, (uint32_t)my_slot);
+      reinterpret_cast<uint4*>(P.out)[j] = rec;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
+cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
+  if (T.n_pools == 0) return cudaSuccess;
+  worker_pool_kernel<<<T.n_pools, 128, 0, s>>>(T);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dispatch(const KParams& P, uint32_t mode, int sm_count, cudaStream_t s) {
+  if (P.n_jobs == 0) return cudaSuccess;
+  const uint32_t tiles = (P.n_jobs + 31u) / 32u;
+  uint32_t blocks = (tiles + 7u) / 8u;                  // 8 warps (tiles) per 256-thread CTA
+  const uint32_t cap = (uint32_t)sm_count * 8u;         // persistent: grid = multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  switch (mode) {
+    case CORDUM_MODE_POLICY_ONLY: dispatch_kernel<CORDUM_MODE_POLICY_ONLY><<<blocks, 256, 0, s>>>(P); break;
+    case CORDUM_MODE_POLICY_AND_ROUTE: dispatch_kernel<CORDUM_MODE_POLICY_AND_ROUTE><<<blocks, 256, 0, s>>>(P); break;
+    case CORDUM_MODE_ROUTE_ONLY: dispatch_kernel<CORDUM_MODE_ROUTE_ONLY><<<blocks, 256, 0, s>>>(P); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}

@@ -1,0 +1,96 @@
+// test_hooks.cpp — host-only access to the table compiler and encoder, for CPU tests.
+//
+// These entry points create a Host (no CUDA involved), load documents, encode envelopes
+// into a caller-provided slab and expose the compiled tables by name, so tests can check
+// the tables + encoding against the oracle without a GPU (tests/table_walk.py re-walks
+// the tables in Python the way kernels.cu does).  They evaluate nothing themselves.
+#include <cstring>
+#include <string>
+
+#include "host.hpp"
+
+using cordum::Host;
+using cordum::HostColumns;
+using cordum::HostTables;
+using cordum::sv;
+
+namespace {
+thread_local std::string t_err;
+constexpr int kU32Cols = 14, kU64Cols = 5;
+inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+}  // namespace
+
+extern "C" {
+
+const char* cordum_test_last_error(void) { return t_err.c_str(); }
+void* cordum_test_host_new(uint32_t max_topics, uint32_t max_effcfgs, uint32_t threads) {
+  return new Host(max_topics, max_effcfgs, threads);
+}
+void cordum_test_host_free(void* h) { delete (Host*)h; }
+int32_t cordum_test_host_policy(void* h, const char* json, uint64_t len) {
+  return ((Host*)h)->load_policy(sv(json ? json : "", json ? len : 0), sv("test"), t_err);
+}
+int32_t cordum_test_host_routing(void* h, const char* json, uint64_t len) {
+  return ((Host*)h)->load_routing(sv(json ? json : "", json ? len : 0), t_err);
+}
+int32_t cordum_test_host_workers(void* h, const cordum_workers* w) { return ((Host*)h)->load_workers(w, t_err); }
+int32_t cordum_test_host_update(void* h, uint32_t n, const uint32_t* slots, const cordum_worker_load* loads) {
+  return ((Host*)h)->update_loads(n, slots, loads, t_err);
+}
+uint64_t cordum_test_slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) + kU64Cols * align16((size_t)n * 8); }
+
+// encode into `slab` (cordum_test_slab_bytes(n) bytes): same layout as a batch's pinned columns
+int32_t cordum_test_host_encode(void* h, const cordum_envelopes* env, uint8_t* slab) {
+  uint32_t n = env->n_jobs;
+  uint32_t* a[kU32Cols];
+  uint64_t* b[kU64Cols];
+  size_t off = 0;
+  for (int i = 0; i < kU32Cols; ++i) { a[i] = (uint32_t*)(slab + off); off += align16((size_t)n * 4); }
+  for (int i = 0; i < kU64Cols; ++i) { b[i] = (uint64_t*)(slab + off); off += align16((size_t)n * 8); }
+  HostColumns c;
+  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
+  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
+  c.effcfg = a[12]; c.flags = a[13];
+  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
+  return ((Host*)h)->encode(env, c, t_err);
+}
+
+// table access by name: returns pointer + byte length (valid until the next load/encode)
+int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint64_t* bytes) {
+  const HostTables& t = ((Host*)h)->tables();
+  std::string n(name);
+#define VEC(nm, v) if (n == nm) { *ptr = (v).data(); *bytes = (v).size() * sizeof((v)[0]); return 0; }
+  VEC("row_tenant", t.row_tenant.data) VEC("row_topic", t.row_topic.data) VEC("row_cap", t.row_cap.data)
+  VEC("row_pack", t.row_pack.data) VEC("row_actor", t.row_actor.data) VEC("row_combo", t.row_combo.data)
+  VEC("row_risk", t.row_risk.data) VEC("row_check", t.row_check.data)
+  VEC("row_mcp0", t.row_mcp[0].data) VEC("row_mcp1", t.row_mcp[1].data) VEC("row_mcp2", t.row_mcp[2].data)
+  VEC("row_mcp3", t.row_mcp[3].data)
+  VEC("rule_req_need", t.rule_req_need) VEC("rule_lab_need", t.rule_lab_need) VEC("rule_dec", t.rule_dec)
+  VEC("tenant_mcp", t.tenant_mcp) VEC("eff_mcp", t.eff_mcp) VEC("eff_topic", t.eff_topic)
+  VEC("topic_pool_off", t.topic_pool_off) VEC("topic_pool_cnt", t.topic_pool_cnt) VEC("pool_list", t.pool_list)
+  VEC("pool_req_mask", t.pool_req_mask) VEC("pool_req_nonempty", t.pool_req_nonempty)
+  VEC("pool_off", t.pool_off) VEC("pos_pool", t.pos_pool) VEC("pos_slot", t.pos_slot) VEC("pos_rank", t.pos_rank)
+  VEC("slot_pos", t.slot_pos) VEC("rank_slot", t.rank_slot) VEC("pos_label_lo", t.pos_label_lo)
+  VEC("pos_label_hi", t.pos_label_hi) VEC("loads", t.loads)
+#undef VEC
+  t_err = "unknown table " + n;
+  return -1;
+}
+uint64_t cordum_test_host_scalar(void* h, const char* name) {
+  const HostTables& t = ((Host*)h)->tables();
+  std::string n(name);
+  if (n == "n_rules") return t.n_rules;
+  if (n == "n_seg") return t.n_seg;
+  if (n == "row_words") return t.row_words;
+  if (n == "mcp_stride") return t.mcp_stride;
+  if (n == "topic_stride") return t.topic_stride;
+  if (n == "n_effcfg") return t.n_effcfg;
+  if (n == "req_blank_mask") return t.req_blank_mask;
+  if (n == "n_pools") return t.n_pools;
+  if (n == "n_pos") return t.n_pos;
+  if (n == "n_slots") return t.n_slots;
+  if (n == "n_topics") return t.row_topic.n_rows;
+  return ~0ull;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+"""Engine: thin Python handle over the C ABI (no logic of its own)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib, policy_io, wire
+
+
+class CordumError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("cordum_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Batch:
+    def __init__(self, eng: "Engine", max_jobs: int):
+        self.eng = eng
+        self.L = eng.L
+        h = C.c_void_p()
+        eng._ck(self.L.cordum_batch_alloc(eng.h, max_jobs, C.byref(h)))
+        self.h = h
+        self.max_jobs = max_jobs
+
+    def free(self):
+        if self.h:
+            self.L.cordum_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return self.L.cordum_batch_size(self.h)
+
+    def encode(self, env):
+        if not isinstance(env, wire.EnvelopeBatch):
+            env = wire.EnvelopeBatch.from_jobs(env)
+        self._env = env   # keep the buffers alive for the duration of the call chain
+        self.eng._ck(self.L.cordum_encode(self.eng.h, self.h, C.addressof(env.struct)))
+        return self
+
+    def dispatch(self, mode=wire.MODE_POLICY_AND_ROUTE) -> np.ndarray:
+        self.eng._ck(self.L.cordum_dispatch(self.eng.h, self.h, mode))
+        return self.results()
+
+    def dispatch_async(self, mode=wire.MODE_POLICY_AND_ROUTE):
+        self.eng._ck(self.L.cordum_dispatch_async(self.eng.h, self.h, mode))
+
+    def wait(self) -> np.ndarray:
+        self.eng._ck(self.L.cordum_batch_wait(self.h))
+        return self.results()
+
+    def dispatch_resident(self, mode=wire.MODE_POLICY_AND_ROUTE):
+        self.eng._ck(self.L.cordum_dispatch_resident(self.eng.h, self.h, mode))
+
+    def fetch(self) -> np.ndarray:
+        self.eng._ck(self.L.cordum_batch_fetch(self.h))
+        return self.results()
+
+    def results(self) -> np.ndarray:
+        n = self.size
+        ptr = self.L.cordum_batch_results(self.h)
+        buf = (C.c_uint8 * (n * wire.DECISION_DTYPE.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=wire.DECISION_DTYPE, count=n)
+
+    def timing(self):
+        t, k = C.c_float(), C.c_float()
+        self.eng._ck(self.L.cordum_batch_timing(self.h, C.byref(t), C.byref(k)))
+        return t.value, k.value
+
+    def _text(self, fn, job: int) -> str:
+        buf = C.create_string_buffer(4096)
+        fn(self.eng.h, self.h, job, buf, len(buf))
+        return buf.value.decode("utf-8", "replace")
+
+    def reason(self, job: int) -> str:
+        return self._text(self.L.cordum_reason, job)
+
+    def subject(self, job: int) -> str:
+        return self._text(self.L.cordum_subject, job)
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_topics: int = 0, max_effcfgs: int = 0, encode_threads: int = 0):
+        self.L = _lib.load()
+        opts = wire.CordumEngineOpts(device, max_topics, max_effcfgs, encode_threads)
+        h = C.c_void_p()
+        rc = self.L.cordum_engine_create(C.byref(opts), C.byref(h))
+        if rc:
+            raise CordumError(rc, self.L.cordum_last_error().decode())
+        self.h = h
+        self._keep = []
+
+    def _ck(self, rc: int):
+        if rc:
+            raise CordumError(rc, self.L.cordum_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.cordum_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_policy(self, policy, snapshot: str = ""):
+        doc = policy if isinstance(policy, (bytes, bytearray)) else policy_io.to_json(policy)
+        snap = snapshot.encode()
+        self._ck(self.L.cordum_policy_load(self.h, bytes(doc), len(doc), snap, len(snap)))
+
+    def load_routing(self, routing):
+        doc = routing if isinstance(routing, (bytes, bytearray)) else policy_io.to_json(routing)
+        self._ck(self.L.cordum_routing_load(self.h, bytes(doc), len(doc)))
+
+    def load_workers(self, workers):
+        wt = workers if isinstance(workers, wire.WorkerTable) else wire.WorkerTable.from_workers(workers)
+        self._workers = wt
+        self._ck(self.L.cordum_workers_load(self.h, C.addressof(wt.struct)))
+
+    def update_workers(self, slots, loads):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        loads = np.ascontiguousarray(loads, dtype=wire.LOAD_DTYPE)
+        self._ck(self.L.cordum_workers_update(self.h, len(slots), slots.ctypes.data, loads.ctypes.data))
+
+    def set_loads_device(self, dptr: int, n_workers: int, stream: int = 0):
+        self._ck(self.L.cordum_workers_set_loads_device(self.h, C.c_void_p(dptr), n_workers, C.c_void_p(stream)))
+
+    def snapshots(self) -> list[str]:
+        buf = C.create_string_buffer(1 << 16)
+        n = C.c_uint32()
+        self._ck(self.L.cordum_policy_snapshots(self.h, buf, len(buf), C.byref(n)))
+        return [s.decode() for s in buf.raw.split(b"\0")[: n.value]]
+
+    def batch(self, max_jobs: int) -> Batch:
+        return Batch(self, max_jobs)
+
+    def rule_id(self, idx: int) -> str:
+        buf = C.create_string_buffer(4096)
+        self.L.cordum_rule_id(self.h, idx, buf, len(buf))
+        return buf.value.decode("utf-8", "replace")
+
+    def rule_constraints(self, idx: int):
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.cordum_rule_constraints_json(self.h, idx, buf, len(buf))
+        return json.loads(buf.value.decode()) if n > 0 else None
+
+    def rule_remediations(self, idx: int):
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.cordum_rule_remediations_json(self.h, idx, buf, len(buf))
+        return json.loads(buf.value.decode()) if n > 0 else []
+
+    def stats(self) -> wire.CordumTableStats:
+        st = wire.CordumTableStats()
+        self._ck(self.L.cordum_stats(self.h, C.byref(st)))
+        return st
+
+    def launch_count(self) -> int:
+        return int(self.L.cordum_launch_count(self.h))

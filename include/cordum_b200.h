@@ -228,6 +228,11 @@ int32_t cordum_batch_wait(cordum_batch* b);
  * last dispatch on this batch are still in HBM; runs the kernels only, no copies. */
 int32_t cordum_dispatch_resident(cordum_engine* e, cordum_batch* b, uint32_t mode);
 
+/* After a resident run: copy the decision records from HBM into the pinned result buffer. */
+int32_t cordum_batch_fetch(cordum_batch* b);
+/* The batch's cudaStream_t, so a harness can bracket launches with its own CUDA events. */
+void* cordum_batch_stream(cordum_batch* b);
+
 uint32_t cordum_batch_size(const cordum_batch* b);
 /* Decision records of the last completed dispatch (pinned host memory, n = batch size). */
 const cordum_decision* cordum_batch_results(const cordum_batch* b);
@@ -260,6 +265,13 @@ int32_t cordum_stats(cordum_engine* e, cordum_table_stats* out);
 
 /* Number of kernels this library has launched on the handle since creation. */
 uint64_t cordum_launch_count(cordum_engine* e);
+
+/* Test hooks: the library's own string primitives (table-compile time semantics), exported so
+ * the test-suite can run them differentially against the oracle.  Not part of the drop-in surface. */
+int32_t cordum_test_glob(const char* pat, uint64_t plen, const char* name, uint64_t nlen); /* 1, 0, -1 malformed */
+void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len);
+int32_t cordum_test_normalize_decision(const char* s, uint64_t n);
+int32_t cordum_test_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,331 @@
+"""CPU re-walk of the compiled tables, mirroring kernels.cu step for step.
+
+TEST INFRASTRUCTURE.  The product evaluates jobs only on the GPU; this module lets the
+CPU test-suite check the table compiler and the encoder (host C++ in
+cordum_b200/csrc/host.cpp) against the oracle without a GPU: it loads the same library,
+pulls the host-side tables and encoded columns out through the cordum_test_host_* hooks
+and applies the kernel's algorithm (AND of pass-rows, first set bit, per-rule subset
+tests, verdict tables, per-pool argmin) in plain Python/numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from cordum_b200 import _lib, policy_io, wire
+
+JF_COMBO_MASK, JF_MCP_USED, JF_HAS_LABELS, JF_APPROVED = 0x7, 0x8, 0x10, 0x20
+JF_REQ_NONEMPTY, JF_REQ_UNKNOWN, JF_PLACE_UNSAT = 0x40, 0x80, 0x100
+JF_TOPIC_MISSING, JF_TOPIC_UNSUPPORTED, JF_TOPIC_RAW_EMPTY = 0x200, 0x400, 0x800
+PREF_UNKNOWN = 0xFFFFFFFF
+KEY_NONE = (1 << 64) - 1
+U32_COLS = ["tenant", "tenant_pol", "topic", "capability", "pack", "actor", "mcp0", "mcp1", "mcp2", "mcp3",
+            "pref_pool", "pref_worker", "effcfg", "flags"]
+U64_COLS = ["risk_mask", "req_mask", "lab_mask", "place_lo", "place_hi"]
+TABLES = {
+    "row_tenant": np.uint32, "row_topic": np.uint32, "row_cap": np.uint32, "row_pack": np.uint32,
+    "row_actor": np.uint32, "row_combo": np.uint32, "row_risk": np.uint32, "row_check": np.uint32,
+    "row_mcp0": np.uint32, "row_mcp1": np.uint32, "row_mcp2": np.uint32, "row_mcp3": np.uint32,
+    "rule_req_need": np.uint64, "rule_lab_need": np.uint64, "rule_dec": np.uint8, "tenant_mcp": np.uint8,
+    "eff_mcp": np.uint8, "eff_topic": np.uint8, "topic_pool_off": np.uint32, "topic_pool_cnt": np.uint32,
+    "pool_list": np.uint32, "pool_req_mask": np.uint64, "pool_req_nonempty": np.uint8, "pool_off": np.uint32,
+    "pos_pool": np.uint32, "pos_slot": np.uint32, "pos_rank": np.uint32, "slot_pos": np.uint32, "rank_slot": np.uint32,
+    "pos_label_lo": np.uint64, "pos_label_hi": np.uint64, "loads": wire.LOAD_DTYPE,
+}
+SCALARS = ["n_rules", "n_seg", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
+           "n_pos", "n_slots", "n_topics"]
+
+
+def _align16(x):
+    return (x + 15) & ~15
+
+
+def _orderable(score: np.float32) -> int:
+    if score == 0:
+        score = np.float32(0.0)
+    b = int(np.float32(score).view(np.uint32))
+    return (~b) & 0xFFFFFFFF if b & 0x80000000 else b | 0x80000000
+
+
+class HostHarness:
+    """Host (table compiler + encoder) without a GPU."""
+
+    def __init__(self, policy=None, routing=None, workers=None, threads=2):
+        self.L = _lib.load()
+        self.h = C.c_void_p(self.L.cordum_test_host_new(0, 0, threads))
+        self.load_policy(policy)
+        self.load_routing(routing)
+        self.load_workers(workers or [])
+
+    def close(self):
+        if self.h:
+            self.L.cordum_test_host_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise RuntimeError("host: %s" % self.L.cordum_test_last_error().decode())
+
+    def load_policy(self, policy):
+        doc = policy_io.to_json(policy)
+        self._ck(self.L.cordum_test_host_policy(self.h, doc, len(doc)))
+
+    def load_routing(self, routing):
+        doc = policy_io.to_json(routing)
+        self._ck(self.L.cordum_test_host_routing(self.h, doc, len(doc)))
+
+    def load_workers(self, workers):
+        wt = workers if isinstance(workers, wire.WorkerTable) else wire.WorkerTable.from_workers(workers)
+        self._wt = wt
+        self._ck(self.L.cordum_test_host_workers(self.h, C.addressof(wt.struct)))
+
+    def update_workers(self, slots, loads):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        loads = np.ascontiguousarray(loads, dtype=wire.LOAD_DTYPE)
+        self._ck(self.L.cordum_test_host_update(self.h, len(slots), slots.ctypes.data, loads.ctypes.data))
+
+    def encode(self, env) -> dict:
+        if not isinstance(env, wire.EnvelopeBatch):
+            env = wire.EnvelopeBatch.from_jobs(env)
+        n = env.n_jobs
+        slab = np.zeros(int(self.L.cordum_test_slab_bytes(n)) + 16, dtype=np.uint8)
+        self._ck(self.L.cordum_test_host_encode(self.h, C.addressof(env.struct), slab.ctypes.data))
+        cols, off = {}, 0
+        for name in U32_COLS:
+            cols[name] = slab[off: off + 4 * n].view(np.uint32).copy()
+            off += _align16(4 * n)
+        for name in U64_COLS:
+            cols[name] = slab[off: off + 8 * n].view(np.uint64).copy()
+            off += _align16(8 * n)
+        return cols
+
+    def tables(self) -> dict:
+        t = {}
+        for name, dt in TABLES.items():
+            ptr, nbytes = C.c_void_p(), C.c_uint64()
+            self._ck(self.L.cordum_test_host_table(self.h, name.encode(), C.byref(ptr), C.byref(nbytes)))
+            if nbytes.value == 0:
+                t[name] = np.zeros(0, dtype=dt)
+            else:
+                buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
+                t[name] = np.frombuffer(buf, dtype=dt).copy()
+        for s in SCALARS:
+            t[s] = int(self.L.cordum_test_host_scalar(self.h, s.encode()))
+        return t
+
+    def evaluate(self, env, mode=wire.MODE_POLICY_AND_ROUTE) -> np.ndarray:
+        cols = self.encode(env)      # encode first: it may register new topics / effective configs
+        return walk(self.tables(), cols, mode)
+
+
+def _worker_pools(T):
+    """worker_pool_kernel: per-pos key, per-pool best and count at the minimum score."""
+    n_pos, n_pools = T["n_pos"], T["n_pools"]
+    key = [KEY_NONE] * max(n_pos, 1)
+    for pos in range(n_pos):
+        L = T["loads"][T["pos_slot"][pos]]
+        active, maxp = np.float32(int(L["active_jobs"])), int(L["max_parallel_jobs"])
+        cpu, gpu = np.float32(L["cpu_load"]), np.float32(L["gpu_utilization"])
+        over = False
+        if maxp > 0:
+            over = np.float32(active / np.float32(maxp)) >= np.float32(0.9)
+        over = over or cpu >= np.float32(90) or gpu >= np.float32(90)
+        score = np.float32(np.float32(active + np.float32(cpu / np.float32(100))) + np.float32(gpu / np.float32(100)))
+        key[pos] = KEY_NONE if over else (_orderable(score) << 32) | int(T["pos_rank"][pos])
+    best, cnt = [KEY_NONE] * max(n_pools, 1), [0] * max(n_pools, 1)
+    for p in range(n_pools):
+        a, b = int(T["pool_off"][p]), int(T["pool_off"][p + 1])
+        ks = key[a:b]
+        if ks:
+            best[p] = min(ks)
+        if best[p] != KEY_NONE:
+            cnt[p] = sum(1 for k in ks if k != KEY_NONE and (k >> 32) == (best[p] >> 32))
+    return key, best, cnt
+
+
+def _merge(key, cnt, k2, c2):
+    if k2 == KEY_NONE:
+        return key, cnt
+    if key == KEY_NONE or (k2 >> 32) < (key >> 32):
+        return k2, c2
+    if (k2 >> 32) == (key >> 32):
+        return min(key, k2), cnt + c2
+    return key, cnt
+
+
+def walk(T, cols, mode) -> np.ndarray:
+    n = len(cols["flags"])
+    out = np.zeros(n, dtype=wire.DECISION_DTYPE)
+    out["rule_idx"] = -1
+    out["worker_slot"] = -1
+    W = T["row_words"]
+    rows = {k: T[k].reshape(-1, W) if len(T[k]) else np.zeros((0, W), np.uint32)
+            for k in ("row_tenant", "row_topic", "row_cap", "row_pack", "row_actor", "row_combo", "row_risk", "row_check",
+                      "row_mcp0", "row_mcp1", "row_mcp2", "row_mcp3")}
+    key, pool_best, pool_cnt = _worker_pools(T)
+    stride = T["mcp_stride"]
+    for j in range(n):
+        flags = int(cols["flags"][j])
+        topic = int(cols["topic"][j])
+        mid = [int(cols["mcp%d" % f][j]) for f in range(4)]
+        req_mask = int(cols["req_mask"][j])
+        dec = sched = rflags = reason = route = 0
+        rule, slot = -1, -1
+        if mode != wire.MODE_ROUTE_ONLY:
+            if mode == wire.MODE_POLICY_AND_ROUTE and flags & JF_APPROVED:
+                dec = sched = wire.DEC_ALLOW
+                reason, rflags = wire.REASON_APPROVAL_GRANTED, wire.F_APPROVED_BYPASS
+            elif flags & JF_TOPIC_MISSING:
+                dec = sched = wire.DEC_DENY
+                reason = wire.REASON_MISSING_TOPIC
+            elif flags & JF_TOPIC_UNSUPPORTED:
+                dec = sched = wire.DEC_DENY
+                reason = wire.REASON_UNSUPPORTED_TOPIC
+            else:
+                mcp_used, has_labels = bool(flags & JF_MCP_USED), bool(flags & JF_HAS_LABELS)
+                acc = (rows["row_combo"][flags & JF_COMBO_MASK] & rows["row_tenant"][cols["tenant"][j]]
+                       & rows["row_topic"][topic] & rows["row_cap"][cols["capability"][j]]
+                       & rows["row_pack"][cols["pack"][j]] & rows["row_actor"][cols["actor"][j]])
+                risk = int(cols["risk_mask"][j])
+                if risk == 0:
+                    rk = rows["row_risk"][0]
+                else:
+                    rk = np.zeros(W, np.uint32)
+                    for b in range(64):
+                        if risk >> b & 1:
+                            rk = rk | rows["row_risk"][1 + b]
+                acc = acc & rk
+                if mcp_used:
+                    for f in range(4):
+                        acc = acc & rows["row_mcp%d" % f][mid[f]]
+                chk = rows["row_check"][0]
+                lab = int(cols["lab_mask"][j])
+                first = -1
+                for w in np.nonzero(acc)[0]:
+                    bits = int(acc[w])
+                    while bits:
+                        b = (bits & -bits).bit_length() - 1
+                        r = int(w) * 32 + b
+                        if not (int(chk[w]) >> b & 1):
+                            first = r
+                            break
+                        need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
+                        if (need & ~req_mask) == 0 and (ln == 0 or (has_labels and (ln & ~lab) == 0)):
+                            first = r
+                            break
+                        bits &= bits - 1
+                    if first >= 0:
+                        break
+                rule = first
+                code, hascons = wire.DEC_ALLOW, False
+                if first >= 0:
+                    rd = int(T["rule_dec"][first])
+                    code, hascons = rd & 0x7F, bool(rd & 0x80)
+                rule_approval = code == wire.DEC_REQUIRE_HUMAN
+                tm = 0
+                tpol = int(cols["tenant_pol"][j])
+                if mcp_used and tpol:
+                    base = (tpol - 1) * 4 * stride
+                    for f in range(4):
+                        v = int(T["tenant_mcp"][base + f * stride + mid[f]])
+                        if v:
+                            tm = 1 + f * 2 + (v - 1)
+                            break
+                    if tm:
+                        code = wire.DEC_DENY
+                dec = wire.DEC_ALLOW
+                if code == wire.DEC_DENY:
+                    dec, reason = wire.DEC_DENY, (wire.REASON_TENANT_MCP + tm - 1) if tm else wire.REASON_RULE
+                elif code == wire.DEC_REQUIRE_HUMAN:
+                    dec, reason = wire.DEC_REQUIRE_HUMAN, wire.REASON_RULE
+                elif code == wire.DEC_THROTTLE:
+                    dec, reason = wire.DEC_THROTTLE, wire.REASON_RULE
+                elif code == wire.DEC_ALLOW_WITH_CONSTRAINTS or hascons:
+                    dec = wire.DEC_ALLOW_WITH_CONSTRAINTS
+                eff = int(cols["effcfg"][j])
+                if eff:
+                    tb = int(T["eff_topic"][eff * T["topic_stride"] + topic])
+                    if tb & 1:
+                        dec, reason = wire.DEC_DENY, wire.REASON_EFF_DENIED_TOPIC
+                    if tb & 2:
+                        dec, reason = wire.DEC_DENY, wire.REASON_EFF_NOT_ALLOWED_TOPIC
+                    if mcp_used:
+                        base = eff * 4 * stride
+                        for f in range(4):
+                            v = int(T["eff_mcp"][base + f * stride + mid[f]])
+                            if v:
+                                dec, reason = wire.DEC_DENY, wire.REASON_EFF_MCP + f * 2 + (v - 1)
+                                break
+                approval = rule_approval or dec == wire.DEC_REQUIRE_HUMAN
+                rflags = wire.F_HAS_SNAPSHOT | (wire.F_APPROVAL_REQUIRED if approval else 0) | (wire.F_CONSTRAINTS if hascons else 0)
+                sched = dec
+                if approval and dec in (wire.DEC_ALLOW, wire.DEC_ALLOW_WITH_CONSTRAINTS):
+                    sched = wire.DEC_REQUIRE_HUMAN
+        do_route = mode == wire.MODE_ROUTE_ONLY or (mode == wire.MODE_POLICY_AND_ROUTE and sched in (wire.DEC_ALLOW, wire.DEC_ALLOW_WITH_CONSTRAINTS))
+        if do_route:
+            if flags & JF_TOPIC_RAW_EMPTY:
+                route = wire.ROUTE_MISSING_TOPIC
+            else:
+                off, cnt = int(T["topic_pool_off"][topic]), int(T["topic_pool_cnt"][topic])
+                pools = [int(p) for p in T["pool_list"][off:off + cnt]]
+                ppool = int(cols["pref_pool"][j])
+                if ppool:
+                    if ppool == PREF_UNKNOWN or (ppool - 1) not in pools:
+                        route = wire.ROUTE_NO_POOL_PREFERRED
+                    else:
+                        pools = [ppool - 1]
+                if route == 0 and not pools:
+                    route = wire.ROUTE_NO_POOL_TOPIC
+                if route == 0:
+                    req_any, req_unknown = bool(flags & JF_REQ_NONEMPTY), bool(flags & JF_REQ_UNKNOWN)
+                    need_req = req_mask & ~T["req_blank_mask"]
+                    need_lo, need_hi = int(cols["place_lo"][j]), int(cols["place_hi"][j])
+                    unsat = bool(flags & JF_PLACE_UNSAT)
+                    labelled = (need_lo | need_hi) != 0 or unsat
+
+                    def elig(p):
+                        if not req_any:
+                            return True
+                        return bool(T["pool_req_nonempty"][p]) and not req_unknown and (need_req & ~int(T["pool_req_mask"][p])) == 0
+
+                    el = [p for p in pools if elig(p)]
+                    best, bcnt, total = KEY_NONE, 0, 0
+                    if not labelled:
+                        for p in el:
+                            total += int(T["pool_off"][p + 1]) - int(T["pool_off"][p])
+                            best, bcnt = _merge(best, bcnt, pool_best[p], pool_cnt[p])
+                    elif not unsat:
+                        for p in el:
+                            for pos in range(int(T["pool_off"][p]), int(T["pool_off"][p + 1])):
+                                if (int(T["pos_label_lo"][pos]) & need_lo) != need_lo or (int(T["pos_label_hi"][pos]) & need_hi) != need_hi:
+                                    continue
+                                total += 1
+                                best, bcnt = _merge(best, bcnt, key[pos], 1)
+                    if not el:
+                        route = wire.ROUTE_NO_POOL_REQUIRES
+                    else:
+                        took = False
+                        pw = int(cols["pref_worker"][j])
+                        if pw and pw != PREF_UNKNOWN:
+                            p1 = int(T["slot_pos"][pw - 1])
+                            if p1 and int(T["pos_pool"][p1 - 1]) in el and not unsat:
+                                pos = p1 - 1
+                                lab_ok = (int(T["pos_label_lo"][pos]) & need_lo) == need_lo and (int(T["pos_label_hi"][pos]) & need_hi) == need_hi
+                                if lab_ok and key[pos] != KEY_NONE:
+                                    took, route, slot = True, wire.ROUTE_OK_PREFERRED, pw - 1
+                        if not took:
+                            if best != KEY_NONE:
+                                route, slot = wire.ROUTE_OK, int(T["rank_slot"][best & 0xFFFFFFFF])
+                                if bcnt > 1:
+                                    rflags |= wire.F_TIE
+                            else:
+                                route = wire.ROUTE_POOL_OVERLOADED if total > 0 else wire.ROUTE_NO_WORKERS
+        out[j] = (dec, sched, rflags, route, reason, (0, 0, 0), rule, slot)
+    return out

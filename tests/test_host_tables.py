@@ -1,0 +1,117 @@
+"""CPU tests of the PRODUCT's host side (table compiler + encoder, cordum_b200/csrc/host.cpp):
+the compiled tables + encoded columns, re-walked the way kernels.cu walks them
+(tests/table_walk.py), must reproduce the oracle's decision records bit for bit.
+No GPU, no compute through the C ABI's dispatch calls."""
+import numpy as np
+import pytest
+
+import kats
+import oracle_lib
+import table_walk
+from cordum_b200 import synth, wire
+
+FIELDS = ("decision", "sched_decision", "flags", "route_status", "reason_code", "rule_idx", "worker_slot")
+
+
+def assert_same(got, want, what=""):
+    for f in FIELDS:
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert len(bad) == 0, "%s field %s differs at jobs %s: got %s want %s" % (
+            what, f, bad[:8], got[f][bad[:8]], want[f][bad[:8]])
+
+
+@pytest.mark.parametrize("case", kats.CASES, ids=[c["name"] for c in kats.CASES])
+def test_tables_reproduce_reference_kats(case):
+    h = table_walk.HostHarness(case["policy"], case["routing"], case["workers"])
+    o = oracle_lib.Oracle(case["policy"], case["routing"], case["workers"])
+    env = wire.EnvelopeBatch.from_jobs([case["job"]])
+    assert_same(h.evaluate(env, case["mode"]), o.eval(env, case["mode"]), case["name"])
+
+
+@pytest.mark.parametrize("name,n,mode", [("tiny", 2000, wire.MODE_POLICY_AND_ROUTE), ("tiny", 500, wire.MODE_POLICY_ONLY),
+                                         ("tiny", 500, wire.MODE_ROUTE_ONLY), ("c2", 1500, wire.MODE_POLICY_AND_ROUTE)])
+def test_tables_match_oracle_on_synthetic(name, n, mode):
+    cfg = synth.make_config(name, n)
+    h = table_walk.HostHarness(cfg.policy, cfg.routing, cfg.workers)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    want = o.eval(cfg.jobs, mode, threads=4)
+    assert_same(h.evaluate(cfg.jobs, mode), want, name)
+
+
+def test_tables_match_oracle_with_ties_and_load_updates():
+    spec = synth.Spec(**{**synth.SPECS["tiny"].__dict__, "tie_fraction": 0.5, "seed": 11})
+    cfg = synth.make_config(spec)
+    h = table_walk.HostHarness(cfg.policy, cfg.routing, cfg.workers)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    want = o.eval(cfg.jobs, wire.MODE_POLICY_AND_ROUTE)
+    assert (want["flags"] & wire.F_TIE).astype(bool).sum() > 20
+    assert_same(h.evaluate(cfg.jobs), want, "ties")
+    # heartbeat deltas: new loads for a third of the workers
+    rng = np.random.default_rng(1)
+    slots = np.arange(0, cfg.workers.n_workers, 3, dtype=np.uint32)
+    loads = np.zeros(len(slots), dtype=wire.LOAD_DTYPE)
+    loads["active_jobs"] = rng.integers(0, 6, len(slots))
+    loads["max_parallel_jobs"] = rng.choice([0, 4, 8], len(slots))
+    loads["cpu_load"] = (rng.random(len(slots)) * 100).astype(np.float32)
+    loads["gpu_utilization"] = (rng.random(len(slots)) * 100).astype(np.float32)
+    h.update_workers(slots, loads)
+    o.update_workers(slots, loads)
+    assert_same(h.evaluate(cfg.jobs), o.eval(cfg.jobs, wire.MODE_POLICY_AND_ROUTE), "after heartbeat deltas")
+
+
+def test_approved_replay_and_c5():
+    c5 = kats.golden("c5_demo_guardrails.json")
+    jobs, workers, kind = synth.make_c5(3000)
+    h = table_walk.HostHarness(c5["policy"], c5["routing"], workers)
+    o = oracle_lib.Oracle(c5["policy"], c5["routing"], workers)
+    got = h.evaluate(jobs)
+    assert_same(got, o.eval(jobs), "c5")
+    # SURVEY §8d config 5 expectations
+    assert (got["sched_decision"][kind == 0] == wire.DEC_REQUIRE_HUMAN).all()
+    assert (got["decision"][kind == 1] == wire.DEC_ALLOW).all() and (got["rule_idx"][kind == 1] == -1).all()
+    assert (got["decision"][kind == 2] == wire.DEC_DENY).all()
+    assert (got["decision"][kind == 3] == wire.DEC_ALLOW).all() and (got["route_status"][kind == 3] == wire.ROUTE_OK).all()
+    replay = jobs.with_approved(kind == 0)
+    got2 = h.evaluate(replay)
+    assert_same(got2, o.eval(replay), "c5 replay")
+    assert (got2["route_status"][kind == 0] == wire.ROUTE_OK).all()
+
+
+def test_new_topics_and_effective_configs_after_load():
+    """Dictionaries grow on first sight of a topic / effective config (dynamic tables)."""
+    policy = {"default_tenant": "default",
+              "rules": [{"id": "r", "decision": "deny", "reason": "x", "match": {"topics": ["job.a.*"]}}]}
+    routing = {"topics": {"job.b.one": ["p"]}, "pools": {"p": {}}}
+    workers = [kats.hb("w", "p")]
+    h = table_walk.HostHarness(policy, routing, workers)
+    o = oracle_lib.Oracle(policy, routing, workers)
+    jobs = [{"topic": "job.a.new1"}, {"topic": "job.b.one"}, {"topic": " job.a.padded "},
+            {"topic": "job.b.one", "effective_config": b'{"safety":{"denied_topics":["job.b.*"]}}'},
+            {"topic": "job.b.one", "effective_config": b'{"safety":{"allowed_topics":["job.c.*"]}}'},
+            {"topic": "job.c.x", "effective_config": b'{"safety":{"allowed_topics":["job.c.*"]}}'},
+            {"topic": "job.b.one", "labels": {"mcp.server": "evil"},
+             "effective_config": b'{"data":{"safety":{"mcp":{"deny_servers":["EVIL"]}}}}'},
+            {"topic": "job.b.one", "effective_config": b'not json'}]
+    for _ in range(2):   # second pass: everything already in the dictionaries
+        assert_same(h.evaluate(jobs), o.eval(jobs), "dynamic")
+
+
+def test_policy_reload_changes_answers():
+    routing = {"topics": {"job.x": ["p"]}, "pools": {"p": {}}}
+    h = table_walk.HostHarness({"rules": [{"id": "a", "decision": "deny", "match": {"topics": ["job.x"]}}]}, routing,
+                               [kats.hb("w", "p")])
+    jobs = [{"topic": "job.x"}]
+    assert h.evaluate(jobs)["decision"][0] == wire.DEC_DENY
+    h.load_policy({"rules": [{"id": "a", "decision": "allow", "match": {"topics": ["job.x"]}}]})
+    r = h.evaluate(jobs)
+    assert r["decision"][0] == wire.DEC_ALLOW and r["route_status"][0] == wire.ROUTE_OK
+    h.load_policy(None)   # nil policy: allow-all
+    assert h.evaluate(jobs)["decision"][0] == wire.DEC_ALLOW
+
+
+def test_capacity_errors_fail_closed():
+    rules = [{"id": "r%d" % i, "decision": "deny", "match": {"risk_tags": ["tag%d" % i]}} for i in range(65)]
+    h = table_walk.HostHarness()
+    with pytest.raises(RuntimeError, match="64 distinct risk tags"):
+        h.load_policy({"rules": rules})
+    h.load_policy({"rules": rules[:64]})   # exactly at capacity is fine
