@@ -18,7 +18,7 @@ API = [
     "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
     "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
     "cordum_workers_set_loads_device", "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
-    "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_batch_fetch", "cordum_batch_stream",
+    "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
     "cordum_launch_count", "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
@@ -53,7 +53,7 @@ def load() -> C.CDLL:
     L.cordum_batch_free.argtypes = [vp]
     L.cordum_batch_free.restype = None
     L.cordum_encode.argtypes = [vp, vp, vp]
-    for f in ("cordum_dispatch", "cordum_dispatch_async", "cordum_dispatch_resident"):
+    for f in ("cordum_dispatch", "cordum_dispatch_async", "cordum_dispatch_resident", "cordum_dispatch_resident_async"):
         getattr(L, f).argtypes = [vp, vp, u32]
     L.cordum_batch_wait.argtypes = [vp]
     L.cordum_batch_fetch.argtypes = [vp]

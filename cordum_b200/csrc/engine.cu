@@ -56,6 +56,7 @@ inline size_t slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) 
 
 }  // namespace
 
+struct cordum_batch;
 struct cordum_engine {
   int device = 0;
   int sm_count = 148;
@@ -64,7 +65,7 @@ struct cordum_engine {
   bool failed = false;           // sticky CUDA failure
   std::string fail_msg;
   cudaStream_t s_tables = nullptr;
-  cudaEvent_t ev_tables = nullptr;
+  cudaEvent_t ev_tables = nullptr, ev_copy = nullptr;
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
   DevBuf b_row_tenant, b_row_topic, b_row_cap, b_row_pack, b_row_actor, b_row_combo, b_row_risk, b_row_check, b_row_mcp[4];
@@ -73,6 +74,7 @@ struct cordum_engine {
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
   DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush;
   uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
+  std::vector<cordum_batch*> batches;   // live batches (guarded by mu): K2 must wait for their kernels
   bool pools_dirty = true;       // K2 must run before the next dispatch
   bool loads_on_device = false;  // last load table came from cordum_workers_set_loads_device
   std::atomic<uint64_t> launches{0};
@@ -82,7 +84,7 @@ struct cordum_batch {
   cordum_engine* e = nullptr;
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
-  bool encoded = false, resident = false, pending = false;
+  bool encoded = false, resident = false, pending = false, launched = false;
   uint8_t* h_cols = nullptr;     // pinned
   uint8_t* d_cols = nullptr;
   cordum_decision* h_out = nullptr;   // pinned
@@ -216,6 +218,9 @@ int sync_tables(cordum_engine* e) {
 // K2 when the worker loads changed; batches wait on ev_tables.
 int refresh_pools(cordum_engine* e) {
   if (!e->pools_dirty) return CORDUM_OK;
+  // the dispatch kernels read pos_key / pool_best: order K2 after every kernel already enqueued
+  for (cordum_batch* b : e->batches)
+    if (b->launched) CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait dispatch");
   CK(launch_worker_pools(e->dt, e->s_tables), "worker_pool_kernel");
   if (e->dt.n_pools) e->launches++;
   CK(cudaEventRecord(e->ev_tables, e->s_tables), "event record");
@@ -223,8 +228,10 @@ int refresh_pools(cordum_engine* e) {
   return CORDUM_OK;
 }
 
-int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool copy_out, bool flush_l2) {
+int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool copy_out) {
   if (!e || !b) { g_err = "null handle"; return CORDUM_E_INVALID; }
+  const bool flush_l2 = mode & CORDUM_FLAG_FLUSH_L2;
+  mode &= 0xFFu;
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
   if (mode < CORDUM_MODE_POLICY_ONLY || mode > CORDUM_MODE_ROUTE_ONLY) { g_err = "bad mode"; return CORDUM_E_INVALID; }
   if (!b->encoded) { g_err = "batch has not been encoded"; return CORDUM_E_STATE; }
@@ -260,6 +267,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   CK(launch_dispatch(P, mode, e->sm_count, s), "dispatch_kernel");
   if (b->n) e->launches++;
   CK(cudaEventRecord(b->ev2, s), "event");
+  b->launched = true;
   if (copy_out) CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, s), "D2H results");
   CK(cudaEventRecord(b->ev3, s), "event");
   b->pending = true;
@@ -322,6 +330,7 @@ int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->s_tables, cudaStreamNonBlocking), "stream");
     CK(cudaEventCreateWithFlags(&e->ev_tables, cudaEventDisableTiming), "event");
+    CK(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming), "event");
     CK(cudaEventRecord(e->ev_tables, e->s_tables), "event");
   }
   e->host = std::make_unique<Host>(opts ? opts->max_topics : 0, opts ? opts->max_effcfgs : 0, opts ? opts->encode_threads : 0);
@@ -342,6 +351,7 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_flush};
   for (DevBuf* b : all) b->release();
   if (e->ev_tables) cudaEventDestroy(e->ev_tables);
+  if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->s_tables) cudaStreamDestroy(e->s_tables);
   delete e;
 }
@@ -401,6 +411,9 @@ int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint
   cudaEventDestroy(ev);
   CK(e->b_loads.reserve((size_t)std::max<uint32_t>(n_workers, 1) * sizeof(Load16)), "alloc loads");
   CK(cudaMemcpyAsync(e->b_loads.p, dptr, (size_t)n_workers * sizeof(Load16), cudaMemcpyDeviceToDevice, e->s_tables), "D2D loads");
+  // later work on the producer stream (e.g. the next all-gather into the same buffer) must not overtake the copy
+  CK(cudaEventRecord(e->ev_copy, e->s_tables), "event record");
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_copy, 0), "order producer after copy");
   e->dt.loads = (const Load16*)e->b_loads.p;
   e->loads_on_device = true;
   e->pools_dirty = true;
@@ -422,6 +435,7 @@ int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** o
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
   CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event");
   CK(cudaEventCreate(&b->ev2), "event"); CK(cudaEventCreate(&b->ev3), "event");
+  { std::lock_guard<std::mutex> g(e->mu); e->batches.push_back(b.get()); }
   *out = b.release();
   return CORDUM_OK;
 }
@@ -429,6 +443,11 @@ int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** o
 void cordum_batch_free(cordum_batch* b) {
   if (!b) return;
   cudaSetDevice(b->e->device);
+  {
+    std::lock_guard<std::mutex> g(b->e->mu);
+    auto& v = b->e->batches;
+    for (size_t i = 0; i < v.size(); ++i) if (v[i] == b) { v.erase(v.begin() + i); break; }
+  }
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->h_cols) cudaFreeHost(b->h_cols);
   if (b->d_cols) cudaFree(b->d_cols);
@@ -455,19 +474,20 @@ int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes*
   return CORDUM_OK;
 }
 
-int32_t cordum_dispatch_async(cordum_engine* e, cordum_batch* b, uint32_t mode) { return run(e, b, mode, true, true, false); }
+int32_t cordum_dispatch_async(cordum_engine* e, cordum_batch* b, uint32_t mode) { return run(e, b, mode, true, true); }
 int32_t cordum_batch_wait(cordum_batch* b) {
   if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
   return wait(b);
 }
 int32_t cordum_dispatch(cordum_engine* e, cordum_batch* b, uint32_t mode) {
-  int rc = run(e, b, mode, true, true, false);
+  int rc = run(e, b, mode, true, true);
   return rc ? rc : wait(b);
 }
 int32_t cordum_dispatch_resident(cordum_engine* e, cordum_batch* b, uint32_t mode) {
-  int rc = run(e, b, mode, false, false, true);
+  int rc = run(e, b, mode, false, false);
   return rc ? rc : wait(b);
 }
+int32_t cordum_dispatch_resident_async(cordum_engine* e, cordum_batch* b, uint32_t mode) { return run(e, b, mode, false, false); }
 
 uint32_t cordum_batch_size(const cordum_batch* b) { return b ? b->n : 0; }
 const cordum_decision* cordum_batch_results(const cordum_batch* b) { return b ? b->h_out : nullptr; }

@@ -57,8 +57,11 @@ class Batch:
         self.eng._ck(self.L.cordum_batch_wait(self.h))
         return self.results()
 
-    def dispatch_resident(self, mode=wire.MODE_POLICY_AND_ROUTE):
-        self.eng._ck(self.L.cordum_dispatch_resident(self.eng.h, self.h, mode))
+    def dispatch_resident(self, mode=wire.MODE_POLICY_AND_ROUTE, flush_l2=False):
+        self.eng._ck(self.L.cordum_dispatch_resident(self.eng.h, self.h, mode | (wire.FLAG_FLUSH_L2 if flush_l2 else 0)))
+
+    def dispatch_resident_async(self, mode=wire.MODE_POLICY_AND_ROUTE, flush_l2=False):
+        self.eng._ck(self.L.cordum_dispatch_resident_async(self.eng.h, self.h, mode | (wire.FLAG_FLUSH_L2 if flush_l2 else 0)))
 
     def fetch(self) -> np.ndarray:
         self.eng._ck(self.L.cordum_batch_fetch(self.h))

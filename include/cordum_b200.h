@@ -162,6 +162,9 @@ typedef struct cordum_decision {
 #define CORDUM_MODE_POLICY_ONLY 1      /* SafetyKernel Check/Evaluate/Explain/Simulate (kernel.go:106-120) */
 #define CORDUM_MODE_POLICY_AND_ROUTE 2 /* processJob: checkSafetyDecision + PickSubject (engine.go:294,393) */
 #define CORDUM_MODE_ROUTE_ONLY 3       /* SchedulingStrategy.PickSubject alone (types.go:40-42)            */
+/* may be OR-ed into the mode of the *_resident calls (benchmarks): write a 256 MiB scratch buffer
+ * first so the batch's columns are not served from L2 */
+#define CORDUM_FLAG_FLUSH_L2 0x100
 
 /* ------------------------------------------------------------- engine */
 typedef struct cordum_engine cordum_engine;
@@ -227,6 +230,7 @@ int32_t cordum_batch_wait(cordum_batch* b);
 /* Device-resident form used for kernel-only timing: assumes the columns of the
  * last dispatch on this batch are still in HBM; runs the kernels only, no copies. */
 int32_t cordum_dispatch_resident(cordum_engine* e, cordum_batch* b, uint32_t mode);
+int32_t cordum_dispatch_resident_async(cordum_engine* e, cordum_batch* b, uint32_t mode); /* then cordum_batch_wait */
 
 /* After a resident run: copy the decision records from HBM into the pinned result buffer. */
 int32_t cordum_batch_fetch(cordum_batch* b);
