@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — dispatch decisions/sec (policy-eval + route), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (config.workload): BASELINE config 3 — 1,000,000 jobs x 4,096 rules x 65,536 workers
+(seeded synthetic, cordum_b200/synth.py "c3").  At N > 1 the same 1M jobs are sharded
+contiguously by job index across the N ranks (config 4, strong scaling); every rank holds the
+full rule / routing / worker tables.
+
+One step = one pass of the hot path over the rank's job shard:
+    ingest the heartbeat load deltas of this rank's W/N worker slice (pinned host -> HBM)
+    [N > 1]  one NCCL all-gather of the per-rank 16 B/worker load slices   
+    worker_pool_kernel   (load score / overload / per-pool argmin over the 64k workers)
+    dispatch_kernel      (policy first-match + decision mapping + pool filter + least-loaded pick)
+`value`  : job columns already resident in HBM; K steps bracketed by barrier + synchronize on
+           both sides, max over ranks.  Successive steps rotate over enough distinct resident
+           copies of the shard that the working set exceeds 2 x L2 (no step re-reads L2-hot columns).
+`e2e`    : the same decisions produced through the public C ABI from HOST buffers: string-level
+           job envelopes -> cordum_encode (host, multi-threaded) -> pinned H2D -> kernels ->
+           D2H of the decision records, every step.
+`roofline`: dispatch_kernel's algorithmic bytes per launch / its CUDA-event duration, against the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` / --impl reference: the oracle (C++ port of the reference's Go path, oracle/oracle.cpp)
+           timed on the box's host cores on a bounded sample of the same jobs.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "dispatch decisions/sec (policy-eval+route)"
+UNIT = "decisions/s"
+L2_BYTES = 126 << 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU path (oracle)
+def cpu_reference_rate(cfg, threads: int, target_s: float, first: int = 0):
+    """Times the oracle on a bounded, contiguous sample of cfg.jobs.  Returns (decisions/s, sample, seconds)."""
+    import oracle_lib
+    from cordum_b200 import wire
+
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    n = cfg.jobs.n_jobs
+    probe = min(n, max(256, 8 * threads))
+    t0 = time.perf_counter()
+    o.eval(cfg.jobs, wire.MODE_POLICY_AND_ROUTE, threads=threads, first=first % max(1, n - probe), count=probe)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, probe / dt * target_s)))
+    start = first % max(1, n - sample + 1)
+    t0 = time.perf_counter()
+    o.eval(cfg.jobs, wire.MODE_POLICY_AND_ROUTE, threads=threads, first=start, count=sample)
+    dt = time.perf_counter() - t0
+    o.close()
+    return sample / dt, sample, dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from cordum_b200 import synth
+
+    threads = os.cpu_count() or 1
+    cfg = synth.make_config("c3")
+    per_step_s = max(0.5, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
+    for w in range(args.warmup):
+        cpu_reference_rate(cfg, threads, per_step_s, first=w * 50_000)
+    total_jobs, total_s, sample = 0, 0.0, 0
+    for k in range(args.steps):
+        rate, sample, dt = cpu_reference_rate(cfg, threads, per_step_s, first=(args.warmup + k) * 50_000)
+        total_jobs += sample
+        total_s += dt
+    value = total_jobs / total_s
+    desc = "%d steps x ~%d contiguous jobs of the 1M-job c3 batch (about %.1f s each); full 4096-rule set and 65536-worker table" % (
+        args.steps, sample, per_step_s)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total_s / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitmask + f32 score", "data": "synthetic",
+        "config": {"workload": "c3: 1,000,000 jobs x 4096 rules x 65536 workers (seed 3), policy+route",
+                   "note": "reference CPU path = oracle/oracle.cpp (C++ restatement of the Go evaluator; the Go "
+                           "toolchain and the CAP module are absent), one std::thread per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA path
+def run_cuda(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    from cordum_b200 import engine, synth, wire
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = synth.make_config("c3")
+    J, W = cfg.jobs.n_jobs, cfg.workers.n_workers
+    per = (J + world - 1) // world
+    j0, j1 = min(J, rank * per), min(J, (rank + 1) * per)
+    shard = cfg.jobs.slice(j0, j1 - j0) if world > 1 else cfg.jobs
+    n_shard = shard.n_jobs
+    wper = (W + world - 1) // world
+    w0, w1 = min(W, rank * wper), min(W, (rank + 1) * wper)
+    assert wper * world == W, "worker count must divide evenly for the all-gather"
+
+    eng = engine.Engine(device=local_rank)
+    eng.load_policy(cfg.policy, "bench")
+    eng.load_routing(cfg.routing)
+    eng.load_workers(cfg.workers)
+    st = eng.stats()
+    in_b, out_b = st.job_in_bytes, st.job_out_bytes
+    table_bytes = int(st.passrow_bytes + st.rulecol_bytes + st.routing_bytes + st.worker_bytes)
+
+    # resident copies of the shard: enough distinct addresses that successive steps cannot hit L2
+    shard_bytes = n_shard * (in_b + out_b)
+    n_rot = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, shard_bytes))) + 1)
+    batches = [eng.batch(n_shard) for _ in range(n_rot)]
+    t_enc0 = time.perf_counter()
+    for b in batches:
+        b.encode(shard)
+        b.dispatch(wire.MODE_POLICY_AND_ROUTE)   # makes the columns resident (and warms the dictionaries)
+    enc_s = (time.perf_counter() - t_enc0) / n_rot
+    ref_result = batches[0].results().copy()
+
+    # per-step heartbeat deltas for this rank's worker slice (synthetic, seeded per step)
+    base = cfg.workers.loads()
+    n_delta_sets = 8
+    rng = np.random.default_rng(1000 + rank)
+    delta_sets = []
+    for s in range(n_delta_sets):
+        d = base[w0:w1].copy()
+        d["active_jobs"] = rng.integers(0, 9, w1 - w0)
+        d["cpu_load"] = (rng.random(w1 - w0) * 100).astype(np.float32)
+        d["gpu_utilization"] = (rng.random(w1 - w0) * 100).astype(np.float32)
+        delta_sets.append(torch.from_numpy(d.view(np.uint8).reshape(-1, 16).copy()).pin_memory())
+    send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
+    recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    stream = torch.cuda.current_stream()
+
+    def step(k: int, batch, resident: bool):
+        send.copy_(delta_sets[k % n_delta_sets], non_blocking=True)          # heartbeat ingest: pinned host -> HBM
+        if world > 1:
+            buf = recv[k % 2]
+            dist.all_gather_into_tensor(buf.view(-1), send.view(-1))          # the one exchange step
+        else:
+            buf = send
+        eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)           # D2D + worker_pool_kernel
+        if resident:
+            batch.dispatch_resident_async(wire.MODE_POLICY_AND_ROUTE)
+        else:
+            batch.dispatch_async(wire.MODE_POLICY_AND_ROUTE)
+
+    def sync_all():
+        for b in batches:
+            b.wait()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident: `value`
+    for k in range(args.warmup):
+        step(k, batches[k % n_rot], True)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(args.warmup + k, batches[(args.warmup + k) % n_rot], True)
+    sync_all()
+    elapsed = time.perf_counter() - t0
+    launches = eng.launch_count() - launches0
+    kernel_ms = [b.timing()[1] for b in batches[: min(n_rot, args.steps)]]
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = J * args.steps / elapsed
+
+    # parity spot check inside the bench: the last resident run must equal the first copy run's records
+    # (same jobs; only the load table changed, so compare policy fields)
+    chk = batches[(args.warmup + args.steps - 1) % n_rot].fetch()
+    assert np.array_equal(chk["decision"], ref_result["decision"]) and np.array_equal(chk["rule_idx"], ref_result["rule_idx"])
+
+    # ---------------------------------------------------------------- end to end: `e2e`
+    e2e_steps = max(2, min(args.steps, 6))
+    for k in range(2):
+        batches[k % 2].encode(shard)
+        step(k, batches[k % 2], False)
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        b = batches[k % 2]
+        b.encode(shard)                    # waits for this batch's previous run, then host encode
+        step(k, b, False)                  # H2D columns + kernels + D2H records, async
+    sync_all()
+    e2e_elapsed = time.perf_counter() - t0
+    # from already-encoded pinned columns (copies + kernels only)
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        step(k, batches[k % 2], False)
+    sync_all()
+    e2e_cols_elapsed = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_elapsed, e2e_cols_elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_elapsed, e2e_cols_elapsed = float(t[0].item()), float(t[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+
+    peak, peak_src = measured_peaks()
+    algo_bytes = n_shard * (in_b + out_b) + table_bytes
+    k_ms = float(np.mean(kernel_ms))
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dispatch_kernel_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sample, dt = cpu_reference_rate(cfg, threads, 12.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "first %d jobs of the c3 batch in %.1f s, full rule set and worker table; "
+                         "oracle/oracle.cpp, one std::thread per host core" % (sample, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 bitmask + f32 score", "data": "synthetic",
+        "config": {"workload": "c3: 1,000,000 jobs x 4096 rules x 65536 workers (seed 3), policy+route",
+                   "jobs_per_rank": n_shard, "parallelism": "jobs sharded by index x%d, tables replicated" % world,
+                   "l2": "inputs larger than L2: steps rotate over %d resident copies of the shard (%.0f MB total)" % (
+                       n_rot, n_rot * shard_bytes / 1e6),
+                   "step": "heartbeat-slice H2D + %sworker_pool_kernel + dispatch_kernel" % ("NCCL all-gather + " if world > 1 else "")},
+        "clocks": clocks,
+        "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
+                "h2d_bytes_per_step": int(n_shard * in_b + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
+                "includes": "cordum_encode of string-level envelopes on the host + pinned H2D + kernels + D2H, 2 batches in flight",
+                "from_encoded_columns": J * e2e_steps / e2e_cols_elapsed, "host_encode_s_per_batch": enc_s},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "dispatch_kernel<POLICY_AND_ROUTE>", "kernel_ms": k_ms,
+                     "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    for b in batches:
+        b.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cordum_b200", choices=["cordum_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
