@@ -130,13 +130,20 @@ __global__ void __launch_bounds__(128) worker_pool_kernel(DeviceTables T) {
 }
 
 // ------------------------------------------------------------------ fused policy + route
+// A warp owns a tile of 32 consecutive jobs (lane = job for the column loads, the scalar
+// decision/route logic and the record store).  Three phases per tile:
+//   P  policy rows, warp-cooperative PER JOB: lane = one 128-bit slice of the pass-rows, so a
+//      4096-rule set is ANDed in one step with 7-12 independent 16 B gathers per lane in flight
+//      and no divergence; first match = ballot + ffs.  Rule sets > 4096 loop in rule order.
+//   D  decision mapping, tenant MCP, effective-config overlay, scheduler post-step and the pool
+//      filter / per-pool argmin merge, thread-per-job (32 jobs at once, scalar code).
+//   S  only for jobs with placement labels: warp-cooperative scan of the eligible pools' worker
+//      slices (coalesced 8 B loads of label masks and keys) + shuffle reduction.
 template <int MODE>
-__global__ void __launch_bounds__(256) dispatch_kernel(KParams P) {
+__global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
   const unsigned lane = threadIdx.x & 31;
-  const unsigned g = lane >> 3, sub = lane & 7;
-  const unsigned gmask = 0xFFu << (g * 8);
   const uint32_t n_tiles = (P.n_jobs + 31u) >> 5;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -166,220 +173,220 @@ __global__ void __launch_bounds__(256) dispatch_kernel(KParams P) {
         c_plo = ld_stream_u64(C.place_lo + j); c_phi = ld_stream_u64(C.place_hi + j);
       }
     }
-    uint32_t my_head = 0, my_reason = 0;   // head: decision | sched<<8 | flags<<16 | route<<24
-    int my_rule = -1, my_slot = -1;
 
-#pragma unroll 1
-    for (int round = 0; round < 8; ++round) {
-      const int src = round * 4 + (int)g;   // lane owning the job this 8-lane group works on now
-      const bool jv = __shfl_sync(FULL, (int)valid, src) != 0;
-      const uint32_t flags = __shfl_sync(FULL, c_flags, src);
-      const uint32_t topic = __shfl_sync(FULL, c_topic, src);
-      const uint64_t req_mask = shfl64(FULL, c_req, src);
-      uint32_t tenant = 0, tpol = 0, cap = 0, pack = 0, actor = 0, eff = 0, mid[4] = {0, 0, 0, 0};
-      uint64_t risk = 0, lab = 0;
-      if (MODE != CORDUM_MODE_ROUTE_ONLY) {
-        tenant = __shfl_sync(FULL, c_tenant, src); tpol = __shfl_sync(FULL, c_tpol, src);
-        cap = __shfl_sync(FULL, c_cap, src); pack = __shfl_sync(FULL, c_pack, src); actor = __shfl_sync(FULL, c_actor, src);
-        mid[0] = __shfl_sync(FULL, c_m0, src); mid[1] = __shfl_sync(FULL, c_m1, src);
-        mid[2] = __shfl_sync(FULL, c_m2, src); mid[3] = __shfl_sync(FULL, c_m3, src);
-        eff = __shfl_sync(FULL, c_eff, src);
-        risk = shfl64(FULL, c_risk, src); lab = shfl64(FULL, c_lab, src);
-      }
-      uint32_t ppool = 0, pwork = 0;
-      uint64_t plo = 0, phi = 0;
-      if (MODE != CORDUM_MODE_POLICY_ONLY) {
-        ppool = __shfl_sync(FULL, c_ppool, src); pwork = __shfl_sync(FULL, c_pwork, src);
-        plo = shfl64(FULL, c_plo, src); phi = shfl64(FULL, c_phi, src);
-      }
-
-      uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
-      int rule = -1, slot = -1;
-
-      if (jv) {
-        // =============================================================== policy
-        if (MODE != CORDUM_MODE_ROUTE_ONLY) {
-          if (MODE == CORDUM_MODE_POLICY_AND_ROUTE && (flags & JF_APPROVED)) {
-            // engine.go:484-522: stored approval + matching hash (host-verified): policy skipped
-            dec = sched = CORDUM_DEC_ALLOW; reason = CORDUM_REASON_APPROVAL_GRANTED; rflags = CORDUM_F_APPROVED_BYPASS;
-          } else if (flags & JF_TOPIC_MISSING) {
-            dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_MISSING_TOPIC;          // kernel.go:171-173
-          } else if (flags & JF_TOPIC_UNSUPPORTED) {
-            dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_UNSUPPORTED_TOPIC;      // kernel.go:174-176
-          } else {
-            const bool mcp_used = flags & JF_MCP_USED, has_labels = flags & JF_HAS_LABELS;
-            const Row16* p_combo = T.row_combo + (size_t)(flags & JF_COMBO_MASK) * rowu4 + sub;
-            const Row16* p_tenant = T.row_tenant + (size_t)tenant * rowu4 + sub;
-            const Row16* p_topic = T.row_topic + (size_t)topic * rowu4 + sub;
-            const Row16* p_cap = T.row_cap + (size_t)cap * rowu4 + sub;
-            const Row16* p_pack = T.row_pack + (size_t)pack * rowu4 + sub;
-            const Row16* p_actor = T.row_actor + (size_t)actor * rowu4 + sub;
-            int first = -1;
-            for (uint32_t seg = 0; seg < T.n_seg; ++seg) {
-              const uint32_t so = seg * CORDUM_SEG_U4;
-              // issue the independent gathers together (memory-level parallelism), then combine
-              uint4 r0 = ld_row(p_combo + so), r1 = ld_row(p_tenant + so), r2 = ld_row(p_topic + so),
-                    r3 = ld_row(p_cap + so), r4 = ld_row(p_pack + so), r5 = ld_row(p_actor + so);
-              uint4 rk;
-              if (risk == 0) rk = ld_row(T.row_risk + so + sub);
-              else {
-                rk = make_uint4(0, 0, 0, 0);
-                for (uint64_t m = risk; m; m &= m - 1)   // containsAny: OR over the job's tags (:308-318)
-                  rk = or4(rk, ld_row(T.row_risk + (size_t)(1 + (__ffsll((long long)m) - 1)) * rowu4 + so + sub));
-              }
-              uint4 acc = and4(and4(and4(r0, r1), and4(r2, r3)), and4(and4(r4, r5), rk));
-              if (mcp_used) {   // mcpMatch (:365-382)
-#pragma unroll
-                for (int f = 0; f < 4; ++f) acc = and4(acc, ld_row(T.row_mcp[f] + (size_t)mid[f] * rowu4 + so + sub));
-              }
-              int local = -1;
-              if (acc.x | acc.y | acc.z | acc.w)
-                local = lowest_passing(acc, ld_row(T.row_check + so + sub), seg * CORDUM_SEG_RULES + sub * 128u, T, req_mask,
-                                       lab, has_labels);
-              const unsigned bal = __ballot_sync(gmask, local >= 0);
-              if (bal) { first = __shfl_sync(gmask, local, __ffs(bal) - 1); break; }   // lowest lane = lowest rule
-            }
-            rule = first;
-            uint32_t code = CORDUM_DEC_ALLOW;
-            bool hascons = false;
-            if (first >= 0) { uint8_t rd = __ldg(T.rule_dec + first); code = rd & 0x7Fu; hascons = rd & 0x80u; }
-            const bool rule_approval = code == CORDUM_DEC_REQUIRE_HUMAN;   // safety_policy.go:200
-            // tenant MCP lists (kernel.go:190-195): exact-tenant entry, first failing field wins
-            uint32_t tm = 0;
-            if (mcp_used && tpol) {
-              const uint8_t* base = T.tenant_mcp + (size_t)(tpol - 1) * 4 * T.mcp_stride;
-              for (int f = 0; f < 4 && !tm; ++f) { uint8_t v = __ldg(base + f * T.mcp_stride + mid[f]); if (v) tm = 1 + f * 2 + (v - 1); }
-              if (tm) code = CORDUM_DEC_DENY;
-            }
-            dec = CORDUM_DEC_ALLOW;                                             // kernel.go:198-215
-            if (code == CORDUM_DEC_DENY) { dec = CORDUM_DEC_DENY; reason = tm ? CORDUM_REASON_TENANT_MCP + (tm - 1) : CORDUM_REASON_RULE; }
-            else if (code == CORDUM_DEC_REQUIRE_HUMAN) { dec = CORDUM_DEC_REQUIRE_HUMAN; reason = CORDUM_REASON_RULE; }
-            else if (code == CORDUM_DEC_THROTTLE) { dec = CORDUM_DEC_THROTTLE; reason = CORDUM_REASON_RULE; }
-            else if (code == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS) dec = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
-            else if (hascons) dec = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
-            if (eff) {                                                          // kernel.go:218-231
-              const uint8_t tb = __ldg(T.eff_topic + (size_t)eff * T.topic_stride + topic);
-              if (tb & 1) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_DENIED_TOPIC; }
-              if (tb & 2) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC; }
-              if (mcp_used) {
-                const uint8_t* base = T.eff_mcp + (size_t)eff * 4 * T.mcp_stride;
-                uint32_t em = 0;
-                for (int f = 0; f < 4 && !em; ++f) { uint8_t v = __ldg(base + f * T.mcp_stride + mid[f]); if (v) em = 1 + f * 2 + (v - 1); }
-                if (em) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_MCP + (em - 1); }
-              }
-            }
-            const bool approval = rule_approval || dec == CORDUM_DEC_REQUIRE_HUMAN;   // kernel.go:233
-            rflags = CORDUM_F_HAS_SNAPSHOT | (approval ? CORDUM_F_APPROVAL_REQUIRED : 0) | (hascons ? CORDUM_F_CONSTRAINTS : 0);
-            sched = dec;                                                         // engine.go:528-530
-            if (approval && (dec == CORDUM_DEC_ALLOW || dec == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)) sched = CORDUM_DEC_REQUIRE_HUMAN;
-          }
+    // =================================================================== P: first matching rule
+    int first = -1;
+    const bool bypass = MODE == CORDUM_MODE_POLICY_AND_ROUTE && (c_flags & JF_APPROVED);                 // engine.go:484-522
+    const bool early = (c_flags & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED)) != 0;                        // kernel.go:171-176
+    const bool eval = valid && MODE != CORDUM_MODE_ROUTE_ONLY && !bypass && !early;
+    if (MODE != CORDUM_MODE_ROUTE_ONLY) {
+      for (unsigned todo = __ballot_sync(FULL, eval); todo; todo &= todo - 1) {
+        const int i = __ffs(todo) - 1;
+        const uint32_t fl = __shfl_sync(FULL, c_flags, i);
+        const Row16* p_combo = T.row_combo + (size_t)(fl & JF_COMBO_MASK) * rowu4;
+        const Row16* p_tenant = T.row_tenant + (size_t)__shfl_sync(FULL, c_tenant, i) * rowu4;
+        const Row16* p_topic = T.row_topic + (size_t)__shfl_sync(FULL, c_topic, i) * rowu4;
+        const Row16* p_cap = T.row_cap + (size_t)__shfl_sync(FULL, c_cap, i) * rowu4;
+        const Row16* p_pack = T.row_pack + (size_t)__shfl_sync(FULL, c_pack, i) * rowu4;
+        const Row16* p_actor = T.row_actor + (size_t)__shfl_sync(FULL, c_actor, i) * rowu4;
+        const uint64_t risk = shfl64(FULL, c_risk, i);
+        const bool mcp_used = fl & JF_MCP_USED;
+        uint32_t mid[4] = {0, 0, 0, 0};
+        if (mcp_used) {
+          mid[0] = __shfl_sync(FULL, c_m0, i); mid[1] = __shfl_sync(FULL, c_m1, i);
+          mid[2] = __shfl_sync(FULL, c_m2, i); mid[3] = __shfl_sync(FULL, c_m3, i);
         }
-        // =============================================================== route
-        const bool do_route = MODE == CORDUM_MODE_ROUTE_ONLY ||
-                              (MODE == CORDUM_MODE_POLICY_AND_ROUTE &&
-                               (sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS));   // engine.go:298-347
-        if (do_route) {
-          if (flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
-          else {
-            const uint32_t off = __ldg(T.topic_pool_off + topic);
-            uint32_t cnt = __ldg(T.topic_pool_cnt + topic);
-            int single = -1;
-            if (ppool) {                                                         // preferred_pool (:50-55)
-              bool found = false;
-              if (ppool != CORDUM_PREF_UNKNOWN)
-                for (uint32_t k = sub; k < cnt; k += CORDUM_GROUP) found |= __ldg(T.pool_list + off + k) == ppool - 1;
-              found = __ballot_sync(gmask, found) != 0;
-              if (!found) route = CORDUM_ROUTE_NO_POOL_PREFERRED;
-              else { single = (int)(ppool - 1); cnt = 1; }
+        int f = -1;
+        for (uint32_t u0 = 0; u0 < rowu4; u0 += 32) {   // 4096 rules per step, in rule order
+          const uint32_t u = u0 + lane;
+          uint4 acc = make_uint4(0, 0, 0, 0), chk = make_uint4(0, 0, 0, 0);
+          if (u < rowu4) {
+            // independent gathers first (memory-level parallelism), then combine
+            uint4 r0 = ld_row(p_combo + u), r1 = ld_row(p_tenant + u), r2 = ld_row(p_topic + u), r3 = ld_row(p_cap + u),
+                  r4 = ld_row(p_pack + u), r5 = ld_row(p_actor + u);
+            chk = ld_row(T.row_check + u);
+            uint4 rk;
+            if (risk == 0) rk = ld_row(T.row_risk + u);
+            else {
+              rk = make_uint4(0, 0, 0, 0);
+              for (uint64_t m = risk; m; m &= m - 1)   // containsAny: OR over the job's tags (:308-318)
+                rk = or4(rk, ld_row(T.row_risk + (size_t)(1 + (__ffsll((long long)m) - 1)) * rowu4 + u));
             }
-            if (route == CORDUM_ROUTE_NOT_ATTEMPTED && cnt == 0) route = CORDUM_ROUTE_NO_POOL_TOPIC;   // :56-58
-            if (route == CORDUM_ROUTE_NOT_ATTEMPTED) {
-              const bool req_any = flags & JF_REQ_NONEMPTY, req_unknown = flags & JF_REQ_UNKNOWN;
-              const uint64_t need_req = req_mask & ~T.req_blank_mask;
-              const uint64_t need_lo = plo, need_hi = phi;
-              const bool labelled = (need_lo | need_hi) != 0 || (flags & JF_PLACE_UNSAT);
-              const bool unsat = flags & JF_PLACE_UNSAT;
-              // pool eligibility: poolSatisfies (:241-265)
-              auto eligible = [&](uint32_t pid) -> bool {
-                if (!req_any) return true;
-                return __ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0;
-              };
-              uint64_t best = KEY_NONE;
-              uint32_t bcnt = 0, total = 0, n_elig = 0;
-              // preferred worker needs its pool to be in the eligible set
-              int pw_pos = -1;
-              uint32_t pw_pool = 0xFFFFFFFFu;
-              bool pw_in_set = false;
-              if (pwork && pwork != CORDUM_PREF_UNKNOWN) {
-                uint32_t p1 = __ldg(T.slot_pos + (pwork - 1));
-                if (p1) { pw_pos = (int)p1 - 1; pw_pool = __ldg(T.pos_pool + pw_pos); }
-              }
-              if (!labelled) {
-                for (uint32_t k = sub; k < cnt; k += CORDUM_GROUP) {
-                  uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
-                  if (!eligible(pid)) continue;
-                  n_elig++;
-                  pw_in_set |= pid == pw_pool;
-                  total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
-                  merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
-                }
-              } else {
-                // placement labels: scan the eligible pools' worker slices (matchesLabels, :161-175)
-                for (uint32_t k = 0; k < cnt; ++k) {
-                  uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
-                  if (!eligible(pid)) continue;
-                  if (sub == 0) n_elig++;
-                  pw_in_set |= pid == pw_pool;
-                  if (unsat) continue;
-                  const uint32_t a = __ldg(T.pool_off + pid), b = __ldg(T.pool_off + pid + 1);
-                  for (uint32_t pos = a + sub; pos < b; pos += CORDUM_GROUP) {
-                    uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
-                    if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
-                    total++;
-                    merge_best(best, bcnt, T.pos_key[pos], 1);
-                  }
-                }
-              }
-              // reduce over the 8 lanes of the group
+            acc = and4(and4(and4(r0, r1), and4(r2, r3)), and4(and4(r4, r5), rk));
+            if (mcp_used) {   // mcpMatch (:365-382)
 #pragma unroll
-              for (int o = 4; o; o >>= 1) {
-                uint64_t k2 = shfl64_xor(gmask, best, o);
-                uint32_t c2 = __shfl_xor_sync(gmask, bcnt, o);
-                merge_best(best, bcnt, k2, c2);
-                total += __shfl_xor_sync(gmask, total, o);
-                n_elig += __shfl_xor_sync(gmask, n_elig, o);
-              }
-              pw_in_set = __ballot_sync(gmask, pw_in_set) != 0;
-              if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;            // :64-66
-              else {
-                bool took_pref = false;
-                if (pw_pos >= 0 && pw_in_set && !unsat) {                         // :73-87
-                  uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
-                  bool lab_ok = (llo & need_lo) == need_lo && (lhi & need_hi) == need_hi;
-                  if (lab_ok && T.pos_key[pw_pos] != KEY_NONE) { took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(pwork - 1); }
-                }
-                if (!took_pref) {
-                  if (best != KEY_NONE) {
-                    route = CORDUM_ROUTE_OK;
-                    slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
-                    if (bcnt > 1) rflags |= CORDUM_F_TIE;
-                  } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;   // :114-119
-                }
-              }
+              for (int q = 0; q < 4; ++q) acc = and4(acc, ld_row(T.row_mcp[q] + (size_t)mid[q] * rowu4 + u));
             }
           }
+          const uint4 both = and4(acc, chk);
+          int local = -1;
+          if (__any_sync(FULL, (both.x | both.y | both.z | both.w) != 0)) {
+            // some surviving rule carries a requires / labels subset test: fetch the job's masks
+            const uint64_t req = shfl64(FULL, c_req, i), lab = shfl64(FULL, c_lab, i);
+            if (acc.x | acc.y | acc.z | acc.w) local = lowest_passing(acc, chk, u * 128u, T, req, lab, fl & JF_HAS_LABELS);
+          } else if (acc.x | acc.y | acc.z | acc.w) {
+            local = (int)(u * 128u) + (acc.x ? __ffs(acc.x) - 1 : acc.y ? 32 + __ffs(acc.y) - 1 : acc.z ? 64 + __ffs(acc.z) - 1 : 96 + __ffs(acc.w) - 1);
+          }
+          const unsigned bal = __ballot_sync(FULL, local >= 0);
+          if (bal) { f = __shfl_sync(FULL, local, __ffs(bal) - 1); break; }   // lowest lane = lowest rule
         }
+        if ((int)lane == i) first = f;
       }
-      // ---- hand the record to the lane that owns this job (lane L was served in round L>>2 by group L&3)
-      const uint32_t head = dec | (sched << 8) | (rflags << 16) | (route << 24);
-      const int from = (int)(lane & 3) * 8;
-      const uint32_t h2 = __shfl_sync(FULL, head, from), r2 = __shfl_sync(FULL, reason, from);
-      const int ru2 = __shfl_sync(FULL, rule, from), sl2 = __shfl_sync(FULL, slot, from);
-      if ((int)(lane >> 2) == round) { my_head = h2; my_reason = r2; my_rule = ru2; my_slot = sl2; }
     }
+
+    // =================================================================== D: decision (thread per job)
+    uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
+    int rule = -1, slot = -1;
+    if (valid && MODE != CORDUM_MODE_ROUTE_ONLY) {
+      if (bypass) { dec = sched = CORDUM_DEC_ALLOW; reason = CORDUM_REASON_APPROVAL_GRANTED; rflags = CORDUM_F_APPROVED_BYPASS; }
+      else if (c_flags & JF_TOPIC_MISSING) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_MISSING_TOPIC; }
+      else if (c_flags & JF_TOPIC_UNSUPPORTED) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_UNSUPPORTED_TOPIC; }
+      else {
+        const bool mcp_used = c_flags & JF_MCP_USED;
+        const uint32_t mid[4] = {c_m0, c_m1, c_m2, c_m3};
+        rule = first;
+        uint32_t code = CORDUM_DEC_ALLOW;
+        bool hascons = false;
+        if (first >= 0) { uint8_t rd = __ldg(T.rule_dec + first); code = rd & 0x7Fu; hascons = rd & 0x80u; }
+        const bool rule_approval = code == CORDUM_DEC_REQUIRE_HUMAN;   // safety_policy.go:200
+        uint32_t tm = 0;                                               // tenant MCP lists, kernel.go:190-195
+        if (mcp_used && c_tpol) {
+          const uint8_t* base = T.tenant_mcp + (size_t)(c_tpol - 1) * 4 * T.mcp_stride;
+          for (int q = 0; q < 4 && !tm; ++q) { uint8_t v = __ldg(base + q * T.mcp_stride + mid[q]); if (v) tm = 1 + q * 2 + (v - 1); }
+          if (tm) code = CORDUM_DEC_DENY;
+        }
+        dec = CORDUM_DEC_ALLOW;                                        // kernel.go:198-215
+        if (code == CORDUM_DEC_DENY) { dec = CORDUM_DEC_DENY; reason = tm ? CORDUM_REASON_TENANT_MCP + (tm - 1) : CORDUM_REASON_RULE; }
+        else if (code == CORDUM_DEC_REQUIRE_HUMAN) { dec = CORDUM_DEC_REQUIRE_HUMAN; reason = CORDUM_REASON_RULE; }
+        else if (code == CORDUM_DEC_THROTTLE) { dec = CORDUM_DEC_THROTTLE; reason = CORDUM_REASON_RULE; }
+        else if (code == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS || hascons) dec = CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
+        if (c_eff) {                                                   // kernel.go:218-231
+          const uint8_t tb = __ldg(T.eff_topic + (size_t)c_eff * T.topic_stride + c_topic);
+          if (tb & 1) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_DENIED_TOPIC; }
+          if (tb & 2) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC; }
+          if (mcp_used) {
+            const uint8_t* base = T.eff_mcp + (size_t)c_eff * 4 * T.mcp_stride;
+            uint32_t em = 0;
+            for (int q = 0; q < 4 && !em; ++q) { uint8_t v = __ldg(base + q * T.mcp_stride + mid[q]); if (v) em = 1 + q * 2 + (v - 1); }
+            if (em) { dec = CORDUM_DEC_DENY; reason = CORDUM_REASON_EFF_MCP + (em - 1); }
+          }
+        }
+        const bool approval = rule_approval || dec == CORDUM_DEC_REQUIRE_HUMAN;   // kernel.go:233
+        rflags = CORDUM_F_HAS_SNAPSHOT | (approval ? CORDUM_F_APPROVAL_REQUIRED : 0) | (hascons ? CORDUM_F_CONSTRAINTS : 0);
+        sched = dec;                                                   // engine.go:528-530
+        if (approval && (dec == CORDUM_DEC_ALLOW || dec == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)) sched = CORDUM_DEC_REQUIRE_HUMAN;
+      }
+    }
+
+    // =================================================================== D (cont.): pool filter, thread per job
+    bool need_scan = false;
+    uint32_t r_off = 0, r_cnt = 0;
+    int r_single = -1;
+    uint64_t best = KEY_NONE;
+    uint32_t bcnt = 0, total = 0;
+    if (MODE != CORDUM_MODE_POLICY_ONLY) {
+      const bool do_route = valid && (MODE == CORDUM_MODE_ROUTE_ONLY ||
+                                      sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS);   // engine.go:298-347
+      if (do_route) {
+        if (c_flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
+        else {
+          r_off = __ldg(T.topic_pool_off + c_topic);
+          r_cnt = __ldg(T.topic_pool_cnt + c_topic);
+          if (c_ppool) {                                                         // preferred_pool (:50-55)
+            bool found = false;
+            if (c_ppool != CORDUM_PREF_UNKNOWN)
+              for (uint32_t k = 0; k < r_cnt; ++k) found |= __ldg(T.pool_list + r_off + k) == c_ppool - 1;
+            if (!found) route = CORDUM_ROUTE_NO_POOL_PREFERRED;
+            else { r_single = (int)(c_ppool - 1); r_cnt = 1; }
+          }
+          if (route == CORDUM_ROUTE_NOT_ATTEMPTED && r_cnt == 0) route = CORDUM_ROUTE_NO_POOL_TOPIC;   // :56-58
+          if (route == CORDUM_ROUTE_NOT_ATTEMPTED) {
+            const bool req_any = c_flags & JF_REQ_NONEMPTY, req_unknown = c_flags & JF_REQ_UNKNOWN;
+            const uint64_t need_req = c_req & ~T.req_blank_mask;
+            const bool unsat = c_flags & JF_PLACE_UNSAT;
+            const bool labelled = (c_plo | c_phi) != 0 || unsat;
+            int pw_pos = -1;
+            uint32_t pw_pool = 0xFFFFFFFFu;
+            if (c_pwork && c_pwork != CORDUM_PREF_UNKNOWN) {
+              uint32_t p1 = __ldg(T.slot_pos + (c_pwork - 1));
+              if (p1) { pw_pos = (int)p1 - 1; pw_pool = __ldg(T.pos_pool + pw_pos); }
+            }
+            uint32_t n_elig = 0;
+            bool pw_in_set = false;
+            for (uint32_t k = 0; k < r_cnt; ++k) {
+              const uint32_t pid = r_single >= 0 ? (uint32_t)r_single : __ldg(T.pool_list + r_off + k);
+              // poolSatisfies (:241-265)
+              if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+              n_elig++;
+              pw_in_set |= pid == pw_pool;
+              if (!labelled) {
+                total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
+                merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
+              }
+            }
+            if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;              // :64-66
+            else {
+              bool took_pref = false;
+              if (pw_pos >= 0 && pw_in_set && !unsat) {                           // :73-87
+                uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
+                if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && T.pos_key[pw_pos] != KEY_NONE) {
+                  took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
+                }
+              }
+              if (!took_pref) need_scan = labelled && !unsat;   // label-free and unsatisfiable jobs are final already
+              if (!took_pref && !need_scan) {
+                if (best != KEY_NONE) {
+                  route = CORDUM_ROUTE_OK;
+                  slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
+                  if (bcnt > 1) rflags |= CORDUM_F_TIE;
+                } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;   // :114-119
+              }
+            }
+          }
+        }
+      }
+      // ================================================================= S: placement-label scans, warp per job
+      for (unsigned todo = __ballot_sync(FULL, need_scan); todo; todo &= todo - 1) {
+        const int i = __ffs(todo) - 1;
+        const uint32_t off = __shfl_sync(FULL, r_off, i), cnt = __shfl_sync(FULL, r_cnt, i), fl = __shfl_sync(FULL, c_flags, i);
+        const int single = __shfl_sync(FULL, r_single, i);
+        const uint64_t need_req = shfl64(FULL, c_req, i) & ~T.req_blank_mask;
+        const uint64_t need_lo = shfl64(FULL, c_plo, i), need_hi = shfl64(FULL, c_phi, i);
+        const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+        uint64_t b = KEY_NONE;
+        uint32_t bc = 0, tot = 0;
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
+          if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+          const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
+          for (uint32_t pos = a + lane; pos < e; pos += 32) {   // matchesLabels (:161-175), coalesced
+            const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
+            if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
+            tot++;
+            merge_best(b, bc, T.pos_key[pos], 1);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const uint64_t k2 = shfl64_xor(FULL, b, o);
+          const uint32_t c2 = __shfl_xor_sync(FULL, bc, o);
+          merge_best(b, bc, k2, c2);
+          tot += __shfl_xor_sync(FULL, tot, o);
+        }
+        if ((int)lane == i) { best = b; bcnt = bc; total = tot; }
+      }
+      if (need_scan) {
+        if (best != KEY_NONE) {
+          route = CORDUM_ROUTE_OK;
+          slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
+          if (bcnt > 1) rflags |= CORDUM_F_TIE;
+        } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;
+      }
+    }
+
     if (valid) {   // coalesced 16 B store per lane
-      uint4 rec = make_uint4(my_head, my_reason & 0xFFu, (uint32_t)my_rule, (uint32_t)my_slot);
-      reinterpret_cast<uint4*>(P.out)[j] = rec;
+      const uint32_t head = dec | (sched << 8) | (rflags << 16) | (route << 24);
+      reinterpret_cast<uint4*>(P.out)[j] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, (uint32_t)slot);
     }
   }
 }
@@ -395,7 +402,7 @@ cudaError_t launch_dispatch(const KParams& P, uint32_t mode, int sm_count, cudaS
   if (P.n_jobs == 0) return cudaSuccess;
   const uint32_t tiles = (P.n_jobs + 31u) / 32u;
   uint32_t blocks = (tiles + 7u) / 8u;                  // 8 warps (tiles) per 256-thread CTA
-  const uint32_t cap = (uint32_t)sm_count * 8u;         // persistent: grid = multiple of the SM count
+  const uint32_t cap = (uint32_t)sm_count * 3u * 4u;    // grid = multiple of SM count x resident CTAs (3), 4 waves
   if (blocks > cap) blocks = cap;
   switch (mode) {
     case CORDUM_MODE_POLICY_ONLY: dispatch_kernel<CORDUM_MODE_POLICY_ONLY><<<blocks, 256, 0, s>>>(P); break;
