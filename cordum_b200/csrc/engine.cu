@@ -72,7 +72,7 @@ struct cordum_engine {
   DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
-  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush;
+  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush, b_skey, b_slab_lo, b_slab_hi, b_pool_sorted, b_pool_nok, b_lbm, b_lbm_off;
   uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
   std::vector<cordum_batch*> batches;   // live batches (guarded by mu): K2 must wait for their kernels
   bool pools_dirty = true;       // K2 must run before the next dispatch
@@ -193,6 +193,25 @@ int sync_tables(cordum_engine* e) {
     CK(e->b_pos_key.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
     CK(e->b_pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
     CK(e->b_pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+    CK(e->b_skey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+    CK(e->b_slab_lo.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+    CK(e->b_slab_hi.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+    CK(e->b_pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
+    {
+      // K2 sort buffer: next power of two >= the largest pool, capped at 8192 entries (96 KiB of shared memory)
+      uint32_t largest = 1;
+      for (uint32_t p = 0; p < t.n_pools; ++p) largest = std::max(largest, t.pool_off[p + 1] - t.pool_off[p]);
+      uint32_t cap = 32;
+      while (cap < largest && cap < 8192) cap <<= 1;
+      d.sort_cap = cap;
+    }
+    d.skey = (uint64_t*)e->b_skey.p; d.slab_lo = (uint64_t*)e->b_slab_lo.p; d.slab_hi = (uint64_t*)e->b_slab_hi.p;
+    d.pool_sorted = (uint8_t*)e->b_pool_sorted.p;
+    CK(e->b_pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+    CK(e->b_lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
+    CK(up(e->b_lbm_off, t.lbm_off, s), "upload");
+    d.pool_nok = (uint32_t*)e->b_pool_nok.p; d.lbm = (uint32_t*)e->b_lbm.p; d.lbm_off = (const uint32_t*)e->b_lbm_off.p;
+    d.place_bits = t.place_bits;
     d.n_pos = t.n_pos; d.n_pools = t.n_pools;
     d.pool_off = (const uint32_t*)e->b_pool_off.p; d.pos_pool = (const uint32_t*)e->b_pos_pool.p;
     d.pos_slot = (const uint32_t*)e->b_pos_slot.p; d.pos_rank = (const uint32_t*)e->b_pos_rank.p;
@@ -348,7 +367,7 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
                    &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_loads, &e->b_pos_key, &e->b_pool_best, &e->b_pool_mincnt,
-                   &e->b_flush};
+                   &e->b_flush, &e->b_skey, &e->b_slab_lo, &e->b_slab_hi, &e->b_pool_sorted, &e->b_pool_nok, &e->b_lbm, &e->b_lbm_off};
   for (DevBuf* b : all) b->release();
   if (e->ev_tables) cudaEventDestroy(e->ev_tables);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);

@@ -937,6 +937,14 @@ int Host::compile_workers(std::string& err) {
     t.pos_label_lo[i] = m[0]; t.pos_label_hi[i] = m[1];
   }
   for (uint32_t p = 0; p < t.n_pools; ++p) t.pool_off[p + 1] += t.pool_off[p];
+  // per-pool label bitmaps (filled on the device by worker_pool_kernel): place_bits rows of ceil(n/32) words
+  t.place_bits = std::max<uint32_t>(place_bits_, 1);
+  t.lbm_off.assign(std::max<uint32_t>(t.n_pools, 1), 0);
+  t.lbm_words = 0;
+  for (uint32_t p = 0; p < t.n_pools; ++p) {
+    t.lbm_off[p] = (uint32_t)t.lbm_words;
+    t.lbm_words += (uint64_t)t.place_bits * ((t.pool_off[p + 1] - t.pool_off[p] + 31) / 32);
+  }
   if (t.loads.empty()) t.loads.push_back(Load16{0, 0, 0.f, 0.f});
   t.v_workers++;
   t.v_loads++;

@@ -167,7 +167,9 @@ struct HostTables {
   uint32_t n_pools = 0;
   // workers
   uint32_t n_slots = 0, n_pos = 0;
-  std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot;
+  std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot, lbm_off;
+  uint32_t place_bits = 1;
+  uint64_t lbm_words = 0;
   std::vector<uint64_t> pos_label_lo, pos_label_hi;
   std::vector<Load16> loads;
   // change counters (engine re-uploads a group when its version moved)

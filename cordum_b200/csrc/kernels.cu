@@ -11,10 +11,11 @@
 // Integer / bit work only: no tensor cores (north star).  Mapping to the hardware:
 //   * job columns are column-major; a warp loads 32 consecutive jobs with one coalesced
 //     128 B request per u32 column (256 B per u64 column) through the read-only, no-L1-allocate path
-//   * 8 lanes cooperate on one job (4 jobs per warp at a time): one pass-row segment is
-//     1024 rules = 128 B = exactly one cache line = 8 lanes x one 128-bit load
+//   * the 32 lanes of a warp cooperate on one job's rule scan: lane = one 128-bit slice of every
+//     pass-row, so 4096 rules are ANDed per step with 7-12 independent 128-bit gathers per lane
 //   * rows are gathered through L1/L2 (the tables are a few MB: L2-resident, hot rows L1-resident)
-//   * first match = ballot over the 8 lanes + ffs; routing reductions are shuffles
+//   * first match = ballot + ffs; routing reductions are shuffles; worker pools are kept sorted by
+//     load (bitonic sort in shared memory) so label-constrained picks stop at the first match
 //   * decision records are written back coalesced, 16 B per lane
 // IEEE float32 with explicit _rn intrinsics, no fast-math: scores compare exactly like Go's.
 #include <cuda_runtime.h>
@@ -57,76 +58,137 @@ __device__ __forceinline__ uint32_t orderable(float s) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// A worker's key: (orderable load score << 32) | rank.  Overloaded workers keep their rank but carry
+// an all-ones score field, so they sort last and are never selected; KEY_NONE = no candidate / padding.
+__device__ __forceinline__ bool key_over(uint64_t k) { return (uint32_t)(k >> 32) == 0xFFFFFFFFu; }
+
 // (key, count-at-minimum-score) pairs form a commutative monoid under this merge
 __device__ __forceinline__ void merge_best(uint64_t& key, uint32_t& cnt, uint64_t k2, uint32_t c2) {
   uint32_t s1 = (uint32_t)(key >> 32), s2 = (uint32_t)(k2 >> 32);
-  if (k2 == KEY_NONE) return;
-  if (key == KEY_NONE || s2 < s1) { key = k2; cnt = c2; }
+  if (key_over(k2)) return;
+  if (key_over(key) || s2 < s1) { key = k2; cnt = c2; }
   else if (s2 == s1) { key = k2 < key ? k2 : key; cnt += c2; }
 }
 
-// Lowest rule in this lane's 128-bit slice that survives the per-rule subset tests
-// (requires: containsAll, safety_policy.go:320-330; labels: labelsMatch, :332-345), or -1.
-__device__ __forceinline__ int lowest_passing(uint4 acc, uint4 chk, uint32_t base, const DeviceTables& T, uint64_t req_mask,
-                                              uint64_t lab_mask, bool has_labels) {
-  const uint32_t a[4] = {acc.x, acc.y, acc.z, acc.w};
-  const uint32_t c[4] = {chk.x, chk.y, chk.z, chk.w};
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    uint32_t bits = a[w];
-    while (bits) {
-      int b = __ffs(bits) - 1;
-      uint32_t r = base + w * 32 + b;
-      if (!((c[w] >> b) & 1u)) return (int)r;
-      uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
-      bool ok = ((need & ~req_mask) == 0) && (ln == 0 || (has_labels && (ln & ~lab_mask) == 0));
-      if (ok) return (int)r;
-      bits &= bits - 1;
+// First surviving rule of a 4096-rule step, resolved with warp-uniform control flow: take the
+// lowest candidate bit (lowest lane, lowest bit); if that rule carries a requires / labels
+// subset test (containsAll, safety_policy.go:320-330; labelsMatch, :332-345) evaluate it once for
+// the whole warp (uniform address -> one broadcast load) and drop the bit if it fails.
+__device__ __forceinline__ int first_match(uint4 acc, uint4 chk, uint32_t base, unsigned lane, const DeviceTables& T,
+                                           uint64_t req_mask, uint64_t lab_mask, bool has_labels) {
+  while (true) {
+    const unsigned bal = __ballot_sync(FULL, (acc.x | acc.y | acc.z | acc.w) != 0);
+    if (!bal) return -1;
+    const int L = __ffs(bal) - 1;
+    int bit = acc.x ? __ffs(acc.x) - 1 : acc.y ? 32 + __ffs(acc.y) - 1 : acc.z ? 64 + __ffs(acc.z) - 1 : 96 + __ffs(acc.w) - 1;
+    const uint32_t w = (uint32_t)bit >> 5, m = 1u << (bit & 31);
+    const uint32_t cw = w == 0 ? chk.x : w == 1 ? chk.y : w == 2 ? chk.z : chk.w;
+    int info = bit | ((cw & m) ? 0x100 : 0);
+    info = __shfl_sync(FULL, info, L);
+    const int r = (int)(base + (uint32_t)L * 128u) + (info & 0xFF);
+    if (!(info & 0x100)) return r;
+    const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
+    if (((need & ~req_mask) == 0) && (ln == 0 || (has_labels && (ln & ~lab_mask) == 0))) return r;
+    if ((int)lane == L) {   // drop the failed rule and look again
+      if (w == 0) acc.x &= ~m; else if (w == 1) acc.y &= ~m; else if (w == 2) acc.z &= ~m; else acc.w &= ~m;
     }
   }
-  return -1;
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------ K2: one CTA per pool
-__global__ void __launch_bounds__(128) worker_pool_kernel(DeviceTables T) {
-  const uint32_t p = blockIdx.x;
-  const uint32_t a = T.pool_off[p], b = T.pool_off[p + 1];
-  __shared__ uint64_t s_key[4];
-  __shared__ uint32_t s_cnt[4];
-  uint64_t best = KEY_NONE;
-  for (uint32_t pos = a + threadIdx.x; pos < b; pos += blockDim.x) {
-    const Load16 L = T.loads[T.pos_slot[pos]];
-    bool over = false;
-    if (L.max_parallel > 0) over = __fdiv_rn(__int2float_rn(L.active), __int2float_rn(L.max_parallel)) >= 0.9f;
-    over = over || L.cpu >= 90.0f || L.gpu >= 90.0f;
-    float score = __fadd_rn(__fadd_rn(__int2float_rn(L.active), __fdiv_rn(L.cpu, 100.0f)), __fdiv_rn(L.gpu, 100.0f));
-    uint64_t key = over ? KEY_NONE : (((uint64_t)orderable(score) << 32) | T.pos_rank[pos]);
-    T.pos_key[pos] = key;
-    best = key < best ? key : best;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { uint64_t v = shfl64_xor(FULL, best, o); best = v < best ? v : best; }
-  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
-  __syncthreads();
-  best = s_key[0];
-  for (int w = 1; w < 4; ++w) best = s_key[w] < best ? s_key[w] : best;
-  // second pass: how many workers share the minimum score (tie detection)
-  uint32_t cnt = 0;
-  if (best != KEY_NONE)
-    for (uint32_t pos = a + threadIdx.x; pos < b; pos += blockDim.x) {
-      uint64_t k = T.pos_key[pos];
-      cnt += (k != KEY_NONE && (uint32_t)(k >> 32) == (uint32_t)(best >> 32)) ? 1u : 0u;
+// Per heartbeat epoch: load score + overload test per worker, then a bitonic sort of the pool's
+// keys in shared memory.  The sorted view (keys + label masks in load order) lets label-constrained
+// jobs scan a pool from its least-loaded worker and stop at the first label match.
+__global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_cnt;
+  const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a;
+  uint32_t n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  const bool sortable = n_pad <= T.sort_cap;
+  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* si = reinterpret_cast<uint32_t*>(sk + (sortable ? n_pad : 0));
+  if (tid == 0) s_cnt = 0;
+  for (uint32_t i = tid; i < (sortable ? n_pad : n); i += nt) {
+    uint64_t key = KEY_NONE;
+    if (i < n) {
+      const uint32_t pos = a + i;
+      const Load16 L = T.loads[T.pos_slot[pos]];
+      bool over = false;
+      if (L.max_parallel > 0) over = __fdiv_rn(__int2float_rn(L.active), __int2float_rn(L.max_parallel)) >= 0.9f;   // :177-184
+      over = over || L.cpu >= 90.0f || L.gpu >= 90.0f;                                                               // :185-191
+      const float score = __fadd_rn(__fadd_rn(__int2float_rn(L.active), __fdiv_rn(L.cpu, 100.0f)), __fdiv_rn(L.gpu, 100.0f));   // :157-159
+      key = ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
+      T.pos_key[pos] = key;
     }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    T.pool_best[p] = best;
-    T.pool_mincnt[p] = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+    if (sortable) { sk[i] = key; si[i] = i; }
   }
+  __syncthreads();
+  if (!sortable) {   // pool larger than the sort buffer: min/count by reduction, jobs fall back to full scans
+    __shared__ uint64_t s_best;
+    if (tid == 0) s_best = KEY_NONE;
+    __syncthreads();
+    uint64_t best = KEY_NONE;
+    for (uint32_t i = tid; i < n; i += nt) { uint64_t k = T.pos_key[a + i]; if (!key_over(k) && k < best) best = k; }
+    atomicMin(reinterpret_cast<unsigned long long*>(&s_best), (unsigned long long)best);
+    __syncthreads();
+    best = s_best;
+    uint32_t c = 0;
+    for (uint32_t i = tid; i < n; i += nt) { uint64_t k = T.pos_key[a + i]; c += (!key_over(k) && (uint32_t)(k >> 32) == (uint32_t)(best >> 32)) ? 1u : 0u; }
+    if (c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (tid == 0) { T.pool_best[p] = best; T.pool_mincnt[p] = best == KEY_NONE ? 0 : s_cnt; T.pool_sorted[p] = 0; }
+    return;
+  }
+  for (uint32_t k = 2; k <= n_pad; k <<= 1)
+    for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+      for (uint32_t i = tid; i < n_pad; i += nt) {
+        const uint32_t x = i ^ jj;
+        if (x > i) {
+          const uint64_t ki = sk[i], kx = sk[x];
+          if ((ki > kx) == ((i & k) == 0)) { sk[i] = kx; sk[x] = ki; const uint32_t t = si[i]; si[i] = si[x]; si[x] = t; }
+        }
+      }
+      __syncthreads();
+    }
+  const uint64_t k0 = n ? sk[0] : KEY_NONE;
+  const bool none = n == 0 || key_over(k0);
+  __shared__ uint32_t s_nok;
+  if (tid == 0) s_nok = 0;
+  __syncthreads();
+  // sorted view + label bitmaps: a warp takes 32 consecutive sorted workers (one bitmap word per label bit)
+  const uint32_t words = (n + 31) >> 5, lane = tid & 31, nbits = T.place_bits;
+  uint32_t* bm = T.lbm + T.lbm_off[p];
+  uint32_t c = 0, ok = 0;
+  for (uint32_t w = tid >> 5; w < words; w += nt >> 5) {
+    const uint32_t i = w * 32 + lane;
+    uint64_t k = KEY_NONE, llo = 0, lhi = 0;
+    if (i < n) {
+      k = sk[i];
+      const uint32_t src = a + si[i];
+      llo = T.pos_label_lo[src]; lhi = T.pos_label_hi[src];
+      T.skey[a + i] = k; T.slab_lo[a + i] = llo; T.slab_hi[a + i] = lhi;
+      c += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
+      ok += key_over(k) ? 0u : 1u;
+    }
+    for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {   // lane t keeps the word of label bit b0+t, then one strided store each
+      uint32_t mine = 0;
+      const uint32_t lim = nbits - b0 < 32 ? nbits - b0 : 32;
+      for (uint32_t t = 0; t < lim; ++t) {
+        const uint32_t bit = b0 + t;
+        const unsigned bal = __ballot_sync(FULL, ((bit < 64 ? llo >> bit : lhi >> (bit - 64)) & 1ull) != 0);
+        if (lane == t) mine = bal;
+      }
+      if (lane < lim) bm[(size_t)(b0 + lane) * words + w] = mine;
+    }
+  }
+  if (c) atomicAdd(&s_cnt, c);
+  if (ok) atomicAdd(&s_nok, ok);
+  __syncthreads();
+  if (tid == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_mincnt[p] = s_cnt; T.pool_sorted[p] = 1; T.pool_nok[p] = s_nok; }
 }
 
 // ------------------------------------------------------------------ fused policy + route
@@ -219,16 +281,13 @@ __global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
             }
           }
           const uint4 both = and4(acc, chk);
-          int local = -1;
+          uint64_t req = 0, lab = 0;
           if (__any_sync(FULL, (both.x | both.y | both.z | both.w) != 0)) {
             // some surviving rule carries a requires / labels subset test: fetch the job's masks
-            const uint64_t req = shfl64(FULL, c_req, i), lab = shfl64(FULL, c_lab, i);
-            if (acc.x | acc.y | acc.z | acc.w) local = lowest_passing(acc, chk, u * 128u, T, req, lab, fl & JF_HAS_LABELS);
-          } else if (acc.x | acc.y | acc.z | acc.w) {
-            local = (int)(u * 128u) + (acc.x ? __ffs(acc.x) - 1 : acc.y ? 32 + __ffs(acc.y) - 1 : acc.z ? 64 + __ffs(acc.z) - 1 : 96 + __ffs(acc.w) - 1);
+            req = shfl64(FULL, c_req, i); lab = shfl64(FULL, c_lab, i);
           }
-          const unsigned bal = __ballot_sync(FULL, local >= 0);
-          if (bal) { f = __shfl_sync(FULL, local, __ffs(bal) - 1); break; }   // lowest lane = lowest rule
+          f = first_match(acc, chk, u0 * 128u, lane, T, req, lab, fl & JF_HAS_LABELS);
+          if (f >= 0) break;
         }
         if ((int)lane == i) first = f;
       }
@@ -329,7 +388,7 @@ __global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
               bool took_pref = false;
               if (pw_pos >= 0 && pw_in_set && !unsat) {                           // :73-87
                 uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
-                if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && T.pos_key[pw_pos] != KEY_NONE) {
+                if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && !key_over(T.pos_key[pw_pos])) {
                   took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
                 }
               }
@@ -355,23 +414,68 @@ __global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
         const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
         uint64_t b = KEY_NONE;
         uint32_t bc = 0, tot = 0;
+        // pass 1: each eligible pool is walked in load order; the first label match is that pool's argmin
         for (uint32_t k = 0; k < cnt; ++k) {
           const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
           if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
           const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
-          for (uint32_t pos = a + lane; pos < e; pos += 32) {   // matchesLabels (:161-175), coalesced
-            const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
-            if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
-            tot++;
-            merge_best(b, bc, T.pos_key[pos], 1);
-          }
-        }
+          if (!T.pool_sorted[pid]) {   // pool larger than K2's sort buffer: unordered scan
+            uint64_t pb = KEY_NONE; uint32_t pc = 0;
+            for (uint32_t pos = a + lane; pos < e; pos += 32) {
+              const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
+              if ((llo & need_lo) == need_lo && (lhi & need_hi) == need_hi) merge_best(pb, pc, T.pos_key[pos], 1);
+            }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          const uint64_t k2 = shfl64_xor(FULL, b, o);
-          const uint32_t c2 = __shfl_xor_sync(FULL, bc, o);
-          merge_best(b, bc, k2, c2);
-          tot += __shfl_xor_sync(FULL, tot, o);
+            for (int o = 16; o; o >>= 1) { const uint64_t k2 = shfl64_xor(FULL, pb, o); const uint32_t c2 = __shfl_xor_sync(FULL, pc, o); merge_best(pb, pc, k2, c2); }
+            merge_best(b, bc, pb, pc);
+            continue;
+          }
+          // sorted pool: AND the bitmaps of the required label bits (lane = 32 sorted workers).  The first set
+          // bit among the non-overloaded prefix is the pool's least-loaded label match (matchesLabels, :161-175).
+          uint64_t kstar = KEY_NONE;
+          uint32_t kc = 0;
+          bool tie_done = false;
+          const uint32_t words = (e - a + 31) >> 5, nok = T.pool_nok[pid];
+          const uint32_t* bm = T.lbm + __ldg(T.lbm_off + pid);
+          for (uint32_t w0 = 0; w0 < words && !tie_done; w0 += 32) {
+            const uint32_t w = w0 + lane;
+            uint32_t v = 0;
+            if (w < words) {
+              v = 0xFFFFFFFFu;
+              for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(size_t)(__ffsll((long long)m) - 1) * words + w];
+              for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(size_t)(64 + __ffsll((long long)m) - 1) * words + w];
+            }
+            tot += __popc(v);                                     // label-matching candidates, overloaded ones included
+            const uint32_t lo = w * 32;
+            uint32_t okv = lo >= nok ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));   // non-overloaded prefix
+            while (!tie_done) {
+              const unsigned hit = __ballot_sync(FULL, okv != 0);
+              if (!hit) break;
+              const int L = __ffs(hit) - 1;
+              const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(__ffs(okv) - 1), L);
+              const uint64_t kk = T.skey[a + pos];
+              if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
+              else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; tie_done = true; }   // next match decides the tie flag
+              if ((int)lane == L) okv &= okv - 1;
+            }
+          }
+          merge_best(b, bc, kstar, kc);
+        }
+        // Nobody qualified: were there label-matching (overloaded) candidates at all?  (:114-119)
+        // Sorted pools already counted theirs above; unsorted pools need a counting scan.
+        if (b == KEY_NONE) {
+          for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
+            if (T.pool_sorted[pid]) continue;
+            if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+            const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
+            for (uint32_t pos = a + lane; pos < e; pos += 32) {
+              const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
+              tot += ((llo & need_lo) == need_lo && (lhi & need_hi) == need_hi) ? 1u : 0u;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
         }
         if ((int)lane == i) { best = b; bcnt = bc; total = tot; }
       }
@@ -394,7 +498,14 @@ __global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
   if (T.n_pools == 0) return cudaSuccess;
-  worker_pool_kernel<<<T.n_pools, 128, 0, s>>>(T);
+  const size_t smem = (size_t)T.sort_cap * 12;   // u64 key + u32 index per entry
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(worker_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  worker_pool_kernel<<<T.n_pools, 256, smem, s>>>(T);
   return cudaGetLastError();
 }
 

@@ -100,7 +100,17 @@ typedef struct DeviceTables {
   const uint64_t* pos_label_lo;               /* placement label mask                                   */
   const uint64_t* pos_label_hi;
   const Load16* loads;                          /* [n_slots] {active, max_parallel, cpu(f32), gpu(f32)}   */
-  uint64_t* pos_key;                          /* derived: (orderable score << 32) | rank; ~0 overloaded */
+  uint64_t* pos_key;                          /* derived: (orderable score << 32) | rank; score field all-ones = overloaded */
+  uint64_t* skey;                             /* derived: per pool, keys in ascending order (load-sorted view of the pool)  */
+  uint64_t* slab_lo;                          /* derived: label masks permuted into the same order                          */
+  uint64_t* slab_hi;
+  uint8_t* pool_sorted;                       /* derived: 1 if the pool's sorted view is valid (pool fits the sort buffer)  */
+  uint32_t* pool_nok;                         /* derived: workers of the pool that are NOT overloaded (= prefix of the sorted view) */
+  uint32_t* lbm;                              /* derived: label bitmaps over the sorted view: lbm[lbm_off[p] + bit*words(p) + w],
+                                                 bit i of word w = "sorted worker 32w+i carries label bit"               */
+  const uint32_t* lbm_off;                    /* [n_pools] word offset of the pool's bitmaps                               */
+  uint32_t place_bits;                        /* label bits in use (<= 128)                                                */
+  uint32_t sort_cap;                          /* entries the K2 shared-memory sort buffer holds (power of two)             */
   uint64_t* pool_best;                        /* derived: min key per pool (~0 = none)                  */
   uint32_t* pool_mincnt;                      /* derived: workers in the pool sharing the min score     */
 } DeviceTables;
