@@ -154,7 +154,7 @@ int sync_tables(cordum_engine* e) {
     d.row_cap = (const Row16*)e->b_row_cap.p; d.n_cap = t.row_cap.n_rows;
     d.row_pack = (const Row16*)e->b_row_pack.p; d.n_pack = t.row_pack.n_rows;
     d.row_actor = (const Row16*)e->b_row_actor.p; d.n_actor = t.row_actor.n_rows;
-    d.row_combo = (const Row16*)e->b_row_combo.p; d.row_risk = (const Row16*)e->b_row_risk.p;
+    d.row_combo = (const Row16*)e->b_row_combo.p; d.row_risk = (const Row16*)e->b_row_risk.p; d.risk_zero_row = t.risk_zero_row;
     d.row_check = (const Row16*)e->b_row_check.p;
     d.rule_req_need = (const uint64_t*)e->b_req_need.p; d.rule_lab_need = (const uint64_t*)e->b_lab_need.p;
     d.rule_dec = (const uint8_t*)e->b_rule_dec.p;
@@ -173,7 +173,7 @@ int sync_tables(cordum_engine* e) {
   if (t.v_mcp != e->v_mcp) {
     for (int f = 0; f < 4; ++f) {
       CK(up(e->b_row_mcp[f], t.row_mcp[f].data, s), "upload");
-      d.row_mcp[f] = (const Row16*)e->b_row_mcp[f].p; d.n_mcp[f] = t.row_mcp[f].n_rows;
+      d.row_mcp[f] = (const Row16*)e->b_row_mcp[f].p; d.n_mcp[f] = t.row_mcp[f].n_rows; d.mcp_ones_row[f] = t.mcp_ones_row[f];
     }
     CK(up(e->b_tenant_mcp, t.tenant_mcp, s), "upload"); CK(up(e->b_eff_mcp, t.eff_mcp, s), "upload");
     d.tenant_mcp = (const uint8_t*)e->b_tenant_mcp.p; d.eff_mcp = (const uint8_t*)e->b_eff_mcp.p; d.mcp_stride = t.mcp_stride;

@@ -381,6 +381,7 @@ void Host::compile_policy() {
   const uint32_t R = (uint32_t)rules.size();
   t.n_rules = R;
   t.n_seg = std::max<uint32_t>(1, (R + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
+  if (t.n_seg > 2) t.n_seg = (t.n_seg + 3) & ~3u;   // the kernel ANDs 4 segments per step: pad with empty segments
   t.row_words = t.n_seg * 32;
   const uint32_t W = t.row_words;
   d_tenant_.clear(); d_cap_.clear(); d_pack_.clear(); d_actor_.clear(); d_risk_.clear();
@@ -430,7 +431,8 @@ void Host::compile_policy() {
       }
     }
     uint32_t nb = d_risk_.size() - 2;
-    t.row_risk.init(1 + nb, W);
+    t.row_risk.init(2 + nb, W);     // + one all-zero row at the end
+    t.risk_zero_row = 1 + nb;
     or_bits(t.row_risk.row(0), vac);
     for (uint32_t b = 0; b < nb; ++b) {
       uint32_t* row = t.row_risk.row(1 + b);
@@ -582,7 +584,9 @@ void Host::compile_mcp_tables() {
       for (auto& e : m.allow[f]) allow_hits[d.table.find(fold_key(e), 0)].push_back(r);
       for (auto& e : m.deny[f]) deny_hits[d.table.find(fold_key(e), 0)].push_back(r);
     }
-    t.row_mcp[f].init(d.size(), W);
+    t.row_mcp[f].init(d.size() + 1, W);   // + one all-ones row at the end (jobs that carry no MCP labels)
+    t.mcp_ones_row[f] = d.size();
+    for (uint32_t k = 0; k < W; ++k) t.row_mcp[f].row(d.size())[k] = 0xFFFFFFFFu;
     for (uint32_t id = 0; id < d.size(); ++id) {
       uint32_t* row = t.row_mcp[f].row(id);
       or_bits(row, base);

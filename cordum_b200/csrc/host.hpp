@@ -157,6 +157,7 @@ struct HostTables {
   std::vector<uint64_t> rule_req_need, rule_lab_need;
   std::vector<uint8_t> rule_dec;
   uint32_t mcp_stride = 2;
+  uint32_t risk_zero_row = 0, mcp_ones_row[4] = {0, 0, 0, 0};
   std::vector<uint8_t> tenant_mcp, eff_mcp, eff_topic;
   uint32_t topic_stride = 0, n_effcfg = 0;
   // routing

@@ -20,6 +20,7 @@
 // IEEE float32 with explicit _rn intrinsics, no fast-math: scores compare exactly like Go's.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/cordum_b200.h"
 #include "kernels.h"
@@ -68,31 +69,6 @@ __device__ __forceinline__ void merge_best(uint64_t& key, uint32_t& cnt, uint64_
   if (key_over(k2)) return;
   if (key_over(key) || s2 < s1) { key = k2; cnt = c2; }
   else if (s2 == s1) { key = k2 < key ? k2 : key; cnt += c2; }
-}
-
-// First surviving rule of a 4096-rule step, resolved with warp-uniform control flow: take the
-// lowest candidate bit (lowest lane, lowest bit); if that rule carries a requires / labels
-// subset test (containsAll, safety_policy.go:320-330; labelsMatch, :332-345) evaluate it once for
-// the whole warp (uniform address -> one broadcast load) and drop the bit if it fails.
-__device__ __forceinline__ int first_match(uint4 acc, uint4 chk, uint32_t base, unsigned lane, const DeviceTables& T,
-                                           uint64_t req_mask, uint64_t lab_mask, bool has_labels) {
-  while (true) {
-    const unsigned bal = __ballot_sync(FULL, (acc.x | acc.y | acc.z | acc.w) != 0);
-    if (!bal) return -1;
-    const int L = __ffs(bal) - 1;
-    int bit = acc.x ? __ffs(acc.x) - 1 : acc.y ? 32 + __ffs(acc.y) - 1 : acc.z ? 64 + __ffs(acc.z) - 1 : 96 + __ffs(acc.w) - 1;
-    const uint32_t w = (uint32_t)bit >> 5, m = 1u << (bit & 31);
-    const uint32_t cw = w == 0 ? chk.x : w == 1 ? chk.y : w == 2 ? chk.z : chk.w;
-    int info = bit | ((cw & m) ? 0x100 : 0);
-    info = __shfl_sync(FULL, info, L);
-    const int r = (int)(base + (uint32_t)L * 128u) + (info & 0xFF);
-    if (!(info & 0x100)) return r;
-    const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
-    if (((need & ~req_mask) == 0) && (ln == 0 || (has_labels && (ln & ~lab_mask) == 0))) return r;
-    if ((int)lane == L) {   // drop the failed rule and look again
-      if (w == 0) acc.x &= ~m; else if (w == 1) acc.y &= ~m; else if (w == 2) acc.z &= ~m; else acc.w &= ~m;
-    }
-  }
 }
 
 }  // namespace
@@ -201,8 +177,8 @@ __global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
 //      filter / per-pool argmin merge, thread-per-job (32 jobs at once, scalar code).
 //   S  only for jobs with placement labels: warp-cooperative scan of the eligible pools' worker
 //      slices (coalesced 8 B loads of label masks and keys) + shuffle reduction.
-template <int MODE>
-__global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
+template <int MODE, int SEGS, int MINB>
+__global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
   const unsigned lane = threadIdx.x & 31;
@@ -237,59 +213,135 @@ __global__ void __launch_bounds__(256, 3) dispatch_kernel(KParams P) {
     }
 
     // =================================================================== P: first matching rule
+    // 8 rounds x 4 jobs: the 8 lanes of group g AND the pass-rows of job (round*4+g); each lane holds
+    // SEGS 128-bit slices (lane `sub` of segment s covers rules s*1024 + sub*128 ..+127).  All four groups
+    // run the same instruction stream (no divergence) with 7-12 x SEGS independent gathers in flight.
     int first = -1;
     const bool bypass = MODE == CORDUM_MODE_POLICY_AND_ROUTE && (c_flags & JF_APPROVED);                 // engine.go:484-522
     const bool early = (c_flags & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED)) != 0;                        // kernel.go:171-176
     const bool eval = valid && MODE != CORDUM_MODE_ROUTE_ONLY && !bypass && !early;
     if (MODE != CORDUM_MODE_ROUTE_ONLY) {
-      for (unsigned todo = __ballot_sync(FULL, eval); todo; todo &= todo - 1) {
-        const int i = __ffs(todo) - 1;
-        const uint32_t fl = __shfl_sync(FULL, c_flags, i);
-        const Row16* p_combo = T.row_combo + (size_t)(fl & JF_COMBO_MASK) * rowu4;
-        const Row16* p_tenant = T.row_tenant + (size_t)__shfl_sync(FULL, c_tenant, i) * rowu4;
-        const Row16* p_topic = T.row_topic + (size_t)__shfl_sync(FULL, c_topic, i) * rowu4;
-        const Row16* p_cap = T.row_cap + (size_t)__shfl_sync(FULL, c_cap, i) * rowu4;
-        const Row16* p_pack = T.row_pack + (size_t)__shfl_sync(FULL, c_pack, i) * rowu4;
-        const Row16* p_actor = T.row_actor + (size_t)__shfl_sync(FULL, c_actor, i) * rowu4;
-        const uint64_t risk = shfl64(FULL, c_risk, i);
-        const bool mcp_used = fl & JF_MCP_USED;
+      const unsigned g = lane >> 3, sub = lane & 7;
+      // row offsets of this lane's own job (in Row16 units), computed once per tile
+      const uint32_t o_combo = (c_flags & JF_COMBO_MASK) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
+                     o_cap = c_cap * rowu4, o_pack = c_pack * rowu4, o_actor = c_actor * rowu4;
+      const unsigned evalmask = __ballot_sync(FULL, eval);
+#pragma unroll 1
+      for (int round = 0; round < 8; ++round) {
+        if (!((evalmask >> (round * 4)) & 0xFu)) continue;
+        const int src = round * 4 + (int)g;
+        bool active = (evalmask >> src) & 1u;
+        const uint32_t fl = __shfl_sync(FULL, c_flags, src);
+        const Row16* p_combo = T.row_combo + __shfl_sync(FULL, o_combo, src) + sub;
+        const Row16* p_tenant = T.row_tenant + __shfl_sync(FULL, o_tenant, src) + sub;
+        const Row16* p_topic = T.row_topic + __shfl_sync(FULL, o_topic, src) + sub;
+        const Row16* p_cap = T.row_cap + __shfl_sync(FULL, o_cap, src) + sub;
+        const Row16* p_pack = T.row_pack + __shfl_sync(FULL, o_pack, src) + sub;
+        const Row16* p_actor = T.row_actor + __shfl_sync(FULL, o_actor, src) + sub;
+        const uint64_t risk = shfl64(FULL, c_risk, src);
+        const bool mcp_used = active && (fl & JF_MCP_USED);
+        const bool any_mcp = __any_sync(FULL, mcp_used);
         uint32_t mid[4] = {0, 0, 0, 0};
-        if (mcp_used) {
-          mid[0] = __shfl_sync(FULL, c_m0, i); mid[1] = __shfl_sync(FULL, c_m1, i);
-          mid[2] = __shfl_sync(FULL, c_m2, i); mid[3] = __shfl_sync(FULL, c_m3, i);
+        if (any_mcp) {
+          mid[0] = __shfl_sync(FULL, c_m0, src); mid[1] = __shfl_sync(FULL, c_m1, src);
+          mid[2] = __shfl_sync(FULL, c_m2, src); mid[3] = __shfl_sync(FULL, c_m3, src);
         }
-        int f = -1;
-        for (uint32_t u0 = 0; u0 < rowu4; u0 += 32) {   // 4096 rules per step, in rule order
-          const uint32_t u = u0 + lane;
-          uint4 acc = make_uint4(0, 0, 0, 0), chk = make_uint4(0, 0, 0, 0);
-          if (u < rowu4) {
-            // independent gathers first (memory-level parallelism), then combine
-            uint4 r0 = ld_row(p_combo + u), r1 = ld_row(p_tenant + u), r2 = ld_row(p_topic + u), r3 = ld_row(p_cap + u),
-                  r4 = ld_row(p_pack + u), r5 = ld_row(p_actor + u);
-            chk = ld_row(T.row_check + u);
-            uint4 rk;
-            if (risk == 0) rk = ld_row(T.row_risk + u);
-            else {
-              rk = make_uint4(0, 0, 0, 0);
-              for (uint64_t m = risk; m; m &= m - 1)   // containsAny: OR over the job's tags (:308-318)
-                rk = or4(rk, ld_row(T.row_risk + (size_t)(1 + (__ffsll((long long)m) - 1)) * rowu4 + u));
-            }
-            acc = and4(and4(and4(r0, r1), and4(r2, r3)), and4(and4(r4, r5), rk));
-            if (mcp_used) {   // mcpMatch (:365-382)
+        if (any_mcp) {   // groups whose job carries no MCP labels read the all-ones row: same instruction stream
 #pragma unroll
-              for (int q = 0; q < 4; ++q) acc = and4(acc, ld_row(T.row_mcp[q] + (size_t)mid[q] * rowu4 + u));
-            }
-          }
-          const uint4 both = and4(acc, chk);
-          uint64_t req = 0, lab = 0;
-          if (__any_sync(FULL, (both.x | both.y | both.z | both.w) != 0)) {
-            // some surviving rule carries a requires / labels subset test: fetch the job's masks
-            req = shfl64(FULL, c_req, i); lab = shfl64(FULL, c_lab, i);
-          }
-          f = first_match(acc, chk, u0 * 128u, lane, T, req, lab, fl & JF_HAS_LABELS);
-          if (f >= 0) break;
+          for (int q = 0; q < 4; ++q) if (!mcp_used) mid[q] = T.mcp_ones_row[q];
         }
-        if ((int)lane == i) first = f;
+        const Row16* p_mcp[4] = {T.row_mcp[0] + (size_t)mid[0] * rowu4 + sub, T.row_mcp[1] + (size_t)mid[1] * rowu4 + sub,
+                                 T.row_mcp[2] + (size_t)mid[2] * rowu4 + sub, T.row_mcp[3] + (size_t)mid[3] * rowu4 + sub};
+        const Row16* p_risk = T.row_risk + sub;
+        const uint32_t* chk_words = reinterpret_cast<const uint32_t*>(T.row_check);
+        int found = -1;
+        uint32_t rule_base = sub * 128u;   // first rule of this lane's slice in segment s0
+        for (uint32_t s0 = 0; s0 < T.n_seg; s0 += SEGS) {   // n_seg is a multiple of SEGS (host pads)
+          uint4 acc[SEGS];
+#pragma unroll
+          for (int s = 0; s < SEGS; ++s) {
+            const int u = s * (int)CORDUM_SEG_U4;
+            acc[s] = and4(and4(and4(ld_row(p_combo + u), ld_row(p_tenant + u)), and4(ld_row(p_topic + u), ld_row(p_cap + u))),
+                          and4(ld_row(p_pack + u), ld_row(p_actor + u)));
+          }
+          {   // risk tags: containsAny = OR over the job's tags (:308-318).  Branch-free: row 0 = "no referenced tag",
+              // row 1+b = tag b, and lanes that ran out of tags read the all-zero row.
+            uint64_t m = risk;
+            uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
+            m &= m - 1;
+            uint4 rk[SEGS];
+#pragma unroll
+            for (int s = 0; s < SEGS; ++s) rk[s] = ld_row(p_risk + (size_t)idx * rowu4 + s * (int)CORDUM_SEG_U4);
+            while (__any_sync(FULL, m != 0)) {
+              idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
+              m &= m - 1;
+#pragma unroll
+              for (int s = 0; s < SEGS; ++s) rk[s] = or4(rk[s], ld_row(p_risk + (size_t)idx * rowu4 + s * (int)CORDUM_SEG_U4));
+            }
+#pragma unroll
+            for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], rk[s]);
+          }
+          if (any_mcp) {   // mcpMatch (:365-382)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], ld_row(p_mcp[q] + s * (int)CORDUM_SEG_U4));
+          }
+          const uint32_t keep = active ? 0xFFFFFFFFu : 0u;   // jobs that are not evaluated (or already matched) contribute nothing
+#pragma unroll
+          for (int s = 0; s < SEGS; ++s) { acc[s].x &= keep; acc[s].y &= keep; acc[s].z &= keep; acc[s].w &= keep; }
+
+          // lowest surviving rule of each group; re-evaluated only when a requires/labels subset test fails
+          uint64_t req = 0, lab = 0;
+          bool have_masks = false;
+          while (true) {
+            uint32_t nzs = 0;
+#pragma unroll
+            for (int s = 0; s < SEGS; ++s) nzs |= ((acc[s].x | acc[s].y | acc[s].z | acc[s].w) != 0 ? 1u : 0u) << s;
+            uint32_t gk = nzs ? (((uint32_t)__ffs(nzs) - 1u) << 3 | sub) : 63u;   // order: segment, then lane
+            gk = min(gk, __shfl_xor_sync(FULL, gk, 1));
+            gk = min(gk, __shfl_xor_sync(FULL, gk, 2));
+            gk = min(gk, __shfl_xor_sync(FULL, gk, 4));
+            const bool have = gk != 63u;
+            const uint32_t ws = gk >> 3, wl = gk & 7u;   // winning segment / lane of the group
+            uint4 v = acc[0];
+#pragma unroll
+            for (int t = 1; t < SEGS; ++t) if (ws == (uint32_t)t) v = acc[t];
+            const uint64_t vlo = (uint64_t)v.x | ((uint64_t)v.y << 32), vhi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            const int mybit = vlo ? __ffsll((long long)vlo) - 1 : 63 + __ffsll((long long)vhi);
+            const int bit = __shfl_sync(FULL, mybit, (int)(g * 8 + wl));
+            const int gmin = (int)((s0 + ws) * CORDUM_SEG_RULES + wl * 128u) + bit;
+            // does the winning rule carry a requires / labels subset test?  (row_check bit; one address per group)
+            const bool pend = have && ((__ldg(chk_words + ((uint32_t)gmin >> 5)) >> (gmin & 31)) & 1u);
+            const unsigned pb = __ballot_sync(FULL, pend);
+            if (!pb) { if (have) found = gmin; break; }
+            if (!have_masks) { req = shfl64(FULL, c_req, src); lab = shfl64(FULL, c_lab, src); have_masks = true; }
+            bool ok = true;
+            if (pend) {   // containsAll (:320-330), labelsMatch (:332-345)
+              const uint64_t need = __ldg(T.rule_req_need + gmin), ln = __ldg(T.rule_lab_need + gmin);
+              ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
+            }
+            if (pend && !ok && sub == wl) {   // drop the failed rule and look again
+              const uint32_t w = ((uint32_t)bit >> 5) & 3u, mk = ~(1u << (bit & 31));
+#pragma unroll
+              for (int t = 0; t < SEGS; ++t)
+                if ((uint32_t)t == ws) { if (w == 0) acc[t].x &= mk; else if (w == 1) acc[t].y &= mk; else if (w == 2) acc[t].z &= mk; else acc[t].w &= mk; }
+            }
+            if (!__any_sync(FULL, pend && !ok)) { if (have) found = gmin; break; }
+          }
+          if (found >= 0) active = false;
+          if (!__any_sync(FULL, active)) break;   // every job of this round has its first match
+          p_combo += SEGS * CORDUM_SEG_U4; p_tenant += SEGS * CORDUM_SEG_U4; p_topic += SEGS * CORDUM_SEG_U4;
+          p_cap += SEGS * CORDUM_SEG_U4; p_pack += SEGS * CORDUM_SEG_U4; p_actor += SEGS * CORDUM_SEG_U4;
+          p_risk += SEGS * CORDUM_SEG_U4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p_mcp[q] += SEGS * CORDUM_SEG_U4;
+          rule_base += SEGS * CORDUM_SEG_RULES;
+        }
+        (void)rule_base;
+        // hand the result to the lane that owns the job (lane L was served in round L>>2 by group L&3)
+        const int v = __shfl_sync(FULL, found, (int)(lane & 3) * 8);
+        if ((int)(lane >> 2) == round) first = v;
       }
     }
 
@@ -513,13 +565,22 @@ cudaError_t launch_dispatch(const KParams& P, uint32_t mode, int sm_count, cudaS
   if (P.n_jobs == 0) return cudaSuccess;
   const uint32_t tiles = (P.n_jobs + 31u) / 32u;
   uint32_t blocks = (tiles + 7u) / 8u;                  // 8 warps (tiles) per 256-thread CTA
-  const uint32_t cap = (uint32_t)sm_count * 3u * 4u;    // grid = multiple of SM count x resident CTAs (3), 4 waves
+  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 3; }();   // tuning knob
+  static const int waves = []() { const char* v = getenv("CORDUM_WAVES"); return v ? atoi(v) : 4; }();
+  const uint32_t cap = (uint32_t)sm_count * (uint32_t)minb * (uint32_t)waves;   // grid = multiple of SM count x resident CTAs
   if (blocks > cap) blocks = cap;
+  // SEGS = 1024-rule segments each lane group ANDs per step (rule sets beyond 4 segments loop in rule order)
+#define LAUNCH(M) do { \
+    if (P.t.n_seg <= 1) dispatch_kernel<M, 1, 3><<<blocks, 256, 0, s>>>(P); \
+    else if (P.t.n_seg == 2) dispatch_kernel<M, 2, 3><<<blocks, 256, 0, s>>>(P); \
+    else if (minb == 2) dispatch_kernel<M, 4, 2><<<blocks, 256, 0, s>>>(P); \
+    else dispatch_kernel<M, 4, 3><<<blocks, 256, 0, s>>>(P); } while (0)
   switch (mode) {
-    case CORDUM_MODE_POLICY_ONLY: dispatch_kernel<CORDUM_MODE_POLICY_ONLY><<<blocks, 256, 0, s>>>(P); break;
-    case CORDUM_MODE_POLICY_AND_ROUTE: dispatch_kernel<CORDUM_MODE_POLICY_AND_ROUTE><<<blocks, 256, 0, s>>>(P); break;
-    case CORDUM_MODE_ROUTE_ONLY: dispatch_kernel<CORDUM_MODE_ROUTE_ONLY><<<blocks, 256, 0, s>>>(P); break;
+    case CORDUM_MODE_POLICY_ONLY: LAUNCH(CORDUM_MODE_POLICY_ONLY); break;
+    case CORDUM_MODE_POLICY_AND_ROUTE: LAUNCH(CORDUM_MODE_POLICY_AND_ROUTE); break;
+    case CORDUM_MODE_ROUTE_ONLY: LAUNCH(CORDUM_MODE_ROUTE_ONLY); break;
     default: return cudaErrorInvalidValue;
   }
+#undef LAUNCH
   return cudaGetLastError();
 }

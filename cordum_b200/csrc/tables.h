@@ -71,7 +71,9 @@ typedef struct DeviceTables {
   const Row16* row_actor;   uint32_t n_actor;
   const Row16* row_combo;                     /* 6 rows: (actor_type, secrets) & alive-rule mask        */
   const Row16* row_risk;                      /* row 0: job has no referenced tag; row 1+b: tag bit b   */
+  uint32_t risk_zero_row;                     /* index of an all-zero row (padding for branch-free OR loops) */
   const Row16* row_mcp[4];  uint32_t n_mcp[4];
+  uint32_t mcp_ones_row[4];                   /* index of an all-ones row per MCP table (jobs without MCP labels) */
   const Row16* row_check;                     /* rules carrying a requires/labels need-mask             */
   const uint64_t* rule_req_need;              /* per rule: requires tokens it needs (subset test)       */
   const uint64_t* rule_lab_need;              /* per rule: label pairs it needs                          */
