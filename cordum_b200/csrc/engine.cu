@@ -72,7 +72,7 @@ struct cordum_engine {
   DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
-  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush, b_skey, b_slab_lo, b_slab_hi, b_pool_sorted, b_pool_nok, b_lbm, b_lbm_off;
+  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush, b_skey, b_slab_lo, b_slab_hi, b_pool_sorted, b_pool_nok, b_lbm, b_lbm_off, b_rank_pos;
   uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
   std::vector<cordum_batch*> batches;   // live batches (guarded by mu): K2 must wait for their kernels
   bool pools_dirty = true;       // K2 must run before the next dispatch
@@ -189,6 +189,8 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_pool_off, t.pool_off, s), "upload"); CK(up(e->b_pos_pool, t.pos_pool, s), "upload");
     CK(up(e->b_pos_slot, t.pos_slot, s), "upload"); CK(up(e->b_pos_rank, t.pos_rank, s), "upload");
     CK(up(e->b_slot_pos, t.slot_pos, s), "upload"); CK(up(e->b_rank_slot, t.rank_slot, s), "upload");
+    CK(up(e->b_rank_pos, t.rank_pos, s), "upload");
+    d.rank_pos = (const uint32_t*)e->b_rank_pos.p;
     CK(up(e->b_pos_label_lo, t.pos_label_lo, s), "upload"); CK(up(e->b_pos_label_hi, t.pos_label_hi, s), "upload");
     CK(e->b_pos_key.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
     CK(e->b_pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
@@ -367,7 +369,7 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
                    &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_loads, &e->b_pos_key, &e->b_pool_best, &e->b_pool_mincnt,
-                   &e->b_flush, &e->b_skey, &e->b_slab_lo, &e->b_slab_hi, &e->b_pool_sorted, &e->b_pool_nok, &e->b_lbm, &e->b_lbm_off};
+                   &e->b_flush, &e->b_skey, &e->b_slab_lo, &e->b_slab_hi, &e->b_pool_sorted, &e->b_pool_nok, &e->b_lbm, &e->b_lbm_off, &e->b_rank_pos};
   for (DevBuf* b : all) b->release();
   if (e->ev_tables) cudaEventDestroy(e->ev_tables);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);

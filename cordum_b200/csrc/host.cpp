@@ -910,6 +910,7 @@ int Host::compile_workers(std::string& err) {
   t.pos_pool.assign(cap, 0); t.pos_slot.assign(cap, 0); t.pos_rank.assign(cap, 0);
   t.pos_label_lo.assign(cap, 0); t.pos_label_hi.assign(cap, 0);
   t.slot_pos.assign(std::max<uint32_t>(n, 1), 0);
+  t.rank_pos.assign(std::max<uint32_t>(n, 1), 0);
   t.pool_off.assign(t.n_pools + 1, 0);
   // all keys, to set the "absent or empty" bits
   std::vector<std::pair<std::string, uint32_t>> keys;
@@ -922,6 +923,7 @@ int Host::compile_workers(std::string& err) {
     const Pos& p = pos[i];
     t.pos_pool[i] = p.pool; t.pos_slot[i] = p.slot; t.pos_rank[i] = p.rank;
     t.slot_pos[p.slot] = i + 1;
+    t.rank_pos[p.rank] = i;
     t.pool_off[p.pool + 1]++;
     uint64_t m[2] = {0, 0};
     auto setb = [&](uint32_t b) { m[b >> 6] |= 1ull << (b & 63); };

@@ -168,7 +168,7 @@ struct HostTables {
   uint32_t n_pools = 0;
   // workers
   uint32_t n_slots = 0, n_pos = 0;
-  std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot, lbm_off;
+  std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot, rank_pos, lbm_off;
   uint32_t place_bits = 1;
   uint64_t lbm_words = 0;
   std::vector<uint64_t> pos_label_lo, pos_label_hi;

@@ -77,7 +77,7 @@ __device__ __forceinline__ void merge_best(uint64_t& key, uint32_t& cnt, uint64_
 // Per heartbeat epoch: load score + overload test per worker, then a bitonic sort of the pool's
 // keys in shared memory.  The sorted view (keys + label masks in load order) lets label-constrained
 // jobs scan a pool from its least-loaded worker and stop at the first label match.
-__global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
+__global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_cnt;
   const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -85,8 +85,7 @@ __global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
   uint32_t n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   const bool sortable = n_pad <= T.sort_cap;
-  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* si = reinterpret_cast<uint32_t*>(sk + (sortable ? n_pad : 0));
+  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);   // keys only: the key's low word is the worker's rank
   if (tid == 0) s_cnt = 0;
   for (uint32_t i = tid; i < (sortable ? n_pad : n); i += nt) {
     uint64_t key = KEY_NONE;
@@ -100,7 +99,7 @@ __global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
       key = ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
       T.pos_key[pos] = key;
     }
-    if (sortable) { sk[i] = key; si[i] = i; }
+    if (sortable) sk[i] = key;
   }
   __syncthreads();
   if (!sortable) {   // pool larger than the sort buffer: min/count by reduction, jobs fall back to full scans
@@ -119,14 +118,13 @@ __global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
     if (tid == 0) { T.pool_best[p] = best; T.pool_mincnt[p] = best == KEY_NONE ? 0 : s_cnt; T.pool_sorted[p] = 0; }
     return;
   }
+  // bitonic sort, one compare-exchange per (thread, pair): pair q touches i = q with a zero inserted at bit log2(jj)
   for (uint32_t k = 2; k <= n_pad; k <<= 1)
     for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-      for (uint32_t i = tid; i < n_pad; i += nt) {
-        const uint32_t x = i ^ jj;
-        if (x > i) {
-          const uint64_t ki = sk[i], kx = sk[x];
-          if ((ki > kx) == ((i & k) == 0)) { sk[i] = kx; sk[x] = ki; const uint32_t t = si[i]; si[i] = si[x]; si[x] = t; }
-        }
+      for (uint32_t q = tid; q < (n_pad >> 1); q += nt) {
+        const uint32_t i = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), x = i | jj;
+        const uint64_t ki = sk[i], kx = sk[x];
+        if ((ki > kx) == ((i & k) == 0)) { sk[i] = kx; sk[x] = ki; }
       }
       __syncthreads();
     }
@@ -144,7 +142,7 @@ __global__ void __launch_bounds__(256) worker_pool_kernel(DeviceTables T) {
     uint64_t k = KEY_NONE, llo = 0, lhi = 0;
     if (i < n) {
       k = sk[i];
-      const uint32_t src = a + si[i];
+      const uint32_t src = T.rank_pos[(uint32_t)(k & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
       llo = T.pos_label_lo[src]; lhi = T.pos_label_hi[src];
       T.skey[a + i] = k; T.slab_lo[a + i] = llo; T.slab_hi[a + i] = lhi;
       c += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
@@ -550,14 +548,14 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
   if (T.n_pools == 0) return cudaSuccess;
-  const size_t smem = (size_t)T.sort_cap * 12;   // u64 key + u32 index per entry
+  const size_t smem = (size_t)T.sort_cap * 8;   // one u64 key per entry
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(worker_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  worker_pool_kernel<<<T.n_pools, 256, smem, s>>>(T);
+  worker_pool_kernel<<<T.n_pools, 1024, smem, s>>>(T);
   return cudaGetLastError();
 }
 

@@ -99,6 +99,7 @@ typedef struct DeviceTables {
   const uint32_t* pos_rank;                   /* rank of pos in ascending worker_id byte order          */
   const uint32_t* slot_pos;                   /* [n_slots] 1 + pos, 0 = not routable                    */
   const uint32_t* rank_slot;                  /* [n_slots] slot of rank                                 */
+  const uint32_t* rank_pos;                   /* [n_slots] pos of rank (routable workers only)          */
   const uint64_t* pos_label_lo;               /* placement label mask                                   */
   const uint64_t* pos_label_hi;
   const Load16* loads;                          /* [n_slots] {active, max_parallel, cpu(f32), gpu(f32)}   */
