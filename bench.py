@@ -111,7 +111,7 @@ def cpu_reference_rate(cfg, threads: int, target_s: float, first: int = 0):
 
     o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
     n = cfg.jobs.n_jobs
-    probe = min(n, max(256, 8 * threads))
+    probe = min(n, max(4096, 64 * threads))   # large enough that thread start-up does not skew the estimate
     t0 = time.perf_counter()
     o.eval(cfg.jobs, wire.MODE_POLICY_AND_ROUTE, threads=threads, first=first % max(1, n - probe), count=probe)
     dt = max(time.perf_counter() - t0, 1e-6)
@@ -161,20 +161,18 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
-    from cordum_b200 import engine, synth, wire
+    from cordum_b200 import engine, shard, synth, wire
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = synth.make_config("c3")
     J, W = cfg.jobs.n_jobs, cfg.workers.n_workers
-    per = (J + world - 1) // world
-    j0, j1 = min(J, rank * per), min(J, (rank + 1) * per)
-    shard = cfg.jobs.slice(j0, j1 - j0) if world > 1 else cfg.jobs
-    n_shard = shard.n_jobs
-    wper = (W + world - 1) // world
-    w0, w1 = min(W, rank * wper), min(W, (rank + 1) * wper)
-    assert wper * world == W, "worker count must divide evenly for the all-gather"
+    j0, j1 = shard.job_range(rank, world, J)
+    my_jobs = cfg.jobs.slice(j0, j1 - j0) if world > 1 else cfg.jobs
+    n_shard = my_jobs.n_jobs
+    w0, w1 = shard.worker_range(rank, world, W)
+    assert shard.padded_workers(world, W) == W, "worker count must divide evenly for the all-gather"
 
     eng = engine.Engine(device=local_rank)
     eng.load_policy(cfg.policy, "bench")
@@ -190,7 +188,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     batches = [eng.batch(n_shard) for _ in range(n_rot)]
     t_enc0 = time.perf_counter()
     for b in batches:
-        b.encode(shard)
+        b.encode(my_jobs)
         b.dispatch(wire.MODE_POLICY_AND_ROUTE)   # makes the columns resident (and warms the dictionaries)
     enc_s = (time.perf_counter() - t_enc0) / n_rot
     ref_result = batches[0].results().copy()
@@ -213,8 +211,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     def step(k: int, batch, resident: bool):
         send.copy_(delta_sets[k % n_delta_sets], non_blocking=True)          # heartbeat ingest: pinned host -> HBM
         if world > 1:
-            buf = recv[k % 2]
-            dist.all_gather_into_tensor(buf.view(-1), send.view(-1))          # the one exchange step
+            buf = shard.gather_loads(send, out=recv[k % 2])                   # the one exchange step
         else:
             buf = send
         eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)           # D2D + worker_pool_kernel
@@ -260,13 +257,13 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # ---------------------------------------------------------------- end to end: `e2e`
     e2e_steps = max(2, min(args.steps, 6))
     for k in range(2):
-        batches[k % 2].encode(shard)
+        batches[k % 2].encode(my_jobs)
         step(k, batches[k % 2], False)
     sync_all()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         b = batches[k % 2]
-        b.encode(shard)                    # waits for this batch's previous run, then host encode
+        b.encode(my_jobs)                  # waits for this batch's previous run, then host encode
         step(k, b, False)                  # H2D columns + kernels + D2H records, async
     sync_all()
     e2e_elapsed = time.perf_counter() - t0
