@@ -19,7 +19,7 @@ API = [
     "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
     "cordum_workers_set_loads_device", "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
-    "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_rule_id", "cordum_reason",
+    "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
     "cordum_launch_count", "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
     "cordum_test_parse_effective",
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
     L.cordum_batch_results.argtypes = [vp]
     L.cordum_batch_results.restype = vp
     L.cordum_batch_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cordum_batch_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cordum_rule_id.argtypes = [vp, i32, cp, u64]
     L.cordum_rule_id.restype = i64
     L.cordum_rule_constraints_json.argtypes = [vp, i32, cp, u64]

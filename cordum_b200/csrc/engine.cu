@@ -90,8 +90,8 @@ struct cordum_batch {
   cordum_decision* h_out = nullptr;   // pinned
   cordum_decision* d_out = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-  float total_ms = 0, kernel_ms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
+  float total_ms = 0, kernel_ms = 0, policy_ms = 0, route_ms = 0;
   HostColumns hc{};
 };
 
@@ -269,7 +269,6 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     if (rc) return rc;
   }
   cudaStream_t s = b->stream;
-  CK(cudaStreamWaitEvent(s, e->ev_tables, 0), "wait tables");
   if (flush_l2) {   // evict the job columns from L2 between timed iterations (outside the timed region)
     if (!e->b_flush.p) CK(e->b_flush.reserve(size_t(256) << 20), "alloc flush buffer");
     CK(cudaMemsetAsync(e->b_flush.p, 0, e->b_flush.cap, s), "flush");
@@ -285,8 +284,18 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   P.t = e->dt;
   P.out = b->d_out;
   P.n_jobs = b->n;
-  CK(launch_dispatch(P, mode, e->sm_count, s), "dispatch_kernel");
-  if (b->n) e->launches++;
+  P.honor_approved = mode == CORDUM_MODE_POLICY_AND_ROUTE ? 1u : 0u;
+  // policy_kernel needs no worker state: it is NOT ordered after the heartbeat exchange / worker_pool_kernel
+  if (mode != CORDUM_MODE_ROUTE_ONLY) {
+    CK(launch_policy(P, e->sm_count, s), "policy_kernel");
+    if (b->n) e->launches++;
+  }
+  CK(cudaEventRecord(b->evm, s), "event");
+  if (mode != CORDUM_MODE_POLICY_ONLY) {
+    CK(cudaStreamWaitEvent(s, e->ev_tables, 0), "wait worker tables");
+    CK(launch_route(P, mode == CORDUM_MODE_ROUTE_ONLY, e->sm_count, s), "route_kernel");
+    if (b->n) e->launches++;
+  }
   CK(cudaEventRecord(b->ev2, s), "event");
   b->launched = true;
   if (copy_out) CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, s), "D2H results");
@@ -302,6 +311,8 @@ int wait(cordum_batch* b) {
   b->pending = false;
   CK(cudaEventElapsedTime(&b->total_ms, b->ev0, b->ev3), "elapsed");
   CK(cudaEventElapsedTime(&b->kernel_ms, b->ev1, b->ev2), "elapsed");
+  CK(cudaEventElapsedTime(&b->policy_ms, b->ev1, b->evm), "elapsed");
+  CK(cudaEventElapsedTime(&b->route_ms, b->evm, b->ev2), "elapsed");
   return CORDUM_OK;
 }
 
@@ -322,6 +333,18 @@ std::string go_quote(sv s) {
 }
 
 }  // namespace
+
+static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resources; the registry is the caller's business
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->h_cols) cudaFreeHost(b->h_cols);
+  if (b->d_cols) cudaFree(b->d_cols);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  if (b->d_out) cudaFree(b->d_out);
+  for (cudaEvent_t ev : {b->ev0, b->ev1, b->evm, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
 
 // ============================================================ C ABI
 extern "C" {
@@ -363,6 +386,11 @@ void cordum_engine_destroy(cordum_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
+  {
+    std::vector<cordum_batch*> live;
+    { std::lock_guard<std::mutex> g(e->mu); live.swap(e->batches); }
+    for (cordum_batch* b : live) batch_release(b);
+  }
   DevBuf* all[] = {&e->b_row_tenant, &e->b_row_topic, &e->b_row_cap, &e->b_row_pack, &e->b_row_actor, &e->b_row_combo,
                    &e->b_row_risk, &e->b_row_check, &e->b_row_mcp[0], &e->b_row_mcp[1], &e->b_row_mcp[2], &e->b_row_mcp[3],
                    &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic,
@@ -454,13 +482,15 @@ int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** o
   CK(cudaHostAlloc((void**)&b->h_out, (size_t)max_jobs * sizeof(cordum_decision), cudaHostAllocDefault), "pinned results");
   CK(cudaMalloc((void**)&b->d_out, (size_t)max_jobs * sizeof(cordum_decision)), "device results");
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
-  CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event");
+  CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event"); CK(cudaEventCreate(&b->evm), "event");
   CK(cudaEventCreate(&b->ev2), "event"); CK(cudaEventCreate(&b->ev3), "event");
   { std::lock_guard<std::mutex> g(e->mu); e->batches.push_back(b.get()); }
   *out = b.release();
   return CORDUM_OK;
 }
 
+/* A batch must be freed BEFORE its engine is destroyed; cordum_engine_destroy releases any batch
+ * that is still alive, after which those handles are invalid. */
 void cordum_batch_free(cordum_batch* b) {
   if (!b) return;
   cudaSetDevice(b->e->device);
@@ -469,14 +499,7 @@ void cordum_batch_free(cordum_batch* b) {
     auto& v = b->e->batches;
     for (size_t i = 0; i < v.size(); ++i) if (v[i] == b) { v.erase(v.begin() + i); break; }
   }
-  if (b->stream) cudaStreamSynchronize(b->stream);
-  if (b->h_cols) cudaFreeHost(b->h_cols);
-  if (b->d_cols) cudaFree(b->d_cols);
-  if (b->h_out) cudaFreeHost(b->h_out);
-  if (b->d_out) cudaFree(b->d_out);
-  for (cudaEvent_t ev : {b->ev0, b->ev1, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
-  if (b->stream) cudaStreamDestroy(b->stream);
-  delete b;
+  batch_release(b);
 }
 
 int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
@@ -516,6 +539,12 @@ int32_t cordum_batch_timing(const cordum_batch* b, float* total_ms, float* kerne
   if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
   if (total_ms) *total_ms = b->total_ms;
   if (kernel_ms) *kernel_ms = b->kernel_ms;
+  return CORDUM_OK;
+}
+int32_t cordum_batch_kernel_times(const cordum_batch* b, float* policy_ms, float* route_ms) {
+  if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
+  if (policy_ms) *policy_ms = b->policy_ms;
+  if (route_ms) *route_ms = b->route_ms;
   return CORDUM_OK;
 }
 /* copies the decision records still on the device into the pinned result buffer (after a resident run) */

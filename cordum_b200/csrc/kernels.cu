@@ -165,18 +165,17 @@ __global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
   if (tid == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_mincnt[p] = s_cnt; T.pool_sorted[p] = 1; T.pool_nok[p] = s_nok; }
 }
 
-// ------------------------------------------------------------------ fused policy + route
-// A warp owns a tile of 32 consecutive jobs (lane = job for the column loads, the scalar
-// decision/route logic and the record store).  Three phases per tile:
-//   P  policy rows, warp-cooperative PER JOB: lane = one 128-bit slice of the pass-rows, so a
-//      4096-rule set is ANDed in one step with 7-12 independent 16 B gathers per lane in flight
-//      and no divergence; first match = ballot + ffs.  Rule sets > 4096 loop in rule order.
-//   D  decision mapping, tenant MCP, effective-config overlay, scheduler post-step and the pool
-//      filter / per-pool argmin merge, thread-per-job (32 jobs at once, scalar code).
-//   S  only for jobs with placement labels: warp-cooperative scan of the eligible pools' worker
-//      slices (coalesced 8 B loads of label masks and keys) + shuffle reduction.
-template <int MODE, int SEGS, int MINB>
-__global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
+// ------------------------------------------------------------------ policy: first match + decision
+// A warp owns a tile of 32 consecutive jobs (lane = job for the coalesced column loads, the scalar
+// decision logic and the 16 B record store).  Needs no worker state, so it runs concurrently with the
+// heartbeat exchange and worker_pool_kernel.
+//   P  8 rounds x 4 jobs: the 8 lanes of group g AND the pass-rows of job (round*4+g); each lane holds
+//      SEGS 128-bit slices, so one step covers SEGS*1024 rules with 7-12 x SEGS independent 128-bit
+//      gathers per lane in flight and one instruction stream for all four jobs.
+//   D  decision mapping, tenant MCP, effective-config overlay, approval flags, scheduler post-step:
+//      thread per job.
+template <int SEGS, int MINB>
+__global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
   const unsigned lane = threadIdx.x & 31;
@@ -188,26 +187,14 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
   for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
     const uint32_t j = tile * 32 + lane;
     const bool valid = j < P.n_jobs;
-    // ---- coalesced column loads: this lane's own job
-    uint32_t c_tenant = 0, c_tpol = 0, c_topic = 0, c_cap = 0, c_pack = 0, c_actor = 0, c_m0 = 0, c_m1 = 0, c_m2 = 0,
-             c_m3 = 0, c_ppool = 0, c_pwork = 0, c_eff = 0, c_flags = 0;
-    uint64_t c_risk = 0, c_req = 0, c_lab = 0, c_plo = 0, c_phi = 0;
+    // only what the rule scan needs stays in registers; the rest is fetched where it is used
+    uint32_t c_tenant = 0, c_topic = 0, c_cap = 0, c_pack = 0, c_actor = 0, c_flags = 0;
+    uint64_t c_risk = 0;
     if (valid) {
-      c_flags = ld_stream_u32(C.flags + j);
-      c_topic = ld_stream_u32(C.topic + j);
-      if (MODE != CORDUM_MODE_ROUTE_ONLY) {
-        c_tenant = ld_stream_u32(C.tenant + j); c_tpol = ld_stream_u32(C.tenant_pol + j);
-        c_cap = ld_stream_u32(C.capability + j); c_pack = ld_stream_u32(C.pack + j); c_actor = ld_stream_u32(C.actor + j);
-        c_m0 = ld_stream_u32(C.mcp[0] + j); c_m1 = ld_stream_u32(C.mcp[1] + j);
-        c_m2 = ld_stream_u32(C.mcp[2] + j); c_m3 = ld_stream_u32(C.mcp[3] + j);
-        c_eff = ld_stream_u32(C.effcfg + j);
-        c_risk = ld_stream_u64(C.risk_mask + j); c_lab = ld_stream_u64(C.lab_mask + j);
-      }
-      c_req = ld_stream_u64(C.req_mask + j);
-      if (MODE != CORDUM_MODE_POLICY_ONLY) {
-        c_ppool = ld_stream_u32(C.pref_pool + j); c_pwork = ld_stream_u32(C.pref_worker + j);
-        c_plo = ld_stream_u64(C.place_lo + j); c_phi = ld_stream_u64(C.place_hi + j);
-      }
+      c_flags = ld_stream_u32(C.flags + j); c_topic = ld_stream_u32(C.topic + j);
+      c_tenant = ld_stream_u32(C.tenant + j);
+      c_cap = ld_stream_u32(C.capability + j); c_pack = ld_stream_u32(C.pack + j); c_actor = ld_stream_u32(C.actor + j);
+      c_risk = ld_stream_u64(C.risk_mask + j);
     }
 
     // =================================================================== P: first matching rule
@@ -215,10 +202,10 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
     // SEGS 128-bit slices (lane `sub` of segment s covers rules s*1024 + sub*128 ..+127).  All four groups
     // run the same instruction stream (no divergence) with 7-12 x SEGS independent gathers in flight.
     int first = -1;
-    const bool bypass = MODE == CORDUM_MODE_POLICY_AND_ROUTE && (c_flags & JF_APPROVED);                 // engine.go:484-522
+    const bool bypass = P.honor_approved && (c_flags & JF_APPROVED);                 // engine.go:484-522
     const bool early = (c_flags & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED)) != 0;                        // kernel.go:171-176
-    const bool eval = valid && MODE != CORDUM_MODE_ROUTE_ONLY && !bypass && !early;
-    if (MODE != CORDUM_MODE_ROUTE_ONLY) {
+    const bool eval = valid && !bypass && !early;
+    {
       const unsigned g = lane >> 3, sub = lane & 7;
       // row offsets of this lane's own job (in Row16 units), computed once per tile
       const uint32_t o_combo = (c_flags & JF_COMBO_MASK) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
@@ -239,17 +226,12 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
         const uint64_t risk = shfl64(FULL, c_risk, src);
         const bool mcp_used = active && (fl & JF_MCP_USED);
         const bool any_mcp = __any_sync(FULL, mcp_used);
-        uint32_t mid[4] = {0, 0, 0, 0};
+        const uint32_t jsrc = tile * 32 + (uint32_t)src;   // the job this group works on (MCP ids / masks are read on demand)
+        uint32_t o_mcp[4] = {0, 0, 0, 0};   // row offsets; groups whose job carries no MCP labels read the all-ones row
         if (any_mcp) {
-          mid[0] = __shfl_sync(FULL, c_m0, src); mid[1] = __shfl_sync(FULL, c_m1, src);
-          mid[2] = __shfl_sync(FULL, c_m2, src); mid[3] = __shfl_sync(FULL, c_m3, src);
-        }
-        if (any_mcp) {   // groups whose job carries no MCP labels read the all-ones row: same instruction stream
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (!mcp_used) mid[q] = T.mcp_ones_row[q];
+          for (int q = 0; q < 4; ++q) o_mcp[q] = (mcp_used ? __ldg(C.mcp[q] + jsrc) : T.mcp_ones_row[q]) * rowu4 + sub;
         }
-        const Row16* p_mcp[4] = {T.row_mcp[0] + (size_t)mid[0] * rowu4 + sub, T.row_mcp[1] + (size_t)mid[1] * rowu4 + sub,
-                                 T.row_mcp[2] + (size_t)mid[2] * rowu4 + sub, T.row_mcp[3] + (size_t)mid[3] * rowu4 + sub};
         const Row16* p_risk = T.row_risk + sub;
         const uint32_t* chk_words = reinterpret_cast<const uint32_t*>(T.row_check);
         int found = -1;
@@ -283,7 +265,7 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-              for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], ld_row(p_mcp[q] + s * (int)CORDUM_SEG_U4));
+              for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], ld_row(T.row_mcp[q] + o_mcp[q] + s0 * CORDUM_SEG_U4 + s * (int)CORDUM_SEG_U4));
           }
           const uint32_t keep = active ? 0xFFFFFFFFu : 0u;   // jobs that are not evaluated (or already matched) contribute nothing
 #pragma unroll
@@ -313,7 +295,7 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
             const bool pend = have && ((__ldg(chk_words + ((uint32_t)gmin >> 5)) >> (gmin & 31)) & 1u);
             const unsigned pb = __ballot_sync(FULL, pend);
             if (!pb) { if (have) found = gmin; break; }
-            if (!have_masks) { req = shfl64(FULL, c_req, src); lab = shfl64(FULL, c_lab, src); have_masks = true; }
+            if (!have_masks) { req = __ldg(C.req_mask + jsrc); lab = __ldg(C.lab_mask + jsrc); have_masks = true; }
             bool ok = true;
             if (pend) {   // containsAll (:320-330), labelsMatch (:332-345)
               const uint64_t need = __ldg(T.rule_req_need + gmin), ln = __ldg(T.rule_lab_need + gmin);
@@ -332,8 +314,6 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
           p_combo += SEGS * CORDUM_SEG_U4; p_tenant += SEGS * CORDUM_SEG_U4; p_topic += SEGS * CORDUM_SEG_U4;
           p_cap += SEGS * CORDUM_SEG_U4; p_pack += SEGS * CORDUM_SEG_U4; p_actor += SEGS * CORDUM_SEG_U4;
           p_risk += SEGS * CORDUM_SEG_U4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) p_mcp[q] += SEGS * CORDUM_SEG_U4;
           rule_base += SEGS * CORDUM_SEG_RULES;
         }
         (void)rule_base;
@@ -344,15 +324,17 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
     }
 
     // =================================================================== D: decision (thread per job)
-    uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
-    int rule = -1, slot = -1;
-    if (valid && MODE != CORDUM_MODE_ROUTE_ONLY) {
+    uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0;
+    int rule = -1;
+    if (valid) {
       if (bypass) { dec = sched = CORDUM_DEC_ALLOW; reason = CORDUM_REASON_APPROVAL_GRANTED; rflags = CORDUM_F_APPROVED_BYPASS; }
       else if (c_flags & JF_TOPIC_MISSING) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_MISSING_TOPIC; }
       else if (c_flags & JF_TOPIC_UNSUPPORTED) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_UNSUPPORTED_TOPIC; }
       else {
         const bool mcp_used = c_flags & JF_MCP_USED;
-        const uint32_t mid[4] = {c_m0, c_m1, c_m2, c_m3};
+        const uint32_t c_tpol = ld_stream_u32(C.tenant_pol + j), c_eff = ld_stream_u32(C.effcfg + j);
+        uint32_t mid[4] = {0, 0, 0, 0};
+        if (mcp_used) { mid[0] = __ldg(C.mcp[0] + j); mid[1] = __ldg(C.mcp[1] + j); mid[2] = __ldg(C.mcp[2] + j); mid[3] = __ldg(C.mcp[3] + j); }
         rule = first;
         uint32_t code = CORDUM_DEC_ALLOW;
         bool hascons = false;
@@ -387,15 +369,57 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
       }
     }
 
+    if (valid) {   // coalesced 16 B store per lane; the route fields are filled by route_kernel
+      const uint32_t head = dec | (sched << 8) | (rflags << 16);
+      reinterpret_cast<uint4*>(P.out)[j] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, 0xFFFFFFFFu);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------ route: pool filter + least-loaded pick
+// Reads the decision record policy_kernel wrote (or nothing in ROUTE_ONLY mode) and routes the jobs that
+// may dispatch (engine.go:298-347).
+//   D  topic->pools, preferred_pool, requires filter, preferred_worker_id and, for label-free jobs, the
+//      merge of per-pool best keys: thread per job.
+//   S  only for jobs with placement labels: warp per job, AND of the pool's label bitmaps over its
+//      load-sorted view (lane = 32 workers); first set bit in the non-overloaded prefix = argmin.
+template <bool ROUTE_ONLY>
+__global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
+  const DeviceTables& T = P.t;
+  const JobColumns& C = P.cols;
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_tiles = (P.n_jobs + 31u) >> 5;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+  for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+    const uint32_t j = tile * 32 + lane;
+    const bool valid = j < P.n_jobs;
+    uint4 rec = make_uint4(0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint32_t c_flags = 0, c_topic = 0, c_ppool = 0, c_pwork = 0;
+    uint64_t c_req = 0, c_plo = 0, c_phi = 0;
+    bool do_route = false;
+    if (valid) {
+      if (!ROUTE_ONLY) rec = reinterpret_cast<const uint4*>(P.out)[j];
+      const uint32_t sched = (rec.x >> 8) & 0xFFu;
+      do_route = ROUTE_ONLY || sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;   // engine.go:298-347
+      if (do_route) {
+        c_flags = ld_stream_u32(C.flags + j); c_topic = ld_stream_u32(C.topic + j);
+        c_ppool = ld_stream_u32(C.pref_pool + j); c_pwork = ld_stream_u32(C.pref_worker + j);
+        c_req = ld_stream_u64(C.req_mask + j); c_plo = ld_stream_u64(C.place_lo + j); c_phi = ld_stream_u64(C.place_hi + j);
+      }
+    }
+    uint32_t rflags = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
+    int slot = -1;
+
     // =================================================================== D (cont.): pool filter, thread per job
     bool need_scan = false;
     uint32_t r_off = 0, r_cnt = 0;
     int r_single = -1;
     uint64_t best = KEY_NONE;
     uint32_t bcnt = 0, total = 0;
-    if (MODE != CORDUM_MODE_POLICY_ONLY) {
-      const bool do_route = valid && (MODE == CORDUM_MODE_ROUTE_ONLY ||
-                                      sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS);   // engine.go:298-347
+    {
       if (do_route) {
         if (c_flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
         else {
@@ -538,12 +562,14 @@ __global__ void __launch_bounds__(256, MINB) dispatch_kernel(KParams P) {
       }
     }
 
-    if (valid) {   // coalesced 16 B store per lane
-      const uint32_t head = dec | (sched << 8) | (rflags << 16) | (route << 24);
-      reinterpret_cast<uint4*>(P.out)[j] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, (uint32_t)slot);
+    if (valid && (ROUTE_ONLY || do_route)) {
+      rec.x = (rec.x & 0x00FFFFFFu) | (rflags << 16) | (route << 24);   // rflags only adds CORDUM_F_TIE
+      rec.w = (uint32_t)slot;
+      reinterpret_cast<uint4*>(P.out)[j] = rec;
     }
   }
 }
+
 
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
@@ -559,26 +585,31 @@ cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_dispatch(const KParams& P, uint32_t mode, int sm_count, cudaStream_t s) {
-  if (P.n_jobs == 0) return cudaSuccess;
-  const uint32_t tiles = (P.n_jobs + 31u) / 32u;
-  uint32_t blocks = (tiles + 7u) / 8u;                  // 8 warps (tiles) per 256-thread CTA
-  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 3; }();   // tuning knob
+static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
   static const int waves = []() { const char* v = getenv("CORDUM_WAVES"); return v ? atoi(v) : 4; }();
-  const uint32_t cap = (uint32_t)sm_count * (uint32_t)minb * (uint32_t)waves;   // grid = multiple of SM count x resident CTAs
-  if (blocks > cap) blocks = cap;
-  // SEGS = 1024-rule segments each lane group ANDs per step (rule sets beyond 4 segments loop in rule order)
-#define LAUNCH(M) do { \
-    if (P.t.n_seg <= 1) dispatch_kernel<M, 1, 3><<<blocks, 256, 0, s>>>(P); \
-    else if (P.t.n_seg == 2) dispatch_kernel<M, 2, 3><<<blocks, 256, 0, s>>>(P); \
-    else if (minb == 2) dispatch_kernel<M, 4, 2><<<blocks, 256, 0, s>>>(P); \
-    else dispatch_kernel<M, 4, 3><<<blocks, 256, 0, s>>>(P); } while (0)
-  switch (mode) {
-    case CORDUM_MODE_POLICY_ONLY: LAUNCH(CORDUM_MODE_POLICY_ONLY); break;
-    case CORDUM_MODE_POLICY_AND_ROUTE: LAUNCH(CORDUM_MODE_POLICY_AND_ROUTE); break;
-    case CORDUM_MODE_ROUTE_ONLY: LAUNCH(CORDUM_MODE_ROUTE_ONLY); break;
-    default: return cudaErrorInvalidValue;
-  }
-#undef LAUNCH
+  const uint32_t tiles = (n_jobs + 31u) / 32u;
+  uint32_t blocks = (tiles + 7u) / 8u;                                               // 8 warps (tiles) per 256-thread CTA
+  const uint32_t cap = (uint32_t)sm_count * (uint32_t)resident * (uint32_t)waves;   // multiple of SM count x resident CTAs
+  return blocks > cap ? cap : blocks;
+}
+
+cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
+  if (P.n_jobs == 0) return cudaSuccess;
+  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 3; }();   // tuning knob
+  const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
+  // SEGS = 1024-rule segments each lane group ANDs per step (n_seg is 1, 2 or a multiple of 4: host pads)
+  if (P.t.n_seg <= 1) policy_kernel<1, 4><<<blocks, 256, 0, s>>>(P);
+  else if (P.t.n_seg == 2) policy_kernel<2, 4><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 2) policy_kernel<4, 2><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 4) policy_kernel<4, 4><<<blocks, 256, 0, s>>>(P);
+  else policy_kernel<4, 3><<<blocks, 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s) {
+  if (P.n_jobs == 0) return cudaSuccess;
+  const uint32_t blocks = grid_for(P.n_jobs, sm_count, 4);
+  if (route_only) route_kernel<true><<<blocks, 256, 0, s>>>(P);
+  else route_kernel<false><<<blocks, 256, 0, s>>>(P);
   return cudaGetLastError();
 }

@@ -10,7 +10,9 @@ struct KParams {
   DeviceTables t;         // device pointers to the compiled tables
   cordum_decision* out;   // device, n_jobs records
   uint32_t n_jobs;
+  uint32_t honor_approved;   // POLICY_AND_ROUTE: jobs flagged JF_APPROVED bypass the policy (engine.go:484-522)
 };
 
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s);
-cudaError_t launch_dispatch(const KParams& P, uint32_t mode, int sm_count, cudaStream_t s);
+cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s);
+cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s);

@@ -23,11 +23,15 @@ class Batch:
         eng._ck(self.L.cordum_batch_alloc(eng.h, max_jobs, C.byref(h)))
         self.h = h
         self.max_jobs = max_jobs
+        eng._batches.append(self)
 
     def free(self):
-        if self.h:
+        """Safe to call any number of times, and after the engine was closed (which already released the batch)."""
+        if self.h and self.eng.h:
             self.L.cordum_batch_free(self.h)
-            self.h = None
+        self.h = None
+        if self in self.eng._batches:
+            self.eng._batches.remove(self)
 
     def __del__(self):
         try:
@@ -78,6 +82,11 @@ class Batch:
         self.eng._ck(self.L.cordum_batch_timing(self.h, C.byref(t), C.byref(k)))
         return t.value, k.value
 
+    def kernel_times(self):
+        p, r = C.c_float(), C.c_float()
+        self.eng._ck(self.L.cordum_batch_kernel_times(self.h, C.byref(p), C.byref(r)))
+        return p.value, r.value
+
     def _text(self, fn, job: int) -> str:
         buf = C.create_string_buffer(4096)
         fn(self.eng.h, self.h, job, buf, len(buf))
@@ -99,14 +108,17 @@ class Engine:
         if rc:
             raise CordumError(rc, self.L.cordum_last_error().decode())
         self.h = h
-        self._keep = []
+        self._batches: list = []
 
     def _ck(self, rc: int):
         if rc:
             raise CordumError(rc, self.L.cordum_last_error().decode())
 
     def close(self):
+        """Frees every live batch first: a batch must never outlive its engine."""
         if self.h:
+            for b in list(self._batches):
+                b.free()
             self.L.cordum_engine_destroy(self.h)
             self.h = None
 

@@ -241,8 +241,10 @@ uint32_t cordum_batch_size(const cordum_batch* b);
 /* Decision records of the last completed dispatch (pinned host memory, n = batch size). */
 const cordum_decision* cordum_batch_results(const cordum_batch* b);
 /* Device time of the last completed dispatch on this batch (CUDA events on the
- * batch stream): total, and the fused policy+route kernel alone.  Milliseconds. */
+ * batch stream): total (copies included), and the kernels alone.  Milliseconds. */
 int32_t cordum_batch_timing(const cordum_batch* b, float* total_ms, float* kernel_ms);
+/* The two kernels of a dispatch separately: policy_kernel and route_kernel (CUDA events). */
+int32_t cordum_batch_kernel_times(const cordum_batch* b, float* policy_ms, float* route_ms);
 
 /* Host-side materialisation of what the record indexes (pure functions of rule_idx /
  * reason_code / worker_slot).  Each writes a NUL-terminated string

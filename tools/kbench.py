@@ -27,13 +27,17 @@ def main():
         b.dispatch()
     enc = (time.time() - t0) / nb
     for mode, nm in ((wire.MODE_POLICY_AND_ROUTE, "policy+route"), (wire.MODE_POLICY_ONLY, "policy"), (wire.MODE_ROUTE_ONLY, "route")):
-        ks = []
+        ks, ps, rs = [], [], []
         for r in range(reps + 2):
             b = bs[r % nb]
             b.dispatch_resident(mode)
             if r >= 2:
                 ks.append(b.timing()[1])
-        print("%s %-13s kernel_ms min %.4f med %.4f max %.4f" % (name, nm, min(ks), float(np.median(ks)), max(ks)), flush=True)
+                p_, r_ = b.kernel_times()
+                ps.append(p_)
+                rs.append(r_)
+        print("%s %-13s kernels_ms med %.4f (min %.4f)  policy %.4f  route %.4f" % (
+            name, nm, float(np.median(ks)), min(ks), float(np.median(ps)), float(np.median(rs))), flush=True)
     print("encode+dispatch s/batch %.4f" % enc)
 
 
