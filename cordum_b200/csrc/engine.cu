@@ -69,7 +69,7 @@ struct cordum_engine {
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
   DevBuf b_row_tenant, b_row_topic, b_row_cap, b_row_pack, b_row_actor, b_row_combo, b_row_risk, b_row_check, b_row_mcp[4];
-  DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic;
+  DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule, b_tw_off, b_tw_cnt, b_tw_list;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
   DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush, b_skey, b_slab_lo, b_slab_hi, b_pool_sorted, b_pool_nok, b_lbm, b_lbm_off, b_rank_pos;
@@ -148,7 +148,8 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_row_combo, t.row_combo.data, s), "upload"); CK(up(e->b_row_risk, t.row_risk.data, s), "upload");
     CK(up(e->b_row_check, t.row_check.data, s), "upload");
     CK(up(e->b_req_need, t.rule_req_need, s), "upload"); CK(up(e->b_lab_need, t.rule_lab_need, s), "upload");
-    CK(up(e->b_rule_dec, t.rule_dec, s), "upload");
+    CK(up(e->b_rule_dec, t.rule_dec, s), "upload"); CK(up(e->b_pos2rule, t.pos2rule, s), "upload");
+    d.pos2rule = (const uint32_t*)e->b_pos2rule.p;
     d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4;
     d.row_tenant = (const Row16*)e->b_row_tenant.p; d.n_tenant = t.row_tenant.n_rows;
     d.row_cap = (const Row16*)e->b_row_cap.p; d.n_cap = t.row_cap.n_rows;
@@ -164,6 +165,8 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_row_topic, t.row_topic.data, s), "upload"); CK(up(e->b_eff_topic, t.eff_topic, s), "upload");
     CK(up(e->b_topic_pool_off, t.topic_pool_off, s), "upload"); CK(up(e->b_topic_pool_cnt, t.topic_pool_cnt, s), "upload");
     CK(up(e->b_pool_list, t.pool_list, s), "upload");
+    CK(up(e->b_tw_off, t.tw_off, s), "upload"); CK(up(e->b_tw_cnt, t.tw_cnt, s), "upload"); CK(up(e->b_tw_list, t.tw_list, s), "upload");
+    d.tw_off = (const uint32_t*)e->b_tw_off.p; d.tw_cnt = (const uint32_t*)e->b_tw_cnt.p; d.tw_list = (const uint16_t*)e->b_tw_list.p;
     d.row_topic = (const Row16*)e->b_row_topic.p; d.n_topic = t.row_topic.n_rows;
     d.eff_topic = (const uint8_t*)e->b_eff_topic.p; d.topic_stride = t.topic_stride;
     d.topic_pool_off = (const uint32_t*)e->b_topic_pool_off.p; d.topic_pool_cnt = (const uint32_t*)e->b_topic_pool_cnt.p;
@@ -393,7 +396,7 @@ void cordum_engine_destroy(cordum_engine* e) {
   }
   DevBuf* all[] = {&e->b_row_tenant, &e->b_row_topic, &e->b_row_cap, &e->b_row_pack, &e->b_row_actor, &e->b_row_combo,
                    &e->b_row_risk, &e->b_row_check, &e->b_row_mcp[0], &e->b_row_mcp[1], &e->b_row_mcp[2], &e->b_row_mcp[3],
-                   &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic,
+                   &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule, &e->b_tw_off, &e->b_tw_cnt, &e->b_tw_list,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
                    &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_loads, &e->b_pos_key, &e->b_pool_best, &e->b_pool_mincnt,

@@ -380,10 +380,39 @@ void Host::compile_policy() {
   const auto& rules = policy_.rules;
   const uint32_t R = (uint32_t)rules.size();
   t.n_rules = R;
-  t.n_seg = std::max<uint32_t>(1, (R + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
-  if (t.n_seg > 2) t.n_seg = (t.n_seg + 3) & ~3u;   // the kernel ANDs 4 segments per step: pad with empty segments
+  // ---- bit positions.  A rule's bit does not sit at its index.  Each rule gets one position per distinct topic
+  // pattern it lists (one position if it has none): the copy for pattern p carries the rule's other predicates
+  // unchanged but only p's topic bits.  Positions are then ordered so that the rules a given topic can match share
+  // few 128-bit words: topic-vacuous rules first, the rest clustered by the literal "job.<pack>" prefix of the
+  // pattern.  First-match is recovered as the minimum ORIGINAL rule index over the surviving bits (pos2rule), so
+  // duplicates and any ordering are harmless; a good ordering makes topic rows sparse (per-topic word lists).
+  struct Entry { uint32_t rule; int32_t pat; std::string key; };   // pat = index into rules[rule].topics, -1 = none
+  std::vector<Entry> entries;
+  for (uint32_t r = 0; r < R; ++r) {
+    if (rules[r].topics.empty()) { entries.push_back({r, -1, std::string()}); continue; }
+    std::vector<std::string> seen;
+    for (size_t k = 0; k < rules[r].topics.size(); ++k) {
+      sv pt = trim_space(rules[r].topics[k]);
+      if (pt.empty()) continue;   // matchTopic: an empty pattern never matches
+      if (std::find(seen.begin(), seen.end(), std::string(pt)) != seen.end()) continue;
+      seen.emplace_back(pt);
+      size_t cut = pt.find_first_of("*?[\\");
+      sv lit = pt.substr(0, cut == sv::npos ? pt.size() : cut);
+      size_t d1 = lit.find('.'), d2 = d1 == sv::npos ? sv::npos : lit.find('.', d1 + 1);
+      std::string key(d2 == sv::npos ? lit : lit.substr(0, d2));
+      entries.push_back({r, (int32_t)k, "\x02" + key});
+    }
+    if (seen.empty()) entries.push_back({r, -2, "\x01"});   // only blank patterns: the rule can never match a topic
+  }
+  std::stable_sort(entries.begin(), entries.end(), [](const Entry& x, const Entry& y) { return x.key < y.key; });
+  const uint32_t NP = (uint32_t)entries.size();
+  t.n_seg = std::max<uint32_t>(1, (NP + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
   t.row_words = t.n_seg * 32;
   const uint32_t W = t.row_words;
+  rule_pos_.assign(R, {});
+  t.pos2rule.assign((size_t)t.n_seg * CORDUM_SEG_RULES, 0xFFFFFFFFu);
+  for (uint32_t p = 0; p < NP; ++p) { rule_pos_[entries[p].rule].push_back(p); t.pos2rule[p] = entries[p].rule; }
+  auto set_rule = [&](uint32_t* row, uint32_t r) { for (uint32_t p : rule_pos_[r]) row[p >> 5] |= 1u << (p & 31); };
   d_tenant_.clear(); d_cap_.clear(); d_pack_.clear(); d_actor_.clear(); d_risk_.clear();
   for (auto& d : d_mcp_) d.clear();
   d_req_.clear();
@@ -398,7 +427,7 @@ void Host::compile_policy() {
     std::vector<std::vector<uint32_t>> hits;   // hits[id-2] = rules
     for (uint32_t r = 0; r < R; ++r) {
       const std::vector<std::string>& lst = list_of(rules[r]);
-      if (lst.empty()) { set_bit(vac, r); continue; }
+      if (lst.empty()) { set_rule(vac.data(), r); continue; }
       for (auto& e : lst) {
         uint32_t id = d.intern(fold_key(e));
         if (hits.size() < id - 1) hits.resize(id - 1);
@@ -410,7 +439,7 @@ void Host::compile_policy() {
       uint32_t* row = rt.row(id);
       or_bits(row, vac);
       if (id >= 2 && id - 2 < hits.size())
-        for (uint32_t r : hits[id - 2]) row[r >> 5] |= 1u << (r & 31);
+        for (uint32_t r : hits[id - 2]) set_rule(row, r);
     }
   };
   scalar_rows(d_tenant_, t.row_tenant, [](const RuleModel& m) -> const std::vector<std::string>& { return m.tenants; });
@@ -423,7 +452,7 @@ void Host::compile_policy() {
     Bits vac(W, 0);
     std::vector<std::vector<uint32_t>> hits;
     for (uint32_t r = 0; r < R; ++r) {
-      if (rules[r].risk_tags.empty()) { set_bit(vac, r); continue; }
+      if (rules[r].risk_tags.empty()) { set_rule(vac.data(), r); continue; }
       for (auto& e : rules[r].risk_tags) {
         uint32_t id = d_risk_.intern(fold_key(e));
         if (hits.size() < id - 1) hits.resize(id - 1);
@@ -437,7 +466,7 @@ void Host::compile_policy() {
     for (uint32_t b = 0; b < nb; ++b) {
       uint32_t* row = t.row_risk.row(1 + b);
       or_bits(row, vac);
-      if (b < hits.size()) for (uint32_t r : hits[b]) row[r >> 5] |= 1u << (r & 31);
+      if (b < hits.size()) for (uint32_t r : hits[b]) set_rule(row, r);
     }
   }
 
@@ -445,19 +474,17 @@ void Host::compile_policy() {
   vac_topic_.assign(W, 0);
   {
     std::unordered_map<std::string, uint32_t> idx;
-    for (uint32_t r = 0; r < R; ++r) {
-      if (rules[r].topics.empty()) { set_bit(vac_topic_, r); continue; }
-      for (auto& e : rules[r].topics) {
-        sv p = trim_space(e);
-        if (p.empty()) continue;   // matchTopic: empty pattern never matches
-        auto it = idx.find(std::string(p));
-        if (it == idx.end()) {
-          it = idx.emplace(std::string(p), (uint32_t)patterns_.size()).first;
-          patterns_.push_back(Pattern{Glob(p), {}});
-        }
-        auto& rl = patterns_[it->second].rules;
-        if (rl.empty() || rl.back() != r) rl.push_back(r);
+    for (uint32_t p = 0; p < NP; ++p) {
+      const Entry& e = entries[p];
+      if (e.pat == -1) { set_bit(vac_topic_, p); continue; }   // no topic predicate
+      if (e.pat < 0) continue;                                 // only blank patterns
+      sv pt = trim_space(rules[e.rule].topics[(size_t)e.pat]);
+      auto it = idx.find(std::string(pt));
+      if (it == idx.end()) {
+        it = idx.emplace(std::string(pt), (uint32_t)patterns_.size()).first;
+        patterns_.push_back(Pattern{Glob(pt), {}});
       }
+      patterns_[it->second].rules.push_back(p);   // bit positions
     }
   }
 
@@ -493,8 +520,8 @@ void Host::compile_policy() {
       if (bit < 64) lneed |= 1ull << bit;
     }
     t.rule_lab_need[r] = lneed;
-    if (!dead) set_bit(alive, r);
-    if (need || lneed) set_bit(check, r);
+    if (!dead) set_rule(alive.data(), r);
+    if (need || lneed) set_rule(check.data(), r);
   }
   policy_capacity_error_.clear();
   if (d_risk_.size() - 2 > 64) policy_capacity_error_ = "more than 64 distinct risk tags referenced by rules";
@@ -517,7 +544,7 @@ void Host::compile_policy() {
             for (auto& e : m.actor_types) if (fold_key(e) == at_names[at]) ok = true;
         }
         if (m.secrets_present >= 0 && (m.secrets_present == 1) != (s == 1)) ok = false;
-        if (ok && (alive[r >> 5] >> (r & 31) & 1)) row[r >> 5] |= 1u << (r & 31);
+        if (ok) for (uint32_t p : rule_pos_[r]) if (alive[p >> 5] >> (p & 31) & 1) row[p >> 5] |= 1u << (p & 31);
       }
     }
   t.v_policy++;
@@ -580,7 +607,7 @@ void Host::compile_mcp_tables() {
     std::vector<std::vector<uint32_t>> allow_hits(d.size()), deny_hits(d.size());
     for (uint32_t r = 0; r < R; ++r) {
       const McpLists& m = rules[r].mcp;
-      if (m.allow[f].empty()) set_bit(base, r);
+      if (m.allow[f].empty()) for (uint32_t p : rule_pos_[r]) set_bit(base, p);
       for (auto& e : m.allow[f]) allow_hits[d.table.find(fold_key(e), 0)].push_back(r);
       for (auto& e : m.deny[f]) deny_hits[d.table.find(fold_key(e), 0)].push_back(r);
     }
@@ -591,8 +618,8 @@ void Host::compile_mcp_tables() {
       uint32_t* row = t.row_mcp[f].row(id);
       or_bits(row, base);
       if (id >= 2) {
-        for (uint32_t r : allow_hits[id]) row[r >> 5] |= 1u << (r & 31);
-        for (uint32_t r : deny_hits[id]) row[r >> 5] &= ~(1u << (r & 31));
+        for (uint32_t r : allow_hits[id]) for (uint32_t p : rule_pos_[r]) row[p >> 5] |= 1u << (p & 31);
+        for (uint32_t r : deny_hits[id]) for (uint32_t p : rule_pos_[r]) row[p >> 5] &= ~(1u << (p & 31));
       }
     }
   }
@@ -626,6 +653,16 @@ void Host::topic_row(sv trimmed, Bits& out) const {
   for (auto& p : patterns_)
     if (p.glob.match(trimmed))
       for (uint32_t r : p.rules) out[r >> 5] |= 1u << (r & 31);
+}
+
+// The 128-bit words of a topic's pass-row that hold any bit: the only words a job on this topic has to AND.
+void Host::topic_words_append(const uint32_t* row) {
+  HostTables& t = t_;
+  t.tw_off.push_back((uint32_t)t.tw_list.size());
+  uint32_t n = 0;
+  for (uint32_t w = 0; w < t.row_words / 4; ++w)
+    if (row[4 * w] | row[4 * w + 1] | row[4 * w + 2] | row[4 * w + 3]) { t.tw_list.push_back((uint16_t)w); ++n; }
+  t.tw_cnt.push_back(n);
 }
 
 void Host::eff_topic_fill(uint32_t cfg, uint32_t topic_id) {
@@ -686,6 +723,8 @@ void Host::rebuild_topics() {
     for (uint32_t k = 0; k < nth; ++k) ts.emplace_back(work);
     for (auto& th : ts) th.join();
   }
+  t.tw_off.clear(); t.tw_cnt.clear(); t.tw_list.clear();
+  for (uint32_t i = 0; i < n; ++i) topic_words_append(t.row_topic.row(i));
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t ri = routing_topics_.find(topic_keys_[i], kMiss);
     topic_entries_[i].pool_off = (uint32_t)t.pool_list.size();
@@ -729,6 +768,7 @@ uint32_t Host::add_topic(sv raw) {
   Bits row(t.row_words, 0);
   if (!e.flags) topic_row(trimmed, row);
   t.row_topic.append(row);
+  topic_words_append(row.data());
   topic_pools_.emplace_back();
   uint32_t ri = routing_topics_.find(raw, kMiss);
   if (t.topic_pool_off.empty() && t.pool_list.size() == 1) {}   // keep placeholder entry

@@ -156,6 +156,9 @@ struct HostTables {
   RowTable row_tenant, row_topic, row_cap, row_pack, row_actor, row_combo, row_risk, row_check, row_mcp[4];
   std::vector<uint64_t> rule_req_need, rule_lab_need;
   std::vector<uint8_t> rule_dec;
+  std::vector<uint32_t> pos2rule;                 // bit position -> original rule index (0xFFFFFFFF = padding)
+  std::vector<uint32_t> tw_off, tw_cnt;           // per topic: its non-zero 128-bit words (offset/count into tw_list)
+  std::vector<uint16_t> tw_list;
   uint32_t mcp_stride = 2;
   uint32_t risk_zero_row = 0, mcp_ones_row[4] = {0, 0, 0, 0};
   std::vector<uint8_t> tenant_mcp, eff_mcp, eff_topic;
@@ -234,6 +237,7 @@ class Host {
   std::vector<std::vector<std::pair<std::string, uint32_t>>> label_key_pairs_;   // per key: (value, bit)
   uint64_t label_empty_mask_ = 0;   // bits of pairs whose value is ""
   std::string default_tenant_trim_;
+  std::vector<std::vector<uint32_t>> rule_pos_;   // rule index -> its bit positions (see compile_policy)
   // topic patterns (distinct trimmed pattern -> rules)
   struct Pattern { Glob glob; std::vector<uint32_t> rules; };
   std::vector<Pattern> patterns_;
@@ -269,6 +273,7 @@ class Host {
   uint32_t add_effcfg(sv payload);     // under mu_
   void topic_row(sv trimmed, Bits& out) const;
   void eff_topic_fill(uint32_t cfg, uint32_t topic_id);
+  void topic_words_append(const uint32_t* row);
   void encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
                     std::vector<uint32_t>& misses) const;
   void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss) const;

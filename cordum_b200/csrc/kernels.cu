@@ -169,12 +169,12 @@ __global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
 // A warp owns a tile of 32 consecutive jobs (lane = job for the coalesced column loads, the scalar
 // decision logic and the 16 B record store).  Needs no worker state, so it runs concurrently with the
 // heartbeat exchange and worker_pool_kernel.
-//   P  8 rounds x 4 jobs: the 8 lanes of group g AND the pass-rows of job (round*4+g); each lane holds
-//      SEGS 128-bit slices, so one step covers SEGS*1024 rules with 7-12 x SEGS independent 128-bit
-//      gathers per lane in flight and one instruction stream for all four jobs.
+//   P  the per-topic word lists of the tile's 32 jobs are walked 32 (job, word) items at a time: each lane ANDs one
+//      128-bit word of the 7-12 pass-rows its job selects (rule bits are permuted so that a topic touches few
+//      words); surviving bits map back to original rule indices; first match = min per job.
 //   D  decision mapping, tenant MCP, effective-config overlay, approval flags, scheduler post-step:
 //      thread per job.
-template <int SEGS, int MINB>
+template <int MINB>
 __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
@@ -198,129 +198,100 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
     }
 
     // =================================================================== P: first matching rule
-    // 8 rounds x 4 jobs: the 8 lanes of group g AND the pass-rows of job (round*4+g); each lane holds
-    // SEGS 128-bit slices (lane `sub` of segment s covers rules s*1024 + sub*128 ..+127).  All four groups
-    // run the same instruction stream (no divergence) with 7-12 x SEGS independent gathers in flight.
-    int first = -1;
-    const bool bypass = P.honor_approved && (c_flags & JF_APPROVED);                 // engine.go:484-522
+    // Rule bits are permuted (and multi-pattern rules duplicated) so that a topic's pass-row is non-zero in only a
+    // few 128-bit words: its word list.  The word lists of the tile's 32 jobs are laid end to end and the 32 lanes
+    // walk that sequence 32 items at a time: lane = one (job, word) item.  It ANDs that word of the 7-12 rows the
+    // job selects and turns surviving bits back into ORIGINAL rule indices (pos2rule); the first match is the
+    // minimum per job (shared-memory atomicMin; survivors are rare).  Every lane is busy in every step and all
+    // lanes run one instruction stream.
+    const bool bypass = P.honor_approved && (c_flags & JF_APPROVED);                                    // engine.go:484-522
     const bool early = (c_flags & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED)) != 0;                        // kernel.go:171-176
     const bool eval = valid && !bypass && !early;
+    __shared__ uint32_t s_best[8][32];
+    uint32_t* my_best = s_best[threadIdx.x >> 5];
+    int first = -1;
     {
-      const unsigned g = lane >> 3, sub = lane & 7;
-      // row offsets of this lane's own job (in Row16 units), computed once per tile
       const uint32_t o_combo = (c_flags & JF_COMBO_MASK) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
                      o_cap = c_cap * rowu4, o_pack = c_pack * rowu4, o_actor = c_actor * rowu4;
-      const unsigned evalmask = __ballot_sync(FULL, eval);
-#pragma unroll 1
-      for (int round = 0; round < 8; ++round) {
-        if (!((evalmask >> (round * 4)) & 0xFu)) continue;
-        const int src = round * 4 + (int)g;
-        bool active = (evalmask >> src) & 1u;
-        const uint32_t fl = __shfl_sync(FULL, c_flags, src);
-        const Row16* p_combo = T.row_combo + __shfl_sync(FULL, o_combo, src) + sub;
-        const Row16* p_tenant = T.row_tenant + __shfl_sync(FULL, o_tenant, src) + sub;
-        const Row16* p_topic = T.row_topic + __shfl_sync(FULL, o_topic, src) + sub;
-        const Row16* p_cap = T.row_cap + __shfl_sync(FULL, o_cap, src) + sub;
-        const Row16* p_pack = T.row_pack + __shfl_sync(FULL, o_pack, src) + sub;
-        const Row16* p_actor = T.row_actor + __shfl_sync(FULL, o_actor, src) + sub;
-        const uint64_t risk = shfl64(FULL, c_risk, src);
-        const bool mcp_used = active && (fl & JF_MCP_USED);
-        const bool any_mcp = __any_sync(FULL, mcp_used);
-        const uint32_t jsrc = tile * 32 + (uint32_t)src;   // the job this group works on (MCP ids / masks are read on demand)
-        uint32_t o_mcp[4] = {0, 0, 0, 0};   // row offsets; groups whose job carries no MCP labels read the all-ones row
-        if (any_mcp) {
+      uint32_t c_twoff = 0, c_twcnt = 0;
+      if (eval) { c_twoff = __ldg(T.tw_off + c_topic); c_twcnt = __ldg(T.tw_cnt + c_topic); }
+      uint32_t incl = c_twcnt;   // inclusive prefix sum of the word counts over the tile
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o_mcp[q] = (mcp_used ? __ldg(C.mcp[q] + jsrc) : T.mcp_ones_row[q]) * rowu4 + sub;
-        }
-        const Row16* p_risk = T.row_risk + sub;
-        const uint32_t* chk_words = reinterpret_cast<const uint32_t*>(T.row_check);
-        int found = -1;
-        uint32_t rule_base = sub * 128u;   // first rule of this lane's slice in segment s0
-        for (uint32_t s0 = 0; s0 < T.n_seg; s0 += SEGS) {   // n_seg is a multiple of SEGS (host pads)
-          uint4 acc[SEGS];
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += t; }
+      const uint32_t excl = incl - c_twcnt, total = __shfl_sync(FULL, incl, 31);
+      my_best[lane] = 0xFFFFFFFFu;
+      __syncwarp();
+      const uint32_t* chk_words = reinterpret_cast<const uint32_t*>(T.row_check);
+      for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const bool have = q < total;
+        // owner of item q = the last lane whose exclusive prefix is <= q (binary search over the warp's registers)
+        int jl = 0;
 #pragma unroll
-          for (int s = 0; s < SEGS; ++s) {
-            const int u = s * (int)CORDUM_SEG_U4;
-            acc[s] = and4(and4(and4(ld_row(p_combo + u), ld_row(p_tenant + u)), and4(ld_row(p_topic + u), ld_row(p_cap + u))),
-                          and4(ld_row(p_pack + u), ld_row(p_actor + u)));
-          }
-          {   // risk tags: containsAny = OR over the job's tags (:308-318).  Branch-free: row 0 = "no referenced tag",
-              // row 1+b = tag b, and lanes that ran out of tags read the all-zero row.
-            uint64_t m = risk;
-            uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
+        for (int st = 16; st; st >>= 1) { const uint32_t e = __shfl_sync(FULL, excl, jl + st); if (e <= q) jl += st; }
+        const uint32_t li = q - __shfl_sync(FULL, excl, jl);
+        const uint32_t fl = __shfl_sync(FULL, c_flags, jl);
+        const uint32_t twoff = __shfl_sync(FULL, c_twoff, jl);   // every lane takes part in every shuffle
+        const uint32_t wi = have ? (uint32_t)__ldg(T.tw_list + twoff + li) : 0u;   // word 0: valid address for idle lanes
+        const Row16* p_combo = T.row_combo + __shfl_sync(FULL, o_combo, jl) + wi;
+        const Row16* p_tenant = T.row_tenant + __shfl_sync(FULL, o_tenant, jl) + wi;
+        const Row16* p_topic = T.row_topic + __shfl_sync(FULL, o_topic, jl) + wi;
+        const Row16* p_cap = T.row_cap + __shfl_sync(FULL, o_cap, jl) + wi;
+        const Row16* p_pack = T.row_pack + __shfl_sync(FULL, o_pack, jl) + wi;
+        const Row16* p_actor = T.row_actor + __shfl_sync(FULL, o_actor, jl) + wi;
+        uint4 acc = and4(and4(and4(ld_row(p_combo), ld_row(p_tenant)), and4(ld_row(p_topic), ld_row(p_cap))),
+                         and4(ld_row(p_pack), ld_row(p_actor)));
+        {   // risk tags: containsAny = OR over the job's tags (:308-318).  Branch-free: row 0 = "no referenced tag",
+            // row 1+b = tag b, and lanes that ran out of tags read the all-zero row.
+          uint64_t m = shfl64(FULL, c_risk, jl);
+          uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
+          m &= m - 1;
+          uint4 rk = ld_row(T.row_risk + (size_t)idx * rowu4 + wi);
+          while (__any_sync(FULL, m != 0)) {
+            idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
             m &= m - 1;
-            uint4 rk[SEGS];
-#pragma unroll
-            for (int s = 0; s < SEGS; ++s) rk[s] = ld_row(p_risk + (size_t)idx * rowu4 + s * (int)CORDUM_SEG_U4);
-            while (__any_sync(FULL, m != 0)) {
-              idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
-              m &= m - 1;
-#pragma unroll
-              for (int s = 0; s < SEGS; ++s) rk[s] = or4(rk[s], ld_row(p_risk + (size_t)idx * rowu4 + s * (int)CORDUM_SEG_U4));
-            }
-#pragma unroll
-            for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], rk[s]);
+            rk = or4(rk, ld_row(T.row_risk + (size_t)idx * rowu4 + wi));
           }
-          if (any_mcp) {   // mcpMatch (:365-382)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int s = 0; s < SEGS; ++s) acc[s] = and4(acc[s], ld_row(T.row_mcp[q] + o_mcp[q] + s0 * CORDUM_SEG_U4 + s * (int)CORDUM_SEG_U4));
-          }
-          const uint32_t keep = active ? 0xFFFFFFFFu : 0u;   // jobs that are not evaluated (or already matched) contribute nothing
-#pragma unroll
-          for (int s = 0; s < SEGS; ++s) { acc[s].x &= keep; acc[s].y &= keep; acc[s].z &= keep; acc[s].w &= keep; }
-
-          // lowest surviving rule of each group; re-evaluated only when a requires/labels subset test fails
-          uint64_t req = 0, lab = 0;
-          bool have_masks = false;
-          while (true) {
-            uint32_t nzs = 0;
-#pragma unroll
-            for (int s = 0; s < SEGS; ++s) nzs |= ((acc[s].x | acc[s].y | acc[s].z | acc[s].w) != 0 ? 1u : 0u) << s;
-            uint32_t gk = nzs ? (((uint32_t)__ffs(nzs) - 1u) << 3 | sub) : 63u;   // order: segment, then lane
-            gk = min(gk, __shfl_xor_sync(FULL, gk, 1));
-            gk = min(gk, __shfl_xor_sync(FULL, gk, 2));
-            gk = min(gk, __shfl_xor_sync(FULL, gk, 4));
-            const bool have = gk != 63u;
-            const uint32_t ws = gk >> 3, wl = gk & 7u;   // winning segment / lane of the group
-            uint4 v = acc[0];
-#pragma unroll
-            for (int t = 1; t < SEGS; ++t) if (ws == (uint32_t)t) v = acc[t];
-            const uint64_t vlo = (uint64_t)v.x | ((uint64_t)v.y << 32), vhi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-            const int mybit = vlo ? __ffsll((long long)vlo) - 1 : 63 + __ffsll((long long)vhi);
-            const int bit = __shfl_sync(FULL, mybit, (int)(g * 8 + wl));
-            const int gmin = (int)((s0 + ws) * CORDUM_SEG_RULES + wl * 128u) + bit;
-            // does the winning rule carry a requires / labels subset test?  (row_check bit; one address per group)
-            const bool pend = have && ((__ldg(chk_words + ((uint32_t)gmin >> 5)) >> (gmin & 31)) & 1u);
-            const unsigned pb = __ballot_sync(FULL, pend);
-            if (!pb) { if (have) found = gmin; break; }
-            if (!have_masks) { req = __ldg(C.req_mask + jsrc); lab = __ldg(C.lab_mask + jsrc); have_masks = true; }
-            bool ok = true;
-            if (pend) {   // containsAll (:320-330), labelsMatch (:332-345)
-              const uint64_t need = __ldg(T.rule_req_need + gmin), ln = __ldg(T.rule_lab_need + gmin);
-              ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
-            }
-            if (pend && !ok && sub == wl) {   // drop the failed rule and look again
-              const uint32_t w = ((uint32_t)bit >> 5) & 3u, mk = ~(1u << (bit & 31));
-#pragma unroll
-              for (int t = 0; t < SEGS; ++t)
-                if ((uint32_t)t == ws) { if (w == 0) acc[t].x &= mk; else if (w == 1) acc[t].y &= mk; else if (w == 2) acc[t].z &= mk; else acc[t].w &= mk; }
-            }
-            if (!__any_sync(FULL, pend && !ok)) { if (have) found = gmin; break; }
-          }
-          if (found >= 0) active = false;
-          if (!__any_sync(FULL, active)) break;   // every job of this round has its first match
-          p_combo += SEGS * CORDUM_SEG_U4; p_tenant += SEGS * CORDUM_SEG_U4; p_topic += SEGS * CORDUM_SEG_U4;
-          p_cap += SEGS * CORDUM_SEG_U4; p_pack += SEGS * CORDUM_SEG_U4; p_actor += SEGS * CORDUM_SEG_U4;
-          p_risk += SEGS * CORDUM_SEG_U4;
-          rule_base += SEGS * CORDUM_SEG_RULES;
+          acc = and4(acc, rk);
         }
-        (void)rule_base;
-        // hand the result to the lane that owns the job (lane L was served in round L>>2 by group L&3)
-        const int v = __shfl_sync(FULL, found, (int)(lane & 3) * 8);
-        if ((int)(lane >> 2) == round) first = v;
+        const uint32_t jsrc = tile * 32 + (uint32_t)jl;   // the job this lane works for (MCP ids / masks are read on demand)
+        const bool mcp_used = have && (fl & JF_MCP_USED);
+        if (__any_sync(FULL, mcp_used)) {   // mcpMatch (:365-382); lanes whose job carries no MCP labels read the all-ones row
+#pragma unroll
+          for (int qf = 0; qf < 4; ++qf) {
+            const uint32_t id = mcp_used ? __ldg(C.mcp[qf] + jsrc) : T.mcp_ones_row[qf];
+            acc = and4(acc, ld_row(T.row_mcp[qf] + (size_t)id * rowu4 + wi));
+          }
+        }
+        const uint32_t keep = have ? 0xFFFFFFFFu : 0u;
+        acc.x &= keep; acc.y &= keep; acc.z &= keep; acc.w &= keep;
+        // surviving bits -> original rule indices; rules carrying a requires / labels subset test are verified
+        // (containsAll :320-330, labelsMatch :332-345).  Usually 0-2 bits per word.
+        uint32_t best = 0xFFFFFFFFu;
+        uint64_t req = 0, lab = 0;
+        bool have_masks = false;
+        while (__any_sync(FULL, (acc.x | acc.y | acc.z | acc.w) != 0)) {
+          const uint64_t vlo = (uint64_t)acc.x | ((uint64_t)acc.y << 32), vhi = (uint64_t)acc.z | ((uint64_t)acc.w << 32);
+          const bool nz = (vlo | vhi) != 0;
+          const int bit = vlo ? __ffsll((long long)vlo) - 1 : (vhi ? 63 + __ffsll((long long)vhi) : 0);
+          const uint32_t pos = wi * 128u + (uint32_t)bit;
+          uint32_t r = nz ? __ldg(T.pos2rule + pos) : 0xFFFFFFFFu;
+          const bool pend = nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u);
+          if (pend) {
+            if (!have_masks) { req = __ldg(C.req_mask + jsrc); lab = __ldg(C.lab_mask + jsrc); have_masks = true; }
+            const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
+            const bool ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
+            if (!ok) r = 0xFFFFFFFFu;
+          }
+          best = min(best, r);
+          const uint32_t mk = ~(1u << (bit & 31)), w = ((uint32_t)bit >> 5) & 3u;   // clear the bit just handled
+          if (nz) { if (w == 0) acc.x &= mk; else if (w == 1) acc.y &= mk; else if (w == 2) acc.z &= mk; else acc.w &= mk; }
+        }
+        if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
       }
+      __syncwarp();
+      first = (int)my_best[lane];   // 0xFFFFFFFF -> -1: no rule matched
+      __syncwarp();
     }
 
     // =================================================================== D: decision (thread per job)
@@ -595,14 +566,11 @@ static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
 
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
-  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 3; }();   // tuning knob
+  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
-  // SEGS = 1024-rule segments each lane group ANDs per step (n_seg is 1, 2 or a multiple of 4: host pads)
-  if (P.t.n_seg <= 1) policy_kernel<1, 4><<<blocks, 256, 0, s>>>(P);
-  else if (P.t.n_seg == 2) policy_kernel<2, 4><<<blocks, 256, 0, s>>>(P);
-  else if (minb == 2) policy_kernel<4, 2><<<blocks, 256, 0, s>>>(P);
-  else if (minb == 4) policy_kernel<4, 4><<<blocks, 256, 0, s>>>(P);
-  else policy_kernel<4, 3><<<blocks, 256, 0, s>>>(P);
+  if (minb == 2) policy_kernel<2><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
+  else policy_kernel<4><<<blocks, 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 

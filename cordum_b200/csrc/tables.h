@@ -78,6 +78,10 @@ typedef struct DeviceTables {
   const uint64_t* rule_req_need;              /* per rule: requires tokens it needs (subset test)       */
   const uint64_t* rule_lab_need;              /* per rule: label pairs it needs                          */
   const uint8_t* rule_dec;                    /* per rule: CORDUM_DEC_* | 0x80 if constraints non-empty */
+  const uint32_t* pos2rule;                   /* bit position -> rule index: rule bits are permuted so that topic rows are sparse */
+  const uint32_t* tw_off;                     /* per topic: offset of its word list in tw_list                           */
+  const uint32_t* tw_cnt;                     /* per topic: number of non-zero 128-bit words of its pass-row             */
+  const uint16_t* tw_list;                    /* word indices (units of Row16 within a row)                              */
   /* tenant-level MCP lists (kernel.go:190-195) and effective-config overlay (kernel.go:218-231):
      verdict per (entry, field, value id): 0 ok, 1 denied, 2 not allowed */
   const uint8_t* tenant_mcp; uint32_t mcp_stride;   /* [n_tenant_pol][4][mcp_stride]                    */

@@ -65,6 +65,7 @@ int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint
   VEC("row_risk", t.row_risk.data) VEC("row_check", t.row_check.data)
   VEC("row_mcp0", t.row_mcp[0].data) VEC("row_mcp1", t.row_mcp[1].data) VEC("row_mcp2", t.row_mcp[2].data)
   VEC("row_mcp3", t.row_mcp[3].data)
+  VEC("pos2rule", t.pos2rule) VEC("tw_off", t.tw_off) VEC("tw_cnt", t.tw_cnt) VEC("tw_list", t.tw_list)
   VEC("rule_req_need", t.rule_req_need) VEC("rule_lab_need", t.rule_lab_need) VEC("rule_dec", t.rule_dec)
   VEC("tenant_mcp", t.tenant_mcp) VEC("eff_mcp", t.eff_mcp) VEC("eff_topic", t.eff_topic)
   VEC("topic_pool_off", t.topic_pool_off) VEC("topic_pool_cnt", t.topic_pool_cnt) VEC("pool_list", t.pool_list)

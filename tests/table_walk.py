@@ -27,6 +27,7 @@ TABLES = {
     "row_tenant": np.uint32, "row_topic": np.uint32, "row_cap": np.uint32, "row_pack": np.uint32,
     "row_actor": np.uint32, "row_combo": np.uint32, "row_risk": np.uint32, "row_check": np.uint32,
     "row_mcp0": np.uint32, "row_mcp1": np.uint32, "row_mcp2": np.uint32, "row_mcp3": np.uint32,
+    "pos2rule": np.uint32, "tw_off": np.uint32, "tw_cnt": np.uint32, "tw_list": np.uint16,
     "rule_req_need": np.uint64, "rule_lab_need": np.uint64, "rule_dec": np.uint8, "tenant_mcp": np.uint8,
     "eff_mcp": np.uint8, "eff_topic": np.uint8, "topic_pool_off": np.uint32, "topic_pool_cnt": np.uint32,
     "pool_list": np.uint32, "pool_req_mask": np.uint64, "pool_req_nonempty": np.uint8, "pool_off": np.uint32,
@@ -207,22 +208,29 @@ def walk(T, cols, mode) -> np.ndarray:
                         acc = acc & rows["row_mcp%d" % f][mid[f]]
                 chk = rows["row_check"][0]
                 lab = int(cols["lab_mask"][j])
-                first = -1
-                for w in np.nonzero(acc)[0]:
-                    bits = int(acc[w])
-                    while bits:
-                        b = (bits & -bits).bit_length() - 1
-                        r = int(w) * 32 + b
-                        if not (int(chk[w]) >> b & 1):
-                            first = r
-                            break
-                        need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
-                        if (need & ~req_mask) == 0 and (ln == 0 or (has_labels and (ln & ~lab) == 0)):
-                            first = r
-                            break
-                        bits &= bits - 1
-                    if first >= 0:
-                        break
+                # rule bits are permuted: only the topic's listed 128-bit words can hold survivors, and the
+                # first match is the minimum ORIGINAL rule index over the surviving bits (kernels.cu phase P)
+                o, c = int(T["tw_off"][topic]), int(T["tw_cnt"][topic])
+                listed = [int(x) for x in T["tw_list"][o:o + c]]
+                outside = acc.copy()
+                for wi in listed:
+                    outside[4 * wi: 4 * wi + 4] = 0
+                assert not outside.any(), "a surviving bit lies outside the topic's word list"
+                best = 1 << 62
+                for wi in listed:
+                    for w in range(4 * wi, 4 * wi + 4):
+                        bits = int(acc[w])
+                        while bits:
+                            b = (bits & -bits).bit_length() - 1
+                            bits &= bits - 1
+                            pos = w * 32 + b
+                            r = int(T["pos2rule"][pos])
+                            if int(chk[w]) >> b & 1:
+                                need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
+                                if not ((need & ~req_mask) == 0 and (ln == 0 or (has_labels and (ln & ~lab) == 0))):
+                                    continue
+                            best = min(best, r)
+                first = best if best < (1 << 62) else -1
                 rule = first
                 code, hascons = wire.DEC_ALLOW, False
                 if first >= 0:
