@@ -246,11 +246,11 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
           uint64_t m = shfl64(FULL, c_risk, jl);
           uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
           m &= m - 1;
-          uint4 rk = ld_row(T.row_risk + (size_t)idx * rowu4 + wi);
+          uint4 rk = ld_row(T.row_risk + (idx * rowu4 + wi));
           while (__any_sync(FULL, m != 0)) {
             idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
             m &= m - 1;
-            rk = or4(rk, ld_row(T.row_risk + (size_t)idx * rowu4 + wi));
+            rk = or4(rk, ld_row(T.row_risk + (idx * rowu4 + wi)));
           }
           acc = and4(acc, rk);
         }
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
 #pragma unroll
           for (int qf = 0; qf < 4; ++qf) {
             const uint32_t id = mcp_used ? __ldg(C.mcp[qf] + jsrc) : T.mcp_ones_row[qf];
-            acc = and4(acc, ld_row(T.row_mcp[qf] + (size_t)id * rowu4 + wi));
+            acc = and4(acc, ld_row(T.row_mcp[qf] + (id * rowu4 + wi)));
           }
         }
         const uint32_t keep = have ? 0xFFFFFFFFu : 0u;
@@ -270,12 +270,14 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
         uint32_t best = 0xFFFFFFFFu;
         uint64_t req = 0, lab = 0;
         bool have_masks = false;
-        while (__any_sync(FULL, (acc.x | acc.y | acc.z | acc.w) != 0)) {
-          const uint64_t vlo = (uint64_t)acc.x | ((uint64_t)acc.y << 32), vhi = (uint64_t)acc.z | ((uint64_t)acc.w << 32);
-          const bool nz = (vlo | vhi) != 0;
-          const int bit = vlo ? __ffsll((long long)vlo) - 1 : (vhi ? 63 + __ffsll((long long)vhi) : 0);
-          const uint32_t pos = wi * 128u + (uint32_t)bit;
-          uint32_t r = nz ? __ldg(T.pos2rule + pos) : 0xFFFFFFFFu;
+        uint64_t vlo = (uint64_t)acc.x | ((uint64_t)acc.y << 32), vhi = (uint64_t)acc.z | ((uint64_t)acc.w << 32);
+        while (__any_sync(FULL, (vlo | vhi) != 0)) {
+          // lowest surviving bit of the 128-bit word, branch-free
+          const bool lo_nz = vlo != 0, nz = (vlo | vhi) != 0;
+          const int b_lo = __ffsll((long long)vlo), b_hi = __ffsll((long long)vhi);
+          const uint32_t bit = lo_nz ? (uint32_t)(b_lo - 1) : (uint32_t)(63 + b_hi);
+          const uint32_t pos = nz ? wi * 128u + bit : 0u;
+          uint32_t r = __ldg(T.pos2rule + pos);
           const bool pend = nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u);
           if (pend) {
             if (!have_masks) { req = __ldg(C.req_mask + jsrc); lab = __ldg(C.lab_mask + jsrc); have_masks = true; }
@@ -283,9 +285,10 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
             const bool ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
             if (!ok) r = 0xFFFFFFFFu;
           }
-          best = min(best, r);
-          const uint32_t mk = ~(1u << (bit & 31)), w = ((uint32_t)bit >> 5) & 3u;   // clear the bit just handled
-          if (nz) { if (w == 0) acc.x &= mk; else if (w == 1) acc.y &= mk; else if (w == 2) acc.z &= mk; else acc.w &= mk; }
+          best = min(best, nz ? r : 0xFFFFFFFFu);
+          const uint64_t lo_cleared = vlo & (vlo - 1), hi_cleared = vhi & (vhi - 1);   // drop the bit just handled
+          vhi = lo_nz ? vhi : hi_cleared;
+          vlo = lo_cleared;
         }
         if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
       }
