@@ -61,7 +61,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms from the start of the timed region to the end of the
+    measurement loops (throughput, per-kernel, end-to-end)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,14 +74,14 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
@@ -258,10 +259,11 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # Serialized launches (wait after every step) so the CUDA-event span of a kernel contains that kernel only;
     # in the throughput loop above policy_kernel overlaps the previous step's route_kernel / worker_pool_kernel.
     pol_ms, rte_ms = [], []
-    for k in range(max(6, min(args.steps, 12))):
+    step(0, batches[0], True)          # one more heartbeat epoch, then hold the worker tables still so that
+    sync_all()                         # route_kernel's event span does not contain a wait for worker_pool_kernel
+    for k in range(max(8, min(args.steps, 16))):
         b = batches[k % n_rot]
-        step(k, b, True)
-        b.wait()
+        b.dispatch_resident(wire.MODE_POLICY_AND_ROUTE)
         if k >= 2:
             p_, r_ = b.kernel_times()
             pol_ms.append(p_)
@@ -269,7 +271,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     sync_all()
 
     # ---------------------------------------------------------------- end to end: `e2e`
-    e2e_steps = max(2, min(args.steps, 6))
+    e2e_steps = max(4, min(args.steps, 12))
     for k in range(2):
         batches[k % 2].encode(my_jobs)
         step(k, batches[k % 2], False)
@@ -337,7 +339,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                 "from_encoded_columns": J * e2e_steps / e2e_cols_elapsed, "host_encode_s_per_batch": enc_s},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "policy_kernel<4,3>", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "policy_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src,
                      "other_kernels": {"route_kernel_ms": r_ms},
                      "whole_path": {"algorithmic_bytes": int(path_bytes), "kernels_ms": k_ms + r_ms, "achieved": path_gbs,

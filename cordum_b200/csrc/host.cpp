@@ -360,6 +360,46 @@ int test_glob(sv pattern, sv name) {
   return g.match(name) ? 1 : 0;
 }
 
+// ============================================================ WorkPool
+WorkPool::WorkPool(uint32_t threads) {
+  for (uint32_t i = 1; i < threads; ++i) threads_.emplace_back([this, i]() { worker(i); });
+}
+WorkPool::~WorkPool() {
+  { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+  cv_.notify_all();
+  for (auto& t : threads_) t.join();
+}
+void WorkPool::drain(uint32_t id) {
+  while (true) {
+    uint32_t b = next_.fetch_add(grain_);
+    if (b >= n_) break;
+    (*fn_)(b, std::min(n_, b + grain_), id);
+  }
+}
+void WorkPool::worker(uint32_t id) {
+  uint64_t seen = 0;
+  while (true) {
+    {
+      std::unique_lock<std::mutex> g(mu_);
+      cv_.wait(g, [&]() { return stop_ || epoch_ != seen; });
+      if (stop_) return;
+      seen = epoch_;
+    }
+    drain(id);
+    { std::lock_guard<std::mutex> g(mu_); if (--active_ == 0) done_cv_.notify_one(); }
+  }
+}
+void WorkPool::parallel_for(uint32_t n, uint32_t grain, const std::function<void(uint32_t, uint32_t, uint32_t)>& fn) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    fn_ = &fn; n_ = n; grain_ = grain ? grain : 1; next_.store(0); active_ = (uint32_t)threads_.size(); ++epoch_;
+  }
+  cv_.notify_all();
+  drain(0);   // the caller works too
+  std::unique_lock<std::mutex> g(mu_);
+  done_cv_.wait(g, [&]() { return active_ == 0; });
+}
+
 // ============================================================ Host
 Host::Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads)
     : max_topics_(max_topics ? max_topics : 65536), max_effcfgs_(max_effcfgs ? max_effcfgs : 4096) {
@@ -1192,17 +1232,11 @@ int Host::encode(const cordum_envelopes* env, HostColumns& out, std::string& err
   if (!env) { err = "null envelopes"; return CORDUM_E_INVALID; }
   std::lock_guard<std::mutex> g(mu_);
   const uint32_t n = env->n_jobs;
-  uint32_t nth = std::min<uint32_t>(threads_, std::max<uint32_t>(1, n / 4096));
-  std::vector<std::vector<uint32_t>> misses(nth);
-  if (nth <= 1) encode_range(env, 0, n, out, misses[0]);
+  std::vector<std::vector<uint32_t>> misses(threads_);
+  if (n < 8192 || threads_ <= 1) encode_range(env, 0, n, out, misses[0]);
   else {
-    std::vector<std::thread> ts;
-    uint32_t per = (n + nth - 1) / nth;
-    for (uint32_t k = 0; k < nth; ++k) {
-      uint32_t a = std::min(n, k * per), b = std::min(n, a + per);
-      ts.emplace_back([&, a, b, k]() { encode_range(env, a, b, out, misses[k]); });
-    }
-    for (auto& t : ts) t.join();
+    if (!pool_) pool_ = std::make_unique<WorkPool>(threads_);
+    pool_->parallel_for(n, 2048, [&](uint32_t a, uint32_t b, uint32_t w) { encode_range(env, a, b, out, misses[w]); });
   }
   // dictionary misses: register the new topics / effective configs, then re-encode just those jobs
   for (auto& lst : misses)

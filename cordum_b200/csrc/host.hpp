@@ -12,8 +12,12 @@
 //   pool / label filtering          core/controlplane/scheduler/strategy_least_loaded.go:161-265
 #pragma once
 #include <cstdint>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <string_view>
 #include <unordered_map>
@@ -187,6 +191,28 @@ struct HostColumns {
   uint32_t* flags;
 };
 
+// Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks, so a
+// descheduled thread on a busy host delays one chunk, not 1/T of the batch.
+class WorkPool {
+ public:
+  explicit WorkPool(uint32_t threads);
+  ~WorkPool();
+  void parallel_for(uint32_t n, uint32_t grain, const std::function<void(uint32_t, uint32_t, uint32_t)>& fn);   // fn(begin, end, worker)
+  uint32_t size() const { return (uint32_t)threads_.size() + 1; }
+
+ private:
+  void worker(uint32_t id);
+  void drain(uint32_t id);
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(uint32_t, uint32_t, uint32_t)>* fn_ = nullptr;
+  std::atomic<uint32_t> next_{0};
+  uint32_t n_ = 0, grain_ = 1, active_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
 class Host {
  public:
   Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads);
@@ -224,6 +250,7 @@ class Host {
   uint32_t max_topics_, max_effcfgs_, threads_;
   std::string policy_capacity_error_, routing_capacity_error_;
   std::vector<WorkerRaw> workers_raw_;
+  std::unique_ptr<WorkPool> pool_;   // created on first large encode
   PolicyModel policy_;
   RoutingModel routing_;
   std::string snapshot_;
