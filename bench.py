@@ -277,12 +277,16 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         step(k, batches[k % 2], False)
     sync_all()
     t0 = time.perf_counter()
+    enc_ms = []
     for k in range(e2e_steps):
         b = batches[k % 2]
+        te = time.perf_counter()
         b.encode(my_jobs)                  # waits for this batch's previous run, then host encode
+        enc_ms.append((time.perf_counter() - te) * 1e3)
         step(k, b, False)                  # H2D columns + kernels + D2H records, async
     sync_all()
     e2e_elapsed = time.perf_counter() - t0
+    log("e2e per-step encode(+wait) ms:", " ".join("%.1f" % x for x in enc_ms))
     # from already-encoded pinned columns (copies + kernels only)
     t0 = time.perf_counter()
     for k in range(e2e_steps):

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -369,35 +371,36 @@ WorkPool::~WorkPool() {
   cv_.notify_all();
   for (auto& t : threads_) t.join();
 }
-void WorkPool::drain(uint32_t id) {
+void WorkPool::drain(Job& j, uint32_t id) {
   while (true) {
-    uint32_t b = next_.fetch_add(grain_);
-    if (b >= n_) break;
-    (*fn_)(b, std::min(n_, b + grain_), id);
+    uint32_t b = j.next.fetch_add(j.grain, std::memory_order_relaxed);
+    if (b >= j.n) break;
+    uint32_t e = std::min(j.n, b + j.grain);
+    (*j.fn)(b, e, id);
+    j.done.fetch_add(e - b, std::memory_order_release);
   }
 }
 void WorkPool::worker(uint32_t id) {
   uint64_t seen = 0;
   while (true) {
+    std::shared_ptr<Job> job;
     {
       std::unique_lock<std::mutex> g(mu_);
       cv_.wait(g, [&]() { return stop_ || epoch_ != seen; });
       if (stop_) return;
       seen = epoch_;
+      job = current_;
     }
-    drain(id);
-    { std::lock_guard<std::mutex> g(mu_); if (--active_ == 0) done_cv_.notify_one(); }
+    if (job) drain(*job, id);   // a late waker finds the queue empty and goes back to sleep
   }
 }
-void WorkPool::parallel_for(uint32_t n, uint32_t grain, const std::function<void(uint32_t, uint32_t, uint32_t)>& fn) {
-  {
-    std::lock_guard<std::mutex> g(mu_);
-    fn_ = &fn; n_ = n; grain_ = grain ? grain : 1; next_.store(0); active_ = (uint32_t)threads_.size(); ++epoch_;
-  }
+void WorkPool::parallel_for(uint32_t n, uint32_t grain, const Fn& fn) {
+  auto job = std::make_shared<Job>();
+  job->fn = &fn; job->n = n; job->grain = grain ? grain : 1;
+  { std::lock_guard<std::mutex> g(mu_); current_ = job; ++epoch_; }
   cv_.notify_all();
-  drain(0);   // the caller works too
-  std::unique_lock<std::mutex> g(mu_);
-  done_cv_.wait(g, [&]() { return active_ == 0; });
+  drain(*job, 0);   // the caller works too
+  while (job->done.load(std::memory_order_acquire) < n) std::this_thread::yield();   // only chunks still in flight
 }
 
 // ============================================================ Host
@@ -405,6 +408,21 @@ Host::Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads)
     : max_topics_(max_topics ? max_topics : 65536), max_effcfgs_(max_effcfgs ? max_effcfgs : 4096) {
   unsigned hw = std::thread::hardware_concurrency();
   threads_ = encode_threads ? encode_threads : (hw ? hw : 4);
+  if (!encode_threads) {
+    // Containers: more busy threads than the CPU quota only buys CFS throttling stalls.
+    double quota = 0;
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {                       // cgroup v2: "<quota|max> <period>"
+      char q[32]; long per = 0;
+      if (fscanf(f, "%31s %ld", q, &per) == 2 && per > 0 && q[0] != 'm') quota = atof(q) / (double)per;
+      fclose(f);
+    } else {
+      long q = -1, per = 0;                                                      // cgroup v1
+      if (FILE* a = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(a, "%ld", &q) != 1) q = -1; fclose(a); }
+      if (FILE* b = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(b, "%ld", &per) != 1) per = 0; fclose(b); }
+      if (q > 0 && per > 0) quota = (double)q / (double)per;
+    }
+    if (quota >= 1.0 && quota < threads_) threads_ = (uint32_t)(quota + 0.5);
+  }
   if (threads_ > 64) threads_ = 64;
   std::string err;
   compile_policy();
@@ -1060,6 +1078,23 @@ const std::vector<std::string>& Host::topic_pool_names(uint32_t topic_id) const 
 }
 
 // ============================================================ encoder
+// Span-identity caches.  Envelope strings are (offset,len) spans into one arena and equal strings usually share
+// one span (the arena packers intern), so within a call most lookups repeat an address already resolved.  A small
+// direct-mapped cache keyed by (pointer, length) skips the byte hash + fold for those; it lives on the worker's
+// stack for the duration of one encode call, while the arena is immutable.
+struct EncodeCaches {
+  struct Entry { const char* p = nullptr; uint32_t len = 0, val = 0, aux = 0; };
+  static constexpr uint32_t N = 512;
+  Entry topic[N], tenant[N], cap[N], pack[N], actor[N], risk[N], req[N];
+  static uint32_t slot(sv s) { return (uint32_t)((((uintptr_t)s.data() >> 1) ^ s.size()) * 0x9E3779B1u) >> 23; }   // 9 bits
+  static bool get(const Entry* t, sv s, uint32_t& val, uint32_t& aux) {
+    const Entry& e = t[slot(s)];
+    if (e.p == s.data() && e.len == s.size()) { val = e.val; aux = e.aux; return true; }
+    return false;
+  }
+  static void put(Entry* t, sv s, uint32_t val, uint32_t aux) { t[slot(s)] = Entry{s.data(), (uint32_t)s.size(), val, aux}; }
+};
+
 namespace {
 inline sv span(const cordum_envelopes* e, const cordum_str* col, uint32_t j) {
   return col ? sv((const char*)e->arena + col[j].off, col[j].len) : sv();
@@ -1088,12 +1123,18 @@ inline int mcp_key(sv k) {
 }
 }  // namespace
 
-void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss) const {
+void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss, EncodeCaches& cc) const {
+  uint32_t cv = 0, ca = 0;
   uint32_t flags = 0;
   // ---- topic (dictionary keyed by the RAW string: policy sees TrimSpace(topic), routing the raw one)
   sv topic_raw = span(env, env->topic, j);
-  uint32_t tid = topic_ids_.find(topic_raw, kMiss);
-  if (tid == kMiss) { miss = true; tid = 0; }
+  uint32_t tid;
+  if (!topic_raw.empty() && EncodeCaches::get(cc.topic, topic_raw, cv, ca)) tid = cv;
+  else {
+    tid = topic_ids_.find(topic_raw, kMiss);
+    if (tid == kMiss) { miss = true; tid = 0; }
+    else if (!topic_raw.empty()) EncodeCaches::put(cc.topic, topic_raw, tid, 0);
+  }
   out.topic[j] = tid;
   flags |= topic_entries_[tid].flags;
   // ---- tenant (kernel.go:134-169)
@@ -1102,8 +1143,12 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
   if (tenant.empty() && has_meta) tenant = trim_space(span(env, env->meta_tenant_id, j));
   if (tenant.empty()) tenant = default_tenant_trim_;
   if (tenant.empty()) tenant = "default";
-  out.tenant_pol[j] = tenant_pol_.find(tenant, 0);   // exact-string map lookup (kernel.go:190)
-  out.tenant[j] = lookup_value(d_tenant_, tenant);
+  if (EncodeCaches::get(cc.tenant, tenant, cv, ca)) { out.tenant[j] = cv; out.tenant_pol[j] = ca; }
+  else {
+    out.tenant_pol[j] = tenant_pol_.find(tenant, 0);   // exact-string map lookup (kernel.go:190)
+    out.tenant[j] = lookup_value(d_tenant_, tenant);
+    EncodeCaches::put(cc.tenant, tenant, out.tenant[j], out.tenant_pol[j]);
+  }
   // ---- meta (policyMetaFromRequest, kernel.go:348-368)
   sv principal = span(env, env->principal_id, j);
   sv cap, pack, actor = principal;
@@ -1116,27 +1161,47 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
     int raw_at = env->actor_type ? env->actor_type[j] : 0;
     at = (raw_at == 1 || raw_at == 2) ? raw_at : 0;
   }
-  out.capability[j] = lookup_value(d_cap_, cap);
-  out.pack[j] = lookup_value(d_pack_, pack);
-  out.actor[j] = lookup_value(d_actor_, actor);
+  auto cached = [&](EncodeCaches::Entry* tab, const Dict& d, sv v) -> uint32_t {
+    if (v.empty()) return CORDUM_ID_EMPTY;
+    uint32_t val, aux;
+    if (EncodeCaches::get(tab, v, val, aux)) return val;
+    val = lookup_value(d, v);
+    EncodeCaches::put(tab, v, val, 0);
+    return val;
+  };
+  out.capability[j] = cached(cc.cap, d_cap_, cap);
+  out.pack[j] = cached(cc.pack, d_pack_, pack);
+  out.actor[j] = cached(cc.actor, d_actor_, actor);
   // ---- risk tags / requires
   uint64_t risk = 0, req = 0;
   bool secrets_tag = false;
   if (has_meta && env->risk_off)
     for (uint32_t k = env->risk_off[j]; k < env->risk_off[j + 1]; ++k) {
       sv tag = span(env, env->risk_tags, k);
-      if (fold_eq(tag, "secrets")) secrets_tag = true;   // kernel.go:387-391 (no trim)
-      uint32_t id = lookup_value(d_risk_, tag);
+      uint32_t id, is_secrets;
+      if (tag.empty()) continue;
+      if (!EncodeCaches::get(cc.risk, tag, id, is_secrets)) {
+        is_secrets = fold_eq(tag, "secrets") ? 1u : 0u;   // kernel.go:387-391 (no trim)
+        id = lookup_value(d_risk_, tag);
+        EncodeCaches::put(cc.risk, tag, id, is_secrets);
+      }
+      if (is_secrets) secrets_tag = true;
       if (id >= 2 && id - 2 < 64) risk |= 1ull << (id - 2);
     }
   if (has_meta && env->requires_off) {
     uint32_t a = env->requires_off[j], b = env->requires_off[j + 1];
     if (b > a) flags |= JF_REQ_NONEMPTY;
     for (uint32_t k = a; k < b; ++k) {
-      FoldBuf f(span(env, env->requires_, k));
-      uint32_t id = d_req_.table.find(f.view, 0);
+      sv tok = span(env, env->requires_, k);
+      uint32_t id, blank;
+      if (tok.empty() || !EncodeCaches::get(cc.req, tok, id, blank)) {
+        FoldBuf f(tok);
+        id = d_req_.table.find(f.view, 0);
+        blank = f.view.empty() ? 1u : 0u;
+        if (!tok.empty()) EncodeCaches::put(cc.req, tok, id, blank);
+      }
       if (id >= 2 && id - 2 < 64) req |= 1ull << (id - 2);
-      else if (!f.view.empty()) flags |= JF_REQ_UNKNOWN;   // no pool declares it -> no pool satisfies (:255-262)
+      else if (!blank) flags |= JF_REQ_UNKNOWN;   // no pool declares it -> no pool satisfies (:255-262)
     }
   }
   out.risk_mask[j] = risk;
@@ -1221,9 +1286,10 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
 
 void Host::encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
                         std::vector<uint32_t>& misses) const {
+  auto cc = std::make_unique<EncodeCaches>();   // ~56 KB, per chunk
   for (uint32_t j = a; j < b; ++j) {
     bool miss = false;
-    encode_job(env, j, out, miss);
+    encode_job(env, j, out, miss, *cc);
     if (miss) misses.push_back(j);
   }
 }
@@ -1246,7 +1312,8 @@ int Host::encode(const cordum_envelopes* env, HostColumns& out, std::string& err
       sv eff = span(env, env->effective_config, j);
       if (!eff.empty() && add_effcfg(eff) == kMiss) { err = "effective-config dictionary full (max_effcfgs)"; return CORDUM_E_CAPACITY; }
       bool miss = false;
-      encode_job(env, j, out, miss);
+      EncodeCaches cc;
+      encode_job(env, j, out, miss, cc);
     }
   return CORDUM_OK;
 }

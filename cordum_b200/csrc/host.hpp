@@ -29,6 +29,8 @@
 
 namespace cordum {
 
+struct EncodeCaches;
+
 // ------------------------------------------------------------------ string-keyed hash table
 // Open addressing, keyed by bytes, lookups take a string_view (no allocation on the encode path).
 class StrTable {
@@ -191,24 +193,29 @@ struct HostColumns {
   uint32_t* flags;
 };
 
-// Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks, so a
-// descheduled thread on a busy host delays one chunk, not 1/T of the batch.
+// Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks.  Completion
+// is "every item processed", not "every worker checked in": a worker the OS has descheduled (busy or
+// quota-throttled host) costs nothing once the others have drained the queue.
 class WorkPool {
  public:
   explicit WorkPool(uint32_t threads);
   ~WorkPool();
-  void parallel_for(uint32_t n, uint32_t grain, const std::function<void(uint32_t, uint32_t, uint32_t)>& fn);   // fn(begin, end, worker)
+  using Fn = std::function<void(uint32_t, uint32_t, uint32_t)>;   // fn(begin, end, worker)
+  void parallel_for(uint32_t n, uint32_t grain, const Fn& fn);
   uint32_t size() const { return (uint32_t)threads_.size() + 1; }
 
  private:
+  struct Job {
+    const Fn* fn;
+    uint32_t n, grain;
+    std::atomic<uint32_t> next{0}, done{0};
+  };
   void worker(uint32_t id);
-  void drain(uint32_t id);
+  static void drain(Job& j, uint32_t id);
   std::vector<std::thread> threads_;
   std::mutex mu_;
-  std::condition_variable cv_, done_cv_;
-  const std::function<void(uint32_t, uint32_t, uint32_t)>* fn_ = nullptr;
-  std::atomic<uint32_t> next_{0};
-  uint32_t n_ = 0, grain_ = 1, active_ = 0;
+  std::condition_variable cv_;
+  std::shared_ptr<Job> current_;
   uint64_t epoch_ = 0;
   bool stop_ = false;
 };
@@ -303,7 +310,7 @@ class Host {
   void topic_words_append(const uint32_t* row);
   void encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
                     std::vector<uint32_t>& misses) const;
-  void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss) const;
+  void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss, struct EncodeCaches& cc) const;
 };
 
 // test hooks (also exported through the C ABI as cordum_test_*)
