@@ -1,21 +1,22 @@
 // kernels.cu — sm_100a kernels of the policy-gate + dispatch path.
 //
-//   worker_pool_kernel   per heartbeat epoch: load score / overload per worker, per-pool argmin
-//                        (strategy_least_loaded.go:157-159 loadScore, :177-193 isOverloaded)
-//   dispatch_kernel      per job batch: bit-parallel first-match over the rule set
-//                        (safety_policy.go:187-206, 259-294), decision mapping + tenant MCP +
-//                        effective-config overlay (kernel.go:187-248), scheduler post-step
-//                        (engine.go:528-530), pool filter + least-loaded pick
-//                        (strategy_least_loaded.go:40-136)
+//   worker_pool_kernel   per heartbeat epoch: load score / overload per worker (strategy_least_loaded.go:157-159,
+//                        :177-193), pool kept sorted by load, per-label bitmaps over that order, per-pool argmin
+//   policy_kernel        per job batch: first-match over the rule set (safety_policy.go:187-206, 259-294), decision
+//                        mapping + tenant MCP + effective-config overlay (kernel.go:187-248), scheduler post-step
+//                        (engine.go:528-530)
+//   route_kernel         per job batch: pool filter + least-loaded pick (strategy_least_loaded.go:40-136) for the
+//                        jobs that may dispatch (engine.go:298-347)
 //
 // Integer / bit work only: no tensor cores (north star).  Mapping to the hardware:
-//   * job columns are column-major; a warp loads 32 consecutive jobs with one coalesced
-//     128 B request per u32 column (256 B per u64 column) through the read-only, no-L1-allocate path
-//   * the 32 lanes of a warp cooperate on one job's rule scan: lane = one 128-bit slice of every
-//     pass-row, so 4096 rules are ANDed per step with 7-12 independent 128-bit gathers per lane
-//   * rows are gathered through L1/L2 (the tables are a few MB: L2-resident, hot rows L1-resident)
-//   * first match = ballot + ffs; routing reductions are shuffles; worker pools are kept sorted by
-//     load (bitonic sort in shared memory) so label-constrained picks stop at the first match
+//   * job columns are column-major; a warp loads 32 consecutive jobs with one coalesced 128 B request per u32
+//     column (256 B per u64 column) through the read-only, no-L1-allocate path
+//   * rule predicates live in bit-rows ("pass-rows"); rule bits are laid out so that a topic touches few 128-bit
+//     words, and a warp walks the (job, word) items of its 32 jobs densely: one 128-bit gather per row per lane,
+//     7-12 independent gathers in flight, all lanes on one instruction stream
+//   * the tables are a few MB: L2-resident, hot rows L1-resident; DRAM traffic is the job columns and records
+//   * first match / argmin = ballot, ffs, shuffles and shared-memory atomicMin; worker pools are kept sorted by
+//     load (bitonic sort in shared memory) so label-constrained picks are bitmap ANDs
 //   * decision records are written back coalesced, 16 B per lane
 // IEEE float32 with explicit _rn intrinsics, no fast-math: scores compare exactly like Go's.
 #include <cuda_runtime.h>
