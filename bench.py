@@ -166,6 +166,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     from cordum_b200 import engine, shard, synth, wire
 
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = synth.make_config("c3")

@@ -65,18 +65,25 @@ struct cordum_engine {
   bool failed = false;           // sticky CUDA failure
   std::string fail_msg;
   cudaStream_t s_tables = nullptr;
-  cudaEvent_t ev_tables = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_prod = nullptr;
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
   DevBuf b_row_tenant, b_row_topic, b_row_cap, b_row_pack, b_row_actor, b_row_combo, b_row_risk, b_row_check, b_row_mcp[4];
   DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule, b_tw_off, b_tw_cnt, b_tw_list;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
-  DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi, b_loads;
-  DevBuf b_pos_key, b_pool_best, b_pool_mincnt, b_flush, b_skey, b_slab_lo, b_slab_hi, b_pool_sorted, b_pool_nok, b_lbm, b_lbm_off, b_rank_pos;
+  DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi;
+  DevBuf b_flush, b_lbm_off, b_rank_pos;
+  // Everything worker_pool_kernel derives from the loads, in TWO copies: the refresh for heartbeat epoch k+1 writes
+  // one set while route kernels of epoch k still read the other, so consecutive steps pipeline instead of serialising.
+  struct DerivedSet {
+    DevBuf loads, pos_key, skey, slab_lo, slab_hi, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
+    cudaEvent_t ready = nullptr;
+  } ds[2];
+  int cur = 0;                   // set holding the latest refresh
+  bool host_loads = true;        // the next refresh takes the loads from the host tables
   uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
   std::vector<cordum_batch*> batches;   // live batches (guarded by mu): K2 must wait for their kernels
   bool pools_dirty = true;       // K2 must run before the next dispatch
-  bool loads_on_device = false;  // last load table came from cordum_workers_set_loads_device
   std::atomic<uint64_t> launches{0};
 };
 
@@ -85,10 +92,12 @@ struct cordum_batch {
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
   bool encoded = false, resident = false, pending = false, launched = false;
+  int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned
   uint8_t* d_cols = nullptr;
   cordum_decision* h_out = nullptr;   // pinned
   cordum_decision* d_out = nullptr;
+  uint32_t* d_route = nullptr;        // [0] = count, [1..] = compacted list of dispatchable jobs
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
   float total_ms = 0, kernel_ms = 0, policy_ms = 0, route_ms = 0;
@@ -195,13 +204,18 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_rank_pos, t.rank_pos, s), "upload");
     d.rank_pos = (const uint32_t*)e->b_rank_pos.p;
     CK(up(e->b_pos_label_lo, t.pos_label_lo, s), "upload"); CK(up(e->b_pos_label_hi, t.pos_label_hi, s), "upload");
-    CK(e->b_pos_key.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-    CK(e->b_pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
-    CK(e->b_pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
-    CK(e->b_skey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-    CK(e->b_slab_lo.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-    CK(e->b_slab_hi.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-    CK(e->b_pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
+    for (auto& D : e->ds) {
+      CK(D.pos_key.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+      CK(D.pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
+      CK(D.pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+      CK(D.skey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+      CK(D.slab_lo.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+      CK(D.slab_hi.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+      CK(D.pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
+      CK(D.pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+      CK(D.lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
+      CK(D.loads.reserve((size_t)std::max<uint32_t>(t.n_slots, 1) * sizeof(Load16)), "alloc");
+    }
     {
       // K2 sort buffer: next power of two >= the largest pool, capped at 8192 entries (96 KiB of shared memory)
       uint32_t largest = 1;
@@ -210,44 +224,65 @@ int sync_tables(cordum_engine* e) {
       while (cap < largest && cap < 8192) cap <<= 1;
       d.sort_cap = cap;
     }
-    d.skey = (uint64_t*)e->b_skey.p; d.slab_lo = (uint64_t*)e->b_slab_lo.p; d.slab_hi = (uint64_t*)e->b_slab_hi.p;
-    d.pool_sorted = (uint8_t*)e->b_pool_sorted.p;
-    CK(e->b_pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
-    CK(e->b_lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
     CK(up(e->b_lbm_off, t.lbm_off, s), "upload");
-    d.pool_nok = (uint32_t*)e->b_pool_nok.p; d.lbm = (uint32_t*)e->b_lbm.p; d.lbm_off = (const uint32_t*)e->b_lbm_off.p;
+    d.lbm_off = (const uint32_t*)e->b_lbm_off.p;
     d.place_bits = t.place_bits;
     d.n_pos = t.n_pos; d.n_pools = t.n_pools;
     d.pool_off = (const uint32_t*)e->b_pool_off.p; d.pos_pool = (const uint32_t*)e->b_pos_pool.p;
     d.pos_slot = (const uint32_t*)e->b_pos_slot.p; d.pos_rank = (const uint32_t*)e->b_pos_rank.p;
     d.slot_pos = (const uint32_t*)e->b_slot_pos.p; d.rank_slot = (const uint32_t*)e->b_rank_slot.p;
     d.pos_label_lo = (const uint64_t*)e->b_pos_label_lo.p; d.pos_label_hi = (const uint64_t*)e->b_pos_label_hi.p;
-    d.pos_key = (uint64_t*)e->b_pos_key.p; d.pool_best = (uint64_t*)e->b_pool_best.p; d.pool_mincnt = (uint32_t*)e->b_pool_mincnt.p;
     e->v_workers = t.v_workers;
     e->pools_dirty = true;
-    e->loads_on_device = false;
+    e->host_loads = true;
   }
-  if (t.v_loads != e->v_loads) {
-    if (!e->loads_on_device) {
-      CK(up(e->b_loads, t.loads, s), "upload");
-      d.loads = (const Load16*)e->b_loads.p;
-    }
+  if (t.v_loads != e->v_loads) {   // heartbeat deltas applied on the host (cordum_workers_update)
     e->v_loads = t.v_loads;
     e->pools_dirty = true;
+    e->host_loads = true;
   }
   CK(cudaStreamSynchronize(s), "table upload");
   return CORDUM_OK;
 }
 
-// K2 when the worker loads changed; batches wait on ev_tables.
-int refresh_pools(cordum_engine* e) {
-  if (!e->pools_dirty) return CORDUM_OK;
-  // the dispatch kernels read pos_key / pool_best: order K2 after every kernel already enqueued
+// The kernels' view of the tables with the derived pointers of one set.
+DeviceTables view(const cordum_engine* e, int set) {
+  DeviceTables d = e->dt;
+  const auto& D = e->ds[set];
+  d.loads = (const Load16*)D.loads.p;
+  d.pos_key = (uint64_t*)D.pos_key.p; d.skey = (uint64_t*)D.skey.p; d.slab_lo = (uint64_t*)D.slab_lo.p; d.slab_hi = (uint64_t*)D.slab_hi.p;
+  d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.lbm = (uint32_t*)D.lbm.p;
+  d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
+  return d;
+}
+
+// worker_pool_kernel for a new heartbeat epoch, into the set that is NOT being read.  dev_loads: the full slot-ordered
+// load table already in HBM (produced on `producer`), or null to take the host tables' loads.  Called with both mutexes held.
+int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer) {
+  if (!e->pools_dirty && !dev_loads) return CORDUM_OK;
+  const int target = e->cur ^ 1;
+  auto& D = e->ds[target];
+  // route kernels that still read the target set (launched two epochs ago) must have finished
   for (cordum_batch* b : e->batches)
-    if (b->launched) CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait dispatch");
-  CK(launch_worker_pools(e->dt, e->s_tables), "worker_pool_kernel");
+    if (b->launched && b->table_set == target) { CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait route"); b->launched = false; }
+  const HostTables& t = e->host->tables();
+  const size_t bytes = (size_t)t.n_slots * sizeof(Load16);
+  if (dev_loads) {
+    // order after the producer (e.g. the NCCL all-gather stream), then copy on the tables stream
+    CK(cudaEventRecord(e->ev_prod, producer), "event record");
+    CK(cudaStreamWaitEvent(e->s_tables, e->ev_prod, 0), "wait producer");
+    if (bytes) CK(cudaMemcpyAsync(D.loads.p, dev_loads, bytes, cudaMemcpyDeviceToDevice, e->s_tables), "D2D loads");
+    // later work on the producer stream (e.g. the next all-gather into the same buffer) must not overtake the copy
+    CK(cudaEventRecord(e->ev_copy, e->s_tables), "event record");
+    CK(cudaStreamWaitEvent(producer, e->ev_copy, 0), "order producer after copy");
+    e->host_loads = false;
+  } else if (bytes) {
+    CK(cudaMemcpyAsync(D.loads.p, t.loads.data(), bytes, cudaMemcpyHostToDevice, e->s_tables), "H2D loads");
+  }
+  CK(launch_worker_pools(view(e, target), e->s_tables), "worker_pool_kernel");
   if (e->dt.n_pools) e->launches++;
-  CK(cudaEventRecord(e->ev_tables, e->s_tables), "event record");
+  CK(cudaEventRecord(D.ready, e->s_tables), "event record");
+  e->cur = target;
   e->pools_dirty = false;
   return CORDUM_OK;
 }
@@ -262,14 +297,19 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   if (!copy_in && !b->resident) { g_err = "batch columns are not resident on the device"; return CORDUM_E_STATE; }
   if (b->pending) { CK(cudaStreamSynchronize(b->stream), "wait previous"); b->pending = false; }
   CK(cudaSetDevice(e->device), "cudaSetDevice");
+  KParams P;
+  cudaEvent_t ev_ready = nullptr;
   {
     std::lock_guard<std::mutex> g(e->mu);
     std::lock_guard<std::mutex> gh(e->host->mutex());
     if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
     int rc = sync_tables(e);
     if (rc) return rc;
-    rc = refresh_pools(e);
+    rc = refresh_pools(e, nullptr, nullptr);
     if (rc) return rc;
+    P.t = view(e, e->cur);
+    b->table_set = e->cur;
+    ev_ready = e->ds[e->cur].ready;
   }
   cudaStream_t s = b->stream;
   if (flush_l2) {   // evict the job columns from L2 between timed iterations (outside the timed region)
@@ -282,12 +322,15 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     b->resident = true;
   }
   CK(cudaEventRecord(b->ev1, s), "event");
-  KParams P;
   device_columns(b->d_cols, b->n, P.cols);
-  P.t = e->dt;
   P.out = b->d_out;
   P.n_jobs = b->n;
   P.honor_approved = mode == CORDUM_MODE_POLICY_AND_ROUTE ? 1u : 0u;
+  P.route_count = nullptr; P.route_list = nullptr;
+  if (mode == CORDUM_MODE_POLICY_AND_ROUTE) {   // policy_kernel compacts the dispatchable jobs for route_kernel
+    P.route_count = b->d_route; P.route_list = b->d_route + 4;
+    CK(cudaMemsetAsync(b->d_route, 0, sizeof(uint32_t), s), "reset route count");
+  }
   // policy_kernel needs no worker state: it is NOT ordered after the heartbeat exchange / worker_pool_kernel
   if (mode != CORDUM_MODE_ROUTE_ONLY) {
     CK(launch_policy(P, e->sm_count, s), "policy_kernel");
@@ -295,7 +338,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   }
   CK(cudaEventRecord(b->evm, s), "event");
   if (mode != CORDUM_MODE_POLICY_ONLY) {
-    CK(cudaStreamWaitEvent(s, e->ev_tables, 0), "wait worker tables");
+    CK(cudaStreamWaitEvent(s, ev_ready, 0), "wait worker tables");
     CK(launch_route(P, mode == CORDUM_MODE_ROUTE_ONLY, e->sm_count, s), "route_kernel");
     if (b->n) e->launches++;
   }
@@ -343,6 +386,7 @@ static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resourc
   if (b->d_cols) cudaFree(b->d_cols);
   if (b->h_out) cudaFreeHost(b->h_out);
   if (b->d_out) cudaFree(b->d_out);
+  if (b->d_route) cudaFree(b->d_route);
   for (cudaEvent_t ev : {b->ev0, b->ev1, b->evm, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -376,9 +420,12 @@ int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out
     CK(cudaGetDeviceProperties(&prop, e->device), "device properties");
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->s_tables, cudaStreamNonBlocking), "stream");
-    CK(cudaEventCreateWithFlags(&e->ev_tables, cudaEventDisableTiming), "event");
+    for (auto& D : e->ds) {
+      CK(cudaEventCreateWithFlags(&D.ready, cudaEventDisableTiming), "event");
+      CK(cudaEventRecord(D.ready, e->s_tables), "event");
+    }
     CK(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming), "event");
-    CK(cudaEventRecord(e->ev_tables, e->s_tables), "event");
+    CK(cudaEventCreateWithFlags(&e->ev_prod, cudaEventDisableTiming), "event");
   }
   e->host = std::make_unique<Host>(opts ? opts->max_topics : 0, opts ? opts->max_effcfgs : 0, opts ? opts->encode_threads : 0);
   *out = e.release();
@@ -399,11 +446,14 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule, &e->b_tw_off, &e->b_tw_cnt, &e->b_tw_list,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
-                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_loads, &e->b_pos_key, &e->b_pool_best, &e->b_pool_mincnt,
-                   &e->b_flush, &e->b_skey, &e->b_slab_lo, &e->b_slab_hi, &e->b_pool_sorted, &e->b_pool_nok, &e->b_lbm, &e->b_lbm_off, &e->b_rank_pos};
+                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos};
   for (DevBuf* b : all) b->release();
-  if (e->ev_tables) cudaEventDestroy(e->ev_tables);
+  for (auto& D : e->ds) {
+    for (DevBuf* b : {&D.loads, &D.pos_key, &D.skey, &D.slab_lo, &D.slab_hi, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
+    if (D.ready) cudaEventDestroy(D.ready);
+  }
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+  if (e->ev_prod) cudaEventDestroy(e->ev_prod);
   if (e->s_tables) cudaStreamDestroy(e->s_tables);
   delete e;
 }
@@ -442,7 +492,6 @@ int32_t cordum_workers_load(cordum_engine* e, const cordum_workers* w) {
 int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slots, const cordum_worker_load* loads) {
   if (!e || (n && (!slots || !loads))) { g_err = "null argument"; return CORDUM_E_INVALID; }
   int rc = e->host->update_loads(n, slots, loads, g_err);
-  if (rc == CORDUM_OK) { std::lock_guard<std::mutex> g(e->mu); e->loads_on_device = false; }
   return rc;
 }
 
@@ -455,21 +504,7 @@ int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   int rc = sync_tables(e);
   if (rc) return rc;
-  // order after the producer (e.g. the NCCL all-gather stream), then copy on the tables stream
-  cudaEvent_t ev;
-  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-  CK(cudaEventRecord(ev, (cudaStream_t)stream), "event record");
-  CK(cudaStreamWaitEvent(e->s_tables, ev, 0), "wait producer");
-  cudaEventDestroy(ev);
-  CK(e->b_loads.reserve((size_t)std::max<uint32_t>(n_workers, 1) * sizeof(Load16)), "alloc loads");
-  CK(cudaMemcpyAsync(e->b_loads.p, dptr, (size_t)n_workers * sizeof(Load16), cudaMemcpyDeviceToDevice, e->s_tables), "D2D loads");
-  // later work on the producer stream (e.g. the next all-gather into the same buffer) must not overtake the copy
-  CK(cudaEventRecord(e->ev_copy, e->s_tables), "event record");
-  CK(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_copy, 0), "order producer after copy");
-  e->dt.loads = (const Load16*)e->b_loads.p;
-  e->loads_on_device = true;
-  e->pools_dirty = true;
-  return refresh_pools(e);
+  return refresh_pools(e, dptr, (cudaStream_t)stream);
 }
 
 int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out) {
@@ -484,6 +519,7 @@ int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** o
   CK(cudaMalloc((void**)&b->d_cols, bytes), "device columns");
   CK(cudaHostAlloc((void**)&b->h_out, (size_t)max_jobs * sizeof(cordum_decision), cudaHostAllocDefault), "pinned results");
   CK(cudaMalloc((void**)&b->d_out, (size_t)max_jobs * sizeof(cordum_decision)), "device results");
+  CK(cudaMalloc((void**)&b->d_route, ((size_t)max_jobs + 4) * sizeof(uint32_t)), "device route list");
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
   CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event"); CK(cudaEventCreate(&b->evm), "event");
   CK(cudaEventCreate(&b->ev2), "event"); CK(cudaEventCreate(&b->ev3), "event");

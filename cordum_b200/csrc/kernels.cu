@@ -348,203 +348,229 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
       const uint32_t head = dec | (sched << 8) | (rflags << 16);
       reinterpret_cast<uint4*>(P.out)[j] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, 0xFFFFFFFFu);
     }
+    if (P.route_list) {   // compact the jobs that may dispatch (engine.go:298-347): one atomic per tile
+      const bool dr = valid && (sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS);
+      const unsigned m = __ballot_sync(FULL, dr);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(P.route_count, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (dr) P.route_list[base + __popc(m & ((1u << lane) - 1u))] = j;
+      }
+    }
   }
 }
 
 
 // ------------------------------------------------------------------ route: pool filter + least-loaded pick
-// Reads the decision record policy_kernel wrote (or nothing in ROUTE_ONLY mode) and routes the jobs that
-// may dispatch (engine.go:298-347).
+// Works on the compacted list of jobs that may dispatch (written by policy_kernel; in ROUTE_ONLY mode: all jobs).
 //   D  topic->pools, preferred_pool, requires filter, preferred_worker_id and, for label-free jobs, the
 //      merge of per-pool best keys: thread per job.
-//   S  only for jobs with placement labels: warp per job, AND of the pool's label bitmaps over its
-//      load-sorted view (lane = 32 workers); first set bit in the non-overloaded prefix = argmin.
+//   S  jobs with placement labels: 4 jobs per warp step, 8 lanes each.  For every eligible pool the group ANDs the
+//      pool's label bitmaps over its load-sorted view (lane = 32 workers); first set bit in the non-overloaded
+//      prefix = argmin, the next match decides the tie flag, popcount = candidate total.
+//   S' jobs that touch a pool larger than K2's sort buffer: warp per job, coalesced scan (rare).
 template <bool ROUTE_ONLY>
 __global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
-  const unsigned lane = threadIdx.x & 31;
-  const uint32_t n_tiles = (P.n_jobs + 31u) >> 5;
+  const unsigned lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  const uint32_t n_items = ROUTE_ONLY ? P.n_jobs : *P.route_count;
+  const uint32_t n_tiles = (n_items + 31u) >> 5;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
   for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
-    const uint32_t j = tile * 32 + lane;
-    const bool valid = j < P.n_jobs;
+    const uint32_t item = tile * 32 + lane;
+    const bool valid = item < n_items;
+    const uint32_t j = valid ? (ROUTE_ONLY ? item : P.route_list[item]) : 0u;
     uint4 rec = make_uint4(0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu);
     uint32_t c_flags = 0, c_topic = 0, c_ppool = 0, c_pwork = 0;
     uint64_t c_req = 0, c_plo = 0, c_phi = 0;
-    bool do_route = false;
     if (valid) {
       if (!ROUTE_ONLY) rec = reinterpret_cast<const uint4*>(P.out)[j];
-      const uint32_t sched = (rec.x >> 8) & 0xFFu;
-      do_route = ROUTE_ONLY || sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;   // engine.go:298-347
-      if (do_route) {
-        c_flags = ld_stream_u32(C.flags + j); c_topic = ld_stream_u32(C.topic + j);
-        c_ppool = ld_stream_u32(C.pref_pool + j); c_pwork = ld_stream_u32(C.pref_worker + j);
-        c_req = ld_stream_u64(C.req_mask + j); c_plo = ld_stream_u64(C.place_lo + j); c_phi = ld_stream_u64(C.place_hi + j);
-      }
+      c_flags = __ldg(C.flags + j); c_topic = __ldg(C.topic + j);
+      c_ppool = __ldg(C.pref_pool + j); c_pwork = __ldg(C.pref_worker + j);
+      c_req = __ldg(C.req_mask + j); c_plo = __ldg(C.place_lo + j); c_phi = __ldg(C.place_hi + j);
     }
     uint32_t rflags = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
     int slot = -1;
 
-    // =================================================================== D (cont.): pool filter, thread per job
-    bool need_scan = false;
+    // =================================================================== D: pool filter, thread per job
+    bool need_scan = false, slow = false;
     uint32_t r_off = 0, r_cnt = 0;
     int r_single = -1;
     uint64_t best = KEY_NONE;
     uint32_t bcnt = 0, total = 0;
-    {
-      if (do_route) {
-        if (c_flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
-        else {
-          r_off = __ldg(T.topic_pool_off + c_topic);
-          r_cnt = __ldg(T.topic_pool_cnt + c_topic);
-          if (c_ppool) {                                                         // preferred_pool (:50-55)
-            bool found = false;
-            if (c_ppool != CORDUM_PREF_UNKNOWN)
-              for (uint32_t k = 0; k < r_cnt; ++k) found |= __ldg(T.pool_list + r_off + k) == c_ppool - 1;
-            if (!found) route = CORDUM_ROUTE_NO_POOL_PREFERRED;
-            else { r_single = (int)(c_ppool - 1); r_cnt = 1; }
-          }
-          if (route == CORDUM_ROUTE_NOT_ATTEMPTED && r_cnt == 0) route = CORDUM_ROUTE_NO_POOL_TOPIC;   // :56-58
-          if (route == CORDUM_ROUTE_NOT_ATTEMPTED) {
-            const bool req_any = c_flags & JF_REQ_NONEMPTY, req_unknown = c_flags & JF_REQ_UNKNOWN;
-            const uint64_t need_req = c_req & ~T.req_blank_mask;
-            const bool unsat = c_flags & JF_PLACE_UNSAT;
-            const bool labelled = (c_plo | c_phi) != 0 || unsat;
-            int pw_pos = -1;
-            uint32_t pw_pool = 0xFFFFFFFFu;
-            if (c_pwork && c_pwork != CORDUM_PREF_UNKNOWN) {
-              uint32_t p1 = __ldg(T.slot_pos + (c_pwork - 1));
-              if (p1) { pw_pos = (int)p1 - 1; pw_pool = __ldg(T.pos_pool + pw_pos); }
-            }
-            uint32_t n_elig = 0;
-            bool pw_in_set = false;
-            for (uint32_t k = 0; k < r_cnt; ++k) {
-              const uint32_t pid = r_single >= 0 ? (uint32_t)r_single : __ldg(T.pool_list + r_off + k);
-              // poolSatisfies (:241-265)
-              if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
-              n_elig++;
-              pw_in_set |= pid == pw_pool;
-              if (!labelled) {
-                total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
-                merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
-              }
-            }
-            if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;              // :64-66
-            else {
-              bool took_pref = false;
-              if (pw_pos >= 0 && pw_in_set && !unsat) {                           // :73-87
-                uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
-                if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && !key_over(T.pos_key[pw_pos])) {
-                  took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
-                }
-              }
-              if (!took_pref) need_scan = labelled && !unsat;   // label-free and unsatisfiable jobs are final already
-              if (!took_pref && !need_scan) {
-                if (best != KEY_NONE) {
-                  route = CORDUM_ROUTE_OK;
-                  slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
-                  if (bcnt > 1) rflags |= CORDUM_F_TIE;
-                } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;   // :114-119
-              }
-            }
-          }
+    if (valid) {
+      if (c_flags & JF_TOPIC_RAW_EMPTY) route = CORDUM_ROUTE_MISSING_TOPIC;   // :41-43
+      else {
+        r_off = __ldg(T.topic_pool_off + c_topic);
+        r_cnt = __ldg(T.topic_pool_cnt + c_topic);
+        if (c_ppool) {                                                         // preferred_pool (:50-55)
+          bool found = false;
+          if (c_ppool != CORDUM_PREF_UNKNOWN)
+            for (uint32_t k = 0; k < r_cnt; ++k) found |= __ldg(T.pool_list + r_off + k) == c_ppool - 1;
+          if (!found) route = CORDUM_ROUTE_NO_POOL_PREFERRED;
+          else { r_single = (int)(c_ppool - 1); r_cnt = 1; }
         }
-      }
-      // ================================================================= S: placement-label scans, warp per job
-      for (unsigned todo = __ballot_sync(FULL, need_scan); todo; todo &= todo - 1) {
-        const int i = __ffs(todo) - 1;
-        const uint32_t off = __shfl_sync(FULL, r_off, i), cnt = __shfl_sync(FULL, r_cnt, i), fl = __shfl_sync(FULL, c_flags, i);
-        const int single = __shfl_sync(FULL, r_single, i);
-        const uint64_t need_req = shfl64(FULL, c_req, i) & ~T.req_blank_mask;
-        const uint64_t need_lo = shfl64(FULL, c_plo, i), need_hi = shfl64(FULL, c_phi, i);
-        const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
-        uint64_t b = KEY_NONE;
-        uint32_t bc = 0, tot = 0;
-        // pass 1: each eligible pool is walked in load order; the first label match is that pool's argmin
-        for (uint32_t k = 0; k < cnt; ++k) {
-          const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
-          if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
-          const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
-          if (!T.pool_sorted[pid]) {   // pool larger than K2's sort buffer: unordered scan
-            uint64_t pb = KEY_NONE; uint32_t pc = 0;
-            for (uint32_t pos = a + lane; pos < e; pos += 32) {
-              const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
-              if ((llo & need_lo) == need_lo && (lhi & need_hi) == need_hi) merge_best(pb, pc, T.pos_key[pos], 1);
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) { const uint64_t k2 = shfl64_xor(FULL, pb, o); const uint32_t c2 = __shfl_xor_sync(FULL, pc, o); merge_best(pb, pc, k2, c2); }
-            merge_best(b, bc, pb, pc);
-            continue;
+        if (route == CORDUM_ROUTE_NOT_ATTEMPTED && r_cnt == 0) route = CORDUM_ROUTE_NO_POOL_TOPIC;   // :56-58
+        if (route == CORDUM_ROUTE_NOT_ATTEMPTED) {
+          const bool req_any = c_flags & JF_REQ_NONEMPTY, req_unknown = c_flags & JF_REQ_UNKNOWN;
+          const uint64_t need_req = c_req & ~T.req_blank_mask;
+          const bool unsat = c_flags & JF_PLACE_UNSAT;
+          const bool labelled = (c_plo | c_phi) != 0 || unsat;
+          int pw_pos = -1;
+          uint32_t pw_pool = 0xFFFFFFFFu;
+          if (c_pwork && c_pwork != CORDUM_PREF_UNKNOWN) {
+            uint32_t p1 = __ldg(T.slot_pos + (c_pwork - 1));
+            if (p1) { pw_pos = (int)p1 - 1; pw_pool = __ldg(T.pos_pool + pw_pos); }
           }
-          // sorted pool: AND the bitmaps of the required label bits (lane = 32 sorted workers).  The first set
-          // bit among the non-overloaded prefix is the pool's least-loaded label match (matchesLabels, :161-175).
-          uint64_t kstar = KEY_NONE;
-          uint32_t kc = 0;
-          bool tie_done = false;
-          const uint32_t words = (e - a + 31) >> 5, nok = T.pool_nok[pid];
-          const uint32_t* bm = T.lbm + __ldg(T.lbm_off + pid);
-          for (uint32_t w0 = 0; w0 < words && !tie_done; w0 += 32) {
-            const uint32_t w = w0 + lane;
-            uint32_t v = 0;
-            if (w < words) {
-              v = 0xFFFFFFFFu;
-              for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(size_t)(__ffsll((long long)m) - 1) * words + w];
-              for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(size_t)(64 + __ffsll((long long)m) - 1) * words + w];
-            }
-            tot += __popc(v);                                     // label-matching candidates, overloaded ones included
-            const uint32_t lo = w * 32;
-            uint32_t okv = lo >= nok ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));   // non-overloaded prefix
-            while (!tie_done) {
-              const unsigned hit = __ballot_sync(FULL, okv != 0);
-              if (!hit) break;
-              const int L = __ffs(hit) - 1;
-              const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(__ffs(okv) - 1), L);
-              const uint64_t kk = T.skey[a + pos];
-              if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
-              else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; tie_done = true; }   // next match decides the tie flag
-              if ((int)lane == L) okv &= okv - 1;
-            }
-          }
-          merge_best(b, bc, kstar, kc);
-        }
-        // Nobody qualified: were there label-matching (overloaded) candidates at all?  (:114-119)
-        // Sorted pools already counted theirs above; unsorted pools need a counting scan.
-        if (b == KEY_NONE) {
-          for (uint32_t k = 0; k < cnt; ++k) {
-            const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
-            if (T.pool_sorted[pid]) continue;
+          uint32_t n_elig = 0;
+          bool pw_in_set = false;
+          for (uint32_t k = 0; k < r_cnt; ++k) {
+            const uint32_t pid = r_single >= 0 ? (uint32_t)r_single : __ldg(T.pool_list + r_off + k);
+            // poolSatisfies (:241-265)
             if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
-            const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
-            for (uint32_t pos = a + lane; pos < e; pos += 32) {
-              const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
-              tot += ((llo & need_lo) == need_lo && (lhi & need_hi) == need_hi) ? 1u : 0u;
+            n_elig++;
+            pw_in_set |= pid == pw_pool;
+            if (!labelled) {
+              total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
+              merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
+            } else slow |= T.pool_sorted[pid] == 0;
+          }
+          if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;              // :64-66
+          else {
+            bool took_pref = false;
+            if (pw_pos >= 0 && pw_in_set && !unsat) {                           // :73-87
+              uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
+              if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && !key_over(T.pos_key[pw_pos])) {
+                took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
+              }
+            }
+            if (!took_pref) need_scan = labelled && !unsat;   // label-free and unsatisfiable jobs are final already
+            if (!took_pref && !need_scan) {
+              if (best != KEY_NONE) {
+                route = CORDUM_ROUTE_OK;
+                slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
+                if (bcnt > 1) rflags |= CORDUM_F_TIE;
+              } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;   // :114-119
             }
           }
-#pragma unroll
-          for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
         }
-        if ((int)lane == i) { best = b; bcnt = bc; total = tot; }
-      }
-      if (need_scan) {
-        if (best != KEY_NONE) {
-          route = CORDUM_ROUTE_OK;
-          slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
-          if (bcnt > 1) rflags |= CORDUM_F_TIE;
-        } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;
       }
     }
 
-    if (valid && (ROUTE_ONLY || do_route)) {
+    // =================================================================== S: label picks, 4 jobs x 8 lanes per step
+    for (unsigned todo = __ballot_sync(FULL, need_scan && !slow); todo;) {
+      int own[4];   // the (up to) four jobs of this step: group q serves lane own[q]
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { own[q] = todo ? __ffs(todo) - 1 : -1; todo &= todo - 1; }
+      const int src = g == 0 ? own[0] : g == 1 ? own[1] : g == 2 ? own[2] : own[3];
+      const bool act = src >= 0;
+      const int s_ = act ? src : 0;
+      const uint32_t off = __shfl_sync(FULL, r_off, s_), fl = __shfl_sync(FULL, c_flags, s_);
+      const uint32_t cnt_all = __shfl_sync(FULL, r_cnt, s_);   // every lane takes part in every shuffle
+      const uint32_t cnt = act ? cnt_all : 0u;
+      const int single = __shfl_sync(FULL, r_single, s_);
+      const uint64_t need_req = shfl64(FULL, c_req, s_) & ~T.req_blank_mask;
+      const uint64_t need_lo = shfl64(FULL, c_plo, s_), need_hi = shfl64(FULL, c_phi, s_);
+      const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+      uint64_t b = KEY_NONE;
+      uint32_t bc = 0, tot = 0;
+      for (uint32_t k = 0; __any_sync(FULL, k < cnt); ++k) {
+        const bool kin = k < cnt;
+        const uint32_t pid = kin ? (single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k)) : 0u;
+        const bool elig = kin && (!req_any || (__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0));
+        const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
+        const uint32_t words = elig ? (e - a + 31) >> 5 : 0u, nok = T.pool_nok[pid];
+        const uint32_t* bm = T.lbm + __ldg(T.lbm_off + pid);
+        uint64_t kstar = KEY_NONE;
+        uint32_t kc = 0;
+        bool tie_done = false;
+        for (uint32_t w0 = 0; __any_sync(FULL, w0 < words && !tie_done); w0 += CORDUM_GROUP) {
+          const uint32_t w = w0 + sub;
+          uint32_t v = 0;
+          if (w < words && !tie_done) {   // matchesLabels (:161-175) for 32 load-sorted workers at once
+            v = 0xFFFFFFFFu;
+            for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(size_t)(__ffsll((long long)m) - 1) * words + w];
+            for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(size_t)(64 + __ffsll((long long)m) - 1) * words + w];
+          }
+          tot += __popc(v);                                     // label-matching candidates, overloaded ones included
+          const uint32_t lo = w * 32;
+          uint32_t okv = lo >= nok ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));   // non-overloaded prefix
+          while (true) {   // at most two rounds per group: the argmin, then the next match for the tie flag
+            const unsigned hit = __ballot_sync(FULL, okv != 0 && !tie_done);
+            if (!hit) break;
+            const unsigned gb = (hit >> (g * 8)) & 0xFFu;
+            const int L = (int)(g * 8) + (gb ? __ffs(gb) - 1 : 0);
+            const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(okv ? __ffs(okv) - 1 : 0), L);
+            if (gb) {
+              const uint64_t kk = T.skey[a + pos];
+              if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
+              else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; tie_done = true; }
+              if ((int)lane == L) okv &= okv - 1;
+            }
+          }
+        }
+        merge_best(b, bc, kstar, kc);
+      }
+      tot += __shfl_xor_sync(FULL, tot, 1);
+      tot += __shfl_xor_sync(FULL, tot, 2);
+      tot += __shfl_xor_sync(FULL, tot, 4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // hand each job's result to its owner lane
+        const uint64_t vb = shfl64(FULL, b, q * 8);
+        const uint32_t vc = __shfl_sync(FULL, bc, q * 8), vt = __shfl_sync(FULL, tot, q * 8);
+        if ((int)lane == own[q]) { best = vb; bcnt = vc; total = vt; }
+      }
+    }
+
+    // =================================================================== S': pools beyond the sort buffer, warp per job
+    for (unsigned todo = __ballot_sync(FULL, need_scan && slow); todo; todo &= todo - 1) {
+      const int i = __ffs(todo) - 1;
+      const uint32_t off = __shfl_sync(FULL, r_off, i), cnt = __shfl_sync(FULL, r_cnt, i), fl = __shfl_sync(FULL, c_flags, i);
+      const int single = __shfl_sync(FULL, r_single, i);
+      const uint64_t need_req = shfl64(FULL, c_req, i) & ~T.req_blank_mask;
+      const uint64_t need_lo = shfl64(FULL, c_plo, i), need_hi = shfl64(FULL, c_phi, i);
+      const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+      uint64_t b = KEY_NONE;
+      uint32_t bc = 0, tot = 0;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
+        if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+        const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
+        for (uint32_t pos = a + lane; pos < e; pos += 32) {   // matchesLabels (:161-175), coalesced
+          const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
+          if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
+          tot++;
+          merge_best(b, bc, T.pos_key[pos], 1);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const uint64_t k2 = shfl64_xor(FULL, b, o);
+        const uint32_t c2 = __shfl_xor_sync(FULL, bc, o);
+        merge_best(b, bc, k2, c2);
+        tot += __shfl_xor_sync(FULL, tot, o);
+      }
+      if ((int)lane == i) { best = b; bcnt = bc; total = tot; }
+    }
+
+    if (need_scan) {
+      if (best != KEY_NONE) {
+        route = CORDUM_ROUTE_OK;
+        slot = (int)__ldg(T.rank_slot + (uint32_t)(best & 0xFFFFFFFFu));
+        if (bcnt > 1) rflags |= CORDUM_F_TIE;
+      } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;
+    }
+    if (valid) {
       rec.x = (rec.x & 0x00FFFFFFu) | (rflags << 16) | (route << 24);   // rflags only adds CORDUM_F_TIE
       rec.w = (uint32_t)slot;
       reinterpret_cast<uint4*>(P.out)[j] = rec;
     }
   }
 }
-
 
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {

@@ -10,6 +10,8 @@ struct KParams {
   DeviceTables t;         // device pointers to the compiled tables
   cordum_decision* out;   // device, n_jobs records
   uint32_t n_jobs;
+  uint32_t* route_count;     // device: number of jobs policy_kernel found dispatchable (null: no compaction)
+  uint32_t* route_list;      // device: their job indices
   uint32_t honor_approved;   // POLICY_AND_ROUTE: jobs flagged JF_APPROVED bypass the policy (engine.go:484-522)
 };
 

@@ -120,6 +120,31 @@ def test_device_load_table_path(eng):
     b.free()
 
 
+def test_pool_larger_than_sort_buffer(eng):
+    """A pool beyond worker_pool_kernel's 8192-entry sort buffer takes the unordered-scan path (route_kernel S')."""
+    rng = np.random.default_rng(5)
+    n = 9000
+    workers = [kats.hb("w%05d" % i, "big" if i < 8800 else "small", int(rng.integers(0, 6)), float(rng.random() * 100),
+                       float(rng.random() * 100), int(rng.choice([0, 4, 8])),
+                       {"zone": "z%d" % rng.integers(0, 4), **({"gpu": "true"} if rng.random() < 0.3 else {})}) for i in range(n)]
+    routing = {"topics": {"job.a": ["big", "small"], "job.b": ["small"]}, "pools": {"big": {}, "small": {}}}
+    jobs = []
+    for i in range(400):
+        labels = {}
+        if i % 3 != 0:
+            labels["zone"] = "z%d" % (i % 5)       # z4 matches nobody
+        if i % 4 == 0:
+            labels["gpu"] = "true"
+        jobs.append({"topic": "job.a" if i % 5 else "job.b", "labels": labels})
+    load(eng, None, routing, workers)
+    b = eng.batch(len(jobs))
+    got = b.encode(jobs).dispatch(wire.MODE_ROUTE_ONLY)
+    want = oracle_lib.Oracle(None, routing, workers).eval(jobs, wire.MODE_ROUTE_ONLY)
+    assert_same(got, want, "big pool")
+    assert set(got["route_status"].tolist()) >= {wire.ROUTE_OK, wire.ROUTE_NO_WORKERS}
+    b.free()
+
+
 def test_c5_demo_guardrails_replay_100k(eng):
     c5 = kats.golden("c5_demo_guardrails.json")
     jobs, workers, kind = synth.make_c5(100_000)
