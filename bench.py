@@ -12,7 +12,7 @@ full rule / routing / worker tables.
 One step = one pass of the hot path over the rank's job shard:
     ingest the heartbeat load deltas of this rank's W/N worker slice (pinned host -> HBM)
     [N > 1]  one NCCL all-gather of the per-rank 16 B/worker load slices   
-    worker_pool_kernel   (load score / overload / per-pool argmin over the 64k workers)
+    worker_chunk_kernel + worker_merge_kernel   (load score / overload / per-pool argmin over the 64k workers)
     policy_kernel        (first-match over the rule set + decision mapping; overlaps the two lines above)
     route_kernel         (pool filter + least-loaded pick for the jobs that may dispatch)
 `value`  : job columns already resident in HBM; K steps bracketed by barrier + synchronize on
@@ -218,7 +218,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             buf = shard.gather_loads(send, out=recv[k % 2])                   # the one exchange step
         else:
             buf = send
-        eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)           # D2D + worker_pool_kernel
+        eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)           # D2D + worker_chunk_kernel + worker_merge_kernel
         if resident:
             batch.dispatch_resident_async(wire.MODE_POLICY_AND_ROUTE)
         else:
@@ -240,16 +240,25 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
+    # Device time: a CUDA event on the ingest stream before the first step and one after every batch stream has been
+    # joined into it (the kernels run on per-batch streams); the wall clock between the synchronizes is kept beside it.
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ext = [torch.cuda.ExternalStream(b.stream, device=torch.device("cuda", local_rank)) for b in batches]
     t0 = time.perf_counter()
+    ev_a.record(stream)
     for k in range(args.steps):
         step(args.warmup + k, batches[(args.warmup + k) % n_rot], True)
+    for x in ext:
+        stream.wait_stream(x)
+    ev_b.record(stream)
     sync_all()
-    elapsed = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    elapsed = ev_a.elapsed_time(ev_b) * 1e-3
     launches = eng.launch_count() - launches0
     if world > 1:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        t = torch.tensor([elapsed, wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
+        elapsed, wall = (float(x) for x in t.tolist())
     value = J * args.steps / elapsed
 
     # parity spot check inside the bench: the last resident run must equal the first copy run's records
@@ -259,10 +268,10 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
 
     # ---------------------------------------------------------------- per-kernel durations for the roofline
     # Serialized launches (wait after every step) so the CUDA-event span of a kernel contains that kernel only;
-    # in the throughput loop above policy_kernel overlaps the previous step's route_kernel / worker_pool_kernel.
+    # in the throughput loop above policy_kernel overlaps the previous step's route_kernel / worker_chunk_kernel + worker_merge_kernel.
     pol_ms, rte_ms = [], []
     step(0, batches[0], True)          # one more heartbeat epoch, then hold the worker tables still so that
-    sync_all()                         # route_kernel's event span does not contain a wait for worker_pool_kernel
+    sync_all()                         # route_kernel's event span does not contain a wait for worker_chunk_kernel + worker_merge_kernel
     for k in range(max(8, min(args.steps, 16))):
         b = batches[k % n_rot]
         b.dispatch_resident(wire.MODE_POLICY_AND_ROUTE)
@@ -333,11 +342,13 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 bitmask + f32 score", "data": "synthetic",
+        "timing": {"clock": "CUDA events (first ingest -> all batch streams joined), max over ranks",
+                   "wall_ms_per_step": 1000.0 * wall / args.steps},
         "config": {"workload": "c3: 1,000,000 jobs x 4096 rules x 65536 workers (seed 3), policy+route",
                    "jobs_per_rank": n_shard, "parallelism": "jobs sharded by index x%d, tables replicated" % world,
                    "l2": "inputs larger than L2: steps rotate over %d resident copies of the shard (%.0f MB total)" % (
                        n_rot, n_rot * shard_bytes / 1e6),
-                   "step": "heartbeat-slice H2D + %sworker_pool_kernel (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else "")},
+                   "step": "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(n_shard * in_b + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),

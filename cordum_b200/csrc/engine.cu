@@ -57,6 +57,8 @@ inline size_t slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) 
 }  // namespace
 
 struct cordum_batch;
+constexpr int kSets = 3;
+
 struct cordum_engine {
   int device = 0;
   int sm_count = 148;
@@ -64,7 +66,7 @@ struct cordum_engine {
   std::mutex mu;                 // serialises table sync
   bool failed = false;           // sticky CUDA failure
   std::string fail_msg;
-  cudaStream_t s_tables = nullptr;
+  cudaStream_t s_tables = nullptr, s_copy = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_prod = nullptr;
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
@@ -72,13 +74,14 @@ struct cordum_engine {
   DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule, b_tw_off, b_tw_cnt, b_tw_list;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi;
-  DevBuf b_flush, b_lbm_off, b_rank_pos;
-  // Everything worker_pool_kernel derives from the loads, in TWO copies: the refresh for heartbeat epoch k+1 writes
-  // one set while route kernels of epoch k still read the other, so consecutive steps pipeline instead of serialising.
+  DevBuf b_flush, b_lbm_off, b_rank_pos, b_chunk_pool, b_pool_chunk0, b_merge_list;
+  // Everything the worker-table refresh kernels derive from the loads, in kSets copies used round-robin: the refresh
+  // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
+  // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
   struct DerivedSet {
-    DevBuf loads, pos_key, skey, slab_lo, slab_hi, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
-    cudaEvent_t ready = nullptr;
-  } ds[2];
+    DevBuf loads, pos_key, ckey, skey, slab_lo, slab_hi, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
+    cudaEvent_t ready = nullptr, loads_read = nullptr;   // refresh complete / load table consumed by the refresh
+  } ds[kSets];
   int cur = 0;                   // set holding the latest refresh
   bool host_loads = true;        // the next refresh takes the loads from the host tables
   uint64_t v_policy = ~0ull, v_topic = ~0ull, v_mcp = ~0ull, v_routing = ~0ull, v_workers = ~0ull, v_loads = ~0ull;
@@ -91,7 +94,7 @@ struct cordum_batch {
   cordum_engine* e = nullptr;
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
-  bool encoded = false, resident = false, pending = false, launched = false;
+  bool encoded = false, resident = false, pending = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned
   uint8_t* d_cols = nullptr;
@@ -209,6 +212,7 @@ int sync_tables(cordum_engine* e) {
       CK(D.pool_best.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 8), "alloc");
       CK(D.pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
       CK(D.skey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
+      CK(D.ckey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.slab_lo.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.slab_hi.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
@@ -216,14 +220,11 @@ int sync_tables(cordum_engine* e) {
       CK(D.lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
       CK(D.loads.reserve((size_t)std::max<uint32_t>(t.n_slots, 1) * sizeof(Load16)), "alloc");
     }
-    {
-      // K2 sort buffer: next power of two >= the largest pool, capped at 8192 entries (96 KiB of shared memory)
-      uint32_t largest = 1;
-      for (uint32_t p = 0; p < t.n_pools; ++p) largest = std::max(largest, t.pool_off[p + 1] - t.pool_off[p]);
-      uint32_t cap = 32;
-      while (cap < largest && cap < 8192) cap <<= 1;
-      d.sort_cap = cap;
-    }
+    CK(up(e->b_chunk_pool, t.chunk_pool, s), "upload"); CK(up(e->b_pool_chunk0, t.pool_chunk0, s), "upload");
+    CK(up(e->b_merge_list, t.merge_list, s), "upload");
+    d.chunk_pool = (const uint32_t*)e->b_chunk_pool.p; d.pool_chunk0 = (const uint32_t*)e->b_pool_chunk0.p;
+    d.merge_list = (const uint32_t*)e->b_merge_list.p;
+    d.n_chunks = t.n_chunks; d.n_merge = t.n_merge; d.merge_smem = t.merge_smem;
     CK(up(e->b_lbm_off, t.lbm_off, s), "upload");
     d.lbm_off = (const uint32_t*)e->b_lbm_off.p;
     d.place_bits = t.place_bits;
@@ -250,37 +251,41 @@ DeviceTables view(const cordum_engine* e, int set) {
   DeviceTables d = e->dt;
   const auto& D = e->ds[set];
   d.loads = (const Load16*)D.loads.p;
-  d.pos_key = (uint64_t*)D.pos_key.p; d.skey = (uint64_t*)D.skey.p; d.slab_lo = (uint64_t*)D.slab_lo.p; d.slab_hi = (uint64_t*)D.slab_hi.p;
+  d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p; d.slab_lo = (uint64_t*)D.slab_lo.p; d.slab_hi = (uint64_t*)D.slab_hi.p;
   d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.lbm = (uint32_t*)D.lbm.p;
   d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
   return d;
 }
 
-// worker_pool_kernel for a new heartbeat epoch, into the set that is NOT being read.  dev_loads: the full slot-ordered
+// worker-table refresh kernels for a new heartbeat epoch, into the set that is NOT being read.  dev_loads: the full slot-ordered
 // load table already in HBM (produced on `producer`), or null to take the host tables' loads.  Called with both mutexes held.
 int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer) {
   if (!e->pools_dirty && !dev_loads) return CORDUM_OK;
-  const int target = e->cur ^ 1;
+  const int target = (e->cur + 1) % kSets;
   auto& D = e->ds[target];
-  // route kernels that still read the target set (launched two epochs ago) must have finished
+  // route kernels that still read the target set (launched kSets-1 epochs ago) must have finished
   for (cordum_batch* b : e->batches)
     if (b->launched && b->table_set == target) { CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait route"); b->launched = false; }
   const HostTables& t = e->host->tables();
   const size_t bytes = (size_t)t.n_slots * sizeof(Load16);
   if (dev_loads) {
-    // order after the producer (e.g. the NCCL all-gather stream), then copy on the tables stream
+    // The gathered table is copied on its own stream, ordered after the producer (e.g. the NCCL all-gather stream) and
+    // after the last refresh that read this set's copy - NOT after the refresh in flight on the tables stream - so the
+    // refresh kernels of epoch k+1 sit directly behind those of epoch k and start ahead of epoch k's route kernel.
     CK(cudaEventRecord(e->ev_prod, producer), "event record");
-    CK(cudaStreamWaitEvent(e->s_tables, e->ev_prod, 0), "wait producer");
-    if (bytes) CK(cudaMemcpyAsync(D.loads.p, dev_loads, bytes, cudaMemcpyDeviceToDevice, e->s_tables), "D2D loads");
+    CK(cudaStreamWaitEvent(e->s_copy, e->ev_prod, 0), "wait producer");
+    CK(cudaStreamWaitEvent(e->s_copy, D.loads_read, 0), "wait previous readers");
+    if (bytes) CK(cudaMemcpyAsync(D.loads.p, dev_loads, bytes, cudaMemcpyDeviceToDevice, e->s_copy), "D2D loads");
     // later work on the producer stream (e.g. the next all-gather into the same buffer) must not overtake the copy
-    CK(cudaEventRecord(e->ev_copy, e->s_tables), "event record");
+    CK(cudaEventRecord(e->ev_copy, e->s_copy), "event record");
     CK(cudaStreamWaitEvent(producer, e->ev_copy, 0), "order producer after copy");
+    CK(cudaStreamWaitEvent(e->s_tables, e->ev_copy, 0), "order refresh after copy");
     e->host_loads = false;
   } else if (bytes) {
     CK(cudaMemcpyAsync(D.loads.p, t.loads.data(), bytes, cudaMemcpyHostToDevice, e->s_tables), "H2D loads");
   }
-  CK(launch_worker_pools(view(e, target), e->s_tables), "worker_pool_kernel");
-  if (e->dt.n_pools) e->launches++;
+  CK(launch_worker_pools(view(e, target), e->s_tables, D.loads_read), "worker-table refresh kernels");
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
   CK(cudaEventRecord(D.ready, e->s_tables), "event record");
   e->cur = target;
   e->pools_dirty = false;
@@ -316,8 +321,10 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     if (!e->b_flush.p) CK(e->b_flush.reserve(size_t(256) << 20), "alloc flush buffer");
     CK(cudaMemsetAsync(e->b_flush.p, 0, e->b_flush.cap, s), "flush");
   }
-  CK(cudaEventRecord(b->ev0, s), "event");
+  // timing events: a resident run has no copies, so its span is [ev1, ev2] and ev0 / ev3 are not recorded
+  b->timed_in = copy_in; b->timed_out = copy_out;
   if (copy_in) {
+    CK(cudaEventRecord(b->ev0, s), "event");
     CK(cudaMemcpyAsync(b->d_cols, b->h_cols, slab_bytes(b->n), cudaMemcpyHostToDevice, s), "H2D columns");
     b->resident = true;
   }
@@ -331,7 +338,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     P.route_count = b->d_route; P.route_list = b->d_route + 4;
     CK(cudaMemsetAsync(b->d_route, 0, sizeof(uint32_t), s), "reset route count");
   }
-  // policy_kernel needs no worker state: it is NOT ordered after the heartbeat exchange / worker_pool_kernel
+  // policy_kernel needs no worker state: it is NOT ordered after the heartbeat exchange / worker-table refresh kernels
   if (mode != CORDUM_MODE_ROUTE_ONLY) {
     CK(launch_policy(P, e->sm_count, s), "policy_kernel");
     if (b->n) e->launches++;
@@ -344,8 +351,10 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   }
   CK(cudaEventRecord(b->ev2, s), "event");
   b->launched = true;
-  if (copy_out) CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, s), "D2H results");
-  CK(cudaEventRecord(b->ev3, s), "event");
+  if (copy_out) {
+    CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * sizeof(cordum_decision), cudaMemcpyDeviceToHost, s), "D2H results");
+    CK(cudaEventRecord(b->ev3, s), "event");
+  }
   b->pending = true;
   return CORDUM_OK;
 }
@@ -355,7 +364,7 @@ int wait(cordum_batch* b) {
   if (!b->pending) return CORDUM_OK;
   CK(cudaStreamSynchronize(b->stream), "batch wait");
   b->pending = false;
-  CK(cudaEventElapsedTime(&b->total_ms, b->ev0, b->ev3), "elapsed");
+  CK(cudaEventElapsedTime(&b->total_ms, b->timed_in ? b->ev0 : b->ev1, b->timed_out ? b->ev3 : b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->kernel_ms, b->ev1, b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->policy_ms, b->ev1, b->evm), "elapsed");
   CK(cudaEventElapsedTime(&b->route_ms, b->evm, b->ev2), "elapsed");
@@ -419,10 +428,19 @@ int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, e->device), "device properties");
     e->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&e->s_tables, cudaStreamNonBlocking), "stream");
+    {
+      // the worker-table refresh is the head of every step's dependency chain (route kernels wait for it): its CTAs go
+      // ahead of queued policy / route CTAs
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range");
+      CK(cudaStreamCreateWithPriority(&e->s_tables, cudaStreamNonBlocking, hi), "stream");
+      CK(cudaStreamCreateWithPriority(&e->s_copy, cudaStreamNonBlocking, hi), "stream");
+    }
     for (auto& D : e->ds) {
       CK(cudaEventCreateWithFlags(&D.ready, cudaEventDisableTiming), "event");
       CK(cudaEventRecord(D.ready, e->s_tables), "event");
+      CK(cudaEventCreateWithFlags(&D.loads_read, cudaEventDisableTiming), "event");
+      CK(cudaEventRecord(D.loads_read, e->s_tables), "event");
     }
     CK(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming), "event");
     CK(cudaEventCreateWithFlags(&e->ev_prod, cudaEventDisableTiming), "event");
@@ -446,15 +464,18 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule, &e->b_tw_off, &e->b_tw_cnt, &e->b_tw_list,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
-                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos};
+                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos,
+                   &e->b_chunk_pool, &e->b_pool_chunk0, &e->b_merge_list};
   for (DevBuf* b : all) b->release();
   for (auto& D : e->ds) {
-    for (DevBuf* b : {&D.loads, &D.pos_key, &D.skey, &D.slab_lo, &D.slab_hi, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
+    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.slab_lo, &D.slab_hi, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
     if (D.ready) cudaEventDestroy(D.ready);
+    if (D.loads_read) cudaEventDestroy(D.loads_read);
   }
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->ev_prod) cudaEventDestroy(e->ev_prod);
   if (e->s_tables) cudaStreamDestroy(e->s_tables);
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
   delete e;
 }
 

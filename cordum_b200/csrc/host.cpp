@@ -1041,7 +1041,7 @@ int Host::compile_workers(std::string& err) {
     t.pos_label_lo[i] = m[0]; t.pos_label_hi[i] = m[1];
   }
   for (uint32_t p = 0; p < t.n_pools; ++p) t.pool_off[p + 1] += t.pool_off[p];
-  // per-pool label bitmaps (filled on the device by worker_pool_kernel): place_bits rows of ceil(n/32) words
+  // per-pool label bitmaps (filled on the device by worker-table refresh kernels): place_bits rows of ceil(n/32) words
   t.place_bits = std::max<uint32_t>(place_bits_, 1);
   t.lbm_off.assign(std::max<uint32_t>(t.n_pools, 1), 0);
   t.lbm_words = 0;
@@ -1049,6 +1049,27 @@ int Host::compile_workers(std::string& err) {
     t.lbm_off[p] = (uint32_t)t.lbm_words;
     t.lbm_words += (uint64_t)t.place_bits * ((t.pool_off[p + 1] - t.pool_off[p] + 31) / 32);
   }
+  // refresh work list: chunks of CORDUM_POOL_CHUNK workers (an empty pool still owns one, empty, chunk)
+  t.chunk_pool.clear(); t.merge_list.clear();
+  t.pool_chunk0.assign(t.n_pools + 1, 0);
+  t.merge_smem = 0;
+  for (uint32_t p = 0; p < t.n_pools; ++p) {
+    const uint32_t n = t.pool_off[p + 1] - t.pool_off[p];
+    const uint32_t m = std::max<uint32_t>(1, (n + CORDUM_POOL_CHUNK - 1) / CORDUM_POOL_CHUNK);
+    const uint32_t g0 = (uint32_t)t.chunk_pool.size();
+    t.pool_chunk0[p] = g0;
+    for (uint32_t c = 0; c < m; ++c) t.chunk_pool.push_back(p);
+    if (n > CORDUM_POOL_SORT_MAX) t.merge_list.push_back(g0);
+    else if (m > 1) {
+      for (uint32_t c = 0; c < m; ++c) t.merge_list.push_back(g0 + c);
+      t.merge_smem = std::max<uint32_t>(t.merge_smem, n * 8u);
+    }
+  }
+  t.pool_chunk0[t.n_pools] = (uint32_t)t.chunk_pool.size();
+  t.n_chunks = (uint32_t)t.chunk_pool.size();
+  t.n_merge = (uint32_t)t.merge_list.size();
+  if (t.chunk_pool.empty()) t.chunk_pool.push_back(0);
+  if (t.merge_list.empty()) t.merge_list.push_back(0);
   if (t.loads.empty()) t.loads.push_back(Load16{0, 0, 0.f, 0.f});
   t.v_workers++;
   t.v_loads++;

@@ -1,6 +1,6 @@
 // kernels.cu — sm_100a kernels of the policy-gate + dispatch path.
 //
-//   worker_pool_kernel   per heartbeat epoch: load score / overload per worker (strategy_least_loaded.go:157-159,
+//   worker_chunk_kernel + worker_merge_kernel   per heartbeat epoch: load score / overload per worker (strategy_least_loaded.go:157-159,
 //                        :177-193), pool kept sorted by load, per-label bitmaps over that order, per-pool argmin
 //   policy_kernel        per job batch: first-match over the rule set (safety_policy.go:187-206, 259-294), decision
 //                        mapping + tenant MCP + effective-config overlay (kernel.go:187-248), scheduler post-step
@@ -74,71 +74,68 @@ __device__ __forceinline__ void merge_best(uint64_t& key, uint32_t& cnt, uint64_
 
 }  // namespace
 
-// ------------------------------------------------------------------ K2: one CTA per pool
-// Per heartbeat epoch: load score + overload test per worker, then a bitonic sort of the pool's
-// keys in shared memory.  The sorted view (keys + label masks in load order) lets label-constrained
-// jobs scan a pool from its least-loaded worker and stop at the first label match.
-__global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_cnt;
-  const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+// ------------------------------------------------------------------ K2: worker-table refresh, one CTA per pool chunk
+// Per heartbeat epoch: load score + overload test per worker, then the pool's keys in ascending order (the
+// load-sorted view lets label-constrained jobs find the least-loaded worker carrying their labels from per-label
+// bitmaps).  A pool is cut into chunks of CORDUM_POOL_CHUNK workers so that the whole GPU takes part in the refresh
+// instead of one SM per pool: worker_chunk_kernel sorts one chunk per CTA in shared memory (and finishes pools that
+// have a single chunk); worker_merge_kernel places every worker of a multi-chunk pool at
+//     its index in its own chunk + the number of smaller keys in each sibling chunk        (keys are unique: rank)
+// Pools above CORDUM_POOL_SORT_MAX workers keep only min / count-at-min; their jobs scan (route_kernel S').
+__device__ __forceinline__ uint64_t worker_key(const DeviceTables& T, uint32_t pos) {
+  const Load16 L = T.loads[T.pos_slot[pos]];
+  bool over = false;
+  if (L.max_parallel > 0) over = __fdiv_rn(__int2float_rn(L.active), __int2float_rn(L.max_parallel)) >= 0.9f;   // :177-184
+  over = over || L.cpu >= 90.0f || L.gpu >= 90.0f;                                                               // :185-191
+  const float score = __fadd_rn(__fadd_rn(__int2float_rn(L.active), __fdiv_rn(L.cpu, 100.0f)), __fdiv_rn(L.gpu, 100.0f));   // :157-159
+  return ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
+}
+
+template <uint32_t NT>
+__global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
+  constexpr uint32_t CH = CORDUM_POOL_CHUNK;
+  __shared__ uint64_t sk[CH];
+  __shared__ uint32_t s_cnt, s_nok;
+  const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const uint32_t p = T.chunk_pool[g], c = g - T.pool_chunk0[p], m = T.pool_chunk0[p + 1] - T.pool_chunk0[p];
   const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a;
+  const uint32_t cs = c * CH, len = n - cs < CH ? n - cs : CH;   // an empty pool has one empty chunk
+  const bool sortable = n <= CORDUM_POOL_SORT_MAX;
   uint32_t n_pad = 1;
-  while (n_pad < n) n_pad <<= 1;
-  const bool sortable = n_pad <= T.sort_cap;
-  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);   // keys only: the key's low word is the worker's rank
-  if (tid == 0) s_cnt = 0;
-  for (uint32_t i = tid; i < (sortable ? n_pad : n); i += nt) {
+  while (n_pad < len) n_pad <<= 1;
+  if (tid == 0) { s_cnt = 0; s_nok = 0; }
+  for (uint32_t i = tid; i < n_pad; i += NT) {
     uint64_t key = KEY_NONE;
-    if (i < n) {
-      const uint32_t pos = a + i;
-      const Load16 L = T.loads[T.pos_slot[pos]];
-      bool over = false;
-      if (L.max_parallel > 0) over = __fdiv_rn(__int2float_rn(L.active), __int2float_rn(L.max_parallel)) >= 0.9f;   // :177-184
-      over = over || L.cpu >= 90.0f || L.gpu >= 90.0f;                                                               // :185-191
-      const float score = __fadd_rn(__fadd_rn(__int2float_rn(L.active), __fdiv_rn(L.cpu, 100.0f)), __fdiv_rn(L.gpu, 100.0f));   // :157-159
-      key = ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
-      T.pos_key[pos] = key;
-    }
-    if (sortable) sk[i] = key;
+    if (i < len) { key = worker_key(T, a + cs + i); T.pos_key[a + cs + i] = key; }
+    sk[i] = key;
   }
+  if (!sortable) return;   // chunk 0 of the pool reduces min / count in worker_merge_kernel
   __syncthreads();
-  if (!sortable) {   // pool larger than the sort buffer: min/count by reduction, jobs fall back to full scans
-    __shared__ uint64_t s_best;
-    if (tid == 0) s_best = KEY_NONE;
-    __syncthreads();
-    uint64_t best = KEY_NONE;
-    for (uint32_t i = tid; i < n; i += nt) { uint64_t k = T.pos_key[a + i]; if (!key_over(k) && k < best) best = k; }
-    atomicMin(reinterpret_cast<unsigned long long*>(&s_best), (unsigned long long)best);
-    __syncthreads();
-    best = s_best;
-    uint32_t c = 0;
-    for (uint32_t i = tid; i < n; i += nt) { uint64_t k = T.pos_key[a + i]; c += (!key_over(k) && (uint32_t)(k >> 32) == (uint32_t)(best >> 32)) ? 1u : 0u; }
-    if (c) atomicAdd(&s_cnt, c);
-    __syncthreads();
-    if (tid == 0) { T.pool_best[p] = best; T.pool_mincnt[p] = best == KEY_NONE ? 0 : s_cnt; T.pool_sorted[p] = 0; }
-    return;
-  }
   // bitonic sort, one compare-exchange per (thread, pair): pair q touches i = q with a zero inserted at bit log2(jj)
   for (uint32_t k = 2; k <= n_pad; k <<= 1)
     for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-      for (uint32_t q = tid; q < (n_pad >> 1); q += nt) {
+      for (uint32_t q = tid; q < (n_pad >> 1); q += NT) {
         const uint32_t i = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), x = i | jj;
         const uint64_t ki = sk[i], kx = sk[x];
         if ((ki > kx) == ((i & k) == 0)) { sk[i] = kx; sk[x] = ki; }
       }
       __syncthreads();
     }
+  const uint32_t words = (n + 31) >> 5, nbits = T.place_bits;
+  uint32_t* bm = T.lbm + T.lbm_off[p];
+  if (m > 1) {
+    // hand the sorted chunk to worker_merge_kernel; clear what it accumulates into
+    for (uint32_t i = tid; i < len; i += NT) T.ckey[a + cs + i] = sk[i];
+    const uint64_t total = (uint64_t)nbits * words;
+    for (uint64_t i = total * c / m + tid; i < total * (c + 1) / m; i += NT) bm[i] = 0;
+    if (c == 0 && tid == 0) { T.pool_mincnt[p] = 0; T.pool_nok[p] = 0; }
+    return;
+  }
+  // single chunk: sorted view + label bitmaps; a warp takes 32 consecutive sorted workers (one bitmap word per label bit)
   const uint64_t k0 = n ? sk[0] : KEY_NONE;
   const bool none = n == 0 || key_over(k0);
-  __shared__ uint32_t s_nok;
-  if (tid == 0) s_nok = 0;
-  __syncthreads();
-  // sorted view + label bitmaps: a warp takes 32 consecutive sorted workers (one bitmap word per label bit)
-  const uint32_t words = (n + 31) >> 5, lane = tid & 31, nbits = T.place_bits;
-  uint32_t* bm = T.lbm + T.lbm_off[p];
-  uint32_t c = 0, ok = 0;
-  for (uint32_t w = tid >> 5; w < words; w += nt >> 5) {
+  uint32_t cnt = 0, ok = 0;
+  for (uint32_t w = tid >> 5; w < words; w += NT >> 5) {
     const uint32_t i = w * 32 + lane;
     uint64_t k = KEY_NONE, llo = 0, lhi = 0;
     if (i < n) {
@@ -146,7 +143,7 @@ __global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
       const uint32_t src = T.rank_pos[(uint32_t)(k & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
       llo = T.pos_label_lo[src]; lhi = T.pos_label_hi[src];
       T.skey[a + i] = k; T.slab_lo[a + i] = llo; T.slab_hi[a + i] = lhi;
-      c += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
+      cnt += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
       ok += key_over(k) ? 0u : 1u;
     }
     for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {   // lane t keeps the word of label bit b0+t, then one strided store each
@@ -160,16 +157,82 @@ __global__ void __launch_bounds__(1024) worker_pool_kernel(DeviceTables T) {
       if (lane < lim) bm[(size_t)(b0 + lane) * words + w] = mine;
     }
   }
-  if (c) atomicAdd(&s_cnt, c);
-  if (ok) atomicAdd(&s_nok, ok);
+  cnt = __reduce_add_sync(FULL, cnt); ok = __reduce_add_sync(FULL, ok);
+  if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  if (lane == 0 && ok) atomicAdd(&s_nok, ok);
   __syncthreads();
   if (tid == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_mincnt[p] = s_cnt; T.pool_sorted[p] = 1; T.pool_nok[p] = s_nok; }
+}
+
+__global__ void __launch_bounds__(256) worker_merge_kernel(DeviceTables T) {
+  constexpr uint32_t CH = CORDUM_POOL_CHUNK, NT = 256;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_cnt, s_nok;
+  __shared__ uint64_t s_best;
+  uint64_t* sp = reinterpret_cast<uint64_t*>(smem_raw);   // the pool's keys, chunk by chunk, each chunk ascending
+  const uint32_t g = T.merge_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31;
+  const uint32_t p = T.chunk_pool[g], c = g - T.pool_chunk0[p], m = T.pool_chunk0[p + 1] - T.pool_chunk0[p];
+  const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a;
+  if (tid == 0) { s_cnt = 0; s_nok = 0; s_best = KEY_NONE; }
+  __syncthreads();
+  if (n > CORDUM_POOL_SORT_MAX) {   // unsorted pool: min / count-at-min by reduction (listed once, as chunk 0)
+    uint64_t best = KEY_NONE;
+    for (uint32_t i = tid; i < n; i += NT) { const uint64_t k = T.pos_key[a + i]; if (!key_over(k) && k < best) best = k; }
+    for (int o = 16; o; o >>= 1) { const uint64_t v = shfl64_xor(FULL, best, o); best = v < best ? v : best; }
+    if (lane == 0) atomicMin(reinterpret_cast<unsigned long long*>(&s_best), (unsigned long long)best);
+    __syncthreads();
+    best = s_best;
+    uint32_t cnt = 0;
+    for (uint32_t i = tid; i < n; i += NT) { const uint64_t k = T.pos_key[a + i]; cnt += (!key_over(k) && (uint32_t)(k >> 32) == (uint32_t)(best >> 32)) ? 1u : 0u; }
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (tid == 0) { T.pool_best[p] = best; T.pool_mincnt[p] = best == KEY_NONE ? 0 : s_cnt; T.pool_sorted[p] = 0; }
+    return;
+  }
+  for (uint32_t i = tid; i < n; i += NT) sp[i] = T.ckey[a + i];
+  __syncthreads();
+  uint64_t k0 = KEY_NONE;
+  for (uint32_t cc = 0; cc < m; ++cc) { const uint64_t h = sp[cc * CH]; k0 = h < k0 ? h : k0; }
+  const bool none = key_over(k0);
+  const uint32_t cs = c * CH, len = n - cs < CH ? n - cs : CH;
+  const uint32_t words = (n + 31) >> 5;
+  uint32_t* bm = T.lbm + T.lbm_off[p];
+  uint32_t cnt = 0, ok = 0;
+  for (uint32_t i = tid; i < len; i += NT) {
+    const uint64_t k = sp[cs + i];
+    uint32_t idx = i;
+    for (uint32_t cc = 0; cc < m; ++cc) {
+      if (cc == c) continue;
+      const uint64_t* q = sp + cc * CH;
+      uint32_t lo = 0, hi = n - cc * CH < CH ? n - cc * CH : CH;   // lower bound of k in the sibling chunk
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (q[mid] < k) lo = mid + 1; else hi = mid; }
+      idx += lo;
+    }
+    const uint32_t src = T.rank_pos[(uint32_t)(k & 0xFFFFFFFFu)];
+    uint64_t llo = T.pos_label_lo[src], lhi = T.pos_label_hi[src];
+    T.skey[a + idx] = k; T.slab_lo[a + idx] = llo; T.slab_hi[a + idx] = lhi;
+    const uint32_t w = idx >> 5, bitv = 1u << (idx & 31);
+    while (llo) { const uint32_t b = __ffsll((long long)llo) - 1; llo &= llo - 1; atomicOr(&bm[(size_t)b * words + w], bitv); }
+    while (lhi) { const uint32_t b = 64 + __ffsll((long long)lhi) - 1; lhi &= lhi - 1; atomicOr(&bm[(size_t)b * words + w], bitv); }
+    cnt += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
+    ok += key_over(k) ? 0u : 1u;
+  }
+  cnt = __reduce_add_sync(FULL, cnt); ok = __reduce_add_sync(FULL, ok);
+  if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  if (lane == 0 && ok) atomicAdd(&s_nok, ok);
+  __syncthreads();
+  if (tid == 0) {
+    if (s_cnt) atomicAdd(&T.pool_mincnt[p], s_cnt);
+    if (s_nok) atomicAdd(&T.pool_nok[p], s_nok);
+    if (c == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_sorted[p] = 1; }
+  }
 }
 
 // ------------------------------------------------------------------ policy: first match + decision
 // A warp owns a tile of 32 consecutive jobs (lane = job for the coalesced column loads, the scalar
 // decision logic and the 16 B record store).  Needs no worker state, so it runs concurrently with the
-// heartbeat exchange and worker_pool_kernel.
+// heartbeat exchange and the worker-table refresh.
 //   P  the per-topic word lists of the tile's 32 jobs are walked 32 (job, word) items at a time: each lane ANDs one
 //      128-bit word of the 7-12 pass-rows its job selects (rule bits are permuted so that a topic touches few
 //      words); surviving bits map back to original rule indices; first match = min per job.
@@ -573,16 +636,41 @@ __global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
 }
 
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
-cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s) {
-  if (T.n_pools == 0) return cudaSuccess;
-  const size_t smem = (size_t)T.sort_cap * 8;   // one u64 key per entry
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(worker_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// An SM changes its L1 / shared-memory split only when it is idle, so kernels that ask for different splits cannot
+// share an SM: a refresh CTA (5 KiB of shared memory) would wait for every route / policy CTA (1-2 KiB, i.e. the
+// smallest split) on that SM to drain.  All kernels of the path therefore ask for the same carveout, large enough
+// for their resident CTAs side by side; the rest (>= 128 KiB) stays L1 for the pass-row gathers.
+static cudaError_t configure_kernels() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 32; }();   // tuning knob
+  const int pct = (kb * 100 + 227) / 228;
+  const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
+                       (const void*)policy_kernel<2>, (const void*)policy_kernel<3>, (const void*)policy_kernel<4>,
+                       (const void*)route_kernel<true>, (const void*)route_kernel<false>};
+  for (const void* f : fns) {
+    e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
-  worker_pool_kernel<<<T.n_pools, 1024, smem, s>>>(T);
+  e = cudaFuncSetAttribute(worker_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CORDUM_POOL_SORT_MAX * 8u));
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+
+cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read) {
+  if (T.n_pools == 0) return loads_read ? cudaEventRecord(loads_read, s) : cudaSuccess;
+  if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
+  static const int nt = []() { const char* v = getenv("CORDUM_CHUNK_NT"); return v ? atoi(v) : 256; }();   // tuning knob
+  if (nt == 256) worker_chunk_kernel<256><<<T.n_chunks, 256, 0, s>>>(T);
+  else worker_chunk_kernel<128><<<T.n_chunks, 128, 0, s>>>(T);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && loads_read) e = cudaEventRecord(loads_read, s);   // the load table is not read past this point
+  if (e != cudaSuccess || T.n_merge == 0) return e;
+  worker_merge_kernel<<<T.n_merge, 256, T.merge_smem, s>>>(T);
   return cudaGetLastError();
 }
 
@@ -596,6 +684,7 @@ static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
 
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
+  if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
   if (minb == 2) policy_kernel<2><<<blocks, 256, 0, s>>>(P);
@@ -606,6 +695,7 @@ cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
 
 cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
+  if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, 4);
   if (route_only) route_kernel<true><<<blocks, 256, 0, s>>>(P);
   else route_kernel<false><<<blocks, 256, 0, s>>>(P);

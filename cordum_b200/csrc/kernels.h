@@ -15,6 +15,7 @@ struct KParams {
   uint32_t honor_approved;   // POLICY_AND_ROUTE: jobs flagged JF_APPROVED bypass the policy (engine.go:484-522)
 };
 
-cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s);
+// loads_read (optional) is recorded once T.loads has been consumed (between the chunk and the merge kernel)
+cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read);
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s);
 cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s);

@@ -61,6 +61,9 @@ typedef struct JobColumns {
 #define CORDUM_JOB_OUT_BYTES 16u
 
 /* Everything the kernels read besides the job columns.  Pointers are device pointers. */
+#define CORDUM_POOL_CHUNK 512u
+#define CORDUM_POOL_SORT_MAX 8192u
+
 typedef struct DeviceTables {
   /* ---- policy */
   uint32_t n_rules, n_seg, row_u4;            /* row_u4 = n_seg * 8 uint4 per pass-row                 */
@@ -117,7 +120,15 @@ typedef struct DeviceTables {
                                                  bit i of word w = "sorted worker 32w+i carries label bit"               */
   const uint32_t* lbm_off;                    /* [n_pools] word offset of the pool's bitmaps                               */
   uint32_t place_bits;                        /* label bits in use (<= 128)                                                */
-  uint32_t sort_cap;                          /* entries the K2 shared-memory sort buffer holds (power of two)             */
+  /* worker-table refresh: a pool is cut into chunks of CORDUM_POOL_CHUNK workers, one CTA sorts one chunk, a second
+     kernel merges the chunks of pools that have more than one (pools above CORDUM_POOL_SORT_MAX stay unsorted)       */
+  const uint32_t* chunk_pool;                 /* [n_chunks] pool of the chunk                                              */
+  const uint32_t* pool_chunk0;                /* [n_pools+1] first chunk of the pool                                       */
+  const uint32_t* merge_list;                 /* [n_merge] chunks worker_merge_kernel runs (all chunks of a multi-chunk
+                                                 sortable pool; chunk 0 only of an unsortable pool)                       */
+  uint32_t n_chunks, n_merge;
+  uint32_t merge_smem;                        /* bytes of shared memory worker_merge_kernel needs (largest merged pool)    */
+  uint64_t* ckey;                             /* derived scratch: per chunk, its keys in ascending order                   */
   uint64_t* pool_best;                        /* derived: min key per pool (~0 = none)                  */
   uint32_t* pool_mincnt;                      /* derived: workers in the pool sharing the min score     */
 } DeviceTables;

@@ -82,6 +82,11 @@ class Batch:
         self.eng._ck(self.L.cordum_batch_timing(self.h, C.byref(t), C.byref(k)))
         return t.value, k.value
 
+    @property
+    def stream(self) -> int:
+        """The batch's cudaStream_t (as an integer), for harnesses that bracket launches with their own CUDA events."""
+        return int(self.L.cordum_batch_stream(self.h) or 0)
+
     def kernel_times(self):
         p, r = C.c_float(), C.c_float()
         self.eng._ck(self.L.cordum_batch_kernel_times(self.h, C.byref(p), C.byref(r)))

@@ -120,14 +120,22 @@ def test_device_load_table_path(eng):
     b.free()
 
 
-def test_pool_larger_than_sort_buffer(eng):
-    """A pool beyond worker_pool_kernel's 8192-entry sort buffer takes the unordered-scan path (route_kernel S')."""
-    rng = np.random.default_rng(5)
-    n = 9000
-    workers = [kats.hb("w%05d" % i, "big" if i < 8800 else "small", int(rng.integers(0, 6)), float(rng.random() * 100),
-                       float(rng.random() * 100), int(rng.choice([0, 4, 8])),
-                       {"zone": "z%d" % rng.integers(0, 4), **({"gpu": "true"} if rng.random() < 0.3 else {})}) for i in range(n)]
-    routing = {"topics": {"job.a": ["big", "small"], "job.b": ["small"]}, "pools": {"big": {}, "small": {}}}
+@pytest.mark.parametrize("n_big,coarse", [(512, False), (513, True), (1500, True), (5000, False), (8192, True), (8800, False)])
+def test_pool_sizes_across_refresh_paths(eng, n_big, coarse):
+    """Worker-table refresh paths by pool size: one chunk (<= 512 workers, finished by worker_chunk_kernel), several
+    chunks merged by worker_merge_kernel (<= 8192), and the unsorted pool whose jobs scan (route_kernel S').
+    `coarse` loads make many equal scores, so the merge must keep worker_id order inside a score and report ties."""
+    rng = np.random.default_rng(n_big)
+    n = n_big + 200
+
+    def mk(i):
+        cpu, gpu = (float(rng.integers(0, 3)) * 25.0, 0.0) if coarse else (float(rng.random() * 100), float(rng.random() * 100))
+        return kats.hb("w%05d" % i, "big" if i < n_big else "small", int(rng.integers(0, 3 if coarse else 6)), cpu, gpu,
+                       int(rng.choice([0, 4, 8])),
+                       {"zone": "z%d" % rng.integers(0, 4), **({"gpu": "true"} if rng.random() < 0.3 else {})})
+    workers = [mk(i) for i in range(n)]
+    rng.shuffle(workers)   # slot order is not worker_id order
+    routing = {"topics": {"job.a": ["big", "small"], "job.b": ["small"], "job.c": ["big"]}, "pools": {"big": {}, "small": {}}}
     jobs = []
     for i in range(400):
         labels = {}
@@ -135,13 +143,24 @@ def test_pool_larger_than_sort_buffer(eng):
             labels["zone"] = "z%d" % (i % 5)       # z4 matches nobody
         if i % 4 == 0:
             labels["gpu"] = "true"
-        jobs.append({"topic": "job.a" if i % 5 else "job.b", "labels": labels})
+        jobs.append({"topic": ("job.a", "job.b", "job.c")[i % 3] if i % 5 else "job.b", "labels": labels})
     load(eng, None, routing, workers)
     b = eng.batch(len(jobs))
-    got = b.encode(jobs).dispatch(wire.MODE_ROUTE_ONLY)
-    want = oracle_lib.Oracle(None, routing, workers).eval(jobs, wire.MODE_ROUTE_ONLY)
-    assert_same(got, want, "big pool")
+    got = b.encode(jobs).dispatch(wire.MODE_ROUTE_ONLY).copy()
+    o = oracle_lib.Oracle(None, routing, workers)
+    assert_same(got, o.eval(jobs, wire.MODE_ROUTE_ONLY), "pool of %d" % n_big)
     assert set(got["route_status"].tolist()) >= {wire.ROUTE_OK, wire.ROUTE_NO_WORKERS}
+    if coarse:
+        assert (got["flags"] & wire.F_TIE).any()
+    # a heartbeat epoch that overloads most of the big pool, then one that overloads all of it
+    for frac in (0.9, 1.0):
+        slots = np.arange(n, dtype=np.uint32)
+        loads = wire.WorkerTable.from_workers(workers).loads()
+        hot = rng.random(n) < frac
+        loads["cpu_load"] = np.where(hot, 95.0, loads["cpu_load"]).astype(np.float32)
+        eng.update_workers(slots, loads)
+        o.update_workers(slots, loads)
+        assert_same(b.dispatch(wire.MODE_ROUTE_ONLY), o.eval(jobs, wire.MODE_ROUTE_ONLY), "pool of %d, %.0f%% overloaded" % (n_big, frac * 100))
     b.free()
 
 
