@@ -464,6 +464,12 @@ void Host::compile_policy() {
   }
   std::stable_sort(entries.begin(), entries.end(), [](const Entry& x, const Entry& y) { return x.key < y.key; });
   const uint32_t NP = (uint32_t)entries.size();
+  // Inside one 128-bit word the positions are put in ascending rule order (which words a topic touches does not
+  // depend on the order inside a word): the lowest surviving bit of a word is then that word's first match, and the
+  // kernel looks at further bits only when a requires / labels subset test fails.
+  for (uint32_t w0 = 0; w0 < NP; w0 += 128)
+    std::stable_sort(entries.begin() + w0, entries.begin() + std::min<uint32_t>(NP, w0 + 128),
+                     [](const Entry& x, const Entry& y) { return x.rule < y.rule; });
   t.n_seg = std::max<uint32_t>(1, (NP + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
   t.row_words = t.n_seg * 32;
   const uint32_t W = t.row_words;

@@ -329,30 +329,27 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
         }
         const uint32_t keep = have ? 0xFFFFFFFFu : 0u;
         acc.x &= keep; acc.y &= keep; acc.z &= keep; acc.w &= keep;
-        // surviving bits -> original rule indices; rules carrying a requires / labels subset test are verified
-        // (containsAll :320-330, labelsMatch :332-345).  Usually 0-2 bits per word.
+        // Surviving bits -> original rule index.  Inside a word the positions ascend with the rule index, so the
+        // lowest surviving bit is the word's first match; a further bit is looked at only when that rule carries a
+        // requires / labels subset test (containsAll :320-330, labelsMatch :332-345) and the test fails.
         uint32_t best = 0xFFFFFFFFu;
-        uint64_t req = 0, lab = 0;
-        bool have_masks = false;
-        uint64_t vlo = (uint64_t)acc.x | ((uint64_t)acc.y << 32), vhi = (uint64_t)acc.z | ((uint64_t)acc.w << 32);
-        while (__any_sync(FULL, (vlo | vhi) != 0)) {
-          // lowest surviving bit of the 128-bit word, branch-free
-          const bool lo_nz = vlo != 0, nz = (vlo | vhi) != 0;
-          const int b_lo = __ffsll((long long)vlo), b_hi = __ffsll((long long)vhi);
-          const uint32_t bit = lo_nz ? (uint32_t)(b_lo - 1) : (uint32_t)(63 + b_hi);
-          const uint32_t pos = nz ? wi * 128u + bit : 0u;
-          uint32_t r = __ldg(T.pos2rule + pos);
-          const bool pend = nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u);
-          if (pend) {
-            if (!have_masks) { req = __ldg(C.req_mask + jsrc); lab = __ldg(C.lab_mask + jsrc); have_masks = true; }
+        uint32_t w0 = acc.x, w1 = acc.y, w2 = acc.z, w3 = acc.w;
+        while (__any_sync(FULL, (w0 | w1 | w2 | w3) != 0)) {
+          const uint32_t sel = w0 ? w0 : (w1 ? w1 : (w2 ? w2 : w3));
+          const uint32_t base = w0 ? 0u : (w1 ? 32u : (w2 ? 64u : 96u));
+          const bool nz = sel != 0;
+          const uint32_t pos = nz ? wi * 128u + base + (uint32_t)__ffs((int)sel) - 1u : 0u;
+          const uint32_t r = __ldg(T.pos2rule + pos);
+          bool ok = nz;
+          if (nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u)) {
+            const uint64_t req = __ldg(C.req_mask + jsrc), lab = __ldg(C.lab_mask + jsrc);
             const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
-            const bool ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
-            if (!ok) r = 0xFFFFFFFFu;
+            ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
           }
-          best = min(best, nz ? r : 0xFFFFFFFFu);
-          const uint64_t lo_cleared = vlo & (vlo - 1), hi_cleared = vhi & (vhi - 1);   // drop the bit just handled
-          vhi = lo_nz ? vhi : hi_cleared;
-          vlo = lo_cleared;
+          if (ok) { best = r; w0 = w1 = w2 = w3 = 0; }
+          else if (nz) {   // drop the bit just handled
+            if (w0) w0 &= w0 - 1; else if (w1) w1 &= w1 - 1; else if (w2) w2 &= w2 - 1; else w3 &= w3 - 1;
+          }
         }
         if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
       }
@@ -649,7 +646,7 @@ static cudaError_t configure_kernels() {
   static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 32; }();   // tuning knob
   const int pct = (kb * 100 + 227) / 228;
   const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
-                       (const void*)policy_kernel<2>, (const void*)policy_kernel<3>, (const void*)policy_kernel<4>,
+                       (const void*)policy_kernel<3>, (const void*)policy_kernel<4>, (const void*)policy_kernel<5>, (const void*)policy_kernel<6>,
                        (const void*)route_kernel<true>, (const void*)route_kernel<false>};
   for (const void* f : fns) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -685,10 +682,11 @@ static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
-  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
+  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 5; }();   // tuning knob
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
-  if (minb == 2) policy_kernel<2><<<blocks, 256, 0, s>>>(P);
-  else if (minb == 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
+  if (minb == 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 5) policy_kernel<5><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 6) policy_kernel<6><<<blocks, 256, 0, s>>>(P);
   else policy_kernel<4><<<blocks, 256, 0, s>>>(P);
   return cudaGetLastError();
 }

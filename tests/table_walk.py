@@ -218,6 +218,9 @@ def walk(T, cols, mode) -> np.ndarray:
                 assert not outside.any(), "a surviving bit lies outside the topic's word list"
                 best = 1 << 62
                 for wi in listed:
+                    # like the kernel: inside a word positions ascend with the rule index, so the first surviving bit
+                    # that passes its subset test is the word's first match and the rest of the word is not looked at
+                    word_best, prev = None, -1
                     for w in range(4 * wi, 4 * wi + 4):
                         bits = int(acc[w])
                         while bits:
@@ -225,11 +228,16 @@ def walk(T, cols, mode) -> np.ndarray:
                             bits &= bits - 1
                             pos = w * 32 + b
                             r = int(T["pos2rule"][pos])
+                            assert r >= prev, "positions inside a 128-bit word must ascend with the rule index"
+                            prev = r
                             if int(chk[w]) >> b & 1:
                                 need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
                                 if not ((need & ~req_mask) == 0 and (ln == 0 or (has_labels and (ln & ~lab) == 0))):
                                     continue
-                            best = min(best, r)
+                            if word_best is None:
+                                word_best = r
+                    if word_best is not None:
+                        best = min(best, word_best)
                 first = best if best < (1 << 62) else -1
                 rule = first
                 code, hascons = wire.DEC_ALLOW, False
