@@ -162,7 +162,7 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_req_need, t.rule_req_need, s), "upload"); CK(up(e->b_lab_need, t.rule_lab_need, s), "upload");
     CK(up(e->b_rule_dec, t.rule_dec, s), "upload"); CK(up(e->b_pos2rule, t.pos2rule, s), "upload");
     d.pos2rule = (const uint32_t*)e->b_pos2rule.p;
-    d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4;
+    d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4; d.item_u4 = t.item_u4;
     d.row_tenant = (const Row16*)e->b_row_tenant.p; d.n_tenant = t.row_tenant.n_rows;
     d.row_cap = (const Row16*)e->b_row_cap.p; d.n_cap = t.row_cap.n_rows;
     d.row_pack = (const Row16*)e->b_row_pack.p; d.n_pack = t.row_pack.n_rows;

@@ -406,6 +406,10 @@ void WorkPool::parallel_for(uint32_t n, uint32_t grain, const Fn& fn) {
 // ============================================================ Host
 Host::Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads)
     : max_topics_(max_topics ? max_topics : 65536), max_effcfgs_(max_effcfgs ? max_effcfgs : 4096) {
+  if (const char* v = getenv("CORDUM_ITEM_U4")) {   // tuning knob: 128-bit words per scan item
+    int k = atoi(v);
+    if (k == 1 || k == 2 || k == 4) t_.item_u4 = (uint32_t)k;
+  }
   unsigned hw = std::thread::hardware_concurrency();
   threads_ = encode_threads ? encode_threads : (hw ? hw : 4);
   if (!encode_threads) {
@@ -464,11 +468,12 @@ void Host::compile_policy() {
   }
   std::stable_sort(entries.begin(), entries.end(), [](const Entry& x, const Entry& y) { return x.key < y.key; });
   const uint32_t NP = (uint32_t)entries.size();
-  // Inside one 128-bit word the positions are put in ascending rule order (which words a topic touches does not
-  // depend on the order inside a word): the lowest surviving bit of a word is then that word's first match, and the
-  // kernel looks at further bits only when a requires / labels subset test fails.
-  for (uint32_t w0 = 0; w0 < NP; w0 += 128)
-    std::stable_sort(entries.begin() + w0, entries.begin() + std::min<uint32_t>(NP, w0 + 128),
+  // Inside one scan item (item_u4 x 128 bits) the positions are put in ascending rule order (which items a topic
+  // touches does not depend on the order inside an item): the lowest surviving bit of an item is then that item's
+  // first match, and the kernel looks at further bits only when a requires / labels subset test fails.
+  const uint32_t item_bits = t.item_u4 * 128u;
+  for (uint32_t w0 = 0; w0 < NP; w0 += item_bits)
+    std::stable_sort(entries.begin() + w0, entries.begin() + std::min<uint32_t>(NP, w0 + item_bits),
                      [](const Entry& x, const Entry& y) { return x.rule < y.rule; });
   t.n_seg = std::max<uint32_t>(1, (NP + CORDUM_SEG_RULES - 1) / CORDUM_SEG_RULES);
   t.row_words = t.n_seg * 32;
@@ -593,24 +598,28 @@ void Host::compile_policy() {
   t.row_check.init(1, W);
   or_bits(t.row_check.row(0), check);
 
-  // combo rows: (actor_type in {"", human, service}) x secrets_present, ANDed with the alive mask
-  t.row_combo.init(6, W);
+  // combo rows: (actor_type in {"", human, service}) x secrets_present x "job has none of the requires tokens rules
+  // list" x "job has none of the label pairs rules list", ANDed with the alive mask.  The last two settle the subset
+  // tests of most jobs inside the row AND; what they leave is verified per surviving bit (row_check).
+  t.row_combo.init(CORDUM_COMBO_ROWS, W);
   static const char* at_names[3] = {"", "human", "service"};
-  for (int at = 0; at < 3; ++at)
-    for (int s = 0; s < 2; ++s) {
-      uint32_t* row = t.row_combo.row(at * 2 + s);
-      for (uint32_t r = 0; r < R; ++r) {
-        const RuleModel& m = rules[r];
-        bool ok = true;
-        if (!m.actor_types.empty()) {
-          ok = false;
-          if (at != 0)
-            for (auto& e : m.actor_types) if (fold_key(e) == at_names[at]) ok = true;
-        }
-        if (m.secrets_present >= 0 && (m.secrets_present == 1) != (s == 1)) ok = false;
-        if (ok) for (uint32_t p : rule_pos_[r]) if (alive[p >> 5] >> (p & 31) & 1) row[p >> 5] |= 1u << (p & 31);
+  for (uint32_t c = 0; c < CORDUM_COMBO_ROWS; ++c) {
+    const int at = (int)(c % 6) / 2, s = (int)(c % 2);
+    const bool no_req = (c / 6) & 1, no_lab = (c / 12) & 1;
+    uint32_t* row = t.row_combo.row(c);
+    for (uint32_t r = 0; r < R; ++r) {
+      const RuleModel& m = rules[r];
+      bool ok = true;
+      if (!m.actor_types.empty()) {
+        ok = false;
+        if (at != 0)
+          for (auto& e : m.actor_types) if (fold_key(e) == at_names[at]) ok = true;
       }
+      if (m.secrets_present >= 0 && (m.secrets_present == 1) != (s == 1)) ok = false;
+      if ((no_req && t.rule_req_need[r]) || (no_lab && t.rule_lab_need[r])) ok = false;
+      if (ok) for (uint32_t p : rule_pos_[r]) if (alive[p >> 5] >> (p & 31) & 1) row[p >> 5] |= 1u << (p & 31);
     }
+  }
   t.v_policy++;
 }
 
@@ -719,13 +728,17 @@ void Host::topic_row(sv trimmed, Bits& out) const {
       for (uint32_t r : p.rules) out[r >> 5] |= 1u << (r & 31);
 }
 
-// The 128-bit words of a topic's pass-row that hold any bit: the only words a job on this topic has to AND.
+// The scan items (item_u4 x 128 bits) of a topic's pass-row that hold any bit: the only ones a job on this topic ANDs.
 void Host::topic_words_append(const uint32_t* row) {
   HostTables& t = t_;
   t.tw_off.push_back((uint32_t)t.tw_list.size());
   uint32_t n = 0;
-  for (uint32_t w = 0; w < t.row_words / 4; ++w)
-    if (row[4 * w] | row[4 * w + 1] | row[4 * w + 2] | row[4 * w + 3]) { t.tw_list.push_back((uint16_t)w); ++n; }
+  const uint32_t iw = t.item_u4 * 4;   // u32 words per scan item; row_words is a multiple of 32
+  for (uint32_t w = 0; w < t.row_words / iw; ++w) {
+    uint32_t any = 0;
+    for (uint32_t k = 0; k < iw; ++k) any |= row[iw * w + k];
+    if (any) { t.tw_list.push_back((uint16_t)w); ++n; }
+  }
   t.tw_cnt.push_back(n);
 }
 
@@ -1293,6 +1306,8 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
   if (have_secrets_label && !secrets_label.empty())
     secrets = secrets_label == "true" || secrets_label == "1" || fold_eq(secrets_label, "yes");
   flags |= (uint32_t)(at * 2 + (secrets ? 1 : 0));
+  if (req == 0) flags |= JF_NO_REQ;
+  if (!(flags & JF_HAS_LABELS) || lab == 0) flags |= JF_NO_LAB;
   // ---- routing hints
   uint32_t pp = 0, pw = 0;
   if (!pref_pool.empty()) { uint32_t id = d_pool_.table.find(pref_pool, 0); pp = id >= 2 ? id - 1 : CORDUM_PREF_UNKNOWN; }

@@ -180,6 +180,7 @@ struct HostTables {
   std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot, rank_pos, lbm_off;
   uint32_t place_bits = 1;
   uint64_t lbm_words = 0;
+  uint32_t item_u4 = 1;                                        // 128-bit words per scan item (tables.h)
   std::vector<uint32_t> chunk_pool, pool_chunk0, merge_list;   // worker-table refresh work list (tables.h)
   uint32_t n_chunks = 0, n_merge = 0, merge_smem = 0;
   std::vector<uint64_t> pos_label_lo, pos_label_hi;

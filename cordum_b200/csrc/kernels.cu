@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) worker_merge_kernel(DeviceTables T) {
 //      words); surviving bits map back to original rule indices; first match = min per job.
 //   D  decision mapping, tenant MCP, effective-config overlay, approval flags, scheduler post-step:
 //      thread per job.
-template <int MINB>
+template <int MINB, int IU>
 __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
     uint32_t* my_best = s_best[threadIdx.x >> 5];
     int first = -1;
     {
-      const uint32_t o_combo = (c_flags & JF_COMBO_MASK) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
+      const uint32_t o_combo = CORDUM_COMBO_INDEX(c_flags) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
                      o_cap = c_cap * rowu4, o_pack = c_pack * rowu4, o_actor = c_actor * rowu4;
       uint32_t c_twoff = 0, c_twcnt = 0;
       if (eval) { c_twoff = __ldg(T.tw_off + c_topic); c_twcnt = __ldg(T.tw_cnt + c_topic); }
@@ -296,27 +296,35 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
         const uint32_t li = q - __shfl_sync(FULL, excl, jl);
         const uint32_t fl = __shfl_sync(FULL, c_flags, jl);
         const uint32_t twoff = __shfl_sync(FULL, c_twoff, jl);   // every lane takes part in every shuffle
-        const uint32_t wi = have ? (uint32_t)__ldg(T.tw_list + twoff + li) : 0u;   // word 0: valid address for idle lanes
+        // wi: the item's first 128-bit word within a row (item 0: valid address for idle lanes)
+        const uint32_t wi = have ? (uint32_t)__ldg(T.tw_list + twoff + li) * (uint32_t)IU : 0u;
         const Row16* p_combo = T.row_combo + __shfl_sync(FULL, o_combo, jl) + wi;
         const Row16* p_tenant = T.row_tenant + __shfl_sync(FULL, o_tenant, jl) + wi;
         const Row16* p_topic = T.row_topic + __shfl_sync(FULL, o_topic, jl) + wi;
         const Row16* p_cap = T.row_cap + __shfl_sync(FULL, o_cap, jl) + wi;
         const Row16* p_pack = T.row_pack + __shfl_sync(FULL, o_pack, jl) + wi;
         const Row16* p_actor = T.row_actor + __shfl_sync(FULL, o_actor, jl) + wi;
-        uint4 acc = and4(and4(and4(ld_row(p_combo), ld_row(p_tenant)), and4(ld_row(p_topic), ld_row(p_cap))),
-                         and4(ld_row(p_pack), ld_row(p_actor)));
+        uint4 acc[IU];
+#pragma unroll
+        for (int u = 0; u < IU; ++u)
+          acc[u] = and4(and4(and4(ld_row(p_combo + u), ld_row(p_tenant + u)), and4(ld_row(p_topic + u), ld_row(p_cap + u))),
+                        and4(ld_row(p_pack + u), ld_row(p_actor + u)));
         {   // risk tags: containsAny = OR over the job's tags (:308-318).  Branch-free: row 0 = "no referenced tag",
             // row 1+b = tag b, and lanes that ran out of tags read the all-zero row.
           uint64_t m = shfl64(FULL, c_risk, jl);
           uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
           m &= m - 1;
-          uint4 rk = ld_row(T.row_risk + (idx * rowu4 + wi));
+          uint4 rk[IU];
+#pragma unroll
+          for (int u = 0; u < IU; ++u) rk[u] = ld_row(T.row_risk + (idx * rowu4 + wi + u));
           while (__any_sync(FULL, m != 0)) {
             idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
             m &= m - 1;
-            rk = or4(rk, ld_row(T.row_risk + (idx * rowu4 + wi)));
+#pragma unroll
+            for (int u = 0; u < IU; ++u) rk[u] = or4(rk[u], ld_row(T.row_risk + (idx * rowu4 + wi + u)));
           }
-          acc = and4(acc, rk);
+#pragma unroll
+          for (int u = 0; u < IU; ++u) acc[u] = and4(acc[u], rk[u]);
         }
         const uint32_t jsrc = tile * 32 + (uint32_t)jl;   // the job this lane works for (MCP ids / masks are read on demand)
         const bool mcp_used = have && (fl & JF_MCP_USED);
@@ -324,20 +332,26 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
 #pragma unroll
           for (int qf = 0; qf < 4; ++qf) {
             const uint32_t id = mcp_used ? __ldg(C.mcp[qf] + jsrc) : T.mcp_ones_row[qf];
-            acc = and4(acc, ld_row(T.row_mcp[qf] + (id * rowu4 + wi)));
+#pragma unroll
+            for (int u = 0; u < IU; ++u) acc[u] = and4(acc[u], ld_row(T.row_mcp[qf] + (id * rowu4 + wi + u)));
           }
         }
-        const uint32_t keep = have ? 0xFFFFFFFFu : 0u;
-        acc.x &= keep; acc.y &= keep; acc.z &= keep; acc.w &= keep;
-        // Surviving bits -> original rule index.  Inside a word the positions ascend with the rule index, so the
-        // lowest surviving bit is the word's first match; a further bit is looked at only when that rule carries a
+        // Surviving bits -> original rule index.  Inside an item the positions ascend with the rule index, so the
+        // lowest surviving bit is the item's first match; a further bit is looked at only when that rule carries a
         // requires / labels subset test (containsAll :320-330, labelsMatch :332-345) and the test fails.
         uint32_t best = 0xFFFFFFFFu;
-        uint32_t w0 = acc.x, w1 = acc.y, w2 = acc.z, w3 = acc.w;
-        while (__any_sync(FULL, (w0 | w1 | w2 | w3) != 0)) {
-          const uint32_t sel = w0 ? w0 : (w1 ? w1 : (w2 ? w2 : w3));
-          const uint32_t base = w0 ? 0u : (w1 ? 32u : (w2 ? 64u : 96u));
+        uint32_t w[4 * IU];
+#pragma unroll
+        for (int u = 0; u < IU; ++u) {
+          w[4 * u] = have ? acc[u].x : 0u; w[4 * u + 1] = have ? acc[u].y : 0u;
+          w[4 * u + 2] = have ? acc[u].z : 0u; w[4 * u + 3] = have ? acc[u].w : 0u;
+        }
+        while (true) {
+          uint32_t sel = 0, base = 0;   // lowest non-zero 32-bit word of the item
+#pragma unroll
+          for (int k = 4 * IU - 1; k >= 0; --k) if (w[k]) { sel = w[k]; base = 32u * (uint32_t)k; }
           const bool nz = sel != 0;
+          if (!__any_sync(FULL, nz)) break;
           const uint32_t pos = nz ? wi * 128u + base + (uint32_t)__ffs((int)sel) - 1u : 0u;
           const uint32_t r = __ldg(T.pos2rule + pos);
           bool ok = nz;
@@ -346,10 +360,10 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
             const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
             ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
           }
-          if (ok) { best = r; w0 = w1 = w2 = w3 = 0; }
-          else if (nz) {   // drop the bit just handled
-            if (w0) w0 &= w0 - 1; else if (w1) w1 &= w1 - 1; else if (w2) w2 &= w2 - 1; else w3 &= w3 - 1;
-          }
+          if (ok) best = r;
+          const uint32_t drop = sel & (sel - 1);   // the selected word without the bit just handled
+#pragma unroll
+          for (int k = 0; k < 4 * IU; ++k) w[k] = ok ? 0u : ((nz && base == 32u * (uint32_t)k) ? drop : w[k]);
         }
         if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
       }
@@ -646,7 +660,8 @@ static cudaError_t configure_kernels() {
   static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 32; }();   // tuning knob
   const int pct = (kb * 100 + 227) / 228;
   const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
-                       (const void*)policy_kernel<3>, (const void*)policy_kernel<4>, (const void*)policy_kernel<5>, (const void*)policy_kernel<6>,
+                       (const void*)policy_kernel<4, 1>, (const void*)policy_kernel<5, 1>, (const void*)policy_kernel<4, 2>,
+                       (const void*)policy_kernel<5, 2>, (const void*)policy_kernel<3, 4>, (const void*)policy_kernel<4, 4>,
                        (const void*)route_kernel<true>, (const void*)route_kernel<false>};
   for (const void* f : fns) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -684,10 +699,11 @@ cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 5; }();   // tuning knob
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
-  if (minb == 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
-  else if (minb == 5) policy_kernel<5><<<blocks, 256, 0, s>>>(P);
-  else if (minb == 6) policy_kernel<6><<<blocks, 256, 0, s>>>(P);
-  else policy_kernel<4><<<blocks, 256, 0, s>>>(P);
+  const uint32_t iu = P.t.item_u4;
+  if (iu == 1) { if (minb >= 5) policy_kernel<5, 1><<<blocks, 256, 0, s>>>(P); else policy_kernel<4, 1><<<blocks, 256, 0, s>>>(P); }
+  else if (iu == 2) { if (minb >= 5) policy_kernel<5, 2><<<blocks, 256, 0, s>>>(P); else policy_kernel<4, 2><<<blocks, 256, 0, s>>>(P); }
+  else if (iu == 4) { if (minb >= 4) policy_kernel<4, 4><<<blocks, 256, 0, s>>>(P); else policy_kernel<3, 4><<<blocks, 256, 0, s>>>(P); }
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

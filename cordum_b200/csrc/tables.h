@@ -35,6 +35,13 @@ typedef struct __attribute__((aligned(16))) Load16 { int32_t active, max_paralle
 #define JF_TOPIC_RAW_EMPTY 0x800u       /* req.Topic == ""          (strategy_least_loaded.go:41)      */
 #define JF_EFF_DENIED 0x1000u           /* effective config: topic matches denied_topics (kernel.go:219)*/
 #define JF_EFF_NOT_ALLOWED 0x2000u      /* allowed_topics set and topic not in it (kernel.go:223)       */
+#define JF_NO_REQ 0x4000u               /* the job carries no requires token any rule lists: every rule with a
+                                           requires list fails containsAll (safety_policy.go:320-330)            */
+#define JF_NO_LAB 0x8000u               /* no labels, or none of the label pairs any rule lists: every rule with a
+                                           labels map fails labelsMatch (safety_policy.go:332-345)               */
+/* row_combo index: actor_type / secrets_present combination + 6 * NO_REQ + 12 * NO_LAB (24 rows) */
+#define CORDUM_COMBO_ROWS 24u
+#define CORDUM_COMBO_INDEX(flags) (((flags) & JF_COMBO_MASK) + (((flags) >> 14) & 3u) * 6u)
 
 #define CORDUM_PREF_UNKNOWN 0xFFFFFFFFu /* preferred_pool / preferred_worker_id names nothing known    */
 
@@ -67,6 +74,8 @@ typedef struct JobColumns {
 typedef struct DeviceTables {
   /* ---- policy */
   uint32_t n_rules, n_seg, row_u4;            /* row_u4 = n_seg * 8 uint4 per pass-row                 */
+  uint32_t item_u4;                           /* uint4 (128-bit words) per scan item: a lane ANDs item_u4 * 128 rule bits
+                                                 per step; tw_list holds item indices (1, 2 or 4)                  */
   const Row16* row_tenant;  uint32_t n_tenant;
   const Row16* row_topic;   uint32_t n_topic;
   const Row16* row_cap;     uint32_t n_cap;

@@ -82,6 +82,7 @@ uint64_t cordum_test_host_scalar(void* h, const char* name) {
   std::string n(name);
   if (n == "n_rules") return t.n_rules;
   if (n == "n_seg") return t.n_seg;
+  if (n == "item_u4") return t.item_u4;
   if (n == "row_words") return t.row_words;
   if (n == "mcp_stride") return t.mcp_stride;
   if (n == "topic_stride") return t.topic_stride;

@@ -34,7 +34,7 @@ TABLES = {
     "pos_pool": np.uint32, "pos_slot": np.uint32, "pos_rank": np.uint32, "slot_pos": np.uint32, "rank_slot": np.uint32,
     "pos_label_lo": np.uint64, "pos_label_hi": np.uint64, "loads": wire.LOAD_DTYPE,
 }
-SCALARS = ["n_rules", "n_seg", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
+SCALARS = ["n_rules", "n_seg", "item_u4", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
            "n_pos", "n_slots", "n_topics"]
 
 
@@ -191,7 +191,7 @@ def walk(T, cols, mode) -> np.ndarray:
                 reason = wire.REASON_UNSUPPORTED_TOPIC
             else:
                 mcp_used, has_labels = bool(flags & JF_MCP_USED), bool(flags & JF_HAS_LABELS)
-                acc = (rows["row_combo"][flags & JF_COMBO_MASK] & rows["row_tenant"][cols["tenant"][j]]
+                acc = (rows["row_combo"][(flags & JF_COMBO_MASK) + ((flags >> 14) & 3) * 6] & rows["row_tenant"][cols["tenant"][j]]
                        & rows["row_topic"][topic] & rows["row_cap"][cols["capability"][j]]
                        & rows["row_pack"][cols["pack"][j]] & rows["row_actor"][cols["actor"][j]])
                 risk = int(cols["risk_mask"][j])
@@ -212,23 +212,24 @@ def walk(T, cols, mode) -> np.ndarray:
                 # first match is the minimum ORIGINAL rule index over the surviving bits (kernels.cu phase P)
                 o, c = int(T["tw_off"][topic]), int(T["tw_cnt"][topic])
                 listed = [int(x) for x in T["tw_list"][o:o + c]]
+                iw = 4 * int(T["item_u4"])   # u32 words per scan item
                 outside = acc.copy()
                 for wi in listed:
-                    outside[4 * wi: 4 * wi + 4] = 0
-                assert not outside.any(), "a surviving bit lies outside the topic's word list"
+                    outside[iw * wi: iw * wi + iw] = 0
+                assert not outside.any(), "a surviving bit lies outside the topic's item list"
                 best = 1 << 62
                 for wi in listed:
                     # like the kernel: inside a word positions ascend with the rule index, so the first surviving bit
                     # that passes its subset test is the word's first match and the rest of the word is not looked at
                     word_best, prev = None, -1
-                    for w in range(4 * wi, 4 * wi + 4):
+                    for w in range(iw * wi, iw * wi + iw):
                         bits = int(acc[w])
                         while bits:
                             b = (bits & -bits).bit_length() - 1
                             bits &= bits - 1
                             pos = w * 32 + b
                             r = int(T["pos2rule"][pos])
-                            assert r >= prev, "positions inside a 128-bit word must ascend with the rule index"
+                            assert r >= prev, "positions inside a scan item must ascend with the rule index"
                             prev = r
                             if int(chk[w]) >> b & 1:
                                 need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
