@@ -550,6 +550,21 @@ __global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
       const uint64_t need_req = shfl64(FULL, c_req, s_) & ~T.req_blank_mask;
       const uint64_t need_lo = shfl64(FULL, c_plo, s_), need_hi = shfl64(FULL, c_phi, s_);
       const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+      // required label bits -> bitmap row numbers, once per job (not per pool and word): four 8-bit row numbers in lbp
+      uint32_t lbp = 0, nlb = 0;
+      bool more;
+      {
+        uint64_t rl = need_lo, rh = need_hi;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint32_t bit = 0;
+          bool got = false;
+          if (rl) { bit = (uint32_t)__ffsll((long long)rl) - 1u; rl &= rl - 1; got = true; }
+          else if (rh) { bit = 64u + (uint32_t)__ffsll((long long)rh) - 1u; rh &= rh - 1; got = true; }
+          if (got) { nlb = (uint32_t)t + 1u; lbp |= bit << (8 * t); }
+        }
+        more = (rl | rh) != 0;
+      }
       uint64_t b = KEY_NONE;
       uint32_t bc = 0, tot = 0;
       for (uint32_t k = 0; __any_sync(FULL, k < cnt); ++k) {
@@ -566,9 +581,16 @@ __global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
           const uint32_t w = w0 + sub;
           uint32_t v = 0;
           if (w < words && !tie_done) {   // matchesLabels (:161-175) for 32 load-sorted workers at once
-            v = 0xFFFFFFFFu;
-            for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(size_t)(__ffsll((long long)m) - 1) * words + w];
-            for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(size_t)(64 + __ffsll((long long)m) - 1) * words + w];
+            // the first four required label bits are independent predicated loads; more than four is rare
+            const uint32_t x0 = nlb > 0 ? bm[(lbp & 0xFFu) * words + w] : 0xFFFFFFFFu;
+            const uint32_t x1 = nlb > 1 ? bm[((lbp >> 8) & 0xFFu) * words + w] : 0xFFFFFFFFu;
+            const uint32_t x2 = nlb > 2 ? bm[((lbp >> 16) & 0xFFu) * words + w] : 0xFFFFFFFFu;
+            const uint32_t x3 = nlb > 3 ? bm[(lbp >> 24) * words + w] : 0xFFFFFFFFu;
+            v = (x0 & x1) & (x2 & x3);
+            if (more) {   // AND is idempotent: walk all required bits again
+              for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(uint32_t)(__ffsll((long long)m) - 1) * words + w];
+              for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(uint32_t)(64 + __ffsll((long long)m) - 1) * words + w];
+            }
           }
           tot += __popc(v);                                     // label-matching candidates, overloaded ones included
           const uint32_t lo = w * 32;

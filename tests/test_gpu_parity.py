@@ -164,6 +164,22 @@ def test_pool_sizes_across_refresh_paths(eng, n_big, coarse):
     b.free()
 
 
+def test_many_placement_labels(eng):
+    """More than four placement labels on a job (route_kernel keeps four bitmap rows in registers, the rest loop)."""
+    rng = np.random.default_rng(11)
+    keys = ["zone", "tier", "region", "env", "arch", "gpu", "disk"]
+    workers = [kats.hb("w%03d" % i, "p", int(rng.integers(0, 4)), float(rng.random() * 80), 0.0, 0,
+                       {k: "v%d" % rng.integers(0, 3) for k in keys}) for i in range(300)]
+    routing = {"topics": {"job.a": ["p"]}, "pools": {"p": {}}}
+    jobs = [{"topic": "job.a", "labels": {k: "v%d" % rng.integers(0, 3) for k in keys[:n]}} for n in range(0, 8) for _ in range(20)]
+    load(eng, None, routing, workers)
+    b = eng.batch(len(jobs))
+    got = b.encode(jobs).dispatch(wire.MODE_ROUTE_ONLY).copy()
+    assert_same(got, oracle_lib.Oracle(None, routing, workers).eval(jobs, wire.MODE_ROUTE_ONLY), "many labels")
+    assert set(got["route_status"].tolist()) >= {wire.ROUTE_OK, wire.ROUTE_NO_WORKERS}
+    b.free()
+
+
 def test_c5_demo_guardrails_replay_100k(eng):
     c5 = kats.golden("c5_demo_guardrails.json")
     jobs, workers, kind = synth.make_c5(100_000)
