@@ -1124,15 +1124,34 @@ const std::vector<std::string>& Host::topic_pool_names(uint32_t topic_id) const 
 // stack for the duration of one encode call, while the arena is immutable.
 struct EncodeCaches {
   struct Entry { const char* p = nullptr; uint32_t len = 0, val = 0, aux = 0; };
-  static constexpr uint32_t N = 512;
-  Entry topic[N], tenant[N], cap[N], pack[N], actor[N], risk[N], req[N];
-  static uint32_t slot(sv s) { return (uint32_t)((((uintptr_t)s.data() >> 1) ^ s.size()) * 0x9E3779B1u) >> 23; }   // 9 bits
-  static bool get(const Entry* t, sv s, uint32_t& val, uint32_t& aux) {
-    const Entry& e = t[slot(s)];
-    if (e.p == s.data() && e.len == s.size()) { val = e.val; aux = e.aux; return true; }
-    return false;
+  template <uint32_t BITS>
+  struct Tab {
+    Entry e[1u << BITS];
+    static uint32_t slot(sv s) { return (uint32_t)((((uintptr_t)s.data() >> 1) ^ s.size()) * 0x9E3779B1u) >> (32 - BITS); }
+    bool get(sv s, uint32_t& val, uint32_t& aux) const {
+      const Entry& x = e[slot(s)];
+      if (x.p == s.data() && x.len == s.size()) { val = x.val; aux = x.aux; return true; }
+      return false;
+    }
+    void put(sv s, uint32_t val, uint32_t aux) { e[slot(s)] = Entry{s.data(), (uint32_t)s.size(), val, aux}; }
+  };
+  // sized for the cardinalities a batch typically shows (thousands of topics / capabilities, many principals)
+  Tab<12> topic;
+  Tab<11> cap, actor;
+  Tab<9> tenant, pack, risk, req;
+  // (label key, label value) pairs: what the pair does to the rule label mask and to the placement mask.  Keys that
+  // carry per-job values (MCP aliases, secrets_present, preferred_pool, preferred_worker_id) are never cached.
+  struct LabelEntry {
+    const char* kp = nullptr; const char* vp = nullptr;
+    uint32_t klen = 0, vlen = 0;
+    uint64_t set = 0, clear = 0;   // rule label pairs: lab = (lab | set) & ~clear
+    uint32_t place = 0;            // placement bit, or kPlaceNone / kPlaceUnsat
+  };
+  static constexpr uint32_t kPlaceNone = 0xFFFFFFFFu, kPlaceUnsat = 0xFFFFFFFEu;
+  LabelEntry label[1024];
+  static uint32_t lslot(sv k, sv v) {
+    return (uint32_t)(((((uintptr_t)k.data() >> 1) ^ k.size()) * 0x9E3779B1u) ^ ((((uintptr_t)v.data() >> 1) ^ v.size()) * 0x85EBCA6Bu)) >> 22;
   }
-  static void put(Entry* t, sv s, uint32_t val, uint32_t aux) { t[slot(s)] = Entry{s.data(), (uint32_t)s.size(), val, aux}; }
 };
 
 namespace {
@@ -1169,11 +1188,11 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
   // ---- topic (dictionary keyed by the RAW string: policy sees TrimSpace(topic), routing the raw one)
   sv topic_raw = span(env, env->topic, j);
   uint32_t tid;
-  if (!topic_raw.empty() && EncodeCaches::get(cc.topic, topic_raw, cv, ca)) tid = cv;
+  if (!topic_raw.empty() && cc.topic.get(topic_raw, cv, ca)) tid = cv;
   else {
     tid = topic_ids_.find(topic_raw, kMiss);
     if (tid == kMiss) { miss = true; tid = 0; }
-    else if (!topic_raw.empty()) EncodeCaches::put(cc.topic, topic_raw, tid, 0);
+    else if (!topic_raw.empty()) cc.topic.put(topic_raw, tid, 0);
   }
   out.topic[j] = tid;
   flags |= topic_entries_[tid].flags;
@@ -1183,11 +1202,11 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
   if (tenant.empty() && has_meta) tenant = trim_space(span(env, env->meta_tenant_id, j));
   if (tenant.empty()) tenant = default_tenant_trim_;
   if (tenant.empty()) tenant = "default";
-  if (EncodeCaches::get(cc.tenant, tenant, cv, ca)) { out.tenant[j] = cv; out.tenant_pol[j] = ca; }
+  if (cc.tenant.get(tenant, cv, ca)) { out.tenant[j] = cv; out.tenant_pol[j] = ca; }
   else {
     out.tenant_pol[j] = tenant_pol_.find(tenant, 0);   // exact-string map lookup (kernel.go:190)
     out.tenant[j] = lookup_value(d_tenant_, tenant);
-    EncodeCaches::put(cc.tenant, tenant, out.tenant[j], out.tenant_pol[j]);
+    cc.tenant.put(tenant, out.tenant[j], out.tenant_pol[j]);
   }
   // ---- meta (policyMetaFromRequest, kernel.go:348-368)
   sv principal = span(env, env->principal_id, j);
@@ -1201,12 +1220,12 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
     int raw_at = env->actor_type ? env->actor_type[j] : 0;
     at = (raw_at == 1 || raw_at == 2) ? raw_at : 0;
   }
-  auto cached = [&](EncodeCaches::Entry* tab, const Dict& d, sv v) -> uint32_t {
+  auto cached = [&](auto& tab, const Dict& d, sv v) -> uint32_t {
     if (v.empty()) return CORDUM_ID_EMPTY;
     uint32_t val, aux;
-    if (EncodeCaches::get(tab, v, val, aux)) return val;
+    if (tab.get(v, val, aux)) return val;
     val = lookup_value(d, v);
-    EncodeCaches::put(tab, v, val, 0);
+    tab.put(v, val, 0);
     return val;
   };
   out.capability[j] = cached(cc.cap, d_cap_, cap);
@@ -1220,10 +1239,10 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
       sv tag = span(env, env->risk_tags, k);
       uint32_t id, is_secrets;
       if (tag.empty()) continue;
-      if (!EncodeCaches::get(cc.risk, tag, id, is_secrets)) {
+      if (!cc.risk.get(tag, id, is_secrets)) {
         is_secrets = fold_eq(tag, "secrets") ? 1u : 0u;   // kernel.go:387-391 (no trim)
         id = lookup_value(d_risk_, tag);
-        EncodeCaches::put(cc.risk, tag, id, is_secrets);
+        cc.risk.put(tag, id, is_secrets);
       }
       if (is_secrets) secrets_tag = true;
       if (id >= 2 && id - 2 < 64) risk |= 1ull << (id - 2);
@@ -1234,11 +1253,11 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
     for (uint32_t k = a; k < b; ++k) {
       sv tok = span(env, env->requires_, k);
       uint32_t id, blank;
-      if (tok.empty() || !EncodeCaches::get(cc.req, tok, id, blank)) {
+      if (tok.empty() || !cc.req.get(tok, id, blank)) {
         FoldBuf f(tok);
         id = d_req_.table.find(f.view, 0);
         blank = f.view.empty() ? 1u : 0u;
-        if (!tok.empty()) EncodeCaches::put(cc.req, tok, id, blank);
+        if (!tok.empty()) cc.req.put(tok, id, blank);
       }
       if (id >= 2 && id - 2 < 64) req |= 1ull << (id - 2);
       else if (!blank) flags |= JF_REQ_UNKNOWN;   // no pool declares it -> no pool satisfies (:255-262)
@@ -1258,37 +1277,50 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
     bool shadowed = false;   // map semantics: a later entry with the same key wins
     for (uint32_t k2 = k + 1; k2 < lb && !shadowed; ++k2) shadowed = span(env, env->label_keys, k2) == key;
     if (shadowed) continue;
+    EncodeCaches::LabelEntry& ce = cc.label[EncodeCaches::lslot(key, val)];
+    if (ce.kp == key.data() && ce.klen == key.size() && ce.vp == val.data() && ce.vlen == val.size()) {
+      lab = (lab | ce.set) & ~ce.clear;
+      if (ce.place == EncodeCaches::kPlaceUnsat) flags |= JF_PLACE_UNSAT;
+      else if (ce.place != EncodeCaches::kPlaceNone) place[ce.place >> 6] |= 1ull << (ce.place & 63);
+      continue;
+    }
     // rule label pairs: labels.get(k,"") == v
+    uint64_t lset = 0, lclear = 0;
     uint32_t ki = label_key_.find(key, kMiss);
     if (ki != kMiss)
       for (auto& pv : label_key_pairs_[ki]) {
         if (pv.second >= 64) continue;
-        if (sv(pv.first) == val) lab |= 1ull << pv.second; else lab &= ~(1ull << pv.second);
+        if (sv(pv.first) == val) lset |= 1ull << pv.second; else lclear |= 1ull << pv.second;
       }
+    lab = (lab | lset) & ~lclear;
+    bool special = false;   // the value matters per job: not cacheable
     int mk = mcp_key(key);
-    if (mk >= 0) mcpv[mk] = trim_space(val);
-    if (key == "secrets_present") { secrets_label = trim_space(val); have_secrets_label = true; }
-    else if (key == "preferred_pool") pref_pool = val;
-    else if (key == "preferred_worker_id") pref_worker = val;
+    if (mk >= 0) { mcpv[mk] = trim_space(val); special = true; }
+    if (key == "secrets_present") { secrets_label = trim_space(val); have_secrets_label = true; special = true; }
+    else if (key == "preferred_pool") { pref_pool = val; special = true; }
+    else if (key == "preferred_worker_id") { pref_worker = val; special = true; }
     // placement constraint?
-    if (placement_skips(key) || starts_with(key, "cordum.")) continue;
-    uint32_t bit;
-    if (!val.empty()) {
-      char small[256];
-      std::string big;
-      sv pk;
-      size_t n = key.size() + 1 + val.size();
-      if (n <= sizeof small) {
-        std::memcpy(small, key.data(), key.size()); small[key.size()] = 0; std::memcpy(small + key.size() + 1, val.data(), val.size());
-        pk = sv(small, n);
-      } else { big.assign(key); big.push_back('\0'); big.append(val); pk = big; }
-      bit = place_pair_.find(pk, kMiss);
-      if (bit == kMiss) { flags |= JF_PLACE_UNSAT; continue; }
-    } else {
-      bit = place_key_.find(key, kMiss);
-      if (bit == kMiss) bit = place_any_bit_;   // no worker carries this key: any labelled worker passes
+    uint32_t bit = EncodeCaches::kPlaceNone;
+    if (!(placement_skips(key) || starts_with(key, "cordum."))) {
+      if (!val.empty()) {
+        char small[256];
+        std::string big;
+        sv pk;
+        size_t n = key.size() + 1 + val.size();
+        if (n <= sizeof small) {
+          std::memcpy(small, key.data(), key.size()); small[key.size()] = 0; std::memcpy(small + key.size() + 1, val.data(), val.size());
+          pk = sv(small, n);
+        } else { big.assign(key); big.push_back('\0'); big.append(val); pk = big; }
+        bit = place_pair_.find(pk, kMiss);
+        if (bit == kMiss) bit = EncodeCaches::kPlaceUnsat;
+      } else {
+        bit = place_key_.find(key, kMiss);
+        if (bit == kMiss) bit = place_any_bit_;   // no worker carries this key: any labelled worker passes
+      }
+      if (bit == EncodeCaches::kPlaceUnsat) flags |= JF_PLACE_UNSAT;
+      else place[bit >> 6] |= 1ull << (bit & 63);
     }
-    place[bit >> 6] |= 1ull << (bit & 63);
+    if (!special) ce = EncodeCaches::LabelEntry{key.data(), val.data(), (uint32_t)key.size(), (uint32_t)val.size(), lset, lclear, bit};
   }
   out.lab_mask[j] = lab;
   out.place_lo[j] = place[0];
@@ -1327,8 +1359,8 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
 }
 
 void Host::encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
-                        std::vector<uint32_t>& misses) const {
-  auto cc = std::make_unique<EncodeCaches>();   // ~56 KB, per chunk
+                        std::vector<uint32_t>& misses, std::unique_ptr<EncodeCaches>& cc) const {
+  if (!cc) cc = std::make_unique<EncodeCaches>();   // ~250 KB, one per worker thread for the duration of the call
   for (uint32_t j = a; j < b; ++j) {
     bool miss = false;
     encode_job(env, j, out, miss, *cc);
@@ -1341,10 +1373,11 @@ int Host::encode(const cordum_envelopes* env, HostColumns& out, std::string& err
   std::lock_guard<std::mutex> g(mu_);
   const uint32_t n = env->n_jobs;
   std::vector<std::vector<uint32_t>> misses(threads_);
-  if (n < 8192 || threads_ <= 1) encode_range(env, 0, n, out, misses[0]);
+  std::vector<std::unique_ptr<EncodeCaches>> caches(threads_);   // span-identity caches are only valid within this call
+  if (n < 8192 || threads_ <= 1) encode_range(env, 0, n, out, misses[0], caches[0]);
   else {
     if (!pool_) pool_ = std::make_unique<WorkPool>(threads_);
-    pool_->parallel_for(n, 2048, [&](uint32_t a, uint32_t b, uint32_t w) { encode_range(env, a, b, out, misses[w]); });
+    pool_->parallel_for(n, 2048, [&](uint32_t a, uint32_t b, uint32_t w) { encode_range(env, a, b, out, misses[w], caches[w]); });
   }
   // dictionary misses: register the new topics / effective configs, then re-encode just those jobs
   for (auto& lst : misses)
@@ -1354,8 +1387,8 @@ int Host::encode(const cordum_envelopes* env, HostColumns& out, std::string& err
       sv eff = span(env, env->effective_config, j);
       if (!eff.empty() && add_effcfg(eff) == kMiss) { err = "effective-config dictionary full (max_effcfgs)"; return CORDUM_E_CAPACITY; }
       bool miss = false;
-      EncodeCaches cc;
-      encode_job(env, j, out, miss, cc);
+      if (!caches[0]) caches[0] = std::make_unique<EncodeCaches>();
+      encode_job(env, j, out, miss, *caches[0]);
     }
   return CORDUM_OK;
 }

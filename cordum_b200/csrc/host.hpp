@@ -312,7 +312,7 @@ class Host {
   void eff_topic_fill(uint32_t cfg, uint32_t topic_id);
   void topic_words_append(const uint32_t* row);
   void encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
-                    std::vector<uint32_t>& misses) const;
+                    std::vector<uint32_t>& misses, std::unique_ptr<struct EncodeCaches>& cc) const;
   void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss, struct EncodeCaches& cc) const;
 };
 
