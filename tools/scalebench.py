@@ -4,7 +4,8 @@ Variants (all: K steps, wall clock between synchronizes, max over ranks):
    dispatch      resident dispatch only (no heartbeat epoch)
    ingest        H2D slice + set_loads_device (no collective) + dispatch
    allgather     the collective alone
-   full          H2D slice + all-gather + set_loads_device + dispatch (= bench.py's step)
+   full          H2D slice + all-gather + set_loads_device + dispatch on one ingest stream
+   full2         the same with two alternating ingest streams and buffers (= bench.py's step)
 """
 import os
 import sys
@@ -44,6 +45,8 @@ w0, w1 = shard.worker_range(rank, world, W)
 host = torch.from_numpy(cfg.workers.loads()[w0:w1].view(np.uint8).reshape(-1, 16).copy()).pin_memory()
 full_host = torch.from_numpy(cfg.workers.loads().view(np.uint8).reshape(-1, 16).copy()).pin_memory()
 send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
+send2 = [torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
+ingest = [torch.cuda.Stream(), torch.cuda.Stream()]
 full_dev = torch.empty((W, 16), dtype=torch.uint8, device="cuda")
 full_dev.copy_(full_host)
 recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
@@ -68,6 +71,11 @@ def run(variant, K):
             buf = shard.gather_loads(send, out=recv[k % 2]) if world > 1 else send
             if variant == "full":
                 eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)
+        elif variant == "full2":
+            with torch.cuda.stream(ingest[k % 2]):
+                send2[k % 2].copy_(host, non_blocking=True)
+                buf = shard.gather_loads(send2[k % 2], out=recv[k % 2]) if world > 1 else send2[k % 2]
+                eng.set_loads_device(buf.data_ptr(), W, ingest[k % 2].cuda_stream)
         elif variant == "ingest":
             send.copy_(host, non_blocking=True)
             eng.set_loads_device(full_dev.data_ptr(), W, stream.cuda_stream)
@@ -77,7 +85,7 @@ def run(variant, K):
     return th
 
 
-for variant in ("dispatch", "ingest", "allgather", "full", "full"):
+for variant in ("dispatch", "ingest", "allgather", "full", "full2", "full", "full2"):
     run(variant, 10)
     sync()
     K = 200
