@@ -208,17 +208,25 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         d["cpu_load"] = (rng.random(w1 - w0) * 100).astype(np.float32)
         d["gpu_utilization"] = (rng.random(w1 - w0) * 100).astype(np.float32)
         delta_sets.append(torch.from_numpy(d.view(np.uint8).reshape(-1, 16).copy()).pin_memory())
-    send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
-    recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
     stream = torch.cuda.current_stream()
+    if args.exchange == "engine":
+        # the engine owns the exchange (cordum_exchange_init / cordum_workers_ingest): what a Go host would call
+        if world > 1:
+            box = [engine.Engine.exchange_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            eng.exchange_init(box[0], rank, world)
+    else:
+        send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
+        recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
 
     def step(k: int, batch, resident: bool):
-        send.copy_(delta_sets[k % n_delta_sets], non_blocking=True)          # heartbeat ingest: pinned host -> HBM
-        if world > 1:
-            buf = shard.gather_loads(send, out=recv[k % 2])                   # the one exchange step
+        if args.exchange == "engine":
+            # heartbeat ingest (pinned host -> HBM) + NCCL all-gather of the per-rank slices + refresh
+            eng.ingest(delta_sets[k % n_delta_sets].data_ptr(), w0, w1 - w0)
         else:
-            buf = send
-        eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)           # D2D + worker_chunk_kernel + worker_merge_kernel
+            send.copy_(delta_sets[k % n_delta_sets], non_blocking=True)
+            buf = shard.gather_loads(send, out=recv[k % 2]) if world > 1 else send   # torch.distributed all-gather
+            eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)
         if resident:
             batch.dispatch_resident_async(wire.MODE_POLICY_AND_ROUTE)
         else:
@@ -265,6 +273,35 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # (same jobs; only the load table changed, so compare policy fields)
     chk = batches[(args.warmup + args.steps - 1) % n_rot].fetch()
     assert np.array_equal(chk["decision"], ref_result["decision"]) and np.array_equal(chk["rule_idx"], ref_result["rule_idx"])
+
+    # parity of the sharded path, exchange included: one more epoch with a known delta set, then the first jobs of
+    # rank 0's shard against the oracle evaluated on the table all ranks' slices add up to (checker only, untimed)
+    parity = None
+    k_chk = 3
+    step(k_chk, batches[0], True)
+    sync_all()
+    if rank == 0:
+        import oracle_lib
+        full = base.copy()
+        for r in range(world):
+            r0, r1 = shard.worker_range(r, world, W)
+            rr = np.random.default_rng(1000 + r)
+            for s_ in range(k_chk % n_delta_sets + 1):   # replay rank r's generator up to the set in use
+                act = rr.integers(0, 9, r1 - r0)
+                cpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
+                gpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
+            full["active_jobs"][r0:r1] = act
+            full["cpu_load"][r0:r1] = cpu_
+            full["gpu_utilization"][r0:r1] = gpu_
+        n_chk = min(2000, n_shard)
+        o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+        o.update_workers(np.arange(W, dtype=np.uint32), full)
+        want = o.eval(my_jobs, wire.MODE_POLICY_AND_ROUTE, threads=4, first=0, count=n_chk)
+        got = batches[0].fetch()[:n_chk]
+        fields = ("decision", "sched_decision", "flags", "route_status", "reason_code", "rule_idx", "worker_slot")
+        bad = [f for f in fields if not np.array_equal(got[f], want[f])]
+        assert not bad, "sharded path differs from the oracle in %s" % bad
+        parity = {"jobs_checked": int(n_chk), "fields": list(fields), "ok": True}
 
     # ---------------------------------------------------------------- per-kernel durations for the roofline
     # Serialized launches (wait after every step) so the CUDA-event span of a kernel contains that kernel only;
@@ -348,7 +385,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                    "jobs_per_rank": n_shard, "parallelism": "jobs sharded by index x%d, tables replicated" % world,
                    "l2": "inputs larger than L2: steps rotate over %d resident copies of the shard (%.0f MB total)" % (
                        n_rot, n_rot * shard_bytes / 1e6),
-                   "step": "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else "")},
+                   "step": "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else ""),
+                   "exchange": args.exchange},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(n_shard * in_b + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
@@ -362,6 +400,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                      "whole_path": {"algorithmic_bytes": int(path_bytes), "kernels_ms": k_ms + r_ms, "achieved": path_gbs,
                                     "frac": path_gbs / peak}},
         "cpu_baseline": cpu,
+        "parity_check": parity,
     }
     print(json.dumps(line), flush=True)
     for b in batches:
@@ -378,6 +417,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cordum_b200", choices=["cordum_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="engine", choices=["engine", "torch"],
+                    help="heartbeat exchange: the engine's own NCCL communicator (cordum_workers_ingest) or "
+                         "torch.distributed all_gather + cordum_workers_set_loads_device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(HERE, "libcordum_b200.so")
 API = [
     "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
     "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
-    "cordum_workers_set_loads_device", "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
+    "cordum_workers_set_loads_device", "cordum_exchange_unique_id", "cordum_exchange_init", "cordum_workers_ingest",
+    "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
@@ -49,6 +50,9 @@ def load() -> C.CDLL:
     L.cordum_workers_load.argtypes = [vp, vp]
     L.cordum_workers_update.argtypes = [vp, u32, vp, vp]
     L.cordum_workers_set_loads_device.argtypes = [vp, vp, u32, vp]
+    L.cordum_exchange_unique_id.argtypes = [vp]
+    L.cordum_exchange_init.argtypes = [vp, vp, i32, i32]
+    L.cordum_workers_ingest.argtypes = [vp, vp, u32, u32]
     L.cordum_batch_alloc.argtypes = [vp, u32, C.POINTER(vp)]
     L.cordum_batch_free.argtypes = [vp]
     L.cordum_batch_free.restype = None

@@ -2,9 +2,11 @@
 // (include/cordum_b200.h).  The product has NO CPU evaluation path: every decision
 // record is produced by kernels.cu; without a CUDA device engine creation fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -66,7 +68,14 @@ struct cordum_engine {
   std::mutex mu;                 // serialises table sync
   bool failed = false;           // sticky CUDA failure
   std::string fail_msg;
-  cudaStream_t s_tables = nullptr, s_copy = nullptr;
+  cudaStream_t s_tables = nullptr, s_copy = nullptr, s_xchg = nullptr;
+  // engine-owned heartbeat exchange (cordum_exchange_init / cordum_workers_ingest)
+  void* nccl_comm = nullptr;
+  int xrank = 0, xworld = 1;
+  uint64_t xepoch = 0;
+  DevBuf gather[2];                              // gathered load tables, alternating per epoch
+  cudaEvent_t gather_free[2] = {nullptr, nullptr};   // recorded once the refresh has consumed the table
+  cudaEvent_t ev_xchg = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_prod = nullptr;
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
@@ -402,6 +411,88 @@ static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resourc
 }
 
 
+// ------------------------------------------------------------ NCCL, loaded at run time
+// The library must not depend on libnccl at link time (single-GPU hosts do not need it), and inside a PyTorch process it
+// has to use the copy PyTorch already loaded.  Prototypes restated from nccl.h (2.x ABI).
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclUint8 = 1;   // ncclDataType_t: ncclInt8 = 0, ncclUint8 = 1
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[3] = {getenv("CORDUM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      if (void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) { api.lib = h; break; }
+    }
+    if (!api.lib) return;
+    api.GetUniqueId = (int (*)(NcclId*))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+    api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) { dlclose(api.lib); api = NcclApi{}; }
+  });
+  return api.lib ? &api : nullptr;
+}
+int nccl_fail(cordum_engine* e, int rc, const char* what) {
+  NcclApi* a = nccl_api();
+  g_err = std::string(what) + ": NCCL error " + std::to_string(rc) + (a && a->GetErrorString ? std::string(" (") + a->GetErrorString(rc) + ")" : "");
+  if (e) { e->failed = true; e->fail_msg = g_err; }
+  return CORDUM_E_CUDA;
+}
+
+// One heartbeat epoch through the engine-owned exchange.  Called with both mutexes held.
+int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice) {
+  const HostTables& t = e->host->tables();
+  const uint32_t W = t.n_slots;
+  if (W == 0) { g_err = "no workers loaded"; return CORDUM_E_STATE; }
+  const uint32_t per = W / (uint32_t)e->xworld;
+  if (W % (uint32_t)e->xworld) { g_err = "worker registry size is not a multiple of the exchange world size"; return CORDUM_E_INVALID; }
+  if (first_slot != (uint32_t)e->xrank * per || n_slice != per) { g_err = "slice is not this rank's share of the worker registry"; return CORDUM_E_INVALID; }
+  const int g = (int)(e->xepoch & 1);
+  e->xepoch++;
+  const size_t bytes = (size_t)W * sizeof(Load16), slice_bytes = (size_t)per * sizeof(Load16);
+  if (e->gather[g].cap < bytes) {   // first use / registry grew: nothing may still read the old buffer
+    CK(cudaDeviceSynchronize(), "sync before gather buffer allocation");
+    CK(e->gather[g].reserve(bytes), "alloc gather buffer");
+  }
+  uint8_t* table = (uint8_t*)e->gather[g].p;
+  // the refresh two epochs ago read this buffer
+  CK(cudaStreamWaitEvent(e->s_xchg, e->gather_free[g], 0), "wait gather buffer");
+  CK(cudaMemcpyAsync(table + (size_t)first_slot * sizeof(Load16), slice, slice_bytes, cudaMemcpyHostToDevice, e->s_xchg), "H2D heartbeat slice");
+  if (e->xworld > 1) {   // in place: this rank's slice already sits at its offset of the receive buffer
+    int rc = nccl_api()->AllGather(table + (size_t)first_slot * sizeof(Load16), table, slice_bytes, kNcclUint8, e->nccl_comm, e->s_xchg);
+    if (rc) return nccl_fail(e, rc, "ncclAllGather");
+  }
+  CK(cudaEventRecord(e->ev_xchg, e->s_xchg), "event record");
+  const int target = (e->cur + 1) % kSets;
+  auto& D = e->ds[target];
+  for (cordum_batch* b : e->batches)   // route kernels that still read the target set
+    if (b->launched && b->table_set == target) { CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait route"); b->launched = false; }
+  CK(cudaStreamWaitEvent(e->s_tables, e->ev_xchg, 0), "order refresh after exchange");
+  DeviceTables tv = view(e, target);
+  tv.loads = (const Load16*)table;   // the refresh reads the gathered table in place
+  CK(launch_worker_pools(tv, e->s_tables, e->gather_free[g]), "worker-table refresh kernels");
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
+  CK(cudaEventRecord(D.ready, e->s_tables), "event record");
+  e->cur = target;
+  e->pools_dirty = false;
+  e->host_loads = false;
+  return CORDUM_OK;
+}
+}  // namespace
+
 // ============================================================ C ABI
 extern "C" {
 
@@ -435,6 +526,12 @@ int32_t cordum_engine_create(const cordum_engine_opts* opts, cordum_engine** out
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range");
       CK(cudaStreamCreateWithPriority(&e->s_tables, cudaStreamNonBlocking, hi), "stream");
       CK(cudaStreamCreateWithPriority(&e->s_copy, cudaStreamNonBlocking, hi), "stream");
+      CK(cudaStreamCreateWithPriority(&e->s_xchg, cudaStreamNonBlocking, hi), "stream");
+      for (auto& ev : e->gather_free) {
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+        CK(cudaEventRecord(ev, e->s_xchg), "event");
+      }
+      CK(cudaEventCreateWithFlags(&e->ev_xchg, cudaEventDisableTiming), "event");
     }
     for (auto& D : e->ds) {
       CK(cudaEventCreateWithFlags(&D.ready, cudaEventDisableTiming), "event");
@@ -476,6 +573,11 @@ void cordum_engine_destroy(cordum_engine* e) {
   if (e->ev_prod) cudaEventDestroy(e->ev_prod);
   if (e->s_tables) cudaStreamDestroy(e->s_tables);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  if (e->nccl_comm && nccl_api()) nccl_api()->CommDestroy(e->nccl_comm);
+  for (auto& b : e->gather) b.release();
+  for (auto& ev : e->gather_free) if (ev) cudaEventDestroy(ev);
+  if (e->ev_xchg) cudaEventDestroy(e->ev_xchg);
+  if (e->s_xchg) cudaStreamDestroy(e->s_xchg);
   delete e;
 }
 
@@ -526,6 +628,48 @@ int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint
   int rc = sync_tables(e);
   if (rc) return rc;
   return refresh_pools(e, dptr, (cudaStream_t)stream);
+}
+
+int32_t cordum_exchange_unique_id(char id[CORDUM_EXCHANGE_ID_BYTES]) {
+  if (!id) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  NcclApi* a = nccl_api();
+  if (!a) { g_err = "libnccl not found (set CORDUM_NCCL_LIB)"; return CORDUM_E_STATE; }
+  NcclId u;
+  int rc = a->GetUniqueId(&u);
+  if (rc) return nccl_fail(nullptr, rc, "ncclGetUniqueId");
+  std::memcpy(id, u.internal, CORDUM_EXCHANGE_ID_BYTES);
+  return CORDUM_OK;
+}
+
+int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_BYTES], int32_t rank, int32_t world) {
+  if (!e || !id || world < 1 || rank < 0 || rank >= world) { g_err = "bad argument"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->nccl_comm) { g_err = "exchange already initialised"; return CORDUM_E_STATE; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  if (world > 1) {
+    NcclApi* a = nccl_api();
+    if (!a) { g_err = "libnccl not found (set CORDUM_NCCL_LIB)"; return CORDUM_E_STATE; }
+    NcclId u;
+    std::memcpy(u.internal, id, CORDUM_EXCHANGE_ID_BYTES);
+    void* comm = nullptr;
+    int rc = a->CommInitRank(&comm, world, u, rank);
+    if (rc) return nccl_fail(e, rc, "ncclCommInitRank");
+    e->nccl_comm = comm;
+  }
+  e->xrank = rank; e->xworld = world;
+  return CORDUM_OK;
+}
+
+int32_t cordum_workers_ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice) {
+  if (!e || !slice) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<std::mutex> gh(e->host->mutex());
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  int rc = sync_tables(e);
+  if (rc) return rc;
+  return ingest(e, slice, first_slot, n_slice);
 }
 
 int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out) {

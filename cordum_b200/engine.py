@@ -155,6 +155,28 @@ class Engine:
     def set_loads_device(self, dptr: int, n_workers: int, stream: int = 0):
         self._ck(self.L.cordum_workers_set_loads_device(self.h, C.c_void_p(dptr), n_workers, C.c_void_p(stream)))
 
+    # ---- engine-owned multi-GPU heartbeat exchange (include/cordum_b200.h: cordum_exchange_*)
+    @staticmethod
+    def exchange_unique_id() -> bytes:
+        """Rank 0 creates the id and ships the 128 bytes to the other ranks (any transport)."""
+        L = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = L.cordum_exchange_unique_id(buf)
+        if rc:
+            raise CordumError(rc, L.cordum_last_error().decode("utf-8", "replace"))
+        return buf.raw
+
+    def exchange_init(self, unique_id: bytes, rank: int, world: int):
+        """Collective: every rank calls it with the same id; blocks until all have joined."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.L.cordum_exchange_init(self.h, buf, rank, world))
+
+    def ingest(self, slice_ptr: int, first_slot: int, n_slice: int):
+        """One heartbeat epoch: this rank's slice of 16 B load records (host pointer, pinned for an asynchronous
+        copy) -> device, all-gather across ranks, worker-table refresh.  Returns once enqueued."""
+        self._ck(self.L.cordum_workers_ingest(self.h, C.c_void_p(slice_ptr), first_slot, n_slice))
+
     def snapshots(self) -> list[str]:
         buf = C.create_string_buffer(1 << 16)
         n = C.c_uint32()

@@ -212,6 +212,24 @@ int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slot
 int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint32_t n_workers,
                                         void* stream);
 
+/* ---- multi-GPU heartbeat exchange owned by the engine (BASELINE config 4).
+ * One process per GPU; jobs are sharded by the caller, the worker registry is replicated, and each
+ * rank ingests the heartbeats of its own contiguous slice of worker slots.  The engine keeps the
+ * NCCL communicator (libnccl is loaded at run time: $CORDUM_NCCL_LIB, else libnccl.so.2), so a host
+ * that is not a PyTorch process (the Go scheduler) gets the same path.
+ *   rank 0: cordum_exchange_unique_id(id)   -> ship the 128 bytes to the other ranks (any transport)
+ *   all   : cordum_exchange_init(e, id, rank, world)        collective, blocks until all ranks joined
+ *   per heartbeat epoch, all ranks: cordum_workers_ingest(e, loads_of_my_slice, first_slot, n)
+ * cordum_workers_ingest copies the slice to the device (pinned host memory makes the copy
+ * asynchronous), all-gathers the 16 B/worker records of all ranks in place, and refreshes the worker
+ * tables from the gathered table; it returns once the work is enqueued.  The registry must divide
+ * evenly: slice of rank r = slots [r * n_slots/world, (r+1) * n_slots/world).  Without
+ * cordum_exchange_init (world = 1) the slice must be the whole table. */
+#define CORDUM_EXCHANGE_ID_BYTES 128
+int32_t cordum_exchange_unique_id(char id[CORDUM_EXCHANGE_ID_BYTES]);
+int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_BYTES], int32_t rank, int32_t world);
+int32_t cordum_workers_ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice);
+
 /* Library-owned pinned SoA slabs for up to max_jobs jobs. */
 int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out);
 void cordum_batch_free(cordum_batch* b);

@@ -120,6 +120,33 @@ def test_device_load_table_path(eng):
     b.free()
 
 
+def test_engine_owned_ingest_single_rank(eng):
+    """cordum_workers_ingest without an exchange (world = 1): the slice is the whole registry; it must be this rank's
+    share exactly, epochs alternate between two gather buffers, and results follow the ingested loads."""
+    cfg = synth.make_config("tiny")
+    load(eng, cfg.policy, cfg.routing, cfg.workers)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    rng = np.random.default_rng(4)
+    n = cfg.workers.n_workers
+    b = eng.batch(cfg.jobs.n_jobs)
+    b.encode(cfg.jobs)
+    keep = []
+    for epoch in range(5):
+        loads = cfg.workers.loads()
+        loads["active_jobs"] = rng.integers(0, 9, n)
+        loads["cpu_load"] = (rng.random(n) * 100).astype(np.float32)
+        loads["gpu_utilization"] = (rng.random(n) * 100).astype(np.float32)
+        keep.append(loads)                       # the host buffer must stay alive until the copy has run
+        eng.ingest(loads.ctypes.data, 0, n)
+        o.update_workers(np.arange(n, dtype=np.uint32), loads)
+        assert_same(b.dispatch(), o.eval(cfg.jobs), "ingest epoch %d" % epoch)
+    with pytest.raises(Exception):
+        eng.ingest(keep[0].ctypes.data, 0, n - 1)
+    with pytest.raises(Exception):
+        eng.ingest(keep[0].ctypes.data, 1, n)
+    b.free()
+
+
 @pytest.mark.parametrize("n_big,coarse", [(512, False), (513, True), (1500, True), (5000, False), (8192, True), (8800, False)])
 def test_pool_sizes_across_refresh_paths(eng, n_big, coarse):
     """Worker-table refresh paths by pool size: one chunk (<= 512 workers, finished by worker_chunk_kernel), several
