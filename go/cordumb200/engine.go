@@ -85,6 +85,41 @@ func (e *Engine) LoadRouting(topics map[string][]string, pools map[string][]stri
 	return nil
 }
 
+// ---- multi-GPU: one scheduler process per GPU, jobs sharded by the queue group, registry replicated.
+// Rank 0 calls ExchangeID and ships the 128 bytes to the other ranks (e.g. through the config KV the
+// schedulers already share); every rank then calls JoinExchange (collective).  Per heartbeat epoch each
+// rank hands IngestHeartbeats the loads of ITS slice of worker slots (the heartbeat fan-in is sharded by
+// slot): the engine copies them to the GPU, all-gathers the slices over NCCL and refreshes its tables.
+
+// ExchangeID mirrors ncclGetUniqueId.
+func ExchangeID() ([]byte, error) {
+	id := make([]byte, C.CORDUM_EXCHANGE_ID_BYTES)
+	if rc := C.cordum_exchange_unique_id((*C.char)(unsafe.Pointer(&id[0]))); rc != 0 {
+		return nil, lastErr()
+	}
+	return id, nil
+}
+
+// JoinExchange blocks until all `world` ranks have joined.
+func (e *Engine) JoinExchange(id []byte, rank, world int) error {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.cordum_exchange_init(e.h, (*C.char)(unsafe.Pointer(&id[0])), C.int32_t(rank), C.int32_t(world)); rc != 0 {
+		return lastErr()
+	}
+	return nil
+}
+
+// IngestHeartbeats takes the {active_jobs, max_parallel_jobs, cpu_load, gpu_utilization} records of this
+// rank's slots [first, first+len(loads)), in slot order (registry_memory.go:43-51 keeps the latest heartbeat
+// per worker).  loads must live in C memory (C.malloc / cudaHostAlloc) until the next call.
+func (e *Engine) IngestHeartbeats(loads *C.cordum_worker_load, first, n int) error {
+	if rc := C.cordum_workers_ingest(e.h, loads, C.uint32_t(first), C.uint32_t(n)); rc != 0 {
+		return lastErr()
+	}
+	return nil
+}
+
 // arena packs Go strings into one C-allocated byte slab + (off,len) spans.  Nothing Go-allocated is
 // retained by C after a call returns (cgo pointer rule): the slab is freed by the caller.
 type arena struct {
