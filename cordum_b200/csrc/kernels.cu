@@ -444,8 +444,8 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
 //      pool's label bitmaps over its load-sorted view (lane = 32 workers); first set bit in the non-overloaded
 //      prefix = argmin, the next match decides the tie flag, popcount = candidate total.
 //   S' jobs that touch a pool larger than K2's sort buffer: warp per job, coalesced scan (rare).
-template <bool ROUTE_ONLY>
-__global__ void __launch_bounds__(256, 4) route_kernel(KParams P) {
+template <bool ROUTE_ONLY, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
   const DeviceTables& T = P.t;
   const JobColumns& C = P.cols;
   const unsigned lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
@@ -684,7 +684,8 @@ static cudaError_t configure_kernels() {
   const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
                        (const void*)policy_kernel<4, 1>, (const void*)policy_kernel<5, 1>, (const void*)policy_kernel<4, 2>,
                        (const void*)policy_kernel<5, 2>, (const void*)policy_kernel<3, 4>, (const void*)policy_kernel<4, 4>,
-                       (const void*)route_kernel<true>, (const void*)route_kernel<false>};
+                       (const void*)route_kernel<true>, (const void*)route_kernel<false>,
+                       (const void*)route_kernel<false, 3>, (const void*)route_kernel<false, 5>};
   for (const void* f : fns) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
@@ -732,8 +733,11 @@ cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
 cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
-  const uint32_t blocks = grid_for(P.n_jobs, sm_count, 4);
+  static const int minb = []() { const char* v = getenv("CORDUM_ROUTE_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
+  const uint32_t blocks = grid_for(P.n_jobs, sm_count, route_only ? 4 : minb);
   if (route_only) route_kernel<true><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 3) route_kernel<false, 3><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 5) route_kernel<false, 5><<<blocks, 256, 0, s>>>(P);
   else route_kernel<false><<<blocks, 256, 0, s>>>(P);
   return cudaGetLastError();
 }
