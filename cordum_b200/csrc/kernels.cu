@@ -346,25 +346,31 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
           w[4 * u] = have ? acc[u].x : 0u; w[4 * u + 1] = have ? acc[u].y : 0u;
           w[4 * u + 2] = have ? acc[u].z : 0u; w[4 * u + 3] = have ? acc[u].w : 0u;
         }
-        while (true) {
+        bool alive;   // this lane still has a surviving bit whose rule has not passed its subset test
+        do {
           uint32_t sel = 0, base = 0;   // lowest non-zero 32-bit word of the item
 #pragma unroll
           for (int k = 4 * IU - 1; k >= 0; --k) if (w[k]) { sel = w[k]; base = 32u * (uint32_t)k; }
           const bool nz = sel != 0;
-          if (!__any_sync(FULL, nz)) break;
-          const uint32_t pos = nz ? wi * 128u + base + (uint32_t)__ffs((int)sel) - 1u : 0u;
-          const uint32_t r = __ldg(T.pos2rule + pos);
-          bool ok = nz;
-          if (nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u)) {
-            const uint64_t req = __ldg(C.req_mask + jsrc), lab = __ldg(C.lab_mask + jsrc);
-            const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
-            ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
-          }
-          if (ok) best = r;
-          const uint32_t drop = sel & (sel - 1);   // the selected word without the bit just handled
+          alive = false;
+          if (__any_sync(FULL, nz)) {
+            const uint32_t pos = nz ? wi * 128u + base + (uint32_t)__ffs((int)sel) - 1u : 0u;
+            const uint32_t r = __ldg(T.pos2rule + pos);
+            bool ok = nz;
+            if (nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u)) {
+              const uint64_t req = __ldg(C.req_mask + jsrc), lab = __ldg(C.lab_mask + jsrc);
+              const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
+              ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
+            }
+            if (ok) best = r;
+            alive = nz && !ok;
+            if (alive) {   // drop the bit just handled and look at the next one (rare)
+              const uint32_t drop = sel & (sel - 1);
 #pragma unroll
-          for (int k = 0; k < 4 * IU; ++k) w[k] = ok ? 0u : ((nz && base == 32u * (uint32_t)k) ? drop : w[k]);
-        }
+              for (int k = 0; k < 4 * IU; ++k) if (base == 32u * (uint32_t)k) w[k] = drop;
+            }
+          }
+        } while (__any_sync(FULL, alive));
         if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
       }
       __syncwarp();

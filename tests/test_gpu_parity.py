@@ -191,6 +191,25 @@ def test_pool_sizes_across_refresh_paths(eng, n_big, coarse):
     b.free()
 
 
+def test_many_risk_tags(eng):
+    """Jobs with up to seven referenced risk tags (policy_kernel reads three risk rows branch-free, the rest loop)."""
+    rng = np.random.default_rng(12)
+    tags = ["t%d" % i for i in range(10)]
+    rules = [{"id": "r%d" % i, "decision": ["deny", "require_approval", "throttle"][i % 3], "reason": "x",
+              "match": {"topics": ["job.a.*"], "risk_tags": [tags[i % 10], tags[(i * 3 + 1) % 10]]}} for i in range(40)]
+    policy = {"default_tenant": "default", "rules": rules}
+    jobs = []
+    for n in range(0, 8):
+        for _ in range(40):
+            jobs.append({"topic": "job.a.x", "meta": {"risk_tags": [str(x) for x in rng.choice(tags, size=n, replace=False)]}})
+    load(eng, policy, {"topics": {}, "pools": {}}, [])
+    b = eng.batch(len(jobs))
+    got = b.encode(jobs).dispatch(wire.MODE_POLICY_ONLY).copy()
+    assert_same(got, oracle_lib.Oracle(policy, {"topics": {}, "pools": {}}, []).eval(jobs, wire.MODE_POLICY_ONLY), "many risk tags")
+    assert len(set(got["rule_idx"].tolist())) > 5
+    b.free()
+
+
 def test_many_placement_labels(eng):
     """More than four placement labels on a job (route_kernel keeps four bitmap rows in registers, the rest loop)."""
     rng = np.random.default_rng(11)
