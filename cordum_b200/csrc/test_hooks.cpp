@@ -73,6 +73,7 @@ int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint
   VEC("pool_off", t.pool_off) VEC("pos_pool", t.pos_pool) VEC("pos_slot", t.pos_slot) VEC("pos_rank", t.pos_rank)
   VEC("slot_pos", t.slot_pos) VEC("rank_slot", t.rank_slot) VEC("pos_label_lo", t.pos_label_lo)
   VEC("pos_label_hi", t.pos_label_hi) VEC("loads", t.loads)
+  VEC("chunk_pool", t.chunk_pool) VEC("pool_chunk0", t.pool_chunk0) VEC("merge_list", t.merge_list)
 #undef VEC
   t_err = "unknown table " + n;
   return -1;
@@ -83,6 +84,9 @@ uint64_t cordum_test_host_scalar(void* h, const char* name) {
   if (n == "n_rules") return t.n_rules;
   if (n == "n_seg") return t.n_seg;
   if (n == "item_u4") return t.item_u4;
+  if (n == "n_chunks") return t.n_chunks;
+  if (n == "n_merge") return t.n_merge;
+  if (n == "merge_smem") return t.merge_smem;
   if (n == "row_words") return t.row_words;
   if (n == "mcp_stride") return t.mcp_stride;
   if (n == "topic_stride") return t.topic_stride;

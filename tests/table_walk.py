@@ -33,8 +33,9 @@ TABLES = {
     "pool_list": np.uint32, "pool_req_mask": np.uint64, "pool_req_nonempty": np.uint8, "pool_off": np.uint32,
     "pos_pool": np.uint32, "pos_slot": np.uint32, "pos_rank": np.uint32, "slot_pos": np.uint32, "rank_slot": np.uint32,
     "pos_label_lo": np.uint64, "pos_label_hi": np.uint64, "loads": wire.LOAD_DTYPE,
+    "chunk_pool": np.uint32, "pool_chunk0": np.uint32, "merge_list": np.uint32,
 }
-SCALARS = ["n_rules", "n_seg", "item_u4", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
+SCALARS = ["n_rules", "n_seg", "item_u4", "n_chunks", "n_merge", "merge_smem", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
            "n_pos", "n_slots", "n_topics"]
 
 

@@ -115,3 +115,34 @@ def test_capacity_errors_fail_closed():
     with pytest.raises(RuntimeError, match="64 distinct risk tags"):
         h.load_policy({"rules": rules})
     h.load_policy({"rules": rules[:64]})   # exactly at capacity is fine
+
+
+@pytest.mark.parametrize("sizes", [[0], [1], [512], [513], [1500, 3, 0, 600], [8192, 8193], [20000]])
+def test_refresh_work_list(sizes):
+    """Chunk table of the worker-table refresh (tables.h): every pool owns ceil(n/512) chunks (an empty pool one, empty,
+    chunk); worker_merge_kernel runs all chunks of a multi-chunk pool up to 8192 workers and chunk 0 of larger pools."""
+    workers, pools = [], {}
+    for p, n in enumerate(sizes):
+        pools["p%d" % p] = {}
+        workers += [kats.hb("w-%d-%05d" % (p, i), "p%d" % p) for i in range(n)]
+    routing = {"topics": {"job.x": list(pools)}, "pools": pools}
+    h = table_walk.HostHarness(None, routing, workers)
+    T = h.tables()
+    off = T["pool_off"]
+    assert [int(off[p + 1] - off[p]) for p in range(len(sizes))] == sizes
+    want_chunks, want_merge, smem = [], [], 0
+    for p, n in enumerate(sizes):
+        m = max(1, -(-n // 512))
+        g0 = len(want_chunks)
+        assert int(T["pool_chunk0"][p]) == g0
+        want_chunks += [p] * m
+        if n > 8192:
+            want_merge.append(g0)
+        elif m > 1:
+            want_merge += list(range(g0, g0 + m))
+            smem = max(smem, n * 8)
+    assert int(T["pool_chunk0"][len(sizes)]) == len(want_chunks) == int(T["n_chunks"])
+    assert T["chunk_pool"][:len(want_chunks)].tolist() == want_chunks
+    assert int(T["n_merge"]) == len(want_merge) and T["merge_list"][:len(want_merge)].tolist() == want_merge
+    assert int(T["merge_smem"]) == smem <= 8192 * 8
+    h.close()
