@@ -212,10 +212,20 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     if args.exchange == "engine":
         # the engine owns the exchange (cordum_exchange_init / cordum_workers_ingest): what a Go host would call
         if world > 1:
-            box = [engine.Engine.exchange_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            eng.exchange_init(box[0], rank, world)
-    else:
+            ok = 1
+            try:
+                box = [engine.Engine.exchange_unique_id() if rank == 0 else None]
+            except Exception as ex:   # libnccl not loadable from the engine: every rank falls back together
+                print("engine exchange unavailable (%s): using torch.distributed" % ex, file=sys.stderr)
+                box, ok = [None], 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.broadcast(flag, src=0)
+            if int(flag.item()):
+                dist.broadcast_object_list(box, src=0)
+                eng.exchange_init(box[0], rank, world)
+            else:
+                args.exchange = "torch"
+    if args.exchange != "engine":
         send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
         recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
 
