@@ -206,9 +206,12 @@ int32_t cordum_workers_load(cordum_engine* e, const cordum_workers* w);
 int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slots,
                               const cordum_worker_load* loads);
 /* Same, but the full slot-ordered load table is already on the device (e.g. the
- * receive buffer of the NCCL all-gather of per-rank slices).
+ * receive buffer of a host-side all-gather of per-rank slices).
  * dptr: n_workers x cordum_worker_load on this engine's device; stream: cudaStream_t
- * the data was produced on (0 = legacy default). */
+ * the data was produced on (0 = legacy default).  The engine copies the table on a
+ * stream of its own, ordered after `stream`; work submitted to `stream` after this
+ * call returns is ordered after that copy, so the buffer may be refilled there.
+ * Asynchronous: returns once the copy and the table refresh are enqueued. */
 int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint32_t n_workers,
                                         void* stream);
 
