@@ -1174,7 +1174,7 @@ inline bool placement_skips(sv k) {
 }
 // mcp label aliases (kernel.go:400-403): field*3 + variant, or -1
 inline int mcp_key(sv k) {
-  if (k.size() < 8 || k[0] != 'm' || k[1] != 'c' || k[2] != 'p') return -1;
+  if (k.size() < 7 || k[0] != 'm' || k[1] != 'c' || k[2] != 'p') return -1;   // shortest alias: "mcpTool"
   static const char* names[12] = {"mcp.server", "mcp_server", "mcpServer", "mcp.tool", "mcp_tool", "mcpTool",
                                   "mcp.resource", "mcp_resource", "mcpResource", "mcp.action", "mcp_action", "mcpAction"};
   for (int i = 0; i < 12; ++i) if (k == names[i]) return i;
