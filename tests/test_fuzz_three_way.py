@@ -56,14 +56,14 @@ def mcp_lists(rng):
     return m
 
 
-def make_policy(rng):
-    if rng.random() < 0.15:   # legacy form: no rules, per-tenant allow / deny topic lists
+def make_policy(rng, max_rules=12):
+    if max_rules <= 12 and rng.random() < 0.15:   # legacy form: no rules, per-tenant allow / deny topic lists
         tenants = {}
         for t in rng.sample(["default", "t1", "acme"], rng.randint(1, 3)):
             tenants[t] = {"allow_topics": pick(rng, PATTERNS, 0, 2), "deny_topics": pick(rng, PATTERNS, 0, 2), "mcp": mcp_lists(rng)}
         return {"default_tenant": rng.choice(["default", " t1", ""]), "tenants": tenants}
     rules = []
-    for i in range(rng.randint(1, 12)):
+    for i in range(rng.randint(max(1, max_rules // 3), max_rules)):
         m = {}
         if rng.random() < 0.5:
             m["tenants"] = pick(rng, TENANTS, 1, 2)
@@ -157,7 +157,16 @@ def make_job(rng, workers):
             eff["allowed_topics"] = pick(rng, PATTERNS, 0, 2)
         if rng.random() < 0.4:
             eff["mcp"] = mcp_lists(rng)
-        j["effective_config"] = json.dumps({"safety": eff})
+        # ParseEffectiveSafety (effective.go:12-39): encoding/json field matching is case-insensitive, wrong types fail
+        shape = rng.random()
+        if shape < 0.7:
+            j["effective_config"] = json.dumps({"safety": eff})
+        elif shape < 0.8:
+            j["effective_config"] = json.dumps({"Safety": {k.upper(): v for k, v in eff.items()}})
+        elif shape < 0.9:
+            j["effective_config"] = json.dumps({"safety": {"denied_topics": "job.*"}})   # not an array
+        else:
+            j["effective_config"] = rng.choice(["{", "null", "[]", '{"safety": null}', '{"other": 1}', '{"safety": {"denied_topics": [1]}}'])
     if rng.random() < 0.1:
         j["approved"] = True
     return j
@@ -181,11 +190,13 @@ def rec_tuples(rec):
              bool(r["flags"] & wire.F_TIE)) for r in rec]
 
 
-@pytest.mark.parametrize("seed", range(60))
-def test_three_implementations_agree(seed):
+@pytest.mark.parametrize("seed,max_rules", [(s, 12) for s in range(60)] + [(100 + s, 400) for s in range(12)])
+def test_three_implementations_agree(seed, max_rules):
+    """max_rules = 400: several 128-bit words of rule positions, so clustering by topic prefix, duplicated positions of
+    multi-pattern rules, per-topic word lists and the ascending order inside a word all take part."""
     rng = random.Random(7000 + seed)
-    policy, routing, workers = make_policy(rng), make_routing(rng), make_workers(rng)
-    jobs = [make_job(rng, workers) for _ in range(40)]
+    policy, routing, workers = make_policy(rng, max_rules), make_routing(rng), make_workers(rng)
+    jobs = [make_job(rng, workers) for _ in range(40 if max_rules <= 12 else 120)]
     env = wire.EnvelopeBatch.from_jobs(jobs)
     o = oracle_lib.Oracle(policy, routing, workers)
     want = o.eval(env, wire.MODE_POLICY_AND_ROUTE)
