@@ -211,3 +211,52 @@ def test_three_implementations_agree(seed, max_rules):
     a, b = rec_tuples(want), py_records(policy, routing, workers, jobs)
     bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y]
     assert not bad, "seed %d C++ vs Python oracle: %s\n%s" % (seed, bad[:3], json.dumps(jobs[bad[0][0]]))
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_reloads_and_heartbeats_keep_agreeing(seed):
+    """The same engine-side objects across a life cycle: heartbeat deltas (loads by slot), a worker-registry reload, a
+    routing reload and a policy reload, each followed by a re-evaluation of freshly encoded jobs - dictionaries are
+    rebuilt, ids are reassigned and the tables must still agree with an oracle that went through the same calls."""
+    rng = random.Random(9000 + seed)
+    policy, routing, workers = make_policy(rng), make_routing(rng), make_workers(rng)
+    o = oracle_lib.Oracle(policy, routing, workers)
+    h = table_walk.HostHarness(policy, routing, workers)
+
+    def check(what):
+        jobs = [make_job(rng, workers) for _ in range(30)]
+        env = wire.EnvelopeBatch.from_jobs(jobs)
+        want, got = o.eval(env, wire.MODE_POLICY_AND_ROUTE), h.evaluate(env, wire.MODE_POLICY_AND_ROUTE)
+        for f in FIELDS:
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert len(bad) == 0, "seed %d after %s: field %s job %s: tables %s oracle %s\n%s" % (
+                seed, what, f, bad[:4], got[f][bad[:4]], want[f][bad[:4]], json.dumps(jobs[int(bad[0])]))
+
+    check("load")
+    for step in range(6):
+        kind = rng.choice(["heartbeat", "heartbeat", "workers", "routing", "policy"])
+        if kind == "heartbeat" and workers:
+            n = len(workers)
+            slots = np.array(sorted(rng.sample(range(n), rng.randint(1, n))), dtype=np.uint32)
+            loads = np.zeros(len(slots), dtype=wire.LOAD_DTYPE)
+            loads["active_jobs"] = [rng.randint(0, 9) for _ in slots]
+            loads["max_parallel_jobs"] = [rng.choice([0, 4, 10]) for _ in slots]
+            loads["cpu_load"] = np.array([rng.choice([0, 50, 89.99, 90, 100 * rng.random()]) for _ in slots], dtype=np.float32)
+            loads["gpu_utilization"] = np.array([rng.choice([0, 0, 90, 100 * rng.random()]) for _ in slots], dtype=np.float32)
+            o.update_workers(slots, loads)
+            h.update_workers(slots, loads)
+        elif kind == "workers":
+            workers = make_workers(rng)
+            o.load_workers(workers)
+            h.load_workers(workers)
+        elif kind == "routing":
+            routing = make_routing(rng)
+            o.load_routing(routing)
+            h.load_routing(routing)
+        elif kind == "policy":
+            policy = make_policy(rng)
+            o.load_policy(policy)
+            h.load_policy(policy)
+        check("%s (step %d)" % (kind, step))
+    o.close()
+    h.close()
