@@ -199,15 +199,16 @@ def test_three_implementations_agree(seed, max_rules):
     jobs = [make_job(rng, workers) for _ in range(40 if max_rules <= 12 else 120)]
     env = wire.EnvelopeBatch.from_jobs(jobs)
     o = oracle_lib.Oracle(policy, routing, workers)
+    h = table_walk.HostHarness(policy, routing, workers)
+    for mode in (wire.MODE_POLICY_AND_ROUTE, wire.MODE_POLICY_ONLY, wire.MODE_ROUTE_ONLY):
+        want_m, got = o.eval(env, mode), h.evaluate(env, mode)
+        for f in FIELDS:   # product host tables vs C++ oracle: every field of the record
+            bad = np.nonzero(got[f] != want_m[f])[0]
+            assert len(bad) == 0, "seed %d mode %d field %s job %s: tables %s oracle %s\n%s" % (
+                seed, mode, f, bad[:4], got[f][bad[:4]], want_m[f][bad[:4]], json.dumps(jobs[int(bad[0])]))
     want = o.eval(env, wire.MODE_POLICY_AND_ROUTE)
     o.close()
-    h = table_walk.HostHarness(policy, routing, workers)
-    got = h.evaluate(env, wire.MODE_POLICY_AND_ROUTE)
     h.close()
-    for f in FIELDS:   # product host tables vs C++ oracle: every field of the record
-        bad = np.nonzero(got[f] != want[f])[0]
-        assert len(bad) == 0, "seed %d field %s job %s: tables %s oracle %s\n%s" % (
-            seed, f, bad[:4], got[f][bad[:4]], want[f][bad[:4]], json.dumps(jobs[int(bad[0])]))
     a, b = rec_tuples(want), py_records(policy, routing, workers, jobs)
     bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y]
     assert not bad, "seed %d C++ vs Python oracle: %s\n%s" % (seed, bad[:3], json.dumps(jobs[bad[0][0]]))
