@@ -97,3 +97,15 @@ def test_product_effective_config_parser_matches_oracle():
         a, dn = C.c_uint32(), C.c_uint32()
         ok = bool(L.cordum_test_parse_effective(d, len(d), C.byref(a), C.byref(dn)))
         assert (ok, a.value, dn.value) == oracle_lib.parse_effective(d), d
+
+
+def test_exchange_unique_id_needs_no_gpu():
+    """The engine loads libnccl at run time; creating the 128-byte id (rank 0's first step) needs no device.
+    When no libnccl can be found the call must fail with an error, not crash."""
+    from cordum_b200 import engine
+    try:
+        a, b = engine.Engine.exchange_unique_id(), engine.Engine.exchange_unique_id()
+    except engine.CordumError as e:
+        assert "nccl" in str(e).lower()
+        return
+    assert len(a) == 128 and len(b) == 128 and a != b
