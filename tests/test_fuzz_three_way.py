@@ -39,6 +39,16 @@ POOLS = ["p0", "p1", "p2", "gpu-pool"]
 PATTERNS = ["job.*", "job.sre.*", "job.[sd]*.*", "job.[^s]*.collect", "job.db.delete", "job.?b.*", "job.\\*.x", "job.[abc",
             " job.sre.collect ", "", "*", "job.sre.c*t", "JOB.sre.*", "job.web.*", "job.*.a.b"]
 MCP_VALS = ["srv", "SRV", " srv ", "other", "bad", "read", "WRITE", ""]
+# non-ASCII: Unicode White_Space that TrimSpace strips (NBSP, EM SPACE, IDEOGRAPHIC SPACE, NEL, LINE SEPARATOR), characters it
+# does not (ZERO WIDTH SPACE, BOM), letters that only fold outside ASCII (EqualFold is restated as ASCII-only), multi-byte
+# runes under '?' and character classes of path.Match
+TENANTS += ["\u00a0t1\u00a0", "\u2003acme", "t1\u3000", "\u00c9cole", "\u00e9cole", "t1\u200b", "\u0085t1\u2028"]
+CAPS += ["\u00a0cap.read", "CAP.R\u00c9AD", "cap.r\u00e9ad"]
+RISKS += ["\u2002write", "write\ufeff"]
+REQS += ["\u00a0git", "g\u0131t"]
+MCP_VALS += ["\u2003srv\u2003", "s\u0280v"]
+PATTERNS += ["job.\u00e9*", "\u00a0job.sre.*\u00a0", "job.[\u00e0-\u00ff]*.*", "job.?\u00e9.*"]
+PACKS += ["\u00e9t\u00e9"]
 DECISIONS = ["allow", "deny", "require_approval", "throttle", "allow_with_constraints", "permit", "block", "REQUIRE-HUMAN", ""]
 
 
