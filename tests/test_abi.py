@@ -109,3 +109,24 @@ def test_exchange_unique_id_needs_no_gpu():
         assert "nccl" in str(e).lower()
         return
     assert len(a) == 128 and len(b) == 128 and a != b
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/cordum_b200.h must be consumable by a C compiler (cgo uses one): examples/host_min.c builds as strict C99
+    against the header and the shared library, and on a machine without a GPU reports that there is no CPU path."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "host_min")
+    libdir = os.path.join(ROOT, "cordum_b200")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_min.c"), "-L" + libdir, "-lcordum_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the example's device path is exercised by hand, not by the CPU suite")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "no CUDA device" in r.stdout, (r.stdout, r.stderr)
