@@ -146,3 +146,23 @@ def test_refresh_work_list(sizes):
     assert int(T["n_merge"]) == len(want_merge) and T["merge_list"][:len(want_merge)].tolist() == want_merge
     assert int(T["merge_smem"]) == smem <= 8192 * 8
     h.close()
+
+
+def test_tables_match_oracle_on_config3_sample():
+    """BASELINE config 3 (4,096 rules, 65,536 workers, 1M jobs): the host tables of the headline workload, walked for
+    eight 100-job windows spread over the batch, against the oracle."""
+    cfg = synth.make_config("c3")
+    h = table_walk.HostHarness(cfg.policy, cfg.routing, cfg.workers, threads=4)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    T = h.tables()
+    assert int(T["n_rules"]) == 4096 and int(T["n_slots"]) == 65536 and int(T["n_merge"]) > 0
+    rng = np.random.default_rng(5)
+    seen = set()
+    for s in rng.integers(0, cfg.jobs.n_jobs - 100, 8):
+        env = cfg.jobs.slice(int(s), 100)
+        want = o.eval(env, wire.MODE_POLICY_AND_ROUTE, threads=4)
+        assert_same(h.evaluate(env), want, "c3 window at %d" % s)
+        seen |= set(want["decision"].tolist())
+    assert len(seen) >= 4
+    h.close()
+    o.close()
