@@ -131,7 +131,9 @@ def run_reference(args, rank: int, world: int):
         return
     from cordum_b200 import synth
 
-    threads = os.cpu_count() or 1
+    from cordum_b200 import hostinfo
+
+    threads = hostinfo.usable_cores()   # affinity and cgroup quota, not os.cpu_count()
     cfg = synth.make_config("c3")
     per_step_s = max(0.5, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
     for w in range(args.warmup):
@@ -151,7 +153,8 @@ def run_reference(args, rank: int, world: int):
         "config": {"workload": "c3: 1,000,000 jobs x 4096 rules x 65536 workers (seed 3), policy+route",
                    "note": "reference CPU path = oracle/oracle.cpp (C++ restatement of the Go evaluator; the Go "
                            "toolchain and the CAP module are absent), one std::thread per host core"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                         "host": hostinfo.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -284,34 +287,48 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     chk = batches[(args.warmup + args.steps - 1) % n_rot].fetch()
     assert np.array_equal(chk["decision"], ref_result["decision"]) and np.array_equal(chk["rule_idx"], ref_result["rule_idx"])
 
-    # parity of the sharded path, exchange included: one more epoch with a known delta set, then the first jobs of
-    # rank 0's shard against the oracle evaluated on the table all ranks' slices add up to (checker only, untimed)
-    parity = None
+    # parity of the sharded path, exchange included: one more epoch with a known delta set, then EVERY rank compares
+    # EVERY record of its shard with the oracle evaluated on the table all ranks' slices add up to (checker only,
+    # untimed; the mismatch count is summed over ranks into the JSON line).  At N=1 the same oracle pass over the full
+    # 1M-job batch is also the cpu_baseline measurement.
+    from cordum_b200 import hostinfo
+    import oracle_lib
+
     k_chk = 3
     step(k_chk, batches[0], True)
     sync_all()
-    if rank == 0:
-        import oracle_lib
-        full = base.copy()
-        for r in range(world):
-            r0, r1 = shard.worker_range(r, world, W)
-            rr = np.random.default_rng(1000 + r)
-            for s_ in range(k_chk % n_delta_sets + 1):   # replay rank r's generator up to the set in use
-                act = rr.integers(0, 9, r1 - r0)
-                cpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
-                gpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
-            full["active_jobs"][r0:r1] = act
-            full["cpu_load"][r0:r1] = cpu_
-            full["gpu_utilization"][r0:r1] = gpu_
-        n_chk = min(2000, n_shard)
-        o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
-        o.update_workers(np.arange(W, dtype=np.uint32), full)
-        want = o.eval(my_jobs, wire.MODE_POLICY_AND_ROUTE, threads=4, first=0, count=n_chk)
-        got = batches[0].fetch()[:n_chk]
-        fields = ("decision", "sched_decision", "flags", "route_status", "reason_code", "rule_idx", "worker_slot")
-        bad = [f for f in fields if not np.array_equal(got[f], want[f])]
-        assert not bad, "sharded path differs from the oracle in %s" % bad
-        parity = {"jobs_checked": int(n_chk), "fields": list(fields), "ok": True}
+    full = base.copy()
+    for r in range(world):
+        r0, r1 = shard.worker_range(r, world, W)
+        rr = np.random.default_rng(1000 + r)
+        for s_ in range(k_chk % n_delta_sets + 1):   # replay rank r's generator up to the set in use
+            act = rr.integers(0, 9, r1 - r0)
+            cpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
+            gpu_ = (rr.random(r1 - r0) * 100).astype(np.float32)
+        full["active_jobs"][r0:r1] = act
+        full["cpu_load"][r0:r1] = cpu_
+        full["gpu_utilization"][r0:r1] = gpu_
+    cores = hostinfo.usable_cores()
+    o_threads = max(1, cores // world)
+    n_chk = n_shard if not args.parity_sample else min(args.parity_sample, n_shard)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    o.update_workers(np.arange(W, dtype=np.uint32), full)
+    t_or = time.perf_counter()
+    want = o.eval(my_jobs, wire.MODE_POLICY_AND_ROUTE, threads=o_threads, first=0, count=n_chk)
+    oracle_s = time.perf_counter() - t_or
+    o.close()
+    got = batches[0].fetch()[:n_chk]
+    fields = ("decision", "sched_decision", "flags", "route_status", "reason_code", "rule_idx", "worker_slot")
+    bad_rows = np.zeros(n_chk, dtype=bool)
+    for f in fields:
+        bad_rows |= got[f] != want[f]
+    counts = torch.tensor([int(bad_rows.sum()), int(n_chk)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    n_bad, n_checked = (int(x) for x in counts.tolist())
+    parity = {"jobs_checked": n_checked, "mismatches": n_bad, "fields": list(fields), "ok": n_bad == 0,
+              "ranks_checked": world, "oracle_threads_per_rank": o_threads, "oracle_s": oracle_s}
+    assert n_bad == 0, "sharded path differs from the oracle on %d of %d jobs" % (n_bad, n_checked)
 
     # ---------------------------------------------------------------- per-kernel durations for the roofline
     # Serialized launches (wait after every step) so the CUDA-event span of a kernel contains that kernel only;
@@ -383,11 +400,12 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate, sample, dt = cpu_reference_rate(cfg, threads, 12.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "first %d jobs of the c3 batch in %.1f s, full rule set and worker table; "
-                         "oracle/oracle.cpp, one std::thread per host core" % (sample, dt)}
+        # the parity pass above ran the oracle over the whole 1M-job batch on all usable host cores: that IS the CPU
+        # path on this workload (no sampling, no extrapolation)
+        cpu = {"value": n_chk / oracle_s, "unit": UNIT, "cores": o_threads, "kind": "port",
+               "sample": "all %d jobs of the c3 batch in %.1f s, full rule set and worker table; oracle/oracle.cpp, "
+                         "one std::thread per usable host core" % (n_chk, oracle_s),
+               "host": hostinfo.describe()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -429,10 +447,12 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cordum_b200", choices=["cordum_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-sample", type=int, default=0,
+                    help="check only the first N jobs of each rank's shard against the oracle (0 = every job; for quick runs)")
     ap.add_argument("--exchange", default="engine", choices=["engine", "torch"],
                     help="heartbeat exchange: the engine's own NCCL communicator (cordum_workers_ingest) or "
                          "torch.distributed all_gather + cordum_workers_set_loads_device")
