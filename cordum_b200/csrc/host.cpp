@@ -949,28 +949,40 @@ int Host::load_routing(sv json, std::string& err) {
   }
   compile_mcp_tables();
   rebuild_topics();
-  epoch_++;
   std::string e2;
-  return compile_workers(e2) == CORDUM_OK ? CORDUM_OK : (err = e2, CORDUM_E_CAPACITY);
+  if (compile_workers(e2) != CORDUM_OK) {   // the new pool set makes more labelled workers routable than the label
+    err = e2;                               // dictionary holds: keep the previous routing (nothing was committed for
+    routing_ = std::move(old);              // the workers: compile_workers checks capacity before it mutates)
+    compile_policy();
+    compile_routing();
+    compile_mcp_tables();
+    rebuild_topics();
+    std::string e3;
+    compile_workers(e3);
+    return CORDUM_E_CAPACITY;
+  }
+  epoch_++;
+  return CORDUM_OK;
 }
 
 int Host::load_workers(const cordum_workers* w, std::string& err) {
   std::lock_guard<std::mutex> g(mu_);
-  auto& store = workers_raw_;
-  store.clear();
-  t_.loads.clear();
-  worker_ids_.clear();
+  // Everything is built in temporaries and committed only when the new registry compiles: a rejected load (NaN load,
+  // label dictionary overflow) leaves the previous registry, its tables and every encoded batch untouched.
+  std::vector<WorkerRaw> store;
+  std::vector<Load16> loads;
+  std::vector<std::string> ids;
   if (w) {
     auto sp = [&](const cordum_str* col, uint32_t i) { return sv((const char*)w->arena + col[i].off, col[i].len); };
     store.resize(w->n_workers);
-    t_.loads.resize(w->n_workers);
-    worker_ids_.resize(w->n_workers);
+    loads.resize(w->n_workers);
+    ids.resize(w->n_workers);
     for (uint32_t i = 0; i < w->n_workers; ++i) {
       float cpu = w->cpu_load[i], gpu = w->gpu_utilization[i];
       if (cpu != cpu || gpu != gpu) { err = "worker load is NaN (ordering undefined in the reference)"; return CORDUM_E_INVALID; }
       store[i].id = std::string(sp(w->worker_id, i));
       store[i].pool = std::string(sp(w->pool, i));
-      worker_ids_[i] = store[i].id;
+      ids[i] = store[i].id;
       if (w->label_off)
         for (uint32_t k = w->label_off[i]; k < w->label_off[i + 1]; ++k) {
           std::string key(sp(w->label_keys, k));
@@ -978,28 +990,30 @@ int Host::load_workers(const cordum_workers* w, std::string& err) {
           for (auto& kv : store[i].labels) if (kv.first == key) { kv.second = std::string(sp(w->label_vals, k)); found = true; }
           if (!found) store[i].labels.emplace_back(key, std::string(sp(w->label_vals, k)));
         }
-      t_.loads[i] = Load16{w->active_jobs[i], w->max_parallel_jobs[i], cpu, gpu};
+      loads[i] = Load16{w->active_jobs[i], w->max_parallel_jobs[i], cpu, gpu};
     }
   }
+  std::vector<WorkerRaw> old_store = std::move(workers_raw_);
+  workers_raw_ = std::move(store);
+  int rc = compile_workers(err, &loads);
+  if (rc != CORDUM_OK) { workers_raw_ = std::move(old_store); return rc; }   // compile_workers mutated nothing
+  worker_ids_ = std::move(ids);
   epoch_++;
-  return compile_workers(err);
+  return CORDUM_OK;
 }
 
-int Host::compile_workers(std::string& err) {
+int Host::compile_workers(std::string& err, const std::vector<Load16>* new_loads) {
   HostTables& t = t_;
   auto& store = workers_raw_;
   const uint32_t n = (uint32_t)store.size();
-  t.n_slots = n;
-  worker_slot_.clear();
-  place_pair_.clear();
-  place_key_.clear();
-  for (uint32_t s = 0; s < n; ++s) worker_slot_.put(store[s].id, s);   // map semantics: last wins
+  // ---- phase 1: everything that can fail, into locals (no member is written before the capacity check)
+  StrTable worker_slot, place_pair, place_key;
+  for (uint32_t s = 0; s < n; ++s) worker_slot.put(store[s].id, s);   // map semantics: last wins
   std::vector<uint32_t> live;
-  for (uint32_t s = 0; s < n; ++s) if (worker_slot_.find(store[s].id, kMiss) == s) live.push_back(s);
+  for (uint32_t s = 0; s < n; ++s) if (worker_slot.find(store[s].id, kMiss) == s) live.push_back(s);
   std::sort(live.begin(), live.end(), [&](uint32_t a, uint32_t b) { return store[a].id < store[b].id; });
-  t.rank_slot.assign(std::max<uint32_t>(n, 1), 0);
   std::vector<uint32_t> rank_of(n, 0);
-  for (uint32_t r = 0; r < live.size(); ++r) { t.rank_slot[r] = live[r]; rank_of[live[r]] = r; }
+  for (uint32_t r = 0; r < live.size(); ++r) rank_of[live[r]] = r;
   // routable = live and in a pool the routing table knows
   struct Pos { uint32_t pool, rank, slot; };
   std::vector<Pos> pos;
@@ -1010,17 +1024,26 @@ int Host::compile_workers(std::string& err) {
   std::sort(pos.begin(), pos.end(), [](const Pos& a, const Pos& b) { return a.pool != b.pool ? a.pool < b.pool : a.rank < b.rank; });
   // placement-label dictionary: pairs (k,v!=""), per-key "absent or empty" bits, "has any label" bit
   uint32_t nbits = 0;
-  place_any_bit_ = nbits++;
+  const uint32_t any_bit = nbits++;
   for (auto& p : pos)
     for (auto& kv : store[p.slot].labels) {
-      if (place_key_.find(kv.first, kMiss) == kMiss) place_key_.put(kv.first, nbits++);
+      if (place_key.find(kv.first, kMiss) == kMiss) place_key.put(kv.first, nbits++);
       if (!kv.second.empty()) {
         std::string pk = kv.first; pk.push_back('\0'); pk += kv.second;
-        if (place_pair_.find(pk, kMiss) == kMiss) place_pair_.put(pk, nbits++);
+        if (place_pair.find(pk, kMiss) == kMiss) place_pair.put(pk, nbits++);
       }
     }
-  place_bits_ = nbits;
   if (nbits > 128) { err = "more than 128 placement-label bits (pairs + keys) on routable workers"; return CORDUM_E_CAPACITY; }
+  // ---- phase 2: commit (cannot fail)
+  t.n_slots = n;
+  if (new_loads) t.loads = *new_loads;
+  worker_slot_ = std::move(worker_slot);
+  place_pair_ = std::move(place_pair);
+  place_key_ = std::move(place_key);
+  place_any_bit_ = any_bit;
+  place_bits_ = nbits;
+  t.rank_slot.assign(std::max<uint32_t>(n, 1), 0);
+  for (uint32_t r = 0; r < live.size(); ++r) t.rank_slot[r] = live[r];
   const uint32_t np = (uint32_t)pos.size();
   t.n_pos = np;
   uint32_t cap = std::max<uint32_t>(np, 1);

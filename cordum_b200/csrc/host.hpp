@@ -304,7 +304,7 @@ class Host {
   void compile_policy();
   void compile_routing();
   void compile_mcp_tables();
-  int compile_workers(std::string& err);
+  int compile_workers(std::string& err, const std::vector<Load16>* new_loads = nullptr);   // checks capacity before mutating
   void rebuild_topics();
   uint32_t add_topic(sv raw);          // under mu_
   uint32_t add_effcfg(sv payload);     // under mu_

@@ -166,3 +166,53 @@ def test_tables_match_oracle_on_config3_sample():
     assert len(seen) >= 4
     h.close()
     o.close()
+
+
+def test_rejected_worker_load_keeps_the_previous_registry():
+    """A cordum_workers_load that fails (label dictionary over capacity, NaN load) must leave the previous registry in
+    place: same tables, same encoding, same results (a failed load used to leave n_slots / loads of the
+    new registry next to slot_pos / pos_slot of the old one, and later calls indexed out of bounds)."""
+    routing = {"topics": {"job.a": ["p"]}, "pools": {"p": {}}}
+    good = [kats.hb("w0", "p", 1, 10.0, 0.0, 4, {"zone": "a"}), kats.hb("w1", "p", 0, 20.0, 0.0, 4, {"zone": "b"})]
+    jobs = [{"topic": "job.a"}, {"topic": "job.a", "labels": {"zone": "b"}},
+            {"topic": "job.a", "labels": {"preferred_worker_id": "w1"}}, {"topic": "job.a", "labels": {"preferred_worker_id": "w079"}}]
+    h = table_walk.HostHarness(None, routing, good)
+    o = oracle_lib.Oracle(None, routing, good)
+    want = o.eval(jobs, wire.MODE_ROUTE_ONLY)
+    assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "before")
+    before = h.tables()
+    too_many = [kats.hb("w%03d" % i, "p", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(80)]   # 80 keys + 80 pairs > 128 bits
+    with pytest.raises(RuntimeError, match="placement-label"):
+        h.load_workers(too_many)
+    nan = [kats.hb("w0", "p", 1, float("nan"), 0.0, 4)]
+    with pytest.raises(RuntimeError, match="NaN"):
+        h.load_workers(nan)
+    after = h.tables()
+    for k in ("n_slots", "n_pos"):
+        assert before[k] == after[k] == 2, k
+    for k in ("slot_pos", "pos_slot", "pos_rank", "rank_slot", "pool_off", "pos_label_lo", "pos_label_hi"):
+        assert np.array_equal(before[k], after[k]), k
+    assert np.array_equal(before["loads"], after["loads"])
+    assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "after the rejected loads")
+    # heartbeat deltas are still bounded by the OLD registry
+    with pytest.raises(RuntimeError):
+        h.update_workers(np.array([2], np.uint32), np.zeros(1, wire.LOAD_DTYPE))
+    h.update_workers(np.array([1], np.uint32), np.array([(3, 4, 50.0, 0.0)], wire.LOAD_DTYPE))
+    o.update_workers(np.array([1], np.uint32), np.array([(3, 4, 50.0, 0.0)], wire.LOAD_DTYPE))
+    assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), o.eval(jobs, wire.MODE_ROUTE_ONLY), "after a delta")
+
+
+def test_rejected_routing_load_keeps_the_previous_routing():
+    """A routing reload that makes more labelled workers routable than the label dictionary holds is refused whole."""
+    workers = [kats.hb("a%03d" % i, "p", 0, float(i), 0.0, 0, {"zone": "z"}) for i in range(3)] + \
+              [kats.hb("b%03d" % i, "q", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(80)]
+    r1 = {"topics": {"job.a": ["p"]}, "pools": {"p": {}}}
+    r2 = {"topics": {"job.a": ["p", "q"]}, "pools": {"p": {}, "q": {}}}
+    jobs = [{"topic": "job.a"}, {"topic": "job.a", "labels": {"zone": "z"}}]
+    h = table_walk.HostHarness(None, r1, workers)
+    o = oracle_lib.Oracle(None, r1, workers)
+    want = o.eval(jobs, wire.MODE_ROUTE_ONLY)
+    assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "before")
+    with pytest.raises(RuntimeError, match="placement-label"):
+        h.load_routing(r2)
+    assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "after the rejected routing")
