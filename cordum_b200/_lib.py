@@ -23,7 +23,7 @@ API = [
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
     "cordum_launch_count", "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
-    "cordum_test_parse_effective",
+    "cordum_test_parse_effective", "cordum_test_canon",
 ]
 
 _lib = None
@@ -85,6 +85,8 @@ def load() -> C.CDLL:
     L.cordum_test_glob.argtypes = [cp, u64, cp, u64]
     L.cordum_test_trim.argtypes = [cp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.cordum_test_normalize_decision.argtypes = [cp, u64]
+    L.cordum_test_canon.argtypes = [i32, cp, u64, cp, u64]
+    L.cordum_test_canon.restype = i64
     L.cordum_test_parse_effective.argtypes = [cp, u64, C.POINTER(u32), C.POINTER(u32)]
     # host-only hooks (CPU tests of the table compiler / encoder)
     L.cordum_test_last_error.restype = cp

@@ -856,6 +856,12 @@ void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len) {
   *off = t.empty() ? 0 : (uint64_t)(t.data() - s);
   *len = t.size();
 }
+/* canonical forms the table compiler uses: kind 0 = strings.EqualFold class of the string (no trim), 1 = strings.ToLower */
+int64_t cordum_test_canon(int32_t kind, const char* s, uint64_t n, char* buf, uint64_t cap) {
+  std::string o = kind == 0 ? cordum::fold_str(sv(s, n)) : cordum::lower_copy(sv(s, n));
+  if (buf && cap) std::memcpy(buf, o.data(), std::min<size_t>(o.size(), cap));
+  return (int64_t)o.size();
+}
 int32_t cordum_test_normalize_decision(const char* s, uint64_t n) { return cordum::normalize_decision_code(sv(s, n)); }
 int32_t cordum_test_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied) {
   cordum::EffSafety cfg;

@@ -4,17 +4,22 @@
 // encode time, never on the device.  These helpers restate the Go
 // stdlib behaviour the reference relies on:
 //   strings.TrimSpace   (kernel.go:133-134, safety_policy.go:301,357)
-//   strings.EqualFold   (safety_policy.go:301)   -> canonical form = ASCII-lowered bytes
-//   strings.ToLower     (strategy_least_loaded.go:250,256; kernel.go:403)
+//   strings.EqualFold   (safety_policy.go:301)   -> canonical form = every rune replaced by the representative of
+//                       its simple-case-folding class (all of Unicode 15.0.0, as go1.24: U+212A KELVIN ~ k,
+//                       U+017F ~ s, final sigma ~ sigma; U+0130 / U+0131 fold with nothing), invalid UTF-8 -> U+FFFD
+//   strings.ToLower     (strategy_least_loaded.go:250,256; kernel.go:403) -> unicode.ToLower per rune (a different
+//                       canonical form: U+017F lower-cases to itself)
 //   path.Match          (safety_policy.go:361; kernel.go:482)
 // Implementation is independent of oracle/ (different algorithms on purpose): globs are
 // compiled once into element lists and matched with single-star backtracking.
-// Limitation (documented in DESIGN.md): case folding is ASCII-only.
+// Tables: common/go_unicode_tables.h (generated from the Unicode Character Database, tools/gen_go_unicode.py).
 #pragma once
 #include <cstdint>
 #include <string>
 #include <string_view>
 #include <vector>
+
+#include "../../common/go_unicode_tables.h"
 
 namespace cordum {
 
@@ -88,18 +93,53 @@ inline sv trim_space(sv s) {
 
 inline char lower_ascii(char c) { return (c >= 'A' && c <= 'Z') ? char(c + 32) : c; }
 
-// Canonical form under strings.EqualFold(TrimSpace(a), TrimSpace(b)) (ASCII folding).
-inline std::string fold_key(sv s) {
-  s = trim_space(s);
-  std::string o(s);
-  for (auto& c : o) c = lower_ascii(c);
+inline uint32_t rune_map(const GoRunePair* tab, uint32_t n, uint32_t r) {   // sorted by .from
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (tab[mid].from < r) lo = mid + 1; else hi = mid;
+  }
+  return (lo < n && tab[lo].from == r) ? tab[lo].to : r;
+}
+inline void utf8_append(std::string& o, uint32_t r) {
+  if (r < 0x80) o.push_back((char)r);
+  else if (r < 0x800) { o.push_back((char)(0xC0 | (r >> 6))); o.push_back((char)(0x80 | (r & 0x3F))); }
+  else if (r < 0x10000) { o.push_back((char)(0xE0 | (r >> 12))); o.push_back((char)(0x80 | ((r >> 6) & 0x3F))); o.push_back((char)(0x80 | (r & 0x3F))); }
+  else { o.push_back((char)(0xF0 | (r >> 18))); o.push_back((char)(0x80 | ((r >> 12) & 0x3F))); o.push_back((char)(0x80 | ((r >> 6) & 0x3F))); o.push_back((char)(0x80 | (r & 0x3F))); }
+}
+inline bool is_ascii(sv s) {
+  unsigned char acc = 0;
+  for (unsigned char c : s) acc |= c;
+  return acc < 0x80;
+}
+// rune-wise map of a string (Go: `for _, r := range s`: an invalid byte decodes to U+FFFD, width 1)
+inline std::string map_runes(sv s, const GoRunePair* tab, uint32_t n) {
+  std::string o;
+  o.reserve(s.size());
+  const unsigned char* p = (const unsigned char*)s.data();
+  for (size_t i = 0; i < s.size();) {
+    int w;
+    uint32_t r = utf8_next(p + i, s.size() - i, w);
+    i += (size_t)w;
+    utf8_append(o, r < 0x80 ? (uint32_t)(unsigned char)lower_ascii((char)r) : rune_map(tab, n, r));
+  }
   return o;
 }
+
+// Canonical form under strings.EqualFold(a, b): two strings are EqualFold iff their fold_str are byte-equal.
+inline std::string fold_str(sv s) {
+  if (is_ascii(s)) { std::string o(s); for (auto& c : o) c = lower_ascii(c); return o; }
+  return map_runes(s, kGoFoldRep, kGoFoldRepCount);
+}
+// Canonical form under strings.EqualFold(TrimSpace(a), TrimSpace(b)).
+inline std::string fold_key(sv s) { return fold_str(trim_space(s)); }
+// strings.ToLower
 inline std::string lower_copy(sv s) {
-  std::string o(s);
-  for (auto& c : o) c = lower_ascii(c);
-  return o;
+  if (is_ascii(s)) { std::string o(s); for (auto& c : o) c = lower_ascii(c); return o; }
+  return map_runes(s, kGoLower, kGoLowerCount);
 }
+// strings.ToLower(strings.TrimSpace(s))
+inline std::string lower_key(sv s) { return lower_copy(trim_space(s)); }
 inline bool starts_with(sv s, sv p) { return s.size() >= p.size() && s.compare(0, p.size(), p) == 0; }
 
 // ------------------------------------------------------------------ compiled glob

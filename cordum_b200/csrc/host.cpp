@@ -19,28 +19,31 @@ namespace {
 
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
 
-// fold_key without heap allocation for ordinary-sized values
+// fold_key without heap allocation for ordinary-sized ASCII values (anything else takes the general path)
 struct FoldBuf {
   char small[160];
   std::string big;
   sv view;
   explicit FoldBuf(sv raw) {
     sv t = trim_space(raw);
-    if (t.size() <= sizeof small) {
+    if (t.size() <= sizeof small && is_ascii(t)) {
       for (size_t i = 0; i < t.size(); ++i) small[i] = lower_ascii(t[i]);
       view = sv(small, t.size());
     } else {
-      big = lower_copy(t);
+      big = fold_str(t);
       view = big;
     }
   }
 };
 
-bool fold_eq(sv a, sv b) {   // strings.EqualFold, ASCII
-  if (a.size() != b.size()) return false;
-  for (size_t i = 0; i < a.size(); ++i)
-    if (lower_ascii(a[i]) != lower_ascii(b[i])) return false;
-  return true;
+bool fold_eq(sv a, sv b) {   // strings.EqualFold
+  if (is_ascii(a) && is_ascii(b)) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+      if (lower_ascii(a[i]) != lower_ascii(b[i])) return false;
+    return true;
+  }
+  return fold_str(a) == fold_str(b);
 }
 
 // dictionary lookup of a job value under containsString semantics (safety_policy.go:296-306)
@@ -152,7 +155,7 @@ std::string go_quote(sv s) {   // fmt %q for the printable-ASCII strings that oc
 
 // ============================================================ document parsing
 uint8_t normalize_decision_code(sv raw) {   // safety_policy.go:208-223
-  std::string s = fold_key(raw);
+  std::string s = lower_key(raw);   // strings.ToLower(strings.TrimSpace(raw))
   if (s == "deny" || s == "block") return CORDUM_DEC_DENY;
   if (s == "require_approval" || s == "require-approval" || s == "require_human") return CORDUM_DEC_REQUIRE_HUMAN;
   if (s == "allow_with_constraints" || s == "allow-with-constraints") return CORDUM_DEC_ALLOW_WITH_CONSTRAINTS;
@@ -1353,7 +1356,10 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out,
   for (int f = 0; f < 4; ++f) {
     sv v;
     for (int a = 0; a < 3 && v.empty(); ++a) v = mcpv[f * 3 + a];
-    out.mcp[f][j] = lookup_value(d_mcp_[f], v);
+    if (f == 3 && !is_ascii(v)) {   // Action: strings.ToLower(pickLabel(...)) (kernel.go:403), then EqualFold against the lists
+      std::string lv = lower_copy(v);
+      out.mcp[f][j] = lookup_value(d_mcp_[f], lv);
+    } else out.mcp[f][j] = lookup_value(d_mcp_[f], v);
     used |= !v.empty();
   }
   if (used) flags |= JF_MCP_USED;

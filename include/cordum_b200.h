@@ -298,6 +298,7 @@ uint64_t cordum_launch_count(cordum_engine* e);
 int32_t cordum_test_glob(const char* pat, uint64_t plen, const char* name, uint64_t nlen); /* 1, 0, -1 malformed */
 void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len);
 int32_t cordum_test_normalize_decision(const char* s, uint64_t n);
+int64_t cordum_test_canon(int32_t kind, const char* s, uint64_t n, char* buf, uint64_t cap); /* 0: EqualFold class form, 1: strings.ToLower */
 int32_t cordum_test_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied);
 
 #ifdef __cplusplus

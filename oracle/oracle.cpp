@@ -31,9 +31,8 @@
 // against an independent pure-Python restatement (oracle/py_oracle.py) on randomized
 // inputs.  Behaviour the reference's tests do not exercise (see SURVEY.md §8c last row)
 // is "pinned only by two independent restatements of the cited lines".
-// Known limitation shared with the product: case folding / lower-casing is ASCII-only
-// (Go folds all of Unicode); every string in the reference's fixtures and in the
-// synthetic configs is ASCII.  TrimSpace handles the full Unicode White_Space set.
+// Case folding follows go1.24: strings.EqualFold walks unicode.SimpleFold orbits (all of Unicode 15.0.0, e.g.
+// U+212A KELVIN SIGN ~ k, U+017F ~ s), strings.ToLower maps rune by rune; TrimSpace handles the full White_Space set.
 //
 // Tie rule: Go's map iteration order is random and PickSubject keeps the
 // first strict minimum, so on equal scores the reference's answer is nondeterministic.
@@ -55,6 +54,7 @@
 #include <unordered_set>
 #include <vector>
 
+#include "../common/go_unicode_tables.h"
 #include "../common/mini_json.hpp"
 
 using sv = std::string_view;
@@ -141,18 +141,92 @@ sv trim_space(sv s) {
 
 inline unsigned char ascii_lower(unsigned char c) { return (c >= 'A' && c <= 'Z') ? (unsigned char)(c + 32) : c; }
 
-// strings.EqualFold — ASCII folding only (see header note)
-bool equal_fold(sv a, sv b) {
-  if (a.size() != b.size()) return false;
-  for (size_t i = 0; i < a.size(); ++i)
-    if (ascii_lower((unsigned char)a[i]) != ascii_lower((unsigned char)b[i])) return false;
-  return true;
+// unicode.SimpleFold (go1.24 unicode/letter.go:SimpleFold; Unicode 15.0.0): the next rune of r's simple-case-folding
+// class in ascending cyclic order; a rune that folds with nothing maps to itself (also U+0130 / U+0131: "has lower/upper
+// but no case fold", unicode/letter_test.go simpleFoldTests).  Classes come from common/go_unicode_tables.h (generated
+// from the Unicode Character Database, tools/gen_go_unicode.py).
+const std::unordered_map<uint32_t, uint32_t>& fold_successor() {
+  static const std::unordered_map<uint32_t, uint32_t> next = [] {
+    std::map<uint32_t, std::vector<uint32_t>> classes;   // representative -> members
+    for (uint32_t i = 0; i < kGoFoldRepCount; ++i) classes[kGoFoldRep[i].to].push_back(kGoFoldRep[i].from);
+    std::unordered_map<uint32_t, uint32_t> m;
+    for (auto& kv : classes) {
+      std::vector<uint32_t> ms = kv.second;
+      ms.push_back(kv.first);
+      std::sort(ms.begin(), ms.end());
+      for (size_t i = 0; i < ms.size(); ++i) m[ms[i]] = ms[(i + 1) % ms.size()];
+    }
+    return m;
+  }();
+  return next;
+}
+uint32_t simple_fold(uint32_t r) {
+  auto& m = fold_successor();
+  auto it = m.find(r);
+  return it == m.end() ? r : it->second;
 }
 
-// strings.ToLower — ASCII only
+// strings.EqualFold (go1.24 strings/strings.go): ASCII fast path, then rune by rune
+bool equal_fold(sv s, sv t) {
+  size_t i = 0;
+  for (; i < s.size() && i < t.size(); ++i) {
+    unsigned char sr = (unsigned char)s[i], tr = (unsigned char)t[i];
+    if ((sr | tr) >= 0x80) goto has_unicode;
+    if (tr == sr) continue;
+    if (tr < sr) std::swap(tr, sr);
+    if ('A' <= sr && sr <= 'Z' && tr == sr + 'a' - 'A') continue;
+    return false;
+  }
+  return s.size() == t.size();
+has_unicode:
+  s = s.substr(i);
+  t = t.substr(i);
+  while (!s.empty()) {          // for _, sr := range s
+    if (t.empty()) return false;
+    int ns, nt;
+    uint32_t sr = decode_rune(s, ns), tr = decode_rune(t, nt);
+    s.remove_prefix(ns);
+    t.remove_prefix(nt);
+    if (tr == sr) continue;
+    if (tr < sr) std::swap(tr, sr);
+    if (tr < 0x80) {
+      if ('A' <= sr && sr <= 'Z' && tr == sr + 'a' - 'A') continue;
+      return false;
+    }
+    uint32_t r = simple_fold(sr);
+    while (r != sr && r < tr) r = simple_fold(r);
+    if (r == tr) continue;
+    return false;
+  }
+  return t.empty();
+}
+
+void append_rune(std::string& o, uint32_t r) {   // utf8.AppendRune
+  if (r < 0x80) o.push_back((char)r);
+  else if (r < 0x800) { o.push_back((char)(0xC0 | (r >> 6))); o.push_back((char)(0x80 | (r & 0x3F))); }
+  else if (r < 0x10000) { o.push_back((char)(0xE0 | (r >> 12))); o.push_back((char)(0x80 | ((r >> 6) & 0x3F))); o.push_back((char)(0x80 | (r & 0x3F))); }
+  else { o.push_back((char)(0xF0 | (r >> 18))); o.push_back((char)(0x80 | ((r >> 12) & 0x3F))); o.push_back((char)(0x80 | ((r >> 6) & 0x3F))); o.push_back((char)(0x80 | (r & 0x3F))); }
+}
+
+// strings.ToLower (go1.24): ASCII fast path, else strings.Map(unicode.ToLower, s) - invalid UTF-8 becomes U+FFFD
 std::string to_lower(sv s) {
-  std::string o(s);
-  for (auto& c : o) c = (char)ascii_lower((unsigned char)c);
+  bool ascii = true;
+  for (unsigned char c : s) if (c >= 0x80) { ascii = false; break; }
+  std::string o;
+  if (ascii) {
+    o.assign(s);
+    for (auto& c : o) c = (char)ascii_lower((unsigned char)c);
+    return o;
+  }
+  while (!s.empty()) {
+    int n;
+    uint32_t r = decode_rune(s, n);
+    s.remove_prefix(n);
+    if (r < 0x80) { o.push_back((char)ascii_lower((unsigned char)r)); continue; }
+    uint32_t lo = 0, hi = kGoLowerCount;   // unicode.ToLower: simple lowercase mapping
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (kGoLower[mid].from < r) lo = mid + 1; else hi = mid; }
+    append_rune(o, (lo < kGoLowerCount && kGoLower[lo].from == r) ? kGoLower[lo].to : r);
+  }
   return o;
 }
 
@@ -1305,6 +1379,12 @@ int32_t oracle_path_match(const char* pat, uint64_t plen, const char* name, uint
 }
 int32_t oracle_equal_fold(const char* a, uint64_t alen, const char* b, uint64_t blen) {
   return equal_fold(sv(a, alen), sv(b, blen)) ? 1 : 0;
+}
+/* strings.ToLower: writes min(cap, len) bytes, returns the full length */
+int64_t oracle_to_lower(const char* s, uint64_t n, char* buf, uint64_t cap) {
+  std::string o = to_lower(sv(s, n));
+  if (buf && cap) std::memcpy(buf, o.data(), std::min<size_t>(o.size(), cap));
+  return (int64_t)o.size();
 }
 void oracle_trim_space(const char* s, uint64_t n, uint64_t* off, uint64_t* len) {
   sv t = trim_space(sv(s, n));

@@ -11,8 +11,8 @@ Each function cites the Go it follows (paths relative to /root/reference):
   core/infra/config/effective.go              -> parse_effective_safety
   core/controlplane/scheduler/strategy_least_loaded.go -> pick_subject and helpers
   core/controlplane/scheduler/engine.go:298-347,484-531 -> process_job
-Go stdlib restated: strings.TrimSpace / EqualFold (ASCII folding only) / ToLower
-(ASCII only), path.Match (go1.24 src/path/match.go).
+Go stdlib restated: strings.TrimSpace / EqualFold (Unicode simple case folding) / ToLower
+(simple lowercase mapping), path.Match (go1.24 src/path/match.go).
 
 Inputs: policy = dict shaped like config.SafetyPolicy with yaml tag names (or None);
 routing = {"topics": {t: [pools]}, "pools": {p: {"requires": [...]}}};
@@ -36,15 +36,29 @@ def trim_space(s: str) -> str:
     return s[a:b]
 
 
-def _ascii_lower(s: str) -> str:
-    return "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in s)
+def _fold_rep(c: str) -> str:
+    """Representative of c's class under Go's rune-level EqualFold (simple case folding, Unicode 15.0.0 = this
+    interpreter's unicodedata).  Derived independently of common/go_unicode_tables.h from Python's own case mappings:
+    a single-character full case folding is the simple folding; where the full folding expands (U+1E9E, the Greek
+    iota-subscript capitals ...) the simple folding is the single-character lower case; characters whose only foldings
+    are multi-character or Turkic (U+00DF, U+0130, U+0131, U+0390 ...) fold with nothing but their own lower/upper pair."""
+    f = c.casefold()
+    if len(f) == 1:
+        return f
+    low = c.lower()
+    return low if len(low) == 1 else c
 
 
 def equal_fold(a: str, b: str) -> bool:
-    return len(a) == len(b) and _ascii_lower(a) == _ascii_lower(b)
+    """strings.EqualFold: rune by rune, two runes are equal iff they are in the same simple-folding class."""
+    return len(a) == len(b) and all(x == y or _fold_rep(x) == _fold_rep(y) for x, y in zip(a, b))
 
 
-to_lower = _ascii_lower
+def to_lower(s: str) -> str:
+    """strings.ToLower: unicode.ToLower per rune = the simple lowercase mapping (U+0130 -> 'i', not 'i' + U+0307)."""
+    import _sre
+
+    return "".join(chr(_sre.unicode_tolower(ord(c))) for c in s)
 
 
 class BadPattern(Exception):

@@ -20,7 +20,8 @@ LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle.h")] + [
-        os.path.join(ROOT, "include", "cordum_b200.h"), os.path.join(ROOT, "common", "mini_json.hpp")]
+        os.path.join(ROOT, "include", "cordum_b200.h"), os.path.join(ROOT, "common", "mini_json.hpp"),
+        os.path.join(ROOT, "common", "go_unicode_tables.h")]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -47,6 +48,8 @@ def lib():
         L.oracle_eval_one_json.restype = C.c_int64
         L.oracle_path_match.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
         L.oracle_equal_fold.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.oracle_to_lower.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.oracle_to_lower.restype = C.c_int64
         L.oracle_trim_space.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_normalize_decision.argtypes = [C.c_char_p, C.c_uint64]
         L.oracle_parse_effective.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -66,6 +69,13 @@ def path_match(pat, name) -> int:
 def equal_fold(a, b) -> bool:
     a, b = _b(a), _b(b)
     return bool(lib().oracle_equal_fold(a, len(a), b, len(b)))
+
+
+def to_lower(s) -> bytes:
+    s = _b(s)
+    buf = C.create_string_buffer(4 * len(s) + 8)
+    n = lib().oracle_to_lower(s, len(s), buf, len(buf))
+    return buf.raw[:n]
 
 
 def trim_space(s) -> bytes:
