@@ -5,6 +5,7 @@
 // Object members keep their textual order and duplicates (callers decide the
 // duplicate rule; Go's encoding/json is "last one wins").
 #pragma once
+#include <cerrno>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,20 @@ class Parser {
     }
   }
 
+  // length of the valid UTF-8 sequence starting at p (2..4), 0 if p[0] does not start one
+  static size_t utf8_len(const char* q, size_t n) {
+    const unsigned char* p = (const unsigned char*)q;
+    unsigned c = p[0];
+    if (c < 0xC2 || c > 0xF4) return 0;
+    size_t need = c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : 1;
+    if (n < need + 1) return 0;
+    unsigned lo = 0x80, hi = 0xBF;
+    if (c == 0xE0) lo = 0xA0; else if (c == 0xED) hi = 0x9F; else if (c == 0xF0) lo = 0x90; else if (c == 0xF4) hi = 0x8F;
+    if (p[1] < lo || p[1] > hi) return 0;
+    for (size_t k = 2; k <= need; ++k) if ((p[k] & 0xC0) != 0x80) return 0;
+    return need + 1;
+  }
+
   bool hex4(uint32_t& v) {
     if (e_ - p_ < 4) return fail("short \\u escape");
     v = 0;
@@ -107,7 +122,16 @@ class Parser {
       unsigned char c = (unsigned char)*p_++;
       if (c == '"') return true;
       if (c < 0x20) return fail("control character in string");
-      if (c != '\\') { out.push_back(char(c)); continue; }
+      if (c != '\\') {
+        if (c < 0x80) { out.push_back(char(c)); continue; }
+        // encoding/json coerces string contents to well-formed UTF-8: every byte that does not start a valid sequence
+        // becomes U+FFFD (utf8.DecodeRune semantics, one replacement per byte)
+        --p_;
+        size_t w = utf8_len(p_, size_t(e_ - p_));
+        if (w == 0) { put_utf8(out, 0xFFFD); ++p_; }
+        else { out.append(p_, w); p_ += w; }
+        continue;
+      }
       if (p_ >= e_) return fail("unterminated escape");
       char esc = *p_++;
       switch (esc) {
@@ -165,8 +189,9 @@ class Parser {
     v.is_int = false;
     if (integral && tmp.size() <= 19) {
       char* end = nullptr;
+      errno = 0;
       long long ll = std::strtoll(tmp.c_str(), &end, 10);
-      if (end && *end == 0) { v.is_int = true; v.i = ll; }
+      if (end && *end == 0 && errno != ERANGE) { v.is_int = true; v.i = ll; }   // 2^63 saturates: keep the double
     }
     return true;
   }

@@ -102,6 +102,8 @@ def load() -> C.CDLL:
     L.cordum_test_slab_bytes.restype = u64
     L.cordum_test_host_encode.argtypes = [vp, vp, vp]
     L.cordum_test_host_table.argtypes = [vp, cp, C.POINTER(vp), C.POINTER(u64)]
+    L.cordum_test_json_canon.argtypes = [cp, u64, cp, u64]
+    L.cordum_test_json_canon.restype = i64
     L.cordum_test_host_scalar.argtypes = [vp, cp]
     L.cordum_test_host_scalar.restype = u64
     _lib = L

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -73,6 +74,7 @@ void json_dump(const mjson::Value& v, std::string& o) {
     case mjson::Kind::Bool: o += v.b ? "true" : "false"; break;
     case mjson::Kind::Number:
       if (v.is_int) o += std::to_string(v.i);
+      else if (!std::isfinite(v.d)) o += v.d < 0 ? "-1e999" : "1e999";   // beyond double: still a JSON number
       else { char b[40]; snprintf(b, sizeof b, "%.17g", v.d); o += b; }
       break;
     case mjson::Kind::String: o += json_quote(v.s); break;
@@ -336,7 +338,7 @@ bool eff_struct(const mjson::Value& v, EffSafety& cfg) {
       case 'm':
         if (x.is_null()) break;
         if (!x.is_obj()) { ok = false; break; }
-        for (auto& e : x.obj) if (!e.second.is_null() && !e.second.is_num()) ok = false;
+        for (auto& e : x.obj) if (!e.second.is_null() && !(e.second.is_num() && std::isfinite(e.second.d))) ok = false;   // float64 out of range: the Unmarshal fails
         break;
       case 'p': if (!eff_mcp(x, cfg.mcp)) ok = false; break;
     }
@@ -357,6 +359,14 @@ bool parse_effective_safety(sv payload, EffSafety& out) {
       if (eff_struct(*raw, out)) return true;
   out = EffSafety{};
   return false;
+}
+
+bool json_canon(sv text, std::string& out) {   // test hook: parse with the product's JSON reader, dump the tree
+  mjson::Value v;
+  if (!mjson::parse(text, v)) return false;
+  out.clear();
+  json_dump(v, out);
+  return true;
 }
 
 int test_glob(sv pattern, sv name) {

@@ -318,5 +318,6 @@ class Host {
 
 // test hooks (also exported through the C ABI as cordum_test_*)
 int test_glob(sv pattern, sv name);   // 1 match, 0 no, -1 malformed
+bool json_canon(sv text, std::string& out);   // parse + re-dump (differential test of common/mini_json.hpp)
 
 }  // namespace cordum

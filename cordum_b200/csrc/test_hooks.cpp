@@ -55,6 +55,15 @@ int32_t cordum_test_host_encode(void* h, const cordum_envelopes* env, uint8_t* s
   return ((Host*)h)->encode(env, c, t_err);
 }
 
+// common/mini_json.hpp (shared by the product and the oracle) differentially against an independent parser:
+// returns -1 when the document is rejected, else the length of the re-dumped tree (written to buf up to cap)
+int64_t cordum_test_json_canon(const char* text, uint64_t n, char* buf, uint64_t cap) {
+  std::string out;
+  if (!cordum::json_canon(sv(text, n), out)) return -1;
+  if (buf && cap) std::memcpy(buf, out.data(), out.size() < cap ? out.size() : cap);
+  return (int64_t)out.size();
+}
+
 // table access by name: returns pointer + byte length (valid until the next load/encode)
 int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint64_t* bytes) {
   const HostTables& t = ((Host*)h)->tables();

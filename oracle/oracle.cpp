@@ -43,6 +43,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -765,7 +766,7 @@ bool decode_safety_config(const mjson::Value& v, EffSafety& cfg) {
       case M:
         if (x.is_null()) break;
         if (!x.is_obj()) { ok = false; break; }
-        for (auto& e : x.obj) if (!e.second.is_null() && !e.second.is_num()) ok = false;
+        for (auto& e : x.obj) if (!e.second.is_null() && !(e.second.is_num() && std::isfinite(e.second.d))) ok = false;   // float64: strconv.ParseFloat range error fails the Unmarshal
         break;
       case P: if (!decode_mcp_policy(x, cfg.mcp)) ok = false; break;
     }

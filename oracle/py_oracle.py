@@ -354,8 +354,13 @@ def _field(key, names):
     return None
 
 
-def _is_num(x):
-    return isinstance(x, (int, float)) and not isinstance(x, bool)
+def _is_num(x):   # a JSON number that fits float64 (strconv.ParseFloat reports a range error otherwise)
+    if isinstance(x, bool) or not isinstance(x, (int, float)):
+        return False
+    try:
+        return float(x) not in (float("inf"), float("-inf"))
+    except OverflowError:
+        return False
 
 
 def _str_list(x):
