@@ -18,7 +18,7 @@
 #include "kernels.h"
 
 using cordum::Host;
-using cordum::HostColumns;
+using cordum::HostRecords;
 using cordum::HostTables;
 using cordum::sv;
 
@@ -51,10 +51,8 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// column slab layout for n jobs: 14 u32 columns, then 5 u64 columns (each 16 B aligned)
-constexpr int kU32Cols = 14, kU64Cols = 5;
-inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-inline size_t slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) + kU64Cols * align16((size_t)n * 8); }
+// record slab for n jobs: n JobRec (64 B), then n RouteRec (32 B) - one contiguous H2D copy of 96 B per job
+inline size_t slab_bytes(uint32_t n) { return (size_t)n * (sizeof(JobRec) + sizeof(RouteRec)); }
 
 }  // namespace
 
@@ -79,8 +77,9 @@ struct cordum_engine {
   cudaEvent_t ev_copy = nullptr, ev_prod = nullptr;
   DeviceTables dt{};             // device pointers + scalars, as passed to kernels
   // device copies, one DevBuf per host vector
-  DevBuf b_row_tenant, b_row_topic, b_row_cap, b_row_pack, b_row_actor, b_row_combo, b_row_risk, b_row_check, b_row_mcp[4];
-  DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule, b_tw_off, b_tw_cnt, b_tw_list;
+  DevBuf b_rows, b_row_check;   // all pass-row tables, word-major, in one array (tables.h)
+  DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule;
+  DevBuf b_sum_tenant, b_sum_topic, b_sum_cap, b_sum_pack, b_sum_actor, b_sum_combo, b_sum_risk;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi;
   DevBuf b_flush, b_lbm_off, b_rank_pos, b_chunk_pool, b_pool_chunk0, b_merge_list;
@@ -105,15 +104,16 @@ struct cordum_batch {
   uint64_t epoch = 0;
   bool encoded = false, resident = false, pending = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
-  uint8_t* h_cols = nullptr;     // pinned
+  uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
   uint8_t* d_cols = nullptr;
+  uint32_t* slot_of = nullptr;   // host: position of caller job j in the sorted records
   cordum_decision* h_out = nullptr;   // pinned
   cordum_decision* d_out = nullptr;
-  uint32_t* d_route = nullptr;        // [0] = count, [1..] = compacted list of dispatchable jobs
+  uint2* d_route = nullptr;           // [0].x = count, [2..] = compacted list of dispatchable jobs {slot, head}
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
   float total_ms = 0, kernel_ms = 0, policy_ms = 0, route_ms = 0;
-  HostColumns hc{};
+  HostRecords hr{};
 };
 
 namespace {
@@ -125,28 +125,14 @@ int fail(cordum_engine* e, cudaError_t err, const char* what) {
 }
 #define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(e, _e, what); } while (0)
 
-// carve the column pointers out of a slab for n jobs
-template <class P32, class P64>
-void carve(uint8_t* base, uint32_t n, P32** u32cols, P64** u64cols) {
-  size_t off = 0;
-  for (int i = 0; i < kU32Cols; ++i) { u32cols[i] = (P32*)(base + off); off += align16((size_t)n * 4); }
-  for (int i = 0; i < kU64Cols; ++i) { u64cols[i] = (P64*)(base + off); off += align16((size_t)n * 8); }
+void host_records(cordum_batch* b) {
+  b->hr.job = (JobRec*)b->h_cols;
+  b->hr.route = (RouteRec*)(b->h_cols + (size_t)b->n * sizeof(JobRec));
+  b->hr.slot_of = b->slot_of;
 }
-void host_columns(uint8_t* base, uint32_t n, HostColumns& c) {
-  uint32_t* a[kU32Cols]; uint64_t* b[kU64Cols];
-  carve(base, n, a, b);
-  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
-  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
-  c.effcfg = a[12]; c.flags = a[13];
-  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
-}
-void device_columns(uint8_t* base, uint32_t n, JobColumns& c) {
-  const uint32_t* a[kU32Cols]; const uint64_t* b[kU64Cols];
-  carve(base, n, a, b);
-  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
-  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
-  c.effcfg = a[12]; c.flags = a[13];
-  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
+void device_records(const cordum_batch* b, JobRecords& r) {
+  r.job = (const JobRec*)b->d_cols;
+  r.route = (const RouteRec*)(b->d_cols + (size_t)b->n * sizeof(JobRec));
 }
 
 template <class T>
@@ -163,42 +149,57 @@ int sync_tables(cordum_engine* e) {
   // reload, first sight of a topic) so a full device sync here is acceptable.
   CK(cudaDeviceSynchronize(), "sync before table upload");
   cudaStream_t s = e->s_tables;
+  if (t.v_policy != e->v_policy || t.v_topic != e->v_topic || t.v_mcp != e->v_mcp) {
+    // the unified word-major pass-row array (rebuilt whole: a few MB, and only on a reload or a first-seen topic)
+    const cordum::RowTable* tabs[11] = {&t.row_topic, &t.row_tenant, &t.row_cap, &t.row_pack, &t.row_actor, &t.row_combo, &t.row_risk,
+                                       &t.row_mcp[0], &t.row_mcp[1], &t.row_mcp[2], &t.row_mcp[3]};
+    uint32_t off[11], cells = 0;
+    for (int k = 0; k < 11; ++k) { off[k] = cells; cells += tabs[k]->n_rows; }
+    const size_t w4 = t.row_words / 4;
+    std::vector<uint32_t> wm((size_t)cells * t.row_words, 0);
+    for (int k = 0; k < 11; ++k)
+      for (size_t v = 0; v < tabs[k]->n_rows; ++v) {
+        const uint32_t* row = tabs[k]->row((uint32_t)v);
+        for (size_t w = 0; w < w4; ++w) std::memcpy(&wm[(w * cells + off[k] + v) * 4], row + 4 * w, 16);
+      }
+    CK(up(e->b_rows, wm, s), "upload");
+    CK(cudaStreamSynchronize(s), "upload");   // wm is a local
+    d.rows = (const Row16*)e->b_rows.p; d.n_cells = cells;
+    d.off_topic = off[0]; d.off_tenant = off[1]; d.off_cap = off[2]; d.off_pack = off[3]; d.off_actor = off[4];
+    d.off_combo = off[5]; d.off_risk = off[6];
+    for (int f = 0; f < 4; ++f) d.off_mcp[f] = off[7 + f];
+    d.n_topic = t.row_topic.n_rows;
+  }
   if (t.v_policy != e->v_policy) {
-    CK(up(e->b_row_tenant, t.row_tenant.data, s), "upload"); CK(up(e->b_row_cap, t.row_cap.data, s), "upload");
-    CK(up(e->b_row_pack, t.row_pack.data, s), "upload"); CK(up(e->b_row_actor, t.row_actor.data, s), "upload");
-    CK(up(e->b_row_combo, t.row_combo.data, s), "upload"); CK(up(e->b_row_risk, t.row_risk.data, s), "upload");
     CK(up(e->b_row_check, t.row_check.data, s), "upload");
+    CK(up(e->b_sum_tenant, t.sum_tenant, s), "upload"); CK(up(e->b_sum_cap, t.sum_cap, s), "upload");
+    CK(up(e->b_sum_pack, t.sum_pack, s), "upload"); CK(up(e->b_sum_actor, t.sum_actor, s), "upload");
+    CK(up(e->b_sum_combo, t.sum_combo, s), "upload"); CK(up(e->b_sum_risk, t.sum_risk, s), "upload");
     CK(up(e->b_req_need, t.rule_req_need, s), "upload"); CK(up(e->b_lab_need, t.rule_lab_need, s), "upload");
     CK(up(e->b_rule_dec, t.rule_dec, s), "upload"); CK(up(e->b_pos2rule, t.pos2rule, s), "upload");
     d.pos2rule = (const uint32_t*)e->b_pos2rule.p;
-    d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4; d.item_u4 = t.item_u4;
-    d.row_tenant = (const Row16*)e->b_row_tenant.p; d.n_tenant = t.row_tenant.n_rows;
-    d.row_cap = (const Row16*)e->b_row_cap.p; d.n_cap = t.row_cap.n_rows;
-    d.row_pack = (const Row16*)e->b_row_pack.p; d.n_pack = t.row_pack.n_rows;
-    d.row_actor = (const Row16*)e->b_row_actor.p; d.n_actor = t.row_actor.n_rows;
-    d.row_combo = (const Row16*)e->b_row_combo.p; d.row_risk = (const Row16*)e->b_row_risk.p; d.risk_zero_row = t.risk_zero_row;
-    d.row_check = (const Row16*)e->b_row_check.p;
+    d.n_rules = t.n_rules; d.n_seg = t.n_seg; d.row_u4 = t.n_seg * CORDUM_SEG_U4; d.sum_group = t.sum_group;
+    d.sum_tenant = (const uint64_t*)e->b_sum_tenant.p; d.sum_cap = (const uint64_t*)e->b_sum_cap.p;
+    d.sum_pack = (const uint64_t*)e->b_sum_pack.p; d.sum_actor = (const uint64_t*)e->b_sum_actor.p;
+    d.sum_combo = (const uint64_t*)e->b_sum_combo.p; d.sum_risk = (const uint64_t*)e->b_sum_risk.p;
+    d.chk_words = (const uint32_t*)e->b_row_check.p;
     d.rule_req_need = (const uint64_t*)e->b_req_need.p; d.rule_lab_need = (const uint64_t*)e->b_lab_need.p;
     d.rule_dec = (const uint8_t*)e->b_rule_dec.p;
     e->v_policy = t.v_policy;
   }
   if (t.v_topic != e->v_topic) {
-    CK(up(e->b_row_topic, t.row_topic.data, s), "upload"); CK(up(e->b_eff_topic, t.eff_topic, s), "upload");
+    CK(up(e->b_sum_topic, t.sum_topic, s), "upload");
+    CK(up(e->b_eff_topic, t.eff_topic, s), "upload");
     CK(up(e->b_topic_pool_off, t.topic_pool_off, s), "upload"); CK(up(e->b_topic_pool_cnt, t.topic_pool_cnt, s), "upload");
     CK(up(e->b_pool_list, t.pool_list, s), "upload");
-    CK(up(e->b_tw_off, t.tw_off, s), "upload"); CK(up(e->b_tw_cnt, t.tw_cnt, s), "upload"); CK(up(e->b_tw_list, t.tw_list, s), "upload");
-    d.tw_off = (const uint32_t*)e->b_tw_off.p; d.tw_cnt = (const uint32_t*)e->b_tw_cnt.p; d.tw_list = (const uint16_t*)e->b_tw_list.p;
-    d.row_topic = (const Row16*)e->b_row_topic.p; d.n_topic = t.row_topic.n_rows;
+    d.sum_topic = (const uint64_t*)e->b_sum_topic.p;
+    d.sum_use = t.sum_use;   // chosen against the topic rows (Host::choose_summaries)
     d.eff_topic = (const uint8_t*)e->b_eff_topic.p; d.topic_stride = t.topic_stride;
     d.topic_pool_off = (const uint32_t*)e->b_topic_pool_off.p; d.topic_pool_cnt = (const uint32_t*)e->b_topic_pool_cnt.p;
     d.pool_list = (const uint32_t*)e->b_pool_list.p;
     e->v_topic = t.v_topic;
   }
   if (t.v_mcp != e->v_mcp) {
-    for (int f = 0; f < 4; ++f) {
-      CK(up(e->b_row_mcp[f], t.row_mcp[f].data, s), "upload");
-      d.row_mcp[f] = (const Row16*)e->b_row_mcp[f].p; d.n_mcp[f] = t.row_mcp[f].n_rows; d.mcp_ones_row[f] = t.mcp_ones_row[f];
-    }
     CK(up(e->b_tenant_mcp, t.tenant_mcp, s), "upload"); CK(up(e->b_eff_mcp, t.eff_mcp, s), "upload");
     d.tenant_mcp = (const uint8_t*)e->b_tenant_mcp.p; d.eff_mcp = (const uint8_t*)e->b_eff_mcp.p; d.mcp_stride = t.mcp_stride;
     e->v_mcp = t.v_mcp;
@@ -313,8 +314,11 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   KParams P;
   cudaEvent_t ev_ready = nullptr;
+  // e->mu is held until every launch of this dispatch is enqueued: a table sync on another thread (first sight of a
+  // topic, a reload) synchronizes the device and may then free and reallocate table buffers - it must not slip in
+  // between view() and the launches that use those pointers.
+  std::lock_guard<std::mutex> g(e->mu);
   {
-    std::lock_guard<std::mutex> g(e->mu);
     std::lock_guard<std::mutex> gh(e->host->mutex());
     if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
     int rc = sync_tables(e);
@@ -338,13 +342,13 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     b->resident = true;
   }
   CK(cudaEventRecord(b->ev1, s), "event");
-  device_columns(b->d_cols, b->n, P.cols);
+  device_records(b, P.recs);
   P.out = b->d_out;
   P.n_jobs = b->n;
   P.honor_approved = mode == CORDUM_MODE_POLICY_AND_ROUTE ? 1u : 0u;
   P.route_count = nullptr; P.route_list = nullptr;
   if (mode == CORDUM_MODE_POLICY_AND_ROUTE) {   // policy_kernel compacts the dispatchable jobs for route_kernel
-    P.route_count = b->d_route; P.route_list = b->d_route + 4;
+    P.route_count = reinterpret_cast<uint32_t*>(b->d_route); P.route_list = b->d_route + 2;
     CK(cudaMemsetAsync(b->d_route, 0, sizeof(uint32_t), s), "reset route count");
   }
   // policy_kernel needs no worker state: it is NOT ordered after the heartbeat exchange / worker-table refresh kernels
@@ -405,6 +409,7 @@ static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resourc
   if (b->h_out) cudaFreeHost(b->h_out);
   if (b->d_out) cudaFree(b->d_out);
   if (b->d_route) cudaFree(b->d_route);
+  std::free(b->slot_of);
   for (cudaEvent_t ev : {b->ev0, b->ev1, b->evm, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -556,9 +561,9 @@ void cordum_engine_destroy(cordum_engine* e) {
     { std::lock_guard<std::mutex> g(e->mu); live.swap(e->batches); }
     for (cordum_batch* b : live) batch_release(b);
   }
-  DevBuf* all[] = {&e->b_row_tenant, &e->b_row_topic, &e->b_row_cap, &e->b_row_pack, &e->b_row_actor, &e->b_row_combo,
-                   &e->b_row_risk, &e->b_row_check, &e->b_row_mcp[0], &e->b_row_mcp[1], &e->b_row_mcp[2], &e->b_row_mcp[3],
-                   &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule, &e->b_tw_off, &e->b_tw_cnt, &e->b_tw_list,
+  DevBuf* all[] = {&e->b_rows, &e->b_row_check,
+                   &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule,
+                   &e->b_sum_tenant, &e->b_sum_topic, &e->b_sum_cap, &e->b_sum_pack, &e->b_sum_actor, &e->b_sum_combo, &e->b_sum_risk,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
                    &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos,
@@ -684,7 +689,9 @@ int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** o
   CK(cudaMalloc((void**)&b->d_cols, bytes), "device columns");
   CK(cudaHostAlloc((void**)&b->h_out, (size_t)max_jobs * sizeof(cordum_decision), cudaHostAllocDefault), "pinned results");
   CK(cudaMalloc((void**)&b->d_out, (size_t)max_jobs * sizeof(cordum_decision)), "device results");
-  CK(cudaMalloc((void**)&b->d_route, ((size_t)max_jobs + 4) * sizeof(uint32_t)), "device route list");
+  CK(cudaMalloc((void**)&b->d_route, ((size_t)max_jobs + 2) * sizeof(uint2)), "device route list");
+  b->slot_of = (uint32_t*)std::malloc((size_t)max_jobs * sizeof(uint32_t));
+  if (!b->slot_of) { g_err = "out of host memory"; return CORDUM_E_INVALID; }
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
   CK(cudaEventCreate(&b->ev0), "event"); CK(cudaEventCreate(&b->ev1), "event"); CK(cudaEventCreate(&b->evm), "event");
   CK(cudaEventCreate(&b->ev2), "event"); CK(cudaEventCreate(&b->ev3), "event");
@@ -713,9 +720,9 @@ int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes*
   b->n = env->n_jobs;
   b->encoded = false;
   b->resident = false;
-  host_columns(b->h_cols, b->n, b->hc);
+  host_records(b);
   uint64_t epoch_before = e->host->epoch();
-  int rc = e->host->encode(env, b->hc, g_err);
+  int rc = e->host->encode(env, b->hr, g_err);
   if (rc) return rc;
   b->epoch = epoch_before;
   b->encoded = true;
@@ -798,7 +805,7 @@ int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, cha
   else if (code == CORDUM_REASON_UNSUPPORTED_TOPIC) s = "unsupported topic";
   else if (code == CORDUM_REASON_APPROVAL_GRANTED) s = "approval granted";
   else if (code == CORDUM_REASON_EFF_DENIED_TOPIC || code == CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC) {
-    std::string topic(cordum::trim_space(e->host->topic_raw(b->hc.topic[job])));
+    std::string topic(cordum::trim_space(e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic)));
     s = "topic '" + topic + (code == CORDUM_REASON_EFF_DENIED_TOPIC ? "' denied by effective config" : "' not allowed by effective config");
   } else if ((code >= CORDUM_REASON_TENANT_MCP && code < CORDUM_REASON_TENANT_MCP + 8) ||
              (code >= CORDUM_REASON_EFF_MCP && code < CORDUM_REASON_EFF_MCP + 8)) {
@@ -806,7 +813,7 @@ int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, cha
     int f = (int)(k >> 1);
     // canonical (trimmed, ASCII-lowered) form of the value; the Go adapter substitutes the
     // request's own spelling, which it still holds
-    std::string v = e->host->mcp_value_string(f, b->hc.mcp[f][job]);
+    std::string v = e->host->mcp_value_string(f, b->hr.job[b->hr.slot_of[job]].mcp[f]);
     s = std::string("mcp ") + fields[f] + " " + go_quote(v) + ((k & 1) ? " not allowed" : " denied");
   }
   return copy_out(s, buf, cap);
@@ -820,7 +827,7 @@ int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, ch
   if ((r.route_status == CORDUM_ROUTE_OK || r.route_status == CORDUM_ROUTE_OK_PREFERRED) && r.worker_slot >= 0 &&
       (uint32_t)r.worker_slot < e->host->n_worker_slots()) {
     const std::string& id = e->host->worker_id((uint32_t)r.worker_slot);
-    s = id.empty() ? e->host->topic_raw(b->hc.topic[job]) : "worker." + id + ".jobs";   // bus/nats.go:94-99; :131-135
+    s = id.empty() ? e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic) : "worker." + id + ".jobs";   // bus/nats.go:94-99; :131-135
   }
   return copy_out(s, buf, cap);
 }

@@ -157,16 +157,16 @@ struct RowTable {                      // rows for one attribute, row-major
 struct TopicEntry { uint32_t flags; uint32_t pool_off, pool_cnt; };
 
 struct HostTables {
-  // policy
+  // policy (pass-rows are kept row-major here; the engine uploads them word-major, tables.h)
   uint32_t n_rules = 0, n_seg = 1, row_words = 32;
   RowTable row_tenant, row_topic, row_cap, row_pack, row_actor, row_combo, row_risk, row_check, row_mcp[4];
+  // per row: which 128-bit word groups hold any bit (bit g = words [g*sum_group, (g+1)*sum_group))
+  std::vector<uint64_t> sum_tenant, sum_topic, sum_cap, sum_pack, sum_actor, sum_combo, sum_risk;
+  uint32_t sum_group = 1, sum_use = 0;
   std::vector<uint64_t> rule_req_need, rule_lab_need;
   std::vector<uint8_t> rule_dec;
   std::vector<uint32_t> pos2rule;                 // bit position -> original rule index (0xFFFFFFFF = padding)
-  std::vector<uint32_t> tw_off, tw_cnt;           // per topic: its non-zero 128-bit words (offset/count into tw_list)
-  std::vector<uint16_t> tw_list;
   uint32_t mcp_stride = 2;
-  uint32_t risk_zero_row = 0, mcp_ones_row[4] = {0, 0, 0, 0};
   std::vector<uint8_t> tenant_mcp, eff_mcp, eff_topic;
   uint32_t topic_stride = 0, n_effcfg = 0;
   // routing
@@ -180,7 +180,6 @@ struct HostTables {
   std::vector<uint32_t> pool_off, pos_pool, pos_slot, pos_rank, slot_pos, rank_slot, rank_pos, lbm_off;
   uint32_t place_bits = 1;
   uint64_t lbm_words = 0;
-  uint32_t item_u4 = 1;                                        // 128-bit words per scan item (tables.h)
   std::vector<uint32_t> chunk_pool, pool_chunk0, merge_list;   // worker-table refresh work list (tables.h)
   uint32_t n_chunks = 0, n_merge = 0, merge_smem = 0;
   std::vector<uint64_t> pos_label_lo, pos_label_hi;
@@ -189,11 +188,12 @@ struct HostTables {
   uint64_t v_policy = 0, v_topic = 0, v_mcp = 0, v_routing = 0, v_workers = 0, v_loads = 0;
 };
 
-// Encoded batch columns on the host (engine allocates them pinned and hands pointers in).
-struct HostColumns {
-  uint32_t *tenant, *tenant_pol, *topic, *capability, *pack, *actor, *mcp[4], *pref_pool, *pref_worker, *effcfg;
-  uint64_t *risk_mask, *req_mask, *lab_mask, *place_lo, *place_hi;
-  uint32_t* flags;
+// Encoded batch on the host (engine allocates the record arrays pinned and hands pointers in).  Records are in
+// topic-sorted order; slot_of[j] is the position of caller job j (pageable host memory, host-side use only).
+struct HostRecords {
+  JobRec* job = nullptr;
+  RouteRec* route = nullptr;
+  uint32_t* slot_of = nullptr;
 };
 
 // Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks.  Completion
@@ -226,6 +226,7 @@ class WorkPool {
 class Host {
  public:
   Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads);
+  ~Host();
 
   // documents
   int load_policy(sv json, sv snapshot, std::string& err);
@@ -234,7 +235,7 @@ class Host {
   int update_loads(uint32_t n, const uint32_t* slots, const cordum_worker_load* loads, std::string& err);
 
   // encode a batch (thread-safe against itself via mu_)
-  int encode(const cordum_envelopes* env, HostColumns& out, std::string& err);
+  int encode(const cordum_envelopes* env, HostRecords& out, std::string& err);
 
   // bumps whenever dictionary ids may have been reassigned (policy / routing / worker reload):
   // batches encoded under an older epoch must be re-encoded before dispatch
@@ -261,6 +262,13 @@ class Host {
   std::string policy_capacity_error_, routing_capacity_error_;
   std::vector<WorkerRaw> workers_raw_;
   std::unique_ptr<WorkPool> pool_;   // created on first large encode
+  std::vector<std::unique_ptr<EncodeCaches>> caches_;   // one per encoder thread, generation-tagged
+  uint32_t encode_gen_ = 0;
+  std::vector<uint32_t> scratch_tid_, scratch_ten_, scratch_hist_;   // encode() temporaries, kept between calls
+  // sort key of the encoded records: (topic id, tenant class); class = which word group holds the tenant's per-tenant rule copies
+  static constexpr uint32_t kMaxTenantClasses = 16;
+  uint32_t tenant_classes_ = 1;
+  std::vector<uint8_t> tenant_class_;   // per tenant dictionary id
   PolicyModel policy_;
   RoutingModel routing_;
   std::string snapshot_;
@@ -275,6 +283,8 @@ class Host {
   uint64_t label_empty_mask_ = 0;   // bits of pairs whose value is ""
   std::string default_tenant_trim_;
   std::vector<std::vector<uint32_t>> rule_pos_;   // rule index -> its bit positions (see compile_policy)
+  std::vector<std::vector<std::string>> rule_pos_tenant_;   // parallel: "" = the copy stands for every tenant the rule lists,
+                                                            // else the one (folded) tenant this copy stands for
   // topic patterns (distinct trimmed pattern -> rules)
   struct Pattern { Glob glob; std::vector<uint32_t> rules; };
   std::vector<Pattern> patterns_;
@@ -310,10 +320,12 @@ class Host {
   uint32_t add_effcfg(sv payload);     // under mu_
   void topic_row(sv trimmed, Bits& out) const;
   void eff_topic_fill(uint32_t cfg, uint32_t topic_id);
-  void topic_words_append(const uint32_t* row);
-  void encode_range(const cordum_envelopes* env, uint32_t a, uint32_t b, HostColumns& out,
-                    std::vector<uint32_t>& misses, std::unique_ptr<struct EncodeCaches>& cc) const;
-  void encode_job(const cordum_envelopes* env, uint32_t j, HostColumns& out, bool& miss, struct EncodeCaches& cc) const;
+  uint64_t row_summary(const uint32_t* row) const;
+  void choose_summaries();
+  void summarize(const RowTable& rt, std::vector<uint64_t>& out) const;
+  uint32_t resolve_topic(const cordum_envelopes* env, uint32_t j, struct EncodeCaches& cc) const;   // kMiss = not in the dictionary
+  uint32_t resolve_tenant(const cordum_envelopes* env, uint32_t j, struct EncodeCaches& cc) const;   // id | exact-policy index << 16
+  void encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uint32_t ten, JobRec& jr, RouteRec& rr, bool& miss, struct EncodeCaches& cc) const;
 };
 
 // test hooks (also exported through the C ABI as cordum_test_*)

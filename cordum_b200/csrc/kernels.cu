@@ -9,15 +9,19 @@
 //                        jobs that may dispatch (engine.go:298-347)
 //
 // Integer / bit work only: no tensor cores (north star).  Mapping to the hardware:
-//   * job columns are column-major; a warp loads 32 consecutive jobs with one coalesced 128 B request per u32
-//     column (256 B per u64 column) through the read-only, no-L1-allocate path
-//   * rule predicates live in bit-rows ("pass-rows"); rule bits are laid out so that a topic touches few 128-bit
-//     words, and a warp walks the (job, word) items of its 32 jobs densely: one 128-bit gather per row per lane,
-//     7-12 independent gathers in flight, all lanes on one instruction stream
-//   * the tables are a few MB: L2-resident, hot rows L1-resident; DRAM traffic is the job columns and records
-//   * first match / argmin = ballot, ffs, shuffles and shared-memory atomicMin; worker pools are kept sorted by
-//     load (bitonic sort in shared memory) so label-constrained picks are bitmap ANDs
-//   * decision records are written back coalesced, 16 B per lane
+//   * a batch is two record arrays sorted by topic (64 B policy record, 32 B routing record per job).  A warp owns a
+//     tile of 32 consecutive records; its 2 KB of policy records arrive in shared memory by ONE bulk async copy
+//     (cp.async.bulk, completion on an mbarrier), issued for the next tile as soon as the lanes hold the current one in
+//     registers, so the copy of tile k+1 overlaps the evaluation of tile k; lane = job, four 128-bit shared loads
+//   * rule predicates live in bit-rows ("pass-rows") over rule positions; per attribute value a 64-bit summary says
+//     which 128-bit words of its row hold anything.  A lane ANDs the summaries of its job's values and visits only the
+//     surviving words; the warp walks the union of its lanes' live words, and because the records are topic-sorted and
+//     the tables are stored word-major (tab[word][value]), the lanes' 16 B gathers for one word fall into few cache
+//     lines (the gather rate of L1 - one 128 B line per cycle - is what bounds this kernel, not HBM)
+//   * the tables are a few MB: L2-resident, hot words L1-resident; DRAM traffic is the records and the results
+//   * first match = lowest surviving bit per word -> pos2rule -> min over words, all in the lane's registers; argmin
+//     over workers = per-pool sorted views + label bitmaps (bitonic sort in shared memory at refresh time)
+//   * decision records are written to the job's original index, 16 B per lane
 // IEEE float32 with explicit _rn intrinsics, no fast-math: scores compare exactly like Go's.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,18 +35,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint4 ld_row(const Row16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
 __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
 __device__ __forceinline__ uint64_t shfl64(unsigned mask, uint64_t v, int src) {
   uint32_t lo = __shfl_sync(mask, (uint32_t)v, src), hi = __shfl_sync(mask, (uint32_t)(v >> 32), src);
@@ -230,153 +222,162 @@ __global__ void __launch_bounds__(256) worker_merge_kernel(DeviceTables T) {
 }
 
 // ------------------------------------------------------------------ policy: first match + decision
-// A warp owns a tile of 32 consecutive jobs (lane = job for the coalesced column loads, the scalar
-// decision logic and the 16 B record store).  Needs no worker state, so it runs concurrently with the
-// heartbeat exchange and the worker-table refresh.
-//   P  the per-topic word lists of the tile's 32 jobs are walked 32 (job, word) items at a time: each lane ANDs one
-//      128-bit word of the 7-12 pass-rows its job selects (rule bits are permuted so that a topic touches few
-//      words); surviving bits map back to original rule indices; first match = min per job.
-//   D  decision mapping, tenant MCP, effective-config overlay, approval flags, scheduler post-step:
-//      thread per job.
-template <int MINB, int IU>
+// A warp owns a tile of 32 consecutive (topic-sorted) job records: lane = job.  Needs no worker state, so it runs
+// concurrently with the heartbeat exchange and the worker-table refresh.
+//   L  the tile's records arrive in shared memory through one bulk async copy per tile (prefetched one tile ahead)
+//   P  live words = AND of the summaries of the job's attribute values; the warp walks the union of its lanes' live
+//      words; in each, a lane ANDs the 128-bit cells of the 7-12 rows its job selects; the lowest surviving bit maps
+//      back to an original rule index; first match = min over words
+//   D  decision mapping, tenant MCP, effective-config overlay, approval flags, scheduler post-step
+namespace {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (the TMA engine; no tensor map needed for a contiguous run), completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint4 and3(uint4 a, uint4 b, uint4 c) { return make_uint4(a.x & b.x & c.x, a.y & b.y & c.y, a.z & b.z & c.z, a.w & b.w & c.w); }
+}  // namespace
+
+template <int MINB>
 __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
   const DeviceTables& T = P.t;
-  const JobColumns& C = P.cols;
-  const unsigned lane = threadIdx.x & 31;
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t n_tiles = (P.n_jobs + 31u) >> 5;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t rowu4 = T.row_u4;
+  __shared__ __align__(128) JobRec s_tile[8][32];   // one tile per warp
+  __shared__ __align__(8) uint64_t s_bar[8];
+  JobRec* tile_buf = s_tile[wib];
+  uint64_t* bar = &s_bar[wib];
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  auto prefetch = [&](uint32_t tile) {   // lane 0: this warp's next tile, global -> shared
+    if (lane == 0 && tile < n_tiles) {
+      const uint32_t jobs = P.n_jobs - tile * 32u < 32u ? P.n_jobs - tile * 32u : 32u;
+      const uint32_t bytes = jobs * (uint32_t)sizeof(JobRec);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' reads of the buffer precede the async write
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(tile_buf, P.recs.job + (size_t)tile * 32u, bytes, bar);
+    }
+  };
+  prefetch(warp_id);
+  uint32_t parity = 0;
+  const uint32_t n_words = T.row_u4, G = T.sum_group, use = T.sum_use;
 
   for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
-    const uint32_t j = tile * 32 + lane;
-    const bool valid = j < P.n_jobs;
-    // only what the rule scan needs stays in registers; the rest is fetched where it is used
-    uint32_t c_tenant = 0, c_topic = 0, c_cap = 0, c_pack = 0, c_actor = 0, c_flags = 0;
-    uint64_t c_risk = 0;
+    const uint32_t s = tile * 32 + lane;   // slot in the sorted order
+    const bool valid = s < P.n_jobs;
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    // ---- L: the lane's record, four 128-bit shared loads
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
     if (valid) {
-      c_flags = ld_stream_u32(C.flags + j); c_topic = ld_stream_u32(C.topic + j);
-      c_tenant = ld_stream_u32(C.tenant + j);
-      c_cap = ld_stream_u32(C.capability + j); c_pack = ld_stream_u32(C.pack + j); c_actor = ld_stream_u32(C.actor + j);
-      c_risk = ld_stream_u64(C.risk_mask + j);
+      const uint4* rp = reinterpret_cast<const uint4*>(tile_buf + lane);
+      q0 = rp[0]; q1 = rp[1]; q2 = rp[2]; q3 = rp[3];
     }
+    __syncwarp();
+    prefetch(tile + warps_total);
+    const uint32_t c_topic = q0.x, c_flags = q0.y, c_orig = q0.z, c_tenant = q0.w & 0xFFFFu, c_tpol = q0.w >> 16;
+    const uint32_t c_cap = q1.x & 0xFFFFu, c_pack = q1.x >> 16, c_actor = q1.y & 0xFFFFu, c_eff = q1.y >> 16;
+    const uint32_t mid[4] = {q1.z & 0xFFFFu, q1.z >> 16, q1.w & 0xFFFFu, q1.w >> 16};
+    const uint64_t c_risk = ((uint64_t)q2.y << 32) | q2.x, c_req = ((uint64_t)q2.w << 32) | q2.z, c_lab = ((uint64_t)q3.y << 32) | q3.x;
 
     // =================================================================== P: first matching rule
-    // Rule bits are permuted (and multi-pattern rules duplicated) so that a topic's pass-row is non-zero in only a
-    // few 128-bit words: its word list.  The word lists of the tile's 32 jobs are laid end to end and the 32 lanes
-    // walk that sequence 32 items at a time: lane = one (job, word) item.  It ANDs that word of the 7-12 rows the
-    // job selects and turns surviving bits back into ORIGINAL rule indices (pos2rule); the first match is the
-    // minimum per job (shared-memory atomicMin; survivors are rare).  Every lane is busy in every step and all
-    // lanes run one instruction stream.
     const bool bypass = P.honor_approved && (c_flags & JF_APPROVED);                                    // engine.go:484-522
     const bool early = (c_flags & (JF_TOPIC_MISSING | JF_TOPIC_UNSUPPORTED)) != 0;                        // kernel.go:171-176
     const bool eval = valid && !bypass && !early;
-    __shared__ uint32_t s_best[8][32];
-    uint32_t* my_best = s_best[threadIdx.x >> 5];
-    int first = -1;
-    {
-      const uint32_t o_combo = CORDUM_COMBO_INDEX(c_flags) * rowu4, o_tenant = c_tenant * rowu4, o_topic = c_topic * rowu4,
-                     o_cap = c_cap * rowu4, o_pack = c_pack * rowu4, o_actor = c_actor * rowu4;
-      uint32_t c_twoff = 0, c_twcnt = 0;
-      if (eval) { c_twoff = __ldg(T.tw_off + c_topic); c_twcnt = __ldg(T.tw_cnt + c_topic); }
-      uint32_t incl = c_twcnt;   // inclusive prefix sum of the word counts over the tile
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += t; }
-      const uint32_t excl = incl - c_twcnt, total = __shfl_sync(FULL, incl, 31);
-      my_best[lane] = 0xFFFFFFFFu;
-      __syncwarp();
-      const uint32_t* chk_words = reinterpret_cast<const uint32_t*>(T.row_check);
-      for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-        const uint32_t q = q0 + lane;
-        const bool have = q < total;
-        // owner of item q = the last lane whose exclusive prefix is <= q (binary search over the warp's registers)
-        int jl = 0;
-#pragma unroll
-        for (int st = 16; st; st >>= 1) { const uint32_t e = __shfl_sync(FULL, excl, jl + st); if (e <= q) jl += st; }
-        const uint32_t li = q - __shfl_sync(FULL, excl, jl);
-        const uint32_t fl = __shfl_sync(FULL, c_flags, jl);
-        const uint32_t twoff = __shfl_sync(FULL, c_twoff, jl);   // every lane takes part in every shuffle
-        // wi: the item's first 128-bit word within a row (item 0: valid address for idle lanes)
-        const uint32_t wi = have ? (uint32_t)__ldg(T.tw_list + twoff + li) * (uint32_t)IU : 0u;
-        const Row16* p_combo = T.row_combo + __shfl_sync(FULL, o_combo, jl) + wi;
-        const Row16* p_tenant = T.row_tenant + __shfl_sync(FULL, o_tenant, jl) + wi;
-        const Row16* p_topic = T.row_topic + __shfl_sync(FULL, o_topic, jl) + wi;
-        const Row16* p_cap = T.row_cap + __shfl_sync(FULL, o_cap, jl) + wi;
-        const Row16* p_pack = T.row_pack + __shfl_sync(FULL, o_pack, jl) + wi;
-        const Row16* p_actor = T.row_actor + __shfl_sync(FULL, o_actor, jl) + wi;
-        uint4 acc[IU];
-#pragma unroll
-        for (int u = 0; u < IU; ++u)
-          acc[u] = and4(and4(and4(ld_row(p_combo + u), ld_row(p_tenant + u)), and4(ld_row(p_topic + u), ld_row(p_cap + u))),
-                        and4(ld_row(p_pack + u), ld_row(p_actor + u)));
-        {   // risk tags: containsAny = OR over the job's tags (:308-318).  Branch-free: row 0 = "no referenced tag",
-            // row 1+b = tag b, and lanes that ran out of tags read the all-zero row.
-          uint64_t m = shfl64(FULL, c_risk, jl);
-          uint32_t idx = (uint32_t)__ffsll((long long)m);   // 0 when the job has no referenced tag, else 1 + lowest bit
-          m &= m - 1;
-          uint4 rk[IU];
-#pragma unroll
-          for (int u = 0; u < IU; ++u) rk[u] = ld_row(T.row_risk + (idx * rowu4 + wi + u));
-          while (__any_sync(FULL, m != 0)) {
-            idx = m ? (uint32_t)__ffsll((long long)m) : T.risk_zero_row;
-            m &= m - 1;
-#pragma unroll
-            for (int u = 0; u < IU; ++u) rk[u] = or4(rk[u], ld_row(T.row_risk + (idx * rowu4 + wi + u)));
-          }
-#pragma unroll
-          for (int u = 0; u < IU; ++u) acc[u] = and4(acc[u], rk[u]);
-        }
-        const uint32_t jsrc = tile * 32 + (uint32_t)jl;   // the job this lane works for (MCP ids / masks are read on demand)
-        const bool mcp_used = have && (fl & JF_MCP_USED);
-        if (__any_sync(FULL, mcp_used)) {   // mcpMatch (:365-382); lanes whose job carries no MCP labels read the all-ones row
-#pragma unroll
-          for (int qf = 0; qf < 4; ++qf) {
-            const uint32_t id = mcp_used ? __ldg(C.mcp[qf] + jsrc) : T.mcp_ones_row[qf];
-#pragma unroll
-            for (int u = 0; u < IU; ++u) acc[u] = and4(acc[u], ld_row(T.row_mcp[qf] + (id * rowu4 + wi + u)));
-          }
-        }
-        // Surviving bits -> original rule index.  Inside an item the positions ascend with the rule index, so the
-        // lowest surviving bit is the item's first match; a further bit is looked at only when that rule carries a
-        // requires / labels subset test (containsAll :320-330, labelsMatch :332-345) and the test fails.
-        uint32_t best = 0xFFFFFFFFu;
-        uint32_t w[4 * IU];
-#pragma unroll
-        for (int u = 0; u < IU; ++u) {
-          w[4 * u] = have ? acc[u].x : 0u; w[4 * u + 1] = have ? acc[u].y : 0u;
-          w[4 * u + 2] = have ? acc[u].z : 0u; w[4 * u + 3] = have ? acc[u].w : 0u;
-        }
-        bool alive;   // this lane still has a surviving bit whose rule has not passed its subset test
-        do {
-          uint32_t sel = 0, base = 0;   // lowest non-zero 32-bit word of the item
-#pragma unroll
-          for (int k = 4 * IU - 1; k >= 0; --k) if (w[k]) { sel = w[k]; base = 32u * (uint32_t)k; }
-          const bool nz = sel != 0;
-          alive = false;
-          if (__any_sync(FULL, nz)) {
-            const uint32_t pos = nz ? wi * 128u + base + (uint32_t)__ffs((int)sel) - 1u : 0u;
-            const uint32_t r = __ldg(T.pos2rule + pos);
-            bool ok = nz;
-            if (nz && ((__ldg(chk_words + (pos >> 5)) >> (pos & 31)) & 1u)) {
-              const uint64_t req = __ldg(C.req_mask + jsrc), lab = __ldg(C.lab_mask + jsrc);
-              const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
-              ok = ((need & ~req) == 0) && (ln == 0 || ((fl & JF_HAS_LABELS) && (ln & ~lab) == 0));
-            }
-            if (ok) best = r;
-            alive = nz && !ok;
-            if (alive) {   // drop the bit just handled and look at the next one (rare)
-              const uint32_t drop = sel & (sel - 1);
-#pragma unroll
-              for (int k = 0; k < 4 * IU; ++k) if (base == 32u * (uint32_t)k) w[k] = drop;
-            }
-          }
-        } while (__any_sync(FULL, alive));
-        if (best != 0xFFFFFFFFu) atomicMin(&my_best[jl], best);
+    const bool mcp_used = (c_flags & JF_MCP_USED) != 0;
+    const uint32_t combo = CORDUM_COMBO_INDEX(c_flags);
+    uint64_t live = 0;
+    if (eval) {
+      live = __ldg(T.sum_topic + c_topic);
+      if (use & SUM_TENANT) live &= __ldg(T.sum_tenant + c_tenant);
+      if (use & SUM_CAP) live &= __ldg(T.sum_cap + c_cap);
+      if (use & SUM_PACK) live &= __ldg(T.sum_pack + c_pack);
+      if (use & SUM_ACTOR) live &= __ldg(T.sum_actor + c_actor);
+      if (use & SUM_COMBO) live &= __ldg(T.sum_combo + combo);
+      if (use & SUM_RISK) {
+        uint64_t rs = c_risk ? 0ull : __ldg(T.sum_risk);
+        for (uint64_t m = c_risk; m; m &= m - 1) rs |= __ldg(T.sum_risk + __ffsll((long long)m));
+        live &= rs;
       }
-      __syncwarp();
-      first = (int)my_best[lane];   // 0xFFFFFFFF -> -1: no rule matched
-      __syncwarp();
     }
+    // cell indices inside one word of the unified table: fixed for the tile
+    const uint32_t i_topic = T.off_topic + c_topic, i_tenant = T.off_tenant + c_tenant, i_cap = T.off_cap + c_cap,
+                   i_pack = T.off_pack + c_pack, i_actor = T.off_actor + c_actor, i_combo = T.off_combo + combo;
+    // risk tags: containsAny = OR over the job's tags (:308-318); row 0 = "no referenced tag", row 1+b = tag b.  The first
+    // three rows are loaded without branching (a job with fewer tags repeats its first row); a fourth tag onwards loops.
+    uint64_t rm = c_risk;
+    const uint32_t i_risk0 = T.off_risk + (uint32_t)__ffsll((long long)rm);
+    rm &= rm - 1;
+    const bool risk2 = rm != 0;
+    const uint32_t i_risk1 = risk2 ? T.off_risk + (uint32_t)__ffsll((long long)rm) : i_risk0;
+    rm &= rm - 1;
+    const bool risk3 = rm != 0;
+    const uint32_t i_risk2 = risk3 ? T.off_risk + (uint32_t)__ffsll((long long)rm) : i_risk0;
+    rm &= rm - 1;   // tags beyond the third
+    uint32_t best = 0xFFFFFFFFu;
+    uint32_t u_lo = __reduce_or_sync(FULL, (uint32_t)live), u_hi = __reduce_or_sync(FULL, (uint32_t)(live >> 32));
+    for (uint64_t un = ((uint64_t)u_hi << 32) | u_lo; un; un &= un - 1) {   // warp-uniform walk over the union
+      const uint32_t g = (uint32_t)__ffsll((long long)un) - 1u;
+      if (!((live >> g) & 1ull)) continue;
+      for (uint32_t w = g * G; w < (g + 1) * G && w < n_words; ++w) {
+        const uint4* bw = reinterpret_cast<const uint4*>(T.rows) + (size_t)w * T.n_cells;
+        uint4 rk = __ldg(bw + i_risk0);
+        if (risk2) rk = or4(rk, __ldg(bw + i_risk1));
+        if (risk3) rk = or4(rk, __ldg(bw + i_risk2));
+        for (uint64_t m = rm; m; m &= m - 1) rk = or4(rk, __ldg(bw + T.off_risk + (uint32_t)__ffsll((long long)m)));
+        uint4 acc = and3(__ldg(bw + i_topic), __ldg(bw + i_tenant), __ldg(bw + i_cap));
+        acc = and3(acc, __ldg(bw + i_pack), __ldg(bw + i_actor));
+        acc = and3(acc, __ldg(bw + i_combo), rk);
+        if (mcp_used) {   // mcpMatch (:365-382)
+          acc = and3(acc, __ldg(bw + T.off_mcp[0] + mid[0]), __ldg(bw + T.off_mcp[1] + mid[1]));
+          acc = and3(acc, __ldg(bw + T.off_mcp[2] + mid[2]), __ldg(bw + T.off_mcp[3] + mid[3]));
+        }
+        // Surviving bits -> original rule index.  Inside a word the positions ascend with the rule index, so the lowest
+        // surviving bit is the word's first match; a further bit is looked at only when that rule carries a requires /
+        // labels subset test (containsAll :320-330, labelsMatch :332-345) and the test fails.
+        uint32_t wv[4] = {acc.x, acc.y, acc.z, acc.w};
+        while (wv[0] | wv[1] | wv[2] | wv[3]) {
+          uint32_t sel = 0, base = 0;
+#pragma unroll
+          for (int k = 3; k >= 0; --k) if (wv[k]) { sel = wv[k]; base = 32u * (uint32_t)k; }
+          const uint32_t pos = w * 128u + base + (uint32_t)__ffs((int)sel) - 1u;
+          const uint32_t r = __ldg(T.pos2rule + pos);
+          bool ok = true;
+          if ((__ldg(T.chk_words + (pos >> 5)) >> (pos & 31)) & 1u) {
+            const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
+            ok = ((need & ~c_req) == 0) && (ln == 0 || ((c_flags & JF_HAS_LABELS) && (ln & ~c_lab) == 0));
+          }
+          if (ok) { best = r < best ? r : best; break; }
+          const uint32_t drop = sel & (sel - 1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (base == 32u * (uint32_t)k) wv[k] = drop;
+        }
+      }
+    }
+    const int first = (int)best;   // 0xFFFFFFFF -> -1: no rule matched
 
     // =================================================================== D: decision (thread per job)
     uint32_t dec = CORDUM_DEC_UNSPECIFIED, sched = CORDUM_DEC_UNSPECIFIED, rflags = 0, reason = 0;
@@ -386,10 +387,6 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
       else if (c_flags & JF_TOPIC_MISSING) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_MISSING_TOPIC; }
       else if (c_flags & JF_TOPIC_UNSUPPORTED) { dec = sched = CORDUM_DEC_DENY; reason = CORDUM_REASON_UNSUPPORTED_TOPIC; }
       else {
-        const bool mcp_used = c_flags & JF_MCP_USED;
-        const uint32_t c_tpol = ld_stream_u32(C.tenant_pol + j), c_eff = ld_stream_u32(C.effcfg + j);
-        uint32_t mid[4] = {0, 0, 0, 0};
-        if (mcp_used) { mid[0] = __ldg(C.mcp[0] + j); mid[1] = __ldg(C.mcp[1] + j); mid[2] = __ldg(C.mcp[2] + j); mid[3] = __ldg(C.mcp[3] + j); }
         rule = first;
         uint32_t code = CORDUM_DEC_ALLOW;
         bool hascons = false;
@@ -424,10 +421,9 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
       }
     }
 
-    if (valid) {   // coalesced 16 B store per lane; the route fields are filled by route_kernel
-      const uint32_t head = dec | (sched << 8) | (rflags << 16);
-      reinterpret_cast<uint4*>(P.out)[j] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, 0xFFFFFFFFu);
-    }
+    const uint32_t head = dec | (sched << 8) | (rflags << 16);
+    if (valid)   // 16 B store per lane at the job's original index; the route fields are filled by route_kernel
+      reinterpret_cast<uint4*>(P.out)[c_orig] = make_uint4(head, reason & 0xFFu, (uint32_t)rule, 0xFFFFFFFFu);
     if (P.route_list) {   // compact the jobs that may dispatch (engine.go:298-347): one atomic per tile
       const bool dr = valid && (sched == CORDUM_DEC_ALLOW || sched == CORDUM_DEC_ALLOW_WITH_CONSTRAINTS);
       const unsigned m = __ballot_sync(FULL, dr);
@@ -435,7 +431,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(P.route_count, (uint32_t)__popc(m));
         base = __shfl_sync(FULL, base, 0);
-        if (dr) P.route_list[base + __popc(m & ((1u << lane) - 1u))] = j;
+        if (dr) P.route_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(s, head);   // slot + what policy decided
       }
     }
   }
@@ -453,7 +449,6 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
 template <bool ROUTE_ONLY, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
   const DeviceTables& T = P.t;
-  const JobColumns& C = P.cols;
   const unsigned lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   const uint32_t n_items = ROUTE_ONLY ? P.n_jobs : *P.route_count;
   const uint32_t n_tiles = (n_items + 31u) >> 5;
@@ -463,15 +458,17 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
   for (uint32_t tile = warp_id; tile < n_tiles; tile += warps_total) {
     const uint32_t item = tile * 32 + lane;
     const bool valid = item < n_items;
-    const uint32_t j = valid ? (ROUTE_ONLY ? item : P.route_list[item]) : 0u;
-    uint4 rec = make_uint4(0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint32_t j = 0, head = 0, c_orig = 0;   // j: slot in the sorted record arrays
     uint32_t c_flags = 0, c_topic = 0, c_ppool = 0, c_pwork = 0;
     uint64_t c_req = 0, c_plo = 0, c_phi = 0;
     if (valid) {
-      if (!ROUTE_ONLY) rec = reinterpret_cast<const uint4*>(P.out)[j];
-      c_flags = __ldg(C.flags + j); c_topic = __ldg(C.topic + j);
-      c_ppool = __ldg(C.pref_pool + j); c_pwork = __ldg(C.pref_worker + j);
-      c_req = __ldg(C.req_mask + j); c_plo = __ldg(C.place_lo + j); c_phi = __ldg(C.place_hi + j);
+      if (ROUTE_ONLY) j = item;
+      else { const uint2 e = P.route_list[item]; j = e.x; head = e.y; }
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.recs.job + j));   // topic, flags, orig of the 64 B record
+      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(P.recs.route + j)), r1 = __ldg(reinterpret_cast<const uint4*>(P.recs.route + j) + 1);
+      c_topic = a.x; c_flags = a.y; c_orig = a.z;
+      c_plo = ((uint64_t)r0.y << 32) | r0.x; c_phi = ((uint64_t)r0.w << 32) | r0.z;
+      c_req = ((uint64_t)r1.y << 32) | r1.x; c_ppool = r1.z; c_pwork = r1.w;
     }
     uint32_t rflags = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
     int slot = -1;
@@ -667,9 +664,10 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       } else route = total > 0 ? CORDUM_ROUTE_POOL_OVERLOADED : CORDUM_ROUTE_NO_WORKERS;
     }
     if (valid) {
-      rec.x = (rec.x & 0x00FFFFFFu) | (rflags << 16) | (route << 24);   // rflags only adds CORDUM_F_TIE
-      rec.w = (uint32_t)slot;
-      reinterpret_cast<uint4*>(P.out)[j] = rec;
+      const uint32_t h = (head & 0x00FFFFFFu) | (rflags << 16) | (route << 24);   // rflags only adds CORDUM_F_TIE
+      uint32_t* o = reinterpret_cast<uint32_t*>(P.out + c_orig);
+      if (ROUTE_ONLY) *reinterpret_cast<uint4*>(o) = make_uint4(h, 0u, 0xFFFFFFFFu, (uint32_t)slot);
+      else { o[0] = h; o[3] = (uint32_t)slot; }   // policy_kernel wrote the record; only these two words change
     }
   }
 }
@@ -685,11 +683,10 @@ static cudaError_t configure_kernels() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 32; }();   // tuning knob
+  static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 72; }();   // tuning knob (policy_kernel: 16 KB of record tiles per CTA)
   const int pct = (kb * 100 + 227) / 228;
   const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
-                       (const void*)policy_kernel<4, 1>, (const void*)policy_kernel<5, 1>, (const void*)policy_kernel<4, 2>,
-                       (const void*)policy_kernel<5, 2>, (const void*)policy_kernel<3, 4>, (const void*)policy_kernel<4, 4>,
+                       (const void*)policy_kernel<3>, (const void*)policy_kernel<4>, (const void*)policy_kernel<5>, (const void*)policy_kernel<6>,
                        (const void*)route_kernel<true>, (const void*)route_kernel<false>,
                        (const void*)route_kernel<false, 3>, (const void*)route_kernel<false, 5>};
   for (const void* f : fns) {
@@ -726,13 +723,12 @@ static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   if (P.n_jobs == 0) return cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
-  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 5; }();   // tuning knob
+  static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
   const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
-  const uint32_t iu = P.t.item_u4;
-  if (iu == 1) { if (minb >= 5) policy_kernel<5, 1><<<blocks, 256, 0, s>>>(P); else policy_kernel<4, 1><<<blocks, 256, 0, s>>>(P); }
-  else if (iu == 2) { if (minb >= 5) policy_kernel<5, 2><<<blocks, 256, 0, s>>>(P); else policy_kernel<4, 2><<<blocks, 256, 0, s>>>(P); }
-  else if (iu == 4) { if (minb >= 4) policy_kernel<4, 4><<<blocks, 256, 0, s>>>(P); else policy_kernel<3, 4><<<blocks, 256, 0, s>>>(P); }
-  else return cudaErrorInvalidValue;
+  if (minb <= 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 4) policy_kernel<4><<<blocks, 256, 0, s>>>(P);
+  else if (minb == 5) policy_kernel<5><<<blocks, 256, 0, s>>>(P);
+  else policy_kernel<6><<<blocks, 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 

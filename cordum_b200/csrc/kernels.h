@@ -6,12 +6,12 @@
 #include "tables.h"
 
 struct KParams {
-  JobColumns cols;        // device pointers to the encoded columns of this batch
+  JobRecords recs;        // device pointers to the encoded (topic-sorted) records of this batch
   DeviceTables t;         // device pointers to the compiled tables
   cordum_decision* out;   // device, n_jobs records
   uint32_t n_jobs;
   uint32_t* route_count;     // device: number of jobs policy_kernel found dispatchable (null: no compaction)
-  uint32_t* route_list;      // device: their job indices
+  uint2* route_list;         // device: {slot in the sorted records, head word policy_kernel wrote} per dispatchable job
   uint32_t honor_approved;   // POLICY_AND_ROUTE: jobs flagged JF_APPROVED bypass the policy (engine.go:484-522)
 };
 

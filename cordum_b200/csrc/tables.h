@@ -1,12 +1,16 @@
-// tables.h — layout of the compiled tables and encoded job columns, shared by the
+// tables.h — layout of the compiled tables and encoded job records, shared by the
 // host compiler/encoder (C++) and the CUDA kernels.  Plain C structs only.
 //
 // Bit-parallel first-match: for every dictionary value v of every scalar
-// attribute a there is a PASS-ROW: an R-bit vector whose bit r says "rule r's predicate on a
-// passes for v" (vacuous predicates -> 1).  A job's candidate rules = AND of the rows its
-// attribute values select; the lowest set bit is Go's first match (safety_policy.go:192-204).
-// Rows are padded to whole SEGMENTS of 1024 rules = 128 B = one cache line = 8 lanes x uint4,
-// which is the unit the kernel scans in rule order with early exit.
+// attribute a there is a PASS-ROW: a bit vector over rule POSITIONS whose bit p says "the rule at
+// position p passes its predicate on a for v" (vacuous predicates -> 1).  A job's candidate rules =
+// AND of the rows its attribute values select; the first match is the minimum original rule index
+// over the surviving bits (safety_policy.go:192-204).  Positions are laid out by the compiler so
+// that a job's AND is non-zero in few 128-bit words (host.cpp compile_policy):
+//   * per attribute value a 64-bit SUMMARY says which words of its row hold any bit; a job ANDs the
+//     summaries first and only visits the words that survive;
+//   * on the device a table is stored WORD-MAJOR, tab[word][value] (16 B cells): jobs are sorted by
+//     topic, so the lanes of a warp visit the same word and their gathers fall into few cache lines.
 #pragma once
 #include <stdint.h>
 
@@ -14,8 +18,8 @@
 typedef struct __attribute__((aligned(16))) Row16 { uint32_t w[4]; } Row16;
 typedef struct __attribute__((aligned(16))) Load16 { int32_t active, max_parallel; float cpu, gpu; } Load16;
 
-#define CORDUM_SEG_RULES 1024u          /* rules per segment                                  */
-#define CORDUM_SEG_U4 8u                /* uint4 per row per segment (8 lanes x 16 B = 128 B) */
+#define CORDUM_SEG_RULES 1024u          /* rule positions per segment (rows are padded to whole segments) */
+#define CORDUM_SEG_U4 8u                /* 128-bit words per row per segment                              */
 #define CORDUM_GROUP 8u                 /* lanes cooperating on one job                       */
 
 /* dictionary ids common to every attribute */
@@ -45,55 +49,67 @@ typedef struct __attribute__((aligned(16))) Load16 { int32_t active, max_paralle
 
 #define CORDUM_PREF_UNKNOWN 0xFFFFFFFFu /* preferred_pool / preferred_worker_id names nothing known    */
 
-/* Encoded job columns: column-major (one contiguous array per attribute), 96 B/job. */
-typedef struct JobColumns {
-  const uint32_t* tenant;       /* tenant dictionary id (fold+trim canonical)                */
-  const uint32_t* tenant_pol;   /* 1 + index into policy.Tenants by EXACT string, 0 = none   */
-  const uint32_t* topic;        /* topic dictionary id (keyed by the raw topic string)       */
-  const uint32_t* capability;
-  const uint32_t* pack;
-  const uint32_t* actor;
-  const uint32_t* mcp[4];       /* server, tool, resource, action                            */
-  const uint32_t* pref_pool;    /* 0 none, else 1 + pool id, or CORDUM_PREF_UNKNOWN          */
-  const uint32_t* pref_worker;  /* 0 none, else 1 + worker slot, or CORDUM_PREF_UNKNOWN      */
-  const uint32_t* effcfg;       /* 0 none/unparsable, else effective-config id               */
-  const uint64_t* risk_mask;    /* bit per referenced risk tag                               */
-  const uint64_t* req_mask;     /* bit per referenced requires token (rules U pools)         */
-  const uint64_t* lab_mask;     /* bit per rule label pair (k,v): labels.get(k,"") == v      */
-  const uint64_t* place_lo;     /* placement need mask, bits 0..63                           */
-  const uint64_t* place_hi;     /* bits 64..127                                              */
-  const uint32_t* flags;        /* JF_*                                                      */
-} JobColumns;
+/* DeviceTables.sum_use */
+#define SUM_TENANT 1u
+#define SUM_CAP 2u
+#define SUM_PACK 4u
+#define SUM_ACTOR 8u
+#define SUM_COMBO 16u
+#define SUM_RISK 32u
+
+/* Encoded jobs: two record arrays in the SAME order - sorted by topic id (stable), so that a warp's 32
+   consecutive jobs share their topic's rows.  `orig` is the job's index in the caller's batch; results are written
+   there.  Dictionary ids are 16-bit (a dictionary holds only values some rule / pool / tenant policy references). */
+typedef struct __attribute__((aligned(16))) JobRec {   /* 64 B: everything policy_kernel reads */
+  uint32_t topic;        /* topic dictionary id (keyed by the raw topic string)                        */
+  uint32_t flags;        /* JF_*                                                                       */
+  uint32_t orig;         /* index of the job in the caller's batch                                     */
+  uint16_t tenant;       /* tenant dictionary id (fold+trim canonical)                                 */
+  uint16_t tenant_pol;   /* 1 + index into policy.Tenants by EXACT string, 0 = none                    */
+  uint16_t cap, pack, actor;
+  uint16_t effcfg;       /* 0 none/unparsable, else effective-config id                                */
+  uint16_t mcp[4];       /* server, tool, resource, action                                             */
+  uint64_t risk;         /* bit per referenced risk tag                                                */
+  uint64_t req;          /* bit per referenced requires token, EqualFold canonical (rules' containsAll) */
+  uint64_t lab;          /* bit per rule label pair (k,v): labels.get(k,"") == v                       */
+  uint32_t spare[2];
+} JobRec;
+typedef struct __attribute__((aligned(16))) RouteRec {   /* 32 B: what only route_kernel reads */
+  uint64_t place_lo, place_hi;   /* placement need mask                                                */
+  uint64_t req_pool;     /* bit per requires token, ToLower canonical (poolSatisfies)                  */
+  uint32_t pref_pool;    /* 0 none, else 1 + pool id, or CORDUM_PREF_UNKNOWN                           */
+  uint32_t pref_worker;  /* 0 none, else 1 + worker slot, or CORDUM_PREF_UNKNOWN                       */
+} RouteRec;
 #define CORDUM_JOB_IN_BYTES 96u
 #define CORDUM_JOB_OUT_BYTES 16u
+#define CORDUM_ID16_MAX 65535u
+
+typedef struct JobRecords {
+  const JobRec* job;
+  const RouteRec* route;
+} JobRecords;
 
 /* Everything the kernels read besides the job columns.  Pointers are device pointers. */
 #define CORDUM_POOL_CHUNK 512u
 #define CORDUM_POOL_SORT_MAX 8192u
 
 typedef struct DeviceTables {
-  /* ---- policy */
-  uint32_t n_rules, n_seg, row_u4;            /* row_u4 = n_seg * 8 uint4 per pass-row                 */
-  uint32_t item_u4;                           /* uint4 (128-bit words) per scan item: a lane ANDs item_u4 * 128 rule bits
-                                                 per step; tw_list holds item indices (1, 2 or 4)                  */
-  const Row16* row_tenant;  uint32_t n_tenant;
-  const Row16* row_topic;   uint32_t n_topic;
-  const Row16* row_cap;     uint32_t n_cap;
-  const Row16* row_pack;    uint32_t n_pack;
-  const Row16* row_actor;   uint32_t n_actor;
-  const Row16* row_combo;                     /* 6 rows: (actor_type, secrets) & alive-rule mask        */
-  const Row16* row_risk;                      /* row 0: job has no referenced tag; row 1+b: tag bit b   */
-  uint32_t risk_zero_row;                     /* index of an all-zero row (padding for branch-free OR loops) */
-  const Row16* row_mcp[4];  uint32_t n_mcp[4];
-  uint32_t mcp_ones_row[4];                   /* index of an all-ones row per MCP table (jobs without MCP labels) */
-  const Row16* row_check;                     /* rules carrying a requires/labels need-mask             */
+  /* ---- policy.  All pass-row tables live in ONE word-major array on the device: the 16 B cell of word w for value v of
+     table X is rows[w * n_cells + off_X + v] (n_cells = rows of all tables together), so a lane keeps one 32-bit cell
+     index per attribute for the whole tile and a word costs one base computation.
+     sum_X[v] bit g = "row v has a bit in word group g" (group g = words [g*sum_group, (g+1)*sum_group)). */
+  uint32_t n_rules, n_seg, row_u4;            /* row_u4 = n_seg * 8 128-bit words per pass-row                       */
+  uint32_t sum_group;                         /* words per summary bit = ceil(row_u4 / 64)                            */
+  uint32_t sum_use;                           /* SUM_* bits: attributes whose summaries are worth ANDing              */
+  const Row16* rows;  uint32_t n_cells;
+  uint32_t off_topic, off_tenant, off_cap, off_pack, off_actor, off_combo, off_risk, off_mcp[4];
+  uint32_t n_topic;                           /* topic rows (the dictionary grows on first sight of a topic)          */
+  const uint64_t *sum_topic, *sum_tenant, *sum_cap, *sum_pack, *sum_actor, *sum_combo, *sum_risk;
+  const uint32_t* chk_words;                  /* bit per position: the rule carries a requires/labels need-mask       */
   const uint64_t* rule_req_need;              /* per rule: requires tokens it needs (subset test)       */
   const uint64_t* rule_lab_need;              /* per rule: label pairs it needs                          */
   const uint8_t* rule_dec;                    /* per rule: CORDUM_DEC_* | 0x80 if constraints non-empty */
-  const uint32_t* pos2rule;                   /* bit position -> rule index: rule bits are permuted so that topic rows are sparse */
-  const uint32_t* tw_off;                     /* per topic: offset of its word list in tw_list                           */
-  const uint32_t* tw_cnt;                     /* per topic: number of non-zero 128-bit words of its pass-row             */
-  const uint16_t* tw_list;                    /* word indices (units of Row16 within a row)                              */
+  const uint32_t* pos2rule;                   /* bit position -> rule index                              */
   /* tenant-level MCP lists (kernel.go:190-195) and effective-config overlay (kernel.go:218-231):
      verdict per (entry, field, value id): 0 ok, 1 denied, 2 not allowed */
   const uint8_t* tenant_mcp; uint32_t mcp_stride;   /* [n_tenant_pol][4][mcp_stride]                    */

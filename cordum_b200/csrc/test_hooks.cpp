@@ -10,14 +10,12 @@
 #include "host.hpp"
 
 using cordum::Host;
-using cordum::HostColumns;
+using cordum::HostRecords;
 using cordum::HostTables;
 using cordum::sv;
 
 namespace {
 thread_local std::string t_err;
-constexpr int kU32Cols = 14, kU64Cols = 5;
-inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 }  // namespace
 
 extern "C" {
@@ -37,22 +35,17 @@ int32_t cordum_test_host_workers(void* h, const cordum_workers* w) { return ((Ho
 int32_t cordum_test_host_update(void* h, uint32_t n, const uint32_t* slots, const cordum_worker_load* loads) {
   return ((Host*)h)->update_loads(n, slots, loads, t_err);
 }
-uint64_t cordum_test_slab_bytes(uint32_t n) { return kU32Cols * align16((size_t)n * 4) + kU64Cols * align16((size_t)n * 8); }
+uint64_t cordum_test_slab_bytes(uint32_t n) { return (uint64_t)n * (sizeof(JobRec) + sizeof(RouteRec) + sizeof(uint32_t)); }
 
-// encode into `slab` (cordum_test_slab_bytes(n) bytes): same layout as a batch's pinned columns
+// encode into `slab` (cordum_test_slab_bytes(n) bytes, 16 B aligned): n JobRec, then n RouteRec (both in topic-sorted
+// order, as a batch's pinned buffers hold them), then slot_of[n]
 int32_t cordum_test_host_encode(void* h, const cordum_envelopes* env, uint8_t* slab) {
   uint32_t n = env->n_jobs;
-  uint32_t* a[kU32Cols];
-  uint64_t* b[kU64Cols];
-  size_t off = 0;
-  for (int i = 0; i < kU32Cols; ++i) { a[i] = (uint32_t*)(slab + off); off += align16((size_t)n * 4); }
-  for (int i = 0; i < kU64Cols; ++i) { b[i] = (uint64_t*)(slab + off); off += align16((size_t)n * 8); }
-  HostColumns c;
-  c.tenant = a[0]; c.tenant_pol = a[1]; c.topic = a[2]; c.capability = a[3]; c.pack = a[4]; c.actor = a[5];
-  c.mcp[0] = a[6]; c.mcp[1] = a[7]; c.mcp[2] = a[8]; c.mcp[3] = a[9]; c.pref_pool = a[10]; c.pref_worker = a[11];
-  c.effcfg = a[12]; c.flags = a[13];
-  c.risk_mask = b[0]; c.req_mask = b[1]; c.lab_mask = b[2]; c.place_lo = b[3]; c.place_hi = b[4];
-  return ((Host*)h)->encode(env, c, t_err);
+  HostRecords r;
+  r.job = (JobRec*)slab;
+  r.route = (RouteRec*)(slab + (size_t)n * sizeof(JobRec));
+  r.slot_of = (uint32_t*)(slab + (size_t)n * (sizeof(JobRec) + sizeof(RouteRec)));
+  return ((Host*)h)->encode(env, r, t_err);
 }
 
 // common/mini_json.hpp (shared by the product and the oracle) differentially against an independent parser:
@@ -74,7 +67,9 @@ int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint
   VEC("row_risk", t.row_risk.data) VEC("row_check", t.row_check.data)
   VEC("row_mcp0", t.row_mcp[0].data) VEC("row_mcp1", t.row_mcp[1].data) VEC("row_mcp2", t.row_mcp[2].data)
   VEC("row_mcp3", t.row_mcp[3].data)
-  VEC("pos2rule", t.pos2rule) VEC("tw_off", t.tw_off) VEC("tw_cnt", t.tw_cnt) VEC("tw_list", t.tw_list)
+  VEC("pos2rule", t.pos2rule)
+  VEC("sum_tenant", t.sum_tenant) VEC("sum_topic", t.sum_topic) VEC("sum_cap", t.sum_cap) VEC("sum_pack", t.sum_pack)
+  VEC("sum_actor", t.sum_actor) VEC("sum_combo", t.sum_combo) VEC("sum_risk", t.sum_risk)
   VEC("rule_req_need", t.rule_req_need) VEC("rule_lab_need", t.rule_lab_need) VEC("rule_dec", t.rule_dec)
   VEC("tenant_mcp", t.tenant_mcp) VEC("eff_mcp", t.eff_mcp) VEC("eff_topic", t.eff_topic)
   VEC("topic_pool_off", t.topic_pool_off) VEC("topic_pool_cnt", t.topic_pool_cnt) VEC("pool_list", t.pool_list)
@@ -92,7 +87,8 @@ uint64_t cordum_test_host_scalar(void* h, const char* name) {
   std::string n(name);
   if (n == "n_rules") return t.n_rules;
   if (n == "n_seg") return t.n_seg;
-  if (n == "item_u4") return t.item_u4;
+  if (n == "sum_group") return t.sum_group;
+  if (n == "sum_use") return t.sum_use;
   if (n == "n_chunks") return t.n_chunks;
   if (n == "n_merge") return t.n_merge;
   if (n == "merge_smem") return t.merge_smem;

@@ -20,14 +20,18 @@ JF_REQ_NONEMPTY, JF_REQ_UNKNOWN, JF_PLACE_UNSAT = 0x40, 0x80, 0x100
 JF_TOPIC_MISSING, JF_TOPIC_UNSUPPORTED, JF_TOPIC_RAW_EMPTY = 0x200, 0x400, 0x800
 PREF_UNKNOWN = 0xFFFFFFFF
 KEY_NONE = (1 << 64) - 1
-U32_COLS = ["tenant", "tenant_pol", "topic", "capability", "pack", "actor", "mcp0", "mcp1", "mcp2", "mcp3",
-            "pref_pool", "pref_worker", "effcfg", "flags"]
-U64_COLS = ["risk_mask", "req_mask", "lab_mask", "place_lo", "place_hi"]
+JOB_DTYPE = np.dtype([("topic", "<u4"), ("flags", "<u4"), ("orig", "<u4"), ("tenant", "<u2"), ("tenant_pol", "<u2"),
+                      ("capability", "<u2"), ("pack", "<u2"), ("actor", "<u2"), ("effcfg", "<u2"), ("mcp", "<u2", (4,)),
+                      ("risk_mask", "<u8"), ("req_mask", "<u8"), ("lab_mask", "<u8"), ("spare", "<u4", (2,))])
+ROUTE_DTYPE = np.dtype([("place_lo", "<u8"), ("place_hi", "<u8"), ("req_pool", "<u8"), ("pref_pool", "<u4"), ("pref_worker", "<u4")])
+assert JOB_DTYPE.itemsize == 64 and ROUTE_DTYPE.itemsize == 32
+SUM_TENANT, SUM_CAP, SUM_PACK, SUM_ACTOR, SUM_COMBO, SUM_RISK = 1, 2, 4, 8, 16, 32
 TABLES = {
     "row_tenant": np.uint32, "row_topic": np.uint32, "row_cap": np.uint32, "row_pack": np.uint32,
     "row_actor": np.uint32, "row_combo": np.uint32, "row_risk": np.uint32, "row_check": np.uint32,
     "row_mcp0": np.uint32, "row_mcp1": np.uint32, "row_mcp2": np.uint32, "row_mcp3": np.uint32,
-    "pos2rule": np.uint32, "tw_off": np.uint32, "tw_cnt": np.uint32, "tw_list": np.uint16,
+    "pos2rule": np.uint32, "sum_tenant": np.uint64, "sum_topic": np.uint64, "sum_cap": np.uint64, "sum_pack": np.uint64,
+    "sum_actor": np.uint64, "sum_combo": np.uint64, "sum_risk": np.uint64,
     "rule_req_need": np.uint64, "rule_lab_need": np.uint64, "rule_dec": np.uint8, "tenant_mcp": np.uint8,
     "eff_mcp": np.uint8, "eff_topic": np.uint8, "topic_pool_off": np.uint32, "topic_pool_cnt": np.uint32,
     "pool_list": np.uint32, "pool_req_mask": np.uint64, "pool_req_nonempty": np.uint8, "pool_off": np.uint32,
@@ -35,7 +39,7 @@ TABLES = {
     "pos_label_lo": np.uint64, "pos_label_hi": np.uint64, "loads": wire.LOAD_DTYPE,
     "chunk_pool": np.uint32, "pool_chunk0": np.uint32, "merge_list": np.uint32,
 }
-SCALARS = ["n_rules", "n_seg", "item_u4", "n_chunks", "n_merge", "merge_smem", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
+SCALARS = ["n_rules", "n_seg", "sum_group", "sum_use", "n_chunks", "n_merge", "merge_smem", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
            "n_pos", "n_slots", "n_topics"]
 
 
@@ -94,18 +98,32 @@ class HostHarness:
         self._ck(self.L.cordum_test_host_update(self.h, len(slots), slots.ctypes.data, loads.ctypes.data))
 
     def encode(self, env) -> dict:
+        """Encoded records as the batch holds them (topic-sorted), un-sorted into caller order for the walk; the
+        sorted arrays are kept under "_job" / "_route" / "_slot_of" for tests of the order itself."""
         if not isinstance(env, wire.EnvelopeBatch):
             env = wire.EnvelopeBatch.from_jobs(env)
         n = env.n_jobs
-        slab = np.zeros(int(self.L.cordum_test_slab_bytes(n)) + 16, dtype=np.uint8)
+        slab = np.zeros(int(self.L.cordum_test_slab_bytes(n)) + 64, dtype=np.uint8)
+        base = (-slab.ctypes.data) % 16
+        slab = slab[base:]
         self._ck(self.L.cordum_test_host_encode(self.h, C.addressof(env.struct), slab.ctypes.data))
-        cols, off = {}, 0
-        for name in U32_COLS:
-            cols[name] = slab[off: off + 4 * n].view(np.uint32).copy()
-            off += _align16(4 * n)
-        for name in U64_COLS:
-            cols[name] = slab[off: off + 8 * n].view(np.uint64).copy()
-            off += _align16(8 * n)
+        job = slab[: 64 * n].view(JOB_DTYPE).copy()
+        route = slab[64 * n: 96 * n].view(ROUTE_DTYPE).copy()
+        slot_of = slab[96 * n: 100 * n].view(np.uint32).copy()
+        assert np.array_equal(job["orig"][slot_of], np.arange(n, dtype=np.uint32)), "slot_of / orig are not inverse"
+        assert np.all(np.diff(job["topic"].astype(np.int64)) >= 0), "records are not sorted by topic id"
+        # inside a topic the records are grouped by tenant class; the sort is stable, so two neighbours with the same
+        # topic and the same tenant keep their batch order
+        same = (np.diff(job["topic"].astype(np.int64)) == 0) & (np.diff(job["tenant"].astype(np.int64)) == 0)
+        assert np.all(np.diff(job["orig"].astype(np.int64))[same] > 0), "the sort is not stable"
+        j, r = job[slot_of], route[slot_of]
+        cols = {k: j[k] for k in ("topic", "flags", "tenant", "tenant_pol", "capability", "pack", "actor", "effcfg",
+                                  "risk_mask", "req_mask", "lab_mask")}
+        for f in range(4):
+            cols["mcp%d" % f] = j["mcp"][:, f]
+        for k in ("place_lo", "place_hi", "req_pool", "pref_pool", "pref_worker"):
+            cols[k] = r[k]
+        cols["_job"], cols["_route"], cols["_slot_of"] = job, route, slot_of
         return cols
 
     def tables(self) -> dict:
@@ -209,15 +227,39 @@ def walk(T, cols, mode) -> np.ndarray:
                         acc = acc & rows["row_mcp%d" % f][mid[f]]
                 chk = rows["row_check"][0]
                 lab = int(cols["lab_mask"][j])
-                # rule bits are permuted: only the topic's listed 128-bit words can hold survivors, and the
-                # first match is the minimum ORIGINAL rule index over the surviving bits (kernels.cu phase P)
-                o, c = int(T["tw_off"][topic]), int(T["tw_cnt"][topic])
-                listed = [int(x) for x in T["tw_list"][o:o + c]]
-                iw = 4 * int(T["item_u4"])   # u32 words per scan item
+                # rule bits are permuted; the kernel ANDs the per-row summaries first and visits only the word groups
+                # that survive (kernels.cu phase P): no surviving bit may lie outside them.  The first match is the
+                # minimum ORIGINAL rule index over the surviving bits.
+                G = int(T["sum_group"])
+                use = int(T["sum_use"])
+                live = int(T["sum_topic"][topic])
+                if use & SUM_TENANT:
+                    live &= int(T["sum_tenant"][cols["tenant"][j]])
+                if use & SUM_CAP:
+                    live &= int(T["sum_cap"][cols["capability"][j]])
+                if use & SUM_PACK:
+                    live &= int(T["sum_pack"][cols["pack"][j]])
+                if use & SUM_ACTOR:
+                    live &= int(T["sum_actor"][cols["actor"][j]])
+                if use & SUM_COMBO:
+                    live &= int(T["sum_combo"][(flags & JF_COMBO_MASK) + ((flags >> 14) & 3) * 6])
+                if use & SUM_RISK:
+                    rs = int(T["sum_risk"][0]) if risk == 0 else 0
+                    for b in range(64):
+                        if risk >> b & 1:
+                            rs |= int(T["sum_risk"][1 + b])
+                    live &= rs
+                n128 = W // 4
+                listed = [w for w in range(n128) if live >> (w // G) & 1]
                 outside = acc.copy()
                 for wi in listed:
-                    outside[iw * wi: iw * wi + iw] = 0
-                assert not outside.any(), "a surviving bit lies outside the topic's item list"
+                    outside[4 * wi: 4 * wi + 4] = 0
+                assert not outside.any(), "a surviving bit lies outside the live word groups"
+                # the summaries themselves must be exact: a group is flagged iff the row has a bit there
+                trow = rows["row_topic"][topic]
+                for g in range((n128 + G - 1) // G):
+                    assert bool(trow[4 * G * g: 4 * G * (g + 1)].any()) == bool(int(T["sum_topic"][topic]) >> g & 1)
+                iw = 4
                 best = 1 << 62
                 for wi in listed:
                     # like the kernel: inside a word positions ascend with the rule index, so the first surviving bit
@@ -230,7 +272,7 @@ def walk(T, cols, mode) -> np.ndarray:
                             bits &= bits - 1
                             pos = w * 32 + b
                             r = int(T["pos2rule"][pos])
-                            assert r >= prev, "positions inside a scan item must ascend with the rule index"
+                            assert r >= prev, "positions inside a word must ascend with the rule index"
                             prev = r
                             if int(chk[w]) >> b & 1:
                                 need, ln = int(T["rule_req_need"][r]), int(T["rule_lab_need"][r])
@@ -303,7 +345,7 @@ def walk(T, cols, mode) -> np.ndarray:
                     route = wire.ROUTE_NO_POOL_TOPIC
                 if route == 0:
                     req_any, req_unknown = bool(flags & JF_REQ_NONEMPTY), bool(flags & JF_REQ_UNKNOWN)
-                    need_req = req_mask & ~T["req_blank_mask"]
+                    need_req = int(cols["req_pool"][j]) & ~T["req_blank_mask"]
                     need_lo, need_hi = int(cols["place_lo"][j]), int(cols["place_hi"][j])
                     unsat = bool(flags & JF_PLACE_UNSAT)
                     labelled = (need_lo | need_hi) != 0 or unsat
