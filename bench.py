@@ -346,57 +346,73 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     sync_all()
 
     # ---------------------------------------------------------------- end to end: `e2e`
+    # Input = string-level envelopes in host memory where NOTHING is shared between jobs: every job's strings are laid out
+    # contiguously, job after job, as a shim unpacking protobuf JobRequests would leave them (wire.EnvelopeBatch.deinterned).
+    # The variant with an interned arena (equal strings share one span, which lets the encoder resolve values by address)
+    # is measured beside it and reported as `interned_arena`.
     e2e_steps = max(4, min(args.steps, 12))
-    for k in range(2):
-        batches[k % 2].encode(my_jobs)
-        step(k, batches[k % 2], False)
-    sync_all()
-    t0 = time.perf_counter()
-    enc_ms = []
-    for k in range(e2e_steps):
-        b = batches[k % 2]
-        te = time.perf_counter()
-        b.encode(my_jobs)                  # waits for this batch's previous run, then host encode
-        enc_ms.append((time.perf_counter() - te) * 1e3)
-        step(k, b, False)                  # H2D columns + kernels + D2H records, async
-    sync_all()
-    e2e_elapsed = time.perf_counter() - t0
-    log("e2e per-step encode(+wait) ms:", " ".join("%.1f" % x for x in enc_ms))
-    # from already-encoded pinned columns (copies + kernels only)
+    plain_jobs = my_jobs.deinterned()
+
+    def e2e_run(jobs_in):
+        for k in range(2):
+            batches[k % 2].encode(jobs_in)
+            step(k, batches[k % 2], False)
+        sync_all()
+        t0 = time.perf_counter()
+        enc = []
+        for k in range(e2e_steps):
+            b = batches[k % 2]
+            te = time.perf_counter()
+            b.encode(jobs_in)                  # waits for this batch's previous run, then host encode
+            enc.append((time.perf_counter() - te) * 1e3)
+            step(k, b, False)                  # H2D records + kernels + D2H decisions, async
+        sync_all()
+        return time.perf_counter() - t0, enc
+
+    e2e_elapsed, enc_ms = e2e_run(plain_jobs)
+    chk2 = batches[(e2e_steps - 1) % 2].results()
+    assert np.array_equal(chk2["decision"], ref_result["decision"]) and np.array_equal(chk2["rule_idx"], ref_result["rule_idx"]), \
+        "the de-interned envelopes encode to different decisions"
+    log("e2e per-step encode(+wait) ms, de-interned arena:", " ".join("%.1f" % x for x in enc_ms))
+    e2e_int_elapsed, enc_int_ms = e2e_run(my_jobs)
+    log("e2e per-step encode(+wait) ms, interned arena:   ", " ".join("%.1f" % x for x in enc_int_ms))
+    # from already-encoded pinned records (copies + kernels only)
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         step(k, batches[k % 2], False)
     sync_all()
     e2e_cols_elapsed = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([e2e_elapsed, e2e_cols_elapsed], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed, e2e_cols_elapsed = float(t[0].item()), float(t[1].item())
+        e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed = (float(x) for x in t.tolist())
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
 
     peak, peak_src = measured_peaks()
-    # dominant kernel = policy_kernel.  Its algorithmic bytes per job: the columns it must read (flags, topic, tenant,
-    # capability, pack, actor, tenant_pol, effcfg: 8 x 4 B; risk mask 8 B) + the 16 B record it writes = 56 B, plus the
-    # policy tables once per launch.  (MCP ids and requires/label masks are read only for the jobs that need them.)
-    pol_job_bytes = 8 * 4 + 8 + out_b
+    # Dominant kernel = policy_kernel.  Its algorithmic bytes per job: the 64 B policy record it reads + the 16 B decision
+    # record it writes + 8 B per dispatchable job into the route list (counted as 8 B for every job: an upper bound on
+    # what it may write), plus the policy tables once per launch.
+    pol_job_bytes = 64 + out_b + 8
     pol_tables = int(st.passrow_bytes + st.rulecol_bytes)
     algo_bytes = n_shard * pol_job_bytes + pol_tables
     k_ms = float(np.mean(pol_ms))
     r_ms = float(np.mean(rte_ms))
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    path_bytes = n_shard * (in_b + out_b) + table_bytes
+    # whole path: 96 B of records in (64 B policy + 32 B routing), 16 B out, the 8 B route-list entry written and read
+    path_bytes = n_shard * (in_b + out_b + 16) + table_bytes
     path_gbs = path_bytes / ((k_ms + r_ms) * 1e-3) / 1e9
-    # SURVEY.md §8(d) fixes 100 B per decision (84 B of attribute columns + the 16 B record) + the tables once per batch for
-    # the whole path; this layout moves 112 B (96 B of columns; route_kernel re-reads the record), so both are reported
+    # SURVEY.md §8(d) fixes 100 B per decision (84 B of attribute columns + the 16 B record) + the tables once per batch
     s8d_bytes = n_shard * 100 + table_bytes
     s8d_gbs = s8d_bytes / ((k_ms + r_ms) * 1e-3) / 1e9
     traffic = None
+    traffic_note = None
     tp = os.path.join(ROOT, "profiles", "policy_kernel_traffic.json")
-    if os.path.exists(tp) and world == 1:
-        with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    if os.path.exists(tp) and world == 1:   # from the ncu --set full capture of this kernel (tools/ncu_metrics.py); the
+        with open(tp) as f:                  # file names the commit it was taken at, so a stale number is visible
+            tj = json.load(f)
+        traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("source")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -418,15 +434,20 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                    "l2": "inputs larger than L2: steps rotate over %d resident copies of the shard (%.0f MB total)" % (
                        n_rot, n_rot * shard_bytes / 1e6),
                    "step": "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else ""),
+                   "layout": "jobs as topic-sorted 64 B + 32 B records (host encoder), bulk-async tile loads",
                    "exchange": args.exchange},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(n_shard * in_b + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
-                "includes": "cordum_encode of string-level envelopes on the host + pinned H2D + kernels + D2H, 2 batches in flight",
-                "from_encoded_columns": J * e2e_steps / e2e_cols_elapsed, "host_encode_s_per_batch": enc_s},
+                "includes": "cordum_encode of string-level envelopes (per-job strings, nothing interned) on the host + pinned H2D + kernels + D2H, 2 batches in flight",
+                "input": "de-interned arena: %.0f MB of strings for %d jobs, every job's strings contiguous" % (len(plain_jobs.arena) / 1e6, n_shard),
+                "interned_arena": J * e2e_steps / e2e_int_elapsed,
+                "from_encoded_records": J * e2e_steps / e2e_cols_elapsed,
+                "host_encode_ms_per_batch": float(np.median(enc_ms)), "host_encode_ms_per_batch_interned": float(np.median(enc_int_ms)),
+                "host": hostinfo.describe()},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "policy_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_note, "kernel": "policy_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src,
                      "other_kernels": {"route_kernel_ms": r_ms},
                      "whole_path": {"algorithmic_bytes": int(path_bytes), "kernels_ms": k_ms + r_ms, "achieved": path_gbs,

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,9 +48,16 @@ bool fold_eq(sv a, sv b) {   // strings.EqualFold
   return fold_str(a) == fold_str(b);
 }
 
-// dictionary lookup of a job value under containsString semantics (safety_policy.go:296-306)
+// No TrimSpace needed: the string starts and ends with an ASCII byte that is not white space (every Unicode space is
+// either <= 0x20 or starts with a byte >= 0x80 in UTF-8).
+inline bool untrimmed_ok(sv s) {
+  const unsigned char a = (unsigned char)s.front(), b = (unsigned char)s.back();
+  return a > 0x20 && a < 0x80 && b > 0x20 && b < 0x80;
+}
+// dictionary lookup of a job value under containsString semantics (safety_policy.go:296-306): EqualFold(Trim(v), Trim(x))
 inline uint32_t lookup_value(const Dict& d, sv raw) {
   if (raw.empty()) return CORDUM_ID_EMPTY;
+  if (untrimmed_ok(raw) && is_ascii(raw)) return d.table.find_fold_ascii(raw, CORDUM_ID_OTHER);   // the common case: one pass, no copy
   FoldBuf f(raw);
   return d.table.find(f.view, CORDUM_ID_OTHER);
 }
@@ -1497,15 +1505,7 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
     uint32_t bit = EncodeCaches::kPlaceNone;
     if (!(placement_skips(key) || starts_with(key, "cordum."))) {
       if (!val.empty()) {
-        char small[256];
-        std::string big;
-        sv pk;
-        size_t n = key.size() + 1 + val.size();
-        if (n <= sizeof small) {
-          std::memcpy(small, key.data(), key.size()); small[key.size()] = 0; std::memcpy(small + key.size() + 1, val.data(), val.size());
-          pk = sv(small, n);
-        } else { big.assign(key); big.push_back('\0'); big.append(val); pk = big; }
-        bit = place_pair_.find(pk, kMiss);
+        bit = place_pair_.find_pair(key, val, kMiss);
         if (bit == kMiss) bit = EncodeCaches::kPlaceUnsat;
       } else {
         bit = place_key_.find(key, kMiss);
@@ -1573,6 +1573,9 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
     caches[i]->gen = encode_gen_;
   }
   if (nthreads > 1 && !pool_) pool_ = std::make_unique<WorkPool>(threads_);
+  static const bool trace = getenv("CORDUM_ENCODE_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_start = now();
   // parts: contiguous job ranges, more of them than threads so that a descheduled thread costs little
   uint32_t parts = nthreads == 1 ? 1u : std::min<uint32_t>(4 * nthreads, (n + 4095) / 4096);
   auto part_range = [&](uint32_t p, uint32_t np, uint32_t& a, uint32_t& b) { a = (uint32_t)((uint64_t)n * p / np); b = (uint32_t)((uint64_t)n * (p + 1) / np); };
@@ -1601,6 +1604,7 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
       if (id == kMiss) { err = "topic dictionary full (max_topics)"; return CORDUM_E_CAPACITY; }
       tid[j] = id;
     }
+  auto t_pass1 = now();
   // ---- slots: hist[p][key] -> first slot of (part p, key); key = topic * classes + tenant class
   const uint32_t ncls = std::max<uint32_t>(1, tenant_classes_);
   const uint32_t nk = (uint32_t)topic_keys_.size() * ncls;
@@ -1624,6 +1628,7 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
     for (uint32_t k = 0; k < nk; ++k)
       for (uint32_t p = 0; p < parts; ++p) { uint32_t c = hist[(size_t)p * nk + k]; hist[(size_t)p * nk + k] = run; run += c; }
   }
+  auto t_slots = now();
   // ---- pass 2: encode every job into its slot
   for (auto& m : misses) m.clear();
   auto pass2 = [&](uint32_t p0, uint32_t p1, uint32_t w) {
@@ -1642,6 +1647,11 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
   };
   if (nthreads == 1) pass2(0, parts, 0);
   else pool_->parallel_for(parts, 1, pass2);
+  if (trace) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "encode %u jobs, %u threads, %u parts: pass1 %.2f ms, slots %.2f ms, pass2 %.2f ms\n", n, nthreads, parts,
+            ms(t_start, t_pass1), ms(t_pass1, t_slots), ms(t_slots, now()));
+  }
   // effective configs seen for the first time: register them, then re-encode just those jobs in place
   for (auto& lst : misses)
     for (uint32_t j : lst) {

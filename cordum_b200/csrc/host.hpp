@@ -12,6 +12,7 @@
 //   pool / label filtering          core/controlplane/scheduler/strategy_least_loaded.go:161-265
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -33,15 +34,39 @@ struct EncodeCaches;
 
 // ------------------------------------------------------------------ string-keyed hash table
 // Open addressing, keyed by bytes, lookups take a string_view (no allocation on the encode path).
+// The hash reads 8 bytes per step (two multiplies per 16 bytes).  hash_fold() lower-cases ASCII letters on the fly
+// (SWAR), so that an ASCII value can be looked up under strings.EqualFold semantics without first being copied into
+// its canonical form: canonical strings hold no upper-case ASCII, hence hash_fold(raw) == hash(fold_str(raw)).
 class StrTable {
  public:
   StrTable() { slots_.assign(16, Slot{}); }
-  static uint64_t hash(sv s) {
-    uint64_t h = 0xcbf29ce484222325ull;
-    for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
-    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+  static uint64_t rd8(const char* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+  static uint64_t rd4(const char* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+  static uint64_t mix(uint64_t a, uint64_t b) { __uint128_t r = (__uint128_t)a * b; return (uint64_t)r ^ (uint64_t)(r >> 64); }
+  static uint64_t lower8(uint64_t v) {   // ASCII 'A'..'Z' -> 'a'..'z' in each byte, other bytes untouched
+    const uint64_t v7 = v & 0x7F7F7F7F7F7F7F7Full;
+    const uint64_t up = (v7 + 0x3F3F3F3F3F3F3F3Full) & ~(v7 + 0x2525252525252525ull) & ~v & 0x8080808080808080ull;
+    return v | (up >> 2);
+  }
+  template <bool FOLD>
+  static uint64_t hash_impl(sv s) {
+    const char* p = s.data();
+    size_t n = s.size();
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xA0761D6478BD642Full);
+    auto L = [](uint64_t v) { return FOLD ? lower8(v) : v; };
+    while (n > 16) {
+      h = mix(L(rd8(p)) ^ 0xE7037ED1A0B428DBull, L(rd8(p + 8)) ^ h);
+      p += 16; n -= 16;
+    }
+    uint64_t a = 0, b = 0;
+    if (n >= 8) { a = L(rd8(p)); b = L(rd8(p + n - 8)); }
+    else if (n >= 4) { a = L(rd4(p)); b = L(rd4(p + n - 4)); }
+    else if (n > 0) { a = L(((uint64_t)(unsigned char)p[0] << 16) | ((uint64_t)(unsigned char)p[n >> 1] << 8) | (unsigned char)p[n - 1]); }
+    h = mix(a ^ 0x8EBC6AF09C88C6E3ull, b ^ h);
     return h | 1;
   }
+  static uint64_t hash(sv s) { return hash_impl<false>(s); }
+  static uint64_t hash_fold(sv s) { return hash_impl<true>(s); }
   // returns value or `miss`
   uint32_t find(sv key, uint32_t miss) const {
     uint64_t h = hash(key);
@@ -49,9 +74,35 @@ class StrTable {
     for (size_t i = h & m;; i = (i + 1) & m) {
       const Slot& s = slots_[i];
       if (s.hash == 0) return miss;
-      if (s.hash == h && s.len == key.size() && std::char_traits<char>::compare(pool_.data() + s.off, key.data(), s.len) == 0)
-        return s.val;
+      if (s.hash == h && s.len == key.size() && std::memcmp(pool_.data() + s.off, key.data(), s.len) == 0) return s.val;
     }
+  }
+  // key: an ASCII string; matches the stored canonical (ASCII-lowered) string it folds to
+  uint32_t find_fold_ascii(sv key, uint32_t miss) const {
+    uint64_t h = hash_fold(key);
+    size_t m = slots_.size() - 1;
+    for (size_t i = h & m;; i = (i + 1) & m) {
+      const Slot& s = slots_[i];
+      if (s.hash == 0) return miss;
+      if (s.hash == h && s.len == key.size()) {
+        const char* c = pool_.data() + s.off;
+        size_t k = 0;
+        for (; k < key.size(); ++k) {
+          char x = key[k];
+          if (x >= 'A' && x <= 'Z') x = char(x + 32);
+          if (x != c[k]) break;
+        }
+        if (k == key.size()) return s.val;
+      }
+    }
+  }
+  // key = a '\0' b, without building it
+  uint32_t find_pair(sv a, sv b, uint32_t miss) const {
+    char small[256];
+    const size_t n = a.size() + 1 + b.size();
+    if (n > sizeof small) { std::string big(a); big.push_back('\0'); big.append(b); return find(big, miss); }
+    std::memcpy(small, a.data(), a.size()); small[a.size()] = 0; std::memcpy(small + a.size() + 1, b.data(), b.size());
+    return find(sv(small, n), miss);
   }
   bool contains(sv key) const { return find(key, 0xFFFFFFFEu) != 0xFFFFFFFEu; }
   void put(sv key, uint32_t val) {
@@ -66,7 +117,7 @@ class StrTable {
         ++count_;
         return;
       }
-      if (s.hash == h && s.len == key.size() && std::char_traits<char>::compare(pool_.data() + s.off, key.data(), s.len) == 0) {
+      if (s.hash == h && s.len == key.size() && std::memcmp(pool_.data() + s.off, key.data(), s.len) == 0) {
         s.val = val;
         return;
       }

@@ -268,6 +268,66 @@ class EnvelopeBatch:
             out.append(job)
         return out
 
+    def deinterned(self) -> "EnvelopeBatch":
+        """The same jobs with NOTHING shared between them: every job's strings are laid out contiguously, job after job
+        (topic, tenant, principal, meta fields, risk tags, requires, label key/value pairs, effective config), the way
+        a shim unpacking one protobuf JobRequest after another would produce them.  Equal strings of different jobs
+        are different byte ranges, so nothing downstream can resolve a value by its address."""
+        c = self.cols
+        n = self.n_jobs
+        order = ["topic", "tenant", "principal_id", "meta_tenant_id", "actor_id", "capability", "pack_id"]
+        lens = {k: c[k]["len"].astype(np.int64) for k in order + ["effective_config"]}
+
+        def run_sums(off, ln):   # per-job sum of a CSR column's entry lengths, and each entry's prefix inside its run
+            cs = np.concatenate([[0], np.cumsum(ln)])
+            o = off.astype(np.int64)
+            per_job = cs[o[1:]] - cs[o[:-1]]
+            counts = np.diff(o)
+            start_of_entry = np.repeat(cs[o[:-1]], counts)
+            return per_job, cs[:len(ln)][: int(o[-1])] - start_of_entry
+
+        nr, nq, nl = int(c["risk_off"][-1]), int(c["requires_off"][-1]), int(c["label_off"][-1])
+        rl = c["risk_tags"]["len"][:nr].astype(np.int64)
+        ql = c["requires_"]["len"][:nq].astype(np.int64)
+        kl = c["label_keys"]["len"][:nl].astype(np.int64)
+        vl = c["label_vals"]["len"][:nl].astype(np.int64)
+        risk_job, risk_pre = run_sums(c["risk_off"], rl)
+        req_job, req_pre = run_sums(c["requires_off"], ql)
+        lab_job, lab_pre = run_sums(c["label_off"], kl + vl)
+        total_job = sum(lens[k] for k in order) + risk_job + req_job + lab_job + lens["effective_config"]
+        base = np.concatenate([[1], 1 + np.cumsum(total_job)])   # byte 0 stays reserved: (0, 0) is the empty string
+        arena = np.zeros(int(base[-1]), dtype=np.uint8)
+        new_cols = dict(c)
+
+        def place(name, src_spans, dst_off, ln):
+            ln = np.asarray(ln, dtype=np.int64)
+            out = np.zeros(len(src_spans), dtype=STR_DTYPE)
+            nz = ln > 0
+            out["off"][: len(ln)][nz] = dst_off[nz]
+            out["len"][: len(ln)] = ln
+            tot = int(ln.sum())
+            if tot:
+                ramp = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(ln) - ln, ln)
+                arena[np.repeat(dst_off, ln) + ramp] = self.arena[np.repeat(src_spans["off"][: len(ln)].astype(np.int64), ln) + ramp]
+            new_cols[name] = out
+
+        cur = base[:-1].copy()
+        for k in order:
+            place(k, c[k], cur, lens[k])
+            cur = cur + lens[k]
+        jr = np.repeat(np.arange(n), np.diff(c["risk_off"].astype(np.int64)))
+        place("risk_tags", c["risk_tags"], cur[jr] + risk_pre, rl)
+        cur = cur + risk_job
+        jq = np.repeat(np.arange(n), np.diff(c["requires_off"].astype(np.int64)))
+        place("requires_", c["requires_"], cur[jq] + req_pre, ql)
+        cur = cur + req_job
+        jl = np.repeat(np.arange(n), np.diff(c["label_off"].astype(np.int64)))
+        place("label_keys", c["label_keys"], cur[jl] + lab_pre, kl)
+        place("label_vals", c["label_vals"], cur[jl] + lab_pre + kl, vl)
+        cur = cur + lab_job
+        place("effective_config", c["effective_config"], cur, lens["effective_config"])
+        return EnvelopeBatch(n, arena, new_cols)
+
     def with_approved(self, mask) -> "EnvelopeBatch":
         cols = dict(self.cols)
         cols["approved"] = np.ascontiguousarray(mask, dtype=np.uint8)
