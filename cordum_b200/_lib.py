@@ -18,7 +18,8 @@ API = [
     "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
     "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
     "cordum_workers_set_loads_device", "cordum_exchange_unique_id", "cordum_exchange_init", "cordum_workers_ingest",
-    "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_dispatch",
+    "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_encode_device", "cordum_envelopes_alloc",
+    "cordum_envelopes_free", "cordum_host_fallbacks", "cordum_batch_records", "cordum_dispatch",
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
@@ -57,6 +58,13 @@ def load() -> C.CDLL:
     L.cordum_batch_free.argtypes = [vp]
     L.cordum_batch_free.restype = None
     L.cordum_encode.argtypes = [vp, vp, vp]
+    L.cordum_encode_device.argtypes = [vp, vp, vp]
+    L.cordum_envelopes_alloc.argtypes = [vp, C.POINTER(wire.CordumEnvelopeCaps), C.POINTER(vp)]
+    L.cordum_envelopes_free.argtypes = [vp, vp]
+    L.cordum_envelopes_free.restype = None
+    L.cordum_host_fallbacks.argtypes = [vp]
+    L.cordum_host_fallbacks.restype = u64
+    L.cordum_batch_records.argtypes = [vp, vp, vp, vp]
     for f in ("cordum_dispatch", "cordum_dispatch_async", "cordum_dispatch_resident", "cordum_dispatch_resident_async"):
         getattr(L, f).argtypes = [vp, vp, u32]
     L.cordum_batch_wait.argtypes = [vp]

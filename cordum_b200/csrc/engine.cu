@@ -83,6 +83,10 @@ struct cordum_engine {
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi;
   DevBuf b_flush, b_lbm_off, b_rank_pos, b_chunk_pool, b_pool_chunk0, b_merge_list;
+  DevBuf b_dicts;                // device encoder: dictionary images + side arrays (Host::export_dicts)
+  EncodeTables et{};             // rebased onto b_dicts
+  uint64_t v_dict = ~0ull;
+  std::vector<cordum_envelopes*> env_sets;   // pinned envelope staging sets handed out by cordum_envelopes_alloc
   // Everything the worker-table refresh kernels derive from the loads, in kSets copies used round-robin: the refresh
   // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
   // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
@@ -102,11 +106,18 @@ struct cordum_batch {
   cordum_engine* e = nullptr;
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
-  bool encoded = false, resident = false, pending = false, launched = false, timed_in = false, timed_out = false;
+  bool encoded = false, resident = false, pending = false, enc_inflight = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
   uint8_t* d_cols = nullptr;
   uint32_t* slot_of = nullptr;   // host: position of caller job j in the sorted records
+  // device-side encode (cordum_encode_device)
+  bool device_encoded = false, host_records_valid = true;
+  const cordum_envelopes* env = nullptr;   // the caller's envelopes, kept until the batch has been waited for (host fallback)
+  DevBuf d_env, d_work;          // envelope arrays on the device; tid / ten / key / slot_of / hist / flag
+  uint32_t* h_fallback = nullptr;   // pinned: 1 = the device encoder left something to the host
+  uint32_t last_mode = 0;
+  bool last_copy_out = false;
   cordum_decision* h_out = nullptr;   // pinned
   cordum_decision* d_out = nullptr;
   uint2* d_route = nullptr;           // [0].x = count, [2..] = compacted list of dispatchable jobs {slot, head}
@@ -256,6 +267,26 @@ int sync_tables(cordum_engine* e) {
   return CORDUM_OK;
 }
 
+// Device encoder: the dictionaries follow the host's (called with the host mutex held, nothing in flight on the blob:
+// callers go through sync_tables first, and a dictionary change always comes with a table change or a reload).
+int sync_dicts(cordum_engine* e) {
+  if (e->v_dict == e->host->dict_version()) return CORDUM_OK;
+  CK(cudaDeviceSynchronize(), "sync before dictionary upload");
+  std::vector<uint8_t> blob;
+  EncodeTables et;
+  e->host->export_dicts(blob, et);
+  CK(e->b_dicts.upload(blob.data(), blob.size(), e->s_tables), "upload dictionaries");
+  CK(cudaStreamSynchronize(e->s_tables), "upload dictionaries");
+  const uint8_t* base = (const uint8_t*)e->b_dicts.p;
+  et.blob = base;
+  et.topic_flags = (const uint32_t*)(base + (size_t)et.topic_flags);
+  et.tenant_class = base + (size_t)et.tenant_class;
+  et.label_keymask = (const uint64_t*)(base + (size_t)et.label_keymask);
+  e->et = et;
+  e->v_dict = e->host->dict_version();
+  return CORDUM_OK;
+}
+
 // The kernels' view of the tables with the derived pointers of one set.
 DeviceTables view(const cordum_engine* e, int set) {
   DeviceTables d = e->dt;
@@ -309,8 +340,11 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
   if (mode < CORDUM_MODE_POLICY_ONLY || mode > CORDUM_MODE_ROUTE_ONLY) { g_err = "bad mode"; return CORDUM_E_INVALID; }
   if (!b->encoded) { g_err = "batch has not been encoded"; return CORDUM_E_STATE; }
+  if (b->device_encoded) copy_in = false;   // the records were produced on the device
   if (!copy_in && !b->resident) { g_err = "batch columns are not resident on the device"; return CORDUM_E_STATE; }
-  if (b->pending) { CK(cudaStreamSynchronize(b->stream), "wait previous"); b->pending = false; }
+  b->last_mode = mode | (flush_l2 ? CORDUM_FLAG_FLUSH_L2 : 0u);
+  b->last_copy_out = copy_out;
+  if (b->pending) { CK(cudaStreamSynchronize(b->stream), "wait previous"); b->pending = false; b->enc_inflight = false; }
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   KParams P;
   cudaEvent_t ev_ready = nullptr;
@@ -372,11 +406,29 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   return CORDUM_OK;
 }
 
+int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env);
+
 int wait(cordum_batch* b) {
   cordum_engine* e = b->e;
-  if (!b->pending) return CORDUM_OK;
+  if (!b->pending && !b->enc_inflight) return CORDUM_OK;
   CK(cudaStreamSynchronize(b->stream), "batch wait");
+  const bool dispatched = b->pending;
   b->pending = false;
+  b->enc_inflight = false;
+  if (b->device_encoded && b->h_fallback && *b->h_fallback) {
+    // The device encoder met something it leaves to the host (first sight of a topic / effective config, non-ASCII
+    // text, an oversized string): encode the batch on the host - which also registers what is new - and run it again.
+    *b->h_fallback = 0;
+    e->host->host_fallbacks++;
+    int rc = host_encode_into(e, b, b->env);
+    if (rc) return rc;
+    if (!dispatched) return CORDUM_OK;
+    rc = run(e, b, b->last_mode, true, b->last_copy_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(b->stream), "batch wait");
+    b->pending = false;
+  }
+  if (!dispatched) return CORDUM_OK;
   CK(cudaEventElapsedTime(&b->total_ms, b->timed_in ? b->ev0 : b->ev1, b->timed_out ? b->ev3 : b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->kernel_ms, b->ev1, b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->policy_ms, b->ev1, b->evm), "elapsed");
@@ -410,6 +462,8 @@ static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resourc
   if (b->d_out) cudaFree(b->d_out);
   if (b->d_route) cudaFree(b->d_route);
   std::free(b->slot_of);
+  b->d_env.release(); b->d_work.release();
+  if (b->h_fallback) cudaFreeHost(b->h_fallback);
   for (cudaEvent_t ev : {b->ev0, b->ev1, b->evm, b->ev2, b->ev3}) if (ev) cudaEventDestroy(ev);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -498,6 +552,24 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
 }
 }  // namespace
 
+namespace {
+int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
+  if (!env) { g_err = "envelopes no longer available for the host encoder"; return CORDUM_E_STATE; }
+  b->n = env->n_jobs;
+  b->encoded = false;
+  b->resident = false;
+  b->device_encoded = false;
+  host_records(b);
+  uint64_t epoch_before = e->host->epoch();
+  int rc = e->host->encode(env, b->hr, g_err);
+  if (rc) return rc;
+  b->epoch = epoch_before;
+  b->encoded = true;
+  b->host_records_valid = true;
+  return CORDUM_OK;
+}
+}  // namespace
+
 // ============================================================ C ABI
 extern "C" {
 
@@ -561,7 +633,9 @@ void cordum_engine_destroy(cordum_engine* e) {
     { std::lock_guard<std::mutex> g(e->mu); live.swap(e->batches); }
     for (cordum_batch* b : live) batch_release(b);
   }
-  DevBuf* all[] = {&e->b_rows, &e->b_row_check,
+  for (cordum_envelopes* env : e->env_sets) cudaFreeHost(env);
+  e->env_sets.clear();
+  DevBuf* all[] = {&e->b_dicts, &e->b_rows, &e->b_row_check,
                    &e->b_req_need, &e->b_lab_need, &e->b_rule_dec, &e->b_tenant_mcp, &e->b_eff_mcp, &e->b_eff_topic, &e->b_pos2rule,
                    &e->b_sum_tenant, &e->b_sum_topic, &e->b_sum_cap, &e->b_sum_pack, &e->b_sum_actor, &e->b_sum_combo, &e->b_sum_risk,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
@@ -716,18 +790,173 @@ void cordum_batch_free(cordum_batch* b) {
 int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
   if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
-  if (b->pending) { int rc = wait(b); if (rc) return rc; }
-  b->n = env->n_jobs;
-  b->encoded = false;
-  b->resident = false;
-  host_records(b);
-  uint64_t epoch_before = e->host->epoch();
-  int rc = e->host->encode(env, b->hr, g_err);
-  if (rc) return rc;
-  b->epoch = epoch_before;
-  b->encoded = true;
+  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  return host_encode_into(e, b, env);
+}
+
+/* ---- device-side encode ---------------------------------------------------------------------------------------- */
+namespace {
+struct EnvLayout { size_t off[15]; size_t total; };   // arena + the 14 arrays, 256 B aligned, in cordum_envelopes order
+EnvLayout env_layout(uint32_t n, uint64_t arena, uint32_t n_risk, uint32_t n_req, uint32_t n_lab) {
+  const size_t sz[15] = {(size_t)arena + 16, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n, (size_t)n * 8, (size_t)n * 8,
+                         (size_t)n, (size_t)n * 8, (size_t)n * 8, ((size_t)n + 1) * 4 + (size_t)n_risk * 8, ((size_t)n + 1) * 4 + (size_t)n_req * 8,
+                         ((size_t)n + 1) * 4 + (size_t)n_lab * 16, (size_t)n};
+  EnvLayout L{};
+  size_t at = 0;
+  for (int i = 0; i < 15; ++i) { L.off[i] = at; at += (sz[i] + 255) & ~size_t(255); }
+  L.total = at;
+  return L;
+}
+}  // namespace
+
+int32_t cordum_envelopes_alloc(cordum_engine* e, const cordum_envelope_caps* caps, cordum_envelopes** out) {
+  if (!e || !caps || !out || caps->max_jobs == 0) { g_err = "bad argument"; return CORDUM_E_INVALID; }
+  *out = nullptr;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  const uint32_t n = caps->max_jobs;
+  const size_t sz[14] = {(size_t)caps->arena_bytes + 16, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n, (size_t)n * 8,
+                         (size_t)n * 8, (size_t)n, (size_t)n * 8, (size_t)n * 8, ((size_t)n + 1) * 4, ((size_t)n + 1) * 4, ((size_t)n + 1) * 4};
+  const size_t lists[4] = {(size_t)std::max<uint32_t>(caps->max_risk_tags, 1) * 8, (size_t)std::max<uint32_t>(caps->max_requires, 1) * 8,
+                           (size_t)std::max<uint32_t>(caps->max_labels, 1) * 8, (size_t)std::max<uint32_t>(caps->max_labels, 1) * 8};
+  size_t total = sizeof(cordum_envelopes) + 256 + n;
+  for (size_t x : sz) total += (x + 255) & ~size_t(255);
+  for (size_t x : lists) total += (x + 255) & ~size_t(255);
+  uint8_t* base = nullptr;
+  CK(cudaHostAlloc((void**)&base, total, cudaHostAllocDefault), "pinned envelope buffers");
+  std::memset(base, 0, total);
+  auto* env = reinterpret_cast<cordum_envelopes*>(base);
+  size_t at = (sizeof(cordum_envelopes) + 255) & ~size_t(255);
+  auto take = [&](size_t bytes) { uint8_t* p = base + at; at += (bytes + 255) & ~size_t(255); return p; };
+  env->n_jobs = 0;
+  env->arena = take(sz[0]); env->arena_len = 0;
+  env->topic = (const cordum_str*)take(sz[1]); env->tenant = (const cordum_str*)take(sz[2]);
+  env->principal_id = (const cordum_str*)take(sz[3]); env->effective_config = (const cordum_str*)take(sz[4]);
+  env->has_meta = take(sz[5]); env->meta_tenant_id = (const cordum_str*)take(sz[6]); env->actor_id = (const cordum_str*)take(sz[7]);
+  env->actor_type = take(sz[8]); env->capability = (const cordum_str*)take(sz[9]); env->pack_id = (const cordum_str*)take(sz[10]);
+  env->risk_off = (const uint32_t*)take(sz[11]); env->risk_tags = (const cordum_str*)take(lists[0]);
+  env->requires_off = (const uint32_t*)take(sz[12]); env->requires_ = (const cordum_str*)take(lists[1]);
+  env->label_off = (const uint32_t*)take(sz[13]); env->label_keys = (const cordum_str*)take(lists[2]);
+  env->label_vals = (const cordum_str*)take(lists[3]);
+  env->approved = take(n);
+  { std::lock_guard<std::mutex> g(e->mu); e->env_sets.push_back(env); }
+  *out = env;
   return CORDUM_OK;
 }
+
+void cordum_envelopes_free(cordum_engine* e, cordum_envelopes* env) {
+  if (!e || !env) return;
+  cudaSetDevice(e->device);
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    auto& v = e->env_sets;
+    for (size_t i = 0; i < v.size(); ++i) if (v[i] == env) { v.erase(v.begin() + i); break; }
+  }
+  cudaFreeHost(env);
+}
+
+int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
+  if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  const uint32_t n = env->n_jobs;
+  b->n = n;
+  b->encoded = false; b->resident = false; b->device_encoded = false;
+  if (n == 0) { b->encoded = true; b->resident = true; b->device_encoded = true; b->host_records_valid = true; b->epoch = e->host->epoch(); return CORDUM_OK; }
+  if (!b->h_fallback) { CK(cudaHostAlloc((void**)&b->h_fallback, 64, cudaHostAllocDefault), "pinned flag"); *b->h_fallback = 0; }
+  const uint32_t n_risk = env->risk_off ? env->risk_off[n] : 0, n_req = env->requires_off ? env->requires_off[n] : 0,
+                 n_lab = env->label_off ? env->label_off[n] : 0;
+  const EnvLayout L = env_layout(n, env->arena_len, n_risk, n_req, n_lab);
+  EncodeParams P{};
+  uint32_t n_keys = 0;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> gh(e->host->mutex());
+    int rc = sync_tables(e);
+    if (rc) return rc;
+    rc = sync_dicts(e);
+    if (rc) return rc;
+    P.et = e->et;
+    n_keys = P.et.n_topics * P.et.tenant_classes;
+    b->epoch = e->host->epoch();
+    // device buffers of this batch (grown on demand; nothing of this batch is in flight: it was waited for above)
+    if (b->d_env.cap < L.total) CK(b->d_env.reserve(L.total + L.total / 8), "device envelope buffers");
+    const size_t work = ((size_t)n * 4 + 255) / 256 * 256 * 4 + ((size_t)n_keys * 4 + 255) / 256 * 256 + 256;
+    if (b->d_work.cap < work) CK(b->d_work.reserve(work + work / 8), "device encode work arrays");
+  }
+  cudaStream_t s = b->stream;
+  uint8_t* d = (uint8_t*)b->d_env.p;
+  auto h2d = [&](int i, const void* src, size_t bytes, size_t extra_off = 0) -> cudaError_t {
+    if (!src || !bytes) return cudaSuccess;
+    return cudaMemcpyAsync(d + L.off[i] + extra_off, src, bytes, cudaMemcpyHostToDevice, s);
+  };
+  CK(h2d(0, env->arena, env->arena_len), "H2D arena");
+  CK(h2d(1, env->topic, (size_t)n * 8), "H2D"); CK(h2d(2, env->tenant, (size_t)n * 8), "H2D");
+  CK(h2d(3, env->principal_id, (size_t)n * 8), "H2D"); CK(h2d(4, env->effective_config, (size_t)n * 8), "H2D");
+  CK(h2d(5, env->has_meta, n), "H2D"); CK(h2d(6, env->meta_tenant_id, (size_t)n * 8), "H2D");
+  CK(h2d(7, env->actor_id, (size_t)n * 8), "H2D"); CK(h2d(8, env->actor_type, n), "H2D");
+  CK(h2d(9, env->capability, (size_t)n * 8), "H2D"); CK(h2d(10, env->pack_id, (size_t)n * 8), "H2D");
+  const size_t offs = ((size_t)n + 1) * 4;
+  CK(h2d(11, env->risk_off, offs), "H2D"); CK(h2d(11, env->risk_tags, (size_t)n_risk * 8, offs), "H2D");
+  CK(h2d(12, env->requires_off, offs), "H2D"); CK(h2d(12, env->requires_, (size_t)n_req * 8, offs), "H2D");
+  CK(h2d(13, env->label_off, offs), "H2D"); CK(h2d(13, env->label_keys, (size_t)n_lab * 8, offs), "H2D");
+  CK(h2d(13, env->label_vals, (size_t)n_lab * 8, offs + (size_t)n_lab * 8), "H2D");
+  CK(h2d(14, env->approved, n), "H2D");
+  P.n_jobs = n;
+  P.arena = d + L.off[0];
+  auto col = [&](int i, const void* src) { return src ? (const cordum_str*)(d + L.off[i]) : nullptr; };
+  P.topic = col(1, env->topic); P.tenant = col(2, env->tenant); P.principal_id = col(3, env->principal_id);
+  P.effective_config = col(4, env->effective_config); P.has_meta = env->has_meta ? d + L.off[5] : nullptr;
+  P.meta_tenant_id = col(6, env->meta_tenant_id); P.actor_id = col(7, env->actor_id);
+  P.actor_type = env->actor_type ? d + L.off[8] : nullptr; P.capability = col(9, env->capability); P.pack_id = col(10, env->pack_id);
+  P.risk_off = env->risk_off ? (const uint32_t*)(d + L.off[11]) : nullptr; P.risk_tags = (const cordum_str*)(d + L.off[11] + offs);
+  P.requires_off = env->requires_off ? (const uint32_t*)(d + L.off[12]) : nullptr; P.requires_ = (const cordum_str*)(d + L.off[12] + offs);
+  P.label_off = env->label_off ? (const uint32_t*)(d + L.off[13]) : nullptr;
+  P.label_keys = (const cordum_str*)(d + L.off[13] + offs); P.label_vals = (const cordum_str*)(d + L.off[13] + offs + (size_t)n_lab * 8);
+  P.approved = env->approved ? d + L.off[14] : nullptr;
+  uint8_t* w = (uint8_t*)b->d_work.p;
+  const size_t arr = ((size_t)n * 4 + 255) / 256 * 256;
+  P.tid = (uint32_t*)w; P.ten = (uint32_t*)(w + arr); P.key = (uint32_t*)(w + 2 * arr); P.slot_of = (uint32_t*)(w + 3 * arr);
+  P.hist = (uint32_t*)(w + 4 * arr);
+  P.fallback = (uint32_t*)(w + 4 * arr + ((size_t)n_keys * 4 + 255) / 256 * 256);
+  P.out_job = (JobRec*)b->d_cols;
+  P.out_route = (RouteRec*)(b->d_cols + (size_t)n * sizeof(JobRec));
+  CK(launch_encode(P, n_keys, s), "encode kernels");
+  e->launches += 3;
+  CK(cudaMemcpyAsync(b->h_fallback, P.fallback, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H fallback flag");
+  b->env = env;
+  b->encoded = true; b->resident = true; b->device_encoded = true; b->host_records_valid = false;
+  b->enc_inflight = true;   // work is in flight on the batch stream; a dispatch simply queues behind it
+  return CORDUM_OK;
+}
+
+/* host copies of the records of a device-encoded batch (cordum_reason / cordum_subject read topic and MCP ids) */
+static int ensure_host_records(cordum_batch* b) {
+  cordum_engine* e = b->e;
+  if (b->host_records_valid) return CORDUM_OK;
+  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  if (b->host_records_valid) return CORDUM_OK;   // the wait fell back to the host encoder
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  host_records(b);
+  CK(cudaMemcpy(b->h_cols, b->d_cols, slab_bytes(b->n), cudaMemcpyDeviceToHost), "D2H records");
+  const size_t arr = ((size_t)b->n * 4 + 255) / 256 * 256;
+  CK(cudaMemcpy(b->slot_of, (uint8_t*)b->d_work.p + 3 * arr, (size_t)b->n * 4, cudaMemcpyDeviceToHost), "D2H slot_of");
+  b->host_records_valid = true;
+  return CORDUM_OK;
+}
+
+/* test / diagnostics: the encoded records of a batch, as (JobRec[n], RouteRec[n], slot_of[n]) in host memory */
+int32_t cordum_batch_records(cordum_batch* b, void* job_out, void* route_out, uint32_t* slot_of_out) {
+  if (!b) { g_err = "null batch"; return CORDUM_E_INVALID; }
+  int rc = ensure_host_records(b);
+  if (rc) return rc;
+  if (job_out) std::memcpy(job_out, b->hr.job, (size_t)b->n * sizeof(JobRec));
+  if (route_out) std::memcpy(route_out, b->hr.route, (size_t)b->n * sizeof(RouteRec));
+  if (slot_of_out) std::memcpy(slot_of_out, b->slot_of, (size_t)b->n * sizeof(uint32_t));
+  return CORDUM_OK;
+}
+uint64_t cordum_host_fallbacks(cordum_engine* e) { return e ? e->host->host_fallbacks : 0; }
 
 int32_t cordum_dispatch_async(cordum_engine* e, cordum_batch* b, uint32_t mode) { return run(e, b, mode, true, true); }
 int32_t cordum_batch_wait(cordum_batch* b) {
@@ -793,6 +1022,7 @@ int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* 
 
 int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
   if (!e || !b || job >= b->n) return -1;
+  if (ensure_host_records(const_cast<cordum_batch*>(b))) return -1;
   std::lock_guard<std::mutex> g(e->host->mutex());
   const cordum_decision& r = b->h_out[job];
   const uint32_t code = r.reason_code;
@@ -821,6 +1051,7 @@ int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, cha
 
 int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
   if (!e || !b || job >= b->n) return -1;
+  if (ensure_host_records(const_cast<cordum_batch*>(b))) return -1;
   std::lock_guard<std::mutex> g(e->host->mutex());
   const cordum_decision& r = b->h_out[job];
   std::string s;

@@ -1026,6 +1026,7 @@ uint32_t Host::add_topic(sv raw) {
   }
   for (uint32_t c = 1; c <= t.n_effcfg; ++c) eff_topic_fill(c, id);
   t.v_topic++;
+  v_dict_++;
   return id;
 }
 
@@ -1035,7 +1036,7 @@ uint32_t Host::add_effcfg(sv payload) {
   if (effcfg_ids_.size() >= max_effcfgs_) return kMiss;
   EffSafety cfg;
   bool ok = parse_effective_safety(payload, cfg);
-  if (!ok) { effcfg_ids_.put(payload, 0); return 0; }   // unparsable: the overlay is skipped (kernel.go:218)
+  if (!ok) { effcfg_ids_.put(payload, 0); v_dict_++; return 0; }   // unparsable: the overlay is skipped (kernel.go:218)
   if (effcfgs_.empty()) { effcfgs_.emplace_back(); effcfg_ok_.push_back(0); eff_globs_.emplace_back(); }
   id = (uint32_t)effcfgs_.size();
   effcfg_ids_.put(payload, id);
@@ -1052,6 +1053,7 @@ uint32_t Host::add_effcfg(sv payload) {
   t.eff_topic.resize((size_t)(t.n_effcfg + 1) * t.topic_stride, 0);
   for (uint32_t i = 0; i < topic_keys_.size(); ++i) eff_topic_fill(id, i);
   t.v_topic++;
+  v_dict_++;
   return id;
 }
 
@@ -1077,6 +1079,7 @@ int Host::load_policy(sv json, sv snapshot, std::string& err) {
   }
   rebuild_topics();
   epoch_++;
+  v_dict_++;
   snapshot_ = std::string(snapshot);
   if (!snapshot.empty()) {   // setPolicy, kernel.go:510-521
     snapshots_.insert(snapshots_.begin(), snapshot_);
@@ -1117,6 +1120,7 @@ int Host::load_routing(sv json, std::string& err) {
     return CORDUM_E_CAPACITY;
   }
   epoch_++;
+  v_dict_++;
   return CORDUM_OK;
 }
 
@@ -1154,6 +1158,7 @@ int Host::load_workers(const cordum_workers* w, std::string& err) {
   if (rc != CORDUM_OK) { workers_raw_ = std::move(old_store); return rc; }   // compile_workers mutated nothing
   worker_ids_ = std::move(ids);
   epoch_++;
+  v_dict_++;
   return CORDUM_OK;
 }
 
@@ -1662,6 +1667,51 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
       encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], miss, *caches[0]);
     }
   return CORDUM_OK;
+}
+
+void Host::export_dicts(std::vector<uint8_t>& blob, EncodeTables& et) const {
+  blob.clear();
+  et = EncodeTables{};
+  const StrTable* tabs[DD_COUNT] = {&topic_ids_, &d_tenant_.table, &tenant_pol_, &d_cap_.table, &d_pack_.table, &d_actor_.table,
+                                    &d_risk_.table, &d_req_.table, &d_mcp_[0].table, &d_mcp_[1].table, &d_mcp_[2].table,
+                                    &d_mcp_[3].table, &label_key_, nullptr, &place_pair_, &place_key_, &d_pool_.table,
+                                    &worker_slot_, &effcfg_ids_};
+  StrTable label_pair;   // "key \0 value" -> bit, for the rule label pairs (host keeps them as per-key lists)
+  std::vector<uint64_t> keymask(std::max<size_t>(label_key_pairs_.size(), 1), 0);
+  for (size_t ki = 0; ki < label_key_pairs_.size(); ++ki)
+    for (auto& pv : label_key_pairs_[ki])
+      if (pv.second < 64) keymask[ki] |= 1ull << pv.second;
+  // label_key_ stores key -> index; the pair table needs the key string: recover it by walking the rules
+  for (auto& r : policy_.rules)
+    for (auto& kv : r.labels) {
+      uint32_t ki = label_key_.find(kv.first, kMiss);
+      if (ki == kMiss) continue;
+      for (auto& pv : label_key_pairs_[ki])
+        if (pv.first == kv.second && pv.second < 64) { std::string k = kv.first; k.push_back('\0'); k += kv.second; label_pair.put(k, pv.second); }
+    }
+  tabs[DD_LABEL_PAIR] = &label_pair;
+  for (int i = 0; i < DD_COUNT; ++i) tabs[i]->export_to(blob, et.dict[i]);
+  auto append = [&](const void* p, size_t n, size_t align) {
+    blob.resize((blob.size() + align - 1) / align * align);
+    size_t off = blob.size();
+    blob.insert(blob.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+    return off;
+  };
+  std::vector<uint32_t> tflags(topic_entries_.size());
+  for (size_t i = 0; i < topic_entries_.size(); ++i) tflags[i] = topic_entries_[i].flags;
+  // offsets are smuggled through the pointer fields; the engine rebases them onto the device copy of the blob
+  et.topic_flags = (const uint32_t*)append(tflags.data(), tflags.size() * 4, 16);
+  std::vector<uint8_t> cls = tenant_class_;
+  cls.resize(std::max<size_t>(cls.size(), d_tenant_.size()), 0);
+  et.tenant_class = (const uint8_t*)append(cls.data(), cls.size(), 16);
+  et.label_keymask = (const uint64_t*)append(keymask.data(), keymask.size() * 8, 16);
+  et.n_topics = (uint32_t)topic_entries_.size();
+  et.tenant_classes = std::max<uint32_t>(1, tenant_classes_);
+  sv dt = default_tenant_trim_.empty() ? sv("default") : sv(default_tenant_trim_);
+  et.default_tenant = lookup_value(d_tenant_, dt) | (tenant_pol_.find(dt, 0) << 16);
+  et.place_any_bit = place_any_bit_;
+  et.label_empty_mask = label_empty_mask_;
+  blob.resize(blob.size() + 64);
 }
 
 Host::~Host() = default;   // here, where EncodeCaches is complete

@@ -125,6 +125,25 @@ class StrTable {
   }
   size_t size() const { return count_; }
   void clear() { slots_.assign(16, Slot{}); pool_.clear(); count_ = 0; }
+  // Device image (tables.h DevDict): 32 B slots {hash, off, len, val} + the key bytes, appended to `blob`; the device
+  // probes it with the same hash and the same linear probing, so host and device lookups agree by construction.
+  void export_to(std::vector<uint8_t>& blob, DevDict& ref) const {
+    auto align = [&](size_t a) { blob.resize((blob.size() + a - 1) / a * a); };
+    align(32);
+    ref.slots_off = (uint32_t)blob.size();
+    ref.mask = (uint32_t)slots_.size() - 1;
+    blob.resize(blob.size() + slots_.size() * 32);
+    uint8_t* p = blob.data() + ref.slots_off;
+    for (size_t i = 0; i < slots_.size(); ++i) {
+      const Slot& s = slots_[i];
+      uint32_t rec[8] = {(uint32_t)s.hash, (uint32_t)(s.hash >> 32), s.off, s.len, s.val, 0, 0, 0};
+      std::memcpy(p + i * 32, rec, 32);
+    }
+    align(16);
+    ref.pool_off = (uint32_t)blob.size();
+    blob.insert(blob.end(), pool_.begin(), pool_.end());
+    blob.resize(blob.size() + 16);   // slack: the device may read up to 8 bytes past a key
+  }
 
  private:
   struct Slot { uint64_t hash = 0; uint32_t off = 0, len = 0, val = 0; };
@@ -295,6 +314,14 @@ class Host {
   HostTables& tables_mut() { return t_; }
   std::mutex& mutex() { return mu_; }
 
+  // Everything the device-side encoder needs besides the compiled tables: the dictionaries as probe-able images, the
+  // per-id side arrays and a few scalars (tables.h EncodeTables).  Rebuilt when dict_version() moves.  Under mutex().
+  uint64_t dict_version() const { return v_dict_; }
+  void export_dicts(std::vector<uint8_t>& blob, EncodeTables& et) const;
+  // the device encoder met something it leaves to the host (first sight of a topic / effective config, non-ASCII text):
+  // same contract as encode(); kept separate so that callers can count how often it happens
+  uint64_t host_fallbacks = 0;
+
   // string materialisation
   const PolicyModel& policy() const { return policy_; }
   const std::vector<std::string>& snapshots() const { return snapshots_; }
@@ -309,6 +336,7 @@ class Host {
  private:
   std::mutex mu_;
   uint64_t epoch_ = 1;
+  uint64_t v_dict_ = 1;   // bumps whenever any dictionary changes (loads, first sight of a topic / effective config)
   uint32_t max_topics_, max_effcfgs_, threads_;
   std::string policy_capacity_error_, routing_capacity_error_;
   std::vector<WorkerRaw> workers_raw_;

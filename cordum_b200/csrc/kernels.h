@@ -19,3 +19,20 @@ struct KParams {
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read);
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s);
 cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s);
+
+// ---- device-side encoder (encode.cu)
+struct EncodeParams {
+  uint32_t n_jobs;
+  EncodeTables et;                 // device pointers (the engine rebases Host::export_dicts' offsets)
+  // the envelope arrays of include/cordum_b200.h cordum_envelopes, on the device
+  const uint8_t* arena;
+  const cordum_str *topic, *tenant, *principal_id, *effective_config, *meta_tenant_id, *actor_id, *capability, *pack_id;
+  const uint8_t *has_meta, *actor_type, *approved;
+  const uint32_t *risk_off, *requires_off, *label_off;
+  const cordum_str *risk_tags, *requires_, *label_keys, *label_vals;
+  // work arrays (device)
+  uint32_t *tid, *ten, *key, *hist, *slot_of, *fallback;
+  JobRec* out_job;
+  RouteRec* out_route;
+};
+cudaError_t launch_encode(const EncodeParams& P, uint32_t n_keys, cudaStream_t s);

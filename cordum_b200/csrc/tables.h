@@ -84,6 +84,26 @@ typedef struct __attribute__((aligned(16))) RouteRec {   /* 32 B: what only rout
 #define CORDUM_JOB_OUT_BYTES 16u
 #define CORDUM_ID16_MAX 65535u
 
+/* ---- device-side encoder (encode.cu): the host's dictionaries as probe-able images.
+   A DevDict is an open-addressing table inside one byte blob: 32 B slots {u64 hash (0 = empty), u32 key offset into
+   the dict's key bytes, u32 key length, u32 value, pad}, linear probing, hash = host.hpp StrTable::hash. */
+typedef struct DevDict { uint32_t slots_off, mask, pool_off, pad; } DevDict;
+enum {
+  DD_TOPIC = 0, DD_TENANT, DD_TENANT_POL, DD_CAP, DD_PACK, DD_ACTOR, DD_RISK, DD_REQ, DD_MCP0, DD_MCP1, DD_MCP2, DD_MCP3,
+  DD_LABEL_KEY, DD_LABEL_PAIR, DD_PLACE_PAIR, DD_PLACE_KEY, DD_POOL, DD_WORKER, DD_EFFCFG, DD_COUNT
+};
+typedef struct EncodeTables {
+  const uint8_t* blob;            /* device: all dictionaries                                             */
+  DevDict dict[DD_COUNT];
+  const uint32_t* topic_flags;    /* device, per topic id: JF_TOPIC_* of the topic                        */
+  const uint8_t* tenant_class;    /* device, per tenant id: sort class (host.hpp tenant_class_)           */
+  const uint64_t* label_keymask;  /* device, per rule label key: bits of all pairs of that key            */
+  uint32_t n_topics, tenant_classes;
+  uint32_t default_tenant;        /* tenant id | exact-policy index << 16 of the fallback tenant          */
+  uint32_t place_any_bit;
+  uint64_t label_empty_mask;
+} EncodeTables;
+
 typedef struct JobRecords {
   const JobRec* job;
   const RouteRec* route;

@@ -43,12 +43,34 @@ class Batch:
     def size(self) -> int:
         return self.L.cordum_batch_size(self.h)
 
+    default_device_encode = False   # tests flip this to run whole suites through cordum_encode_device
+
     def encode(self, env):
+        if self.default_device_encode:
+            return self.encode_device(env)
         if not isinstance(env, wire.EnvelopeBatch):
             env = wire.EnvelopeBatch.from_jobs(env)
         self._env = env   # keep the buffers alive for the duration of the call chain
-        self.eng._ck(self.L.cordum_encode(self.eng.h, self.h, C.addressof(env.struct)))
+        self.eng._ck(self.L.cordum_encode(self.eng.h, self.h, env.address))
         return self
+
+    def encode_device(self, env):
+        """Encode on the GPU (cordum_encode_device).  `env`: a PinnedEnvelopes (DMA at PCIe rate) or an EnvelopeBatch
+        (pageable memory).  Asynchronous; the envelope buffers must stay unchanged until wait()."""
+        if not isinstance(env, (wire.EnvelopeBatch, PinnedEnvelopes)):
+            env = wire.EnvelopeBatch.from_jobs(env)
+        self._env = env
+        self.eng._ck(self.L.cordum_encode_device(self.eng.h, self.h, env.address))
+        return self
+
+    def records(self):
+        """(JobRec[n], RouteRec[n], slot_of[n]) of the encoded batch, whichever encoder produced them."""
+        n = self.size
+        job = np.zeros(max(n, 1), dtype=wire.JOB_REC_DTYPE)
+        route = np.zeros(max(n, 1), dtype=wire.ROUTE_REC_DTYPE)
+        slot = np.zeros(max(n, 1), dtype=np.uint32)
+        self.eng._ck(self.L.cordum_batch_records(self.h, job.ctypes.data, route.ctypes.data, slot.ctypes.data))
+        return job[:n], route[:n], slot[:n]
 
     def dispatch(self, mode=wire.MODE_POLICY_AND_ROUTE) -> np.ndarray:
         self.eng._ck(self.L.cordum_dispatch(self.eng.h, self.h, mode))
@@ -102,6 +124,54 @@ class Batch:
 
     def subject(self, job: int) -> str:
         return self._text(self.L.cordum_subject, job)
+
+
+class PinnedEnvelopes:
+    """A cordum_envelopes whose arrays live in page-locked memory owned by the library (cordum_envelopes_alloc): the
+    host writes strings and spans straight into what the GPU will DMA.  fill() copies an EnvelopeBatch in - standing
+    in for a shim that unpacks its requests directly into these buffers."""
+
+    LISTS = (("risk_off", ("risk_tags",)), ("requires_off", ("requires_",)), ("label_off", ("label_keys", "label_vals")))
+
+    def __init__(self, eng: "Engine", max_jobs: int, arena_bytes: int, max_risk: int, max_requires: int, max_labels: int):
+        self.eng = eng
+        self.caps = wire.CordumEnvelopeCaps(max_jobs, max_risk, max_requires, max_labels, arena_bytes)
+        h = C.c_void_p()
+        eng._ck(eng.L.cordum_envelopes_alloc(eng.h, C.byref(self.caps), C.byref(h)))
+        self.h = h
+        self.struct = wire.CordumEnvelopes.from_address(h.value)
+        self.address = h.value
+
+    def _view(self, name, dtype, count):
+        ptr = getattr(self.struct, name)
+        buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def fill(self, env: "wire.EnvelopeBatch"):
+        n = env.n_jobs
+        c = env.cols
+        assert n <= self.caps.max_jobs and len(env.arena) <= self.caps.arena_bytes
+        self._view("arena", np.uint8, len(env.arena))[:] = env.arena
+        for k in wire.EnvelopeBatch.SCALARS:
+            self._view(k, wire.STR_DTYPE, n)[:] = c[k][:n]
+        for k in ("has_meta", "actor_type", "approved"):
+            self._view(k, np.uint8, n)[:] = c[k][:n]
+        for off, vals in self.LISTS:
+            self._view(off, np.uint32, n + 1)[:] = c[off]
+            m = int(c[off][n])
+            cap = {"risk_off": self.caps.max_risk_tags, "requires_off": self.caps.max_requires, "label_off": self.caps.max_labels}[off]
+            assert m <= max(cap, 1)
+            for v in vals:
+                self._view(v, wire.STR_DTYPE, max(m, 1))[:m] = c[v][:m]
+        self.struct.n_jobs = n
+        self.struct.arena_len = len(env.arena)
+        self.n_jobs = n
+        return self
+
+    def free(self):
+        if self.h and self.eng.h:
+            self.eng.L.cordum_envelopes_free(self.eng.h, self.h)
+        self.h = None
 
 
 class Engine:
@@ -182,6 +252,18 @@ class Engine:
         n = C.c_uint32()
         self._ck(self.L.cordum_policy_snapshots(self.h, buf, len(buf), C.byref(n)))
         return [s.decode() for s in buf.raw.split(b"\0")[: n.value]]
+
+    def pinned_envelopes(self, like: "wire.EnvelopeBatch" = None, max_jobs=0, arena_bytes=0, max_risk=0, max_requires=0, max_labels=0) -> PinnedEnvelopes:
+        """Page-locked envelope staging (cordum_envelopes_alloc), sized for `like` if given, and filled from it."""
+        if like is not None:
+            n = like.n_jobs
+            p = PinnedEnvelopes(self, max(max_jobs, n), max(arena_bytes, len(like.arena)), max(max_risk, int(like.cols["risk_off"][n])),
+                                max(max_requires, int(like.cols["requires_off"][n])), max(max_labels, int(like.cols["label_off"][n])))
+            return p.fill(like)
+        return PinnedEnvelopes(self, max_jobs, arena_bytes, max_risk, max_requires, max_labels)
+
+    def host_fallbacks(self) -> int:
+        return int(self.L.cordum_host_fallbacks(self.h))
 
     def batch(self, max_jobs: int) -> Batch:
         return Batch(self, max_jobs)

@@ -115,6 +115,18 @@ class CordumTableStats(C.Structure):
     ]
 
 
+class CordumEnvelopeCaps(C.Structure):
+    _fields_ = [("max_jobs", C.c_uint32), ("max_risk_tags", C.c_uint32), ("max_requires", C.c_uint32), ("max_labels", C.c_uint32),
+                ("arena_bytes", C.c_uint64)]
+
+
+JOB_REC_DTYPE = np.dtype([("topic", "<u4"), ("flags", "<u4"), ("orig", "<u4"), ("tenant", "<u2"), ("tenant_pol", "<u2"),
+                          ("capability", "<u2"), ("pack", "<u2"), ("actor", "<u2"), ("effcfg", "<u2"), ("mcp", "<u2", (4,)),
+                          ("risk_mask", "<u8"), ("req_mask", "<u8"), ("lab_mask", "<u8"), ("spare", "<u4", (2,))])
+ROUTE_REC_DTYPE = np.dtype([("place_lo", "<u8"), ("place_hi", "<u8"), ("req_pool", "<u8"), ("pref_pool", "<u4"), ("pref_worker", "<u4")])
+assert JOB_REC_DTYPE.itemsize == 64 and ROUTE_REC_DTYPE.itemsize == 32
+
+
 class CordumEngineOpts(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_topics", C.c_uint32), ("max_effcfgs", C.c_uint32), ("encode_threads", C.c_uint32)]
 
@@ -185,6 +197,10 @@ class EnvelopeBatch:
 
     def byref(self):
         return C.byref(self.struct)
+
+    @property
+    def address(self) -> int:
+        return C.addressof(self.struct)
 
     @staticmethod
     def from_jobs(jobs: Sequence[dict]) -> "EnvelopeBatch":

@@ -242,6 +242,34 @@ void cordum_batch_free(cordum_batch* b);
  * strategy_least_loaded.go:46-62,195-222).  Host work, multi-threaded. */
 int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env);
 
+/* ---- encoding on the device.
+ * cordum_encode is host work (hash lookups per string): ~30 ms per million envelopes on 16 cores, against 0.2 ms of
+ * kernels.  cordum_encode_device does the same normalisation + dictionary coding in CUDA kernels: the envelope arrays
+ * (string arena + span columns, ~250 B per job) are copied to the device as they are and encoded there, with the
+ * host's own dictionaries uploaded as probe-able hash tables.  Asynchronous: returns once the copies and kernels are
+ * enqueued on the batch's stream; a dispatch on the same batch queues behind them.  The envelope buffers must stay
+ * unchanged until cordum_batch_wait returns.  Page-locked buffers (cordum_envelopes_alloc) are copied by DMA at full
+ * PCIe rate; pageable memory works too, slower.
+ * What the device leaves to the host - first sight of a topic or of an effective config (pass-rows have to be
+ * computed / JSON parsed), non-ASCII text (Unicode TrimSpace / EqualFold), strings over 4 KiB - raises a per-batch
+ * flag; cordum_batch_wait then encodes that batch with cordum_encode's code path and runs it again, so results are
+ * the same either way (tests compare the two encoders record for record). */
+typedef struct cordum_envelope_caps {
+  uint32_t max_jobs;
+  uint32_t max_risk_tags, max_requires, max_labels; /* total entries of the three list columns */
+  uint64_t arena_bytes;
+} cordum_envelope_caps;
+/* A cordum_envelopes whose arrays are writable page-locked memory owned by the library (cast away the const to fill
+ * them; set n_jobs and arena_len).  Freed by cordum_envelopes_free or with the engine. */
+int32_t cordum_envelopes_alloc(cordum_engine* e, const cordum_envelope_caps* caps, cordum_envelopes** out);
+void cordum_envelopes_free(cordum_engine* e, cordum_envelopes* env);
+int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env);
+/* How many batches the device encoder handed back to the host encoder since the engine was created. */
+uint64_t cordum_host_fallbacks(cordum_engine* e);
+/* The encoded records of a batch (tests / diagnostics): n JobRec (64 B), n RouteRec (32 B) and slot_of[n], copied
+ * into caller memory (any may be NULL).  Layouts: cordum_b200/csrc/tables.h. */
+int32_t cordum_batch_records(cordum_batch* b, void* job_out, void* route_out, uint32_t* slot_of_out);
+
 /* Batched evaluate() [+ post-step + PickSubject()].  Blocking:
  * H2D of the encoded columns, kernels, D2H of the decision records. */
 int32_t cordum_dispatch(cordum_engine* e, cordum_batch* b, uint32_t mode);

@@ -20,13 +20,17 @@ def assert_same(got, want, what=""):
             what, f, len(bad), bad[:8], got[f][bad[:8]], want[f][bad[:8]])
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["host-encode", "device-encode"])
+def eng(request):
+    """Every test of this module runs twice: with the host encoder (cordum_encode) and with the device encoder
+    (cordum_encode_device: the envelope bytes go to the GPU as they are and are dictionary-coded there)."""
     from cordum_b200 import engine
 
+    engine.Batch.default_device_encode = request.param == "device-encode"
     e = engine.Engine(device=0)
     yield e
     e.close()
+    engine.Batch.default_device_encode = False
 
 
 def load(e, policy, routing, workers):
