@@ -352,30 +352,48 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # is measured beside it and reported as `interned_arena`.
     e2e_steps = max(4, min(args.steps, 12))
     plain_jobs = my_jobs.deinterned()
+    pinned = [eng.pinned_envelopes(plain_jobs) for _ in range(2)]   # what a shim would unpack its requests into
+    env_bytes = int(len(plain_jobs.arena) + sum(v.nbytes for v in plain_jobs.cols.values()))
 
-    def e2e_run(jobs_in):
+    def e2e_run(jobs_in, device: bool):
+        """jobs_in: one envelope set per in-flight batch.  device: cordum_encode_device (envelope bytes -> GPU, encoded
+        there) or cordum_encode (host threads) + H2D of the records."""
+        def enc(b, k):
+            if device:
+                b.encode_device(jobs_in[k % 2])
+            else:
+                b.encode(jobs_in[k % 2])
         for k in range(2):
-            batches[k % 2].encode(jobs_in)
+            enc(batches[k % 2], k)
             step(k, batches[k % 2], False)
         sync_all()
         t0 = time.perf_counter()
-        enc = []
+        enc_t = []
         for k in range(e2e_steps):
             b = batches[k % 2]
             te = time.perf_counter()
-            b.encode(jobs_in)                  # waits for this batch's previous run, then host encode
-            enc.append((time.perf_counter() - te) * 1e3)
-            step(k, b, False)                  # H2D records + kernels + D2H decisions, async
+            enc(b, k)                          # waits for this batch's previous run first
+            enc_t.append((time.perf_counter() - te) * 1e3)
+            step(k, b, False)                  # [H2D records +] kernels + D2H decisions, async
         sync_all()
-        return time.perf_counter() - t0, enc
+        return time.perf_counter() - t0, enc_t
 
-    e2e_elapsed, enc_ms = e2e_run(plain_jobs)
-    chk2 = batches[(e2e_steps - 1) % 2].results()
-    assert np.array_equal(chk2["decision"], ref_result["decision"]) and np.array_equal(chk2["rule_idx"], ref_result["rule_idx"]), \
-        "the de-interned envelopes encode to different decisions"
-    log("e2e per-step encode(+wait) ms, de-interned arena:", " ".join("%.1f" % x for x in enc_ms))
-    e2e_int_elapsed, enc_int_ms = e2e_run(my_jobs)
-    log("e2e per-step encode(+wait) ms, interned arena:   ", " ".join("%.1f" % x for x in enc_int_ms))
+    def same_decisions(b):
+        r = b.results()
+        return np.array_equal(r["decision"], ref_result["decision"]) and np.array_equal(r["rule_idx"], ref_result["rule_idx"])
+
+    fb0 = eng.host_fallbacks()
+    e2e_elapsed, enc_ms = e2e_run(pinned, True)
+    assert same_decisions(batches[(e2e_steps - 1) % 2]), "device-encoded envelopes give different decisions"
+    e2e_fallbacks = eng.host_fallbacks() - fb0
+    log("e2e per-step encode_device enqueue(+wait) ms:", " ".join("%.1f" % x for x in enc_ms))
+    e2e_host_elapsed, enc_host_ms = e2e_run([plain_jobs, plain_jobs], False)
+    assert same_decisions(batches[(e2e_steps - 1) % 2]), "the de-interned envelopes encode to different decisions"
+    log("e2e per-step host encode(+wait) ms, de-interned arena:", " ".join("%.1f" % x for x in enc_host_ms))
+    e2e_int_elapsed, enc_int_ms = e2e_run([my_jobs, my_jobs], False)
+    log("e2e per-step host encode(+wait) ms, interned arena:   ", " ".join("%.1f" % x for x in enc_int_ms))
+    for b in batches[:2]:
+        b.encode(my_jobs)                      # leave host-encoded records behind for the records-only loop below
     # from already-encoded pinned records (copies + kernels only)
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -383,9 +401,9 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     sync_all()
     e2e_cols_elapsed = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed, e2e_host_elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed = (float(x) for x in t.tolist())
+        e2e_elapsed, e2e_cols_elapsed, e2e_int_elapsed, e2e_host_elapsed = (float(x) for x in t.tolist())
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -438,12 +456,17 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                    "exchange": args.exchange},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
-                "h2d_bytes_per_step": int(n_shard * in_b + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
-                "includes": "cordum_encode of string-level envelopes (per-job strings, nothing interned) on the host + pinned H2D + kernels + D2H, 2 batches in flight",
-                "input": "de-interned arena: %.0f MB of strings for %d jobs, every job's strings contiguous" % (len(plain_jobs.arena) / 1e6, n_shard),
-                "interned_arena": J * e2e_steps / e2e_int_elapsed,
+                "h2d_bytes_per_step": int(env_bytes + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
+                "includes": "string-level envelopes in page-locked host memory (per-job strings, nothing interned) -> H2D of the "
+                            "envelope bytes -> cordum_encode_device (dictionary coding + topic sort on the GPU) -> kernels -> D2H of "
+                            "the decision records, 2 batches in flight",
+                "input": "de-interned arena: %.0f MB of strings + %.0f MB of spans for %d jobs" % (
+                    len(plain_jobs.arena) / 1e6, (env_bytes - len(plain_jobs.arena)) / 1e6, n_shard),
+                "host_fallbacks": int(e2e_fallbacks),
+                "host_encoder": {"value": J * e2e_steps / e2e_host_elapsed, "interned_arena": J * e2e_steps / e2e_int_elapsed,
+                                 "encode_ms_per_batch": float(np.median(enc_host_ms)), "encode_ms_per_batch_interned": float(np.median(enc_int_ms)),
+                                 "what": "cordum_encode on the host threads + H2D of the 96 B records instead of the device encoder"},
                 "from_encoded_records": J * e2e_steps / e2e_cols_elapsed,
-                "host_encode_ms_per_batch": float(np.median(enc_ms)), "host_encode_ms_per_batch_interned": float(np.median(enc_int_ms)),
                 "host": hostinfo.describe()},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

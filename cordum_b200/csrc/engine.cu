@@ -799,8 +799,8 @@ namespace {
 struct EnvLayout { size_t off[15]; size_t total; };   // arena + the 14 arrays, 256 B aligned, in cordum_envelopes order
 EnvLayout env_layout(uint32_t n, uint64_t arena, uint32_t n_risk, uint32_t n_req, uint32_t n_lab) {
   const size_t sz[15] = {(size_t)arena + 16, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n * 8, (size_t)n, (size_t)n * 8, (size_t)n * 8,
-                         (size_t)n, (size_t)n * 8, (size_t)n * 8, ((size_t)n + 1) * 4 + (size_t)n_risk * 8, ((size_t)n + 1) * 4 + (size_t)n_req * 8,
-                         ((size_t)n + 1) * 4 + (size_t)n_lab * 16, (size_t)n};
+                         (size_t)n, (size_t)n * 8, (size_t)n * 8, ((size_t)n + 1) * 4 + 16 + (size_t)n_risk * 8, ((size_t)n + 1) * 4 + 16 + (size_t)n_req * 8,
+                         ((size_t)n + 1) * 4 + 16 + (size_t)n_lab * 16, (size_t)n};
   EnvLayout L{};
   size_t at = 0;
   for (int i = 0; i < 15; ++i) { L.off[i] = at; at += (sz[i] + 255) & ~size_t(255); }
@@ -897,10 +897,10 @@ int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_env
   CK(h2d(5, env->has_meta, n), "H2D"); CK(h2d(6, env->meta_tenant_id, (size_t)n * 8), "H2D");
   CK(h2d(7, env->actor_id, (size_t)n * 8), "H2D"); CK(h2d(8, env->actor_type, n), "H2D");
   CK(h2d(9, env->capability, (size_t)n * 8), "H2D"); CK(h2d(10, env->pack_id, (size_t)n * 8), "H2D");
-  const size_t offs = ((size_t)n + 1) * 4;
-  CK(h2d(11, env->risk_off, offs), "H2D"); CK(h2d(11, env->risk_tags, (size_t)n_risk * 8, offs), "H2D");
-  CK(h2d(12, env->requires_off, offs), "H2D"); CK(h2d(12, env->requires_, (size_t)n_req * 8, offs), "H2D");
-  CK(h2d(13, env->label_off, offs), "H2D"); CK(h2d(13, env->label_keys, (size_t)n_lab * 8, offs), "H2D");
+  const size_t offs_bytes = ((size_t)n + 1) * 4, offs = (offs_bytes + 15) & ~size_t(15);   // the span lists follow their offset arrays, 16 B aligned
+  CK(h2d(11, env->risk_off, offs_bytes), "H2D"); CK(h2d(11, env->risk_tags, (size_t)n_risk * 8, offs), "H2D");
+  CK(h2d(12, env->requires_off, offs_bytes), "H2D"); CK(h2d(12, env->requires_, (size_t)n_req * 8, offs), "H2D");
+  CK(h2d(13, env->label_off, offs_bytes), "H2D"); CK(h2d(13, env->label_keys, (size_t)n_lab * 8, offs), "H2D");
   CK(h2d(13, env->label_vals, (size_t)n_lab * 8, offs + (size_t)n_lab * 8), "H2D");
   CK(h2d(14, env->approved, n), "H2D");
   P.n_jobs = n;

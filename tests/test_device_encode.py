@@ -47,7 +47,10 @@ def test_device_records_equal_host_records(eng, name, n):
     eng.load_routing(cfg.routing)
     eng.load_workers(cfg.workers)
     bh, bd = eng.batch(cfg.jobs.n_jobs), eng.batch(cfg.jobs.n_jobs)
-    host = by_job(bh.encode(cfg.jobs))                 # also registers every topic / effective config of the batch
+    bh.encode(cfg.jobs)                                # registers every topic / effective config of the batch ...
+    host = by_job(bh.encode(cfg.jobs))                 # ... so this encode sees the final dictionaries (an effective config
+    #                                                    seen for the first time interns its MCP values: a job encoded
+    #                                                    before that carries the equivalent id "other" for them)
     f0 = eng.host_fallbacks()
     for env in (cfg.jobs, cfg.jobs.deinterned(), eng.pinned_envelopes(cfg.jobs.deinterned())):
         dev = by_job(bd.encode_device(env))
