@@ -192,6 +192,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # resident copies of the shard: enough distinct addresses that successive steps cannot hit L2
     shard_bytes = n_shard * (in_b + out_b)
     n_rot = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, shard_bytes))) + 1)
+    if args.step == "tick" or (args.step == "auto" and world > 1):
+        n_rot = (n_rot + 5) // 6 * 6   # tick graphs are cached per (batch pair, tick phase of 6): a multiple of 6 keeps them to n_rot
     batches = [eng.batch(n_shard) for _ in range(n_rot)]
     t_enc0 = time.perf_counter()
     for b in batches:
@@ -232,7 +234,21 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
         recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
 
+    # auto: the multi-stream path at one GPU (measured faster there: 133 vs 153 us per 1M-job step), ticks when sharded
+    # (the per-step host cost of ~17 API calls + the NCCL all-gather is what bounded the 8-GPU step)
+    use_ticks = args.step == "tick" or (args.step == "auto" and world > 1)
+    if use_ticks and world > 1:
+        # peer-memory heartbeat exchange: every rank maps every other rank's slice buffer (CUDA IPC over NVLink)
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.peer_export(rank, world))
+        eng.peer_import(handles)
+        dist.barrier()
+
     def step(k: int, batch, resident: bool):
+        if use_ticks and resident:
+            # one graph launch: heartbeat epoch k (peer gather + refresh) || policy of this batch || route of the previous one
+            batch.tick(delta_sets[k % n_delta_sets].data_ptr(), w0, w1 - w0)
+            return
         if args.exchange == "engine":
             # heartbeat ingest (pinned host -> HBM) + NCCL all-gather of the per-rank slices + refresh
             eng.ingest(delta_sets[k % n_delta_sets].data_ptr(), w0, w1 - w0)
@@ -254,6 +270,10 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident: `value`
+    if use_ticks:
+        for k in range(n_rot + 6):      # untimed: every (batch pair, phase) tick graph is captured here
+            step(k, batches[k % n_rot], True)
+        sync_all()
     for k in range(args.warmup):
         step(k, batches[k % n_rot], True)
     sync_all()
@@ -266,12 +286,21 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ext = [torch.cuda.ExternalStream(b.stream, device=torch.device("cuda", local_rank)) for b in batches]
     t0 = time.perf_counter()
-    ev_a.record(stream)
-    for k in range(args.steps):
-        step(args.warmup + k, batches[(args.warmup + k) % n_rot], True)
-    for x in ext:
-        stream.wait_stream(x)
-    ev_b.record(stream)
+    if use_ticks:
+        # every tick is one graph launch on the engine's tick stream: the events go on that stream
+        tstream = torch.cuda.ExternalStream(eng.tick_stream, device=torch.device("cuda", local_rank))
+        ev_a.record(tstream)
+        for k in range(args.steps):
+            step(args.warmup + k, batches[(args.warmup + k) % n_rot], True)
+        eng.tick_flush()             # the route of the last batch
+        ev_b.record(tstream)
+    else:
+        ev_a.record(stream)
+        for k in range(args.steps):
+            step(args.warmup + k, batches[(args.warmup + k) % n_rot], True)
+        for x in ext:
+            stream.wait_stream(x)
+        ev_b.record(stream)
     sync_all()
     wall = time.perf_counter() - t0
     elapsed = ev_a.elapsed_time(ev_b) * 1e-3
@@ -451,9 +480,12 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                    "jobs_per_rank": n_shard, "parallelism": "jobs sharded by index x%d, tables replicated" % world,
                    "l2": "inputs larger than L2: steps rotate over %d resident copies of the shard (%.0f MB total)" % (
                        n_rot, n_rot * shard_bytes / 1e6),
-                   "step": "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else ""),
+                   "step": ("one CUDA-graph tick: [heartbeat-slice H2D + %sworker_chunk/merge] || policy_kernel(batch k) || route_kernel(batch k-1)" % (
+                       "peer-memory gather over NVLink + " if world > 1 else "")) if use_ticks else (
+                       "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else "")),
+                   "step_mode": args.step,
                    "layout": "jobs as topic-sorted 64 B + 32 B records (host encoder), bulk-async tile loads",
-                   "exchange": args.exchange},
+                   "exchange": ("peer memory (CUDA IPC, NVLink)" if world > 1 else "none") if use_ticks else args.exchange},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(env_bytes + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
@@ -497,6 +529,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=0,
                     help="check only the first N jobs of each rank's shard against the oracle (0 = every job; for quick runs)")
+    ap.add_argument("--step", default="auto", choices=["auto", "tick", "streams"],
+                    help="device-resident step: one CUDA-graph scheduler tick (peer-memory heartbeat exchange at N > 1), or the "
+                         "multi-stream path (cordum_workers_ingest + cordum_dispatch_resident_async, NCCL all-gather at N > 1)")
     ap.add_argument("--exchange", default="engine", choices=["engine", "torch"],
                     help="heartbeat exchange: the engine's own NCCL communicator (cordum_workers_ingest) or "
                          "torch.distributed all_gather + cordum_workers_set_loads_device")

@@ -18,6 +18,7 @@ API = [
     "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
     "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
     "cordum_workers_set_loads_device", "cordum_exchange_unique_id", "cordum_exchange_init", "cordum_workers_ingest",
+    "cordum_tick_async", "cordum_tick_flush", "cordum_tick_stream", "cordum_peer_export", "cordum_peer_import",
     "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_encode_device", "cordum_envelopes_alloc",
     "cordum_envelopes_free", "cordum_host_fallbacks", "cordum_batch_records", "cordum_dispatch",
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
@@ -54,6 +55,12 @@ def load() -> C.CDLL:
     L.cordum_exchange_unique_id.argtypes = [vp]
     L.cordum_exchange_init.argtypes = [vp, vp, i32, i32]
     L.cordum_workers_ingest.argtypes = [vp, vp, u32, u32]
+    L.cordum_tick_async.argtypes = [vp, vp, u32, vp, u32, u32]
+    L.cordum_tick_flush.argtypes = [vp]
+    L.cordum_tick_stream.argtypes = [vp]
+    L.cordum_tick_stream.restype = vp
+    L.cordum_peer_export.argtypes = [vp, i32, i32, vp]
+    L.cordum_peer_import.argtypes = [vp, vp]
     L.cordum_batch_alloc.argtypes = [vp, u32, C.POINTER(vp)]
     L.cordum_batch_free.argtypes = [vp]
     L.cordum_batch_free.restype = None

@@ -5,10 +5,13 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -87,6 +90,33 @@ struct cordum_engine {
   EncodeTables et{};             // rebased onto b_dicts
   uint64_t v_dict = ~0ull;
   std::vector<cordum_envelopes*> env_sets;   // pinned envelope staging sets handed out by cordum_envelopes_alloc
+  uint64_t tables_gen = 0;       // bumps whenever a device table pointer or scalar may have changed (captured graphs bake them in)
+  // ---- scheduler ticks (cordum_tick_async): one CUDA graph launch per tick
+  struct Tick {
+    cudaStream_t s[2] = {nullptr, nullptr};                // tick k is launched on s[k & 1]: consecutive ticks overlap
+    cudaStream_t sa = nullptr, sc = nullptr;               // fork streams used only while capturing
+    cudaEvent_t ev_fork = nullptr, ev_a = nullptr, ev_c = nullptr;   // capture-internal fork / join
+    cudaEvent_t done[2] = {nullptr, nullptr};              // recorded behind tick k on s[k & 1]: staging reuse (host), and the
+                                                           // route branch of tick k+1 waits for it inside its graph
+    cudaEvent_t refreshed[2] = {nullptr, nullptr};         // recorded inside graph k at the end of its heartbeat branch: the
+                                                           // heartbeat branch of tick k+1 starts behind it (the epochs stay ordered)
+    cudaEvent_t ev_join = nullptr;
+    Load16* h_slice[2] = {nullptr, nullptr};               // pinned staging of this rank's heartbeat slice
+    size_t h_cap = 0;
+    cordum_batch* prev = nullptr;                          // its policy ran in the previous tick; its route is due
+    uint64_t n = 0;                                        // ticks so far
+    bool active = false;                                   // ticks have been issued since the last plain dispatch / ingest
+    std::map<std::tuple<cordum_batch*, cordum_batch*, int, uint32_t, uint32_t, uint64_t>, cudaGraphExec_t> graphs;
+  } tick;
+  // ---- peer-memory heartbeat exchange (cordum_peer_export / cordum_peer_import)
+  struct Peers {
+    int rank = 0, world = 1;
+    uint32_t per = 0;                                      // worker slots per rank
+    uint8_t* mine = nullptr;                               // [flags 256 B][slice parity 0][slice parity 1]
+    size_t bytes = 0;
+    uint8_t* base[CORDUM_MAX_PEERS] = {};                  // every rank's buffer as mapped here (mine included)
+    bool ready = false;
+  } peers;
   // Everything the worker-table refresh kernels derive from the loads, in kSets copies used round-robin: the refresh
   // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
   // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
@@ -118,6 +148,8 @@ struct cordum_batch {
   uint32_t* h_fallback = nullptr;   // pinned: 1 = the device encoder left something to the host
   uint32_t last_mode = 0;
   bool last_copy_out = false;
+  bool tick_pending = false;     // dispatched through cordum_tick_async: results are on the device once the tick streams have drained
+  uint64_t tick_no = 0;          // the tick it was handed in with (its route runs in tick_no + 1)
   cordum_decision* h_out = nullptr;   // pinned
   cordum_decision* d_out = nullptr;
   uint2* d_route = nullptr;           // [0].x = count, [2..] = compacted list of dispatchable jobs {slot, head}
@@ -264,6 +296,7 @@ int sync_tables(cordum_engine* e) {
     e->host_loads = true;
   }
   CK(cudaStreamSynchronize(s), "table upload");
+  e->tables_gen++;
   return CORDUM_OK;
 }
 
@@ -288,6 +321,18 @@ int sync_dicts(cordum_engine* e) {
 }
 
 // The kernels' view of the tables with the derived pointers of one set.
+// Ticks keep their own order on their own stream; a plain dispatch / ingest after ticks first lets that stream drain.
+int tick_flush_locked(cordum_engine* e);
+int leave_tick_mode(cordum_engine* e) {
+  if (!e->tick.active) return CORDUM_OK;
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = tick_flush_locked(e);
+  if (rc) return rc;
+  for (cudaStream_t st : e->tick.s) CK(cudaStreamSynchronize(st), "drain tick stream");
+  e->tick.active = false;
+  return CORDUM_OK;
+}
+
 DeviceTables view(const cordum_engine* e, int set) {
   DeviceTables d = e->dt;
   const auto& D = e->ds[set];
@@ -348,6 +393,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   KParams P;
   cudaEvent_t ev_ready = nullptr;
+  if (int rc = leave_tick_mode(e)) return rc;
   // e->mu is held until every launch of this dispatch is enqueued: a table sync on another thread (first sight of a
   // topic, a reload) synchronizes the device and may then free and reallocate table buffers - it must not slip in
   // between view() and the launches that use those pointers.
@@ -410,6 +456,15 @@ int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* 
 
 int wait(cordum_batch* b) {
   cordum_engine* e = b->e;
+  if (b->tick_pending) {   // dispatched by a tick: its route runs in the tick after its policy (or in the flush)
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      if (e->tick.prev == b) { int rc = tick_flush_locked(e); if (rc) return rc; }
+    }
+    for (cudaStream_t st : e->tick.s) CK(cudaStreamSynchronize(st), "tick wait");
+    b->tick_pending = false;
+    b->total_ms = b->kernel_ms = b->policy_ms = b->route_ms = 0;
+  }
   if (!b->pending && !b->enc_inflight) return CORDUM_OK;
   CK(cudaStreamSynchronize(b->stream), "batch wait");
   const bool dispatched = b->pending;
@@ -553,6 +608,205 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
 }  // namespace
 
 namespace {
+// ------------------------------------------------------------ scheduler ticks
+// One tick = one CUDA graph launch with three independent branches:
+//     A  heartbeat epoch k: H2D of this rank's slice -> [peer gather over NVLink] -> worker_chunk -> worker_merge   (set k % 2)
+//     B  policy_kernel of the batch handed in with this tick
+//     C  route_kernel of the batch handed in with the PREVIOUS tick, on the worker tables of epoch k-1            (set (k-1) % 2)
+// so a tick costs max(A, B, C) instead of their sum plus ~17 API calls, and consecutive ticks still overlap what the
+// multi-stream path overlapped.  Graphs are cached per (new batch, previous batch, parity, sizes, table generation).
+int tick_share() { static const int v = []() { const char* s = getenv("CORDUM_TICK_SHARE"); return s ? atoi(s) : 0; }(); return v; }   // > 0: cap each branch at that many CTAs per SM (measured: no gain, 0 = full grids)
+
+int tick_graph(cordum_engine* e, cordum_batch* bn, cordum_batch* bp, int phase, bool bn_routed_last_tick, cudaGraphExec_t* out) {
+  // phase = tick number mod 6: stream / staging / gather-buffer parity = phase & 1, derived-table set = phase % 3
+  auto& T = e->tick;
+  const uint32_t W = e->host->tables().n_slots;
+  const auto key = std::make_tuple(bn, bp, phase + (bn_routed_last_tick ? 8 : 0), bn ? bn->n : 0u, bp ? bp->n : 0u, e->tables_gen);
+  auto it = T.graphs.find(key);
+  if (it != T.graphs.end()) { *out = it->second; return CORDUM_OK; }
+  if (T.graphs.size() > 96) {   // stale generations / batches: start over
+    for (auto& kv : T.graphs) cudaGraphExecDestroy(kv.second);
+    T.graphs.clear();
+  }
+  CK(launch_configure(), "kernel attributes");
+  const int parity = phase & 1, set_new = phase % 3, set_old = (phase + 2) % 3;
+  cudaStream_t S = T.s[parity];
+  CK(cudaStreamBeginCapture(S, cudaStreamCaptureModeThreadLocal), "begin capture");
+  auto fail_capture = [&](cudaError_t err, const char* what) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(S, &g);
+    if (g) cudaGraphDestroy(g);
+    return fail(e, err, what);
+  };
+#define CKC(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail_capture(_e, what); } while (0)
+  CKC(cudaEventRecord(T.ev_fork, S), "fork");
+  // ---- A: heartbeat epoch, behind the heartbeat branch of the previous tick (a graph of its own, on the other stream)
+  CKC(cudaStreamWaitEvent(T.sa, T.ev_fork, 0), "fork");
+  CKC(cudaStreamWaitEvent(T.sa, T.refreshed[parity ^ 1], cudaEventWaitExternal), "order heartbeat epochs");
+  if (W) {
+    uint8_t* table = (uint8_t*)e->gather[parity].p;
+    DeviceTables tv = view(e, set_new);
+    tv.loads = (const Load16*)table;
+    if (e->peers.ready && e->peers.world > 1) {
+      const uint32_t per = e->peers.per;
+      const size_t stride = (size_t)per * sizeof(Load16) + 16;   // a slice buffer: the records, then the epoch word
+      uint8_t* mine = e->peers.mine + 256 + (size_t)parity * stride;
+      // the staging buffer carries the epoch number behind the slice: one copy brings both, and the gather kernel -
+      // whose parameters the graph bakes in - reads the epoch it announces and waits for from there
+      CKC(cudaMemcpyAsync(mine, T.h_slice[parity], stride, cudaMemcpyHostToDevice, T.sa), "H2D heartbeat slice");
+      PeerGather G{};
+      G.rank = (uint32_t)e->peers.rank; G.world = (uint32_t)e->peers.world; G.per = per;
+      for (int q = 0; q < e->peers.world; ++q) {
+        G.peer_slices[q] = (const Load16*)(e->peers.base[q] + 256 + (size_t)parity * stride);
+        G.peer_flags[q] = (uint32_t*)e->peers.base[q];
+      }
+      G.my_flags = (const uint32_t*)e->peers.mine;
+      G.epoch_ptr = (const uint32_t*)(mine + (size_t)per * sizeof(Load16));
+      G.table = (Load16*)table;
+      CKC(launch_peer_gather(G, T.sa), "peer gather");
+    } else {
+      CKC(cudaMemcpyAsync(table, T.h_slice[parity], (size_t)W * sizeof(Load16), cudaMemcpyHostToDevice, T.sa), "H2D heartbeats");
+    }
+    CKC(launch_worker_pools(tv, T.sa, nullptr), "worker-table refresh kernels");
+  }
+  CKC(cudaEventRecordWithFlags(T.refreshed[parity], T.sa, cudaEventRecordExternal), "publish heartbeat epoch");
+  CKC(cudaEventRecord(T.ev_a, T.sa), "join");
+  // ---- C: route of the previous batch on the previous epoch's tables, once the previous tick (policy of that batch, refresh
+  //         of that epoch) has finished
+  if (bp && bp->n) {
+    CKC(cudaStreamWaitEvent(T.sc, T.ev_fork, 0), "fork");
+    CKC(cudaStreamWaitEvent(T.sc, T.done[parity ^ 1], cudaEventWaitExternal), "wait previous tick");
+    KParams P{};
+    P.t = view(e, set_old);
+    device_records(bp, P.recs);
+    P.out = bp->d_out; P.n_jobs = bp->n; P.honor_approved = 1u;
+    P.route_count = reinterpret_cast<uint32_t*>(bp->d_route); P.route_list = bp->d_route + 2;
+    CKC(launch_route(P, false, e->sm_count, T.sc, tick_share()), "route_kernel");
+    CKC(cudaEventRecord(T.ev_c, T.sc), "join");
+  }
+  // ---- B: policy of the new batch
+  if (bn && bn->n) {
+    KParams P{};
+    P.t = view(e, set_old);   // policy_kernel reads no worker state
+    device_records(bn, P.recs);
+    P.out = bn->d_out; P.n_jobs = bn->n; P.honor_approved = 1u;
+    P.route_count = reinterpret_cast<uint32_t*>(bn->d_route); P.route_list = bn->d_route + 2;
+    // this batch's previous use was routed by the tick before this one (only two batches alternate): that route still
+    // reads what this policy run overwrites
+    if (bn_routed_last_tick) CKC(cudaStreamWaitEvent(S, T.done[parity ^ 1], cudaEventWaitExternal), "wait previous route of this batch");
+    CKC(cudaMemsetAsync(bn->d_route, 0, sizeof(uint32_t), S), "reset route count");
+    CKC(launch_policy(P, e->sm_count, S, tick_share()), "policy_kernel");
+  }
+  CKC(cudaStreamWaitEvent(S, T.ev_a, 0), "join");
+  if (bp && bp->n) CKC(cudaStreamWaitEvent(S, T.ev_c, 0), "join");
+#undef CKC
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamEndCapture(S, &g), "end capture");
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (ie != cudaSuccess) return fail(e, ie, "graph instantiate");
+  T.graphs[key] = ge;
+  *out = ge;
+  return CORDUM_OK;
+}
+
+int tick_setup(cordum_engine* e) {
+  auto& T = e->tick;
+  if (T.s[0]) return CORDUM_OK;
+  for (auto& st : T.s) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
+  CK(cudaStreamCreateWithFlags(&T.sa, cudaStreamNonBlocking), "stream");
+  CK(cudaStreamCreateWithFlags(&T.sc, cudaStreamNonBlocking), "stream");
+  for (cudaEvent_t* ev : {&T.ev_fork, &T.ev_a, &T.ev_c, &T.ev_join}) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "event");
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&T.done[i], cudaEventDisableTiming), "event"); CK(cudaEventRecord(T.done[i], T.s[i]), "event");
+    CK(cudaEventCreateWithFlags(&T.refreshed[i], cudaEventDisableTiming), "event"); CK(cudaEventRecord(T.refreshed[i], T.s[i]), "event");
+  }
+  return CORDUM_OK;
+}
+
+// one tick; e->mu and the host mutex held.  bn may be null (flush: only route the previous batch)
+int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* slice, uint32_t n_slice) {
+  auto& T = e->tick;
+  const HostTables& t = e->host->tables();
+  const uint32_t W = t.n_slots;
+  const int phase = (int)(T.n % 6), parity = phase & 1;
+  if (!bn) {
+    // flush: the route of the previous batch alone, behind its tick (policy of that batch, refresh of that epoch); then both
+    // tick streams are joined so that an event recorded on s[0] afterwards covers everything issued so far
+    cordum_batch* bp = T.prev;
+    if (bp) {
+      const int pp = (int)((T.n + 5) % 6);   // phase of the previous tick
+      cudaStream_t S = T.s[parity];
+      CK(cudaStreamWaitEvent(S, T.done[pp & 1], 0), "wait previous tick");
+      KParams P{};
+      P.t = view(e, pp % 3);
+      device_records(bp, P.recs);
+      P.out = bp->d_out; P.n_jobs = bp->n; P.honor_approved = 1u;
+      P.route_count = reinterpret_cast<uint32_t*>(bp->d_route); P.route_list = bp->d_route + 2;
+      CK(launch_route(P, false, e->sm_count, S), "route_kernel");
+      if (bp->n) e->launches++;
+      T.prev = nullptr;
+    }
+    CK(cudaEventRecord(T.ev_join, T.s[1]), "join"); CK(cudaStreamWaitEvent(T.s[0], T.ev_join, 0), "join");
+    CK(cudaEventRecord(T.ev_join, T.s[0]), "join"); CK(cudaStreamWaitEvent(T.s[1], T.ev_join, 0), "join");
+    return CORDUM_OK;
+  }
+  static const bool trace = getenv("CORDUM_TICK_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const auto t0 = now();
+  // staging of this parity was last read by the H2D of tick n-2
+  CK(cudaEventSynchronize(T.done[parity]), "wait staging");
+  const auto t1 = now();
+  const size_t bytes = (size_t)n_slice * sizeof(Load16);
+  if (T.h_cap < bytes) {
+    for (cudaStream_t st : T.s) CK(cudaStreamSynchronize(st), "drain before staging growth");
+    for (auto& p : T.h_slice) { if (p) cudaFreeHost(p); p = nullptr; }
+    for (auto& p : T.h_slice) CK(cudaHostAlloc((void**)&p, bytes + 64, cudaHostAllocDefault), "pinned heartbeat staging");
+    T.h_cap = bytes;
+    for (auto& kv : T.graphs) cudaGraphExecDestroy(kv.second);   // they bake the staging pointers in
+    T.graphs.clear();
+  }
+  if (bytes) std::memcpy(T.h_slice[parity], slice, bytes);
+  *reinterpret_cast<uint32_t*>((uint8_t*)T.h_slice[parity] + bytes) = (uint32_t)(T.n + 1);   // the epoch, behind the slice
+  if (e->gather[parity].cap < (size_t)W * sizeof(Load16)) {
+    CK(cudaDeviceSynchronize(), "sync before gather buffer allocation");
+    CK(e->gather[parity].reserve((size_t)W * sizeof(Load16)), "alloc gather buffer");
+    CK(e->gather[parity ^ 1].reserve((size_t)W * sizeof(Load16)), "alloc gather buffer");
+    e->tables_gen++;
+  }
+  const auto t2 = now();
+  cudaGraphExec_t ge = nullptr;
+  // Ticks up to n-2 have finished when tick n starts (stream order + the route branch's wait); tick n-1 may still run.
+  const bool routed_last = bn->tick_pending && T.n - bn->tick_no == 2;   // handed in with tick n-2, routed by tick n-1
+  int rc = tick_graph(e, bn, T.prev, phase, routed_last, &ge);
+  if (rc) return rc;
+  const auto t3 = now();
+  CK(cudaGraphLaunch(ge, T.s[parity]), "graph launch");
+  CK(cudaEventRecord(T.done[parity], T.s[parity]), "event record");
+  if (trace) {
+    static double acc[4] = {0, 0, 0, 0};
+    static uint64_t cnt = 0;
+    const auto t4 = now();
+    acc[0] += us(t0, t1); acc[1] += us(t1, t2); acc[2] += us(t2, t3); acc[3] += us(t3, t4);
+    if (++cnt % 100 == 0) {
+      fprintf(stderr, "tick host us (mean of 100): wait-staging %.1f  stage-slice %.1f  graph-lookup/capture %.1f  launch+record %.1f\n",
+              acc[0] / 100, acc[1] / 100, acc[2] / 100, acc[3] / 100);
+      acc[0] = acc[1] = acc[2] = acc[3] = 0;
+    }
+  }
+  e->launches += (W ? (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->peers.ready && e->peers.world > 1 ? 1 : 0) : 0) + (bn->n ? 1 : 0) + (T.prev && T.prev->n ? 1 : 0);
+  e->cur = phase % 3;   // the set this tick refreshed (a later plain dispatch continues from it)
+  e->pools_dirty = false; e->host_loads = false;
+  bn->tick_no = T.n;
+  T.prev = bn;
+  T.n++;
+  T.active = true;
+  return CORDUM_OK;
+}
+int tick_flush_locked(cordum_engine* e) { return tick_locked(e, nullptr, nullptr, 0); }
+
 int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
   if (!env) { g_err = "envelopes no longer available for the host encoder"; return CORDUM_E_STATE; }
   b->n = env->n_jobs;
@@ -633,6 +887,12 @@ void cordum_engine_destroy(cordum_engine* e) {
     { std::lock_guard<std::mutex> g(e->mu); live.swap(e->batches); }
     for (cordum_batch* b : live) batch_release(b);
   }
+  for (auto& kv : e->tick.graphs) cudaGraphExecDestroy(kv.second);
+  for (cudaStream_t st : {e->tick.s[0], e->tick.s[1], e->tick.sa, e->tick.sc}) if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : {e->tick.ev_fork, e->tick.ev_a, e->tick.ev_c, e->tick.ev_join, e->tick.done[0], e->tick.done[1], e->tick.refreshed[0], e->tick.refreshed[1]}) if (ev) cudaEventDestroy(ev);
+  for (auto& p : e->tick.h_slice) if (p) cudaFreeHost(p);
+  for (int q = 0; q < e->peers.world && e->peers.ready; ++q) if (q != e->peers.rank && e->peers.base[q]) cudaIpcCloseMemHandle(e->peers.base[q]);
+  if (e->peers.mine) cudaFree(e->peers.mine);
   for (cordum_envelopes* env : e->env_sets) cudaFreeHost(env);
   e->env_sets.clear();
   DevBuf* all[] = {&e->b_dicts, &e->b_rows, &e->b_row_check,
@@ -700,6 +960,7 @@ int32_t cordum_workers_update(cordum_engine* e, uint32_t n, const uint32_t* slot
 int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint32_t n_workers, void* stream) {
   if (!e || !dptr) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  if (int rc = leave_tick_mode(e)) return rc;
   std::lock_guard<std::mutex> g(e->mu);
   std::lock_guard<std::mutex> gh(e->host->mutex());
   if (n_workers != e->host->tables().n_slots) { g_err = "load table size does not match the worker registry"; return CORDUM_E_INVALID; }
@@ -743,12 +1004,103 @@ int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_
 int32_t cordum_workers_ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice) {
   if (!e || !slice) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  if (int rc = leave_tick_mode(e)) return rc;
   std::lock_guard<std::mutex> g(e->mu);
   std::lock_guard<std::mutex> gh(e->host->mutex());
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   int rc = sync_tables(e);
   if (rc) return rc;
   return ingest(e, slice, first_slot, n_slice);
+}
+
+int32_t cordum_peer_export(cordum_engine* e, int32_t rank, int32_t world, char handle[CORDUM_PEER_HANDLE_BYTES]) {
+  if (!e || !handle || world < 1 || world > CORDUM_MAX_PEERS || rank < 0 || rank >= world) { g_err = "bad argument"; return CORDUM_E_INVALID; }
+  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<std::mutex> gh(e->host->mutex());
+  const uint32_t W = e->host->tables().n_slots;
+  if (W == 0 || W % (uint32_t)world) { g_err = "worker registry size is not a multiple of the world size"; return CORDUM_E_INVALID; }
+  if (e->peers.mine) { g_err = "peer exchange already exported"; return CORDUM_E_STATE; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  auto& P = e->peers;
+  P.rank = rank; P.world = world; P.per = W / (uint32_t)world;
+  P.bytes = 256 + 2 * ((size_t)P.per * sizeof(Load16) + 16);
+  CK(cudaMalloc((void**)&P.mine, P.bytes), "peer exchange buffer");
+  CK(cudaMemset(P.mine, 0, P.bytes), "peer exchange buffer");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, P.mine), "cudaIpcGetMemHandle");
+  static_assert(sizeof h <= CORDUM_PEER_HANDLE_BYTES, "handle size");
+  std::memset(handle, 0, CORDUM_PEER_HANDLE_BYTES);
+  std::memcpy(handle, &h, sizeof h);
+  return CORDUM_OK;
+}
+
+int32_t cordum_peer_import(cordum_engine* e, const char* handles) {
+  if (!e || !handles) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  std::lock_guard<std::mutex> g(e->mu);
+  auto& P = e->peers;
+  if (!P.mine) { g_err = "cordum_peer_export first"; return CORDUM_E_STATE; }
+  if (P.ready) { g_err = "peers already imported"; return CORDUM_E_STATE; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  for (int q = 0; q < P.world; ++q) {
+    if (q == P.rank) { P.base[q] = P.mine; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)q * CORDUM_PEER_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    P.base[q] = (uint8_t*)p;
+  }
+  P.ready = true;
+  e->tables_gen++;
+  return CORDUM_OK;
+}
+
+int32_t cordum_tick_async(cordum_engine* e, cordum_batch* b, uint32_t mode, const cordum_worker_load* slice, uint32_t first_slot,
+                          uint32_t n_slice) {
+  if (!e || !b || !slice) { g_err = "null argument"; return CORDUM_E_INVALID; }
+  if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
+  if ((mode & 0xFFu) != CORDUM_MODE_POLICY_AND_ROUTE) { g_err = "a tick evaluates policy and routes (CORDUM_MODE_POLICY_AND_ROUTE)"; return CORDUM_E_INVALID; }
+  if (!b->encoded || !b->resident) { g_err = "the batch must be encoded and resident on the device (dispatch it once, or cordum_encode_device)"; return CORDUM_E_STATE; }
+  // Work of this batch on its own stream (an encode, a plain dispatch) is waited for on the host.  An earlier TICK of the
+  // same batch needs no host wait unless it was the previous tick (its route and this policy would share a graph): the
+  // device-side order covers every older tick (tick_locked).
+  if (b->pending || b->enc_inflight || (b->tick_pending && e->tick.n - b->tick_no < 2)) { int rc = wait(b); if (rc) return rc; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<std::mutex> gh(e->host->mutex());
+  if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
+  const uint32_t W = e->host->tables().n_slots;
+  if (e->peers.ready && e->peers.world > 1) {
+    if (first_slot != (uint32_t)e->peers.rank * e->peers.per || n_slice != e->peers.per || e->peers.per * (uint32_t)e->peers.world != W) {
+      g_err = "slice is not this rank's share of the worker registry"; return CORDUM_E_INVALID;
+    }
+  } else if (first_slot != 0 || n_slice != W) { g_err = "without a peer exchange the slice must be the whole worker table"; return CORDUM_E_INVALID; }
+  if (!e->tick.active) CK(cudaDeviceSynchronize(), "enter tick mode");   // plain dispatches in flight read / write the same table sets
+  int rc = sync_tables(e);
+  if (rc) return rc;
+  rc = tick_setup(e);
+  if (rc) return rc;
+  rc = tick_locked(e, b, slice, n_slice);
+  if (rc) return rc;
+  b->tick_pending = true;
+  b->last_mode = CORDUM_MODE_POLICY_AND_ROUTE;
+  return CORDUM_OK;
+}
+
+/* The cudaStream_t all ticks are launched on, so a harness can bracket them with its own CUDA events. */
+void* cordum_tick_stream(cordum_engine* e) {
+  if (!e) return nullptr;
+  std::lock_guard<std::mutex> g(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess || tick_setup(e) != CORDUM_OK) return nullptr;
+  return (void*)e->tick.s[0];
+}
+
+int32_t cordum_tick_flush(cordum_engine* e) {
+  if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
+  if (!e->tick.s[0]) return CORDUM_OK;
+  std::lock_guard<std::mutex> g(e->mu);
+  std::lock_guard<std::mutex> gh(e->host->mutex());
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  return tick_flush_locked(e);
 }
 
 int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out) {
@@ -790,7 +1142,7 @@ void cordum_batch_free(cordum_batch* b) {
 int32_t cordum_encode(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
   if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
-  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  if (b->pending || b->enc_inflight || b->tick_pending) { int rc = wait(b); if (rc) return rc; }
   return host_encode_into(e, b, env);
 }
 
@@ -858,7 +1210,7 @@ int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_env
   if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
-  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  if (b->pending || b->enc_inflight || b->tick_pending) { int rc = wait(b); if (rc) return rc; }
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   const uint32_t n = env->n_jobs;
   b->n = n;
@@ -935,7 +1287,7 @@ int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_env
 static int ensure_host_records(cordum_batch* b) {
   cordum_engine* e = b->e;
   if (b->host_records_valid) return CORDUM_OK;
-  if (b->pending || b->enc_inflight) { int rc = wait(b); if (rc) return rc; }
+  if (b->pending || b->enc_inflight || b->tick_pending) { int rc = wait(b); if (rc) return rc; }
   if (b->host_records_valid) return CORDUM_OK;   // the wait fell back to the host encoder
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   host_records(b);

@@ -672,6 +672,37 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
   }
 }
 
+// ------------------------------------------------------------------ heartbeat exchange over peer memory
+// One process per GPU; every rank ingests the heartbeats of its own slice of worker slots into a buffer the other ranks
+// have mapped (CUDA IPC over NVLink / NVSwitch).  Per epoch: announce "my slice of epoch e is in place" in every peer's
+// flag array, then pull every slice - waiting, per source rank, for its announcement - into the local full table the
+// refresh kernels read.  No host round trip, no library collective: 128 KiB per peer at 8 GPUs, a few microseconds.
+// Reuse of a slice buffer (two alternate) is safe without acknowledgements: a rank announces epoch e+1 only after its
+// own gather of epoch e has finished (stream order), and nobody overwrites the buffer of epoch e before it has seen
+// everyone's announcement of e+1.
+__global__ void __launch_bounds__(256) peer_gather_kernel(PeerGather G) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t epoch = *G.epoch_ptr;
+  if (blockIdx.x == 0 && tid < G.world && tid != G.rank) {   // announce: the H2D of my slice finished before this kernel started
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(G.peer_flags[tid] + G.rank) = epoch;
+  }
+  const uint32_t per16 = G.per;   // records per rank
+  const uint32_t total = per16 * G.world;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {   // a CTA's 256 records lie in one rank's slice when per % 256 == 0; otherwise per thread
+    const uint32_t i = base + tid;
+    if (i >= total) break;
+    const uint32_t q = i / per16, k = i - q * per16;
+    if (q != G.rank) {
+      const volatile uint32_t* f = G.my_flags + q;
+      while (*f < epoch) { }   // spin: rank q's slice of this epoch is not announced yet
+      __threadfence_system();
+    }
+    const uint4 v = __ldcv(reinterpret_cast<const uint4*>(G.peer_slices[q]) + k);   // over NVLink for q != rank; never from a stale L1 line
+    reinterpret_cast<uint4*>(G.table)[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
 // An SM changes its L1 / shared-memory split only when it is idle, so kernels that ask for different splits cannot
 // share an SM: a refresh CTA (5 KiB of shared memory) would wait for every route / policy CTA (1-2 KiB, i.e. the
@@ -699,6 +730,16 @@ static cudaError_t configure_kernels() {
   return cudaSuccess;
 }
 
+cudaError_t launch_configure() { return configure_kernels(); }   // before a stream capture: attribute calls are not capturable
+
+cudaError_t launch_peer_gather(const PeerGather& G, cudaStream_t s) {
+  const uint32_t total = G.per * G.world;
+  uint32_t blocks = (total + 255) / 256;
+  if (blocks > 64) blocks = 64;   // a spinning CTA holds its SM slot: keep the kernel small next to policy / route
+  peer_gather_kernel<<<blocks, 256, 0, s>>>(G);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read) {
   if (T.n_pools == 0) return loads_read ? cudaEventRecord(loads_read, s) : cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
@@ -720,11 +761,14 @@ static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
   return blocks > cap ? cap : blocks;
 }
 
-cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
+// share > 0: the kernel runs next to others inside one graph (a scheduler tick): its persistent grid is capped at `share`
+// CTAs per SM so that all branches are resident from the start instead of queueing behind each other's CTAs.
+cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s, int share) {
   if (P.n_jobs == 0) return cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   static const int minb = []() { const char* v = getenv("CORDUM_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
-  const uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
+  uint32_t blocks = grid_for(P.n_jobs, sm_count, minb);
+  if (share > 0 && blocks > (uint32_t)(sm_count * share)) blocks = (uint32_t)(sm_count * share);
   if (minb <= 3) policy_kernel<3><<<blocks, 256, 0, s>>>(P);
   else if (minb == 4) policy_kernel<4><<<blocks, 256, 0, s>>>(P);
   else if (minb == 5) policy_kernel<5><<<blocks, 256, 0, s>>>(P);
@@ -732,11 +776,12 @@ cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s) {
+cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s, int share) {
   if (P.n_jobs == 0) return cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   static const int minb = []() { const char* v = getenv("CORDUM_ROUTE_MINB"); return v ? atoi(v) : 4; }();   // tuning knob
-  const uint32_t blocks = grid_for(P.n_jobs, sm_count, route_only ? 4 : minb);
+  uint32_t blocks = grid_for(P.n_jobs, sm_count, route_only ? 4 : minb);
+  if (share > 0 && blocks > (uint32_t)(sm_count * share)) blocks = (uint32_t)(sm_count * share);
   if (route_only) route_kernel<true><<<blocks, 256, 0, s>>>(P);
   else if (minb == 3) route_kernel<false, 3><<<blocks, 256, 0, s>>>(P);
   else if (minb == 5) route_kernel<false, 5><<<blocks, 256, 0, s>>>(P);

@@ -89,6 +89,11 @@ class Batch:
     def dispatch_resident_async(self, mode=wire.MODE_POLICY_AND_ROUTE, flush_l2=False):
         self.eng._ck(self.L.cordum_dispatch_resident_async(self.eng.h, self.h, mode | (wire.FLAG_FLUSH_L2 if flush_l2 else 0)))
 
+    def tick(self, slice_ptr: int, first_slot: int, n_slice: int):
+        """One scheduler tick (cordum_tick_async): heartbeat epoch + policy of this batch + route of the previous tick's batch,
+        one graph launch.  Results: wait() then fetch()."""
+        self.eng._ck(self.L.cordum_tick_async(self.eng.h, self.h, wire.MODE_POLICY_AND_ROUTE, C.c_void_p(slice_ptr), first_slot, n_slice))
+
     def fetch(self) -> np.ndarray:
         self.eng._ck(self.L.cordum_batch_fetch(self.h))
         return self.results()
@@ -241,6 +246,23 @@ class Engine:
         assert len(unique_id) == 128
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.L.cordum_exchange_init(self.h, buf, rank, world))
+
+    def tick_flush(self):
+        self._ck(self.L.cordum_tick_flush(self.h))
+
+    @property
+    def tick_stream(self) -> int:
+        return int(self.L.cordum_tick_stream(self.h) or 0)
+
+    def peer_export(self, rank: int, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.cordum_peer_export(self.h, rank, world, buf))
+        return buf.raw
+
+    def peer_import(self, handles: list):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.L.cordum_peer_import(self.h, buf))
 
     def ingest(self, slice_ptr: int, first_slot: int, n_slice: int):
         """One heartbeat epoch: this rank's slice of 16 B load records (host pointer, pinned for an asynchronous

@@ -233,6 +233,29 @@ int32_t cordum_exchange_unique_id(char id[CORDUM_EXCHANGE_ID_BYTES]);
 int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_BYTES], int32_t rank, int32_t world);
 int32_t cordum_workers_ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice);
 
+/* ---- scheduler ticks: one CUDA graph launch per tick.
+ * A tick = one heartbeat epoch + one batch, pipelined across ticks: it refreshes the worker tables from this rank's
+ * heartbeat slice (exchanged with the other ranks over peer memory when cordum_peer_import was called), evaluates the
+ * policy for `b`, and routes the batch of the PREVIOUS tick on the tables of the previous epoch - three independent
+ * branches of one captured graph, so a tick costs the longest of them and one launch instead of ~17 API calls.
+ * `b` must be encoded and resident (cordum_encode_device, or one cordum_dispatch); results stay on the device:
+ * cordum_batch_wait (which flushes the pipeline if `b` was the last batch) then cordum_batch_fetch.  The slice is copied
+ * into library-owned staging before the call returns.  All ranks of a peer exchange must tick the same number of times. */
+int32_t cordum_tick_async(cordum_engine* e, cordum_batch* b, uint32_t mode, const cordum_worker_load* slice,
+                          uint32_t first_slot, uint32_t n_slice);
+/* Routes the batch of the last tick (otherwise done by the next tick). */
+int32_t cordum_tick_flush(cordum_engine* e);
+/* The cudaStream_t ticks are launched on (for harnesses that bracket them with their own CUDA events). */
+void* cordum_tick_stream(cordum_engine* e);
+/* Peer-memory heartbeat exchange for ticks (replaces the NCCL all-gather of cordum_workers_ingest): each rank exports a
+ * CUDA IPC handle of its exchange buffer, ships the 64 bytes to every other rank by any transport, and imports the
+ * world x 64 bytes of all ranks (rank order).  Ranks then read each other's heartbeat slices over NVLink inside the
+ * tick's gather kernel, with flag words for the epoch barrier - no collective library, no host round trip.
+ * One process per GPU on one node; the worker registry (loaded before the export) must divide evenly. */
+#define CORDUM_PEER_HANDLE_BYTES 64
+int32_t cordum_peer_export(cordum_engine* e, int32_t rank, int32_t world, char handle[CORDUM_PEER_HANDLE_BYTES]);
+int32_t cordum_peer_import(cordum_engine* e, const char* handles /* world x CORDUM_PEER_HANDLE_BYTES */);
+
 /* Library-owned pinned SoA slabs for up to max_jobs jobs. */
 int32_t cordum_batch_alloc(cordum_engine* e, uint32_t max_jobs, cordum_batch** out);
 void cordum_batch_free(cordum_batch* b);
