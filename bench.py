@@ -359,6 +359,18 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
               "ranks_checked": world, "oracle_threads_per_rank": o_threads, "oracle_s": oracle_s}
     assert n_bad == 0, "sharded path differs from the oracle on %d of %d jobs" % (n_bad, n_checked)
 
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": 1000.0 * elapsed / args.steps,
+                              "wall_ms_per_step": 1000.0 * wall / args.steps, "step_mode": "tick" if use_ticks else "streams", "parity_check": parity,
+                              "gpu_launches": int(launches)}), flush=True)
+        for b in batches:
+            b.free()
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---------------------------------------------------------------- per-kernel durations for the roofline
     # Serialized launches (wait after every step) so the CUDA-event span of a kernel contains that kernel only;
     # in the throughput loop above policy_kernel overlaps the previous step's route_kernel / worker_chunk_kernel + worker_merge_kernel.
@@ -527,6 +539,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cordum_b200", choices=["cordum_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="diagnostic runs: skip the end-to-end and per-kernel sections")
     ap.add_argument("--parity-sample", type=int, default=0,
                     help="check only the first N jobs of each rank's shard against the oracle (0 = every job; for quick runs)")
     ap.add_argument("--step", default="auto", choices=["auto", "tick", "streams"],

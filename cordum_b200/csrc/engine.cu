@@ -715,7 +715,11 @@ int tick_setup(cordum_engine* e) {
   auto& T = e->tick;
   if (T.s[0]) return CORDUM_OK;
   for (auto& st : T.s) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
-  CK(cudaStreamCreateWithFlags(&T.sa, cudaStreamNonBlocking), "stream");
+  {   // the heartbeat branch is the head of the next tick's dependency chain: its kernels are captured at high priority
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range");
+    CK(cudaStreamCreateWithPriority(&T.sa, cudaStreamNonBlocking, hi), "stream");
+  }
   CK(cudaStreamCreateWithFlags(&T.sc, cudaStreamNonBlocking), "stream");
   for (cudaEvent_t* ev : {&T.ev_fork, &T.ev_a, &T.ev_c, &T.ev_join}) CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "event");
   for (int i = 0; i < 2; ++i) {

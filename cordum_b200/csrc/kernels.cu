@@ -83,9 +83,12 @@ __device__ __forceinline__ uint64_t worker_key(const DeviceTables& T, uint32_t p
   return ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
 }
 
+// One CTA of CORDUM_POOL_CHUNK (512) threads per chunk: thread i holds key i.  Bitonic network: exchanges inside a warp are
+// register shuffles (35 of the 45 stages of a 512-key sort), only partner distances >= 32 go through shared memory.
 template <uint32_t NT>
 __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
   constexpr uint32_t CH = CORDUM_POOL_CHUNK;
+  static_assert(NT == CH, "one thread per key");
   __shared__ uint64_t sk[CH];
   __shared__ uint32_t s_cnt, s_nok;
   const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -93,57 +96,59 @@ __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
   const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a;
   const uint32_t cs = c * CH, len = n - cs < CH ? n - cs : CH;   // an empty pool has one empty chunk
   const bool sortable = n <= CORDUM_POOL_SORT_MAX;
-  uint32_t n_pad = 1;
+  uint32_t n_pad = 32;   // at least a warp: the shuffle stages need full warps
   while (n_pad < len) n_pad <<= 1;
   if (tid == 0) { s_cnt = 0; s_nok = 0; }
-  for (uint32_t i = tid; i < n_pad; i += NT) {
-    uint64_t key = KEY_NONE;
-    if (i < len) { key = worker_key(T, a + cs + i); T.pos_key[a + cs + i] = key; }
-    sk[i] = key;
-  }
+  uint64_t key = KEY_NONE;
+  if (tid < len) { key = worker_key(T, a + cs + tid); T.pos_key[a + cs + tid] = key; }
   if (!sortable) return;   // chunk 0 of the pool reduces min / count in worker_merge_kernel
-  __syncthreads();
-  // bitonic sort, one compare-exchange per (thread, pair): pair q touches i = q with a zero inserted at bit log2(jj)
+  // bitonic sort of n_pad keys (ascending), thread i = position i; KEY_NONE pads sort to the end
   for (uint32_t k = 2; k <= n_pad; k <<= 1)
     for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-      for (uint32_t q = tid; q < (n_pad >> 1); q += NT) {
-        const uint32_t i = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), x = i | jj;
-        const uint64_t ki = sk[i], kx = sk[x];
-        if ((ki > kx) == ((i & k) == 0)) { sk[i] = kx; sk[x] = ki; }
-      }
-      __syncthreads();
+      uint64_t other;
+      if (jj >= 32) {
+        __syncthreads();
+        sk[tid] = key;
+        __syncthreads();
+        other = sk[tid ^ jj];
+      } else other = shfl64_xor(FULL, key, (int)jj);
+      const bool up = (tid & k) == 0, lower = (tid & jj) == 0;   // ascending block; this thread keeps the smaller one
+      const bool take_min = up == lower;
+      if (tid < n_pad) key = take_min ? (other < key ? other : key) : (other > key ? other : key);
     }
+  __syncthreads();
+  sk[tid] = key;
+  __syncthreads();
   const uint32_t words = (n + 31) >> 5, nbits = T.place_bits;
   uint32_t* bm = T.lbm + T.lbm_off[p];
   if (m > 1) {
     // hand the sorted chunk to worker_merge_kernel; clear what it accumulates into
-    for (uint32_t i = tid; i < len; i += NT) T.ckey[a + cs + i] = sk[i];
+    if (tid < len) T.ckey[a + cs + tid] = key;
     const uint64_t total = (uint64_t)nbits * words;
     for (uint64_t i = total * c / m + tid; i < total * (c + 1) / m; i += NT) bm[i] = 0;
     if (c == 0 && tid == 0) { T.pool_mincnt[p] = 0; T.pool_nok[p] = 0; }
     return;
   }
-  // single chunk: sorted view + label bitmaps; a warp takes 32 consecutive sorted workers (one bitmap word per label bit)
+  // single chunk: sorted view + label bitmaps; warp w = the 32 sorted workers of bitmap word w
   const uint64_t k0 = n ? sk[0] : KEY_NONE;
   const bool none = n == 0 || key_over(k0);
   uint32_t cnt = 0, ok = 0;
-  for (uint32_t w = tid >> 5; w < words; w += NT >> 5) {
-    const uint32_t i = w * 32 + lane;
-    uint64_t k = KEY_NONE, llo = 0, lhi = 0;
-    if (i < n) {
-      k = sk[i];
-      const uint32_t src = T.rank_pos[(uint32_t)(k & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
+  const uint32_t w = tid >> 5;
+  if (w < words) {
+    uint64_t llo = 0, lhi = 0;
+    if (tid < n) {
+      const uint32_t src = T.rank_pos[(uint32_t)(key & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
       llo = T.pos_label_lo[src]; lhi = T.pos_label_hi[src];
-      T.skey[a + i] = k; T.slab_lo[a + i] = llo; T.slab_hi[a + i] = lhi;
-      cnt += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
-      ok += key_over(k) ? 0u : 1u;
+      T.skey[a + tid] = key; T.slab_lo[a + tid] = llo; T.slab_hi[a + tid] = lhi;
+      cnt = (!none && (uint32_t)(key >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
+      ok = key_over(key) ? 0u : 1u;
     }
     for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {   // lane t keeps the word of label bit b0+t, then one strided store each
       uint32_t mine = 0;
       const uint32_t lim = nbits - b0 < 32 ? nbits - b0 : 32;
+      const uint32_t part = b0 < 64 ? (uint32_t)(llo >> b0) : (uint32_t)(lhi >> (b0 - 64));   // b0 is a multiple of 32
       for (uint32_t t = 0; t < lim; ++t) {
-        const uint32_t bit = b0 + t;
-        const unsigned bal = __ballot_sync(FULL, ((bit < 64 ? llo >> bit : lhi >> (bit - 64)) & 1ull) != 0);
+        const unsigned bal = __ballot_sync(FULL, (part >> t) & 1u);
         if (lane == t) mine = bal;
       }
       if (lane < lim) bm[(size_t)(b0 + lane) * words + w] = mine;
@@ -156,8 +161,8 @@ __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
   if (tid == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_mincnt[p] = s_cnt; T.pool_sorted[p] = 1; T.pool_nok[p] = s_nok; }
 }
 
-__global__ void __launch_bounds__(256) worker_merge_kernel(DeviceTables T) {
-  constexpr uint32_t CH = CORDUM_POOL_CHUNK, NT = 256;
+__global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
+  constexpr uint32_t CH = CORDUM_POOL_CHUNK, NT = 512;   // one thread per worker of the chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_cnt, s_nok;
   __shared__ uint64_t s_best;
@@ -716,7 +721,7 @@ static cudaError_t configure_kernels() {
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
   static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 72; }();   // tuning knob (policy_kernel: 16 KB of record tiles per CTA)
   const int pct = (kb * 100 + 227) / 228;
-  const void* fns[] = {(const void*)worker_chunk_kernel<128>, (const void*)worker_chunk_kernel<256>, (const void*)worker_merge_kernel,
+  const void* fns[] = {(const void*)worker_chunk_kernel<CORDUM_POOL_CHUNK>, (const void*)worker_merge_kernel, (const void*)peer_gather_kernel,
                        (const void*)policy_kernel<3>, (const void*)policy_kernel<4>, (const void*)policy_kernel<5>, (const void*)policy_kernel<6>,
                        (const void*)route_kernel<true>, (const void*)route_kernel<false>,
                        (const void*)route_kernel<false, 3>, (const void*)route_kernel<false, 5>};
@@ -743,13 +748,11 @@ cudaError_t launch_peer_gather(const PeerGather& G, cudaStream_t s) {
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read) {
   if (T.n_pools == 0) return loads_read ? cudaEventRecord(loads_read, s) : cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
-  static const int nt = []() { const char* v = getenv("CORDUM_CHUNK_NT"); return v ? atoi(v) : 256; }();   // tuning knob
-  if (nt == 256) worker_chunk_kernel<256><<<T.n_chunks, 256, 0, s>>>(T);
-  else worker_chunk_kernel<128><<<T.n_chunks, 128, 0, s>>>(T);
+  worker_chunk_kernel<CORDUM_POOL_CHUNK><<<T.n_chunks, CORDUM_POOL_CHUNK, 0, s>>>(T);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && loads_read) e = cudaEventRecord(loads_read, s);   // the load table is not read past this point
   if (e != cudaSuccess || T.n_merge == 0) return e;
-  worker_merge_kernel<<<T.n_merge, 256, T.merge_smem, s>>>(T);
+  worker_merge_kernel<<<T.n_merge, 512, T.merge_smem, s>>>(T);
   return cudaGetLastError();
 }
 
