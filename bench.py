@@ -192,7 +192,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # resident copies of the shard: enough distinct addresses that successive steps cannot hit L2
     shard_bytes = n_shard * (in_b + out_b)
     n_rot = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, shard_bytes))) + 1)
-    if args.step == "tick" or (args.step == "auto" and world > 1):
+    if args.step == "tick":
         n_rot = (n_rot + 5) // 6 * 6   # tick graphs are cached per (batch pair, tick phase of 6): a multiple of 6 keeps them to n_rot
     batches = [eng.batch(n_shard) for _ in range(n_rot)]
     t_enc0 = time.perf_counter()
@@ -214,8 +214,15 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         d["gpu_utilization"] = (rng.random(w1 - w0) * 100).astype(np.float32)
         delta_sets.append(torch.from_numpy(d.view(np.uint8).reshape(-1, 16).copy()).pin_memory())
     stream = torch.cuda.current_stream()
-    if args.exchange == "engine":
-        # the engine owns the exchange (cordum_exchange_init / cordum_workers_ingest): what a Go host would call
+    if world > 1 and args.exchange == "peer":
+        # peer-memory heartbeat exchange: every rank maps every other rank's slice buffer (CUDA IPC over NVLink); both
+        # cordum_workers_ingest and cordum_tick_async gather through it, no collective library on the path
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.peer_export(rank, world))
+        eng.peer_import(handles)
+        dist.barrier()
+    if args.exchange == "nccl":
+        # the engine's own NCCL communicator (cordum_exchange_init): all-gather of the slices in cordum_workers_ingest
         if world > 1:
             ok = 1
             try:
@@ -230,34 +237,28 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                 eng.exchange_init(box[0], rank, world)
             else:
                 args.exchange = "torch"
-    if args.exchange != "engine":
+    if args.exchange == "torch":
         send = torch.empty((w1 - w0, 16), dtype=torch.uint8, device="cuda")
         recv = [torch.empty((W, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
 
-    # auto: the multi-stream path at one GPU (measured faster there: 133 vs 153 us per 1M-job step), ticks when sharded
-    # (the per-step host cost of ~17 API calls + the NCCL all-gather is what bounded the 8-GPU step)
-    use_ticks = args.step == "tick" or (args.step == "auto" and world > 1)
+    use_ticks = args.step == "tick"
     if use_ticks and world > 1:
-        # peer-memory heartbeat exchange: every rank maps every other rank's slice buffer (CUDA IPC over NVLink)
-        handles = [None] * world
-        dist.all_gather_object(handles, eng.peer_export(rank, world))
-        eng.peer_import(handles)
-        dist.barrier()
+        assert args.exchange == "peer", "ticks gather over peer memory"
 
     def step(k: int, batch, resident: bool):
         if use_ticks and resident:
             # one graph launch: heartbeat epoch k (peer gather + refresh) || policy of this batch || route of the previous one
             batch.tick(delta_sets[k % n_delta_sets].data_ptr(), w0, w1 - w0)
             return
-        if args.exchange == "engine":
-            # heartbeat ingest (pinned host -> HBM) + NCCL all-gather of the per-rank slices + refresh
+        if args.exchange in ("peer", "nccl"):
+            # heartbeat ingest: pinned host -> HBM, gather of the per-rank slices (peer memory / NCCL), refresh
             eng.ingest(delta_sets[k % n_delta_sets].data_ptr(), w0, w1 - w0)
         else:
             send.copy_(delta_sets[k % n_delta_sets], non_blocking=True)
             buf = shard.gather_loads(send, out=recv[k % 2]) if world > 1 else send   # torch.distributed all-gather
             eng.set_loads_device(buf.data_ptr(), W, stream.cuda_stream)
         if resident:
-            batch.dispatch_resident_async(wire.MODE_POLICY_AND_ROUTE)
+            batch.dispatch_resident_async(wire.MODE_POLICY_AND_ROUTE | wire.FLAG_NO_TIMING)
         else:
             batch.dispatch_async(wire.MODE_POLICY_AND_ROUTE)
 
@@ -494,10 +495,11 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                        n_rot, n_rot * shard_bytes / 1e6),
                    "step": ("one CUDA-graph tick: [heartbeat-slice H2D + %sworker_chunk/merge] || policy_kernel(batch k) || route_kernel(batch k-1)" % (
                        "peer-memory gather over NVLink + " if world > 1 else "")) if use_ticks else (
-                       "heartbeat-slice H2D + %sworker_chunk/merge kernels (overlapped with policy_kernel) + route_kernel" % ("NCCL all-gather + " if world > 1 else "")),
+                       "one graph launch [heartbeat-slice H2D + %sworker_chunk/merge] (overlapped with policy_kernel) + route_kernel" % (
+                           ("peer-memory gather + " if args.exchange == "peer" else "all-gather + ") if world > 1 else "")),
                    "step_mode": args.step,
                    "layout": "jobs as topic-sorted 64 B + 32 B records (host encoder), bulk-async tile loads",
-                   "exchange": ("peer memory (CUDA IPC, NVLink)" if world > 1 else "none") if use_ticks else args.exchange},
+                   "exchange": ("peer memory (CUDA IPC over NVLink, gather kernel inside the ingest graph)" if args.exchange == "peer" else args.exchange) if world > 1 else "none"},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(env_bytes + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
@@ -542,12 +544,12 @@ def main():
     ap.add_argument("--value-only", action="store_true", help="diagnostic runs: skip the end-to-end and per-kernel sections")
     ap.add_argument("--parity-sample", type=int, default=0,
                     help="check only the first N jobs of each rank's shard against the oracle (0 = every job; for quick runs)")
-    ap.add_argument("--step", default="auto", choices=["auto", "tick", "streams"],
-                    help="device-resident step: one CUDA-graph scheduler tick (peer-memory heartbeat exchange at N > 1), or the "
-                         "multi-stream path (cordum_workers_ingest + cordum_dispatch_resident_async, NCCL all-gather at N > 1)")
-    ap.add_argument("--exchange", default="engine", choices=["engine", "torch"],
-                    help="heartbeat exchange: the engine's own NCCL communicator (cordum_workers_ingest) or "
-                         "torch.distributed all_gather + cordum_workers_set_loads_device")
+    ap.add_argument("--step", default="streams", choices=["tick", "streams"],
+                    help="device-resident step: the multi-stream path (cordum_workers_ingest as one graph launch + "
+                         "cordum_dispatch_resident_async; measured faster at 1-8 GPUs) or one CUDA-graph scheduler tick per step")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"],
+                    help="heartbeat exchange at N > 1: peer memory over NVLink (CUDA IPC, gather kernel inside the ingest graph), "
+                         "the engine's NCCL communicator, or torch.distributed all_gather + cordum_workers_set_loads_device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

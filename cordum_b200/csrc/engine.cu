@@ -91,6 +91,10 @@ struct cordum_engine {
   uint64_t v_dict = ~0ull;
   std::vector<cordum_envelopes*> env_sets;   // pinned envelope staging sets handed out by cordum_envelopes_alloc
   uint64_t tables_gen = 0;       // bumps whenever a device table pointer or scalar may have changed (captured graphs bake them in)
+  // ---- cordum_workers_ingest as one graph launch (world = 1, or the peer exchange): H2D -> [peer gather] -> chunk -> merge
+  Load16* ing_stage[2] = {nullptr, nullptr};   // pinned staging of the caller's slice (+ the epoch word behind it)
+  size_t ing_cap = 0;
+  std::map<std::tuple<int, int, uint64_t>, cudaGraphExec_t> ing_graphs;   // (target set, buffer parity, tables generation)
   // ---- scheduler ticks (cordum_tick_async): one CUDA graph launch per tick
   struct Tick {
     cudaStream_t s[2] = {nullptr, nullptr};                // tick k is launched on s[k & 1]: consecutive ticks overlap
@@ -147,7 +151,7 @@ struct cordum_batch {
   DevBuf d_env, d_work;          // envelope arrays on the device; tid / ten / key / slot_of / hist / flag
   uint32_t* h_fallback = nullptr;   // pinned: 1 = the device encoder left something to the host
   uint32_t last_mode = 0;
-  bool last_copy_out = false;
+  bool last_copy_out = false, timed = true;
   bool tick_pending = false;     // dispatched through cordum_tick_async: results are on the device once the tick streams have drained
   uint64_t tick_no = 0;          // the tick it was handed in with (its route runs in tick_no + 1)
   cordum_decision* h_out = nullptr;   // pinned
@@ -381,13 +385,15 @@ int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer
 int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool copy_out) {
   if (!e || !b) { g_err = "null handle"; return CORDUM_E_INVALID; }
   const bool flush_l2 = mode & CORDUM_FLAG_FLUSH_L2;
+  const bool timed = !(mode & CORDUM_FLAG_NO_TIMING);   // per-kernel timing events cost two API calls per dispatch
   mode &= 0xFFu;
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
   if (mode < CORDUM_MODE_POLICY_ONLY || mode > CORDUM_MODE_ROUTE_ONLY) { g_err = "bad mode"; return CORDUM_E_INVALID; }
   if (!b->encoded) { g_err = "batch has not been encoded"; return CORDUM_E_STATE; }
   if (b->device_encoded) copy_in = false;   // the records were produced on the device
   if (!copy_in && !b->resident) { g_err = "batch columns are not resident on the device"; return CORDUM_E_STATE; }
-  b->last_mode = mode | (flush_l2 ? CORDUM_FLAG_FLUSH_L2 : 0u);
+  b->last_mode = mode | (flush_l2 ? CORDUM_FLAG_FLUSH_L2 : 0u) | (timed ? 0u : CORDUM_FLAG_NO_TIMING);
+  b->timed = timed;
   b->last_copy_out = copy_out;
   if (b->pending) { CK(cudaStreamSynchronize(b->stream), "wait previous"); b->pending = false; b->enc_inflight = false; }
   CK(cudaSetDevice(e->device), "cudaSetDevice");
@@ -421,7 +427,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     CK(cudaMemcpyAsync(b->d_cols, b->h_cols, slab_bytes(b->n), cudaMemcpyHostToDevice, s), "H2D columns");
     b->resident = true;
   }
-  CK(cudaEventRecord(b->ev1, s), "event");
+  if (timed) CK(cudaEventRecord(b->ev1, s), "event");
   device_records(b, P.recs);
   P.out = b->d_out;
   P.n_jobs = b->n;
@@ -436,7 +442,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
     CK(launch_policy(P, e->sm_count, s), "policy_kernel");
     if (b->n) e->launches++;
   }
-  CK(cudaEventRecord(b->evm, s), "event");
+  if (timed) CK(cudaEventRecord(b->evm, s), "event");
   if (mode != CORDUM_MODE_POLICY_ONLY) {
     CK(cudaStreamWaitEvent(s, ev_ready, 0), "wait worker tables");
     CK(launch_route(P, mode == CORDUM_MODE_ROUTE_ONLY, e->sm_count, s), "route_kernel");
@@ -484,6 +490,7 @@ int wait(cordum_batch* b) {
     b->pending = false;
   }
   if (!dispatched) return CORDUM_OK;
+  if (!b->timed) { b->total_ms = b->kernel_ms = b->policy_ms = b->route_ms = 0; return CORDUM_OK; }
   CK(cudaEventElapsedTime(&b->total_ms, b->timed_in ? b->ev0 : b->ev1, b->timed_out ? b->ev3 : b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->kernel_ms, b->ev1, b->ev2), "elapsed");
   CK(cudaEventElapsedTime(&b->policy_ms, b->ev1, b->evm), "elapsed");
@@ -577,6 +584,75 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
   const int g = (int)(e->xepoch & 1);
   e->xepoch++;
   const size_t bytes = (size_t)W * sizeof(Load16), slice_bytes = (size_t)per * sizeof(Load16);
+  const bool use_peers = e->peers.ready && e->peers.world > 1 && e->peers.world == e->xworld && e->peers.per == per;
+  if (e->xworld == 1 || use_peers) {
+    // One graph launch: H2D of the slice -> [gather of all ranks' slices over peer memory] -> worker_chunk -> worker_merge.
+    if (e->gather[g].cap < bytes) {
+      CK(cudaDeviceSynchronize(), "sync before gather buffer allocation");
+      CK(e->gather[g].reserve(bytes), "alloc gather buffer");
+      e->tables_gen++;
+    }
+    if (e->ing_cap < slice_bytes) {
+      CK(cudaDeviceSynchronize(), "sync before staging growth");
+      for (auto& p : e->ing_stage) { if (p) cudaFreeHost(p); p = nullptr; }
+      for (auto& p : e->ing_stage) CK(cudaHostAlloc((void**)&p, slice_bytes + 64, cudaHostAllocDefault), "pinned heartbeat staging");
+      e->ing_cap = slice_bytes;
+      for (auto& kv : e->ing_graphs) cudaGraphExecDestroy(kv.second);
+      e->ing_graphs.clear();
+    }
+    CK(cudaEventSynchronize(e->gather_free[g]), "wait staging");   // the epoch two back has consumed this staging / table buffer
+    std::memcpy(e->ing_stage[g], slice, slice_bytes);
+    *reinterpret_cast<uint32_t*>((uint8_t*)e->ing_stage[g] + slice_bytes) = (uint32_t)e->xepoch;   // the epoch, behind the slice
+    const int target = (e->cur + 1) % kSets;
+    auto& D = e->ds[target];
+    for (cordum_batch* b : e->batches)   // route kernels that still read the target set
+      if (b->launched && b->table_set == target) { CK(cudaStreamWaitEvent(e->s_tables, b->ev2, 0), "wait route"); b->launched = false; }
+    const auto key = std::make_tuple(target, g, e->tables_gen);
+    cudaGraphExec_t ge = nullptr;
+    auto it = e->ing_graphs.find(key);
+    if (it != e->ing_graphs.end()) ge = it->second;
+    else {
+      if (e->ing_graphs.size() > 32) { for (auto& kv : e->ing_graphs) cudaGraphExecDestroy(kv.second); e->ing_graphs.clear(); }
+      CK(launch_configure(), "kernel attributes");
+      cudaStream_t S = e->s_tables;
+      CK(cudaStreamBeginCapture(S, cudaStreamCaptureModeThreadLocal), "begin capture");
+      cudaError_t ce = cudaSuccess;
+      uint8_t* table = (uint8_t*)e->gather[g].p;
+      DeviceTables tv = view(e, target);
+      tv.loads = (const Load16*)table;
+      if (use_peers) {
+        const size_t stride = slice_bytes + 16;
+        uint8_t* mine = e->peers.mine + 256 + (size_t)g * stride;
+        ce = cudaMemcpyAsync(mine, e->ing_stage[g], stride, cudaMemcpyHostToDevice, S);
+        PeerGather G{};
+        G.rank = (uint32_t)e->peers.rank; G.world = (uint32_t)e->peers.world; G.per = per;
+        for (int q = 0; q < e->peers.world; ++q) {
+          G.peer_slices[q] = (const Load16*)(e->peers.base[q] + 256 + (size_t)g * stride);
+          G.peer_flags[q] = (uint32_t*)e->peers.base[q];
+        }
+        G.my_flags = (const uint32_t*)e->peers.mine;
+        G.epoch_ptr = (const uint32_t*)(mine + slice_bytes);
+        G.table = (Load16*)table;
+        if (ce == cudaSuccess) ce = launch_peer_gather(G, S);
+      } else ce = cudaMemcpyAsync(table, e->ing_stage[g], slice_bytes, cudaMemcpyHostToDevice, S);
+      if (ce == cudaSuccess) ce = launch_worker_pools(tv, S, nullptr);
+      cudaGraph_t gr = nullptr;
+      cudaError_t ee = cudaStreamEndCapture(S, &gr);
+      if (ce != cudaSuccess || ee != cudaSuccess) { if (gr) cudaGraphDestroy(gr); return fail(e, ce != cudaSuccess ? ce : ee, "capture of the ingest graph"); }
+      cudaError_t ie = cudaGraphInstantiate(&ge, gr, 0);
+      cudaGraphDestroy(gr);
+      if (ie != cudaSuccess) return fail(e, ie, "graph instantiate");
+      e->ing_graphs[key] = ge;
+    }
+    CK(cudaGraphLaunch(ge, e->s_tables), "graph launch");
+    CK(cudaEventRecord(e->gather_free[g], e->s_tables), "event record");
+    CK(cudaEventRecord(D.ready, e->s_tables), "event record");
+    e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (use_peers ? 1 : 0);
+    e->cur = target;
+    e->pools_dirty = false;
+    e->host_loads = false;
+    return CORDUM_OK;
+  }
   if (e->gather[g].cap < bytes) {   // first use / registry grew: nothing may still read the old buffer
     CK(cudaDeviceSynchronize(), "sync before gather buffer allocation");
     CK(e->gather[g].reserve(bytes), "alloc gather buffer");
@@ -773,7 +849,7 @@ int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* sl
     T.graphs.clear();
   }
   if (bytes) std::memcpy(T.h_slice[parity], slice, bytes);
-  *reinterpret_cast<uint32_t*>((uint8_t*)T.h_slice[parity] + bytes) = (uint32_t)(T.n + 1);   // the epoch, behind the slice
+  *reinterpret_cast<uint32_t*>((uint8_t*)T.h_slice[parity] + bytes) = (uint32_t)(++e->xepoch);   // the epoch (shared with cordum_workers_ingest), behind the slice
   if (e->gather[parity].cap < (size_t)W * sizeof(Load16)) {
     CK(cudaDeviceSynchronize(), "sync before gather buffer allocation");
     CK(e->gather[parity].reserve((size_t)W * sizeof(Load16)), "alloc gather buffer");
@@ -891,6 +967,8 @@ void cordum_engine_destroy(cordum_engine* e) {
     { std::lock_guard<std::mutex> g(e->mu); live.swap(e->batches); }
     for (cordum_batch* b : live) batch_release(b);
   }
+  for (auto& kv : e->ing_graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& p : e->ing_stage) if (p) cudaFreeHost(p);
   for (auto& kv : e->tick.graphs) cudaGraphExecDestroy(kv.second);
   for (cudaStream_t st : {e->tick.s[0], e->tick.s[1], e->tick.sa, e->tick.sc}) if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : {e->tick.ev_fork, e->tick.ev_a, e->tick.ev_c, e->tick.ev_join, e->tick.done[0], e->tick.done[1], e->tick.refreshed[0], e->tick.refreshed[1]}) if (ev) cudaEventDestroy(ev);
@@ -1054,6 +1132,7 @@ int32_t cordum_peer_import(cordum_engine* e, const char* handles) {
     P.base[q] = (uint8_t*)p;
   }
   P.ready = true;
+  if (!e->nccl_comm) { e->xrank = P.rank; e->xworld = P.world; }   // cordum_workers_ingest uses the peer exchange too
   e->tables_gen++;
   return CORDUM_OK;
 }

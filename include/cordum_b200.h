@@ -165,6 +165,9 @@ typedef struct cordum_decision {
 /* may be OR-ed into the mode of the *_resident calls (benchmarks): write a 256 MiB scratch buffer
  * first so the batch's columns are not served from L2 */
 #define CORDUM_FLAG_FLUSH_L2 0x100
+/* may be OR-ed into any dispatch mode: do not record the per-kernel timing events (cordum_batch_timing / _kernel_times
+ * then report 0): two API calls less per dispatch, for callers that issue many small dispatches */
+#define CORDUM_FLAG_NO_TIMING 0x200
 
 /* ------------------------------------------------------------- engine */
 typedef struct cordum_engine cordum_engine;
