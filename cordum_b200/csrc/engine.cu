@@ -116,7 +116,7 @@ struct cordum_engine {
   struct Peers {
     int rank = 0, world = 1;
     uint32_t per = 0;                                      // worker slots per rank
-    uint8_t* mine = nullptr;                               // [flags 256 B][slice parity 0][slice parity 1]
+    uint8_t* mine = nullptr;                               // [flags 128 B | push counter | epoch words][full table parity 0][full table parity 1]
     size_t bytes = 0;
     uint8_t* base[CORDUM_MAX_PEERS] = {};                  // every rank's buffer as mapped here (mine included)
     bool ready = false;
@@ -325,6 +325,23 @@ int sync_dicts(cordum_engine* e) {
 }
 
 // The kernels' view of the tables with the derived pointers of one set.
+// Parameters of the peer push for table parity p; returns this rank's full table of that parity (inside its IPC buffer).
+uint8_t* peer_push_params(const cordum_engine* e, int p, PeerPush& G) {
+  const auto& P = e->peers;
+  const size_t tbytes = (size_t)P.per * (size_t)P.world * sizeof(Load16), soff = (size_t)P.rank * P.per * sizeof(Load16);
+  G.rank = (uint32_t)P.rank; G.world = (uint32_t)P.world; G.per = P.per;
+  for (int q = 0; q < P.world; ++q) {
+    G.peer_slices[q] = (Load16*)(P.base[q] + 256 + (size_t)p * tbytes + soff);
+    G.peer_flags[q] = (uint32_t*)P.base[q];
+  }
+  G.my_flags = (const uint32_t*)P.mine;
+  G.done_ctr = (uint32_t*)(P.mine + 128);
+  G.epoch_ptr = (const uint32_t*)(P.mine + 160 + (size_t)p * 16);
+  uint8_t* table = P.mine + 256 + (size_t)p * tbytes;
+  G.my_slice = (const Load16*)(table + soff);
+  return table;
+}
+
 // Ticks keep their own order on their own stream; a plain dispatch / ingest after ticks first lets that stream drain.
 int tick_flush_locked(cordum_engine* e);
 int leave_tick_mode(cordum_engine* e) {
@@ -621,19 +638,12 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
       DeviceTables tv = view(e, target);
       tv.loads = (const Load16*)table;
       if (use_peers) {
-        const size_t stride = slice_bytes + 16;
-        uint8_t* mine = e->peers.mine + 256 + (size_t)g * stride;
-        ce = cudaMemcpyAsync(mine, e->ing_stage[g], stride, cudaMemcpyHostToDevice, S);
-        PeerGather G{};
-        G.rank = (uint32_t)e->peers.rank; G.world = (uint32_t)e->peers.world; G.per = per;
-        for (int q = 0; q < e->peers.world; ++q) {
-          G.peer_slices[q] = (const Load16*)(e->peers.base[q] + 256 + (size_t)g * stride);
-          G.peer_flags[q] = (uint32_t*)e->peers.base[q];
-        }
-        G.my_flags = (const uint32_t*)e->peers.mine;
-        G.epoch_ptr = (const uint32_t*)(mine + slice_bytes);
-        G.table = (Load16*)table;
-        if (ce == cudaSuccess) ce = launch_peer_gather(G, S);
+        PeerPush G{};
+        table = peer_push_params(e, g, G);
+        tv.loads = (const Load16*)table;
+        ce = cudaMemcpyAsync((void*)G.my_slice, e->ing_stage[g], slice_bytes, cudaMemcpyHostToDevice, S);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync((void*)G.epoch_ptr, (const uint8_t*)e->ing_stage[g] + slice_bytes, 4, cudaMemcpyHostToDevice, S);
+        if (ce == cudaSuccess) ce = launch_peer_push(G, S);
       } else ce = cudaMemcpyAsync(table, e->ing_stage[g], slice_bytes, cudaMemcpyHostToDevice, S);
       if (ce == cudaSuccess) ce = launch_worker_pools(tv, S, nullptr);
       cudaGraph_t gr = nullptr;
@@ -724,22 +734,14 @@ int tick_graph(cordum_engine* e, cordum_batch* bn, cordum_batch* bp, int phase, 
     DeviceTables tv = view(e, set_new);
     tv.loads = (const Load16*)table;
     if (e->peers.ready && e->peers.world > 1) {
-      const uint32_t per = e->peers.per;
-      const size_t stride = (size_t)per * sizeof(Load16) + 16;   // a slice buffer: the records, then the epoch word
-      uint8_t* mine = e->peers.mine + 256 + (size_t)parity * stride;
-      // the staging buffer carries the epoch number behind the slice: one copy brings both, and the gather kernel -
-      // whose parameters the graph bakes in - reads the epoch it announces and waits for from there
-      CKC(cudaMemcpyAsync(mine, T.h_slice[parity], stride, cudaMemcpyHostToDevice, T.sa), "H2D heartbeat slice");
-      PeerGather G{};
-      G.rank = (uint32_t)e->peers.rank; G.world = (uint32_t)e->peers.world; G.per = per;
-      for (int q = 0; q < e->peers.world; ++q) {
-        G.peer_slices[q] = (const Load16*)(e->peers.base[q] + 256 + (size_t)parity * stride);
-        G.peer_flags[q] = (uint32_t*)e->peers.base[q];
-      }
-      G.my_flags = (const uint32_t*)e->peers.mine;
-      G.epoch_ptr = (const uint32_t*)(mine + (size_t)per * sizeof(Load16));
-      G.table = (Load16*)table;
-      CKC(launch_peer_gather(G, T.sa), "peer gather");
+      // the staging buffer carries the epoch number behind the slice; the push kernel - whose parameters the graph bakes
+      // in - reads the epoch it announces and waits for from device memory
+      PeerPush G{};
+      table = peer_push_params(e, parity, G);
+      tv.loads = (const Load16*)table;
+      CKC(cudaMemcpyAsync((void*)G.my_slice, T.h_slice[parity], (size_t)e->peers.per * sizeof(Load16), cudaMemcpyHostToDevice, T.sa), "H2D heartbeat slice");
+      CKC(cudaMemcpyAsync((void*)G.epoch_ptr, (const uint8_t*)T.h_slice[parity] + (size_t)e->peers.per * sizeof(Load16), 4, cudaMemcpyHostToDevice, T.sa), "H2D epoch");
+      CKC(launch_peer_push(G, T.sa), "peer push");
     } else {
       CKC(cudaMemcpyAsync(table, T.h_slice[parity], (size_t)W * sizeof(Load16), cudaMemcpyHostToDevice, T.sa), "H2D heartbeats");
     }
@@ -1105,7 +1107,7 @@ int32_t cordum_peer_export(cordum_engine* e, int32_t rank, int32_t world, char h
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   auto& P = e->peers;
   P.rank = rank; P.world = world; P.per = W / (uint32_t)world;
-  P.bytes = 256 + 2 * ((size_t)P.per * sizeof(Load16) + 16);
+  P.bytes = 256 + 2 * (size_t)W * sizeof(Load16);
   CK(cudaMalloc((void**)&P.mine, P.bytes), "peer exchange buffer");
   CK(cudaMemset(P.mine, 0, P.bytes), "peer exchange buffer");
   cudaIpcMemHandle_t h;

@@ -678,34 +678,41 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
 }
 
 // ------------------------------------------------------------------ heartbeat exchange over peer memory
-// One process per GPU; every rank ingests the heartbeats of its own slice of worker slots into a buffer the other ranks
-// have mapped (CUDA IPC over NVLink / NVSwitch).  Per epoch: announce "my slice of epoch e is in place" in every peer's
-// flag array, then pull every slice - waiting, per source rank, for its announcement - into the local full table the
-// refresh kernels read.  No host round trip, no library collective: 128 KiB per peer at 8 GPUs, a few microseconds.
-// Reuse of a slice buffer (two alternate) is safe without acknowledgements: a rank announces epoch e+1 only after its
-// own gather of epoch e has finished (stream order), and nobody overwrites the buffer of epoch e before it has seen
-// everyone's announcement of e+1.
-__global__ void __launch_bounds__(256) peer_gather_kernel(PeerGather G) {
+// One process per GPU; every rank owns a full slot-ordered load table (two alternate) that the other ranks have mapped
+// (CUDA IPC over NVLink / NVSwitch).  Per epoch a rank copies its own slice from the host into its table, PUSHES the slice
+// into every peer's table with plain peer stores (posted writes: no round trip per access), fences, and raises its epoch
+// in every peer's flag array; one CTA then waits until every peer's flag shows the epoch.  After the kernel the local
+// table is complete and the refresh kernels read it where it lies: no host round trip, no library collective, no copy.
+// Reuse of a table (two alternate) is safe without acknowledgements: a rank announces epoch e+1 only after its own
+// refresh of epoch e has consumed its table (stream order), and nobody writes into a peer's table of epoch e+2 before
+// it has seen that peer's announcement of e+1.
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerPush G) {
   const uint32_t tid = threadIdx.x;
   const uint32_t epoch = *G.epoch_ptr;
-  if (blockIdx.x == 0 && tid < G.world && tid != G.rank) {   // announce: the H2D of my slice finished before this kernel started
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(G.peer_flags[tid] + G.rank) = epoch;
+  __shared__ uint32_t s_last;
+  // ---- push: CTA b serves peer (b mod (world-1)), the CTAs of one peer split the slice
+  const uint32_t n_peers = G.world - 1, ctas_per_peer = gridDim.x / n_peers;
+  if (blockIdx.x < ctas_per_peer * n_peers) {
+    const uint32_t pi = blockIdx.x % n_peers, part = blockIdx.x / n_peers;
+    const uint32_t q = pi < G.rank ? pi : pi + 1;
+    const uint4* src = reinterpret_cast<const uint4*>(G.my_slice);
+    uint4* dst = reinterpret_cast<uint4*>(G.peer_slices[q]);
+    for (uint32_t i = part * blockDim.x + tid; i < G.per; i += ctas_per_peer * blockDim.x) dst[i] = src[i];
   }
-  const uint32_t per16 = G.per;   // records per rank
-  const uint32_t total = per16 * G.world;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {   // a CTA's 256 records lie in one rank's slice when per % 256 == 0; otherwise per thread
-    const uint32_t i = base + tid;
-    if (i >= total) break;
-    const uint32_t q = i / per16, k = i - q * per16;
-    if (q != G.rank) {
-      const volatile uint32_t* f = G.my_flags + q;
-      while (*f < epoch) { }   // spin: rank q's slice of this epoch is not announced yet
-      __threadfence_system();
-    }
-    const uint4 v = __ldcv(reinterpret_cast<const uint4*>(G.peer_slices[q]) + k);   // over NVLink for q != rank; never from a stale L1 line
-    reinterpret_cast<uint4*>(G.table)[i] = v;
+  __threadfence_system();   // this thread's peer stores are visible system-wide before anything below
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(G.done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;   // the last CTA to finish its part announces
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) *G.done_ctr = 0;   // for the next launch (stream order)
+  __threadfence_system();
+  if (tid < G.world && tid != G.rank) *reinterpret_cast<volatile uint32_t*>(G.peer_flags[tid] + G.rank) = epoch;
+  // ---- wait: every peer's slice of this epoch has landed in my table
+  if (tid < G.world && tid != G.rank) {
+    const volatile uint32_t* f = G.my_flags + tid;
+    while (*f < epoch) __nanosleep(200);
   }
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------ launchers (C++ linkage, called by engine.cu)
@@ -721,7 +728,7 @@ static cudaError_t configure_kernels() {
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
   static const int kb = []() { const char* v = getenv("CORDUM_SMEM_KB"); return v ? atoi(v) : 72; }();   // tuning knob (policy_kernel: 16 KB of record tiles per CTA)
   const int pct = (kb * 100 + 227) / 228;
-  const void* fns[] = {(const void*)worker_chunk_kernel<CORDUM_POOL_CHUNK>, (const void*)worker_merge_kernel, (const void*)peer_gather_kernel,
+  const void* fns[] = {(const void*)worker_chunk_kernel<CORDUM_POOL_CHUNK>, (const void*)worker_merge_kernel, (const void*)peer_push_kernel,
                        (const void*)policy_kernel<3>, (const void*)policy_kernel<4>, (const void*)policy_kernel<5>, (const void*)policy_kernel<6>,
                        (const void*)route_kernel<true>, (const void*)route_kernel<false>,
                        (const void*)route_kernel<false, 3>, (const void*)route_kernel<false, 5>};
@@ -737,11 +744,12 @@ static cudaError_t configure_kernels() {
 
 cudaError_t launch_configure() { return configure_kernels(); }   // before a stream capture: attribute calls are not capturable
 
-cudaError_t launch_peer_gather(const PeerGather& G, cudaStream_t s) {
-  const uint32_t total = G.per * G.world;
-  uint32_t blocks = (total + 255) / 256;
-  if (blocks > 64) blocks = 64;   // a spinning CTA holds its SM slot: keep the kernel small next to policy / route
-  peer_gather_kernel<<<blocks, 256, 0, s>>>(G);
+cudaError_t launch_peer_push(const PeerPush& G, cudaStream_t s) {
+  if (G.world < 2) return cudaSuccess;
+  const uint32_t n_peers = G.world - 1;
+  uint32_t per_peer = (G.per + 2047) / 2048;   // ~8 records per thread
+  if (per_peer > 8) per_peer = 8;
+  peer_push_kernel<<<n_peers * per_peer, 256, 0, s>>>(G);
   return cudaGetLastError();
 }
 

@@ -15,17 +15,18 @@ struct KParams {
   uint32_t honor_approved;   // POLICY_AND_ROUTE: jobs flagged JF_APPROVED bypass the policy (engine.go:484-522)
 };
 
-// peer-memory heartbeat gather (kernels.cu peer_gather_kernel)
+// peer-memory heartbeat exchange (kernels.cu peer_push_kernel)
 #define CORDUM_MAX_PEERS 16
-struct PeerGather {
+struct PeerPush {
   uint32_t rank, world, per;                 // per = worker slots per rank
   const uint32_t* epoch_ptr;                 // device: the epoch this launch announces and waits for (copied in with the slice)
-  const Load16* peer_slices[CORDUM_MAX_PEERS];   // every rank's slice buffer of this epoch's parity (mine included), device / peer pointers
+  const Load16* my_slice;                    // local: this rank's slice inside its own table of this epoch's parity
+  Load16* peer_slices[CORDUM_MAX_PEERS];     // where this rank's slice goes in every peer's table of that parity
   uint32_t* peer_flags[CORDUM_MAX_PEERS];    // every rank's flag array [CORDUM_MAX_PEERS]: peer_flags[q][r] = last epoch rank r announced to q
   const uint32_t* my_flags;                  // = peer_flags[rank]
-  Load16* table;                             // local: the full slot-ordered load table
+  uint32_t* done_ctr;                        // local scratch: CTAs that have finished pushing
 };
-cudaError_t launch_peer_gather(const PeerGather& G, cudaStream_t s);
+cudaError_t launch_peer_push(const PeerPush& G, cudaStream_t s);
 cudaError_t launch_configure();
 
 // loads_read (optional) is recorded once T.loads has been consumed (between the chunk and the merge kernel)

@@ -22,10 +22,22 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle.h")] + [
         os.path.join(ROOT, "include", "cordum_b200.h"), os.path.join(ROOT, "common", "mini_json.hpp"),
         os.path.join(ROOT, "common", "go_unicode_tables.h")]
-    stale = force or not os.path.exists(LIB_PATH) or any(
-        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    if stale:
-        subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+    import fcntl
+
+    def stale():
+        return force or not os.path.exists(LIB_PATH) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+
+    if stale():
+        # several processes (one per GPU under torchrun, pytest-xdist workers) may get here together: one builds, the
+        # others wait for the lock and then find the library fresh
+        with open(os.path.join(ORACLE_DIR, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
