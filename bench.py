@@ -499,7 +499,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                            ("peer-memory gather + " if args.exchange == "peer" else "all-gather + ") if world > 1 else "")),
                    "step_mode": args.step,
                    "layout": "jobs as topic-sorted 64 B + 32 B records (host encoder), bulk-async tile loads",
-                   "exchange": ("peer memory (CUDA IPC over NVLink, gather kernel inside the ingest graph)" if args.exchange == "peer" else args.exchange) if world > 1 else "none"},
+                   "exchange": ("peer memory (CUDA IPC over NVLink, push kernel inside the ingest graph)" if args.exchange == "peer" else
+                                ("engine-owned NCCL all-gather" if args.exchange == "nccl" else args.exchange)) if world > 1 else "none"},
         "clocks": clocks,
         "e2e": {"value": J * e2e_steps / e2e_elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": int(env_bytes + (w1 - w0) * 16), "d2h_bytes_per_step": int(n_shard * out_b),
@@ -547,9 +548,10 @@ def main():
     ap.add_argument("--step", default="streams", choices=["tick", "streams"],
                     help="device-resident step: the multi-stream path (cordum_workers_ingest as one graph launch + "
                          "cordum_dispatch_resident_async; measured faster at 1-8 GPUs) or one CUDA-graph scheduler tick per step")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"],
-                    help="heartbeat exchange at N > 1: peer memory over NVLink (CUDA IPC, gather kernel inside the ingest graph), "
-                         "the engine's NCCL communicator, or torch.distributed all_gather + cordum_workers_set_loads_device")
+    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl", "torch"],
+                    help="heartbeat exchange at N > 1: the engine's NCCL communicator (all-gather of the slices; measured fastest at "
+                         "2-8 GPUs), peer memory over NVLink (CUDA IPC, push kernel inside the ingest graph), or torch.distributed "
+                         "all_gather + cordum_workers_set_loads_device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
