@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libcordum_b200.so")
 # every symbol include/cordum_b200.h declares (the CPU test-suite checks they are all exported)
 API = [
     "cordum_last_error", "cordum_version", "cordum_engine_create", "cordum_engine_destroy", "cordum_policy_load",
-    "cordum_policy_snapshots", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
+    "cordum_policy_snapshots", "cordum_policy_snapshot", "cordum_routing_load", "cordum_workers_load", "cordum_workers_update",
     "cordum_workers_set_loads_device", "cordum_exchange_unique_id", "cordum_exchange_init", "cordum_workers_ingest",
     "cordum_tick_async", "cordum_tick_flush", "cordum_tick_stream", "cordum_peer_export", "cordum_peer_import",
     "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_encode_device", "cordum_envelopes_alloc",
@@ -24,7 +24,8 @@ API = [
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
-    "cordum_launch_count", "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
+    "cordum_launch_count", "cordum_frontend_create", "cordum_frontend_destroy", "cordum_frontend_submit", "cordum_frontend_stats",
+    "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
     "cordum_test_parse_effective", "cordum_test_canon",
 ]
 
@@ -48,6 +49,8 @@ def load() -> C.CDLL:
     L.cordum_engine_destroy.restype = None
     L.cordum_policy_load.argtypes = [vp, cp, u64, cp, u64]
     L.cordum_policy_snapshots.argtypes = [vp, cp, u64, C.POINTER(u32)]
+    L.cordum_policy_snapshot.argtypes = [vp, cp, u64]
+    L.cordum_policy_snapshot.restype = i64
     L.cordum_routing_load.argtypes = [vp, cp, u64]
     L.cordum_workers_load.argtypes = [vp, vp]
     L.cordum_workers_update.argtypes = [vp, u32, vp, vp]
@@ -95,6 +98,11 @@ def load() -> C.CDLL:
     L.cordum_subject.argtypes = [vp, vp, u32, cp, u64]
     L.cordum_subject.restype = i64
     L.cordum_stats.argtypes = [vp, C.POINTER(wire.CordumTableStats)]
+    L.cordum_frontend_create.argtypes = [vp, vp, C.POINTER(vp)]
+    L.cordum_frontend_destroy.argtypes = [vp]
+    L.cordum_frontend_destroy.restype = None
+    L.cordum_frontend_submit.argtypes = [vp, vp, vp]
+    L.cordum_frontend_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.cordum_launch_count.argtypes = [vp]
     L.cordum_launch_count.restype = u64
     L.cordum_test_glob.argtypes = [cp, u64, cp, u64]

@@ -1025,6 +1025,14 @@ int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint3
   return CORDUM_OK;
 }
 
+/* PolicyCheckResponse.PolicySnapshot = the snapshot of the policy in force (kernel.go:243), which is "" when that policy
+ * was loaded without one - not the newest entry of the history */
+int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> g(e->host->mutex());
+  return copy_out(e->host->current_snapshot(), buf, cap);
+}
+
 int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
   return e->host->load_routing(sv(json ? json : "", json ? len : 0), g_err);

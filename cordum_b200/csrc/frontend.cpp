@@ -1,0 +1,252 @@
+// frontend.cpp — micro-batching front-end over the batch ABI (include/cordum_b200.h, cordum_frontend_*).
+//
+// The reference handles one request at a time: the scheduler's handleJobRequest / processJob
+// (core/controlplane/scheduler/engine.go:203-443) calls SafetyChecker.Check and SchedulingStrategy.PickSubject per job,
+// and grpc-go runs every SafetyKernel RPC on its own goroutine (kernel.go:106-127).  A GPU round trip per request would
+// waste the device, so this front-end turns many concurrent blocking single-request calls into batches:
+//     cordum_frontend_submit(request) -> decision            blocking, thread-safe, one request
+// A lane thread takes the first waiting request, keeps collecting until the batch holds max_batch requests or max_wait_us
+// have passed since that first request, lays the requests out in page-locked envelope buffers, runs ONE cordum_encode +
+// cordum_dispatch for all of them, formats the strings the response carries (rule id, reason, subject, snapshot) and wakes
+// the callers.  Two lanes alternate, so that packing the next batch overlaps the GPU round trip of the current one.
+// Failures are per batch and fail closed: every request of a failed batch gets the engine's status and a DENY record.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/cordum_b200.h"
+
+namespace {
+
+struct Ticket {
+  const cordum_request* req;
+  cordum_response* resp;
+  bool done = false;
+};
+
+struct Lane {
+  cordum_envelopes* env = nullptr;   // page-locked, owned by the engine
+  cordum_batch* batch = nullptr;
+  std::thread th;
+};
+
+}  // namespace
+
+struct cordum_frontend {
+  cordum_engine* eng = nullptr;
+  cordum_frontend_opts opts{};
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<Ticket*> queue;
+  bool stop = false;
+  std::vector<std::unique_ptr<Lane>> lanes;
+  std::atomic<uint64_t> n_batches{0}, n_requests{0}, n_full{0};
+  uint64_t arena_cap = 0;
+  uint32_t max_lists = 0;
+
+  void run(Lane& L);
+  bool pack(Lane& L, std::vector<Ticket*>& items, std::vector<int32_t>& status);
+};
+
+namespace {
+
+inline cordum_str put(uint8_t* arena, uint64_t& at, uint64_t cap, cordum_sv s, bool& overflow) {
+  cordum_str r{0, 0};
+  if (!s.p || s.n == 0) return r;
+  if (at + s.n > cap) { overflow = true; return r; }
+  std::memcpy(arena + at, s.p, s.n);
+  r.off = (uint32_t)at;
+  r.len = s.n;
+  at += s.n;
+  return r;
+}
+
+void fail_closed(cordum_response* r, int32_t status, const char* msg) {
+  std::memset(r, 0, sizeof *r);
+  r->status = status;
+  r->rec.decision = CORDUM_DEC_DENY;
+  r->rec.sched_decision = CORDUM_DEC_DENY;
+  r->rec.rule_idx = -1;
+  r->rec.worker_slot = -1;
+  std::snprintf(r->reason, sizeof r->reason, "safety kernel error: %s", msg ? msg : "");   // safety_client.go:98-101
+}
+
+}  // namespace
+
+// Lay the requests out as one columnar envelope set.  A request that does not fit (arena or list capacity) is failed
+// closed on its own; the rest of the batch goes through.
+bool cordum_frontend::pack(Lane& L, std::vector<Ticket*>& items, std::vector<int32_t>& status) {
+  cordum_envelopes* e = L.env;
+  auto* arena = const_cast<uint8_t*>(e->arena);
+  auto col = [](const cordum_str* p) { return const_cast<cordum_str*>(p); };
+  auto u8 = [](const uint8_t* p) { return const_cast<uint8_t*>(p); };
+  auto u32 = [](const uint32_t* p) { return const_cast<uint32_t*>(p); };
+  uint64_t at = 1;   // offset 0 = the empty string
+  uint32_t n = 0, n_risk = 0, n_req = 0, n_lab = 0;
+  u32(e->risk_off)[0] = 0; u32(e->requires_off)[0] = 0; u32(e->label_off)[0] = 0;
+  for (size_t i = 0; i < items.size(); ++i) {
+    const cordum_request& q = *items[i]->req;
+    const uint64_t at0 = at;
+    bool ov = n_risk + q.n_risk_tags > max_lists || n_req + q.n_requires > max_lists || n_lab + q.n_labels > max_lists;
+    if (!ov) {
+      col(e->topic)[n] = put(arena, at, arena_cap, q.topic, ov);
+      col(e->tenant)[n] = put(arena, at, arena_cap, q.tenant, ov);
+      col(e->principal_id)[n] = put(arena, at, arena_cap, q.principal_id, ov);
+      col(e->effective_config)[n] = put(arena, at, arena_cap, q.effective_config, ov);
+      u8(e->has_meta)[n] = q.has_meta ? 1 : 0;
+      col(e->meta_tenant_id)[n] = put(arena, at, arena_cap, q.meta_tenant_id, ov);
+      col(e->actor_id)[n] = put(arena, at, arena_cap, q.actor_id, ov);
+      u8(e->actor_type)[n] = q.actor_type;
+      col(e->capability)[n] = put(arena, at, arena_cap, q.capability, ov);
+      col(e->pack_id)[n] = put(arena, at, arena_cap, q.pack_id, ov);
+      u8(e->approved)[n] = q.approved ? 1 : 0;
+      for (uint32_t k = 0; k < q.n_risk_tags && !ov; ++k) col(e->risk_tags)[n_risk + k] = put(arena, at, arena_cap, q.risk_tags[k], ov);
+      for (uint32_t k = 0; k < q.n_requires && !ov; ++k) col(e->requires_)[n_req + k] = put(arena, at, arena_cap, q.requires_[k], ov);
+      for (uint32_t k = 0; k < q.n_labels && !ov; ++k) {
+        col(e->label_keys)[n_lab + k] = put(arena, at, arena_cap, q.labels[k].key, ov);
+        col(e->label_vals)[n_lab + k] = put(arena, at, arena_cap, q.labels[k].val, ov);
+      }
+    }
+    if (ov) { at = at0; status[i] = CORDUM_E_CAPACITY; continue; }   // this request alone is refused
+    status[i] = (int32_t)n;   // its row in the batch
+    n_risk += q.n_risk_tags; n_req += q.n_requires; n_lab += q.n_labels;
+    ++n;
+    u32(e->risk_off)[n] = n_risk; u32(e->requires_off)[n] = n_req; u32(e->label_off)[n] = n_lab;
+  }
+  e->n_jobs = n;
+  e->arena_len = at;
+  return n > 0;
+}
+
+void cordum_frontend::run(Lane& L) {
+  std::vector<Ticket*> items;
+  std::vector<int32_t> row;
+  while (true) {
+    items.clear();
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_work.wait(lk, [&] { return stop || !queue.empty(); });
+      if (stop && queue.empty()) return;
+      // the first request opens the batch; collect until it is full or max_wait_us have passed since then
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(opts.max_wait_us);
+      while (true) {
+        while (!queue.empty() && items.size() < opts.max_batch) { items.push_back(queue.front()); queue.pop_front(); }
+        if (items.size() >= opts.max_batch || stop || opts.max_wait_us == 0) break;
+        if (cv_work.wait_until(lk, deadline, [&] { return stop || !queue.empty(); })) { if (queue.empty()) break; continue; }
+        break;   // deadline
+      }
+      if (!queue.empty()) cv_work.notify_one();   // more work than one batch: wake the other lane
+    }
+    if (items.size() >= opts.max_batch) n_full++;
+    row.assign(items.size(), 0);
+    int32_t rc = CORDUM_OK;
+    const char* msg = "";
+    const bool any = pack(L, items, row);
+    if (any) {
+      rc = cordum_encode(eng, L.batch, L.env);
+      if (rc == CORDUM_OK) rc = cordum_dispatch(eng, L.batch, opts.mode);
+      if (rc != CORDUM_OK) msg = cordum_last_error();
+    }
+    const cordum_decision* recs = (any && rc == CORDUM_OK) ? cordum_batch_results(L.batch) : nullptr;
+    char snap[sizeof(((cordum_response*)nullptr)->snapshot)] = {0};
+    if (recs) cordum_policy_snapshot(eng, snap, sizeof snap);   // the CURRENT snapshot (kernel.go:243), "" if the policy has none
+    for (size_t i = 0; i < items.size(); ++i) {
+      cordum_response* r = items[i]->resp;
+      if (row[i] < 0) { fail_closed(r, row[i], "request exceeds the front-end's envelope capacity"); continue; }
+      if (!recs) { fail_closed(r, rc, msg); continue; }
+      const uint32_t j = (uint32_t)row[i];
+      std::memset(r, 0, sizeof *r);
+      r->status = CORDUM_OK;
+      r->rec = recs[j];
+      if (r->rec.flags & CORDUM_F_HAS_SNAPSHOT) {   // kernel.go:239-248: the early DENY returns carry neither snapshot nor rule id
+        std::memcpy(r->snapshot, snap, sizeof snap);
+        cordum_rule_id(eng, r->rec.rule_idx, r->rule_id, sizeof r->rule_id);
+      }
+      // kernel.go:198-215: allow and allow_with_constraints drop the reason
+      if (r->rec.reason_code != CORDUM_REASON_NONE && r->rec.decision != CORDUM_DEC_ALLOW && r->rec.decision != CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)
+        cordum_reason(eng, L.batch, j, r->reason, sizeof r->reason);
+      else if (r->rec.reason_code == CORDUM_REASON_APPROVAL_GRANTED) cordum_reason(eng, L.batch, j, r->reason, sizeof r->reason);
+      if (r->rec.route_status == CORDUM_ROUTE_OK || r->rec.route_status == CORDUM_ROUTE_OK_PREFERRED)
+        cordum_subject(eng, L.batch, j, r->subject, sizeof r->subject);
+    }
+    n_batches++;
+    n_requests += items.size();
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (Ticket* t : items) t->done = true;
+    }
+    cv_done.notify_all();
+  }
+}
+
+extern "C" {
+
+int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* o, cordum_frontend** out) {
+  if (!e || !out) return CORDUM_E_INVALID;
+  *out = nullptr;
+  auto f = std::make_unique<cordum_frontend>();
+  f->eng = e;
+  f->opts.max_batch = o && o->max_batch ? o->max_batch : 1024;
+  f->opts.max_wait_us = o ? o->max_wait_us : 200;
+  f->opts.mode = o && o->mode ? o->mode : CORDUM_MODE_POLICY_AND_ROUTE;
+  f->opts.lanes = o && o->lanes ? o->lanes : 2;
+  f->opts.arena_bytes_per_request = o && o->arena_bytes_per_request ? o->arena_bytes_per_request : 1024;
+  f->arena_cap = (uint64_t)f->opts.max_batch * f->opts.arena_bytes_per_request + 16;
+  f->max_lists = f->opts.max_batch * 8;
+  for (uint32_t i = 0; i < f->opts.lanes; ++i) {
+    auto L = std::make_unique<Lane>();
+    cordum_envelope_caps caps{f->opts.max_batch, f->max_lists, f->max_lists, f->max_lists, f->arena_cap};
+    int32_t rc = cordum_envelopes_alloc(e, &caps, &L->env);
+    if (rc == CORDUM_OK) rc = cordum_batch_alloc(e, f->opts.max_batch, &L->batch);
+    if (rc != CORDUM_OK) {
+      if (L->batch) cordum_batch_free(L->batch);
+      if (L->env) cordum_envelopes_free(e, L->env);
+      for (auto& l : f->lanes) { cordum_batch_free(l->batch); cordum_envelopes_free(e, l->env); }
+      return rc;
+    }
+    f->lanes.push_back(std::move(L));
+  }
+  cordum_frontend* fp = f.get();
+  for (auto& L : f->lanes) { Lane* lp = L.get(); lp->th = std::thread([fp, lp] { fp->run(*lp); }); }
+  *out = f.release();
+  return CORDUM_OK;
+}
+
+void cordum_frontend_destroy(cordum_frontend* f) {
+  if (!f) return;
+  { std::lock_guard<std::mutex> lk(f->mu); f->stop = true; }
+  f->cv_work.notify_all();
+  for (auto& L : f->lanes) if (L->th.joinable()) L->th.join();
+  for (auto& L : f->lanes) { cordum_batch_free(L->batch); cordum_envelopes_free(f->eng, L->env); }
+  delete f;
+}
+
+int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, cordum_response* resp) {
+  if (!f || !req || !resp) return CORDUM_E_INVALID;
+  Ticket t{req, resp, false};
+  {
+    std::unique_lock<std::mutex> lk(f->mu);
+    if (f->stop) { fail_closed(resp, CORDUM_E_STATE, "front-end is shutting down"); return CORDUM_E_STATE; }
+    f->queue.push_back(&t);
+    f->cv_work.notify_one();
+    f->cv_done.wait(lk, [&] { return t.done; });
+  }
+  return resp->status;
+}
+
+int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches) {
+  if (!f) return CORDUM_E_INVALID;
+  if (batches) *batches = f->n_batches.load();
+  if (requests) *requests = f->n_requests.load();
+  if (full_batches) *full_batches = f->n_full.load();
+  return CORDUM_OK;
+}
+
+}  // extern "C"

@@ -287,6 +287,11 @@ class Engine:
     def host_fallbacks(self) -> int:
         return int(self.L.cordum_host_fallbacks(self.h))
 
+    def current_snapshot(self) -> str:
+        buf = C.create_string_buffer(4096)
+        self.L.cordum_policy_snapshot(self.h, buf, len(buf))
+        return buf.value.decode("utf-8", "replace")
+
     def batch(self, max_jobs: int) -> Batch:
         return Batch(self, max_jobs)
 

@@ -107,8 +107,7 @@ class SafetyKernelServer:
             self._batch = self.engine.batch(max(n, 256))
         b = self._batch
         recs = b.encode([_envelope(r) for r in requests]).dispatch(wire.MODE_POLICY_ONLY)
-        snaps = self.engine.snapshots()
-        snapshot = snaps[0] if snaps else ""
+        snapshot = self.engine.current_snapshot()   # s.snapshot (kernel.go:243): "" when the policy in force has none
         out = []
         for j, (req, rec) in enumerate(zip(requests, recs)):
             flags = int(rec["flags"])

@@ -196,6 +196,9 @@ int32_t cordum_policy_load(cordum_engine* e, const char* policy_json, uint64_t l
                            const char* snapshot, uint64_t snapshot_len);
 /* ListSnapshots: writes up to cap NUL-separated snapshot ids, newest first. */
 int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint32_t* n_out);
+/* The snapshot of the policy in force = PolicyCheckResponse.PolicySnapshot (kernel.go:243): "" when the current policy
+ * was loaded without one.  NUL-terminated into buf, returns the full length. */
+int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap);
 
 /* (*LeastLoadedStrategy).UpdateRouting (strategy_least_loaded.go:28-30).
  * routing_json = {"topics": {topic: [pool,...]}, "pools": {pool: {"requires": [...]}}}
@@ -330,6 +333,45 @@ int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, ch
 /* JSON of rules[rule_idx].constraints / .remediations as loaded (kernel.go:244,247). */
 int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
 int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
+
+/* ---- micro-batching front-end (cordum_b200/csrc/frontend.cpp).
+ * The seams it stands behind handle ONE request per call: scheduler.SafetyChecker.Check (types.go:29-31),
+ * scheduler.SchedulingStrategy.PickSubject (types.go:40-42), the four SafetyKernel RPCs (kernel.go:106-127, each on its
+ * own goroutine), and processJob (engine.go:203-443) which calls the first two per job.  cordum_frontend_submit is that
+ * call shape - blocking, thread-safe, one request in, one decision out - and batches concurrent callers behind it: a
+ * batch is flushed when it holds max_batch requests or max_wait_us after its first request, whichever comes first, with
+ * ONE encode + dispatch for all of them.  Strings need not be NUL-terminated. */
+typedef struct cordum_sv { const char* p; uint32_t n; } cordum_sv;
+typedef struct cordum_kv { cordum_sv key, val; } cordum_kv;
+typedef struct cordum_request {      /* PolicyCheckRequest / JobRequest fields the path reads */
+  cordum_sv topic, tenant, principal_id, effective_config;
+  uint8_t has_meta, actor_type /* 0 unspecified, 1 human, 2 service */, approved, pad;
+  cordum_sv meta_tenant_id, actor_id, capability, pack_id;
+  const cordum_sv* risk_tags; uint32_t n_risk_tags;
+  const cordum_sv* requires_; uint32_t n_requires;
+  const cordum_kv* labels; uint32_t n_labels;
+} cordum_request;
+typedef struct cordum_response {     /* PolicyCheckResponse (kernel.go:239-248) + the routed subject (PickSubject) */
+  cordum_decision rec;
+  int32_t status;                    /* CORDUM_OK, or why the request failed closed (rec then says DENY)            */
+  char rule_id[128];                 /* "" when the response carries none (kernel.go:171-176)                       */
+  char reason[256];
+  char subject[192];                 /* "worker.<id>.jobs" when routed (bus/nats.go:94-99)                          */
+  char snapshot[96];                 /* PolicySnapshot                                                              */
+} cordum_response;
+typedef struct cordum_frontend_opts {
+  uint32_t max_batch;                /* flush at this many requests (default 1024)                                  */
+  uint32_t max_wait_us;              /* ... or this long after the first request of the batch (default 200; 0 = never wait) */
+  uint32_t mode;                     /* CORDUM_MODE_* of every batch (default POLICY_AND_ROUTE)                     */
+  uint32_t lanes;                    /* batches in flight (default 2: packing overlaps the GPU round trip)          */
+  uint32_t arena_bytes_per_request;  /* string budget per request in the page-locked staging (default 1024)         */
+} cordum_frontend_opts;
+typedef struct cordum_frontend cordum_frontend;
+int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* opts, cordum_frontend** out);
+void cordum_frontend_destroy(cordum_frontend* f);
+/* Blocking; any number of threads.  Returns resp->status. */
+int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, cordum_response* resp);
+int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches);
 
 /* Introspection for tests/bench: table sizes and algorithmic byte counts. */
 typedef struct cordum_table_stats {
