@@ -24,7 +24,7 @@ API = [
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
     "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
-    "cordum_launch_count", "cordum_frontend_create", "cordum_frontend_destroy", "cordum_frontend_submit", "cordum_frontend_stats",
+    "cordum_launch_count", "cordum_frontend_create", "cordum_frontend_destroy", "cordum_frontend_submit", "cordum_frontend_submit_many", "cordum_frontend_stats", "cordum_frontend_loadgen",
     "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
     "cordum_test_parse_effective", "cordum_test_canon",
 ]
@@ -102,7 +102,10 @@ def load() -> C.CDLL:
     L.cordum_frontend_destroy.argtypes = [vp]
     L.cordum_frontend_destroy.restype = None
     L.cordum_frontend_submit.argtypes = [vp, vp, vp]
+    L.cordum_frontend_submit_many.argtypes = [vp, vp, u32, vp]
     L.cordum_frontend_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.cordum_frontend_loadgen.argtypes = [vp, vp, u32, u32, C.c_double, vp, u64]
+    L.cordum_frontend_loadgen.restype = u64
     L.cordum_launch_count.argtypes = [vp]
     L.cordum_launch_count.restype = u64
     L.cordum_test_glob.argtypes = [cp, u64, cp, u64]

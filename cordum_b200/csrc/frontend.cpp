@@ -28,6 +28,10 @@ namespace {
 struct Ticket {
   const cordum_request* req;
   cordum_response* resp;
+  // completion is signalled per ticket: waking every waiter of the front-end for every batch does not scale to
+  // thousands of blocked callers
+  std::mutex m;
+  std::condition_variable cv;
   bool done = false;
 };
 
@@ -43,7 +47,7 @@ struct cordum_frontend {
   cordum_engine* eng = nullptr;
   cordum_frontend_opts opts{};
   std::mutex mu;
-  std::condition_variable cv_work, cv_done;
+  std::condition_variable cv_work;
   std::deque<Ticket*> queue;
   bool stop = false;
   std::vector<std::unique_ptr<Lane>> lanes;
@@ -178,11 +182,11 @@ void cordum_frontend::run(Lane& L) {
     }
     n_batches++;
     n_requests += items.size();
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      for (Ticket* t : items) t->done = true;
+    for (Ticket* t : items) {
+      std::lock_guard<std::mutex> lk(t->m);   // notify under the lock: the waiter cannot return (and destroy t) before we are done with it
+      t->done = true;
+      t->cv.notify_one();
     }
-    cv_done.notify_all();
   }
 }
 
@@ -230,15 +234,70 @@ void cordum_frontend_destroy(cordum_frontend* f) {
 
 int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, cordum_response* resp) {
   if (!f || !req || !resp) return CORDUM_E_INVALID;
-  Ticket t{req, resp, false};
+  Ticket t;
+  t.req = req; t.resp = resp;
   {
-    std::unique_lock<std::mutex> lk(f->mu);
+    std::lock_guard<std::mutex> lk(f->mu);
     if (f->stop) { fail_closed(resp, CORDUM_E_STATE, "front-end is shutting down"); return CORDUM_E_STATE; }
     f->queue.push_back(&t);
-    f->cv_work.notify_one();
-    f->cv_done.wait(lk, [&] { return t.done; });
+  }
+  f->cv_work.notify_one();
+  {
+    std::unique_lock<std::mutex> lk(t.m);
+    t.cv.wait(lk, [&] { return t.done; });
   }
   return resp->status;
+}
+
+/* n requests from one caller (e.g. a Go adapter that has drained a channel): queued together, answered together. */
+int32_t cordum_frontend_submit_many(cordum_frontend* f, const cordum_request* reqs, uint32_t n, cordum_response* resps) {
+  if (!f || (n && (!reqs || !resps))) return CORDUM_E_INVALID;
+  std::vector<std::unique_ptr<Ticket>> ts(n);
+  {
+    std::lock_guard<std::mutex> lk(f->mu);
+    if (f->stop) { for (uint32_t i = 0; i < n; ++i) fail_closed(&resps[i], CORDUM_E_STATE, "front-end is shutting down"); return CORDUM_E_STATE; }
+    for (uint32_t i = 0; i < n; ++i) {
+      ts[i] = std::make_unique<Ticket>();
+      ts[i]->req = &reqs[i]; ts[i]->resp = &resps[i];
+      f->queue.push_back(ts[i].get());
+    }
+  }
+  f->cv_work.notify_all();
+  int32_t worst = CORDUM_OK;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::unique_lock<std::mutex> lk(ts[i]->m);
+    ts[i]->cv.wait(lk, [&] { return ts[i]->done; });
+    if (resps[i].status != CORDUM_OK) worst = resps[i].status;
+  }
+  return worst;
+}
+
+/* Load generator (diagnostics): `threads` native threads submit the given requests round-robin, one blocking call at a
+ * time, for `seconds`; per-request latencies in microseconds go to lat_us (up to cap entries, thread-interleaved).
+ * Returns the number of requests completed.  Native threads: a Python harness would measure its own interpreter lock. */
+uint64_t cordum_frontend_loadgen(cordum_frontend* f, const cordum_request* reqs, uint32_t n_reqs, uint32_t threads, double seconds,
+                                 float* lat_us, uint64_t cap) {
+  if (!f || !reqs || !n_reqs || !threads) return 0;
+  std::atomic<uint64_t> total{0};
+  const auto stop_at = std::chrono::steady_clock::now() + std::chrono::duration<double>(seconds);
+  std::vector<std::thread> ts;
+  for (uint32_t t = 0; t < threads; ++t)
+    ts.emplace_back([&, t] {
+      cordum_response resp;
+      uint64_t i = t, mine = 0;
+      while (std::chrono::steady_clock::now() < stop_at) {
+        const auto t0 = std::chrono::steady_clock::now();
+        cordum_frontend_submit(f, &reqs[i % n_reqs], &resp);
+        const float us = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        const uint64_t slot = mine * threads + t;
+        if (lat_us && slot < cap) lat_us[slot] = us;
+        ++mine;
+        i += threads;
+      }
+      total += mine;
+    });
+  for (auto& th : ts) th.join();
+  return total.load();
 }
 
 int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches) {

@@ -371,7 +371,12 @@ int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* opt
 void cordum_frontend_destroy(cordum_frontend* f);
 /* Blocking; any number of threads.  Returns resp->status. */
 int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, cordum_response* resp);
+/* n requests of one caller at once (a Go adapter that drained a channel): returns the worst status. */
+int32_t cordum_frontend_submit_many(cordum_frontend* f, const cordum_request* reqs, uint32_t n, cordum_response* resps);
 int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches);
+/* Diagnostics: native client threads submitting round-robin for `seconds`; latencies (us) into lat_us[cap]. */
+uint64_t cordum_frontend_loadgen(cordum_frontend* f, const cordum_request* reqs, uint32_t n_reqs, uint32_t threads, double seconds,
+                                 float* lat_us, uint64_t cap);
 
 /* Introspection for tests/bench: table sizes and algorithmic byte counts. */
 typedef struct cordum_table_stats {
