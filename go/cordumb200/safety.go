@@ -1,77 +1,118 @@
 package cordumb200
 
+/*
+#include "cordum_b200.h"
+*/
+import "C"
+
 import (
 	"context"
-	"time"
+	"encoding/json"
+
+	"gopkg.in/yaml.v3"
 
 	"github.com/cordum/cordum/core/controlplane/scheduler"
 	"github.com/cordum/cordum/core/infra/config"
 	pb "github.com/cordum/cordum/core/protocol/pb/v1"
 )
 
-// SafetyKernel implements pb.SafetyKernelServer (Check/Evaluate/Explain/Simulate/ListSnapshots,
-// kernel.go:106-127) and scheduler.SafetyChecker (types.go:29-31) over one Engine.
-//
-// grpc-go runs every RPC on its own goroutine; a single GPU round trip per request would waste the
-// device, so concurrent calls are micro-batched: a request waits until the batch holds maxBatch
-// requests or maxWait has elapsed, then one cordum_encode + cordum_dispatch(POLICY_ONLY) serves all.
+// SafetyKernel implements pb.SafetyKernelServer (Check/Evaluate/Explain/Simulate/ListSnapshots, kernel.go:106-127)
+// over one Engine.  grpc-go runs every RPC on its own goroutine; each handler converts its request, blocks in
+// cordum_frontend_submit while the request rides in a batch with the other in-flight RPCs, and converts the answer.
 type SafetyKernel struct {
 	pb.UnimplementedSafetyKernelServer
-	eng      *Engine
-	in       chan *pending
-	maxBatch int
-	maxWait  time.Duration
+	eng *Engine
 }
 
-type pending struct {
-	req  *pb.PolicyCheckRequest
-	resp chan *pb.PolicyCheckResponse
+func NewSafetyKernel(eng *Engine) *SafetyKernel { return &SafetyKernel{eng: eng} }
+
+// PolicyJSON renders the merged *config.SafetyPolicy with its yaml tag names as JSON keys, which is the document
+// cordum_policy_load takes (include/cordum_b200.h).  config's structs carry yaml tags only, so go through a generic map.
+func PolicyJSON(p *config.SafetyPolicy) ([]byte, error) {
+	if p == nil {
+		return nil, nil // nil policy: allow-all (kernel.go:187)
+	}
+	y, err := yaml.Marshal(p) // gopkg.in/yaml.v3, the module the reference parses its policies with (go.mod)
+	if err != nil {
+		return nil, err
+	}
+	var generic map[string]any
+	if err := yaml.Unmarshal(y, &generic); err != nil {
+		return nil, err
+	}
+	return json.Marshal(generic)
 }
 
-func NewSafetyKernel(eng *Engine) *SafetyKernel {
-	k := &SafetyKernel{eng: eng, in: make(chan *pending, 4096), maxBatch: 1024, maxWait: 200 * time.Microsecond}
-	go k.loop()
-	return k
+var decisionToProto = map[C.uint8_t]pb.DecisionType{ // include/cordum_b200.h CORDUM_DEC_* -> pb.go:61-66
+	C.CORDUM_DEC_ALLOW:                  pb.DecisionType_DECISION_TYPE_ALLOW,
+	C.CORDUM_DEC_DENY:                   pb.DecisionType_DECISION_TYPE_DENY,
+	C.CORDUM_DEC_REQUIRE_HUMAN:          pb.DecisionType_DECISION_TYPE_REQUIRE_HUMAN,
+	C.CORDUM_DEC_THROTTLE:               pb.DecisionType_DECISION_TYPE_THROTTLE,
+	C.CORDUM_DEC_ALLOW_WITH_CONSTRAINTS: pb.DecisionType_DECISION_TYPE_ALLOW_WITH_CONSTRAINTS,
 }
 
-func (k *SafetyKernel) loop() {
-	for first := range k.in {
-		batch := []*pending{first}
-		timer := time.NewTimer(k.maxWait)
-	fill:
-		for len(batch) < k.maxBatch {
-			select {
-			case p := <-k.in:
-				batch = append(batch, p)
-			case <-timer.C:
-				break fill
-			}
-		}
-		timer.Stop()
-		resps, err := k.eng.evaluate(batch) // encode + dispatch + materialise strings
-		for i, p := range batch {
-			if err != nil {
-				// fail closed, exactly what SafetyClient does on a transport error (safety_client.go:98-101)
-				p.resp <- &pb.PolicyCheckResponse{Decision: pb.DecisionType_DECISION_TYPE_DENY, Reason: "safety kernel error: " + err.Error()}
-				continue
-			}
-			p.resp <- resps[i]
-		}
+func toProtoConstraints(c config.PolicyConstraints) *pb.PolicyConstraints { // kernel.go:416-445 (emptiness was decided by the engine)
+	return &pb.PolicyConstraints{
+		Budgets: &pb.BudgetConstraints{MaxRuntimeMs: c.Budgets.MaxRuntimeMs, MaxRetries: c.Budgets.MaxRetries,
+			MaxArtifactBytes: c.Budgets.MaxArtifactBytes, MaxConcurrentJobs: c.Budgets.MaxConcurrentJobs},
+		Sandbox: &pb.SandboxProfile{Isolated: c.Sandbox.Isolated, NetworkAllowlist: c.Sandbox.NetworkAllowlist,
+			FsReadOnly: c.Sandbox.FsReadOnly, FsReadWrite: c.Sandbox.FsReadWrite},
+		Toolchain:      &pb.ToolchainConstraints{AllowedTools: c.Toolchain.AllowedTools, AllowedCommands: c.Toolchain.AllowedCommands},
+		Diff:           &pb.DiffConstraints{MaxFiles: c.Diff.MaxFiles, MaxLines: c.Diff.MaxLines, DenyPathGlobs: c.Diff.DenyPathGlobs},
+		RedactionLevel: c.RedactionLevel,
 	}
 }
 
+// evaluate is the batched form of (*server).evaluate (kernel.go:129-257) for one request.
 func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest) (*pb.PolicyCheckResponse, error) {
-	p := &pending{req: req, resp: make(chan *pb.PolicyCheckResponse, 1)}
-	k.in <- p
-	select {
-	case r := <-p.resp:
-		return r, nil
-	case <-ctx.Done():
-		return nil, ctx.Err()
+	if err := ctx.Err(); err != nil {
+		return nil, err
 	}
+	creq, free := packRequest(req.GetTopic(), req.GetTenant(), req.GetPrincipalId(), req.GetLabels(), req.GetMeta(), req.GetEffectiveConfig(), false)
+	defer free()
+	r, freeResp, err := submit(k.eng.policyFE, creq)
+	if err != nil {
+		// Evaluate never returns a Go error for policy outcomes (kernel.go:172,175); an engine failure fails closed,
+		// exactly what SafetyClient does on a transport error (safety_client.go:98-101)
+		return &pb.PolicyCheckResponse{Decision: pb.DecisionType_DECISION_TYPE_DENY, Reason: err.Error()}, nil
+	}
+	defer freeResp()
+	out := &pb.PolicyCheckResponse{
+		Decision: decisionToProto[r.rec.decision], Reason: C.GoString(&r.reason[0]),
+		PolicySnapshot: C.GoString(&r.snapshot[0]), RuleId: C.GoString(&r.rule_id[0]),
+		ApprovalRequired: r.rec.flags&C.CORDUM_F_APPROVAL_REQUIRED != 0,
+	}
+	if out.ApprovalRequired {
+		out.ApprovalRef = req.GetJobId() // kernel.go:233-237
+	}
+	if r.rec.flags&C.CORDUM_F_CONSTRAINTS != 0 {
+		if js := k.eng.ruleText(r.rec.rule_idx, func(e *C.cordum_engine, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_constraints_json(e, i, b, n)
+		}); js != nil {
+			var c config.PolicyConstraints
+			if json.Unmarshal(js, &c) == nil { // the engine passes the rule's YAML-tagged object through as JSON
+				out.Constraints = toProtoConstraints(c)
+			}
+		}
+	}
+	if r.rec.rule_idx >= 0 {
+		if js := k.eng.ruleText(r.rec.rule_idx, func(e *C.cordum_engine, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_remediations_json(e, i, b, n)
+		}); js != nil {
+			var rems []config.PolicyRemediation
+			if json.Unmarshal(js, &rems) == nil {
+				for _, rem := range rems { // kernel.go:326-346
+					out.Remediations = append(out.Remediations, &pb.PolicyRemediation{Id: rem.ID, Title: rem.Title, Summary: rem.Summary,
+						ReplacementTopic: rem.ReplacementTopic, ReplacementCapability: rem.ReplacementCapability,
+						AddLabels: rem.AddLabels, RemoveLabels: append([]string{}, rem.RemoveLabels...)})
+				}
+			}
+		}
+	}
+	return out, nil
 }
 
-// All four modes are the same function in the reference (kernel.go:129: the mode string is ignored).
+// All four modes are the same function in the reference (kernel.go:106-120,129: the mode string is ignored).
 func (k *SafetyKernel) Check(ctx context.Context, r *pb.PolicyCheckRequest) (*pb.PolicyCheckResponse, error) {
 	return k.evaluate(ctx, r)
 }
@@ -85,12 +126,14 @@ func (k *SafetyKernel) Simulate(ctx context.Context, r *pb.PolicyCheckRequest) (
 	return k.evaluate(ctx, r)
 }
 func (k *SafetyKernel) ListSnapshots(context.Context, *pb.ListSnapshotsRequest) (*pb.ListSnapshotsResponse, error) {
-	return &pb.ListSnapshotsResponse{Snapshots: k.eng.snapshots()}, nil
+	return &pb.ListSnapshotsResponse{Snapshots: k.eng.Snapshots()}, nil
 }
 
-// Checker is the in-process scheduler.SafetyChecker: same field mapping as SafetyClient.Check
+// Checker is the in-process scheduler.SafetyChecker (types.go:29-31): same field mapping as SafetyClient.Check
 // (safety_client.go:80-95), no gRPC hop.
 type Checker struct{ k *SafetyKernel }
+
+func NewChecker(k *SafetyKernel) Checker { return Checker{k: k} }
 
 func (c Checker) Check(req *pb.JobRequest) (scheduler.SafetyDecisionRecord, error) {
 	creq := &pb.PolicyCheckRequest{

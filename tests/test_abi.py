@@ -130,3 +130,24 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
         pytest.skip("GPU present: the example's device path is exercised by hand, not by the CPU suite")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "no CUDA device" in r.stdout, (r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c_host_runs_the_device_path(tmp_path):
+    """examples/host_min.c - the ABI driven from plain C exactly as a cgo binding would - on the GPU: BASELINE config 1
+    (hello-pack: one echo job, one allow rule, a two-worker pool) must come out ALLOW under rule hello-pack-allow and
+    routed to the idle worker."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "host_min")
+    libdir = os.path.join(ROOT, "cordum_b200")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_min.c"), "-L" + libdir, "-lcordum_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "decision 1 rule hello-pack-allow route_status 1 subject worker.hello-worker-b.jobs" in r.stdout, r.stdout
