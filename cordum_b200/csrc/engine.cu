@@ -524,13 +524,6 @@ int64_t copy_out(const std::string& s, char* buf, uint64_t cap) {
   return (int64_t)s.size();
 }
 
-std::string go_quote(sv s) {
-  std::string o = "\"";
-  for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
-  o.push_back('"');
-  return o;
-}
-
 }  // namespace
 
 static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resources; the registry is the caller's business
@@ -1466,7 +1459,12 @@ int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* 
 }
 
 int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
-  if (!e || !b || job >= b->n) return -1;
+  return cordum_reason_flavor(e, b, job, CORDUM_REASON_FLAVOR_KERNEL, nullptr, buf, cap);
+}
+
+int64_t cordum_reason_flavor(cordum_engine* e, const cordum_batch* b, uint32_t job, uint32_t flavor,
+                             const cordum_envelopes* env, char* buf, uint64_t cap) {
+  if (!e || !b || job >= b->n || flavor > CORDUM_REASON_FLAVOR_GATEWAY || (env && env->n_jobs != b->n)) return -1;
   if (ensure_host_records(const_cast<cordum_batch*>(b))) return -1;
   std::lock_guard<std::mutex> g(e->host->mutex());
   const cordum_decision& r = b->h_out[job];
@@ -1481,15 +1479,18 @@ int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, cha
   else if (code == CORDUM_REASON_APPROVAL_GRANTED) s = "approval granted";
   else if (code == CORDUM_REASON_EFF_DENIED_TOPIC || code == CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC) {
     std::string topic(cordum::trim_space(e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic)));
-    s = "topic '" + topic + (code == CORDUM_REASON_EFF_DENIED_TOPIC ? "' denied by effective config" : "' not allowed by effective config");
+    const char* tail = code == CORDUM_REASON_EFF_DENIED_TOPIC ? " denied by effective config" : " not allowed by effective config";
+    // kernel.go:221,225 print '%s'; the gateway's copy of the evaluator prints %q (policy_bundles.go:1207,1211)
+    s = "topic " + (flavor == CORDUM_REASON_FLAVOR_GATEWAY ? cordum::go_quote(topic) : "'" + topic + "'") + tail;
   } else if ((code >= CORDUM_REASON_TENANT_MCP && code < CORDUM_REASON_TENANT_MCP + 8) ||
              (code >= CORDUM_REASON_EFF_MCP && code < CORDUM_REASON_EFF_MCP + 8)) {
     uint32_t k = code >= CORDUM_REASON_EFF_MCP ? code - CORDUM_REASON_EFF_MCP : code - CORDUM_REASON_TENANT_MCP;
     int f = (int)(k >> 1);
-    // canonical (trimmed, ASCII-lowered) form of the value; the Go adapter substitutes the
-    // request's own spelling, which it still holds
-    std::string v = e->host->mcp_value_string(f, b->hr.job[b->hr.slot_of[job]].mcp[f]);
-    s = std::string("mcp ") + fields[f] + " " + go_quote(v) + ((k & 1) ? " not allowed" : " denied");
+    // %q of the request's own spelling (safety_policy.go:410,413) when the caller still holds the envelopes; without
+    // them, the canonical (trimmed, case-folded) form the dictionaries keep
+    std::string v = env ? cordum::mcp_request_value(env, job, f)
+                        : e->host->mcp_value_string(f, b->hr.job[b->hr.slot_of[job]].mcp[f]);
+    s = std::string("mcp ") + fields[f] + " " + cordum::go_quote(v) + ((k & 1) ? " not allowed" : " denied");
   }
   return copy_out(s, buf, cap);
 }
@@ -1539,9 +1540,9 @@ void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len) {
   *off = t.empty() ? 0 : (uint64_t)(t.data() - s);
   *len = t.size();
 }
-/* canonical forms the table compiler uses: kind 0 = strings.EqualFold class of the string (no trim), 1 = strings.ToLower */
+/* canonical forms the table compiler uses: kind 0 = strings.EqualFold class of the string (no trim), 1 = strings.ToLower, 2 = strconv.Quote */
 int64_t cordum_test_canon(int32_t kind, const char* s, uint64_t n, char* buf, uint64_t cap) {
-  std::string o = kind == 0 ? cordum::fold_str(sv(s, n)) : cordum::lower_copy(sv(s, n));
+  std::string o = kind == 0 ? cordum::fold_str(sv(s, n)) : kind == 1 ? cordum::lower_copy(sv(s, n)) : cordum::go_quote(sv(s, n));
   if (buf && cap) std::memcpy(buf, o.data(), std::min<size_t>(o.size(), cap));
   return (int64_t)o.size();
 }

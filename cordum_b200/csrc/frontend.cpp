@@ -175,8 +175,8 @@ void cordum_frontend::run(Lane& L) {
       }
       // kernel.go:198-215: allow and allow_with_constraints drop the reason
       if (r->rec.reason_code != CORDUM_REASON_NONE && r->rec.decision != CORDUM_DEC_ALLOW && r->rec.decision != CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)
-        cordum_reason(eng, L.batch, j, r->reason, sizeof r->reason);
-      else if (r->rec.reason_code == CORDUM_REASON_APPROVAL_GRANTED) cordum_reason(eng, L.batch, j, r->reason, sizeof r->reason);
+        cordum_reason_flavor(eng, L.batch, j, CORDUM_REASON_FLAVOR_KERNEL, L.env, r->reason, sizeof r->reason);   // the request's own spelling in %q
+      else if (r->rec.reason_code == CORDUM_REASON_APPROVAL_GRANTED) cordum_reason_flavor(eng, L.batch, j, CORDUM_REASON_FLAVOR_KERNEL, L.env, r->reason, sizeof r->reason);   // the request's own spelling in %q
       if (r->rec.route_status == CORDUM_ROUTE_OK || r->rec.route_status == CORDUM_ROUTE_OK_PREFERRED)
         cordum_subject(eng, L.batch, j, r->subject, sizeof r->subject);
     }

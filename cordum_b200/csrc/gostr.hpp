@@ -10,6 +10,7 @@
 //   strings.ToLower     (strategy_least_loaded.go:250,256; kernel.go:403) -> unicode.ToLower per rune (a different
 //                       canonical form: U+017F lower-cases to itself)
 //   path.Match          (safety_policy.go:361; kernel.go:482)
+//   fmt %q / strconv.Quote  (safety_policy.go:410,413 MCP reasons, :235 tenant reasons; gateway/policy_bundles.go:1207,1211)
 // Implementation is independent of oracle/ (different algorithms on purpose): globs are
 // compiled once into element lists and matched with single-star backtracking.
 // Tables: common/go_unicode_tables.h (generated from the Unicode Character Database, tools/gen_go_unicode.py).
@@ -140,6 +141,51 @@ inline std::string lower_copy(sv s) {
 }
 // strings.ToLower(strings.TrimSpace(s))
 inline std::string lower_key(sv s) { return lower_copy(trim_space(s)); }
+
+// strconv.IsPrint: letters, marks, numbers, punctuation, symbols and the ASCII space (Unicode 15.0.0 as go1.24).
+inline bool go_is_print(uint32_t r) {
+  if (r < 0x7F) return r >= 0x20;
+  uint32_t lo = 0, hi = kGoPrintCount;   // first range whose end is >= r
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (kGoPrint[mid].to < r) lo = mid + 1; else hi = mid;
+  }
+  return lo < kGoPrintCount && kGoPrint[lo].from <= r;
+}
+// strconv.Quote (what fmt's %q prints for a string): printable runes pass, `"` and `\` get a backslash, the seven C
+// escapes are named, other control bytes and undecodable bytes are \xhh, the remaining runes \uhhhh / \Uhhhhhhhh.
+inline std::string go_quote(sv s) {
+  static const char* hex = "0123456789abcdef";
+  std::string o = "\"";
+  const unsigned char* p = (const unsigned char*)s.data();
+  for (size_t i = 0; i < s.size();) {
+    int w;
+    uint32_t r = utf8_next(p + i, s.size() - i, w);
+    if (w == 1 && r == 0xFFFD) {   // a byte that starts no valid sequence
+      o += "\\x"; o.push_back(hex[p[i] >> 4]); o.push_back(hex[p[i] & 15]);
+      ++i;
+      continue;
+    }
+    i += (size_t)w;
+    if (r == '"' || r == '\\') { o.push_back('\\'); o.push_back((char)r); continue; }
+    if (go_is_print(r)) { utf8_append(o, r); continue; }
+    switch (r) {
+      case 7: o += "\\a"; continue;
+      case 8: o += "\\b"; continue;
+      case 12: o += "\\f"; continue;
+      case 10: o += "\\n"; continue;
+      case 13: o += "\\r"; continue;
+      case 9: o += "\\t"; continue;
+      case 11: o += "\\v"; continue;
+      default: break;
+    }
+    if (r < 0x20 || r == 0x7F) { o += "\\x"; o.push_back(hex[r >> 4]); o.push_back(hex[r & 15]); }
+    else if (r < 0x10000) { o += "\\u"; for (int sh = 12; sh >= 0; sh -= 4) o.push_back(hex[(r >> sh) & 15]); }
+    else { o += "\\U"; for (int sh = 28; sh >= 0; sh -= 4) o.push_back(hex[(r >> sh) & 15]); }
+  }
+  o.push_back('"');
+  return o;
+}
 inline bool starts_with(sv s, sv p) { return s.size() >= p.size() && s.compare(0, p.size(), p) == 0; }
 
 // ------------------------------------------------------------------ compiled glob

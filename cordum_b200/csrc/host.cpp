@@ -154,13 +154,6 @@ bool constraints_nonempty(const mjson::Value* c) {
   return false;
 }
 
-std::string go_quote(sv s) {   // fmt %q for the printable-ASCII strings that occur in policies
-  std::string o = "\"";
-  for (char c : s) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
-  o.push_back('"');
-  return o;
-}
-
 }  // namespace
 
 // ============================================================ document parsing
@@ -1367,7 +1360,24 @@ inline int mcp_key(sv k) {
   for (int i = 0; i < 12; ++i) if (k == names[i]) return i;
   return -1;
 }
+
 }  // namespace
+
+// extractMCPRequest's value of one field for one envelope, spelled as the request spells it (kernel.go:395-414):
+// the first alias whose value is non-blank, trimmed; the action lower-cased.  What the %q of an MCP reason prints.
+std::string mcp_request_value(const cordum_envelopes* env, uint32_t j, int field) {
+  if (!env || j >= env->n_jobs || !env->label_off) return std::string();
+  sv pick[3];
+  for (uint32_t k = env->label_off[j]; k < env->label_off[j + 1]; ++k) {
+    const cordum_str &ks = env->label_keys[k], &vs = env->label_vals[k];
+    int mk = mcp_key(sv((const char*)env->arena + ks.off, ks.len));
+    if (mk >= 0 && mk / 3 == field) pick[mk % 3] = trim_space(sv((const char*)env->arena + vs.off, vs.len));   // later entry wins
+  }
+  for (const sv& v : pick)
+    if (!v.empty()) return field == 3 ? lower_copy(v) : std::string(v);
+  return std::string();
+}
+
 
 uint32_t Host::resolve_topic(const cordum_envelopes* env, uint32_t j, EncodeCaches& cc) const {
   // dictionary keyed by the RAW string: policy sees TrimSpace(topic), routing the raw one

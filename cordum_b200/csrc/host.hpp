@@ -293,6 +293,9 @@ class WorkPool {
   bool stop_ = false;
 };
 
+// extractMCPRequest's value of one field (0 server, 1 tool, 2 resource, 3 action) as the request spells it (kernel.go:395-414)
+std::string mcp_request_value(const cordum_envelopes* env, uint32_t job, int field);
+
 class Host {
  public:
   Host(uint32_t max_topics, uint32_t max_effcfgs, uint32_t encode_threads);

@@ -119,13 +119,19 @@ class Batch:
         self.eng._ck(self.L.cordum_batch_kernel_times(self.h, C.byref(p), C.byref(r)))
         return p.value, r.value
 
-    def _text(self, fn, job: int) -> str:
+    def _text(self, fn, job: int, *extra) -> str:
         buf = C.create_string_buffer(4096)
-        fn(self.eng.h, self.h, job, buf, len(buf))
+        n = fn(self.eng.h, self.h, job, *extra, buf, len(buf))
+        if n >= len(buf):
+            buf = C.create_string_buffer(n + 1)
+            fn(self.eng.h, self.h, job, *extra, buf, len(buf))
         return buf.value.decode("utf-8", "replace")
 
-    def reason(self, job: int) -> str:
-        return self._text(self.L.cordum_reason, job)
+    def reason(self, job: int, flavor: int = wire.REASON_FLAVOR_KERNEL) -> str:
+        """The reason string of the reference for this job's record, byte for byte.  flavor REASON_FLAVOR_GATEWAY: as the gateway's evaluatePolicyCheck words it (policy_bundles.go:1207,1211)."""
+        env = getattr(self, "_env", None)   # the request's own spelling of an MCP value needs the envelopes
+        addr = env.address if env is not None and getattr(env, "n_jobs", self.size) == self.size else None
+        return self._text(self.L.cordum_reason_flavor, job, flavor, addr)
 
     def subject(self, job: int) -> str:
         return self._text(self.L.cordum_subject, job)

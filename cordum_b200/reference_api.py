@@ -5,6 +5,8 @@ tests read like the reference's own:
 
   SafetyKernelServer.{check,evaluate,explain,simulate,list_snapshots}
         safetykernel.(*server).{Check,Evaluate,Explain,Simulate,ListSnapshots}  kernel.go:106-127
+  GatewayPolicyEvaluator.evaluate_policy_check(policy, snapshot, req)
+        gateway.evaluatePolicyCheck (draft-bundle / pack policy simulation)        gateway/policy_bundles.go:1132-1231
   SafetyClient.check(job_request)            scheduler.(*SafetyClient).Check       safety_client.go:68-115
   extract_tenant(job_request)                scheduler.ExtractTenant               tenant.go:8-21
   LeastLoadedStrategy.{pick_subject,update_routing,current_routing}                strategy_least_loaded.go:21-136
@@ -18,6 +20,7 @@ go/ do the same work in the reference's own language.
 """
 from __future__ import annotations
 
+import json as _json
 import time
 
 import numpy as np
@@ -97,7 +100,7 @@ class SafetyKernelServer:
     def list_snapshots(self) -> list[str]:
         return self.engine.snapshots()
 
-    def evaluate_batch(self, requests: list[dict]) -> list[dict]:
+    def evaluate_batch(self, requests: list[dict], *, flavor: int = wire.REASON_FLAVOR_KERNEL, snapshot: str | None = None) -> list[dict]:
         n = len(requests)
         if n == 0:
             return []
@@ -107,7 +110,8 @@ class SafetyKernelServer:
             self._batch = self.engine.batch(max(n, 256))
         b = self._batch
         recs = b.encode([_envelope(r) for r in requests]).dispatch(wire.MODE_POLICY_ONLY)
-        snapshot = self.engine.current_snapshot()   # s.snapshot (kernel.go:243): "" when the policy in force has none
+        if snapshot is None:
+            snapshot = self.engine.current_snapshot()   # s.snapshot (kernel.go:243): "" when the policy in force has none
         out = []
         for j, (req, rec) in enumerate(zip(requests, recs)):
             flags = int(rec["flags"])
@@ -116,7 +120,8 @@ class SafetyKernelServer:
             approval = bool(flags & wire.F_APPROVAL_REQUIRED)
             out.append({
                 "decision": DECISION_NAMES[int(rec["decision"])],
-                "reason": b.reason(j),
+                "reason": b.reason(j, flavor),
+                "reason_code": int(rec["reason_code"]),                         # not a proto field: the record's own code
                 "policy_snapshot": snapshot if has_snapshot else "",
                 "rule_id": self.engine.rule_id(rule_idx) if rule_idx >= 0 else "",
                 "constraints": self.engine.rule_constraints(rule_idx) if flags & wire.F_CONSTRAINTS else None,
@@ -130,6 +135,61 @@ class SafetyKernelServer:
         return self.evaluate_batch([req])[0]
 
     evaluate = explain = simulate = check
+
+
+class GatewayPolicyEvaluator:
+    """gateway.evaluatePolicyCheck (gateway/policy_bundles.go:1132-1231): the gateway's own copy of the evaluator, which
+    it runs against a policy that is NOT the one in force - the published bundles with one bundle swapped for a draft
+    (handleSimulatePolicyBundle, :322-368).  Decisions are those of the safety kernel; the effective-config reasons
+    print the topic with %q instead of '%s' (:1207,:1211), and the early topic denials carry no snapshot (:1154-1159).
+
+    A draft policy is compiled into a scratch engine of its own (a table compile + upload, milliseconds), so simulating
+    never touches the tables the live SafetyKernelServer dispatches from."""
+
+    def __init__(self, device: int = 0):
+        self._server = SafetyKernelServer(device=device)
+        self._loaded = None
+
+    def _load(self, policy):
+        doc = policy if policy is not None else {}      # nil policy: every job allowed unless the topic is bad
+        key = doc if isinstance(doc, (str, bytes)) else _json.dumps(doc, sort_keys=True)
+        if key != self._loaded:
+            self._server.set_policy(doc, "")
+            self._loaded = key
+
+    def evaluate_batch(self, policy, snapshot: str, requests: list[dict]) -> list[dict]:
+        self._load(policy)
+        out = self._server.evaluate_batch(requests, flavor=wire.REASON_FLAVOR_GATEWAY, snapshot=snapshot)
+        for r in out:
+            if r["reason_code"] in (wire.REASON_MISSING_TOPIC, wire.REASON_UNSUPPORTED_TOPIC):
+                r["policy_snapshot"] = ""           # returned before the snapshot is attached (:1154-1159)
+            else:
+                r["policy_snapshot"] = snapshot     # :1221, unconditional
+        return out
+
+    def evaluate_policy_check(self, policy, snapshot: str, req: dict) -> dict:
+        return self.evaluate_batch(policy, snapshot, [req])[0]
+
+
+def pack_simulation_request(test_request: dict, pack_id: str, default_tenant: str = DEFAULT_TENANT, auth: dict | None = None) -> dict:
+    """The PolicyCheckRequest runPolicySimulation builds from a pack's policy-simulation test (gateway/packs.go:1725-1760)
+    before it calls safetyClient.Simulate: tenant / actor come from the caller's auth when present, pack_id and tenant
+    default to the pack's and the gateway's."""
+    if not test_request.get("topic"):
+        raise ValueError("policy simulation missing topic")                      # :1726-1728
+    tenant = test_request.get("tenant_id", "")
+    meta = {"tenant_id": tenant, "capability": test_request.get("capability", ""),
+            "risk_tags": list(test_request.get("risk_tags") or []), "requires": list(test_request.get("requires") or []),
+            "pack_id": test_request.get("pack_id", ""), "actor_id": test_request.get("actor_id", ""),
+            "actor_type": test_request.get("actor_type", "")}
+    if auth:
+        if auth.get("tenant"):
+            tenant = meta["tenant_id"] = auth["tenant"]
+        if auth.get("principal_id") and not meta["actor_id"]:
+            meta["actor_id"] = auth["principal_id"]
+    meta["pack_id"] = meta["pack_id"] or pack_id
+    meta["tenant_id"] = meta["tenant_id"] or default_tenant
+    return {"topic": test_request["topic"], "tenant": tenant, "meta": meta}
 
 
 class SafetyClient:

@@ -139,6 +139,7 @@ F_APPROVAL_REQUIRED, F_HAS_SNAPSHOT, F_CONSTRAINTS, F_TIE, F_APPROVED_BYPASS = 0
  ROUTE_NO_POOL_TOPIC, ROUTE_NO_POOL_REQUIRES, ROUTE_NO_WORKERS, ROUTE_POOL_OVERLOADED) = range(9)
 MODE_POLICY_ONLY, MODE_POLICY_AND_ROUTE, MODE_ROUTE_ONLY = 1, 2, 3
 FLAG_FLUSH_L2 = 0x100
+REASON_FLAVOR_KERNEL, REASON_FLAVOR_GATEWAY = 0, 1   # cordum_reason_flavor
 FLAG_NO_TIMING = 0x200
 REASON_NONE, REASON_RULE, REASON_MISSING_TOPIC, REASON_UNSUPPORTED_TOPIC, REASON_TENANT_MCP = 0, 1, 2, 3, 4
 REASON_EFF_DENIED_TOPIC, REASON_EFF_NOT_ALLOWED_TOPIC, REASON_EFF_MCP, REASON_APPROVAL_GRANTED = 12, 13, 14, 22

@@ -329,6 +329,17 @@ int32_t cordum_batch_kernel_times(const cordum_batch* b, float* policy_ms, float
  * into buf (truncating to cap) and returns the full length. */
 int64_t cordum_rule_id(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
 int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap);
+/* The reference evaluates a policy check in two places with the same code but one differing format verb in the
+ * effective-config reasons: the safety kernel prints the topic as '%s' (kernel.go:221,225), the gateway's
+ * evaluatePolicyCheck — used by bundle / pack policy simulation against a draft policy — as %q
+ * (gateway/policy_bundles.go:1207,1211; strconv.Quote semantics).  cordum_reason == flavor KERNEL, env NULL.
+ * env: the envelopes the batch was encoded from, or NULL.  The job record keeps an MCP value as the id of its
+ * case-folded form, so without the envelopes an MCP reason quotes that canonical spelling ("evil"); with them it
+ * quotes the request's own, as the reference does (safety_policy.go:410,413: %q of the trimmed label value). */
+#define CORDUM_REASON_FLAVOR_KERNEL 0
+#define CORDUM_REASON_FLAVOR_GATEWAY 1
+int64_t cordum_reason_flavor(cordum_engine* e, const cordum_batch* b, uint32_t job, uint32_t flavor,
+                             const cordum_envelopes* env, char* buf, uint64_t cap);
 int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap);
 /* JSON of rules[rule_idx].constraints / .remediations as loaded (kernel.go:244,247). */
 int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap);
@@ -399,7 +410,7 @@ uint64_t cordum_launch_count(cordum_engine* e);
 int32_t cordum_test_glob(const char* pat, uint64_t plen, const char* name, uint64_t nlen); /* 1, 0, -1 malformed */
 void cordum_test_trim(const char* s, uint64_t n, uint64_t* off, uint64_t* len);
 int32_t cordum_test_normalize_decision(const char* s, uint64_t n);
-int64_t cordum_test_canon(int32_t kind, const char* s, uint64_t n, char* buf, uint64_t cap); /* 0: EqualFold class form, 1: strings.ToLower */
+int64_t cordum_test_canon(int32_t kind, const char* s, uint64_t n, char* buf, uint64_t cap); /* 0: EqualFold class form, 1: strings.ToLower, 2: strconv.Quote */
 int32_t cordum_test_parse_effective(const char* s, uint64_t n, uint32_t* n_allowed, uint32_t* n_denied);
 
 #ifdef __cplusplus

@@ -231,6 +231,57 @@ std::string to_lower(sv s) {
   return o;
 }
 
+// strconv.Quote (go1.24 strconv/quote.go appendQuotedWith / appendEscapedRune with quote '"', ASCIIonly and graphicOnly
+// false).  IsPrint is looked up in the generated Unicode 15.0.0 range list (common/go_unicode_tables.h).
+bool is_print_rune(uint32_t r) {
+  for (uint32_t i = 0; i < kGoPrintCount; ++i) {
+    if (r < kGoPrint[i].from) return false;
+    if (r <= kGoPrint[i].to) return true;
+  }
+  return false;
+}
+std::string strconv_quote(sv s) {
+  const char* lowerhex = "0123456789abcdef";
+  std::string buf;
+  buf.push_back('"');
+  for (int width = 0; !s.empty(); s.remove_prefix(width)) {
+    uint32_t r = (unsigned char)s[0];
+    width = 1;
+    if (r >= 0x80) r = decode_rune(s, width);
+    if (width == 1 && r == kRuneError) {
+      buf += "\\x";
+      buf.push_back(lowerhex[(unsigned char)s[0] >> 4]);
+      buf.push_back(lowerhex[(unsigned char)s[0] & 0xF]);
+      continue;
+    }
+    if (r == '"' || r == '\\') { buf.push_back('\\'); buf.push_back((char)r); continue; }
+    if (is_print_rune(r)) { append_rune(buf, r); continue; }
+    switch (r) {
+      case '\a': buf += "\\a"; break;
+      case '\b': buf += "\\b"; break;
+      case '\f': buf += "\\f"; break;
+      case '\n': buf += "\\n"; break;
+      case '\r': buf += "\\r"; break;
+      case '\t': buf += "\\t"; break;
+      case '\v': buf += "\\v"; break;
+      default:
+        if (r < ' ' || r == 0x7f) {
+          buf += "\\x";
+          buf.push_back(lowerhex[(r >> 4) & 0xF]);
+          buf.push_back(lowerhex[r & 0xF]);
+        } else if (r < 0x10000) {
+          buf += "\\u";
+          for (int sh = 12; sh >= 0; sh -= 4) buf.push_back(lowerhex[(r >> sh) & 0xF]);
+        } else {
+          buf += "\\U";
+          for (int sh = 28; sh >= 0; sh -= 4) buf.push_back(lowerhex[(r >> sh) & 0xF]);
+        }
+    }
+  }
+  buf.push_back('"');
+  return buf;
+}
+
 bool has_prefix(sv s, sv p) { return s.size() >= p.size() && s.substr(0, p.size()) == p; }
 
 // ------------------------------------------------------------------ path.Match
@@ -498,15 +549,7 @@ std::string mcp_reason(int code, const MCPRequest& r) {   // code = mcp_allowed(
   bool not_allowed = k & 1;
   static const char* names[4] = {"server", "tool", "resource", "action"};
   const std::string* vals[4] = {&r.server, &r.tool, &r.resource, &r.action};
-  // fmt %q: Go-quoted string.  Values here are label text; quote like strconv.Quote for
-  // printable ASCII (escape \ and "); other bytes are passed through (tests use ASCII).
-  std::string q = "\"";
-  for (char c : *vals[field]) {
-    if (c == '"' || c == '\\') q.push_back('\\');
-    q.push_back(c);
-  }
-  q.push_back('"');
-  return std::string("mcp ") + names[field] + " " + q + (not_allowed ? " not allowed" : " denied");
+  return std::string("mcp ") + names[field] + " " + strconv_quote(*vals[field]) + (not_allowed ? " not allowed" : " denied");   // %q
 }
 
 // :259-294
@@ -535,10 +578,7 @@ std::vector<PolicyRule> legacy_rules(const SafetyPolicy& p) {
       PolicyRule r;
       r.id = "legacy:" + tenant + ":deny:" + std::to_string(i + 1);
       r.decision = "deny";
-      std::string q = "\"";
-      for (char c : tp.deny_topics[i]) { if (c == '"' || c == '\\') q.push_back('\\'); q.push_back(c); }
-      q.push_back('"');
-      r.reason = "topic " + q + " denied by tenant policy";
+      r.reason = "topic " + strconv_quote(tp.deny_topics[i]) + " denied by tenant policy";   // %q, safety_policy.go:235
       r.match.tenants = {tenant};
       r.match.topics = {tp.deny_topics[i]};
       r.match.mcp = tp.mcp;
@@ -1008,6 +1048,7 @@ bool secrets_present(const PolicyMeta& meta, const LabelMap& labels) {
 }
 
 struct FullResult {
+  bool gateway = false;   // in: evaluate as gateway/policy_bundles.go:1132-1231 does (reason verbs %q), not kernel.go
   cordum_decision rec;
   std::string reason, rule_id, subject, route_error;
 };
@@ -1025,6 +1066,7 @@ const char* dec_name(int d) {
 
 // kernel.go:129-257
 void kernel_evaluate(const oracle_ctx* ctx, const JobView& v, FullResult& out, bool want_strings) {
+  const bool gateway = out.gateway;
   cordum_decision& rec = out.rec;
   int decision = CORDUM_DEC_ALLOW;
   std::string reason;
@@ -1100,12 +1142,14 @@ void kernel_evaluate(const oracle_ctx* ctx, const JobView& v, FullResult& out, b
   if (parse_effective_safety(v.effcfg, eff)) {
     if (match_any(eff.denied_topics, topic)) {
       decision = CORDUM_DEC_DENY;
-      reason = "topic '" + topic + "' denied by effective config";
+      reason = gateway ? "topic " + strconv_quote(topic) + " denied by effective config"   // policy_bundles.go:1207
+                       : "topic '" + topic + "' denied by effective config";
       reason_code = CORDUM_REASON_EFF_DENIED_TOPIC;
     }
     if (!eff.allowed_topics.empty() && !match_any(eff.allowed_topics, topic)) {
       decision = CORDUM_DEC_DENY;
-      reason = "topic '" + topic + "' not allowed by effective config";
+      reason = gateway ? "topic " + strconv_quote(topic) + " not allowed by effective config"   // policy_bundles.go:1211
+                       : "topic '" + topic + "' not allowed by effective config";
       reason_code = CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC;
     }
     if (int c = mcp_allowed(eff.mcp, in.mcp)) {
@@ -1348,8 +1392,20 @@ int32_t oracle_eval(oracle_ctx* c, const cordum_envelopes* env, uint32_t first, 
 
 int64_t oracle_eval_one_json(oracle_ctx* c, const cordum_envelopes* env, uint32_t job, uint32_t mode, char* buf,
                              uint64_t cap) {
+  return oracle_eval_one_json_flavor(c, env, job, mode, 0, buf, cap);
+}
+
+int64_t oracle_quote(const char* s, uint64_t n, char* buf, uint64_t cap) {
+  std::string o = strconv_quote(sv(s, n));
+  if (buf && cap) std::memcpy(buf, o.data(), std::min<size_t>(o.size(), cap));
+  return (int64_t)o.size();
+}
+
+int64_t oracle_eval_one_json_flavor(oracle_ctx* c, const cordum_envelopes* env, uint32_t job, uint32_t mode,
+                                    uint32_t flavor, char* buf, uint64_t cap) {
   if (!c || !env || job >= env->n_jobs) return -1;
   FullResult r;
+  r.gateway = flavor == 1;
   eval_job(c, env, job, mode, r, true);
   std::string o = "{";
   o += "\"decision\": \""; o += dec_name(r.rec.decision); o += "\"";

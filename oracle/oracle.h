@@ -45,6 +45,12 @@ int64_t oracle_eval_one_json(oracle_ctx*, const cordum_envelopes* env, uint32_t 
 /* Direct access to the restated string primitives, for differential tests. */
 int32_t oracle_path_match(const char* pat, uint64_t plen, const char* name, uint64_t nlen); /* 1 match, 0 no, -1 ErrBadPattern */
 int32_t oracle_equal_fold(const char* a, uint64_t alen, const char* b, uint64_t blen);
+/* flavor 0: safety kernel (kernel.go:129-257); 1: the gateway's copy of the evaluator used by policy simulation
+ * (gateway/policy_bundles.go:1132-1231) - same decisions, effective-config reasons printed with %q */
+int64_t oracle_eval_one_json_flavor(oracle_ctx*, const cordum_envelopes* env, uint32_t job, uint32_t mode,
+                                    uint32_t flavor, char* buf, uint64_t cap);
+/* strconv.Quote */
+int64_t oracle_quote(const char* s, uint64_t n, char* buf, uint64_t cap);
 int64_t oracle_to_lower(const char* s, uint64_t n, char* buf, uint64_t cap);
 /* writes the trimmed span [*off,*off+*len) */
 void oracle_trim_space(const char* s, uint64_t n, uint64_t* off, uint64_t* len);

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import json
 import struct
+import unicodedata
 
 # ------------------------------------------------------------------ Go strings
 _GO_SPACE = {chr(c) for c in (0x09, 0x0A, 0x0B, 0x0C, 0x0D, 0x20, 0x85, 0xA0, 0x1680, 0x2028, 0x2029, 0x202F, 0x205F, 0x3000)} | {chr(c) for c in range(0x2000, 0x200B)}
@@ -249,8 +250,37 @@ def mcp_used(req) -> bool:   # :404-406
     return any(trim_space(req[f]) != "" for f in MCP_FIELDS)
 
 
-def go_quote(s: str) -> str:   # fmt %q for printable ASCII
-    return '"' + s.replace("\\", "\\\\").replace('"', '\\"') + '"'
+_C_ESCAPES = {7: "\\a", 8: "\\b", 12: "\\f", 10: "\\n", 13: "\\r", 9: "\\t", 11: "\\v"}
+
+
+def go_quote(s) -> str:
+    """fmt %q on a string = strconv.Quote.  IsPrint (letters, marks, numbers, punctuation, symbols, ASCII space) comes
+    from Python's own unicodedata (15.0.0 in this image's CPython 3.12, the version go1.24 uses), not from the generated
+    table the C++ sides share.  A str is taken as valid UTF-8 (lone surrogates = undecodable bytes via surrogateescape);
+    bytes are decoded the way Go ranges over a string."""
+    if isinstance(s, (bytes, bytearray)):
+        s = bytes(s).decode("utf-8", "surrogateescape")
+    out = ['"']
+    for ch in s:
+        r = ord(ch)
+        if 0xDC80 <= r <= 0xDCFF:                       # an undecodable byte
+            out.append("\\x%02x" % (r - 0xDC00))
+        elif ch in '"\\':
+            out.append("\\" + ch)
+        elif r == 0x20 or unicodedata.category(ch)[0] in "LMNPS":
+            out.append(ch)
+        elif r in _C_ESCAPES:
+            out.append(_C_ESCAPES[r])
+        elif r < 0x20 or r == 0x7F:
+            out.append("\\x%02x" % r)
+        elif 0xD800 <= r <= 0xDFFF:                     # cannot come out of a Go string; RuneError
+            out.append("\\ufffd")
+        elif r < 0x10000:
+            out.append("\\u%04x" % r)
+        else:
+            out.append("\\U%08x" % r)
+    out.append('"')
+    return "".join(out)
 
 
 def mcp_allowed(policy, req):   # :385-402 ; returns (ok, reason, code) code = field*2 + notallowed
@@ -525,7 +555,7 @@ def policy_meta(job):   # kernel.go:348-379
     return out
 
 
-def kernel_evaluate(policy, job):   # kernel.go:129-257
+def kernel_evaluate(policy, job, gateway=False):   # kernel.go:129-257; gateway=True: policy_bundles.go:1132-1231
     decision, reason = "ALLOW", ""
     topic = trim_space(job.get("topic", ""))
     tenant = trim_space(job.get("tenant", ""))
@@ -572,9 +602,11 @@ def kernel_evaluate(policy, job):   # kernel.go:129-257
     eff = parse_effective_safety(job.get("effective_config"))
     if eff is not None:
         if match_any(eff["denied_topics"], topic):
-            decision, reason = "DENY", "topic '%s' denied by effective config" % topic
+            decision, reason = "DENY", ("topic %s denied by effective config" % go_quote(topic) if gateway   # :1207
+                                        else "topic '%s' denied by effective config" % topic)
         if len(eff["allowed_topics"]) > 0 and not match_any(eff["allowed_topics"], topic):
-            decision, reason = "DENY", "topic '%s' not allowed by effective config" % topic
+            decision, reason = "DENY", ("topic %s not allowed by effective config" % go_quote(topic) if gateway   # :1211
+                                        else "topic '%s' not allowed by effective config" % topic)
         ok, why, _ = mcp_allowed(eff["mcp"], inp["mcp"])
         if not ok:
             decision, reason = "DENY", why

@@ -58,6 +58,10 @@ def lib():
         L.oracle_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.oracle_eval_one_json.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
         L.oracle_eval_one_json.restype = C.c_int64
+        L.oracle_eval_one_json_flavor.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.oracle_eval_one_json_flavor.restype = C.c_int64
+        L.oracle_quote.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.oracle_quote.restype = C.c_int64
         L.oracle_path_match.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
         L.oracle_equal_fold.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
         L.oracle_to_lower.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
@@ -87,6 +91,14 @@ def to_lower(s) -> bytes:
     s = _b(s)
     buf = C.create_string_buffer(4 * len(s) + 8)
     n = lib().oracle_to_lower(s, len(s), buf, len(buf))
+    return buf.raw[:n]
+
+
+def quote(s) -> bytes:
+    """strconv.Quote"""
+    s = _b(s)
+    buf = C.create_string_buffer(10 * len(s) + 8)
+    n = lib().oracle_quote(s, len(s), buf, len(buf))
     return buf.raw[:n]
 
 
@@ -162,9 +174,10 @@ class Oracle:
         self._check(self.L.oracle_eval(self.h, C.addressof(env.struct), first, count, mode, threads, out.ctypes.data))
         return out[:count]
 
-    def eval_one(self, job, mode=wire.MODE_POLICY_AND_ROUTE) -> dict:
+    def eval_one(self, job, mode=wire.MODE_POLICY_AND_ROUTE, flavor=0) -> dict:
+        """flavor 1 = the gateway's evaluatePolicyCheck (policy_bundles.go:1132-1231)"""
         env = job if isinstance(job, wire.EnvelopeBatch) else wire.EnvelopeBatch.from_jobs([job])
         buf = C.create_string_buffer(1 << 16)
-        n = self.L.oracle_eval_one_json(self.h, C.addressof(env.struct), 0, mode, buf, len(buf))
+        n = self.L.oracle_eval_one_json_flavor(self.h, C.addressof(env.struct), 0, mode, flavor, buf, len(buf))
         assert 0 <= n < len(buf)
         return json.loads(buf.value.decode("utf-8", "replace"))

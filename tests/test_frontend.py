@@ -86,3 +86,23 @@ def test_oversized_request_fails_closed_alone(eng):
     ok = fe.submit(cfg.jobs.to_jobs(0, 1)[0])
     assert ok.status == 0
     fe.close()
+
+
+def test_mcp_reason_quotes_the_requests_own_spelling(eng):
+    """safety_policy.go:410,413 print %q of the label value as the request wrote it (trimmed; the action lower-cased,
+    kernel.go:403); the job record only keeps the id of its case-folded form."""
+    policy = {"default_tenant": "default", "tenants": {"default": {"mcp": {"deny_servers": ["evil.example"], "allow_actions": ["read"]}}}}
+    eng.load_policy(policy, "t")
+    eng.load_routing({"topics": {}, "pools": {}})
+    eng.load_workers([])
+    fe = frontend.Frontend(eng, max_batch=4, max_wait_us=0, mode=wire.MODE_POLICY_ONLY)
+    o = oracle_lib.Oracle(policy, {"topics": {}, "pools": {}}, [])
+    for labels in ({"mcp.server": "  EVIL.Example\t"}, {"mcp.server": "ok", "mcpAction": "WRITE \"x\""}, {"mcp_server": "Evil.EXAMPLE"}):
+        job = {"topic": "job.x", "tenant": "default", "labels": labels}
+        r = fe.submit(job)
+        want = o.eval_one(job, wire.MODE_POLICY_ONLY)
+        assert r.status == 0 and wire.DEC_NAMES[r.rec.decision] == want["decision"] == "DENY"
+        assert r.reason.decode() == want["reason"]
+    assert fe.submit({"topic": "job.x", "labels": {"mcp.server": "  EVIL.Example\t"}}).reason == b'mcp server "EVIL.Example" denied'
+    fe.close()
+    o.close()

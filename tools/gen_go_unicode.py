@@ -15,6 +15,7 @@ documentation of unicode.SimpleFold and strings.EqualFold):
 The generator emulates that walk for every pair of related runes and emits
   kGoFoldRep[]   rune -> canonical representative of its EqualFold class (only where rep != rune)
   kGoLower[]     rune -> simple lowercase mapping (only where != rune)
+  kGoPrint[]     rune ranges strconv.Quote leaves unescaped (strconv.IsPrint)
 It also asserts that the emulated EqualFold relation is an equivalence on every class it emits (the one-directional
 mappings of U+0130 / U+0131 must relate nothing), so "same representative" is exactly "EqualFold".
 """
@@ -46,6 +47,17 @@ for my $p ("Simple_Case_Folding", "Simple_Lowercase_Mapping", "Simple_Uppercase_
   }
   print "]";
 }
+{
+  my ($list, $map, $fmt, $def) = prop_invmap("General_Category");
+  print ",\"gc\":[";
+  for (my $i = 0; $i < @$list; $i++) {
+    my $lo = $list->[$i];
+    my $hi = ($i + 1 < @$list) ? $list->[$i + 1] - 1 : 0x10FFFF;
+    print "," if $i;
+    print "[$lo,$hi,\"" . $map->[$i] . "\"]";
+  }
+  print "]";
+}
 print ",\"version\":\"" . Unicode::UCD::UnicodeVersion() . "\"}";
 '''
 
@@ -61,7 +73,30 @@ def load():
             for cp in range(lo, hi + 1):
                 m[cp] = base + (cp - lo)
         return m
+    global GC
+    GC = d["gc"]
     return expand("Simple_Case_Folding"), expand("Simple_Lowercase_Mapping"), expand("Simple_Uppercase_Mapping")
+
+
+GC = None
+
+
+def print_ranges():
+    """unicode.IsPrint / strconv.IsPrint: categories L, M, N, P, S plus U+0020 (go1.24 unicode/graphic.go: "letters,
+    marks, numbers, punctuation, symbols, and the ASCII space character").  Merged inclusive ranges."""
+    out = []
+    for lo, hi, cat in GC:
+        ok = cat[0] in "LMNPS"
+        if lo <= 0x20 <= hi and not ok:      # the ASCII space sits in a Zs range of its own
+            assert (lo, hi) == (0x20, 0x20), (lo, hi, cat)
+            ok = True
+        if not ok:
+            continue
+        if out and out[-1][1] + 1 == lo:
+            out[-1][1] = hi
+        else:
+            out.append([lo, hi])
+    return out
 
 
 def main():
@@ -167,6 +202,12 @@ def main():
             for i in range(0, len(items), 6):
                 f.write("  " + " ".join("{0x%X,0x%X}," % kv for kv in items[i:i + 6]) + "\n")
             f.write("};\nstatic const uint32_t %sCount = %d;\n\n" % (name, len(items)))
+        pr = print_ranges()
+        f.write("// kGoPrint: inclusive rune ranges for which strconv.IsPrint is true (categories L, M, N, P, S and U+0020)\n"
+                "static const GoRunePair kGoPrint[%d] = {\n" % len(pr))
+        for i in range(0, len(pr), 6):
+            f.write("  " + " ".join("{0x%X,0x%X}," % (a, b) for a, b in pr[i:i + 6]) + "\n")
+        f.write("};\nstatic const uint32_t kGoPrintCount = %d;\n" % len(pr))
     print("wrote %s: %d fold entries, %d lower entries (%d plain 2-orbits)" % (path, len(rep), len(lowers), plain_pairs))
 
 
