@@ -140,6 +140,7 @@ struct cordum_batch {
   cordum_engine* e = nullptr;
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
+  std::string snapshot;          // policy snapshot in force at the last dispatch (read under the same lock as the epoch check)
   bool encoded = false, resident = false, pending = false, enc_inflight = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
@@ -423,7 +424,8 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   std::lock_guard<std::mutex> g(e->mu);
   {
     std::lock_guard<std::mutex> gh(e->host->mutex());
-    if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
+    if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
+    b->snapshot = e->host->current_snapshot();
     int rc = sync_tables(e);
     if (rc) return rc;
     rc = refresh_pools(e, nullptr, nullptr);
@@ -1026,6 +1028,13 @@ int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap) {
   return copy_out(e->host->current_snapshot(), buf, cap);
 }
 
+/* ...and the one a given batch was dispatched under: a reload that lands after the dispatch does not relabel decisions
+ * that were taken under the previous policy (kernel.go:140-147 reads policy and snapshot under one lock) */
+int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap) {
+  if (!b) return -1;
+  return copy_out(b->snapshot, buf, cap);
+}
+
 int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
   return e->host->load_routing(sv(json ? json : "", json ? len : 0), g_err);
@@ -1153,7 +1162,8 @@ int32_t cordum_tick_async(cordum_engine* e, cordum_batch* b, uint32_t mode, cons
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   std::lock_guard<std::mutex> g(e->mu);
   std::lock_guard<std::mutex> gh(e->host->mutex());
-  if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STATE; }
+  if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
+  b->snapshot = e->host->current_snapshot();
   const uint32_t W = e->host->tables().n_slots;
   if (e->peers.ready && e->peers.world > 1) {
     if (first_slot != (uint32_t)e->peers.rank * e->peers.per || n_slice != e->peers.per || e->peers.per * (uint32_t)e->peers.world != W) {

@@ -51,7 +51,7 @@ struct cordum_frontend {
   std::deque<Ticket*> queue;
   bool stop = false;
   std::vector<std::unique_ptr<Lane>> lanes;
-  std::atomic<uint64_t> n_batches{0}, n_requests{0}, n_full{0};
+  std::atomic<uint64_t> n_batches{0}, n_requests{0}, n_full{0}, n_stale_retries{0};
   uint64_t arena_cap = 0;
   uint32_t max_lists = 0;
 
@@ -154,13 +154,20 @@ void cordum_frontend::run(Lane& L) {
     const char* msg = "";
     const bool any = pack(L, items, row);
     if (any) {
-      rc = cordum_encode(eng, L.batch, L.env);
-      if (rc == CORDUM_OK) rc = cordum_dispatch(eng, L.batch, opts.mode);
+      // a policy / routing / registry reload between the two calls makes the encoded ids stale: encode again against
+      // the new tables (the reference's evaluate reads s.policy once under the lock, kernel.go:140-147 - a request
+      // racing a reload is answered under one policy or the other, never refused)
+      for (int attempt = 0; attempt < 4; ++attempt) {
+        rc = cordum_encode(eng, L.batch, L.env);
+        if (rc == CORDUM_OK) rc = cordum_dispatch(eng, L.batch, opts.mode);
+        if (rc != CORDUM_E_STALE) break;
+        n_stale_retries++;
+      }
       if (rc != CORDUM_OK) msg = cordum_last_error();
     }
     const cordum_decision* recs = (any && rc == CORDUM_OK) ? cordum_batch_results(L.batch) : nullptr;
     char snap[sizeof(((cordum_response*)nullptr)->snapshot)] = {0};
-    if (recs) cordum_policy_snapshot(eng, snap, sizeof snap);   // the CURRENT snapshot (kernel.go:243), "" if the policy has none
+    if (recs) cordum_batch_snapshot(L.batch, snap, sizeof snap);   // the snapshot this batch was evaluated under (kernel.go:141,243), "" if that policy has none
     for (size_t i = 0; i < items.size(); ++i) {
       cordum_response* r = items[i]->resp;
       if (row[i] < 0) { fail_closed(r, row[i], "request exceeds the front-end's envelope capacity"); continue; }

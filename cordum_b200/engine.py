@@ -133,6 +133,12 @@ class Batch:
         addr = env.address if env is not None and getattr(env, "n_jobs", self.size) == self.size else None
         return self._text(self.L.cordum_reason_flavor, job, flavor, addr)
 
+    def snapshot(self) -> str:
+        """The policy snapshot the last dispatch of this batch ran under."""
+        buf = C.create_string_buffer(1024)
+        self.L.cordum_batch_snapshot(self.h, buf, len(buf))
+        return buf.value.decode("utf-8", "replace")
+
     def subject(self, job: int) -> str:
         return self._text(self.L.cordum_subject, job)
 

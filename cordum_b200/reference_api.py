@@ -111,7 +111,7 @@ class SafetyKernelServer:
         b = self._batch
         recs = b.encode([_envelope(r) for r in requests]).dispatch(wire.MODE_POLICY_ONLY)
         if snapshot is None:
-            snapshot = self.engine.current_snapshot()   # s.snapshot (kernel.go:243): "" when the policy in force has none
+            snapshot = b.snapshot()   # s.snapshot as read with the policy (kernel.go:141,243): "" when that policy has none
         out = []
         for j, (req, rec) in enumerate(zip(requests, recs)):
             flags = int(rec["flags"])

@@ -37,6 +37,7 @@ extern "C" {
 #define CORDUM_E_CUDA (-3)      /* CUDA runtime / kernel failure (sticky)         */
 #define CORDUM_E_STATE (-4)     /* call order violated (e.g. dispatch before load)*/
 #define CORDUM_E_NODEVICE (-5)  /* no CUDA device: the product has NO CPU path    */
+#define CORDUM_E_STALE (-6)     /* tables were reloaded after the batch was encoded: encode it again and retry */
 
 /* ------------------------------------------------------ wire: string spans */
 typedef struct cordum_str {
@@ -199,6 +200,8 @@ int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint3
 /* The snapshot of the policy in force = PolicyCheckResponse.PolicySnapshot (kernel.go:243): "" when the current policy
  * was loaded without one.  NUL-terminated into buf, returns the full length. */
 int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap);
+/* The snapshot the batch's last dispatch ran under (read under the same lock as the tables it used). */
+int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap);
 
 /* (*LeastLoadedStrategy).UpdateRouting (strategy_least_loaded.go:28-30).
  * routing_json = {"topics": {topic: [pool,...]}, "pools": {pool: {"requires": [...]}}}
