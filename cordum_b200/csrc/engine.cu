@@ -140,7 +140,10 @@ struct cordum_batch {
   cordum_engine* e = nullptr;
   uint32_t max_jobs = 0, n = 0;
   uint64_t epoch = 0;
-  std::string snapshot;          // policy snapshot in force at the last dispatch (read under the same lock as the epoch check)
+  // what the records of the last dispatch index (read under the same lock as the epoch check): rule text + snapshot of
+  // the policy, worker ids of the registry.  Kept by the batch so that a later reload cannot relabel its decisions.
+  std::shared_ptr<const cordum::PolicyText> text;
+  std::shared_ptr<const std::vector<std::string>> wtext;
   bool encoded = false, resident = false, pending = false, enc_inflight = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
@@ -425,7 +428,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   {
     std::lock_guard<std::mutex> gh(e->host->mutex());
     if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
-    b->snapshot = e->host->current_snapshot();
+    b->text = e->host->policy_text(); b->wtext = e->host->worker_text();
     int rc = sync_tables(e);
     if (rc) return rc;
     rc = refresh_pools(e, nullptr, nullptr);
@@ -1032,8 +1035,9 @@ int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap) {
  * that were taken under the previous policy (kernel.go:140-147 reads policy and snapshot under one lock) */
 int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap) {
   if (!b) return -1;
-  return copy_out(b->snapshot, buf, cap);
+  return copy_out(b->text ? b->text->snapshot : std::string(), buf, cap);
 }
+uint64_t cordum_batch_policy_gen(const cordum_batch* b) { return (b && b->text) ? b->text->gen : 0; }
 
 int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
@@ -1163,7 +1167,7 @@ int32_t cordum_tick_async(cordum_engine* e, cordum_batch* b, uint32_t mode, cons
   std::lock_guard<std::mutex> g(e->mu);
   std::lock_guard<std::mutex> gh(e->host->mutex());
   if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
-  b->snapshot = e->host->current_snapshot();
+  b->text = e->host->policy_text(); b->wtext = e->host->worker_text();
   const uint32_t W = e->host->tables().n_slots;
   if (e->peers.ready && e->peers.world > 1) {
     if (first_slot != (uint32_t)e->peers.rank * e->peers.per || n_slice != e->peers.per || e->peers.per * (uint32_t)e->peers.world != W) {
@@ -1446,26 +1450,40 @@ int32_t cordum_batch_fetch(cordum_batch* b) {
 /* raw CUDA stream of a batch (cudaStream_t) so a harness can bracket launches with its own events */
 void* cordum_batch_stream(cordum_batch* b) { return b ? (void*)b->stream : nullptr; }
 
-int64_t cordum_rule_id(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
-  if (!e) return -1;
+namespace {
+// rule text of policy generation `gen` (0 = the policy in force); null when that generation is no longer kept
+const cordum::PolicyText::Rule* rule_text(cordum_engine* e, uint64_t gen, int32_t rule_idx, std::shared_ptr<const cordum::PolicyText>& keep) {
   std::lock_guard<std::mutex> g(e->host->mutex());
-  const auto& rules = e->host->policy().rules;
-  if (rule_idx < 0 || (size_t)rule_idx >= rules.size()) return copy_out(std::string(), buf, cap);
-  return copy_out(rules[rule_idx].id, buf, cap);
+  keep = e->host->policy_text(gen);
+  if (!keep || rule_idx < 0 || (size_t)rule_idx >= keep->rules.size()) return nullptr;
+  return &keep->rules[rule_idx];
 }
-int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
+}  // namespace
+
+int64_t cordum_rule_id_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap) {
   if (!e) return -1;
-  std::lock_guard<std::mutex> g(e->host->mutex());
-  const auto& rules = e->host->policy().rules;
-  if (rule_idx < 0 || (size_t)rule_idx >= rules.size() || !rules[rule_idx].has_constraints) return copy_out(std::string(), buf, cap);
-  return copy_out(rules[rule_idx].constraints_json, buf, cap);
+  std::shared_ptr<const cordum::PolicyText> keep;
+  const auto* r = rule_text(e, gen, rule_idx, keep);
+  return copy_out(r ? r->id : std::string(), buf, cap);
+}
+int64_t cordum_rule_constraints_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::shared_ptr<const cordum::PolicyText> keep;
+  const auto* r = rule_text(e, gen, rule_idx, keep);
+  return copy_out((r && r->has_constraints) ? r->constraints_json : std::string(), buf, cap);
+}
+int64_t cordum_rule_remediations_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap) {
+  if (!e) return -1;
+  std::shared_ptr<const cordum::PolicyText> keep;
+  const auto* r = rule_text(e, gen, rule_idx, keep);
+  return copy_out(r ? r->remediations_json : std::string(), buf, cap);
+}
+int64_t cordum_rule_id(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) { return cordum_rule_id_at(e, 0, rule_idx, buf, cap); }
+int64_t cordum_rule_constraints_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
+  return cordum_rule_constraints_json_at(e, 0, rule_idx, buf, cap);
 }
 int64_t cordum_rule_remediations_json(cordum_engine* e, int32_t rule_idx, char* buf, uint64_t cap) {
-  if (!e) return -1;
-  std::lock_guard<std::mutex> g(e->host->mutex());
-  const auto& rules = e->host->policy().rules;
-  if (rule_idx < 0 || (size_t)rule_idx >= rules.size()) return copy_out(std::string(), buf, cap);
-  return copy_out(rules[rule_idx].remediations_json, buf, cap);
+  return cordum_rule_remediations_json_at(e, 0, rule_idx, buf, cap);
 }
 
 int64_t cordum_reason(cordum_engine* e, const cordum_batch* b, uint32_t job, char* buf, uint64_t cap) {
@@ -1482,8 +1500,8 @@ int64_t cordum_reason_flavor(cordum_engine* e, const cordum_batch* b, uint32_t j
   std::string s;
   static const char* fields[4] = {"server", "tool", "resource", "action"};
   if (code == CORDUM_REASON_RULE) {
-    const auto& rules = e->host->policy().rules;
-    if (r.rule_idx >= 0 && (size_t)r.rule_idx < rules.size()) s = rules[r.rule_idx].reason;
+    // the policy the batch was dispatched under, not whatever is in force by now
+    if (b->text && r.rule_idx >= 0 && (size_t)r.rule_idx < b->text->rules.size()) s = b->text->rules[r.rule_idx].reason;
   } else if (code == CORDUM_REASON_MISSING_TOPIC) s = "missing topic";
   else if (code == CORDUM_REASON_UNSUPPORTED_TOPIC) s = "unsupported topic";
   else if (code == CORDUM_REASON_APPROVAL_GRANTED) s = "approval granted";
@@ -1498,6 +1516,7 @@ int64_t cordum_reason_flavor(cordum_engine* e, const cordum_batch* b, uint32_t j
     int f = (int)(k >> 1);
     // %q of the request's own spelling (safety_policy.go:410,413) when the caller still holds the envelopes; without
     // them, the canonical (trimmed, case-folded) form the dictionaries keep
+    if (!env && b->epoch != e->host->epoch()) return -1;   // the value dictionaries were rebuilt since: only the envelopes still know
     std::string v = env ? cordum::mcp_request_value(env, job, f)
                         : e->host->mcp_value_string(f, b->hr.job[b->hr.slot_of[job]].mcp[f]);
     s = std::string("mcp ") + fields[f] + " " + cordum::go_quote(v) + ((k & 1) ? " not allowed" : " denied");
@@ -1511,9 +1530,9 @@ int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, ch
   std::lock_guard<std::mutex> g(e->host->mutex());
   const cordum_decision& r = b->h_out[job];
   std::string s;
-  if ((r.route_status == CORDUM_ROUTE_OK || r.route_status == CORDUM_ROUTE_OK_PREFERRED) && r.worker_slot >= 0 &&
-      (uint32_t)r.worker_slot < e->host->n_worker_slots()) {
-    const std::string& id = e->host->worker_id((uint32_t)r.worker_slot);
+  if ((r.route_status == CORDUM_ROUTE_OK || r.route_status == CORDUM_ROUTE_OK_PREFERRED) && r.worker_slot >= 0 && b->wtext &&
+      (size_t)r.worker_slot < b->wtext->size()) {
+    const std::string& id = (*b->wtext)[(size_t)r.worker_slot];   // the registry the batch was dispatched against
     s = id.empty() ? e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic) : "worker." + id + ".jobs";   // bus/nats.go:94-99; :131-135
   }
   return copy_out(s, buf, cap);

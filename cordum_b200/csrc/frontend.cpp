@@ -167,6 +167,7 @@ void cordum_frontend::run(Lane& L) {
     }
     const cordum_decision* recs = (any && rc == CORDUM_OK) ? cordum_batch_results(L.batch) : nullptr;
     char snap[sizeof(((cordum_response*)nullptr)->snapshot)] = {0};
+    const uint64_t gen = recs ? cordum_batch_policy_gen(L.batch) : 0;
     if (recs) cordum_batch_snapshot(L.batch, snap, sizeof snap);   // the snapshot this batch was evaluated under (kernel.go:141,243), "" if that policy has none
     for (size_t i = 0; i < items.size(); ++i) {
       cordum_response* r = items[i]->resp;
@@ -176,9 +177,10 @@ void cordum_frontend::run(Lane& L) {
       std::memset(r, 0, sizeof *r);
       r->status = CORDUM_OK;
       r->rec = recs[j];
+      r->policy_gen = gen;
       if (r->rec.flags & CORDUM_F_HAS_SNAPSHOT) {   // kernel.go:239-248: the early DENY returns carry neither snapshot nor rule id
         std::memcpy(r->snapshot, snap, sizeof snap);
-        cordum_rule_id(eng, r->rec.rule_idx, r->rule_id, sizeof r->rule_id);
+        cordum_rule_id_at(eng, gen, r->rec.rule_idx, r->rule_id, sizeof r->rule_id);
       }
       // kernel.go:198-215: allow and allow_with_constraints drop the reason
       if (r->rec.reason_code != CORDUM_REASON_NONE && r->rec.decision != CORDUM_DEC_ALLOW && r->rec.decision != CORDUM_DEC_ALLOW_WITH_CONSTRAINTS)

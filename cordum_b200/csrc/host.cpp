@@ -557,6 +557,7 @@ void Host::compile_policy() {
   d_req_.clear();
   tenant_pol_.clear(); label_key_.clear(); label_key_pairs_.clear(); label_empty_mask_ = 0;
   patterns_.clear();
+  pat_by_prefix_.clear();
   default_tenant_trim_ = std::string(trim_space(policy_.default_tenant));
   for (size_t i = 0; i < policy_.tenants.size(); ++i) tenant_pol_.put(policy_.tenants[i].name, (uint32_t)i + 1);
 
@@ -660,6 +661,11 @@ void Host::compile_policy() {
       auto it = idx.find(std::string(pt));
       if (it == idx.end()) {
         it = idx.emplace(std::string(pt), (uint32_t)patterns_.size()).first;
+        // index by literal prefix (the bytes before the first metacharacter): a topic can only match patterns whose
+        // literal prefix is a prefix of it, which turns 4k patterns x 2k topics of glob matching into a few per topic
+        size_t lit = 0;
+        while (lit < pt.size() && pt[lit] != '*' && pt[lit] != '?' && pt[lit] != '[' && pt[lit] != '\\') ++lit;
+        pat_by_prefix_[std::string(pt.substr(0, lit))].push_back((uint32_t)patterns_.size());
         patterns_.push_back(Pattern{Glob(pt), {}});
       }
       patterns_[it->second].rules.push_back(p);   // bit positions
@@ -882,9 +888,17 @@ void Host::compile_mcp_tables() {
 // ------------------------------------------------------------ topics
 void Host::topic_row(sv trimmed, Bits& out) const {
   out = vac_topic_;
-  for (auto& p : patterns_)
-    if (p.glob.match(trimmed))
-      for (uint32_t r : p.rules) out[r >> 5] |= 1u << (r & 31);
+  std::string key;
+  for (size_t len = 0; len <= trimmed.size(); ++len) {
+    key.assign(trimmed.data(), len);
+    auto it = pat_by_prefix_.find(key);
+    if (it == pat_by_prefix_.end()) continue;
+    for (uint32_t pi : it->second) {
+      const Pattern& p = patterns_[pi];
+      if (p.glob.match(trimmed))
+        for (uint32_t r : p.rules) out[r >> 5] |= 1u << (r & 31);
+    }
+  }
 }
 
 void Host::eff_topic_fill(uint32_t cfg, uint32_t topic_id) {
@@ -945,8 +959,14 @@ void Host::rebuild_topics() {
     for (uint32_t k = 0; k < nth; ++k) ts.emplace_back(work);
     for (auto& th : ts) th.join();
   }
+  static const bool trace = getenv("CORDUM_LOAD_TRACE") != nullptr;
+  const auto tt0 = std::chrono::steady_clock::now();
   summarize(t.row_topic, t.sum_topic);
+  const auto tt1 = std::chrono::steady_clock::now();
   choose_summaries();
+  const auto tt2 = std::chrono::steady_clock::now();
+  if (trace) fprintf(stderr, "[rebuild_topics] n=%u threads=%u summarize %.2f choose %.2f ms\n", n, nth,
+                     std::chrono::duration<double, std::milli>(tt1 - tt0).count(), std::chrono::duration<double, std::milli>(tt2 - tt1).count());
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t ri = routing_topics_.find(topic_keys_[i], kMiss);
     topic_entries_[i].pool_off = (uint32_t)t.pool_list.size();
@@ -972,6 +992,8 @@ void Host::rebuild_topics() {
   t.eff_topic.assign((size_t)(t.n_effcfg + 1) * stride, 0);
   for (uint32_t c = 1; c <= t.n_effcfg; ++c)
     for (uint32_t i = 0; i < n; ++i) eff_topic_fill(c, i);
+  if (trace) fprintf(stderr, "[rebuild_topics] pools+eff (%u effcfgs) %.2f ms\n", t.n_effcfg,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt2).count());
   t.v_topic++;
 }
 
@@ -1052,14 +1074,23 @@ uint32_t Host::add_effcfg(sv payload) {
 
 // ------------------------------------------------------------ documents
 int Host::load_policy(sv json, sv snapshot, std::string& err) {
+  static const bool trace = getenv("CORDUM_LOAD_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   PolicyModel m;
-  if (!parse_policy_json(json, m, err)) return CORDUM_E_INVALID;
+  if (!parse_policy_json(json, m, err)) return CORDUM_E_INVALID;   // outside the lock: dispatches go on meanwhile
+  const auto t1 = now();
   std::lock_guard<std::mutex> g(mu_);
   PolicyModel old = std::move(policy_);
   policy_ = std::move(m);
+  const auto t2 = now();
   compile_policy();
+  const auto t3 = now();
   compile_routing();
   compile_mcp_tables();
+  const auto t4 = now();
+  struct Tr { bool on; decltype(t0) a, b, c, d, e; decltype(ms)& f; ~Tr() { if (on) fprintf(stderr, "[load_policy] parse %.2f  lock %.2f  compile_policy %.2f  routing+mcp %.2f  rest(topics) %.2f ms\n", f(a, b), f(b, c), f(c, d), f(d, e), f(e, std::chrono::steady_clock::now())); } } tr{trace, t0, t1, t2, t3, t4, ms};
   if (t_.mcp_stride > CORDUM_ID16_MAX) policy_capacity_error_ = "more than 65535 distinct MCP values referenced by allow / deny lists";
   if (!policy_capacity_error_.empty() || !routing_capacity_error_.empty()) {
     err = policy_capacity_error_.empty() ? routing_capacity_error_ : policy_capacity_error_;
@@ -1078,7 +1109,19 @@ int Host::load_policy(sv json, sv snapshot, std::string& err) {
     snapshots_.insert(snapshots_.begin(), snapshot_);
     if (snapshots_.size() > 10) snapshots_.resize(10);
   }
+  publish_text();
   return CORDUM_OK;
+}
+
+void Host::publish_text() {
+  auto t = std::make_shared<PolicyText>();
+  t->gen = text_.empty() ? 1 : text_.back()->gen + 1;
+  t->snapshot = snapshot_;
+  t->rules.reserve(policy_.rules.size());
+  for (const RuleModel& r : policy_.rules)
+    t->rules.push_back(PolicyText::Rule{r.id, r.reason, r.constraints_json, r.remediations_json, r.has_constraints});
+  text_.push_back(std::move(t));
+  if (text_.size() > 8) text_.pop_front();
 }
 
 int Host::load_routing(sv json, std::string& err) {
@@ -1149,7 +1192,7 @@ int Host::load_workers(const cordum_workers* w, std::string& err) {
   workers_raw_ = std::move(store);
   int rc = compile_workers(err, &loads);
   if (rc != CORDUM_OK) { workers_raw_ = std::move(old_store); return rc; }   // compile_workers mutated nothing
-  worker_ids_ = std::move(ids);
+  worker_ids_ = std::make_shared<const std::vector<std::string>>(std::move(ids));
   epoch_++;
   v_dict_++;
   return CORDUM_OK;

@@ -19,6 +19,8 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <deque>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <unordered_map>
@@ -192,6 +194,15 @@ struct RuleModel {
   bool has_constraints = false;
   std::string constraints_json, remediations_json;
 };
+// What the decision records of one dispatch index, as text.  Immutable once published: a batch keeps the one it was
+// dispatched under, so a policy / registry reload after the dispatch cannot relabel its decisions (the reference's
+// evaluate reads policy and snapshot under one lock and builds the whole response from them, kernel.go:140-147,239-248).
+struct PolicyText {
+  uint64_t gen = 0;   // 1, 2, ...: counts successful policy loads
+  std::string snapshot;
+  struct Rule { std::string id, reason, constraints_json, remediations_json; bool has_constraints = false; };
+  std::vector<Rule> rules;
+};
 struct TenantModel { std::string name; std::vector<std::string> allow_topics, deny_topics; McpLists mcp; };
 struct PolicyModel {
   bool nil = true;
@@ -329,8 +340,14 @@ class Host {
   const PolicyModel& policy() const { return policy_; }
   const std::vector<std::string>& snapshots() const { return snapshots_; }
   const std::string& current_snapshot() const { return snapshot_; }
-  const std::string& worker_id(uint32_t slot) const { return worker_ids_[slot]; }
-  uint32_t n_worker_slots() const { return (uint32_t)worker_ids_.size(); }
+  const std::string& worker_id(uint32_t slot) const { return (*worker_ids_)[slot]; }
+  uint32_t n_worker_slots() const { return (uint32_t)worker_ids_->size(); }
+  std::shared_ptr<const std::vector<std::string>> worker_text() const { return worker_ids_; }
+  std::shared_ptr<const PolicyText> policy_text(uint64_t gen = 0) const {   // 0 = the policy in force; else one of the last 8
+    if (gen == 0) return text_.empty() ? nullptr : text_.back();
+    for (auto& t : text_) if (t->gen == gen) return t;
+    return nullptr;
+  }
   const std::string& topic_raw(uint32_t topic_id) const { return topic_keys_[topic_id]; }
   std::string mcp_value_string(int field, uint32_t id) const;
   const std::vector<std::string>& topic_pool_names(uint32_t topic_id) const;
@@ -370,6 +387,7 @@ class Host {
   // topic patterns (distinct trimmed pattern -> rules)
   struct Pattern { Glob glob; std::vector<uint32_t> rules; };
   std::vector<Pattern> patterns_;
+  std::unordered_map<std::string, std::vector<uint32_t>> pat_by_prefix_;   // literal prefix -> patterns
   Bits vac_topic_;
   // topics (dynamic)
   StrTable topic_ids_;
@@ -386,7 +404,9 @@ class Host {
   Dict d_pool_;
   StrTable routing_topics_;   // raw topic -> index in routing_.topics
   // workers
-  std::vector<std::string> worker_ids_;
+  std::shared_ptr<const std::vector<std::string>> worker_ids_ = std::make_shared<std::vector<std::string>>();   // replaced, never edited
+  std::deque<std::shared_ptr<const PolicyText>> text_;   // the last 8 policies' text, oldest first
+  void publish_text();
   StrTable worker_slot_;      // worker_id -> slot (last wins)
   StrTable place_pair_;       // key '\0' value -> bit   (value non-empty)
   StrTable place_key_;        // key -> bit E_k ("labels non-empty and k absent-or-empty")

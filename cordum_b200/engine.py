@@ -139,6 +139,10 @@ class Batch:
         self.L.cordum_batch_snapshot(self.h, buf, len(buf))
         return buf.value.decode("utf-8", "replace")
 
+    def policy_gen(self) -> int:
+        """Generation of the policy the last dispatch ran under (Engine.rule_id(idx, gen) etc.)."""
+        return int(self.L.cordum_batch_policy_gen(self.h))
+
     def subject(self, job: int) -> str:
         return self._text(self.L.cordum_subject, job)
 
@@ -307,20 +311,25 @@ class Engine:
     def batch(self, max_jobs: int) -> Batch:
         return Batch(self, max_jobs)
 
-    def rule_id(self, idx: int) -> str:
-        buf = C.create_string_buffer(4096)
-        self.L.cordum_rule_id(self.h, idx, buf, len(buf))
-        return buf.value.decode("utf-8", "replace")
+    # gen: policy generation the rule index belongs to (Batch.policy_gen()); 0 = the policy in force
+    def _rule_text(self, fn, gen: int, idx: int) -> str:
+        buf = C.create_string_buffer(1 << 12)
+        n = fn(self.h, gen, idx, buf, len(buf))
+        if n >= len(buf):
+            buf = C.create_string_buffer(n + 1)
+            fn(self.h, gen, idx, buf, len(buf))
+        return buf.value.decode("utf-8", "replace") if n > 0 else ""
 
-    def rule_constraints(self, idx: int):
-        buf = C.create_string_buffer(1 << 16)
-        n = self.L.cordum_rule_constraints_json(self.h, idx, buf, len(buf))
-        return json.loads(buf.value.decode()) if n > 0 else None
+    def rule_id(self, idx: int, gen: int = 0) -> str:
+        return self._rule_text(self.L.cordum_rule_id_at, gen, idx)
 
-    def rule_remediations(self, idx: int):
-        buf = C.create_string_buffer(1 << 16)
-        n = self.L.cordum_rule_remediations_json(self.h, idx, buf, len(buf))
-        return json.loads(buf.value.decode()) if n > 0 else []
+    def rule_constraints(self, idx: int, gen: int = 0):
+        s = self._rule_text(self.L.cordum_rule_constraints_json_at, gen, idx)
+        return json.loads(s) if s else None
+
+    def rule_remediations(self, idx: int, gen: int = 0):
+        s = self._rule_text(self.L.cordum_rule_remediations_json_at, gen, idx)
+        return json.loads(s) if s else []
 
     def stats(self) -> wire.CordumTableStats:
         st = wire.CordumTableStats()

@@ -30,7 +30,7 @@ class Decision(C.Structure):
 
 
 class Response(C.Structure):
-    _fields_ = [("rec", Decision), ("status", C.c_int32), ("rule_id", C.c_char * 128), ("reason", C.c_char * 256),
+    _fields_ = [("rec", Decision), ("status", C.c_int32), ("reserved", C.c_uint32), ("policy_gen", C.c_uint64), ("rule_id", C.c_char * 128), ("reason", C.c_char * 256),
                 ("subject", C.c_char * 192), ("snapshot", C.c_char * 96)]
 
 

@@ -110,6 +110,7 @@ class SafetyKernelServer:
             self._batch = self.engine.batch(max(n, 256))
         b = self._batch
         recs = b.encode([_envelope(r) for r in requests]).dispatch(wire.MODE_POLICY_ONLY)
+        gen = b.policy_gen()          # rule text of the policy this batch ran under, whatever has been loaded since
         if snapshot is None:
             snapshot = b.snapshot()   # s.snapshot as read with the policy (kernel.go:141,243): "" when that policy has none
         out = []
@@ -123,11 +124,11 @@ class SafetyKernelServer:
                 "reason": b.reason(j, flavor),
                 "reason_code": int(rec["reason_code"]),                         # not a proto field: the record's own code
                 "policy_snapshot": snapshot if has_snapshot else "",
-                "rule_id": self.engine.rule_id(rule_idx) if rule_idx >= 0 else "",
-                "constraints": self.engine.rule_constraints(rule_idx) if flags & wire.F_CONSTRAINTS else None,
+                "rule_id": self.engine.rule_id(rule_idx, gen) if rule_idx >= 0 else "",
+                "constraints": self.engine.rule_constraints(rule_idx, gen) if flags & wire.F_CONSTRAINTS else None,
                 "approval_required": approval,
                 "approval_ref": req.get("job_id", "") if approval else "",     # kernel.go:234-237
-                "remediations": self.engine.rule_remediations(rule_idx) if rule_idx >= 0 else [],
+                "remediations": self.engine.rule_remediations(rule_idx, gen) if rule_idx >= 0 else [],
             })
         return out
 

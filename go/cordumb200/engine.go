@@ -264,11 +264,13 @@ func submit(fe *C.cordum_frontend, r *C.cordum_request) (*C.cordum_response, fun
 }
 
 // ruleText fetches the pass-through JSON of a rule's constraints / remediations (kernel.go:244,247).
-func (e *Engine) ruleText(idx C.int32_t, f func(*C.cordum_engine, C.int32_t, *C.char, C.uint64_t) C.int64_t) []byte {
+// ruleText resolves a record's rule index against the policy generation the request was evaluated under
+// (cordum_response.policy_gen), not the policy in force by the time the response is assembled.
+func (e *Engine) ruleText(gen C.uint64_t, idx C.int32_t, f func(*C.cordum_engine, C.uint64_t, C.int32_t, *C.char, C.uint64_t) C.int64_t) []byte {
 	const cap = 1 << 16
 	buf := (*C.char)(C.malloc(cap))
 	defer C.free(unsafe.Pointer(buf))
-	n := f(e.h, idx, buf, cap)
+	n := f(e.h, gen, idx, buf, cap)
 	if n <= 0 || n >= cap {
 		return nil
 	}

@@ -86,8 +86,8 @@ func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest)
 		out.ApprovalRef = req.GetJobId() // kernel.go:233-237
 	}
 	if r.rec.flags&C.CORDUM_F_CONSTRAINTS != 0 {
-		if js := k.eng.ruleText(r.rec.rule_idx, func(e *C.cordum_engine, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
-			return C.cordum_rule_constraints_json(e, i, b, n)
+		if js := k.eng.ruleText(r.policy_gen, r.rec.rule_idx, func(e *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_constraints_json_at(e, g, i, b, n)
 		}); js != nil {
 			var c config.PolicyConstraints
 			if json.Unmarshal(js, &c) == nil { // the engine passes the rule's YAML-tagged object through as JSON
@@ -96,8 +96,8 @@ func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest)
 		}
 	}
 	if r.rec.rule_idx >= 0 {
-		if js := k.eng.ruleText(r.rec.rule_idx, func(e *C.cordum_engine, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
-			return C.cordum_rule_remediations_json(e, i, b, n)
+		if js := k.eng.ruleText(r.policy_gen, r.rec.rule_idx, func(e *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_remediations_json_at(e, g, i, b, n)
 		}); js != nil {
 			var rems []config.PolicyRemediation
 			if json.Unmarshal(js, &rems) == nil {

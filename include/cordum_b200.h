@@ -200,8 +200,16 @@ int32_t cordum_policy_snapshots(cordum_engine* e, char* buf, uint64_t cap, uint3
 /* The snapshot of the policy in force = PolicyCheckResponse.PolicySnapshot (kernel.go:243): "" when the current policy
  * was loaded without one.  NUL-terminated into buf, returns the full length. */
 int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap);
-/* The snapshot the batch's last dispatch ran under (read under the same lock as the tables it used). */
+/* The snapshot the batch's last dispatch ran under (read under the same lock as the tables it used), and the generation
+ * (1, 2, ...: successful cordum_policy_load calls) of that policy.  The engine keeps the rule text of the last 8
+ * generations: cordum_rule_*_at(e, gen, rule_idx) resolve a record's rule_idx against the policy its batch ran under even
+ * if a reload has landed since (the reference builds the whole response from the policy pointer it read under the lock,
+ * kernel.go:140-147,239-248).  gen 0 = the policy in force now. */
 int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap);
+uint64_t cordum_batch_policy_gen(const cordum_batch* b);
+int64_t cordum_rule_id_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
+int64_t cordum_rule_constraints_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
+int64_t cordum_rule_remediations_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
 
 /* (*LeastLoadedStrategy).UpdateRouting (strategy_least_loaded.go:28-30).
  * routing_json = {"topics": {topic: [pool,...]}, "pools": {pool: {"requires": [...]}}}
@@ -368,6 +376,8 @@ typedef struct cordum_request {      /* PolicyCheckRequest / JobRequest fields t
 typedef struct cordum_response {     /* PolicyCheckResponse (kernel.go:239-248) + the routed subject (PickSubject) */
   cordum_decision rec;
   int32_t status;                    /* CORDUM_OK, or why the request failed closed (rec then says DENY)            */
+  uint32_t reserved;
+  uint64_t policy_gen;               /* generation of the policy the request was evaluated under: cordum_rule_*_at  */
   char rule_id[128];                 /* "" when the response carries none (kernel.go:171-176)                       */
   char reason[256];
   char subject[192];                 /* "worker.<id>.jobs" when routed (bus/nats.go:94-99)                          */
