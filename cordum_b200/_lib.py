@@ -135,7 +135,9 @@ def load() -> C.CDLL:
     L.cordum_test_host_update.argtypes = [vp, u32, vp, vp]
     L.cordum_test_slab_bytes.argtypes = [u32]
     L.cordum_test_slab_bytes.restype = u64
-    L.cordum_test_host_encode.argtypes = [vp, vp, vp]
+    L.cordum_test_host_encode.argtypes = [vp, vp, vp, vp]
+    L.cordum_test_host_wide_words.argtypes = [vp]
+    L.cordum_test_host_wide_words.restype = u32
     L.cordum_test_host_table.argtypes = [vp, cp, C.POINTER(vp), C.POINTER(u64)]
     L.cordum_test_json_canon.argtypes = [cp, u64, cp, u64]
     L.cordum_test_json_canon.restype = i64

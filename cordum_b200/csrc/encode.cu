@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) encode_key_kernel(EncodeParams P) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= P.n_jobs) return;
   const EncodeTables& E = P.et;
-  bool bad = false;
+  bool bad = E.wide_words != 0;   // masks wider than the records' fields (tables.h WideLayout): the host encoder writes those
   const Str topic = span_of(P.arena, P.topic, j);
   uint32_t tid = topic.n > kMaxStr ? kMiss : find_exact(E, DD_TOPIC, topic, kMiss);   // keyed by the RAW string
   if (tid == kMiss) { bad = true; tid = 0; }

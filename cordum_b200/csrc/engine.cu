@@ -84,6 +84,7 @@ struct cordum_engine {
   DevBuf b_req_need, b_lab_need, b_rule_dec, b_tenant_mcp, b_eff_mcp, b_eff_topic, b_pos2rule;
   DevBuf b_sum_tenant, b_sum_topic, b_sum_cap, b_sum_pack, b_sum_actor, b_sum_combo, b_sum_risk;
   DevBuf b_topic_pool_off, b_topic_pool_cnt, b_pool_list, b_pool_req_mask, b_pool_req_nonempty;
+  DevBuf b_rule_need_x, b_pool_req_x, b_req_blank_x, b_pos_label_x;   // wide masks (tables.h WideLayout)
   DevBuf b_pool_off, b_pos_pool, b_pos_slot, b_pos_rank, b_slot_pos, b_rank_slot, b_pos_label_lo, b_pos_label_hi;
   DevBuf b_flush, b_lbm_off, b_rank_pos, b_chunk_pool, b_pool_chunk0, b_merge_list;
   DevBuf b_dicts;                // device encoder: dictionary images + side arrays (Host::export_dicts)
@@ -125,7 +126,7 @@ struct cordum_engine {
   // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
   // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
   struct DerivedSet {
-    DevBuf loads, pos_key, ckey, skey, slab_lo, slab_hi, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
+    DevBuf loads, pos_key, ckey, skey, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
     cudaEvent_t ready = nullptr, loads_read = nullptr;   // refresh complete / load table consumed by the refresh
   } ds[kSets];
   int cur = 0;                   // set holding the latest refresh
@@ -148,6 +149,9 @@ struct cordum_batch {
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
   uint8_t* d_cols = nullptr;
+  uint64_t *h_wide = nullptr, *d_wide = nullptr;   // wide-mask rows (tables.h WideLayout), allocated on first need
+  uint64_t wide_cap = 0;         // 64-bit words allocated at each of the two
+  uint32_t wide_words = 0;       // row width of the encoded batch
   uint32_t* slot_of = nullptr;   // host: position of caller job j in the sorted records
   // device-side encode (cordum_encode_device)
   bool device_encoded = false, host_records_valid = true;
@@ -180,10 +184,13 @@ void host_records(cordum_batch* b) {
   b->hr.job = (JobRec*)b->h_cols;
   b->hr.route = (RouteRec*)(b->h_cols + (size_t)b->n * sizeof(JobRec));
   b->hr.slot_of = b->slot_of;
+  b->hr.wide = b->h_wide;
+  b->hr.wide_cap = b->wide_cap;
 }
 void device_records(const cordum_batch* b, JobRecords& r) {
   r.job = (const JobRec*)b->d_cols;
   r.route = (const RouteRec*)(b->d_cols + (size_t)b->n * sizeof(JobRec));
+  r.wide = b->wide_words ? b->d_wide : nullptr;
 }
 
 template <class T>
@@ -236,6 +243,8 @@ int sync_tables(cordum_engine* e) {
     d.chk_words = (const uint32_t*)e->b_row_check.p;
     d.rule_req_need = (const uint64_t*)e->b_req_need.p; d.rule_lab_need = (const uint64_t*)e->b_lab_need.p;
     d.rule_dec = (const uint8_t*)e->b_rule_dec.p;
+    CK(up(e->b_rule_need_x, t.rule_need_x, s), "upload");
+    d.rule_need_x = (const uint64_t*)e->b_rule_need_x.p;
     e->v_policy = t.v_policy;
   }
   if (t.v_topic != e->v_topic) {
@@ -259,6 +268,8 @@ int sync_tables(cordum_engine* e) {
     CK(up(e->b_pool_req_mask, t.pool_req_mask, s), "upload"); CK(up(e->b_pool_req_nonempty, t.pool_req_nonempty, s), "upload");
     d.pool_req_mask = (const uint64_t*)e->b_pool_req_mask.p; d.pool_req_nonempty = (const uint8_t*)e->b_pool_req_nonempty.p;
     d.req_blank_mask = t.req_blank_mask; d.n_pools = t.n_pools;
+    CK(up(e->b_pool_req_x, t.pool_req_x, s), "upload"); CK(up(e->b_req_blank_x, t.req_blank_x, s), "upload");
+    d.pool_req_x = (const uint64_t*)e->b_pool_req_x.p; d.req_blank_x = (const uint64_t*)e->b_req_blank_x.p;
     e->v_routing = t.v_routing;
   }
   if (t.v_workers != e->v_workers) {
@@ -274,8 +285,6 @@ int sync_tables(cordum_engine* e) {
       CK(D.pool_mincnt.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
       CK(D.skey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.ckey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-      CK(D.slab_lo.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
-      CK(D.slab_hi.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
       CK(D.pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
       CK(D.lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
@@ -294,6 +303,8 @@ int sync_tables(cordum_engine* e) {
     d.pos_slot = (const uint32_t*)e->b_pos_slot.p; d.pos_rank = (const uint32_t*)e->b_pos_rank.p;
     d.slot_pos = (const uint32_t*)e->b_slot_pos.p; d.rank_slot = (const uint32_t*)e->b_rank_slot.p;
     d.pos_label_lo = (const uint64_t*)e->b_pos_label_lo.p; d.pos_label_hi = (const uint64_t*)e->b_pos_label_hi.p;
+    CK(up(e->b_pos_label_x, t.pos_label_x, s), "upload");
+    d.pos_label_x = (const uint64_t*)e->b_pos_label_x.p;
     e->v_workers = t.v_workers;
     e->pools_dirty = true;
     e->host_loads = true;
@@ -303,6 +314,8 @@ int sync_tables(cordum_engine* e) {
     e->pools_dirty = true;
     e->host_loads = true;
   }
+  d.wide = t.wide;
+  d.wide_words = WIDE_WORDS(t.wide);
   CK(cudaStreamSynchronize(s), "table upload");
   e->tables_gen++;
   return CORDUM_OK;
@@ -362,7 +375,7 @@ DeviceTables view(const cordum_engine* e, int set) {
   DeviceTables d = e->dt;
   const auto& D = e->ds[set];
   d.loads = (const Load16*)D.loads.p;
-  d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p; d.slab_lo = (uint64_t*)D.slab_lo.p; d.slab_hi = (uint64_t*)D.slab_hi.p;
+  d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p;
   d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.lbm = (uint32_t*)D.lbm.p;
   d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
   return d;
@@ -447,6 +460,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   if (copy_in) {
     CK(cudaEventRecord(b->ev0, s), "event");
     CK(cudaMemcpyAsync(b->d_cols, b->h_cols, slab_bytes(b->n), cudaMemcpyHostToDevice, s), "H2D columns");
+    if (b->wide_words) CK(cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)b->n * b->wide_words * 8, cudaMemcpyHostToDevice, s), "H2D wide masks");
     b->resident = true;
   }
   if (timed) CK(cudaEventRecord(b->ev1, s), "event");
@@ -535,6 +549,8 @@ static void batch_release(cordum_batch* b) {   // frees the batch's CUDA resourc
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->h_cols) cudaFreeHost(b->h_cols);
   if (b->d_cols) cudaFree(b->d_cols);
+  if (b->h_wide) cudaFreeHost(b->h_wide);
+  if (b->d_wide) cudaFree(b->d_wide);
   if (b->h_out) cudaFreeHost(b->h_out);
   if (b->d_out) cudaFree(b->d_out);
   if (b->d_route) cudaFree(b->d_route);
@@ -893,10 +909,30 @@ int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* 
   b->encoded = false;
   b->resident = false;
   b->device_encoded = false;
-  host_records(b);
-  uint64_t epoch_before = e->host->epoch();
-  int rc = e->host->encode(env, b->hr, g_err);
-  if (rc) return rc;
+  uint64_t epoch_before = 0;
+  int rc = CORDUM_OK;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    // a policy / registry whose dictionaries outgrow the records' mask fields needs a side row per job (WideLayout)
+    const uint64_t need = (uint64_t)e->host->wide_words() * b->max_jobs;
+    if (need > b->wide_cap) {
+      std::lock_guard<std::mutex> g(e->mu);
+      CK(cudaSetDevice(e->device), "cudaSetDevice");
+      CK(cudaStreamSynchronize(b->stream), "wait before reallocating the wide rows");
+      if (b->h_wide) cudaFreeHost(b->h_wide);
+      if (b->d_wide) cudaFree(b->d_wide);
+      b->h_wide = b->d_wide = nullptr; b->wide_cap = 0;
+      CK(cudaHostAlloc((void**)&b->h_wide, need * 8, cudaHostAllocDefault), "pinned wide rows");
+      CK(cudaMalloc((void**)&b->d_wide, need * 8), "device wide rows");
+      b->wide_cap = need;
+      e->tables_gen++;   // captured graphs bake the batch's pointers in
+    }
+    host_records(b);
+    epoch_before = e->host->epoch();
+    rc = e->host->encode(env, b->hr, g_err);
+    if (rc != cordum::kWideRetry) break;   // the tables changed between the look and the encode: size again
+  }
+  if (rc) return rc == cordum::kWideRetry ? CORDUM_E_STALE : rc;
+  b->wide_words = b->hr.wide_words;
   b->epoch = epoch_before;
   b->encoded = true;
   b->host_records_valid = true;
@@ -982,11 +1018,11 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_sum_tenant, &e->b_sum_topic, &e->b_sum_cap, &e->b_sum_pack, &e->b_sum_actor, &e->b_sum_combo, &e->b_sum_risk,
                    &e->b_topic_pool_off, &e->b_topic_pool_cnt, &e->b_pool_list, &e->b_pool_req_mask, &e->b_pool_req_nonempty,
                    &e->b_pool_off, &e->b_pos_pool, &e->b_pos_slot, &e->b_pos_rank, &e->b_slot_pos, &e->b_rank_slot,
-                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos,
+                   &e->b_pos_label_lo, &e->b_pos_label_hi, &e->b_rule_need_x, &e->b_pool_req_x, &e->b_req_blank_x, &e->b_pos_label_x, &e->b_flush, &e->b_lbm_off, &e->b_rank_pos,
                    &e->b_chunk_pool, &e->b_pool_chunk0, &e->b_merge_list};
   for (DevBuf* b : all) b->release();
   for (auto& D : e->ds) {
-    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.slab_lo, &D.slab_hi, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
+    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
     if (D.ready) cudaEventDestroy(D.ready);
     if (D.loads_read) cudaEventDestroy(D.loads_read);
   }
@@ -1315,6 +1351,7 @@ int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_env
   const uint32_t n = env->n_jobs;
   b->n = n;
   b->encoded = false; b->resident = false; b->device_encoded = false;
+  b->wide_words = 0;   // a batch the device encoder completes has none (wide tables raise the fallback flag)
   if (n == 0) { b->encoded = true; b->resident = true; b->device_encoded = true; b->host_records_valid = true; b->epoch = e->host->epoch(); return CORDUM_OK; }
   if (!b->h_fallback) { CK(cudaHostAlloc((void**)&b->h_fallback, 64, cudaHostAllocDefault), "pinned flag"); *b->h_fallback = 0; }
   const uint32_t n_risk = env->risk_off ? env->risk_off[n] : 0, n_req = env->requires_off ? env->requires_off[n] : 0,

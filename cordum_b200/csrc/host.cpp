@@ -678,6 +678,9 @@ void Host::compile_policy() {
   t.rule_lab_need.assign((size_t)t.n_seg * CORDUM_SEG_RULES, 0);
   Bits alive(W, 0), check(W, 0);
   uint32_t n_pairs = 0;
+  rule_req_ids_.assign(R, {});
+  rule_lab_bits_.assign(R, {});
+  label_empty_x_.clear();
   for (uint32_t r = 0; r < R; ++r) {
     const RuleModel& m = rules[r];
     t.rule_dec[r] = normalize_decision_code(m.decision) | (m.has_constraints ? 0x80 : 0);
@@ -687,6 +690,7 @@ void Host::compile_policy() {
       if (q.empty()) { dead = true; continue; }   // containsString(values, "") is always false (:297)
       uint32_t id = d_req_.intern(fold_key(q));
       need |= (id - 2 < 64) ? (1ull << (id - 2)) : 0;
+      rule_req_ids_[r].push_back(id - 2);          // bits beyond 63 go to rule_need_x (finalize_wide)
     }
     t.rule_req_need[r] = need;
     uint64_t lneed = 0;
@@ -699,17 +703,20 @@ void Host::compile_policy() {
       if (bit == kMiss) {
         bit = n_pairs++;
         pairs.emplace_back(kv.second, bit);
-        if (kv.second.empty() && bit < 64) label_empty_mask_ |= 1ull << bit;
+        if (kv.second.empty()) {
+          if (bit < 64) label_empty_mask_ |= 1ull << bit;
+          else { if (label_empty_x_.size() < (bit >> 6)) label_empty_x_.resize(bit >> 6, 0); label_empty_x_[(bit >> 6) - 1] |= 1ull << (bit & 63); }
+        }
       }
       if (bit < 64) lneed |= 1ull << bit;
+      rule_lab_bits_[r].push_back(bit);
     }
     t.rule_lab_need[r] = lneed;
     if (!dead) set_rule(alive.data(), r);
-    if (need || lneed) set_rule(check.data(), r);
+    if (!rule_req_ids_[r].empty() || !rule_lab_bits_[r].empty()) set_rule(check.data(), r);
   }
+  n_label_pairs_ = n_pairs;
   policy_capacity_error_.clear();
-  if (d_risk_.size() - 2 > 64) policy_capacity_error_ = "more than 64 distinct risk tags referenced by rules";
-  if (n_pairs > 64) policy_capacity_error_ = "more than 64 distinct label pairs referenced by rules";
   if (std::max({d_tenant_.size(), d_cap_.size(), d_pack_.size(), d_actor_.size()}) > CORDUM_ID16_MAX ||
       policy_.tenants.size() >= CORDUM_ID16_MAX)
     policy_capacity_error_ = "more than 65535 distinct values referenced by one predicate (tenants / capabilities / pack_ids / actor_ids)";
@@ -734,7 +741,7 @@ void Host::compile_policy() {
           for (auto& e : m.actor_types) if (fold_key(e) == at_names[at]) ok = true;
       }
       if (m.secrets_present >= 0 && (m.secrets_present == 1) != (s == 1)) ok = false;
-      if ((no_req && t.rule_req_need[r]) || (no_lab && t.rule_lab_need[r])) ok = false;
+      if ((no_req && !rule_req_ids_[r].empty()) || (no_lab && !rule_lab_bits_[r].empty())) ok = false;
       if (ok) for (uint32_t p : rule_pos_[r]) if (alive[p >> 5] >> (p & 31) & 1) row[p >> 5] |= 1u << (p & 31);
     }
   }
@@ -803,6 +810,7 @@ void Host::compile_routing() {
   t.n_pools = d_pool_.size() - 2;
   t.pool_req_mask.assign(std::max<uint32_t>(t.n_pools, 1), 0);
   t.pool_req_nonempty.assign(std::max<uint32_t>(t.n_pools, 1), 0);
+  pool_req_ids_.assign(std::max<uint32_t>(t.n_pools, 1), {});
   for (auto& p : routing_.pools) {
     uint32_t pid = d_pool_.table.find(p.first, 0) - 2;
     t.pool_req_nonempty[pid] = p.second.empty() ? 0 : 1;   // poolSatisfies: len(poolRequires)==0 -> false (:245)
@@ -812,14 +820,40 @@ void Host::compile_routing() {
       if (k.empty()) continue;
       uint32_t id = d_req_.intern(k);
       if (id - 2 < 64) mask |= 1ull << (id - 2);
+      pool_req_ids_[pid].push_back(id - 2);
     }
     t.pool_req_mask[pid] = mask;
   }
   routing_capacity_error_.clear();
-  if (d_req_.size() - 2 > 64) routing_capacity_error_ = "more than 64 distinct requires tokens across rules and pools";
   uint32_t blank = d_req_.table.find(sv(), 0);
   t.req_blank_mask = (blank >= 2 && blank - 2 < 64) ? (1ull << (blank - 2)) : 0;
+  finalize_wide();
   t.v_routing++;
+}
+
+// The dictionaries are final here (compile_policy, then compile_routing): how many mask words beyond the records' own does
+// a job need, and the rules' / pools' bits that live there.  Placement width belongs to the registry (compile_workers).
+void Host::finalize_wide() {
+  HostTables& t = t_;
+  auto extra = [](uint32_t nbits, uint32_t base) { const uint32_t w = (nbits + 63) / 64; return w > base ? w - base : 0u; };
+  t.wide.xw_risk = extra(d_risk_.size() - 2, 1);
+  t.wide.xw_req = extra(d_req_.size() - 2, 1);
+  t.wide.xw_lab = extra(n_label_pairs_, 1);
+  const uint32_t xq = t.wide.xw_req, xl = t.wide.xw_lab, R = (uint32_t)policy_.rules.size();
+  t.rule_need_x.assign((size_t)std::max<uint32_t>(R, 1) * (xq + xl) + 1, 0);
+  for (uint32_t r = 0; r < R && r < rule_req_ids_.size(); ++r) {
+    uint64_t* row = t.rule_need_x.data() + (size_t)r * (xq + xl);
+    for (uint32_t b : rule_req_ids_[r]) if (b >= 64) row[(b >> 6) - 1] |= 1ull << (b & 63);
+    for (uint32_t b : rule_lab_bits_[r]) if (b >= 64) row[xq + (b >> 6) - 1] |= 1ull << (b & 63);
+  }
+  t.pool_req_x.assign((size_t)std::max<uint32_t>(t.n_pools, 1) * xq + 1, 0);
+  for (uint32_t p = 0; p < pool_req_ids_.size(); ++p)
+    for (uint32_t b : pool_req_ids_[p]) if (b >= 64) t.pool_req_x[(size_t)p * xq + (b >> 6) - 1] |= 1ull << (b & 63);
+  t.req_blank_x.assign(xq + 1, 0);
+  const uint32_t blank = d_req_.table.find(sv(), 0);
+  if (blank >= 2 && blank - 2 >= 64) t.req_blank_x[((blank - 2) >> 6) - 1] |= 1ull << ((blank - 2) & 63);
+  label_empty_x_.resize(xl, 0);
+  t.v_policy++;   // rule_need_x travels with the policy group
 }
 
 // ------------------------------------------------------------ MCP tables (rule rows, tenant + effective-config verdicts)
@@ -1229,7 +1263,17 @@ int Host::compile_workers(std::string& err, const std::vector<Load16>* new_loads
         if (place_pair.find(pk, kMiss) == kMiss) place_pair.put(pk, nbits++);
       }
     }
-  if (nbits > 128) { err = "more than 128 placement-label bits (pairs + keys) on routable workers"; return CORDUM_E_CAPACITY; }
+  {   // label bits beyond 128 spill into pos_label_x; what bounds them is the per-pool bitmaps (bits x workers / 8 bytes)
+    std::vector<uint32_t> per_pool(std::max<uint32_t>(t.n_pools, 1), 0);
+    for (auto& p : pos) per_pool[p.pool]++;
+    uint64_t words = 0;
+    for (uint32_t c : per_pool) words += (uint64_t)nbits * ((c + 31) / 32);
+    if (nbits > 65536 || words > (1ull << 31)) {
+      err = "placement labels on routable workers need " + std::to_string(nbits) + " label bits and " + std::to_string(words * 4 >> 20) +
+            " MiB of per-pool label bitmaps (limits: 65536 bits, 8 GiB)";
+      return CORDUM_E_CAPACITY;
+    }
+  }
   // ---- phase 2: commit (cannot fail)
   t.n_slots = n;
   if (new_loads) t.loads = *new_loads;
@@ -1245,6 +1289,9 @@ int Host::compile_workers(std::string& err, const std::vector<Load16>* new_loads
   uint32_t cap = std::max<uint32_t>(np, 1);
   t.pos_pool.assign(cap, 0); t.pos_slot.assign(cap, 0); t.pos_rank.assign(cap, 0);
   t.pos_label_lo.assign(cap, 0); t.pos_label_hi.assign(cap, 0);
+  const uint32_t xp = nbits > 128 ? (nbits - 128 + 63) / 64 : 0;
+  t.wide.xw_place = xp;
+  t.pos_label_x.assign((size_t)cap * xp + 1, 0);
   t.slot_pos.assign(std::max<uint32_t>(n, 1), 0);
   t.rank_pos.assign(std::max<uint32_t>(n, 1), 0);
   t.pool_off.assign(t.n_pools + 1, 0);
@@ -1262,7 +1309,8 @@ int Host::compile_workers(std::string& err, const std::vector<Load16>* new_loads
     t.rank_pos[p.rank] = i;
     t.pool_off[p.pool + 1]++;
     uint64_t m[2] = {0, 0};
-    auto setb = [&](uint32_t b) { m[b >> 6] |= 1ull << (b & 63); };
+    uint64_t* mx = t.pos_label_x.data() + (size_t)i * xp;
+    auto setb = [&](uint32_t b) { if (b < 128) m[b >> 6] |= 1ull << (b & 63); else mx[(b >> 6) - 2] |= 1ull << (b & 63); };
     const auto& labels = store[p.slot].labels;
     if (!labels.empty()) {
       setb(place_any_bit_);
@@ -1447,7 +1495,16 @@ uint32_t Host::resolve_tenant(const cordum_envelopes* env, uint32_t j, EncodeCac
   return cv | (ca << 16);
 }
 
-void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uint32_t ten, JobRec& jr, RouteRec& rr, bool& miss, EncodeCaches& cc) const {
+void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uint32_t ten, JobRec& jr, RouteRec& rr, uint64_t* wx, bool& miss, EncodeCaches& cc) const {
+  // wx: the job's row of extra mask words (tables.h WideLayout), zeroed here; null when the tables have none
+  const WideLayout WL = t_.wide;
+  const uint32_t o_req = WIDE_O_REQ(WL), o_lab = WIDE_O_LAB(WL), o_reqp = WIDE_O_REQP(WL), o_place = WIDE_O_PLACE(WL);
+  if (wx) {
+    std::memset(wx, 0, sizeof(uint64_t) * WIDE_WORDS(WL));
+    for (uint32_t k = 0; k < WL.xw_lab; ++k) wx[o_lab + k] = label_empty_x_[k];
+  }
+  auto setx = [&](uint32_t off, uint32_t bit) { wx[off + (bit >> 6) - 1] |= 1ull << (bit & 63); };   // bit >= 64
+  bool risk_any = false, req_any = false;
   uint32_t flags = 0;
   jr.topic = tid;
   jr.orig = j;
@@ -1493,7 +1550,10 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
         cc.risk.put(tag, id, is_secrets, cc.gen);
       }
       if (is_secrets) secrets_tag = true;
-      if (id >= 2 && id - 2 < 64) risk |= 1ull << (id - 2);
+      if (id >= 2) {
+        if (id - 2 < 64) risk |= 1ull << (id - 2); else setx(0, id - 2);
+        risk_any = true;
+      }
     }
   if (has_meta && env->requires_off) {
     uint32_t a = env->requires_off[j], b = env->requires_off[j + 1];
@@ -1517,8 +1577,11 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
         if (!tok.empty()) cc.req.put(tok, id, idp, cc.gen);
       }
       const uint32_t pid = (idp >> 1) - 1;
-      if (id >= 2 && id - 2 < 64) req |= 1ull << (id - 2);
-      if (pid >= 2 && pid - 2 < 64) req_pool |= 1ull << (pid - 2);
+      if (id >= 2) {
+        if (id - 2 < 64) req |= 1ull << (id - 2); else setx(o_req, id - 2);
+        req_any = true;
+      }
+      if (pid >= 2) { if (pid - 2 < 64) req_pool |= 1ull << (pid - 2); else setx(o_reqp, pid - 2); }
       else if (!(idp & 1)) flags |= JF_REQ_UNKNOWN;   // no pool declares it -> no pool satisfies (:255-262)
     }
   }
@@ -1527,6 +1590,7 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
   rr.req_pool = req_pool;
   // ---- labels: one pass
   uint64_t lab = label_empty_mask_, place[2] = {0, 0};
+  auto set_place = [&](uint32_t bit) { if (bit < 128) place[bit >> 6] |= 1ull << (bit & 63); else wx[o_place + (bit >> 6) - 2] |= 1ull << (bit & 63); };
   sv mcpv[12];
   sv secrets_label, pref_pool, pref_worker;
   bool have_secrets_label = false;
@@ -1541,19 +1605,25 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
     if (ce.gen == cc.gen && ce.kp == key.data() && ce.klen == key.size() && ce.vp == val.data() && ce.vlen == val.size()) {
       lab = (lab | ce.set) & ~ce.clear;
       if (ce.place == EncodeCaches::kPlaceUnsat) flags |= JF_PLACE_UNSAT;
-      else if (ce.place != EncodeCaches::kPlaceNone) place[ce.place >> 6] |= 1ull << (ce.place & 63);
+      else if (ce.place != EncodeCaches::kPlaceNone) set_place(ce.place);
       continue;
     }
     // rule label pairs: labels.get(k,"") == v
     uint64_t lset = 0, lclear = 0;
+    bool special = false;   // the value matters per job: not cacheable
     uint32_t ki = label_key_.find(key, kMiss);
     if (ki != kMiss)
       for (auto& pv : label_key_pairs_[ki]) {
-        if (pv.second >= 64) continue;
+        if (pv.second >= 64) {   // a pair bit in the wide words: set / clear it there; the cache entry has no room for it
+          uint64_t& w = wx[o_lab + (pv.second >> 6) - 1];
+          const uint64_t b = 1ull << (pv.second & 63);
+          if (sv(pv.first) == val) w |= b; else w &= ~b;
+          special = true;
+          continue;
+        }
         if (sv(pv.first) == val) lset |= 1ull << pv.second; else lclear |= 1ull << pv.second;
       }
     lab = (lab | lset) & ~lclear;
-    bool special = false;   // the value matters per job: not cacheable
     int mk = mcp_key(key);
     if (mk >= 0) { mcpv[mk] = trim_space(val); special = true; }
     if (key == "secrets_present") { secrets_label = trim_space(val); have_secrets_label = true; special = true; }
@@ -1570,7 +1640,7 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
         if (bit == kMiss) bit = place_any_bit_;   // no worker carries this key: any labelled worker passes
       }
       if (bit == EncodeCaches::kPlaceUnsat) flags |= JF_PLACE_UNSAT;
-      else place[bit >> 6] |= 1ull << (bit & 63);
+      else set_place(bit);
     }
     if (!special) ce = EncodeCaches::LabelEntry{key.data(), val.data(), (uint32_t)key.size(), (uint32_t)val.size(), lset, lclear, bit, cc.gen};
   }
@@ -1593,8 +1663,11 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
   if (have_secrets_label && !secrets_label.empty())
     secrets = secrets_label == "true" || secrets_label == "1" || fold_eq(secrets_label, "yes");
   flags |= (uint32_t)(at * 2 + (secrets ? 1 : 0));
-  if (req == 0) flags |= JF_NO_REQ;
-  if (!(flags & JF_HAS_LABELS) || lab == 0) flags |= JF_NO_LAB;
+  (void)risk_any;
+  if (!req_any) flags |= JF_NO_REQ;
+  bool lab_any = lab != 0;
+  for (uint32_t k = 0; wx && k < WL.xw_lab; ++k) lab_any |= wx[o_lab + k] != 0;
+  if (!(flags & JF_HAS_LABELS) || !lab_any) flags |= JF_NO_LAB;
   // ---- routing hints
   uint32_t pp = 0, pw = 0;
   if (!pref_pool.empty()) { uint32_t id = d_pool_.table.find(pref_pool, 0); pp = id >= 2 ? id - 1 : CORDUM_PREF_UNKNOWN; }
@@ -1621,7 +1694,10 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
   if (!env) { err = "null envelopes"; return CORDUM_E_INVALID; }
   std::lock_guard<std::mutex> g(mu_);
   const uint32_t n = env->n_jobs;
+  const uint32_t ww = WIDE_WORDS(t_.wide);
+  out.wide_words = ww;
   if (n == 0) return CORDUM_OK;
+  if (ww && (!out.wide || (uint64_t)n * ww > out.wide_cap)) { err = "wide-mask buffer missing or too small for this policy"; return kWideRetry; }
   const uint32_t nthreads = (n < 8192 || threads_ <= 1) ? 1u : threads_;
   auto& caches = caches_;   // span-identity caches: entries are only valid within this call (generation tag)
   if (caches.size() < nthreads) caches.resize(nthreads);
@@ -1698,7 +1774,7 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
         const uint32_t slot = cur[key_of(j)]++;
         out.slot_of[j] = slot;
         bool miss = false;
-        encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], miss, *caches[w]);
+        encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], ww ? out.wide + (size_t)slot * ww : nullptr, miss, *caches[w]);
         if (miss) misses[w].push_back(j);
       }
     }
@@ -1717,7 +1793,7 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
       if (!eff.empty() && add_effcfg(eff) == kMiss) { err = "effective-config dictionary full (max_effcfgs)"; return CORDUM_E_CAPACITY; }
       bool miss = false;
       const uint32_t slot = out.slot_of[j];
-      encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], miss, *caches[0]);
+      encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], ww ? out.wide + (size_t)slot * ww : nullptr, miss, *caches[0]);
     }
   return CORDUM_OK;
 }
@@ -1764,6 +1840,7 @@ void Host::export_dicts(std::vector<uint8_t>& blob, EncodeTables& et) const {
   et.default_tenant = lookup_value(d_tenant_, dt) | (tenant_pol_.find(dt, 0) << 16);
   et.place_any_bit = place_any_bit_;
   et.label_empty_mask = label_empty_mask_;
+  et.wide_words = WIDE_WORDS(t_.wide);
   blob.resize(blob.size() + 64);
 }
 

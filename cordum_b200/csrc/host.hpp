@@ -245,6 +245,9 @@ struct HostTables {
   std::vector<uint64_t> sum_tenant, sum_topic, sum_cap, sum_pack, sum_actor, sum_combo, sum_risk;
   uint32_t sum_group = 1, sum_use = 0;
   std::vector<uint64_t> rule_req_need, rule_lab_need;
+  // wide masks (tables.h WideLayout): all empty / zero unless a dictionary outgrew the record's mask fields
+  WideLayout wide{0, 0, 0, 0};
+  std::vector<uint64_t> rule_need_x, pool_req_x, req_blank_x, pos_label_x;
   std::vector<uint8_t> rule_dec;
   std::vector<uint32_t> pos2rule;                 // bit position -> original rule index (0xFFFFFFFF = padding)
   uint32_t mcp_stride = 2;
@@ -271,10 +274,14 @@ struct HostTables {
 
 // Encoded batch on the host (engine allocates the record arrays pinned and hands pointers in).  Records are in
 // topic-sorted order; slot_of[j] is the position of caller job j (pageable host memory, host-side use only).
+constexpr int kWideRetry = -100;   // Host::encode: HostRecords.wide is too small for the tables as they are now
 struct HostRecords {
   JobRec* job = nullptr;
   RouteRec* route = nullptr;
   uint32_t* slot_of = nullptr;
+  uint64_t* wide = nullptr;      // [n][wide_words] when the tables carry wide masks (Host::wide_words() at encode time)
+  uint64_t wide_cap = 0;         // 64-bit words available at `wide`
+  uint32_t wide_words = 0;       // out: the row width the encode used
 };
 
 // Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks.  Completion
@@ -349,6 +356,7 @@ class Host {
     return nullptr;
   }
   const std::string& topic_raw(uint32_t topic_id) const { return topic_keys_[topic_id]; }
+  uint32_t wide_words() const { return WIDE_WORDS(t_.wide); }
   std::string mcp_value_string(int field, uint32_t id) const;
   const std::vector<std::string>& topic_pool_names(uint32_t topic_id) const;
   uint32_t n_topics() const { return (uint32_t)topic_keys_.size(); }
@@ -380,6 +388,11 @@ class Host {
   StrTable label_key_;    // rule label key -> index into label_key_pairs_
   std::vector<std::vector<std::pair<std::string, uint32_t>>> label_key_pairs_;   // per key: (value, bit)
   uint64_t label_empty_mask_ = 0;   // bits of pairs whose value is ""
+  std::vector<uint64_t> label_empty_x_;   // ... beyond bit 63
+  uint32_t n_label_pairs_ = 0;
+  std::vector<std::vector<uint32_t>> rule_req_ids_, rule_lab_bits_;   // per rule: bit numbers of what it needs
+  std::vector<std::vector<uint32_t>> pool_req_ids_;                   // per pool: bit numbers of what it declares
+  void finalize_wide();
   std::string default_tenant_trim_;
   std::vector<std::vector<uint32_t>> rule_pos_;   // rule index -> its bit positions (see compile_policy)
   std::vector<std::vector<std::string>> rule_pos_tenant_;   // parallel: "" = the copy stands for every tenant the rule lists,
@@ -427,7 +440,7 @@ class Host {
   void summarize(const RowTable& rt, std::vector<uint64_t>& out) const;
   uint32_t resolve_topic(const cordum_envelopes* env, uint32_t j, struct EncodeCaches& cc) const;   // kMiss = not in the dictionary
   uint32_t resolve_tenant(const cordum_envelopes* env, uint32_t j, struct EncodeCaches& cc) const;   // id | exact-policy index << 16
-  void encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uint32_t ten, JobRec& jr, RouteRec& rr, bool& miss, struct EncodeCaches& cc) const;
+  void encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uint32_t ten, JobRec& jr, RouteRec& rr, uint64_t* wx, bool& miss, struct EncodeCaches& cc) const;
 };
 
 // test hooks (also exported through the C ABI as cordum_test_*)

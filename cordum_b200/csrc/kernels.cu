@@ -136,17 +136,21 @@ __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
   const uint32_t w = tid >> 5;
   if (w < words) {
     uint64_t llo = 0, lhi = 0;
+    uint32_t src = 0;
     if (tid < n) {
-      const uint32_t src = T.rank_pos[(uint32_t)(key & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
+      src = T.rank_pos[(uint32_t)(key & 0xFFFFFFFFu)];   // every key (overloaded ones too) carries its rank
       llo = T.pos_label_lo[src]; lhi = T.pos_label_hi[src];
-      T.skey[a + tid] = key; T.slab_lo[a + tid] = llo; T.slab_hi[a + tid] = lhi;
+      T.skey[a + tid] = key;
       cnt = (!none && (uint32_t)(key >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
       ok = key_over(key) ? 0u : 1u;
     }
     for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {   // lane t keeps the word of label bit b0+t, then one strided store each
       uint32_t mine = 0;
       const uint32_t lim = nbits - b0 < 32 ? nbits - b0 : 32;
-      const uint32_t part = b0 < 64 ? (uint32_t)(llo >> b0) : (uint32_t)(lhi >> (b0 - 64));   // b0 is a multiple of 32
+      uint32_t part;   // b0 is a multiple of 32
+      if (b0 < 64) part = (uint32_t)(llo >> b0);
+      else if (b0 < 128) part = (uint32_t)(lhi >> (b0 - 64));
+      else part = tid < n ? (uint32_t)(T.pos_label_x[(size_t)src * T.wide.xw_place + ((b0 - 128) >> 6)] >> (b0 & 32)) : 0u;   // bits 128...
       for (uint32_t t = 0; t < lim; ++t) {
         const unsigned bal = __ballot_sync(FULL, (part >> t) & 1u);
         if (lane == t) mine = bal;
@@ -208,10 +212,13 @@ __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
     }
     const uint32_t src = T.rank_pos[(uint32_t)(k & 0xFFFFFFFFu)];
     uint64_t llo = T.pos_label_lo[src], lhi = T.pos_label_hi[src];
-    T.skey[a + idx] = k; T.slab_lo[a + idx] = llo; T.slab_hi[a + idx] = lhi;
+    T.skey[a + idx] = k;
     const uint32_t w = idx >> 5, bitv = 1u << (idx & 31);
     while (llo) { const uint32_t b = __ffsll((long long)llo) - 1; llo &= llo - 1; atomicOr(&bm[(size_t)b * words + w], bitv); }
     while (lhi) { const uint32_t b = 64 + __ffsll((long long)lhi) - 1; lhi &= lhi - 1; atomicOr(&bm[(size_t)b * words + w], bitv); }
+    for (uint32_t x = 0; x < T.wide.xw_place; ++x)   // label bits 128...
+      for (uint64_t lx = T.pos_label_x[(size_t)src * T.wide.xw_place + x]; lx; lx &= lx - 1)
+        atomicOr(&bm[(size_t)(128u + 64u * x + (uint32_t)__ffsll((long long)lx) - 1u) * words + w], bitv);
     cnt += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
     ok += key_over(k) ? 0u : 1u;
   }
@@ -224,6 +231,41 @@ __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
     if (s_nok) atomicAdd(&T.pool_nok[p], s_nok);
     if (c == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_sorted[p] = 1; }
   }
+}
+
+// ------------------------------------------------------------------ wide masks (tables.h WideLayout)
+// Everything below is reached only when a dictionary outgrew the records' own mask fields (T.wide_words != 0).
+__device__ __forceinline__ bool wide_need_ok(const DeviceTables& T, uint32_t r, const uint64_t* wrow, uint32_t flags) {
+  const uint32_t xq = T.wide.xw_req, xl = T.wide.xw_lab;
+  const uint64_t* nx = T.rule_need_x + (size_t)r * (xq + xl);
+  for (uint32_t k = 0; k < xq; ++k) if (__ldg(nx + k) & ~__ldg(wrow + WIDE_O_REQ(T.wide) + k)) return false;   // containsAll (:320-330)
+  uint64_t any = 0;
+  bool sub = true;
+  for (uint32_t k = 0; k < xl; ++k) { const uint64_t n = __ldg(nx + xq + k); any |= n; sub &= (n & ~__ldg(wrow + WIDE_O_LAB(T.wide) + k)) == 0; }
+  return any == 0 || ((flags & JF_HAS_LABELS) && sub);                                                            // labelsMatch (:332-345)
+}
+// poolSatisfies' subset test (:255-262) over all words of the requires mask
+__device__ __forceinline__ bool pool_req_subset(const DeviceTables& T, uint32_t pid, uint64_t need_req, const uint64_t* wrow) {
+  if (need_req & ~__ldg(T.pool_req_mask + pid)) return false;
+  if (wrow) {
+    const uint32_t xq = T.wide.xw_req;
+    for (uint32_t k = 0; k < xq; ++k)
+      if ((__ldg(wrow + WIDE_O_REQP(T.wide) + k) & ~__ldg(T.req_blank_x + k)) & ~__ldg(T.pool_req_x + (size_t)pid * xq + k)) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ bool place_x_any(const DeviceTables& T, const uint64_t* wrow) {
+  uint64_t any = 0;
+  if (wrow) for (uint32_t k = 0; k < T.wide.xw_place; ++k) any |= __ldg(wrow + WIDE_O_PLACE(T.wide) + k);
+  return any != 0;
+}
+__device__ __forceinline__ bool place_x_ok(const DeviceTables& T, uint32_t pos, const uint64_t* wrow) {   // matchesLabels (:161-175), bits 128...
+  if (wrow)
+    for (uint32_t k = 0; k < T.wide.xw_place; ++k) {
+      const uint64_t need = __ldg(wrow + WIDE_O_PLACE(T.wide) + k);
+      if ((__ldg(T.pos_label_x + (size_t)pos * T.wide.xw_place + k) & need) != need) return false;
+    }
+  return true;
 }
 
 // ------------------------------------------------------------------ policy: first match + decision
@@ -314,6 +356,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
     const bool eval = valid && !bypass && !early;
     const bool mcp_used = (c_flags & JF_MCP_USED) != 0;
     const uint32_t combo = CORDUM_COMBO_INDEX(c_flags);
+    const uint64_t* wrow = (T.wide_words && valid) ? P.recs.wide + (size_t)s * T.wide_words : nullptr;   // rare: masks beyond the record's
     uint64_t live = 0;
     if (eval) {
       live = __ldg(T.sum_topic + c_topic);
@@ -325,6 +368,9 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
       if (use & SUM_RISK) {
         uint64_t rs = c_risk ? 0ull : __ldg(T.sum_risk);
         for (uint64_t m = c_risk; m; m &= m - 1) rs |= __ldg(T.sum_risk + __ffsll((long long)m));
+        if (wrow)
+          for (uint32_t k = 0; k < T.wide.xw_risk; ++k)
+            for (uint64_t m = __ldg(wrow + k); m; m &= m - 1) rs |= __ldg(T.sum_risk + 64u * (k + 1u) + (uint32_t)__ffsll((long long)m));
         live &= rs;
       }
     }
@@ -353,6 +399,9 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
         if (risk2) rk = or4(rk, __ldg(bw + i_risk1));
         if (risk3) rk = or4(rk, __ldg(bw + i_risk2));
         for (uint64_t m = rm; m; m &= m - 1) rk = or4(rk, __ldg(bw + T.off_risk + (uint32_t)__ffsll((long long)m)));
+        if (wrow)   // tags 64...: row 1 + tag
+          for (uint32_t k = 0; k < T.wide.xw_risk; ++k)
+            for (uint64_t m = __ldg(wrow + k); m; m &= m - 1) rk = or4(rk, __ldg(bw + T.off_risk + 64u * (k + 1u) + (uint32_t)__ffsll((long long)m)));
         uint4 acc = and3(__ldg(bw + i_topic), __ldg(bw + i_tenant), __ldg(bw + i_cap));
         acc = and3(acc, __ldg(bw + i_pack), __ldg(bw + i_actor));
         acc = and3(acc, __ldg(bw + i_combo), rk);
@@ -374,6 +423,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
           if ((__ldg(T.chk_words + (pos >> 5)) >> (pos & 31)) & 1u) {
             const uint64_t need = __ldg(T.rule_req_need + r), ln = __ldg(T.rule_lab_need + r);
             ok = ((need & ~c_req) == 0) && (ln == 0 || ((c_flags & JF_HAS_LABELS) && (ln & ~c_lab) == 0));
+            if (ok && wrow) ok = wide_need_ok(T, r, wrow, c_flags);
           }
           if (ok) { best = r < best ? r : best; break; }
           const uint32_t drop = sel & (sel - 1);
@@ -475,6 +525,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       c_plo = ((uint64_t)r0.y << 32) | r0.x; c_phi = ((uint64_t)r0.w << 32) | r0.z;
       c_req = ((uint64_t)r1.y << 32) | r1.x; c_ppool = r1.z; c_pwork = r1.w;
     }
+    const uint64_t* wrow = (T.wide_words && valid) ? P.recs.wide + (size_t)j * T.wide_words : nullptr;   // rare: masks beyond the record's
     uint32_t rflags = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
     int slot = -1;
 
@@ -501,7 +552,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
           const bool req_any = c_flags & JF_REQ_NONEMPTY, req_unknown = c_flags & JF_REQ_UNKNOWN;
           const uint64_t need_req = c_req & ~T.req_blank_mask;
           const bool unsat = c_flags & JF_PLACE_UNSAT;
-          const bool labelled = (c_plo | c_phi) != 0 || unsat;
+          const bool labelled = (c_plo | c_phi) != 0 || unsat || place_x_any(T, wrow);
           int pw_pos = -1;
           uint32_t pw_pool = 0xFFFFFFFFu;
           if (c_pwork && c_pwork != CORDUM_PREF_UNKNOWN) {
@@ -513,7 +564,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
           for (uint32_t k = 0; k < r_cnt; ++k) {
             const uint32_t pid = r_single >= 0 ? (uint32_t)r_single : __ldg(T.pool_list + r_off + k);
             // poolSatisfies (:241-265)
-            if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+            if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && pool_req_subset(T, pid, need_req, wrow))) continue;
             n_elig++;
             pw_in_set |= pid == pw_pool;
             if (!labelled) {
@@ -526,7 +577,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
             bool took_pref = false;
             if (pw_pos >= 0 && pw_in_set && !unsat) {                           // :73-87
               uint64_t llo = __ldg(T.pos_label_lo + pw_pos), lhi = __ldg(T.pos_label_hi + pw_pos);
-              if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && !key_over(T.pos_key[pw_pos])) {
+              if ((llo & c_plo) == c_plo && (lhi & c_phi) == c_phi && place_x_ok(T, (uint32_t)pw_pos, wrow) && !key_over(T.pos_key[pw_pos])) {
                 took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
               }
             }
@@ -558,6 +609,8 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       const uint64_t need_req = shfl64(FULL, c_req, s_) & ~T.req_blank_mask;
       const uint64_t need_lo = shfl64(FULL, c_plo, s_), need_hi = shfl64(FULL, c_phi, s_);
       const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+      const uint32_t jw = __shfl_sync(FULL, j, s_);
+      const uint64_t* wr = (T.wide_words && act) ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
       // required label bits -> bitmap row numbers, once per job (not per pool and word): four 8-bit row numbers in lbp
       uint32_t lbp = 0, nlb = 0;
       bool more;
@@ -571,14 +624,14 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
           else if (rh) { bit = 64u + (uint32_t)__ffsll((long long)rh) - 1u; rh &= rh - 1; got = true; }
           if (got) { nlb = (uint32_t)t + 1u; lbp |= bit << (8 * t); }
         }
-        more = (rl | rh) != 0;
+        more = (rl | rh) != 0 || place_x_any(T, wr);
       }
       uint64_t b = KEY_NONE;
       uint32_t bc = 0, tot = 0;
       for (uint32_t k = 0; __any_sync(FULL, k < cnt); ++k) {
         const bool kin = k < cnt;
         const uint32_t pid = kin ? (single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k)) : 0u;
-        const bool elig = kin && (!req_any || (__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0));
+        const bool elig = kin && (!req_any || (__ldg(T.pool_req_nonempty + pid) && !req_unknown && pool_req_subset(T, pid, need_req, wr)));
         const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
         const uint32_t words = elig ? (e - a + 31) >> 5 : 0u, nok = T.pool_nok[pid];
         const uint32_t* bm = T.lbm + __ldg(T.lbm_off + pid);
@@ -598,6 +651,10 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
             if (more) {   // AND is idempotent: walk all required bits again
               for (uint64_t m = need_lo; m; m &= m - 1) v &= bm[(uint32_t)(__ffsll((long long)m) - 1) * words + w];
               for (uint64_t m = need_hi; m; m &= m - 1) v &= bm[(uint32_t)(64 + __ffsll((long long)m) - 1) * words + w];
+              if (wr)
+                for (uint32_t x = 0; x < T.wide.xw_place; ++x)
+                  for (uint64_t m = __ldg(wr + WIDE_O_PLACE(T.wide) + x); m; m &= m - 1)
+                    v &= bm[(size_t)(128u + 64u * x + (uint32_t)__ffsll((long long)m) - 1u) * words + w];
             }
           }
           tot += __popc(v);                                     // label-matching candidates, overloaded ones included
@@ -638,15 +695,17 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       const uint64_t need_req = shfl64(FULL, c_req, i) & ~T.req_blank_mask;
       const uint64_t need_lo = shfl64(FULL, c_plo, i), need_hi = shfl64(FULL, c_phi, i);
       const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
+      const uint32_t jw = __shfl_sync(FULL, j, i);
+      const uint64_t* wr = T.wide_words ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
       uint64_t b = KEY_NONE;
       uint32_t bc = 0, tot = 0;
       for (uint32_t k = 0; k < cnt; ++k) {
         const uint32_t pid = single >= 0 ? (uint32_t)single : __ldg(T.pool_list + off + k);
-        if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && (need_req & ~__ldg(T.pool_req_mask + pid)) == 0)) continue;
+        if (req_any && !(__ldg(T.pool_req_nonempty + pid) && !req_unknown && pool_req_subset(T, pid, need_req, wr))) continue;
         const uint32_t a = __ldg(T.pool_off + pid), e = __ldg(T.pool_off + pid + 1);
         for (uint32_t pos = a + lane; pos < e; pos += 32) {   // matchesLabels (:161-175), coalesced
           const uint64_t llo = __ldg(T.pos_label_lo + pos), lhi = __ldg(T.pos_label_hi + pos);
-          if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi) continue;
+          if ((llo & need_lo) != need_lo || (lhi & need_hi) != need_hi || !place_x_ok(T, pos, wr)) continue;
           tot++;
           merge_best(b, bc, T.pos_key[pos], 1);
         }

@@ -102,12 +102,27 @@ typedef struct EncodeTables {
   uint32_t default_tenant;        /* tenant id | exact-policy index << 16 of the fallback tenant          */
   uint32_t place_any_bit;
   uint64_t label_empty_mask;
+  uint32_t wide_words;            /* != 0: the device encoder hands the whole batch to the host encoder            */
 } EncodeTables;
 
 typedef struct JobRecords {
   const JobRec* job;
   const RouteRec* route;
+  const uint64_t* wide;   /* [n_jobs][DeviceTables.wide_words], same (sorted) order; NULL when wide_words == 0 */
 } JobRecords;
+
+/* Wide masks.  The records hold 64 bits per mask (placement: 128).  A policy that references more than 64 distinct risk
+   tags / requires tokens / label pairs, or a registry with more than 128 placement-label bits, spills the further bits into
+   a side row of 64-bit words per job: [risk xw_risk][requires, EqualFold form xw_req][label pairs xw_lab]
+   [requires, ToLower form xw_req][placement xw_place].  All xw_* are 0 in the common case and nothing of this is read. */
+typedef struct WideLayout {
+  uint32_t xw_risk, xw_req, xw_lab, xw_place;
+} WideLayout;
+#define WIDE_WORDS(L) ((L).xw_risk + 2u * (L).xw_req + (L).xw_lab + (L).xw_place)
+#define WIDE_O_REQ(L) ((L).xw_risk)
+#define WIDE_O_LAB(L) ((L).xw_risk + (L).xw_req)
+#define WIDE_O_REQP(L) ((L).xw_risk + (L).xw_req + (L).xw_lab)
+#define WIDE_O_PLACE(L) ((L).xw_risk + 2u * (L).xw_req + (L).xw_lab)
 
 /* Everything the kernels read besides the job columns.  Pointers are device pointers. */
 #define CORDUM_POOL_CHUNK 512u
@@ -128,6 +143,11 @@ typedef struct DeviceTables {
   const uint32_t* chk_words;                  /* bit per position: the rule carries a requires/labels need-mask       */
   const uint64_t* rule_req_need;              /* per rule: requires tokens it needs (subset test)       */
   const uint64_t* rule_lab_need;              /* per rule: label pairs it needs                          */
+  WideLayout wide;  uint32_t wide_words;      /* extra mask words (see WideLayout); wide_words = WIDE_WORDS(wide)           */
+  const uint64_t* rule_need_x;                /* [n_rules][xw_req + xw_lab]: the rules' needs beyond bit 63               */
+  const uint64_t* pool_req_x;                 /* [n_pools][xw_req]                                                        */
+  const uint64_t* req_blank_x;                /* [xw_req]                                                                  */
+  const uint64_t* pos_label_x;                /* [n_pos][xw_place]: placement label bits 128...                           */
   const uint8_t* rule_dec;                    /* per rule: CORDUM_DEC_* | 0x80 if constraints non-empty */
   const uint32_t* pos2rule;                   /* bit position -> rule index                              */
   /* tenant-level MCP lists (kernel.go:190-195) and effective-config overlay (kernel.go:218-231):
@@ -157,14 +177,12 @@ typedef struct DeviceTables {
   const Load16* loads;                          /* [n_slots] {active, max_parallel, cpu(f32), gpu(f32)}   */
   uint64_t* pos_key;                          /* derived: (orderable score << 32) | rank; score field all-ones = overloaded */
   uint64_t* skey;                             /* derived: per pool, keys in ascending order (load-sorted view of the pool)  */
-  uint64_t* slab_lo;                          /* derived: label masks permuted into the same order                          */
-  uint64_t* slab_hi;
   uint8_t* pool_sorted;                       /* derived: 1 if the pool's sorted view is valid (pool fits the sort buffer)  */
   uint32_t* pool_nok;                         /* derived: workers of the pool that are NOT overloaded (= prefix of the sorted view) */
   uint32_t* lbm;                              /* derived: label bitmaps over the sorted view: lbm[lbm_off[p] + bit*words(p) + w],
                                                  bit i of word w = "sorted worker 32w+i carries label bit"               */
   const uint32_t* lbm_off;                    /* [n_pools] word offset of the pool's bitmaps                               */
-  uint32_t place_bits;                        /* label bits in use (<= 128)                                                */
+  uint32_t place_bits;                        /* label bits in use (beyond 128: pos_label_x)                               */
   /* worker-table refresh: a pool is cut into chunks of CORDUM_POOL_CHUNK workers, one CTA sorts one chunk, a second
      kernel merges the chunks of pools that have more than one (pools above CORDUM_POOL_SORT_MAX stay unsorted)       */
   const uint32_t* chunk_pool;                 /* [n_chunks] pool of the chunk                                              */

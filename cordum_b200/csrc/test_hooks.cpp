@@ -36,12 +36,16 @@ int32_t cordum_test_host_update(void* h, uint32_t n, const uint32_t* slots, cons
   return ((Host*)h)->update_loads(n, slots, loads, t_err);
 }
 uint64_t cordum_test_slab_bytes(uint32_t n) { return (uint64_t)n * (sizeof(JobRec) + sizeof(RouteRec) + sizeof(uint32_t)); }
+uint32_t cordum_test_host_wide_words(void* h) { return ((Host*)h)->wide_words(); }
 
 // encode into `slab` (cordum_test_slab_bytes(n) bytes, 16 B aligned): n JobRec, then n RouteRec (both in topic-sorted
 // order, as a batch's pinned buffers hold them), then slot_of[n]
-int32_t cordum_test_host_encode(void* h, const cordum_envelopes* env, uint8_t* slab) {
+// `wide`: n * cordum_test_host_wide_words(h) 64-bit words (may be NULL when that is 0)
+int32_t cordum_test_host_encode(void* h, const cordum_envelopes* env, uint8_t* slab, uint64_t* wide) {
   uint32_t n = env->n_jobs;
   HostRecords r;
+  r.wide = wide;
+  r.wide_cap = (uint64_t)n * ((Host*)h)->wide_words();
   r.job = (JobRec*)slab;
   r.route = (RouteRec*)(slab + (size_t)n * sizeof(JobRec));
   r.slot_of = (uint32_t*)(slab + (size_t)n * (sizeof(JobRec) + sizeof(RouteRec)));
@@ -71,6 +75,7 @@ int32_t cordum_test_host_table(void* h, const char* name, const void** ptr, uint
   VEC("sum_tenant", t.sum_tenant) VEC("sum_topic", t.sum_topic) VEC("sum_cap", t.sum_cap) VEC("sum_pack", t.sum_pack)
   VEC("sum_actor", t.sum_actor) VEC("sum_combo", t.sum_combo) VEC("sum_risk", t.sum_risk)
   VEC("rule_req_need", t.rule_req_need) VEC("rule_lab_need", t.rule_lab_need) VEC("rule_dec", t.rule_dec)
+  VEC("rule_need_x", t.rule_need_x) VEC("pool_req_x", t.pool_req_x) VEC("req_blank_x", t.req_blank_x) VEC("pos_label_x", t.pos_label_x)
   VEC("tenant_mcp", t.tenant_mcp) VEC("eff_mcp", t.eff_mcp) VEC("eff_topic", t.eff_topic)
   VEC("topic_pool_off", t.topic_pool_off) VEC("topic_pool_cnt", t.topic_pool_cnt) VEC("pool_list", t.pool_list)
   VEC("pool_req_mask", t.pool_req_mask) VEC("pool_req_nonempty", t.pool_req_nonempty)
@@ -101,6 +106,11 @@ uint64_t cordum_test_host_scalar(void* h, const char* name) {
   if (n == "n_pos") return t.n_pos;
   if (n == "n_slots") return t.n_slots;
   if (n == "n_topics") return t.row_topic.n_rows;
+  if (n == "xw_risk") return t.wide.xw_risk;
+  if (n == "xw_req") return t.wide.xw_req;
+  if (n == "xw_lab") return t.wide.xw_lab;
+  if (n == "xw_place") return t.wide.xw_place;
+  if (n == "place_bits") return t.place_bits;
   return ~0ull;
 }
 

@@ -38,9 +38,10 @@ TABLES = {
     "pos_pool": np.uint32, "pos_slot": np.uint32, "pos_rank": np.uint32, "slot_pos": np.uint32, "rank_slot": np.uint32,
     "pos_label_lo": np.uint64, "pos_label_hi": np.uint64, "loads": wire.LOAD_DTYPE,
     "chunk_pool": np.uint32, "pool_chunk0": np.uint32, "merge_list": np.uint32,
+    "rule_need_x": np.uint64, "pool_req_x": np.uint64, "req_blank_x": np.uint64, "pos_label_x": np.uint64,
 }
 SCALARS = ["n_rules", "n_seg", "sum_group", "sum_use", "n_chunks", "n_merge", "merge_smem", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
-           "n_pos", "n_slots", "n_topics"]
+           "n_pos", "n_slots", "n_topics", "xw_risk", "xw_req", "xw_lab", "xw_place", "place_bits"]
 
 
 def _align16(x):
@@ -106,7 +107,10 @@ class HostHarness:
         slab = np.zeros(int(self.L.cordum_test_slab_bytes(n)) + 64, dtype=np.uint8)
         base = (-slab.ctypes.data) % 16
         slab = slab[base:]
-        self._ck(self.L.cordum_test_host_encode(self.h, C.addressof(env.struct), slab.ctypes.data))
+        ww = int(self.L.cordum_test_host_wide_words(self.h))
+        wide = np.zeros(max(n * ww, 1), dtype=np.uint64)
+        self._ck(self.L.cordum_test_host_encode(self.h, C.addressof(env.struct), slab.ctypes.data, wide.ctypes.data))
+        assert int(self.L.cordum_test_host_wide_words(self.h)) == ww
         job = slab[: 64 * n].view(JOB_DTYPE).copy()
         route = slab[64 * n: 96 * n].view(ROUTE_DTYPE).copy()
         slot_of = slab[96 * n: 100 * n].view(np.uint32).copy()
@@ -124,6 +128,29 @@ class HostHarness:
         for k in ("place_lo", "place_hi", "req_pool", "pref_pool", "pref_worker"):
             cols[k] = r[k]
         cols["_job"], cols["_route"], cols["_slot_of"] = job, route, slot_of
+        # wide masks (tables.h WideLayout): fold the extra words of each mask into one Python int per job
+        xr, xq, xl, xp = (int(self.L.cordum_test_host_scalar(self.h, k)) for k in (b"xw_risk", b"xw_req", b"xw_lab", b"xw_place"))
+        assert ww == xr + 2 * xq + xl + xp
+        wrows = wide[: n * ww].reshape(n, ww)[slot_of] if ww else np.zeros((n, 0), np.uint64)
+        cols["_wide"] = wrows
+
+        def fold(base_cols, off, cnt):
+            out = []
+            for i in range(n):
+                v, sh = 0, 0
+                for c in base_cols:
+                    v |= int(cols[c][i]) << sh
+                    sh += 64
+                for k in range(cnt):
+                    v |= int(wrows[i, off + k]) << sh
+                    sh += 64
+                out.append(v)
+            return out
+        cols["risk_mask"] = fold(["risk_mask"], 0, xr)
+        cols["req_mask"] = fold(["req_mask"], xr, xq)
+        cols["lab_mask"] = fold(["lab_mask"], xr + xq, xl)
+        cols["req_pool"] = fold(["req_pool"], xr + xq + xl, xq)
+        cols["place"] = fold(["place_lo", "place_hi"], xr + 2 * xq + xl, xp)
         return cols
 
     def tables(self) -> dict:
@@ -138,6 +165,22 @@ class HostHarness:
                 t[name] = np.frombuffer(buf, dtype=dt).copy()
         for s in SCALARS:
             t[s] = int(self.L.cordum_test_host_scalar(self.h, s.encode()))
+        # fold the wide words (tables.h WideLayout) into one Python int per rule / pool / worker
+        xq, xl, xp = t["xw_req"], t["xw_lab"], t["xw_place"]
+
+        def wide_int(arr, base, cnt):
+            v = 0
+            for k in range(cnt):
+                v |= int(arr[base + k]) << (64 * k)
+            return v
+        nr = len(t["rule_req_need"])
+        rx = t["rule_need_x"]
+        t["rule_req_need"] = [int(t["rule_req_need"][r]) | (wide_int(rx, r * (xq + xl), xq) << 64 if (xq and (r + 1) * (xq + xl) <= len(rx)) else 0) for r in range(nr)]
+        t["rule_lab_need"] = [int(t["rule_lab_need"][r]) | (wide_int(rx, r * (xq + xl) + xq, xl) << 64 if (xl and (r + 1) * (xq + xl) <= len(rx)) else 0) for r in range(nr)]
+        t["pool_req_mask"] = [int(m) | (wide_int(t["pool_req_x"], p * xq, xq) << 64) for p, m in enumerate(t["pool_req_mask"])]
+        t["req_blank_mask"] = int(t["req_blank_mask"]) | (wide_int(t["req_blank_x"], 0, xq) << 64)
+        t["pos_label"] = [int(lo) | int(hi) << 64 | (wide_int(t["pos_label_x"], i * xp, xp) << 128)
+                          for i, (lo, hi) in enumerate(zip(t["pos_label_lo"], t["pos_label_hi"]))]
         return t
 
     def evaluate(self, env, mode=wire.MODE_POLICY_AND_ROUTE) -> np.ndarray:
@@ -218,7 +261,7 @@ def walk(T, cols, mode) -> np.ndarray:
                     rk = rows["row_risk"][0]
                 else:
                     rk = np.zeros(W, np.uint32)
-                    for b in range(64):
+                    for b in range(risk.bit_length()):
                         if risk >> b & 1:
                             rk = rk | rows["row_risk"][1 + b]
                 acc = acc & rk
@@ -245,7 +288,7 @@ def walk(T, cols, mode) -> np.ndarray:
                     live &= int(T["sum_combo"][(flags & JF_COMBO_MASK) + ((flags >> 14) & 3) * 6])
                 if use & SUM_RISK:
                     rs = int(T["sum_risk"][0]) if risk == 0 else 0
-                    for b in range(64):
+                    for b in range(risk.bit_length()):
                         if risk >> b & 1:
                             rs |= int(T["sum_risk"][1 + b])
                     live &= rs
@@ -346,9 +389,9 @@ def walk(T, cols, mode) -> np.ndarray:
                 if route == 0:
                     req_any, req_unknown = bool(flags & JF_REQ_NONEMPTY), bool(flags & JF_REQ_UNKNOWN)
                     need_req = int(cols["req_pool"][j]) & ~T["req_blank_mask"]
-                    need_lo, need_hi = int(cols["place_lo"][j]), int(cols["place_hi"][j])
+                    need_pl = int(cols["place"][j])
                     unsat = bool(flags & JF_PLACE_UNSAT)
-                    labelled = (need_lo | need_hi) != 0 or unsat
+                    labelled = need_pl != 0 or unsat
 
                     def elig(p):
                         if not req_any:
@@ -364,7 +407,7 @@ def walk(T, cols, mode) -> np.ndarray:
                     elif not unsat:
                         for p in el:
                             for pos in range(int(T["pool_off"][p]), int(T["pool_off"][p + 1])):
-                                if (int(T["pos_label_lo"][pos]) & need_lo) != need_lo or (int(T["pos_label_hi"][pos]) & need_hi) != need_hi:
+                                if (T["pos_label"][pos] & need_pl) != need_pl:
                                     continue
                                 total += 1
                                 best, bcnt = _merge(best, bcnt, key[pos], 1)
@@ -377,7 +420,7 @@ def walk(T, cols, mode) -> np.ndarray:
                             p1 = int(T["slot_pos"][pw - 1])
                             if p1 and int(T["pos_pool"][p1 - 1]) in el and not unsat:
                                 pos = p1 - 1
-                                lab_ok = (int(T["pos_label_lo"][pos]) & need_lo) == need_lo and (int(T["pos_label_hi"][pos]) & need_hi) == need_hi
+                                lab_ok = (T["pos_label"][pos] & need_pl) == need_pl
                                 if lab_ok and key[pos] != KEY_NONE:
                                     took, route, slot = True, wire.ROUTE_OK_PREFERRED, pw - 1
                         if not took:

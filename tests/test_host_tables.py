@@ -110,11 +110,12 @@ def test_policy_reload_changes_answers():
 
 
 def test_capacity_errors_fail_closed():
-    rules = [{"id": "r%d" % i, "decision": "deny", "match": {"risk_tags": ["tag%d" % i]}} for i in range(65)]
-    h = table_walk.HostHarness()
-    with pytest.raises(RuntimeError, match="64 distinct risk tags"):
+    """What still has a ceiling: 16-bit dictionary ids in the job record.  (Mask widths do not: test_wide_masks.py.)"""
+    rules = [{"id": "r", "decision": "deny", "match": {"capabilities": ["cap%d" % i for i in range(70000)]}}]
+    h = table_walk.HostHarness({"rules": [{"id": "ok", "decision": "deny", "match": {"topics": ["job.x"]}}]})
+    with pytest.raises(RuntimeError, match="65535 distinct values"):
         h.load_policy({"rules": rules})
-    h.load_policy({"rules": rules[:64]})   # exactly at capacity is fine
+    assert h.evaluate([{"topic": "job.x"}])["decision"][0] == wire.DEC_DENY   # the previous policy still serves
 
 
 @pytest.mark.parametrize("sizes", [[0], [1], [512], [513], [1500, 3, 0, 600], [8192, 8193], [20000]])
@@ -181,8 +182,8 @@ def test_rejected_worker_load_keeps_the_previous_registry():
     want = o.eval(jobs, wire.MODE_ROUTE_ONLY)
     assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "before")
     before = h.tables()
-    too_many = [kats.hb("w%03d" % i, "p", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(80)]   # 80 keys + 80 pairs > 128 bits
-    with pytest.raises(RuntimeError, match="placement-label"):
+    too_many = [kats.hb("w%05d" % i, "p", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(33000)]   # 33000 keys + 33000 pairs > 65536 bits
+    with pytest.raises(RuntimeError, match="placement labels"):
         h.load_workers(too_many)
     nan = [kats.hb("w0", "p", 1, float("nan"), 0.0, 4)]
     with pytest.raises(RuntimeError, match="NaN"):
@@ -205,7 +206,7 @@ def test_rejected_worker_load_keeps_the_previous_registry():
 def test_rejected_routing_load_keeps_the_previous_routing():
     """A routing reload that makes more labelled workers routable than the label dictionary holds is refused whole."""
     workers = [kats.hb("a%03d" % i, "p", 0, float(i), 0.0, 0, {"zone": "z"}) for i in range(3)] + \
-              [kats.hb("b%03d" % i, "q", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(80)]
+              [kats.hb("b%05d" % i, "q", 0, 1.0, 0.0, 0, {"host-%d" % i: "x"}) for i in range(33000)]
     r1 = {"topics": {"job.a": ["p"]}, "pools": {"p": {}}}
     r2 = {"topics": {"job.a": ["p", "q"]}, "pools": {"p": {}, "q": {}}}
     jobs = [{"topic": "job.a"}, {"topic": "job.a", "labels": {"zone": "z"}}]
@@ -213,6 +214,6 @@ def test_rejected_routing_load_keeps_the_previous_routing():
     o = oracle_lib.Oracle(None, r1, workers)
     want = o.eval(jobs, wire.MODE_ROUTE_ONLY)
     assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "before")
-    with pytest.raises(RuntimeError, match="placement-label"):
+    with pytest.raises(RuntimeError, match="placement labels"):
         h.load_routing(r2)
     assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "after the rejected routing")
