@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128) encode_job_kernel(EncodeParams P) {
         bit = find_exact(E, DD_PLACE_KEY, key, kMiss);
         if (bit == kMiss) bit = E.place_any_bit;   // no worker carries this key: any labelled worker passes
       }
-      if (bit != kMiss) place[bit >> 6] |= 1ull << (bit & 63);
+      if (bit != kMiss && bit < 128) place[bit >> 6] |= 1ull << (bit & 63);   // bits beyond 128: wide tables, the batch goes to the host encoder
     }
   }
   // ---- MCP request (extractMCPRequest, kernel.go:395-414) and secrets (kernel.go:381-393)

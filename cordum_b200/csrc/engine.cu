@@ -18,6 +18,7 @@
 
 #include "../../include/cordum_b200.h"
 #include "host.hpp"
+#include "../../common/nvtx_range.hpp"
 #include "kernels.h"
 
 using cordum::Host;
@@ -126,7 +127,7 @@ struct cordum_engine {
   // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
   // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
   struct DerivedSet {
-    DevBuf loads, pos_key, ckey, skey, pool_sorted, pool_nok, lbm, pool_best, pool_mincnt;
+    DevBuf loads, pos_key, ckey, skey, pool_sorted, pool_nok, lbm, lbest, pool_best, pool_mincnt;
     cudaEvent_t ready = nullptr, loads_read = nullptr;   // refresh complete / load table consumed by the refresh
   } ds[kSets];
   int cur = 0;                   // set holding the latest refresh
@@ -198,6 +199,7 @@ cudaError_t up(DevBuf& b, const std::vector<T>& v, cudaStream_t s) { return b.up
 
 // Bring the device tables up to date with the host tables.  Called with host mutex held.
 int sync_tables(cordum_engine* e) {
+  cordum::NvtxRange nvtx_("cordum:table_upload");
   const HostTables& t = e->host->tables();
   DeviceTables& d = e->dt;
   bool any = t.v_policy != e->v_policy || t.v_topic != e->v_topic || t.v_mcp != e->v_mcp || t.v_routing != e->v_routing ||
@@ -288,6 +290,7 @@ int sync_tables(cordum_engine* e) {
       CK(D.pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
       CK(D.pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
       CK(D.lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
+      if (t.place_bits <= CORDUM_LBEST_MAX_BITS) CK(D.lbest.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * t.place_bits * 16), "alloc");
       CK(D.loads.reserve((size_t)std::max<uint32_t>(t.n_slots, 1) * sizeof(Load16)), "alloc");
     }
     CK(up(e->b_chunk_pool, t.chunk_pool, s), "upload"); CK(up(e->b_pool_chunk0, t.pool_chunk0, s), "upload");
@@ -377,6 +380,7 @@ DeviceTables view(const cordum_engine* e, int set) {
   d.loads = (const Load16*)D.loads.p;
   d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p;
   d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.lbm = (uint32_t*)D.lbm.p;
+  d.lbest = d.place_bits <= CORDUM_LBEST_MAX_BITS ? (uint4*)D.lbest.p : nullptr;
   d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
   return d;
 }
@@ -384,6 +388,7 @@ DeviceTables view(const cordum_engine* e, int set) {
 // worker-table refresh kernels for a new heartbeat epoch, into the set that is NOT being read.  dev_loads: the full slot-ordered
 // load table already in HBM (produced on `producer`), or null to take the host tables' loads.  Called with both mutexes held.
 int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer) {
+  cordum::NvtxRange nvtx_("cordum:worker_refresh");
   if (!e->pools_dirty && !dev_loads) return CORDUM_OK;
   const int target = (e->cur + 1) % kSets;
   auto& D = e->ds[target];
@@ -409,7 +414,7 @@ int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer
     CK(cudaMemcpyAsync(D.loads.p, t.loads.data(), bytes, cudaMemcpyHostToDevice, e->s_tables), "H2D loads");
   }
   CK(launch_worker_pools(view(e, target), e->s_tables, D.loads_read), "worker-table refresh kernels");
-  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0);
   CK(cudaEventRecord(D.ready, e->s_tables), "event record");
   e->cur = target;
   e->pools_dirty = false;
@@ -417,6 +422,7 @@ int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer
 }
 
 int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool copy_out) {
+  cordum::NvtxRange nvtx_("cordum:dispatch");
   if (!e || !b) { g_err = "null handle"; return CORDUM_E_INVALID; }
   const bool flush_l2 = mode & CORDUM_FLAG_FLUSH_L2;
   const bool timed = !(mode & CORDUM_FLAG_NO_TIMING);   // per-kernel timing events cost two API calls per dispatch
@@ -498,6 +504,7 @@ int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* 
 
 int wait(cordum_batch* b) {
   cordum_engine* e = b->e;
+  cordum::NvtxRange nvtx_("cordum:wait");
   if (b->tick_pending) {   // dispatched by a tick: its route runs in the tick after its policy (or in the flush)
     {
       std::lock_guard<std::mutex> g(e->mu);
@@ -671,7 +678,7 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
     CK(cudaGraphLaunch(ge, e->s_tables), "graph launch");
     CK(cudaEventRecord(e->gather_free[g], e->s_tables), "event record");
     CK(cudaEventRecord(D.ready, e->s_tables), "event record");
-    e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (use_peers ? 1 : 0);
+    e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0) + (use_peers ? 1 : 0);
     e->cur = target;
     e->pools_dirty = false;
     e->host_loads = false;
@@ -698,7 +705,7 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
   DeviceTables tv = view(e, target);
   tv.loads = (const Load16*)table;   // the refresh reads the gathered table in place
   CK(launch_worker_pools(tv, e->s_tables, e->gather_free[g]), "worker-table refresh kernels");
-  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0);
   CK(cudaEventRecord(D.ready, e->s_tables), "event record");
   e->cur = target;
   e->pools_dirty = false;
@@ -823,6 +830,7 @@ int tick_setup(cordum_engine* e) {
 
 // one tick; e->mu and the host mutex held.  bn may be null (flush: only route the previous batch)
 int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* slice, uint32_t n_slice) {
+  cordum::NvtxRange nvtx_("cordum:tick");
   auto& T = e->tick;
   const HostTables& t = e->host->tables();
   const uint32_t W = t.n_slots;
@@ -892,7 +900,7 @@ int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* sl
       acc[0] = acc[1] = acc[2] = acc[3] = 0;
     }
   }
-  e->launches += (W ? (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->peers.ready && e->peers.world > 1 ? 1 : 0) : 0) + (bn->n ? 1 : 0) + (T.prev && T.prev->n ? 1 : 0);
+  e->launches += (W ? (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0) + (e->peers.ready && e->peers.world > 1 ? 1 : 0) : 0) + (bn->n ? 1 : 0) + (T.prev && T.prev->n ? 1 : 0);
   e->cur = phase % 3;   // the set this tick refreshed (a later plain dispatch continues from it)
   e->pools_dirty = false; e->host_loads = false;
   bn->tick_no = T.n;
@@ -904,6 +912,7 @@ int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* sl
 int tick_flush_locked(cordum_engine* e) { return tick_locked(e, nullptr, nullptr, 0); }
 
 int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
+  cordum::NvtxRange nvtx_("cordum:encode_host");
   if (!env) { g_err = "envelopes no longer available for the host encoder"; return CORDUM_E_STATE; }
   b->n = env->n_jobs;
   b->encoded = false;
@@ -1022,7 +1031,7 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_chunk_pool, &e->b_pool_chunk0, &e->b_merge_list};
   for (DevBuf* b : all) b->release();
   for (auto& D : e->ds) {
-    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.pool_best, &D.pool_mincnt}) b->release();
+    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.lbest, &D.pool_best, &D.pool_mincnt}) b->release();
     if (D.ready) cudaEventDestroy(D.ready);
     if (D.loads_read) cudaEventDestroy(D.loads_read);
   }
@@ -1039,6 +1048,7 @@ void cordum_engine_destroy(cordum_engine* e) {
 }
 
 int32_t cordum_policy_load(cordum_engine* e, const char* json, uint64_t len, const char* snapshot, uint64_t slen) {
+  cordum::NvtxRange nvtx_("cordum:policy_load");
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
   return e->host->load_policy(sv(json ? json : "", json ? len : 0), sv(snapshot ? snapshot : "", snapshot ? slen : 0), g_err);
 }
@@ -1081,6 +1091,7 @@ int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
 }
 
 int32_t cordum_workers_load(cordum_engine* e, const cordum_workers* w) {
+  cordum::NvtxRange nvtx_("cordum:workers_load");
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }
   return e->host->load_workers(w, g_err);
 }
@@ -1136,6 +1147,7 @@ int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_
 }
 
 int32_t cordum_workers_ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slot, uint32_t n_slice) {
+  cordum::NvtxRange nvtx_("cordum:heartbeat_ingest");
   if (!e || !slice) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }
   if (int rc = leave_tick_mode(e)) return rc;
@@ -1343,6 +1355,7 @@ void cordum_envelopes_free(cordum_engine* e, cordum_envelopes* env) {
 }
 
 int32_t cordum_encode_device(cordum_engine* e, cordum_batch* b, const cordum_envelopes* env) {
+  cordum::NvtxRange nvtx_("cordum:encode_device");
   if (!e || !b || !env) { g_err = "null argument"; return CORDUM_E_INVALID; }
   if (env->n_jobs > b->max_jobs) { g_err = "batch too small for these envelopes"; return CORDUM_E_INVALID; }
   if (e->failed) { g_err = "engine failed earlier: " + e->fail_msg; return CORDUM_E_CUDA; }

@@ -10,6 +10,7 @@
 // cordum_dispatch for all of them, formats the strings the response carries (rule id, reason, subject, snapshot) and wakes
 // the callers.  Two lanes alternate, so that packing the next batch overlaps the GPU round trip of the current one.
 // Failures are per batch and fail closed: every request of a failed batch gets the engine's status and a DENY record.
+#include "../../common/nvtx_range.hpp"
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -148,6 +149,7 @@ void cordum_frontend::run(Lane& L) {
       }
       if (!queue.empty()) cv_work.notify_one();   // more work than one batch: wake the other lane
     }
+    cordum::NvtxRange nvtx_("cordum:frontend_batch");
     if (items.size() >= opts.max_batch) n_full++;
     row.assign(items.size(), 0);
     int32_t rc = CORDUM_OK;

@@ -233,6 +233,35 @@ __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
   }
 }
 
+// Per (pool, label bit): the answer for a job that requires exactly that one placement label (most labelled jobs carry one):
+// first two matches in the non-overloaded prefix of the pool's load-sorted view and the number of matching workers - what
+// route_kernel's scan would find, once per heartbeat epoch instead of once per job.  Thread per (pool, bit).
+__global__ void __launch_bounds__(256) label_best_kernel(DeviceTables T) {
+  const uint32_t nbits = T.place_bits;
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= T.n_pools * nbits) return;
+  const uint32_t p = id / nbits, b = id - p * nbits;
+  uint64_t kstar = KEY_NONE;
+  uint32_t kc = 0, tot = 0;
+  if (T.pool_sorted[p]) {
+    const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a, words = (n + 31) >> 5, nok = T.pool_nok[p];
+    const uint32_t* row = T.lbm + T.lbm_off[p] + (size_t)b * words;
+    bool done = false;
+    for (uint32_t w = 0; w < words; ++w) {
+      const uint32_t v = row[w], lo = w * 32;
+      tot += __popc(v);
+      uint32_t okv = (done || lo >= nok) ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));
+      while (okv && !done) {
+        const uint64_t kk = T.skey[a + lo + (uint32_t)__ffs((int)okv) - 1u];
+        if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
+        else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; done = true; }
+        okv &= okv - 1;
+      }
+    }
+  }
+  T.lbest[id] = make_uint4((uint32_t)kstar, (uint32_t)(kstar >> 32), kc, tot);
+}
+
 // ------------------------------------------------------------------ wide masks (tables.h WideLayout)
 // Everything below is reached only when a dictionary outgrew the records' own mask fields (T.wide_words != 0).
 __device__ __forceinline__ bool wide_need_ok(const DeviceTables& T, uint32_t r, const uint64_t* wrow, uint32_t flags) {
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(256, MINB) policy_kernel(KParams P) {
     const bool eval = valid && !bypass && !early;
     const bool mcp_used = (c_flags & JF_MCP_USED) != 0;
     const uint32_t combo = CORDUM_COMBO_INDEX(c_flags);
-    const uint64_t* wrow = (T.wide_words && valid) ? P.recs.wide + (size_t)s * T.wide_words : nullptr;   // rare: masks beyond the record's
+    const uint64_t* wrow = (T.wide_words && P.recs.wide && valid) ? P.recs.wide + (size_t)s * T.wide_words : nullptr;   // rare: masks beyond the record's
     uint64_t live = 0;
     if (eval) {
       live = __ldg(T.sum_topic + c_topic);
@@ -525,7 +554,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       c_plo = ((uint64_t)r0.y << 32) | r0.x; c_phi = ((uint64_t)r0.w << 32) | r0.z;
       c_req = ((uint64_t)r1.y << 32) | r1.x; c_ppool = r1.z; c_pwork = r1.w;
     }
-    const uint64_t* wrow = (T.wide_words && valid) ? P.recs.wide + (size_t)j * T.wide_words : nullptr;   // rare: masks beyond the record's
+    const uint64_t* wrow = (T.wide_words && P.recs.wide && valid) ? P.recs.wide + (size_t)j * T.wide_words : nullptr;   // rare: masks beyond the record's
     uint32_t rflags = 0, route = CORDUM_ROUTE_NOT_ATTEMPTED;
     int slot = -1;
 
@@ -552,7 +581,14 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
           const bool req_any = c_flags & JF_REQ_NONEMPTY, req_unknown = c_flags & JF_REQ_UNKNOWN;
           const uint64_t need_req = c_req & ~T.req_blank_mask;
           const bool unsat = c_flags & JF_PLACE_UNSAT;
-          const bool labelled = (c_plo | c_phi) != 0 || unsat || place_x_any(T, wrow);
+          const bool wide_place = place_x_any(T, wrow);
+          const bool labelled = (c_plo | c_phi) != 0 || unsat || wide_place;
+          // exactly one required label: the per-(pool, bit) answers of the refresh (label_best_kernel) settle it here
+          int one_bit = -1;
+          if (T.lbest && !unsat && !wide_place) {
+            if (c_phi == 0 && c_plo && !(c_plo & (c_plo - 1))) one_bit = __ffsll((long long)c_plo) - 1;
+            else if (c_plo == 0 && c_phi && !(c_phi & (c_phi - 1))) one_bit = 64 + __ffsll((long long)c_phi) - 1;
+          }
           int pw_pos = -1;
           uint32_t pw_pool = 0xFFFFFFFFu;
           if (c_pwork && c_pwork != CORDUM_PREF_UNKNOWN) {
@@ -570,8 +606,17 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
             if (!labelled) {
               total += __ldg(T.pool_off + pid + 1) - __ldg(T.pool_off + pid);
               merge_best(best, bcnt, T.pool_best[pid], T.pool_mincnt[pid]);
-            } else slow |= T.pool_sorted[pid] == 0;
+            } else {
+              const bool sorted = T.pool_sorted[pid] != 0;
+              slow |= !sorted;
+              if (one_bit >= 0 && sorted) {
+                const uint4 lb = __ldg(T.lbest + (size_t)pid * T.place_bits + (uint32_t)one_bit);
+                total += lb.w;
+                merge_best(best, bcnt, ((uint64_t)lb.y << 32) | lb.x, lb.z);
+              }
+            }
           }
+          const bool settled = one_bit >= 0 && !slow;   // every eligible pool answered from the table
           if (n_elig == 0) route = CORDUM_ROUTE_NO_POOL_REQUIRES;              // :64-66
           else {
             bool took_pref = false;
@@ -581,7 +626,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
                 took_pref = true; route = CORDUM_ROUTE_OK_PREFERRED; slot = (int)(c_pwork - 1);
               }
             }
-            if (!took_pref) need_scan = labelled && !unsat;   // label-free and unsatisfiable jobs are final already
+            if (!took_pref) need_scan = labelled && !unsat && !settled;   // label-free, single-label and unsatisfiable jobs are final already
             if (!took_pref && !need_scan) {
               if (best != KEY_NONE) {
                 route = CORDUM_ROUTE_OK;
@@ -610,7 +655,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       const uint64_t need_lo = shfl64(FULL, c_plo, s_), need_hi = shfl64(FULL, c_phi, s_);
       const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
       const uint32_t jw = __shfl_sync(FULL, j, s_);
-      const uint64_t* wr = (T.wide_words && act) ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
+      const uint64_t* wr = (T.wide_words && P.recs.wide && act) ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
       // required label bits -> bitmap row numbers, once per job (not per pool and word): four 8-bit row numbers in lbp
       uint32_t lbp = 0, nlb = 0;
       bool more;
@@ -696,7 +741,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
       const uint64_t need_lo = shfl64(FULL, c_plo, i), need_hi = shfl64(FULL, c_phi, i);
       const bool req_any = fl & JF_REQ_NONEMPTY, req_unknown = fl & JF_REQ_UNKNOWN;
       const uint32_t jw = __shfl_sync(FULL, j, i);
-      const uint64_t* wr = T.wide_words ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
+      const uint64_t* wr = (T.wide_words && P.recs.wide) ? P.recs.wide + (size_t)jw * T.wide_words : nullptr;
       uint64_t b = KEY_NONE;
       uint32_t bc = 0, tot = 0;
       for (uint32_t k = 0; k < cnt; ++k) {
@@ -812,14 +857,27 @@ cudaError_t launch_peer_push(const PeerPush& G, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+static cudaError_t launch_label_best(const DeviceTables& T, cudaStream_t s);
+
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read) {
   if (T.n_pools == 0) return loads_read ? cudaEventRecord(loads_read, s) : cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   worker_chunk_kernel<CORDUM_POOL_CHUNK><<<T.n_chunks, CORDUM_POOL_CHUNK, 0, s>>>(T);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && loads_read) e = cudaEventRecord(loads_read, s);   // the load table is not read past this point
-  if (e != cudaSuccess || T.n_merge == 0) return e;
-  worker_merge_kernel<<<T.n_merge, 512, T.merge_smem, s>>>(T);
+  if (e != cudaSuccess) return e;
+  if (T.n_merge) {
+    worker_merge_kernel<<<T.n_merge, 512, T.merge_smem, s>>>(T);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return launch_label_best(T, s);
+}
+
+static cudaError_t launch_label_best(const DeviceTables& T, cudaStream_t s) {
+  if (!T.lbest || T.n_pools == 0) return cudaSuccess;
+  const uint32_t n = T.n_pools * T.place_bits;
+  label_best_kernel<<<(n + 255) / 256, 256, 0, s>>>(T);
   return cudaGetLastError();
 }
 

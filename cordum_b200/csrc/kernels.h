@@ -30,7 +30,7 @@ cudaError_t launch_peer_push(const PeerPush& G, cudaStream_t s);
 cudaError_t launch_configure();
 
 // loads_read (optional) is recorded once T.loads has been consumed (between the chunk and the merge kernel)
-cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read);
+cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read);   // chunk sort, merge, label_best
 cudaError_t launch_policy(const KParams& P, int sm_count, cudaStream_t s, int share = 0);
 cudaError_t launch_route(const KParams& P, bool route_only, int sm_count, cudaStream_t s, int share = 0);
 

@@ -13,6 +13,11 @@
 //     topic, so the lanes of a warp visit the same word and their gathers fall into few cache lines.
 #pragma once
 #include <stdint.h>
+#ifdef __CUDACC__
+#include <vector_types.h>
+#else
+typedef struct __attribute__((aligned(16))) uint4 { unsigned int x, y, z, w; } uint4;
+#endif
 
 /* 16-byte units (the kernels reinterpret these as uint4 / int4) */
 typedef struct __attribute__((aligned(16))) Row16 { uint32_t w[4]; } Row16;
@@ -127,6 +132,7 @@ typedef struct WideLayout {
 /* Everything the kernels read besides the job columns.  Pointers are device pointers. */
 #define CORDUM_POOL_CHUNK 512u
 #define CORDUM_POOL_SORT_MAX 8192u
+#define CORDUM_LBEST_MAX_BITS 1024u
 
 typedef struct DeviceTables {
   /* ---- policy.  All pass-row tables live in ONE word-major array on the device: the 16 B cell of word w for value v of
@@ -182,6 +188,9 @@ typedef struct DeviceTables {
   uint32_t* lbm;                              /* derived: label bitmaps over the sorted view: lbm[lbm_off[p] + bit*words(p) + w],
                                                  bit i of word w = "sorted worker 32w+i carries label bit"               */
   const uint32_t* lbm_off;                    /* [n_pools] word offset of the pool's bitmaps                               */
+  uint4* lbest;                               /* derived, or NULL (place_bits > CORDUM_LBEST_MAX_BITS): per (pool, label bit) what a
+                                                 job that requires exactly that one label gets from the pool's sorted view -
+                                                 {key lo, key hi (KEY_NONE: nobody), 1 | 2 = tie inside the pool, matching workers}  */
   uint32_t place_bits;                        /* label bits in use (beyond 128: pos_label_x)                               */
   /* worker-table refresh: a pool is cut into chunks of CORDUM_POOL_CHUNK workers, one CTA sorts one chunk, a second
      kernel merges the chunks of pools that have more than one (pools above CORDUM_POOL_SORT_MAX stay unsorted)       */

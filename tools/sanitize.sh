@@ -1,10 +1,16 @@
 #!/bin/bash
-# compute-sanitizer over the GPU parity tests (memcheck, then racecheck on the refresh / route tests).
-# Run on a GPU box:  gpurun --timeout 1500 -- 'bash tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'
+# compute-sanitizer over every kernel of the engine (tools/sanitize_target.py drives them and checks the results against
+# the oracle): memcheck, racecheck (shared-memory hazards: the bitonic sort / merge of the worker refresh, the per-warp
+# tiles of policy_kernel), synccheck, initcheck.  Run on a GPU box:
+#   gpurun --timeout 1500 -- 'bash tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'
+# The log is what profiles/r02_sanitize.log holds.
 set -u
 cd "$(dirname "$0")/.."
 SAN=/usr/local/cuda/bin/compute-sanitizer
-timeout 900 $SAN --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-  -k "not c3 and not c5" || echo "memcheck: FAILED ($?)"
-timeout 500 $SAN --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-  -k "pool_sizes or ingest or ties" || echo "racecheck: FAILED ($?)"
+for tool in memcheck racecheck synccheck initcheck; do
+  echo "=================================================================== $tool"
+  n=3000; [ "$tool" = racecheck ] && n=1500
+  extra=""; [ "$tool" = initcheck ] && extra="--track-unused-memory no"
+  timeout 600 $SAN --tool $tool $extra --error-exitcode 3 --print-limit 20 python tools/sanitize_target.py $n 2>&1 | grep -v "^$" | tail -40
+  echo "$tool exit code: ${PIPESTATUS[0]}"
+done
