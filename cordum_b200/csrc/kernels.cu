@@ -235,11 +235,12 @@ __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
 
 // Per (pool, label bit): the answer for a job that requires exactly that one placement label (most labelled jobs carry one):
 // first two matches in the non-overloaded prefix of the pool's load-sorted view and the number of matching workers - what
-// route_kernel's scan would find, once per heartbeat epoch instead of once per job.  Thread per (pool, bit).
+// route_kernel's scan would find, once per heartbeat epoch instead of once per job.  Warp per (pool, bit): lane = one
+// 32-worker word of the bit's bitmap, so the largest pool (a few thousand workers) is a handful of coalesced steps.
 __global__ void __launch_bounds__(256) label_best_kernel(DeviceTables T) {
-  const uint32_t nbits = T.place_bits;
-  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= T.n_pools * nbits) return;
+  const uint32_t nbits = T.place_bits, lane = threadIdx.x & 31;
+  const uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (id >= T.n_pools * nbits) return;   // warp-uniform
   const uint32_t p = id / nbits, b = id - p * nbits;
   uint64_t kstar = KEY_NONE;
   uint32_t kc = 0, tot = 0;
@@ -247,19 +248,25 @@ __global__ void __launch_bounds__(256) label_best_kernel(DeviceTables T) {
     const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a, words = (n + 31) >> 5, nok = T.pool_nok[p];
     const uint32_t* row = T.lbm + T.lbm_off[p] + (size_t)b * words;
     bool done = false;
-    for (uint32_t w = 0; w < words; ++w) {
-      const uint32_t v = row[w], lo = w * 32;
+    for (uint32_t w0 = 0; w0 < words; w0 += 32) {
+      const uint32_t w = w0 + lane, lo = w * 32;
+      const uint32_t v = w < words ? row[w] : 0u;
       tot += __popc(v);
       uint32_t okv = (done || lo >= nok) ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));
-      while (okv && !done) {
-        const uint64_t kk = T.skey[a + lo + (uint32_t)__ffs((int)okv) - 1u];
+      while (!done) {   // at most two rounds over the whole row: the argmin, then the next match for the tie flag
+        const unsigned hit = __ballot_sync(FULL, okv != 0);
+        if (!hit) break;
+        const int L = __ffs((int)hit) - 1;
+        const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(okv ? __ffs((int)okv) - 1 : 0), L);
+        const uint64_t kk = T.skey[a + pos];
         if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
         else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; done = true; }
-        okv &= okv - 1;
+        if ((int)lane == L) okv &= okv - 1;
       }
     }
+    tot = __reduce_add_sync(FULL, tot);
   }
-  T.lbest[id] = make_uint4((uint32_t)kstar, (uint32_t)(kstar >> 32), kc, tot);
+  if (lane == 0) T.lbest[id] = make_uint4((uint32_t)kstar, (uint32_t)(kstar >> 32), kc, tot);
 }
 
 // ------------------------------------------------------------------ wide masks (tables.h WideLayout)
@@ -876,8 +883,8 @@ cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent
 
 static cudaError_t launch_label_best(const DeviceTables& T, cudaStream_t s) {
   if (!T.lbest || T.n_pools == 0) return cudaSuccess;
-  const uint32_t n = T.n_pools * T.place_bits;
-  label_best_kernel<<<(n + 255) / 256, 256, 0, s>>>(T);
+  const uint32_t n = T.n_pools * T.place_bits;   // one warp each
+  label_best_kernel<<<(n + 7) / 8, 256, 0, s>>>(T);
   return cudaGetLastError();
 }
 

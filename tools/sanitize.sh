@@ -9,8 +9,9 @@ cd "$(dirname "$0")/.."
 SAN=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck initcheck; do
   echo "=================================================================== $tool"
-  n=3000; [ "$tool" = racecheck ] && n=1500
+  n=2000; mode=full
+  [ "$tool" = racecheck ] && { n=500; mode=light; }
   extra=""; [ "$tool" = initcheck ] && extra="--track-unused-memory no"
-  timeout 600 $SAN --tool $tool $extra --error-exitcode 3 --print-limit 20 python tools/sanitize_target.py $n 2>&1 | grep -v "^$" | tail -40
+  timeout ${SAN_TIMEOUT:-300} $SAN --tool $tool $extra --error-exitcode 3 --print-limit 20 python tools/sanitize_target.py $n $mode 2>&1 | grep -v "^$" | tail -40
   echo "$tool exit code: ${PIPESTATUS[0]}"
 done
