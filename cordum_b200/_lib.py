@@ -22,7 +22,7 @@ API = [
     "cordum_batch_alloc", "cordum_batch_free", "cordum_encode", "cordum_encode_device", "cordum_envelopes_alloc",
     "cordum_envelopes_free", "cordum_host_fallbacks", "cordum_batch_records", "cordum_dispatch",
     "cordum_dispatch_async", "cordum_batch_wait", "cordum_dispatch_resident", "cordum_dispatch_resident_async", "cordum_batch_fetch", "cordum_batch_stream",
-    "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason", "cordum_reason_flavor", "cordum_batch_snapshot", "cordum_batch_policy_gen", "cordum_rule_id_at", "cordum_rule_constraints_json_at", "cordum_rule_remediations_json_at",
+    "cordum_batch_size", "cordum_batch_results", "cordum_batch_timing", "cordum_batch_kernel_times", "cordum_rule_id", "cordum_reason", "cordum_reason_flavor", "cordum_batch_snapshot", "cordum_batch_policy_gen", "cordum_policy_generation", "cordum_frontend_cache_stats", "cordum_rule_id_at", "cordum_rule_constraints_json_at", "cordum_rule_remediations_json_at",
     "cordum_subject", "cordum_rule_constraints_json", "cordum_rule_remediations_json", "cordum_stats",
     "cordum_launch_count", "cordum_frontend_create", "cordum_frontend_destroy", "cordum_frontend_submit", "cordum_frontend_submit_many", "cordum_frontend_stats", "cordum_frontend_loadgen",
     "cordum_test_glob", "cordum_test_trim", "cordum_test_normalize_decision",
@@ -101,6 +101,9 @@ def load() -> C.CDLL:
     L.cordum_batch_snapshot.restype = i64
     L.cordum_batch_policy_gen.argtypes = [vp]
     L.cordum_batch_policy_gen.restype = u64
+    L.cordum_policy_generation.argtypes = [vp]
+    L.cordum_policy_generation.restype = u64
+    L.cordum_frontend_cache_stats.argtypes = [vp, vp, vp, vp]
     for fn in (L.cordum_rule_id_at, L.cordum_rule_constraints_json_at, L.cordum_rule_remediations_json_at):
         fn.argtypes = [vp, u64, i32, cp, u64]
         fn.restype = i64

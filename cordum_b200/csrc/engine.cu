@@ -1084,6 +1084,7 @@ int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap) {
   return copy_out(b->text ? b->text->snapshot : std::string(), buf, cap);
 }
 uint64_t cordum_batch_policy_gen(const cordum_batch* b) { return (b && b->text) ? b->text->gen : 0; }
+uint64_t cordum_policy_generation(cordum_engine* e) { return e ? e->host->policy_generation() : 0; }
 
 int32_t cordum_routing_load(cordum_engine* e, const char* json, uint64_t len) {
   if (!e) { g_err = "null engine"; return CORDUM_E_INVALID; }

@@ -17,9 +17,12 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <algorithm>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cordum_b200.h"
@@ -34,6 +37,39 @@ struct Ticket {
   std::mutex m;
   std::condition_variable cv;
   bool done = false;
+};
+
+// ---- decision cache (kernel.go:149-162,250-303; SAFETY_DECISION_CACHE_TTL).  The reference keys a cached response by
+// snapshot + SHA-256 of the request's deterministic protobuf bytes with the job id cleared.  The key never leaves the
+// process; here it is a 128-bit keyed hash (two multiply-xorshift lanes seeded from std::random_device per front-end, so
+// colliding requests cannot be prepared offline) over the same information: every request field in a fixed order,
+// repeated fields in their order, labels sorted by key (deterministic marshalling sorts map keys), plus the policy
+// generation (which the snapshot string stands for in the reference).  cordum_request has no job id.
+struct CacheKey {
+  uint64_t a, b;
+  bool operator==(const CacheKey& o) const { return a == o.a && b == o.b; }
+};
+struct CacheKeyHash { size_t operator()(const CacheKey& k) const { return (size_t)(k.a ^ (k.b * 0x9E3779B97F4A7C15ull)); } };
+struct CacheEntry {
+  cordum_response resp;
+  std::chrono::steady_clock::time_point expires;
+};
+struct CacheShard {
+  std::mutex m;
+  std::unordered_map<CacheKey, CacheEntry, CacheKeyHash> map;
+};
+struct KeyHasher {
+  uint64_t a, b;
+  inline void word(uint64_t x) {
+    a = (a ^ x) * 0x9FB21C651E98DF25ull; a ^= a >> 32;
+    b = (b ^ (x + 0x632BE59BD9B4E019ull)) * 0xD6E8FEB86659FD93ull; b ^= b >> 29;
+  }
+  void bytes(const char* p, uint32_t n) {
+    word(0x8000000000000000ull | n);   // length first: ("ab","c") and ("a","bc") differ
+    while (n >= 8) { uint64_t x; std::memcpy(&x, p, 8); word(x); p += 8; n -= 8; }
+    if (n) { uint64_t x = 0; std::memcpy(&x, p, n); word(x); }
+  }
+  void sv(const cordum_sv& s) { bytes(s.p ? s.p : "", s.p ? s.n : 0); }
 };
 
 struct Lane {
@@ -55,6 +91,16 @@ struct cordum_frontend {
   std::atomic<uint64_t> n_batches{0}, n_requests{0}, n_full{0}, n_stale_retries{0};
   uint64_t arena_cap = 0;
   uint32_t max_lists = 0;
+  // decision cache (POLICY_ONLY front-ends with cache_ttl_us > 0)
+  static constexpr int kShards = 16;
+  static constexpr size_t kShardMax = 1u << 16;   // entries per shard before the shard is swept / dropped
+  CacheShard cache[kShards];
+  uint64_t seed_a = 0, seed_b = 0;
+  std::atomic<uint64_t> n_hits{0}, n_misses{0};
+  bool cache_on() const { return opts.cache_ttl_us != 0 && opts.mode == CORDUM_MODE_POLICY_ONLY; }
+  CacheKey key_of(const cordum_request& q) const;
+  bool cache_get(const CacheKey& k, cordum_response* out);
+  void cache_put(const CacheKey& k, const cordum_response& r);
 
   void run(Lane& L);
   bool pack(Lane& L, std::vector<Ticket*>& items, std::vector<int32_t>& status);
@@ -201,6 +247,56 @@ void cordum_frontend::run(Lane& L) {
   }
 }
 
+CacheKey cordum_frontend::key_of(const cordum_request& q) const {
+  KeyHasher h{seed_a, seed_b};
+  h.word(cordum_policy_generation(eng));
+  h.sv(q.topic); h.sv(q.tenant); h.sv(q.principal_id); h.sv(q.effective_config);
+  h.word((uint64_t)(q.has_meta ? 1 : 0) | (uint64_t)q.actor_type << 8 | (uint64_t)(q.approved ? 1 : 0) << 16);
+  h.sv(q.meta_tenant_id); h.sv(q.actor_id); h.sv(q.capability); h.sv(q.pack_id);
+  h.word(q.n_risk_tags);
+  for (uint32_t k = 0; k < q.n_risk_tags; ++k) h.sv(q.risk_tags[k]);
+  h.word(q.n_requires);
+  for (uint32_t k = 0; k < q.n_requires; ++k) h.sv(q.requires_[k]);
+  h.word(q.n_labels);
+  if (q.n_labels) {   // a map: order of arrival is not information
+    uint32_t idx_small[32];
+    std::vector<uint32_t> idx_big;
+    uint32_t* idx = idx_small;
+    if (q.n_labels > 32) { idx_big.resize(q.n_labels); idx = idx_big.data(); }
+    for (uint32_t k = 0; k < q.n_labels; ++k) idx[k] = k;
+    std::stable_sort(idx, idx + q.n_labels, [&](uint32_t x, uint32_t y) {
+      const cordum_sv &a = q.labels[x].key, &b = q.labels[y].key;
+      const int c = std::memcmp(a.p ? a.p : "", b.p ? b.p : "", std::min(a.p ? a.n : 0u, b.p ? b.n : 0u));
+      return c != 0 ? c < 0 : (a.p ? a.n : 0u) < (b.p ? b.n : 0u);
+    });
+    for (uint32_t k = 0; k < q.n_labels; ++k) { h.sv(q.labels[idx[k]].key); h.sv(q.labels[idx[k]].val); }
+  }
+  return CacheKey{h.a, h.b};
+}
+
+bool cordum_frontend::cache_get(const CacheKey& k, cordum_response* out) {
+  CacheShard& S = cache[k.a % kShards];
+  std::lock_guard<std::mutex> g(S.m);
+  auto it = S.map.find(k);
+  if (it == S.map.end()) return false;
+  if (std::chrono::steady_clock::now() > it->second.expires) { S.map.erase(it); return false; }   // kernel.go:285-288
+  *out = it->second.resp;
+  return true;
+}
+
+void cordum_frontend::cache_put(const CacheKey& k, const cordum_response& r) {
+  // kernel.go:250-254 caches what the full evaluation returned; the early topic denials return before that point
+  if (r.status != CORDUM_OK || !(r.rec.flags & CORDUM_F_HAS_SNAPSHOT)) return;
+  CacheShard& S = cache[k.a % kShards];
+  const auto now = std::chrono::steady_clock::now();
+  std::lock_guard<std::mutex> g(S.m);
+  if (S.map.size() >= kShardMax) {   // the reference's map only shrinks on access; bound it: sweep, then drop
+    for (auto it = S.map.begin(); it != S.map.end();) it = now > it->second.expires ? S.map.erase(it) : std::next(it);
+    if (S.map.size() >= kShardMax) S.map.clear();
+  }
+  S.map[k] = CacheEntry{r, now + std::chrono::microseconds(opts.cache_ttl_us)};
+}
+
 extern "C" {
 
 int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* o, cordum_frontend** out) {
@@ -213,6 +309,8 @@ int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* o, 
   f->opts.mode = o && o->mode ? o->mode : CORDUM_MODE_POLICY_AND_ROUTE;
   f->opts.lanes = o && o->lanes ? o->lanes : 2;
   f->opts.arena_bytes_per_request = o && o->arena_bytes_per_request ? o->arena_bytes_per_request : 1024;
+  f->opts.cache_ttl_us = o ? o->cache_ttl_us : 0;
+  { std::random_device rd; f->seed_a = ((uint64_t)rd() << 32) | rd(); f->seed_b = ((uint64_t)rd() << 32) | rd(); }
   f->arena_cap = (uint64_t)f->opts.max_batch * f->opts.arena_bytes_per_request + 16;
   f->max_lists = f->opts.max_batch * 8;
   for (uint32_t i = 0; i < f->opts.lanes; ++i) {
@@ -245,6 +343,13 @@ void cordum_frontend_destroy(cordum_frontend* f) {
 
 int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, cordum_response* resp) {
   if (!f || !req || !resp) return CORDUM_E_INVALID;
+  const bool cached = f->cache_on();
+  CacheKey key{0, 0};
+  if (cached) {
+    key = f->key_of(*req);
+    if (f->cache_get(key, resp)) { f->n_hits++; return resp->status; }
+    f->n_misses++;
+  }
   Ticket t;
   t.req = req; t.resp = resp;
   {
@@ -257,6 +362,8 @@ int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, co
     std::unique_lock<std::mutex> lk(t.m);
     t.cv.wait(lk, [&] { return t.done; });
   }
+  // the key carries the generation read before the evaluation: a response evaluated under a newer policy is not stored
+  if (cached && resp->policy_gen == cordum_policy_generation(f->eng)) f->cache_put(key, *resp);
   return resp->status;
 }
 
@@ -309,6 +416,18 @@ uint64_t cordum_frontend_loadgen(cordum_frontend* f, const cordum_request* reqs,
     });
   for (auto& th : ts) th.join();
   return total.load();
+}
+
+int32_t cordum_frontend_cache_stats(cordum_frontend* f, uint64_t* hits, uint64_t* misses, uint64_t* entries) {
+  if (!f) return CORDUM_E_INVALID;
+  if (hits) *hits = f->n_hits.load();
+  if (misses) *misses = f->n_misses.load();
+  if (entries) {
+    uint64_t n = 0;
+    for (auto& S : f->cache) { std::lock_guard<std::mutex> g(S.m); n += S.map.size(); }
+    *entries = n;
+  }
+  return CORDUM_OK;
 }
 
 int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches) {

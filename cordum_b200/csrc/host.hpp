@@ -357,6 +357,7 @@ class Host {
   }
   const std::string& topic_raw(uint32_t topic_id) const { return topic_keys_[topic_id]; }
   uint32_t wide_words() const { return WIDE_WORDS(t_.wide); }
+  uint64_t policy_generation() const { return text_gen_.load(std::memory_order_acquire); }
   std::string mcp_value_string(int field, uint32_t id) const;
   const std::vector<std::string>& topic_pool_names(uint32_t topic_id) const;
   uint32_t n_topics() const { return (uint32_t)topic_keys_.size(); }
@@ -401,6 +402,7 @@ class Host {
   struct Pattern { Glob glob; std::vector<uint32_t> rules; };
   std::vector<Pattern> patterns_;
   std::unordered_map<std::string, std::vector<uint32_t>> pat_by_prefix_;   // literal prefix -> patterns
+  uint32_t eff_topic_n_ = 0;   // topics whose effective-config verdicts are filled in (for every config known)
   Bits vac_topic_;
   // topics (dynamic)
   StrTable topic_ids_;
@@ -419,6 +421,7 @@ class Host {
   // workers
   std::shared_ptr<const std::vector<std::string>> worker_ids_ = std::make_shared<std::vector<std::string>>();   // replaced, never edited
   std::deque<std::shared_ptr<const PolicyText>> text_;   // the last 8 policies' text, oldest first
+  std::atomic<uint64_t> text_gen_{0};                   // generation of text_.back(), readable without the lock
   void publish_text();
   StrTable worker_slot_;      // worker_id -> slot (last wins)
   StrTable place_pair_;       // key '\0' value -> bit   (value non-empty)

@@ -36,7 +36,7 @@ class Response(C.Structure):
 
 class FrontendOpts(C.Structure):
     _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("mode", C.c_uint32), ("lanes", C.c_uint32),
-                ("arena_bytes_per_request", C.c_uint32)]
+                ("arena_bytes_per_request", C.c_uint32), ("reserved", C.c_uint32), ("cache_ttl_us", C.c_uint64)]
 
 
 def _b(s) -> bytes:
@@ -86,10 +86,12 @@ def pack_request(job: dict):
 
 
 class Frontend:
-    def __init__(self, eng, max_batch=1024, max_wait_us=200, mode=wire.MODE_POLICY_AND_ROUTE, lanes=2, arena_bytes_per_request=1024):
+    def __init__(self, eng, max_batch=1024, max_wait_us=200, mode=wire.MODE_POLICY_AND_ROUTE, lanes=2, arena_bytes_per_request=1024,
+                 cache_ttl_us=0):
+        """cache_ttl_us: SAFETY_DECISION_CACHE_TTL (kernel.go:149-162); only POLICY_ONLY front-ends cache."""
         self.eng = eng
         self.L = eng.L
-        opts = FrontendOpts(max_batch, max_wait_us, mode, lanes, arena_bytes_per_request)
+        opts = FrontendOpts(max_batch, max_wait_us, mode, lanes, arena_bytes_per_request, 0, cache_ttl_us)
         h = C.c_void_p()
         eng._ck(self.L.cordum_frontend_create(eng.h, C.byref(opts), C.byref(h)))
         self.h = h
@@ -105,6 +107,11 @@ class Frontend:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.L.cordum_frontend_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
         return {"batches": a.value, "requests": b.value, "full_batches": c.value}
+
+    def cache_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.cordum_frontend_cache_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"hits": a.value, "misses": b.value, "entries": c.value}
 
     def close(self):
         if self.h:

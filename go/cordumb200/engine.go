@@ -29,9 +29,12 @@ import (
 	"encoding/json"
 	"errors"
 	"fmt"
+	"os"
 	"runtime"
 	"sort"
+	"strings"
 	"sync"
+	"time"
 	"unsafe"
 
 	pb "github.com/cordum/cordum/core/protocol/pb/v1"
@@ -68,8 +71,16 @@ func NewEngine(device int) (*Engine, error) {
 	if err := call(func() C.int32_t { return C.cordum_engine_create(&opts, &e.h) }); err != nil {
 		return nil, err
 	}
+	// SAFETY_DECISION_CACHE_TTL (kernel.go:46,87,316-327): the safety kernel's decision cache, kept by the policy front-end
+	var ttlUs C.uint64_t
+	if d, err := time.ParseDuration(strings.TrimSpace(os.Getenv("SAFETY_DECISION_CACHE_TTL"))); err == nil && d > 0 {
+		ttlUs = C.uint64_t(d / time.Microsecond)
+	}
 	mk := func(mode C.uint32_t, out **C.cordum_frontend) error {
 		o := C.cordum_frontend_opts{max_batch: 1024, max_wait_us: 200, mode: mode, lanes: 2, arena_bytes_per_request: 2048}
+		if mode == C.CORDUM_MODE_POLICY_ONLY {
+			o.cache_ttl_us = ttlUs
+		}
 		return call(func() C.int32_t { return C.cordum_frontend_create(e.h, &o, out) })
 	}
 	if err := mk(C.CORDUM_MODE_POLICY_ONLY, &e.policyFE); err != nil {

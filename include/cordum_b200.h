@@ -207,6 +207,7 @@ int64_t cordum_policy_snapshot(cordum_engine* e, char* buf, uint64_t cap);
  * kernel.go:140-147,239-248).  gen 0 = the policy in force now. */
 int64_t cordum_batch_snapshot(const cordum_batch* b, char* buf, uint64_t cap);
 uint64_t cordum_batch_policy_gen(const cordum_batch* b);
+uint64_t cordum_policy_generation(cordum_engine* e);   /* of the policy in force; lock-free */
 int64_t cordum_rule_id_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
 int64_t cordum_rule_constraints_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
 int64_t cordum_rule_remediations_json_at(cordum_engine* e, uint64_t gen, int32_t rule_idx, char* buf, uint64_t cap);
@@ -389,6 +390,10 @@ typedef struct cordum_frontend_opts {
   uint32_t mode;                     /* CORDUM_MODE_* of every batch (default POLICY_AND_ROUTE)                     */
   uint32_t lanes;                    /* batches in flight (default 2: packing overlaps the GPU round trip)          */
   uint32_t arena_bytes_per_request;  /* string budget per request in the page-locked staging (default 1024)         */
+  uint32_t reserved;
+  uint64_t cache_ttl_us;             /* SAFETY_DECISION_CACHE_TTL (kernel.go:40,87,149-162,250-254): > 0 and mode POLICY_ONLY
+                                        = answer a request identical to one evaluated under the same policy within the TTL
+                                        from memory.  0 (the reference's default) = off                              */
 } cordum_frontend_opts;
 typedef struct cordum_frontend cordum_frontend;
 int32_t cordum_frontend_create(cordum_engine* e, const cordum_frontend_opts* opts, cordum_frontend** out);
@@ -398,6 +403,7 @@ int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, co
 /* n requests of one caller at once (a Go adapter that drained a channel): returns the worst status. */
 int32_t cordum_frontend_submit_many(cordum_frontend* f, const cordum_request* reqs, uint32_t n, cordum_response* resps);
 int32_t cordum_frontend_stats(cordum_frontend* f, uint64_t* batches, uint64_t* requests, uint64_t* full_batches);
+int32_t cordum_frontend_cache_stats(cordum_frontend* f, uint64_t* hits, uint64_t* misses, uint64_t* entries);
 /* Diagnostics: native client threads submitting round-robin for `seconds`; latencies (us) into lat_us[cap]. */
 uint64_t cordum_frontend_loadgen(cordum_frontend* f, const cordum_request* reqs, uint32_t n_reqs, uint32_t threads, double seconds,
                                  float* lat_us, uint64_t cap);

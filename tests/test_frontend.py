@@ -106,3 +106,54 @@ def test_mcp_reason_quotes_the_requests_own_spelling(eng):
     assert fe.submit({"topic": "job.x", "labels": {"mcp.server": "  EVIL.Example\t"}}).reason == b'mcp server "EVIL.Example" denied'
     fe.close()
     o.close()
+
+
+def test_decision_cache_like_the_safety_kernels(eng):
+    """SAFETY_DECISION_CACHE_TTL (kernel.go:149-162,250-303): a request identical to one evaluated under the same policy
+    within the TTL is answered from memory; the early topic denials are never stored; a new policy is a new key space."""
+    import time
+
+    policy = {"default_tenant": "default", "rules": [
+        {"id": "gate", "decision": "require_approval", "reason": "needs a human", "match": {"topics": ["job.prod.*"]}},
+        {"id": "lab", "decision": "deny", "reason": "no", "match": {"topics": ["job.l.*"], "labels": {"a": "1", "b": "2"}}}]}
+    eng.load_policy(policy, "snap-c1")
+    eng.load_routing({"topics": {}, "pools": {}})
+    eng.load_workers([])
+    fe = frontend.Frontend(eng, max_batch=8, max_wait_us=0, mode=wire.MODE_POLICY_ONLY, cache_ttl_us=200_000)
+    req = {"topic": "job.prod.deploy", "tenant": "default", "meta": {"risk_tags": ["x", "y"]}}
+    r1 = fe.submit(req)
+    r2 = fe.submit(dict(req))
+    assert fe.cache_stats() == {"hits": 1, "misses": 1, "entries": 1}
+    assert bytes(r1) == bytes(r2) and r2.rule_id == b"gate" and r2.snapshot == b"snap-c1"
+    assert r2.rec.flags & wire.F_APPROVAL_REQUIRED                         # the adapter derives approval_ref from this, per request
+    # a map has no order; a repeated field has
+    a = fe.submit({"topic": "job.l.x", "labels": {"a": "1", "b": "2"}})
+    b = fe.submit({"topic": "job.l.x", "labels": {"b": "2", "a": "1"}})
+    assert a.rec.decision == b.rec.decision == wire.DEC_DENY and fe.cache_stats()["hits"] == 2
+    fe.submit({"topic": "job.prod.deploy", "tenant": "default", "meta": {"risk_tags": ["y", "x"]}})
+    assert fe.cache_stats()["hits"] == 2 and fe.cache_stats()["entries"] == 3
+    # ("ab","c") vs ("a","bc"): lengths are part of the key
+    fe.submit({"topic": "job.k", "tenant": "ab", "principal_id": "c"})
+    fe.submit({"topic": "job.k", "tenant": "a", "principal_id": "bc"})
+    assert fe.cache_stats()["hits"] == 2
+    # early denials are returned before the cache is written (kernel.go:171-176 vs :250)
+    for _ in range(2):
+        assert fe.submit({"topic": "nope"}).reason == b"unsupported topic"
+    assert fe.cache_stats()["hits"] == 2
+    # a reload: new generation, nothing of the old policy is served
+    eng.load_policy({"rules": []}, "snap-c2")
+    r3 = fe.submit(req)
+    assert r3.rec.decision == wire.DEC_ALLOW and r3.snapshot == b"snap-c2" and fe.cache_stats()["hits"] == 2
+    assert fe.submit(req).rec.decision == wire.DEC_ALLOW and fe.cache_stats()["hits"] == 3
+    # expiry
+    time.sleep(0.25)
+    n = fe.cache_stats()["hits"]
+    fe.submit(req)
+    assert fe.cache_stats()["hits"] == n
+    fe.close()
+    # off by default, and never for front-ends that route (the answer depends on the heartbeats)
+    for kw in ({"mode": wire.MODE_POLICY_ONLY}, {"mode": wire.MODE_POLICY_AND_ROUTE, "cache_ttl_us": 10**6}):
+        f2 = frontend.Frontend(eng, max_batch=8, max_wait_us=0, **kw)
+        f2.submit(req); f2.submit(req)
+        assert f2.cache_stats()["hits"] == 0
+        f2.close()

@@ -217,3 +217,28 @@ def test_rejected_routing_load_keeps_the_previous_routing():
     with pytest.raises(RuntimeError, match="placement labels"):
         h.load_routing(r2)
     assert_same(h.evaluate(jobs, wire.MODE_ROUTE_ONLY), want, "after the rejected routing")
+
+
+def test_effective_config_verdicts_survive_reloads():
+    """The (effective config, topic) verdict table is kept across policy / routing reloads (ids are stable) and only
+    extended: old configs on old topics, old configs on topics a reload pre-seeds, new configs after the reload."""
+    p1 = {"rules": [{"id": "a", "decision": "deny", "match": {"topics": ["job.a.*"]}}]}
+    p2 = {"rules": [{"id": "b", "decision": "require_approval", "reason": "r", "match": {"topics": ["job.b.*"]}}]}
+    r1 = {"topics": {"job.a.one": ["p"]}, "pools": {"p": {}}}
+    r2 = {"topics": {"job.a.one": ["p"], "job.b.two": ["p"], "job.c.three": ["p"]}, "pools": {"p": {}}}
+    workers = [kats.hb("w", "p")]
+    effs = [b'{"safety":{"denied_topics":["job.b.*"]}}', b'{"safety":{"allowed_topics":["job.a.*","job.c.*"]}}',
+            b'{"data":{"safety":{"denied_topics":["job.?.one"]}}}']
+    topics = ["job.a.one", "job.b.two", "job.c.three", "job.d.four"]
+    jobs = [{"topic": t, "effective_config": e} for t in topics for e in effs] + [{"topic": t} for t in topics]
+    h = table_walk.HostHarness(p1, r1, workers)
+    o = oracle_lib.Oracle(p1, r1, workers)
+    assert_same(h.evaluate(jobs[:6]), o.eval(jobs[:6]), "before")           # two topics, three configs seen
+    h.load_policy(p2)
+    h.load_routing(r2)                                                      # pre-seeds job.b.two (seen) and job.c.three (new)
+    o2 = oracle_lib.Oracle(p2, r2, workers)
+    assert_same(h.evaluate(jobs), o2.eval(jobs), "after the reloads")
+    more = [{"topic": t, "effective_config": b'{"safety":{"denied_topics":["job.d.*"],"allowed_topics":["job.*"]}}'} for t in topics]
+    assert_same(h.evaluate(more + jobs), o2.eval(more + jobs), "a config first seen after the reloads")
+    h.load_policy(p1)
+    assert_same(h.evaluate(more + jobs), oracle_lib.Oracle(p1, r2, workers).eval(more + jobs), "and back")

@@ -11,7 +11,7 @@ for tool in memcheck racecheck synccheck initcheck; do
   echo "=================================================================== $tool"
   n=2000; mode=full
   [ "$tool" = racecheck ] && { n=500; mode=light; }
-  extra=""; [ "$tool" = initcheck ] && extra="--track-unused-memory no"
+  extra=""; [ "$tool" = initcheck ] && extra=""
   timeout ${SAN_TIMEOUT:-300} $SAN --tool $tool $extra --error-exitcode 3 --print-limit 20 python tools/sanitize_target.py $n $mode 2>&1 | grep -v "^$" | tail -40
   echo "$tool exit code: ${PIPESTATUS[0]}"
 done
