@@ -127,7 +127,7 @@ struct cordum_engine {
   // for heartbeat epoch k+1 (and k+2) writes one set while route kernels of epoch k still read another, so consecutive
   // steps pipeline instead of serialising (with two sets the refresh of epoch k+2 would wait for epoch k's route kernel).
   struct DerivedSet {
-    DevBuf loads, pos_key, ckey, skey, pool_sorted, pool_nok, lbm, lbest, pool_best, pool_mincnt;
+    DevBuf loads, pos_key, ckey, skey, pool_sorted, pool_nok, pool_done, lbm, lbest, pool_best, pool_mincnt;
     cudaEvent_t ready = nullptr, loads_read = nullptr;   // refresh complete / load table consumed by the refresh
   } ds[kSets];
   int cur = 0;                   // set holding the latest refresh
@@ -289,6 +289,7 @@ int sync_tables(cordum_engine* e) {
       CK(D.ckey.reserve((size_t)std::max<uint32_t>(t.n_pos, 1) * 8), "alloc");
       CK(D.pool_sorted.reserve((size_t)std::max<uint32_t>(t.n_pools, 1)), "alloc");
       CK(D.pool_nok.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
+      CK(D.pool_done.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * 4), "alloc");
       CK(D.lbm.reserve((size_t)std::max<uint64_t>(t.lbm_words, 1) * 4), "alloc");
       if (t.place_bits <= CORDUM_LBEST_MAX_BITS) CK(D.lbest.reserve((size_t)std::max<uint32_t>(t.n_pools, 1) * t.place_bits * 16), "alloc");
       CK(D.loads.reserve((size_t)std::max<uint32_t>(t.n_slots, 1) * sizeof(Load16)), "alloc");
@@ -379,7 +380,7 @@ DeviceTables view(const cordum_engine* e, int set) {
   const auto& D = e->ds[set];
   d.loads = (const Load16*)D.loads.p;
   d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p;
-  d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.lbm = (uint32_t*)D.lbm.p;
+  d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.pool_done = (uint32_t*)D.pool_done.p; d.lbm = (uint32_t*)D.lbm.p;
   d.lbest = d.place_bits <= CORDUM_LBEST_MAX_BITS ? (uint4*)D.lbest.p : nullptr;
   d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
   return d;
@@ -414,7 +415,7 @@ int refresh_pools(cordum_engine* e, const void* dev_loads, cudaStream_t producer
     CK(cudaMemcpyAsync(D.loads.p, t.loads.data(), bytes, cudaMemcpyHostToDevice, e->s_tables), "H2D loads");
   }
   CK(launch_worker_pools(view(e, target), e->s_tables, D.loads_read), "worker-table refresh kernels");
-  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0);
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
   CK(cudaEventRecord(D.ready, e->s_tables), "event record");
   e->cur = target;
   e->pools_dirty = false;
@@ -678,7 +679,7 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
     CK(cudaGraphLaunch(ge, e->s_tables), "graph launch");
     CK(cudaEventRecord(e->gather_free[g], e->s_tables), "event record");
     CK(cudaEventRecord(D.ready, e->s_tables), "event record");
-    e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0) + (use_peers ? 1 : 0);
+    e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (use_peers ? 1 : 0);
     e->cur = target;
     e->pools_dirty = false;
     e->host_loads = false;
@@ -705,7 +706,7 @@ int ingest(cordum_engine* e, const cordum_worker_load* slice, uint32_t first_slo
   DeviceTables tv = view(e, target);
   tv.loads = (const Load16*)table;   // the refresh reads the gathered table in place
   CK(launch_worker_pools(tv, e->s_tables, e->gather_free[g]), "worker-table refresh kernels");
-  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0);
+  e->launches += (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0);
   CK(cudaEventRecord(D.ready, e->s_tables), "event record");
   e->cur = target;
   e->pools_dirty = false;
@@ -900,7 +901,7 @@ int tick_locked(cordum_engine* e, cordum_batch* bn, const cordum_worker_load* sl
       acc[0] = acc[1] = acc[2] = acc[3] = 0;
     }
   }
-  e->launches += (W ? (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->dt.n_pools && e->dt.place_bits <= CORDUM_LBEST_MAX_BITS ? 1 : 0) + (e->peers.ready && e->peers.world > 1 ? 1 : 0) : 0) + (bn->n ? 1 : 0) + (T.prev && T.prev->n ? 1 : 0);
+  e->launches += (W ? (e->dt.n_chunks ? 1 : 0) + (e->dt.n_merge ? 1 : 0) + (e->peers.ready && e->peers.world > 1 ? 1 : 0) : 0) + (bn->n ? 1 : 0) + (T.prev && T.prev->n ? 1 : 0);
   e->cur = phase % 3;   // the set this tick refreshed (a later plain dispatch continues from it)
   e->pools_dirty = false; e->host_loads = false;
   bn->tick_no = T.n;
@@ -1031,7 +1032,7 @@ void cordum_engine_destroy(cordum_engine* e) {
                    &e->b_chunk_pool, &e->b_pool_chunk0, &e->b_merge_list};
   for (DevBuf* b : all) b->release();
   for (auto& D : e->ds) {
-    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.pool_sorted, &D.pool_nok, &D.lbm, &D.lbest, &D.pool_best, &D.pool_mincnt}) b->release();
+    for (DevBuf* b : {&D.loads, &D.pos_key, &D.ckey, &D.skey, &D.pool_sorted, &D.pool_nok, &D.pool_done, &D.lbm, &D.lbest, &D.pool_best, &D.pool_mincnt}) b->release();
     if (D.ready) cudaEventDestroy(D.ready);
     if (D.loads_read) cudaEventDestroy(D.loads_read);
   }

@@ -83,6 +83,43 @@ __device__ __forceinline__ uint64_t worker_key(const DeviceTables& T, uint32_t p
   return ((uint64_t)(over ? 0xFFFFFFFFu : orderable(score)) << 32) | T.pos_rank[pos];
 }
 
+// Per (pool, label bit): what a job that requires exactly that one placement label gets from the pool - first two matches in
+// the non-overloaded prefix of the load-sorted view (argmin + tie flag) and the number of matching workers.  Run by the CTA
+// that completes the pool's bitmaps (the single chunk's, or the last merge CTA to finish): a warp per bit, lane = one
+// 32-worker word, so even an 8,192-worker pool is eight coalesced steps per bit.  COHERENT = the view was written by other
+// CTAs (read it past L1).
+template <bool COHERENT>
+__device__ __forceinline__ void pool_label_best(const DeviceTables& T, uint32_t p, uint32_t a, uint32_t words, uint32_t nok,
+                                                uint32_t warp, uint32_t n_warps, uint32_t lane) {
+  if (!T.lbest) return;
+  const uint32_t nbits = T.place_bits;
+  const uint32_t* bm = T.lbm + T.lbm_off[p];
+  for (uint32_t b = warp; b < nbits; b += n_warps) {
+    const uint32_t* row = bm + (size_t)b * words;
+    uint64_t kstar = KEY_NONE;
+    uint32_t kc = 0, tot = 0;
+    bool done = false;
+    for (uint32_t w0 = 0; w0 < words; w0 += 32) {
+      const uint32_t w = w0 + lane, lo = w * 32;
+      const uint32_t v = w < words ? (COHERENT ? __ldcg(row + w) : row[w]) : 0u;
+      tot += __popc(v);
+      uint32_t okv = (done || lo >= nok) ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));
+      while (!done) {   // at most two rounds over the whole row: the argmin, then the next match for the tie flag
+        const unsigned hit = __ballot_sync(FULL, okv != 0);
+        if (!hit) break;
+        const int L = __ffs((int)hit) - 1;
+        const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(okv ? __ffs((int)okv) - 1 : 0), L);
+        const uint64_t kk = COHERENT ? __ldcg(T.skey + a + pos) : T.skey[a + pos];
+        if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
+        else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; done = true; }
+        if ((int)lane == L) okv &= okv - 1;
+      }
+    }
+    tot = __reduce_add_sync(FULL, tot);
+    if (lane == 0) T.lbest[(size_t)p * nbits + b] = make_uint4((uint32_t)kstar, (uint32_t)(kstar >> 32), kc, tot);
+  }
+}
+
 // One CTA of CORDUM_POOL_CHUNK (512) threads per chunk: thread i holds key i.  Bitonic network: exchanges inside a warp are
 // register shuffles (35 of the 45 stages of a 512-key sort), only partner distances >= 32 go through shared memory.
 template <uint32_t NT>
@@ -126,7 +163,7 @@ __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
     if (tid < len) T.ckey[a + cs + tid] = key;
     const uint64_t total = (uint64_t)nbits * words;
     for (uint64_t i = total * c / m + tid; i < total * (c + 1) / m; i += NT) bm[i] = 0;
-    if (c == 0 && tid == 0) { T.pool_mincnt[p] = 0; T.pool_nok[p] = 0; }
+    if (c == 0 && tid == 0) { T.pool_mincnt[p] = 0; T.pool_nok[p] = 0; T.pool_done[p] = 0; }
     return;
   }
   // single chunk: sorted view + label bitmaps; warp w = the 32 sorted workers of bitmap word w
@@ -161,8 +198,9 @@ __global__ void __launch_bounds__(NT) worker_chunk_kernel(DeviceTables T) {
   cnt = __reduce_add_sync(FULL, cnt); ok = __reduce_add_sync(FULL, ok);
   if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
   if (lane == 0 && ok) atomicAdd(&s_nok, ok);
-  __syncthreads();
+  __syncthreads();   // also: this CTA's skey / bitmap stores are visible to all of its threads from here on
   if (tid == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_mincnt[p] = s_cnt; T.pool_sorted[p] = 1; T.pool_nok[p] = s_nok; }
+  pool_label_best<false>(T, p, a, words, s_nok, tid >> 5, NT >> 5, lane);
 }
 
 __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
@@ -222,51 +260,25 @@ __global__ void __launch_bounds__(512) worker_merge_kernel(DeviceTables T) {
     cnt += (!none && (uint32_t)(k >> 32) == (uint32_t)(k0 >> 32)) ? 1u : 0u;
     ok += key_over(k) ? 0u : 1u;
   }
+  __threadfence();   // every thread's stores into the pool's view / bitmaps are ordered before its CTA signs off below
   cnt = __reduce_add_sync(FULL, cnt); ok = __reduce_add_sync(FULL, ok);
   if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
   if (lane == 0 && ok) atomicAdd(&s_nok, ok);
   __syncthreads();
+  __shared__ uint32_t s_last;
   if (tid == 0) {
     if (s_cnt) atomicAdd(&T.pool_mincnt[p], s_cnt);
     if (s_nok) atomicAdd(&T.pool_nok[p], s_nok);
     if (c == 0) { T.pool_best[p] = none ? KEY_NONE : k0; T.pool_sorted[p] = 1; }
+    __threadfence();   // this CTA's share of the view, bitmaps and counters, before it signs off
+    s_last = atomicAdd(&T.pool_done[p], 1u) == m - 1 ? 1u : 0u;
   }
-}
-
-// Per (pool, label bit): the answer for a job that requires exactly that one placement label (most labelled jobs carry one):
-// first two matches in the non-overloaded prefix of the pool's load-sorted view and the number of matching workers - what
-// route_kernel's scan would find, once per heartbeat epoch instead of once per job.  Warp per (pool, bit): lane = one
-// 32-worker word of the bit's bitmap, so the largest pool (a few thousand workers) is a handful of coalesced steps.
-__global__ void __launch_bounds__(256) label_best_kernel(DeviceTables T) {
-  const uint32_t nbits = T.place_bits, lane = threadIdx.x & 31;
-  const uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (id >= T.n_pools * nbits) return;   // warp-uniform
-  const uint32_t p = id / nbits, b = id - p * nbits;
-  uint64_t kstar = KEY_NONE;
-  uint32_t kc = 0, tot = 0;
-  if (T.pool_sorted[p]) {
-    const uint32_t a = T.pool_off[p], n = T.pool_off[p + 1] - a, words = (n + 31) >> 5, nok = T.pool_nok[p];
-    const uint32_t* row = T.lbm + T.lbm_off[p] + (size_t)b * words;
-    bool done = false;
-    for (uint32_t w0 = 0; w0 < words; w0 += 32) {
-      const uint32_t w = w0 + lane, lo = w * 32;
-      const uint32_t v = w < words ? row[w] : 0u;
-      tot += __popc(v);
-      uint32_t okv = (done || lo >= nok) ? 0u : (nok - lo >= 32 ? v : v & ((1u << (nok - lo)) - 1u));
-      while (!done) {   // at most two rounds over the whole row: the argmin, then the next match for the tie flag
-        const unsigned hit = __ballot_sync(FULL, okv != 0);
-        if (!hit) break;
-        const int L = __ffs((int)hit) - 1;
-        const uint32_t pos = __shfl_sync(FULL, lo + (uint32_t)(okv ? __ffs((int)okv) - 1 : 0), L);
-        const uint64_t kk = T.skey[a + pos];
-        if (kstar == KEY_NONE) { kstar = kk; kc = 1; }
-        else { if ((uint32_t)(kk >> 32) == (uint32_t)(kstar >> 32)) kc = 2; done = true; }
-        if ((int)lane == L) okv &= okv - 1;
-      }
-    }
-    tot = __reduce_add_sync(FULL, tot);
+  __syncthreads();
+  if (s_last) {   // every CTA of the pool has signed off: the view is complete
+    __threadfence();
+    const uint32_t nok = __ldcg(T.pool_nok + p);
+    pool_label_best<true>(T, p, a, words, nok, tid >> 5, NT >> 5, lane);
   }
-  if (lane == 0) T.lbest[id] = make_uint4((uint32_t)kstar, (uint32_t)(kstar >> 32), kc, tot);
 }
 
 // ------------------------------------------------------------------ wide masks (tables.h WideLayout)
@@ -590,7 +602,7 @@ __global__ void __launch_bounds__(256, MINB) route_kernel(KParams P) {
           const bool unsat = c_flags & JF_PLACE_UNSAT;
           const bool wide_place = place_x_any(T, wrow);
           const bool labelled = (c_plo | c_phi) != 0 || unsat || wide_place;
-          // exactly one required label: the per-(pool, bit) answers of the refresh (label_best_kernel) settle it here
+          // exactly one required label: the per-(pool, bit) answers of the refresh (pool_label_best) settle it here
           int one_bit = -1;
           if (T.lbest && !unsat && !wide_place) {
             if (c_phi == 0 && c_plo && !(c_plo & (c_plo - 1))) one_bit = __ffsll((long long)c_plo) - 1;
@@ -864,29 +876,17 @@ cudaError_t launch_peer_push(const PeerPush& G, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-static cudaError_t launch_label_best(const DeviceTables& T, cudaStream_t s);
-
 cudaError_t launch_worker_pools(const DeviceTables& T, cudaStream_t s, cudaEvent_t loads_read) {
   if (T.n_pools == 0) return loads_read ? cudaEventRecord(loads_read, s) : cudaSuccess;
   if (cudaError_t c = configure_kernels(); c != cudaSuccess) return c;
   worker_chunk_kernel<CORDUM_POOL_CHUNK><<<T.n_chunks, CORDUM_POOL_CHUNK, 0, s>>>(T);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && loads_read) e = cudaEventRecord(loads_read, s);   // the load table is not read past this point
-  if (e != cudaSuccess) return e;
-  if (T.n_merge) {
-    worker_merge_kernel<<<T.n_merge, 512, T.merge_smem, s>>>(T);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  return launch_label_best(T, s);
-}
-
-static cudaError_t launch_label_best(const DeviceTables& T, cudaStream_t s) {
-  if (!T.lbest || T.n_pools == 0) return cudaSuccess;
-  const uint32_t n = T.n_pools * T.place_bits;   // one warp each
-  label_best_kernel<<<(n + 7) / 8, 256, 0, s>>>(T);
+  if (e != cudaSuccess || T.n_merge == 0) return e;
+  worker_merge_kernel<<<T.n_merge, 512, T.merge_smem, s>>>(T);
   return cudaGetLastError();
 }
+
 
 static uint32_t grid_for(uint32_t n_jobs, int sm_count, int resident) {
   static const int waves = []() { const char* v = getenv("CORDUM_WAVES"); return v ? atoi(v) : 4; }();

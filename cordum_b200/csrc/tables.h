@@ -184,6 +184,7 @@ typedef struct DeviceTables {
   uint64_t* pos_key;                          /* derived: (orderable score << 32) | rank; score field all-ones = overloaded */
   uint64_t* skey;                             /* derived: per pool, keys in ascending order (load-sorted view of the pool)  */
   uint8_t* pool_sorted;                       /* derived: 1 if the pool's sorted view is valid (pool fits the sort buffer)  */
+  uint32_t* pool_done;                        /* derived scratch: merge CTAs of the pool that have signed off this epoch   */
   uint32_t* pool_nok;                         /* derived: workers of the pool that are NOT overloaded (= prefix of the sorted view) */
   uint32_t* lbm;                              /* derived: label bitmaps over the sorted view: lbm[lbm_off[p] + bit*words(p) + w],
                                                  bit i of word w = "sorted worker 32w+i carries label bit"               */
