@@ -923,16 +923,30 @@ int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* 
   int rc = CORDUM_OK;
   for (int attempt = 0; attempt < 3; ++attempt) {
     // a policy / registry whose dictionaries outgrow the records' mask fields needs a side row per job (WideLayout)
-    const uint64_t need = (uint64_t)e->host->wide_words() * b->max_jobs;
-    if (need > b->wide_cap) {
+    // Sized by the jobs actually in the batch (rounded up), not by max_jobs: the rows are dense (a registry with 60k label
+    // bits costs 7.5 KB per job), so a small batch must not pay for the largest one the handle could hold.
+    const uint64_t ww = e->host->wide_words();
+    const uint64_t jobs_cap = std::min<uint64_t>(b->max_jobs, std::max<uint64_t>(1024, (uint64_t)env->n_jobs + env->n_jobs / 4));
+    const uint64_t need = ww * jobs_cap;
+    if (ww * env->n_jobs > b->wide_cap) {
+      if (need * 8 > (uint64_t(4) << 30)) {   // not a device failure: refuse this batch, keep the engine
+        g_err = "wide-mask rows for this batch need " + std::to_string(need * 8 >> 20) + " MiB (" + std::to_string(ww * 8) +
+                " B per job: the policy / registry label universe is very large); submit smaller batches";
+        return CORDUM_E_CAPACITY;
+      }
       std::lock_guard<std::mutex> g(e->mu);
       CK(cudaSetDevice(e->device), "cudaSetDevice");
       CK(cudaStreamSynchronize(b->stream), "wait before reallocating the wide rows");
       if (b->h_wide) cudaFreeHost(b->h_wide);
       if (b->d_wide) cudaFree(b->d_wide);
       b->h_wide = b->d_wide = nullptr; b->wide_cap = 0;
-      CK(cudaHostAlloc((void**)&b->h_wide, need * 8, cudaHostAllocDefault), "pinned wide rows");
-      CK(cudaMalloc((void**)&b->d_wide, need * 8), "device wide rows");
+      if (cudaHostAlloc((void**)&b->h_wide, need * 8, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&b->d_wide, need * 8) != cudaSuccess) {
+        cudaGetLastError();   // an allocation that does not fit is this batch's problem, not a sticky engine failure
+        if (b->h_wide) cudaFreeHost(b->h_wide);
+        b->h_wide = b->d_wide = nullptr;
+        g_err = "out of memory for " + std::to_string(need * 8 >> 20) + " MiB of wide-mask rows; submit smaller batches";
+        return CORDUM_E_CAPACITY;
+      }
       b->wide_cap = need;
       e->tables_gen++;   // captured graphs bake the batch's pointers in
     }
