@@ -271,3 +271,59 @@ def test_reloads_and_heartbeats_keep_agreeing(seed):
         check("%s (step %d)" % (kind, step))
     o.close()
     h.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_three_implementations_agree_with_wide_universes(seed, monkeypatch):
+    """The same agreement with vocabularies large enough that the risk-tag, requires-token, label-pair and placement-label
+    dictionaries outgrow the mask fields of the job record (tables.h WideLayout: side rows of extra mask words), mixed
+    with the awkward strings above, and across a reload back to a narrow policy."""
+    me = sys.modules[__name__]
+    monkeypatch.setattr(me, "RISKS", RISKS + ["tag%02d" % i for i in range(90)] + ["TAG%02d " % i for i in range(0, 90, 7)])
+    monkeypatch.setattr(me, "REQS", REQS + ["req%02d" % i for i in range(100)] + [" REQ%02d" % i for i in range(0, 100, 9)])
+    monkeypatch.setattr(me, "LKEYS", LKEYS + ["k%02d" % i for i in range(30)])
+    monkeypatch.setattr(me, "LVALS", LVALS + ["v%d" % i for i in range(8)])
+    rng = random.Random(12000 + seed)
+    policy, routing, workers = make_policy(rng, 300), make_routing(rng), make_workers(rng) + make_workers(rng) + make_workers(rng)
+    for r in policy.get("rules", []):   # more rules with mask predicates than the base generator makes
+        if rng.random() < 0.5:
+            r["match"]["risk_tags"] = pick(rng, me.RISKS, 2, 5)
+        if rng.random() < 0.4:
+            r["match"]["requires"] = pick(rng, me.REQS, 1, 3)
+        if rng.random() < 0.4:
+            r["match"]["labels"] = {rng.choice(me.LKEYS): rng.choice(me.LVALS) for _ in range(rng.randint(1, 2))}
+    for p in routing["pools"].values():
+        if rng.random() < 0.7:
+            p["requires"] = pick(rng, me.REQS, 1, 6)
+    h = table_walk.HostHarness(policy, routing, workers)
+    T = h.tables()
+    assert T["xw_risk"] + T["xw_req"] + T["xw_lab"] + T["xw_place"] >= 2, (T["xw_risk"], T["xw_req"], T["xw_lab"], T["xw_place"])
+    o = oracle_lib.Oracle(policy, routing, workers)
+    jobs = []
+    for _ in range(150):
+        j = make_job(rng, workers)
+        if rng.random() < 0.5:
+            j.setdefault("meta", {})
+            j["meta"] = dict(j["meta"] or {})
+            j["meta"]["risk_tags"] = pick(rng, me.RISKS, 0, 5)
+            j["meta"]["requires"] = pick(rng, me.REQS, 0, 5)
+        jobs.append(j)
+    env = wire.EnvelopeBatch.from_jobs(jobs)
+    for mode in (wire.MODE_POLICY_AND_ROUTE, wire.MODE_POLICY_ONLY, wire.MODE_ROUTE_ONLY):
+        want_m, got = o.eval(env, mode), h.evaluate(env, mode)
+        for f in FIELDS:
+            bad = np.nonzero(got[f] != want_m[f])[0]
+            assert len(bad) == 0, "seed %d mode %d field %s job %s: tables %s oracle %s\n%s" % (
+                seed, mode, f, bad[:4], got[f][bad[:4]], want_m[f][bad[:4]], json.dumps(jobs[int(bad[0])]))
+    a, b = rec_tuples(o.eval(env, wire.MODE_POLICY_AND_ROUTE)), py_records(policy, routing, workers, jobs)
+    bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y]
+    assert not bad, "seed %d C++ vs Python oracle: %s\n%s" % (seed, bad[:3], json.dumps(jobs[bad[0][0]]))
+    # narrow again: the side rows disappear and the same envelopes still agree
+    monkeypatch.undo()
+    narrow = make_policy(random.Random(seed), 12)
+    h.load_policy(narrow)
+    o2 = oracle_lib.Oracle(narrow, routing, workers)
+    got, want = h.evaluate(env), o2.eval(env)
+    for f in FIELDS:
+        assert np.array_equal(got[f], want[f]), (seed, f)
+    o.close(); o2.close(); h.close()
