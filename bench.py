@@ -12,19 +12,23 @@ full rule / routing / worker tables.
 One step = one pass of the hot path over the rank's job shard:
     ingest the heartbeat load deltas of this rank's W/N worker slice (pinned host -> HBM)
     [N > 1]  one NCCL all-gather of the per-rank 16 B/worker load slices   
-    worker_chunk_kernel + worker_merge_kernel   (load score / overload / per-pool argmin over the 64k workers)
+    worker_chunk_kernel + worker_merge_kernel   (load score / overload / per-pool sorted views, label bitmaps and
+                                                 single-label answers over the 64k workers)
     policy_kernel        (first-match over the rule set + decision mapping; overlaps the two lines above)
     route_kernel         (pool filter + least-loaded pick for the jobs that may dispatch)
 `value`  : job columns already resident in HBM; K steps bracketed by barrier + synchronize on
            both sides, max over ranks.  Successive steps rotate over enough distinct resident
            copies of the shard that the working set exceeds 2 x L2 (no step re-reads L2-hot columns).
 `e2e`    : the same decisions produced through the public C ABI from HOST buffers: string-level
-           job envelopes -> cordum_encode (host, multi-threaded) -> pinned H2D -> kernels ->
-           D2H of the decision records, every step.
+           job envelopes (per-job strings, nothing interned) in page-locked memory -> H2D of the envelope
+           bytes -> cordum_encode_device (dictionary coding + topic sort on the GPU) -> kernels ->
+           D2H of the decision records, every step, two batches in flight.  `e2e.host_encoder` reports
+           the same path through cordum_encode (host threads) beside it.
 `roofline`: policy_kernel's (the dominant kernel) algorithmic bytes per launch / its CUDA-event duration, against the
            measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline` / --impl reference: the oracle (C++ port of the reference's Go path, oracle/oracle.cpp)
-           timed on the box's host cores on a bounded sample of the same jobs.
+           timed on the box's usable host cores (affinity and cgroup quota, cordum_b200/hostinfo.py).
+`parity_check`: untimed; every record of every rank's shard against the oracle, mismatches all-reduced.
 """
 from __future__ import annotations
 
