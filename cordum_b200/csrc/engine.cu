@@ -146,6 +146,7 @@ struct cordum_batch {
   // the policy, worker ids of the registry.  Kept by the batch so that a later reload cannot relabel its decisions.
   std::shared_ptr<const cordum::PolicyText> text;
   std::shared_ptr<const std::vector<std::string>> wtext;
+  std::shared_ptr<const std::vector<std::string>> ttext;   // raw topics by id of the dictionary generation the batch was encoded under
   bool encoded = false, resident = false, pending = false, enc_inflight = false, launched = false, timed_in = false, timed_out = false;
   int table_set = 0;             // derived-table set the last route_kernel of this batch read
   uint8_t* h_cols = nullptr;     // pinned: the encoded records (slab_bytes layout)
@@ -448,7 +449,7 @@ int run(cordum_engine* e, cordum_batch* b, uint32_t mode, bool copy_in, bool cop
   {
     std::lock_guard<std::mutex> gh(e->host->mutex());
     if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
-    b->text = e->host->policy_text(); b->wtext = e->host->worker_text();
+    b->text = e->host->policy_text(); b->wtext = e->host->worker_text(); b->ttext = e->host->topic_text();
     int rc = sync_tables(e);
     if (rc) return rc;
     rc = refresh_pools(e, nullptr, nullptr);
@@ -951,8 +952,8 @@ int host_encode_into(cordum_engine* e, cordum_batch* b, const cordum_envelopes* 
       e->tables_gen++;   // captured graphs bake the batch's pointers in
     }
     host_records(b);
-    epoch_before = e->host->epoch();
     rc = e->host->encode(env, b->hr, g_err);
+    epoch_before = b->hr.epoch;   // the epoch the ids belong to, read under the encoder's lock (a dictionary reset inside the encode moves it)
     if (rc != cordum::kWideRetry) break;   // the tables changed between the look and the encode: size again
   }
   if (rc) return rc == cordum::kWideRetry ? CORDUM_E_STALE : rc;
@@ -1231,7 +1232,7 @@ int32_t cordum_tick_async(cordum_engine* e, cordum_batch* b, uint32_t mode, cons
   std::lock_guard<std::mutex> g(e->mu);
   std::lock_guard<std::mutex> gh(e->host->mutex());
   if (b->epoch != e->host->epoch()) { g_err = "tables were reloaded after this batch was encoded: encode again"; return CORDUM_E_STALE; }
-  b->text = e->host->policy_text(); b->wtext = e->host->worker_text();
+  b->text = e->host->policy_text(); b->wtext = e->host->worker_text(); b->ttext = e->host->topic_text();
   const uint32_t W = e->host->tables().n_slots;
   if (e->peers.ready && e->peers.world > 1) {
     if (first_slot != (uint32_t)e->peers.rank * e->peers.per || n_slice != e->peers.per || e->peers.per * (uint32_t)e->peers.world != W) {
@@ -1572,7 +1573,8 @@ int64_t cordum_reason_flavor(cordum_engine* e, const cordum_batch* b, uint32_t j
   else if (code == CORDUM_REASON_UNSUPPORTED_TOPIC) s = "unsupported topic";
   else if (code == CORDUM_REASON_APPROVAL_GRANTED) s = "approval granted";
   else if (code == CORDUM_REASON_EFF_DENIED_TOPIC || code == CORDUM_REASON_EFF_NOT_ALLOWED_TOPIC) {
-    std::string topic(cordum::trim_space(e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic)));
+    const uint32_t tid = b->hr.job[b->hr.slot_of[job]].topic;
+    std::string topic((b->ttext && tid < b->ttext->size()) ? cordum::trim_space((*b->ttext)[tid]) : sv());
     const char* tail = code == CORDUM_REASON_EFF_DENIED_TOPIC ? " denied by effective config" : " not allowed by effective config";
     // kernel.go:221,225 print '%s'; the gateway's copy of the evaluator prints %q (policy_bundles.go:1207,1211)
     s = "topic " + (flavor == CORDUM_REASON_FLAVOR_GATEWAY ? cordum::go_quote(topic) : "'" + topic + "'") + tail;
@@ -1599,7 +1601,8 @@ int64_t cordum_subject(cordum_engine* e, const cordum_batch* b, uint32_t job, ch
   if ((r.route_status == CORDUM_ROUTE_OK || r.route_status == CORDUM_ROUTE_OK_PREFERRED) && r.worker_slot >= 0 && b->wtext &&
       (size_t)r.worker_slot < b->wtext->size()) {
     const std::string& id = (*b->wtext)[(size_t)r.worker_slot];   // the registry the batch was dispatched against
-    s = id.empty() ? e->host->topic_raw(b->hr.job[b->hr.slot_of[job]].topic) : "worker." + id + ".jobs";   // bus/nats.go:94-99; :131-135
+    const uint32_t tid = b->hr.job[b->hr.slot_of[job]].topic;
+    s = !id.empty() ? "worker." + id + ".jobs" : (b->ttext && tid < b->ttext->size()) ? (*b->ttext)[tid] : std::string();   // bus/nats.go:94-99; :131-135
   }
   return copy_out(s, buf, cap);
 }

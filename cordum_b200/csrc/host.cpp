@@ -938,7 +938,7 @@ void Host::topic_row(sv trimmed, Bits& out) const {
 void Host::eff_topic_fill(uint32_t cfg, uint32_t topic_id) {
   uint8_t v = 0;
   if (effcfg_ok_[cfg]) {
-    sv topic = trim_space(topic_keys_[topic_id]);
+    sv topic = trim_space((*topic_store_)[topic_id]);
     if (!topic.empty()) {   // matchAny: value == "" -> false (kernel.go:456)
       const EffGlobs& g = eff_globs_[cfg];
       for (auto& gl : g.denied) if (gl.match(topic)) { v |= 1; break; }
@@ -955,16 +955,16 @@ void Host::eff_topic_fill(uint32_t cfg, uint32_t topic_id) {
 // Recompute every per-topic table for the topics known so far (ids are stable).
 void Host::rebuild_topics() {
   HostTables& t = t_;
-  if (topic_keys_.empty()) {   // id 0 = the empty raw topic
-    topic_keys_.emplace_back();
+  if ((*topic_store_).empty()) {   // id 0 = the empty raw topic
+    (*topic_store_).emplace_back();
     topic_ids_.put(sv(), 0);
   }
   for (auto& tp : routing_.topics)   // pre-seed so steady state has no dictionary misses
-    if (!topic_ids_.contains(tp.first) && topic_keys_.size() < max_topics_) {
-      topic_ids_.put(tp.first, (uint32_t)topic_keys_.size());
-      topic_keys_.push_back(tp.first);
+    if (!topic_ids_.contains(tp.first) && (*topic_store_).size() < max_topics_) {
+      topic_ids_.put(tp.first, (uint32_t)(*topic_store_).size());
+      (*topic_store_).push_back(tp.first);
     }
-  const uint32_t n = (uint32_t)topic_keys_.size(), W = t.row_words;
+  const uint32_t n = (uint32_t)(*topic_store_).size(), W = t.row_words;
   t.row_topic.init(n, W);
   topic_entries_.assign(n, TopicEntry{0, 0, 0});
   topic_pools_.assign(n, {});
@@ -974,9 +974,9 @@ void Host::rebuild_topics() {
   auto work = [&]() {
     Bits row;
     for (uint32_t i; (i = next.fetch_add(1)) < n;) {
-      sv trimmed = trim_space(topic_keys_[i]);
+      sv trimmed = trim_space((*topic_store_)[i]);
       uint32_t fl = 0;
-      if (topic_keys_[i].empty()) fl |= JF_TOPIC_RAW_EMPTY;
+      if ((*topic_store_)[i].empty()) fl |= JF_TOPIC_RAW_EMPTY;
       if (trimmed.empty()) fl |= JF_TOPIC_MISSING;
       else if (!starts_with(trimmed, "job.")) fl |= JF_TOPIC_UNSUPPORTED;
       topic_entries_[i].flags = fl;
@@ -1002,7 +1002,7 @@ void Host::rebuild_topics() {
   if (trace) fprintf(stderr, "[rebuild_topics] n=%u threads=%u summarize %.2f choose %.2f ms\n", n, nth,
                      std::chrono::duration<double, std::milli>(tt1 - tt0).count(), std::chrono::duration<double, std::milli>(tt2 - tt1).count());
   for (uint32_t i = 0; i < n; ++i) {
-    uint32_t ri = routing_topics_.find(topic_keys_[i], kMiss);
+    uint32_t ri = routing_topics_.find((*topic_store_)[i], kMiss);
     topic_entries_[i].pool_off = (uint32_t)t.pool_list.size();
     if (ri != kMiss) {
       topic_pools_[i] = routing_.topics[ri].second;
@@ -1039,12 +1039,12 @@ void Host::rebuild_topics() {
 uint32_t Host::add_topic(sv raw) {
   uint32_t id = topic_ids_.find(raw, kMiss);
   if (id != kMiss) return id;
-  if (topic_keys_.size() >= max_topics_) return kMiss;
+  if ((*topic_store_).size() >= max_topics_) return kMiss;
   HostTables& t = t_;
-  id = (uint32_t)topic_keys_.size();
+  id = (uint32_t)(*topic_store_).size();
   topic_ids_.put(raw, id);
-  topic_keys_.emplace_back(raw);
-  sv trimmed = trim_space(topic_keys_.back());
+  (*topic_store_).emplace_back(raw);
+  sv trimmed = trim_space((*topic_store_).back());
   TopicEntry e{0, (uint32_t)t.pool_list.size(), 0};
   if (trimmed.empty()) e.flags |= JF_TOPIC_MISSING;
   else if (!starts_with(trimmed, "job.")) e.flags |= JF_TOPIC_UNSUPPORTED;
@@ -1106,7 +1106,7 @@ uint32_t Host::add_effcfg(sv payload) {
   compile_mcp_tables();   // dictionaries may have grown; sets n_effcfg
   if (t.mcp_stride > CORDUM_ID16_MAX) return kMiss;   // ids no longer fit the job record: the encode fails closed
   t.eff_topic.resize((size_t)(t.n_effcfg + 1) * t.topic_stride, 0);
-  for (uint32_t i = 0; i < topic_keys_.size(); ++i) eff_topic_fill(id, i);
+  for (uint32_t i = 0; i < (*topic_store_).size(); ++i) eff_topic_fill(id, i);
   t.v_topic++;
   v_dict_++;
   return id;
@@ -1700,6 +1700,36 @@ void Host::encode_job(const cordum_envelopes* env, uint32_t j, uint32_t tid, uin
 int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err) {
   if (!env) { err = "null envelopes"; return CORDUM_E_INVALID; }
   std::lock_guard<std::mutex> g(mu_);
+  int rc = encode_locked(env, out, err);
+  if (rc == kDictFull) {
+    // A dictionary that grows with the traffic (raw topics, effective configs) is full: start a new generation of both -
+    // keep only what the routing table pre-seeds, bump the epoch (batches encoded under the old ids are refused as stale
+    // and get encoded again) - and encode this batch again; it registers what it needs.
+    reset_dynamic_dictionaries();
+    rc = encode_locked(env, out, err);
+    if (rc == kDictFull) { err = "one batch references more distinct topics / effective configs than the dictionaries hold (max_topics / max_effcfgs)"; rc = CORDUM_E_CAPACITY; }
+  }
+  out.epoch = epoch_;
+  return rc;
+}
+
+void Host::reset_dynamic_dictionaries() {
+  topic_ids_.clear();
+  topic_store_ = std::make_shared<std::vector<std::string>>();   // batches dispatched earlier keep the old names alive
+  topic_entries_.clear();
+  topic_pools_.clear();
+  effcfg_ids_.clear();
+  effcfgs_.clear(); effcfg_ok_.clear(); eff_globs_.clear();
+  eff_topic_n_ = 0;
+  t_.eff_topic.clear();
+  compile_mcp_tables();   // no effective configs any more
+  rebuild_topics();       // the routing table's topics, their rows, pools and (empty) effective-config verdicts
+  epoch_++;
+  v_dict_++;
+  dict_resets_++;
+}
+
+int Host::encode_locked(const cordum_envelopes* env, HostRecords& out, std::string& err) {
   const uint32_t n = env->n_jobs;
   const uint32_t ww = WIDE_WORDS(t_.wide);
   out.wide_words = ww;
@@ -1742,13 +1772,13 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
   for (auto& lst : misses)   // first sight of a topic: register it (computes its pass-row), then the id is known
     for (uint32_t j : lst) {
       uint32_t id = add_topic(span(env, env->topic, j));
-      if (id == kMiss) { err = "topic dictionary full (max_topics)"; return CORDUM_E_CAPACITY; }
+      if (id == kMiss) return kDictFull;
       tid[j] = id;
     }
   auto t_pass1 = now();
   // ---- slots: hist[p][key] -> first slot of (part p, key); key = topic * classes + tenant class
   const uint32_t ncls = std::max<uint32_t>(1, tenant_classes_);
-  const uint32_t nk = (uint32_t)topic_keys_.size() * ncls;
+  const uint32_t nk = (uint32_t)(*topic_store_).size() * ncls;
   while (parts > 1 && (uint64_t)parts * nk > (2u << 20)) parts = (parts + 1) / 2;   // bound the counter table (8 MB)
   auto key_of = [&](uint32_t j) { return tid[j] * ncls + tenant_class_[ten[j] & 0xFFFFu]; };
   std::vector<uint32_t>& hist = scratch_hist_;
@@ -1797,7 +1827,10 @@ int Host::encode(const cordum_envelopes* env, HostRecords& out, std::string& err
   for (auto& lst : misses)
     for (uint32_t j : lst) {
       sv eff = span(env, env->effective_config, j);
-      if (!eff.empty() && add_effcfg(eff) == kMiss) { err = "effective-config dictionary full (max_effcfgs)"; return CORDUM_E_CAPACITY; }
+      if (!eff.empty() && add_effcfg(eff) == kMiss) {
+        if (t_.mcp_stride > CORDUM_ID16_MAX) { err = "more than 65535 distinct MCP values referenced by allow / deny lists"; return CORDUM_E_CAPACITY; }
+        return kDictFull;
+      }
       bool miss = false;
       const uint32_t slot = out.slot_of[j];
       encode_job(env, j, tid[j], ten[j], out.job[slot], out.route[slot], ww ? out.wide + (size_t)slot * ww : nullptr, miss, *caches[0]);

@@ -282,6 +282,7 @@ struct HostRecords {
   uint64_t* wide = nullptr;      // [n][wide_words] when the tables carry wide masks (Host::wide_words() at encode time)
   uint64_t wide_cap = 0;         // 64-bit words available at `wide`
   uint32_t wide_words = 0;       // out: the row width the encode used
+  uint64_t epoch = 0;            // out: the table epoch the ids belong to (read under the encoder's lock)
 };
 
 // Persistent worker pool for the encoder: parallel_for over [0,n) in dynamically claimed chunks.  Completion
@@ -355,12 +356,14 @@ class Host {
     for (auto& t : text_) if (t->gen == gen) return t;
     return nullptr;
   }
-  const std::string& topic_raw(uint32_t topic_id) const { return topic_keys_[topic_id]; }
+  const std::string& topic_raw(uint32_t topic_id) const { return (*topic_store_)[topic_id]; }
+  std::shared_ptr<const std::vector<std::string>> topic_text() const { return topic_store_; }
+  uint64_t dict_resets() const { return dict_resets_; }
   uint32_t wide_words() const { return WIDE_WORDS(t_.wide); }
   uint64_t policy_generation() const { return text_gen_.load(std::memory_order_acquire); }
   std::string mcp_value_string(int field, uint32_t id) const;
   const std::vector<std::string>& topic_pool_names(uint32_t topic_id) const;
-  uint32_t n_topics() const { return (uint32_t)topic_keys_.size(); }
+  uint32_t n_topics() const { return (uint32_t)topic_store_->size(); }
 
  private:
   std::mutex mu_;
@@ -406,7 +409,13 @@ class Host {
   Bits vac_topic_;
   // topics (dynamic)
   StrTable topic_ids_;
-  std::vector<std::string> topic_keys_;          // raw topic per id (id 0 = "")
+  // raw topic per id (id 0 = ""); append-only within a dictionary generation, replaced whole by a reset, shared with
+  // the batches dispatched under it (their strings must outlive a reset)
+  std::shared_ptr<std::vector<std::string>> topic_store_ = std::make_shared<std::vector<std::string>>();
+  uint64_t dict_resets_ = 0;
+  static constexpr int kDictFull = -101;
+  int encode_locked(const cordum_envelopes* env, HostRecords& out, std::string& err);
+  void reset_dynamic_dictionaries();
   std::vector<TopicEntry> topic_entries_;
   std::vector<std::vector<std::string>> topic_pools_;   // original (not deduplicated) lists for messages
   // effective configs (dynamic)

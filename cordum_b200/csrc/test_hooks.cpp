@@ -106,6 +106,7 @@ uint64_t cordum_test_host_scalar(void* h, const char* name) {
   if (n == "n_pos") return t.n_pos;
   if (n == "n_slots") return t.n_slots;
   if (n == "n_topics") return t.row_topic.n_rows;
+  if (n == "dict_resets") return ((Host*)h)->dict_resets();
   if (n == "xw_risk") return t.wide.xw_risk;
   if (n == "xw_req") return t.wide.xw_req;
   if (n == "xw_lab") return t.wide.xw_lab;

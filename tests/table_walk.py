@@ -41,7 +41,7 @@ TABLES = {
     "rule_need_x": np.uint64, "pool_req_x": np.uint64, "req_blank_x": np.uint64, "pos_label_x": np.uint64,
 }
 SCALARS = ["n_rules", "n_seg", "sum_group", "sum_use", "n_chunks", "n_merge", "merge_smem", "row_words", "mcp_stride", "topic_stride", "n_effcfg", "req_blank_mask", "n_pools",
-           "n_pos", "n_slots", "n_topics", "xw_risk", "xw_req", "xw_lab", "xw_place", "place_bits"]
+           "n_pos", "n_slots", "n_topics", "xw_risk", "xw_req", "xw_lab", "xw_place", "place_bits", "dict_resets"]
 
 
 def _align16(x):
@@ -58,9 +58,9 @@ def _orderable(score: np.float32) -> int:
 class HostHarness:
     """Host (table compiler + encoder) without a GPU."""
 
-    def __init__(self, policy=None, routing=None, workers=None, threads=2):
+    def __init__(self, policy=None, routing=None, workers=None, threads=2, max_topics=0, max_effcfgs=0):
         self.L = _lib.load()
-        self.h = C.c_void_p(self.L.cordum_test_host_new(0, 0, threads))
+        self.h = C.c_void_p(self.L.cordum_test_host_new(max_topics, max_effcfgs, threads))
         self.load_policy(policy)
         self.load_routing(routing)
         self.load_workers(workers or [])

@@ -242,3 +242,35 @@ def test_effective_config_verdicts_survive_reloads():
     assert_same(h.evaluate(more + jobs), o2.eval(more + jobs), "a config first seen after the reloads")
     h.load_policy(p1)
     assert_same(h.evaluate(more + jobs), oracle_lib.Oracle(p1, r2, workers).eval(more + jobs), "and back")
+
+
+def test_dynamic_dictionaries_start_a_new_generation_when_full():
+    """Raw topics and effective configs are dictionary-coded on first sight; the dictionaries are bounded (max_topics /
+    max_effcfgs).  The reference has no such bound - it evaluates strings - so a full dictionary must not stop the
+    engine: it starts a new generation (only the routing table's topics survive), and answers stay those of the oracle."""
+    policy = {"rules": [{"id": "d", "decision": "deny", "match": {"topics": ["job.bad.*"]}},
+                        {"id": "a", "decision": "require_approval", "reason": "r", "match": {"topics": ["job.?1.*"]}}]}
+    routing = {"topics": {"job.keep.a": ["p"], "job.keep.b": ["p"]}, "pools": {"p": {}}}
+    workers = [kats.hb("w", "p")]
+    h = table_walk.HostHarness(policy, routing, workers, max_topics=16, max_effcfgs=6)
+    o = oracle_lib.Oracle(policy, routing, workers)
+    n0 = h.tables()["n_topics"]
+    assert n0 == 3                                   # "", and the two routed topics
+    resets = 0
+    for rnd in range(12):
+        jobs = [{"topic": "job.%s%d.x%d" % ("bad" if i % 3 == 0 else "t", rnd % 4, rnd * 10 + i)} for i in range(7)]
+        jobs += [{"topic": "job.keep.a"}, {"topic": "job.keep.b", "effective_config": ('{"safety":{"denied_topics":["job.keep.%s"]}}' % "ab"[rnd % 2]).encode()},
+                 {"topic": "job.t1.e%d" % rnd, "effective_config": ('{"safety":{"allowed_topics":["job.t%d.*"]}}' % (rnd % 5)).encode()}]
+        assert_same(h.evaluate(jobs), o.eval(jobs), "round %d" % rnd)
+        T = h.tables()
+        assert T["n_topics"] <= 16 and T["n_effcfg"] <= 6
+        assert T["dict_resets"] >= resets
+        resets = T["dict_resets"]
+    assert resets >= 3                               # 8 new topics per round into 13 free ids: several generations
+    # one batch that needs more than a whole dictionary is refused (and only that batch)
+    with pytest.raises(RuntimeError, match="more distinct topics"):
+        h.evaluate([{"topic": "job.big.%d" % i} for i in range(20)])
+    assert_same(h.evaluate([{"topic": "job.keep.a"}, {"topic": "job.bad.z"}]), o.eval([{"topic": "job.keep.a"}, {"topic": "job.bad.z"}]), "after the refused batch")
+    with pytest.raises(RuntimeError, match="effective configs"):
+        h.evaluate([{"topic": "job.keep.a", "effective_config": ('{"safety":{"denied_topics":["x%d"]}}' % i).encode()} for i in range(9)])
+    o.close()
