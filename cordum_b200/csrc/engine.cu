@@ -382,7 +382,13 @@ DeviceTables view(const cordum_engine* e, int set) {
   d.loads = (const Load16*)D.loads.p;
   d.pos_key = (uint64_t*)D.pos_key.p; d.ckey = (uint64_t*)D.ckey.p; d.skey = (uint64_t*)D.skey.p;
   d.pool_sorted = (uint8_t*)D.pool_sorted.p; d.pool_nok = (uint32_t*)D.pool_nok.p; d.pool_done = (uint32_t*)D.pool_done.p; d.lbm = (uint32_t*)D.lbm.p;
-  d.lbest = d.place_bits <= CORDUM_LBEST_MAX_BITS ? (uint4*)D.lbest.p : nullptr;
+  // The per-(pool, label) answers take ~25 us out of route_kernel per million jobs and add ~20 us to the refresh chain.
+  // With one or two ranks the chain hides behind policy_kernel; from four ranks on the per-rank batch is small and the
+  // chain is the critical path of a step (measured: profiles/r02_bench_n4.json, _n8.json vs r02x_*), so the table is
+  // built only when it pays.  CORDUM_LBEST=1 / 0 forces it on / off (both paths are exact and parity-tested).
+  const char* lb = getenv("CORDUM_LBEST");
+  const bool use_lbest = lb ? lb[0] == '1' : e->xworld <= 2;
+  d.lbest = (d.place_bits <= CORDUM_LBEST_MAX_BITS && use_lbest) ? (uint4*)D.lbest.p : nullptr;
   d.pool_best = (uint64_t*)D.pool_best.p; d.pool_mincnt = (uint32_t*)D.pool_mincnt.p;
   return d;
 }
@@ -1160,6 +1166,7 @@ int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_
     e->nccl_comm = comm;
   }
   e->xrank = rank; e->xworld = world;
+  e->tables_gen++;   // view() depends on the world size (label-best table on / off): captured graphs are stale
   return CORDUM_OK;
 }
 

@@ -70,6 +70,27 @@ def test_synthetic_configs_bit_exact(eng, name, n, mode):
     b.free()
 
 
+@pytest.mark.parametrize("lbest", ["0", "1"])
+def test_label_picks_with_and_without_the_label_best_table(eng, monkeypatch, lbest):
+    """Single-label jobs are answered from the per-(pool, label) table the refresh builds, or by the bitmap scan: the engine
+    chooses by world size (engine.cu view()); CORDUM_LBEST forces either.  Both are exact."""
+    monkeypatch.setenv("CORDUM_LBEST", lbest)
+    cfg = synth.make_config("c2", 6000)
+    load(eng, cfg.policy, cfg.routing, cfg.workers)
+    o = oracle_lib.Oracle(cfg.policy, cfg.routing, cfg.workers)
+    b = eng.batch(cfg.jobs.n_jobs)
+    for mode in (wire.MODE_POLICY_AND_ROUTE, wire.MODE_ROUTE_ONLY):
+        assert_same(b.encode(cfg.jobs).dispatch(mode), o.eval(cfg.jobs, mode, threads=8), "lbest=%s mode %d" % (lbest, mode))
+    loads = cfg.workers.loads()
+    loads["active_jobs"] = (np.arange(len(loads)) * 7) % 9
+    slots = np.arange(len(loads), dtype=np.uint32)
+    eng.update_workers(slots, loads)
+    o.update_workers(slots, loads)
+    assert_same(b.dispatch(), o.eval(cfg.jobs, threads=8), "lbest=%s after a heartbeat epoch" % lbest)
+    b.free()
+    o.close()
+
+
 def test_ragged_batch_sizes(eng):
     cfg = synth.make_config("tiny", 300)
     load(eng, cfg.policy, cfg.routing, cfg.workers)
