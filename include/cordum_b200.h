@@ -245,7 +245,11 @@ int32_t cordum_workers_set_loads_device(cordum_engine* e, const void* dptr, uint
  * asynchronous), all-gathers the 16 B/worker records of all ranks in place, and refreshes the worker
  * tables from the gathered table; it returns once the work is enqueued.  The registry must divide
  * evenly: slice of rank r = slots [r * n_slots/world, (r+1) * n_slots/world).  Without
- * cordum_exchange_init (world = 1) the slice must be the whole table. */
+ * cordum_exchange_init (world = 1) the slice must be the whole table.
+ * Buffer contract: with world = 1 and on the peer-memory path the slice is copied into library-owned staging before the
+ * call returns.  On the NCCL path (world > 1) a page-locked slice is read by an asynchronous copy: leave it unchanged
+ * until a batch dispatched after this call has been waited for (cordum_batch_wait), or alternate between two buffers and
+ * synchronise once per epoch; a pageable slice is staged by the CUDA runtime before the call returns. */
 #define CORDUM_EXCHANGE_ID_BYTES 128
 int32_t cordum_exchange_unique_id(char id[CORDUM_EXCHANGE_ID_BYTES]);
 int32_t cordum_exchange_init(cordum_engine* e, const char id[CORDUM_EXCHANGE_ID_BYTES], int32_t rank, int32_t world);
