@@ -40,12 +40,13 @@ import (
 	pb "github.com/cordum/cordum/core/protocol/pb/v1"
 )
 
-// Engine owns one GPU's tables, streams and the two front-ends (policy-only for the safety kernel surface, route-only
-// for the strategy).
+// Engine owns one GPU's tables, streams and the front-ends (policy-only for the safety kernel surface, route-only for the
+// strategy, policy-and-route for the scheduler's per-job step).
 type Engine struct {
 	h        *C.cordum_engine
 	policyFE *C.cordum_frontend // CORDUM_MODE_POLICY_ONLY
 	routeFE  *C.cordum_frontend // CORDUM_MODE_ROUTE_ONLY
+	schedFE  *C.cordum_frontend // CORDUM_MODE_POLICY_AND_ROUTE (ProcessJob, process.go)
 	mu       sync.Mutex         // serialises table loads and the worker snapshot below
 
 	// worker registry mirror: slot = index in the last cordum_workers_load
@@ -91,6 +92,10 @@ func NewEngine(device int) (*Engine, error) {
 		e.Close()
 		return nil, err
 	}
+	if err := mk(C.CORDUM_MODE_POLICY_AND_ROUTE, &e.schedFE); err != nil {
+		e.Close()
+		return nil, err
+	}
 	return e, nil
 }
 
@@ -101,10 +106,13 @@ func (e *Engine) Close() {
 	if e.routeFE != nil {
 		C.cordum_frontend_destroy(e.routeFE)
 	}
+	if e.schedFE != nil {
+		C.cordum_frontend_destroy(e.schedFE)
+	}
 	if e.h != nil {
 		C.cordum_engine_destroy(e.h)
 	}
-	e.h, e.policyFE, e.routeFE = nil, nil, nil
+	e.h, e.policyFE, e.routeFE, e.schedFE = nil, nil, nil, nil
 }
 
 // cbytes copies b into C memory (nil for empty); the caller frees it.

@@ -77,17 +77,23 @@ func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest)
 		return &pb.PolicyCheckResponse{Decision: pb.DecisionType_DECISION_TYPE_DENY, Reason: err.Error()}, nil
 	}
 	defer freeResp()
+	return k.eng.policyResponse(r, req.GetJobId()), nil
+}
+
+// policyResponse assembles the PolicyCheckResponse of one front-end response (kernel.go:233-248): strings and pass-through
+// objects come from the policy generation the request was evaluated under (r.policy_gen), not from the policy in force now.
+func (e *Engine) policyResponse(r *C.cordum_response, jobID string) *pb.PolicyCheckResponse {
 	out := &pb.PolicyCheckResponse{
 		Decision: decisionToProto[r.rec.decision], Reason: C.GoString(&r.reason[0]),
 		PolicySnapshot: C.GoString(&r.snapshot[0]), RuleId: C.GoString(&r.rule_id[0]),
 		ApprovalRequired: r.rec.flags&C.CORDUM_F_APPROVAL_REQUIRED != 0,
 	}
 	if out.ApprovalRequired {
-		out.ApprovalRef = req.GetJobId() // kernel.go:233-237
+		out.ApprovalRef = jobID // kernel.go:233-237
 	}
 	if r.rec.flags&C.CORDUM_F_CONSTRAINTS != 0 {
-		if js := k.eng.ruleText(r.policy_gen, r.rec.rule_idx, func(e *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
-			return C.cordum_rule_constraints_json_at(e, g, i, b, n)
+		if js := e.ruleText(r.policy_gen, r.rec.rule_idx, func(h *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_constraints_json_at(h, g, i, b, n)
 		}); js != nil {
 			var c config.PolicyConstraints
 			if json.Unmarshal(js, &c) == nil { // the engine passes the rule's YAML-tagged object through as JSON
@@ -96,8 +102,8 @@ func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest)
 		}
 	}
 	if r.rec.rule_idx >= 0 {
-		if js := k.eng.ruleText(r.policy_gen, r.rec.rule_idx, func(e *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
-			return C.cordum_rule_remediations_json_at(e, g, i, b, n)
+		if js := e.ruleText(r.policy_gen, r.rec.rule_idx, func(h *C.cordum_engine, g C.uint64_t, i C.int32_t, b *C.char, n C.uint64_t) C.int64_t {
+			return C.cordum_rule_remediations_json_at(h, g, i, b, n)
 		}); js != nil {
 			var rems []config.PolicyRemediation
 			if json.Unmarshal(js, &rems) == nil {
@@ -109,7 +115,7 @@ func (k *SafetyKernel) evaluate(ctx context.Context, req *pb.PolicyCheckRequest)
 			}
 		}
 	}
-	return out, nil
+	return out
 }
 
 // All four modes are the same function in the reference (kernel.go:106-120,129: the mode string is ignored).
@@ -150,11 +156,15 @@ func (c Checker) Check(req *pb.JobRequest) (scheduler.SafetyDecisionRecord, erro
 	if err != nil {
 		return scheduler.SafetyDecisionRecord{Decision: scheduler.SafetyDeny, Reason: "safety kernel error: " + err.Error()}, nil
 	}
+	return recordFromResponse(resp), nil
+}
+
+func recordFromResponse(resp *pb.PolicyCheckResponse) scheduler.SafetyDecisionRecord { // safety_client.go:103-114
 	return scheduler.SafetyDecisionRecord{
 		Decision: decisionFromProto(resp.GetDecision()), Reason: resp.GetReason(), RuleID: resp.GetRuleId(),
 		PolicySnapshot: resp.GetPolicySnapshot(), Constraints: resp.GetConstraints(),
 		ApprovalRequired: resp.GetApprovalRequired(), ApprovalRef: resp.GetApprovalRef(), Remediations: resp.GetRemediations(),
-	}, nil
+	}
 }
 
 func decisionFromProto(d pb.DecisionType) scheduler.SafetyDecision { // safety_client.go:117-132

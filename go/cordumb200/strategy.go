@@ -57,6 +57,11 @@ func (s *Strategy) PickSubject(req *pb.JobRequest, _ map[string]*pb.Heartbeat) (
 		return "", fmt.Errorf("%w: engine: %v", scheduler.ErrNoWorkers, err) // retryable: the job is NAK'd, never mis-routed
 	}
 	defer freeResp()
+	return subjectFromResponse(r, req)
+}
+
+// subjectFromResponse maps the routing half of a record to PickSubject's (subject, error) (strategy_least_loaded.go:40-136).
+func subjectFromResponse(r *C.cordum_response, req *pb.JobRequest) (string, error) {
 	switch r.rec.route_status {
 	case C.CORDUM_ROUTE_OK, C.CORDUM_ROUTE_OK_PREFERRED:
 		if subject := C.GoString(&r.subject[0]); subject != "" {
