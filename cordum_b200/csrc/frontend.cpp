@@ -98,7 +98,7 @@ struct cordum_frontend {
   uint64_t seed_a = 0, seed_b = 0;
   std::atomic<uint64_t> n_hits{0}, n_misses{0};
   bool cache_on() const { return opts.cache_ttl_us != 0 && opts.mode == CORDUM_MODE_POLICY_ONLY; }
-  CacheKey key_of(const cordum_request& q) const;
+  CacheKey key_of(const cordum_request& q, uint64_t gen) const;
   bool cache_get(const CacheKey& k, cordum_response* out);
   void cache_put(const CacheKey& k, const cordum_response& r);
 
@@ -247,9 +247,9 @@ void cordum_frontend::run(Lane& L) {
   }
 }
 
-CacheKey cordum_frontend::key_of(const cordum_request& q) const {
+CacheKey cordum_frontend::key_of(const cordum_request& q, uint64_t gen) const {
   KeyHasher h{seed_a, seed_b};
-  h.word(cordum_policy_generation(eng));
+  h.word(gen);
   h.sv(q.topic); h.sv(q.tenant); h.sv(q.principal_id); h.sv(q.effective_config);
   h.word((uint64_t)(q.has_meta ? 1 : 0) | (uint64_t)q.actor_type << 8 | (uint64_t)(q.approved ? 1 : 0) << 16);
   h.sv(q.meta_tenant_id); h.sv(q.actor_id); h.sv(q.capability); h.sv(q.pack_id);
@@ -345,8 +345,10 @@ int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, co
   if (!f || !req || !resp) return CORDUM_E_INVALID;
   const bool cached = f->cache_on();
   CacheKey key{0, 0};
+  uint64_t key_gen = 0;
   if (cached) {
-    key = f->key_of(*req);
+    key_gen = cordum_policy_generation(f->eng);
+    key = f->key_of(*req, key_gen);
     if (f->cache_get(key, resp)) { f->n_hits++; return resp->status; }
     f->n_misses++;
   }
@@ -362,8 +364,8 @@ int32_t cordum_frontend_submit(cordum_frontend* f, const cordum_request* req, co
     std::unique_lock<std::mutex> lk(t.m);
     t.cv.wait(lk, [&] { return t.done; });
   }
-  // the key carries the generation read before the evaluation: a response evaluated under a newer policy is not stored
-  if (cached && resp->policy_gen == cordum_policy_generation(f->eng)) f->cache_put(key, *resp);
+  // the key carries the generation read before the evaluation: a response evaluated under another policy is not stored
+  if (cached && resp->policy_gen == key_gen) f->cache_put(key, *resp);
   return resp->status;
 }
 
